@@ -1,0 +1,241 @@
+/*
+ * orbmatch_b200.h -- C ABI of the B200-native ORB descriptor-matching hot path.
+ *
+ * This is the drop-in boundary for ORB-SLAM3's ORBmatcher family and the DBoW2
+ * vocabulary descent (reference: Herong1212/ORB_SLAM3_comments_ghr).  The
+ * reference has no FFI layer; its boundary is the C++ class ORB_SLAM3::ORBmatcher
+ * (include/ORBmatcher.h:34-99) and ORBVocabulary::transform
+ * (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:146-147).  Every entry point below
+ * names the reference function it replaces.  The C++ adapter with the reference's
+ * exact signatures lives in include/orbmatch_b200/ORBmatcher.hpp and only packs /
+ * unpacks STL containers around these calls.
+ *
+ * Conventions
+ *   - extern "C", POD arguments only, no CUDA or torch types in the signatures.
+ *   - every function returns an int status: ORBGPU_OK (0) or a negative error code;
+ *     orbgpu_last_error() returns a human readable message for the calling thread.
+ *   - "host" pointers are ordinary CPU memory (pinned memory makes copies async).
+ *     "_dev" entry points take CUDA device pointers (for callers that keep data
+ *     resident in HBM, e.g. torch tensors via data_ptr()).
+ *   - descriptors are N x 32 bytes row-major (cv::Mat CV_8U rows, Frame.h:247); on the
+ *     device they live as packed uint4 pairs (two 128-bit words per descriptor).
+ *   - all index outputs are int32; "no match" is -1 (reference: NULL MapPoint* / -1).
+ *   - there is NO CPU fallback: every search runs on the GPU or fails with an error.
+ *   - a context owns one CUDA stream and its workspaces; contexts are independent so
+ *     the three reference threads (Tracking / LocalMapping / LoopClosing,
+ *     System.cc:234,254) each use their own.  A context is not thread-safe itself.
+ */
+#ifndef ORBMATCH_B200_H
+#define ORBMATCH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBGPU_OK 0
+#define ORBGPU_ERR_INVALID (-1)   /* bad argument */
+#define ORBGPU_ERR_CUDA (-2)      /* CUDA runtime error (message in orbgpu_last_error) */
+#define ORBGPU_ERR_NO_DEVICE (-3) /* no usable sm_100 GPU: there is no CPU fallback */
+#define ORBGPU_ERR_OVERFLOW (-4)  /* internal capacity exceeded even after regrow */
+
+/* ORBmatcher.cc:34-36 */
+#define ORBGPU_TH_HIGH 100
+#define ORBGPU_TH_LOW 50
+#define ORBGPU_HISTO_LENGTH 30
+/* Frame.h:44-45 */
+#define ORBGPU_FRAME_GRID_ROWS 48
+#define ORBGPU_FRAME_GRID_COLS 64
+
+typedef struct orbgpu_ctx orbgpu_ctx;
+typedef struct orbgpu_frame orbgpu_frame;   /* device copy of one Frame/KeyFrame feature set */
+typedef struct orbgpu_voc orbgpu_voc;       /* device copy of a DBoW2 vocabulary tree */
+typedef struct orbgpu_kfset orbgpu_kfset;   /* device-resident batch of keyframes (config C4) */
+typedef struct orbgpu_db orbgpu_db;         /* device-resident descriptor database (config C5) */
+
+/* Host-side view of the Frame / KeyFrame members the matcher reads.
+ * Frame.h:219-296, KeyFrame.h:378-406. */
+typedef struct orbgpu_frame_host {
+    int32_t n;              /* Frame::N */
+    const uint8_t *desc;    /* [n][32]  mDescriptors */
+    const float *kp_xy;     /* [n][2]   mvKeysUn[i].pt */
+    const int32_t *octave;  /* [n]      mvKeysUn[i].octave */
+    const float *angle;     /* [n]      mvKeysUn[i].angle */
+    const float *u_right;   /* [n] mvuRight, or NULL == monocular (all -1) */
+    float min_x, min_y, max_x, max_y; /* mnMinX.. (KeyFrame stores ints: pass them converted) */
+    float grid_inv_w, grid_inv_h;     /* mfGridElementWidthInv / HeightInv */
+    int32_t grid_cols, grid_rows;     /* 64 x 48 */
+    int32_t n_levels;                 /* mnScaleLevels (<= 16) */
+    const float *scale_factors;       /* [n_levels] mvScaleFactors */
+    const float *level_sigma2;        /* [n_levels] mvLevelSigma2 */
+    /* optional FeatureVector in CSR form (flattened std::map<NodeId, vector<uint>>,
+     * FeatureVector.h): node ids ascending, feature ids ascending inside a node.
+     * fv_n_nodes == 0 means "no FeatureVector yet" (orbgpu_transform can fill it). */
+    int32_t fv_n_nodes;
+    const uint32_t *fv_node_ids;   /* [fv_n_nodes] */
+    const int32_t *fv_offsets;     /* [fv_n_nodes+1] */
+    const uint32_t *fv_features;   /* [fv_offsets[fv_n_nodes]] */
+} orbgpu_frame_host;
+
+/* Host-side view of a DBoW2 vocabulary (TemplatedVocabulary.h:361-435: m_k, m_L, m_nodes).
+ * Node 0 is the root.  children of node i are child_ids[child_offsets[i] .. child_offsets[i+1]),
+ * in the order of Node::children.  A node without children is a leaf (Node::isLeaf). */
+typedef struct orbgpu_voc_host {
+    int32_t k, L;
+    int32_t n_nodes;
+    const uint8_t *node_desc;       /* [n_nodes][32] Node::descriptor (root row unused) */
+    const int32_t *child_offsets;   /* [n_nodes+1] */
+    const uint32_t *child_ids;      /* [child_offsets[n_nodes]] */
+    const double *weight;           /* [n_nodes] Node::weight */
+    const uint32_t *word_id;        /* [n_nodes] Node::word_id (valid on leaves) */
+} orbgpu_voc_host;
+
+/* ---- context ------------------------------------------------------------------------- */
+int orbgpu_device_count(void);
+int orbgpu_create(int device, orbgpu_ctx **out);
+int orbgpu_create_on_stream(int device, void *cuda_stream, orbgpu_ctx **out);
+void orbgpu_destroy(orbgpu_ctx *ctx);
+int orbgpu_synchronize(orbgpu_ctx *ctx);
+void *orbgpu_stream(orbgpu_ctx *ctx); /* cudaStream_t the context launches on */
+const char *orbgpu_last_error(void);
+const char *orbgpu_version(void);
+/* number of this library's kernels launched through ctx since creation (bench gpu_launches) */
+int64_t orbgpu_launch_count(orbgpu_ctx *ctx);
+/* number of Hamming comparisons (DescriptorDistance-equivalents) the last search call
+ * executed, counted on the device exactly where the reference calls DescriptorDistance. */
+int64_t orbgpu_last_comparisons(orbgpu_ctx *ctx);
+
+/* ---- a1: ORBmatcher::DescriptorDistance (ORBmatcher.cc:2388-2408), FORB::distance (FORB.cpp:92-112)
+ * batched: out[i] = hamming(a[i], b[i]).  Host pointers. */
+int orbgpu_descriptor_distance(orbgpu_ctx *ctx, int64_t n, const uint8_t *a, const uint8_t *b, int32_t *out);
+
+/* ---- a2/a3: Frame::AssignFeaturesToGrid (Frame.cc:469-507), PosInGrid (:973-989),
+ * Frame::GetFeaturesInArea (:868-962), KeyFrame::GetFeaturesInArea (KeyFrame.cc:859-907).
+ * Upload builds the device CSR cell index (cell = ix*rows+iy, in-cell ascending feature id). */
+int orbgpu_frame_upload(orbgpu_ctx *ctx, const orbgpu_frame_host *f, orbgpu_frame **out);
+void orbgpu_frame_destroy(orbgpu_frame *f);
+int orbgpu_frame_n(const orbgpu_frame *f);
+/* copy the device CSR grid back: cell_start[cols*rows+1], cell_items[n] (n_in_grid <= n valid) */
+int orbgpu_frame_grid_download(orbgpu_ctx *ctx, const orbgpu_frame *f, int32_t *cell_start, int32_t *cell_items);
+/* batched GetFeaturesInArea: for query q the indices in reference order are
+ * out_idx[out_offsets[q] .. out_offsets[q+1]).  min_level/max_level as in Frame.cc:868 (pass -1,-1
+ * for the KeyFrame variant).  out_idx capacity is cap entries; total is returned in *total. */
+int orbgpu_features_in_area(orbgpu_ctx *ctx, const orbgpu_frame *f, int32_t nq, const float *x, const float *y,
+                            const float *r, const int32_t *min_level, const int32_t *max_level,
+                            int32_t *out_offsets, int32_t *out_idx, int64_t cap, int64_t *total);
+
+/* ---- a4: ORBmatcher::SearchForInitialization (ORBmatcher.cc:735-878)
+ * prev_matched_xy [n1][2] in/out (vbPrevMatched); matches12 [n1] out (vnMatches12). */
+int orbgpu_search_for_initialization(orbgpu_ctx *ctx, const orbgpu_frame *f1, const orbgpu_frame *f2,
+                                     float *prev_matched_xy, int32_t window_size, float nnratio, int32_t check_ori,
+                                     int32_t *matches12, int32_t *nmatches);
+
+/* ---- a5: ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th, bFarPoints, thFarPoints)
+ * (ORBmatcher.cc:44-242, monocular/RGB-D path Nleft==-1) + RadiusByViewingCos (:245-252).
+ * Map-point inputs are the members the function reads (MapPoint.h:166-177, 209-239). */
+typedef struct orbgpu_mappoints_host {
+    int32_t n;
+    const uint8_t *desc;          /* [n][32] MapPoint::GetDescriptor() */
+    const float *proj_xy;         /* [n][2]  mTrackProjX, mTrackProjY */
+    const float *proj_xr;         /* [n]     mTrackProjXR (stereo gate), or NULL */
+    const int32_t *scale_level;   /* [n]     mnTrackScaleLevel */
+    const float *view_cos;        /* [n]     mTrackViewCos */
+    const float *depth;           /* [n]     mTrackDepth */
+    const uint8_t *in_view;       /* [n]     mbTrackInView */
+    const uint8_t *bad;           /* [n]     isBad() */
+    const int32_t *n_obs;         /* [n]     Observations() */
+} orbgpu_mappoints_host;
+/* kp_mp [F.N] in/out: index of the map point (into mps) assigned to each keypoint, -1 none
+ * (F.mvpMapPoints).  kp_prior_obs [F.N] in: Observations() of the map point a keypoint
+ * already holds on entry (0 when none) -- used by the skip rule at :102-104. */
+int orbgpu_search_by_projection_local(orbgpu_ctx *ctx, const orbgpu_frame *f, const orbgpu_mappoints_host *mps,
+                                      float th, int32_t far_points, float th_far_points, float nnratio,
+                                      const int32_t *kp_prior_obs, int32_t *kp_mp, int32_t *nmatches);
+
+/* ---- a11/a12: TemplatedVocabulary::transform (TemplatedVocabulary.h:1127-1194, 1216-1258) */
+int orbgpu_voc_upload(orbgpu_ctx *ctx, const orbgpu_voc_host *v, orbgpu_voc **out);
+void orbgpu_voc_destroy(orbgpu_voc *v);
+/* Descends every feature of frame f.  Outputs (host, each [n], any may be NULL):
+ *   word_id, node_id (node at level L-levelsup, 0 == root when L-levelsup<=0), weight.
+ * When store_featvec != 0 the frame's device FeatureVector (CSR by node id, stopped
+ * words w==0 dropped, TemplatedVocabulary.h:1157) is (re)built on the device so that
+ * SearchByBoW / SearchForTriangulation can run without a host round trip. */
+int orbgpu_transform(orbgpu_ctx *ctx, const orbgpu_voc *voc, orbgpu_frame *f, int32_t levelsup, int32_t store_featvec,
+                     uint32_t *word_id, uint32_t *node_id, double *weight);
+/* device-built BowVector (BowVector.cpp:35-85): words ascending, value = idf added count
+ * times in feature order, then L1-normalised in ascending word order.  Capacity n each. */
+int orbgpu_bowvector_download(orbgpu_ctx *ctx, const orbgpu_frame *f, int32_t *n_words, uint32_t *words, double *values);
+/* device FeatureVector back to host CSR (capacities: n nodes, n+1 offsets, n features) */
+int orbgpu_featvec_download(orbgpu_ctx *ctx, const orbgpu_frame *f, int32_t *n_nodes, uint32_t *node_ids,
+                            int32_t *offsets, uint32_t *features);
+
+/* ---- a7: ORBmatcher::SearchByBoW (KeyFrame*, Frame&, vector<MapPoint*>&) (ORBmatcher.cc:262-496)
+ * kf_mp_valid [kf.N]: 1 when vpMapPointsKF[i] != NULL && !isBad().
+ * match_f2kf [f.N] out: index of the KF feature whose MapPoint was assigned to F feature i
+ * (vpMapPointMatches[i] = vpMapPointsKF[match]), -1 none. */
+int orbgpu_search_by_bow_kf_f(orbgpu_ctx *ctx, const orbgpu_frame *kf, const orbgpu_frame *f, const uint8_t *kf_mp_valid,
+                              float nnratio, int32_t check_ori, int32_t *match_f2kf, int32_t *nmatches);
+/* KeyFrame <-> KeyFrame variant (ORBmatcher.cc:890-1043): strict best < TH_LOW, vbMatched2.
+ * match_12 [kf1.N] out: index of the KF2 feature matched to KF1 feature i, -1 none. */
+int orbgpu_search_by_bow_kf_kf(orbgpu_ctx *ctx, const orbgpu_frame *kf1, const orbgpu_frame *kf2,
+                               const uint8_t *kf1_mp_valid, const uint8_t *kf2_mp_valid, float nnratio, int32_t check_ori,
+                               int32_t *match_12, int32_t *nmatches);
+
+/* ---- a8/a9: batched ORBmatcher::SearchForTriangulation (ORBmatcher.cc:1045-1328) with
+ * Pinhole::epipolarConstrain (Pinhole.cpp:189-219), monocular pinhole path.
+ * A kfset holds n_kf keyframes of n_feat features each, resident in HBM. */
+typedef struct orbgpu_kfset_host {
+    int32_t n_kf, n_feat;
+    const uint8_t *desc;         /* [n_kf][n_feat][32] */
+    const float *kp_xy;          /* [n_kf][n_feat][2] */
+    const int32_t *octave;       /* [n_kf][n_feat] */
+    const float *angle;          /* [n_kf][n_feat] */
+    const uint8_t *has_mp;       /* [n_kf][n_feat] GetMapPoint(i) != NULL */
+    const float *u_right;        /* [n_kf][n_feat] mvuRight or NULL (mono) */
+    const uint32_t *node_id;     /* [n_kf][n_feat] FeatureVector node of each feature, 0xFFFFFFFF == none */
+    int32_t n_levels;
+    const float *scale_factors;  /* [n_levels] */
+    const float *level_sigma2;   /* [n_levels] */
+} orbgpu_kfset_host;
+int orbgpu_kfset_upload(orbgpu_ctx *ctx, const orbgpu_kfset_host *s, orbgpu_kfset **out);
+void orbgpu_kfset_destroy(orbgpu_kfset *s);
+/* Per pair p: keyframes (kf1[p], kf2[p]); geometry precomputed by the caller with the
+ * reference's own host algebra (ORBmatcher.cc:1053-1071, Pinhole.cpp:194-197):
+ *   ep[p][2]  epipole of camera 1 in image 2;  f12[p][9] row-major F12 = K1^-T [t12]x R12 K2^-1.
+ * matches12 [n_pairs][n_feat] out (vMatches12, -1 none), nmatches [n_pairs] out.
+ * Pointers are HOST pointers; the _dev variant takes device pointers and does no copies. */
+int orbgpu_search_for_triangulation_batch(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs, const int32_t *kf1,
+                                          const int32_t *kf2, const float *ep, const float *f12, int32_t only_stereo,
+                                          int32_t coarse, int32_t check_ori, int32_t *matches12, int32_t *nmatches);
+int orbgpu_search_for_triangulation_batch_dev(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs, const int32_t *kf1_dev,
+                                              const int32_t *kf2_dev, const float *ep_dev, const float *f12_dev,
+                                              int32_t only_stereo, int32_t coarse, int32_t check_ori, int32_t *matches12_dev,
+                                              int32_t *nmatches_dev);
+
+/* ---- brute-force 2-NN + ratio test (north_star "SearchByNN"; not in this fork: semantics are the
+ * inner loop of SearchByBoW, ORBmatcher.cc:327-355 + accept rule :392-395).
+ * For each query: best = first db index attaining the minimum distance, second = second
+ * smallest distance of the multiset (256 when nd < 2).  match = best_idx when
+ * best <= th_low && (float)best < nnratio*(float)second, else -1. */
+int orbgpu_db_upload(orbgpu_ctx *ctx, int64_t nd, const uint8_t *db_desc, orbgpu_db **out);
+int orbgpu_db_from_dev(orbgpu_ctx *ctx, int64_t nd, const void *db_desc_dev, orbgpu_db **out); /* borrows the pointer */
+void orbgpu_db_destroy(orbgpu_db *db);
+int orbgpu_knn2_ratio(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const uint8_t *q_desc, int32_t th_low, float nnratio,
+                      int32_t *best_idx, int32_t *best_dist, int32_t *second_dist, int32_t *match);
+int orbgpu_knn2_ratio_dev(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const void *q_desc_dev, int32_t th_low,
+                          float nnratio, int32_t *best_idx_dev, int32_t *best_dist_dev, int32_t *second_dist_dev,
+                          int32_t *match_dev);
+/* selects the all-pairs engine: 0 = auto, 1 = LOP3+POPC CUDA-core kernel,
+ * 2 = mma.sync b1 and.popc, 3 = tcgen05 (+-1 fp8 contraction, TMEM accumulators). */
+int orbgpu_knn2_set_engine(orbgpu_ctx *ctx, int32_t engine);
+
+/* ---- a10: ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:2341-2383) exposed for testing:
+ * histo[30] bin sizes -> ind[3]. Runs on the device. */
+int orbgpu_compute_three_maxima(orbgpu_ctx *ctx, const int32_t *histo, int32_t L, int32_t *ind);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBMATCH_B200_H */

@@ -1,0 +1,374 @@
+"""ORACLE python bindings (test infrastructure, NOT product code).
+
+Loads oracle/liborb_oracle.so (plain-C restatement) and, when present,
+oracle/_ref/libref_orbmatcher.so (the reference's own ORBmatcher.cc + DBoW2 compiled
+unmodified).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs import this module; the product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+from orb_slam3_comments_ghr_b200._abi import (FrameHostStruct, HostFrame, HostKfSet, HostMapPoints, HostVoc,
+                                              KfSetHostStruct, MapPointsHostStruct, VocHostStruct, as_f32, as_i32,
+                                              as_u8, f32p, f64p, i32p, u8p, u32p)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def build(ref: bool = True) -> None:
+    """compile the C restatement (and oracle/_ref when /root/reference is mounted)."""
+    subprocess.check_call(["make", "-s", "-C", _HERE, "liborb_oracle.so"])
+    if ref:
+        subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t) if a is not None else C.cast(None, t)
+
+
+class Oracle:
+    """Plain-C restatement (orb_oracle.c)."""
+
+    kind = "port"
+
+    def __init__(self):
+        path = os.path.join(_HERE, "liborb_oracle.so")
+        if not os.path.exists(path):
+            build(ref=False)
+        self.lib = L = C.CDLL(path)
+        L.oracle_comparisons.restype = C.c_int64
+        L.oracle_descriptor_distance.argtypes = [u8p, u8p]
+        L.oracle_grid_build.argtypes = [C.POINTER(FrameHostStruct), i32p, i32p]
+        L.oracle_features_in_area.argtypes = [C.POINTER(FrameHostStruct), i32p, i32p, C.c_float, C.c_float, C.c_float,
+                                              C.c_int, C.c_int, i32p]
+        L.oracle_compute_three_maxima.argtypes = [i32p, C.c_int, i32p]
+        L.oracle_search_for_initialization.argtypes = [C.POINTER(FrameHostStruct), C.POINTER(FrameHostStruct), f32p,
+                                                       C.c_int, C.c_float, C.c_int, i32p]
+        L.oracle_search_by_projection_local.argtypes = [C.POINTER(FrameHostStruct), C.POINTER(MapPointsHostStruct),
+                                                        C.c_float, C.c_int, C.c_float, C.c_float, i32p, i32p]
+        L.oracle_voc_transform.argtypes = [C.POINTER(VocHostStruct), C.c_int32, u8p, C.c_int, u32p, u32p, f64p]
+        L.oracle_bowvector.argtypes = [C.c_int32, u32p, f64p, u32p, f64p]
+        L.oracle_featvec.argtypes = [C.c_int32, u32p, f64p, u32p, i32p, u32p]
+        L.oracle_search_by_bow_kf_f.argtypes = [C.POINTER(FrameHostStruct), C.POINTER(FrameHostStruct), u8p, C.c_float,
+                                                C.c_int, i32p]
+        L.oracle_search_by_bow_kf_kf.argtypes = [C.POINTER(FrameHostStruct), C.POINTER(FrameHostStruct), u8p, u8p,
+                                                 C.c_float, C.c_int, i32p]
+        L.oracle_search_for_triangulation.argtypes = [C.POINTER(KfSetHostStruct), C.c_int, C.c_int, f32p, f32p, C.c_int,
+                                                      C.c_int, C.c_int, i32p]
+        L.oracle_search_for_triangulation_batch.argtypes = [C.POINTER(KfSetHostStruct), C.c_int, i32p, i32p, f32p, f32p,
+                                                            C.c_int, C.c_int, C.c_int, i32p, i32p, C.c_int]
+        L.oracle_knn2_ratio.argtypes = [C.c_int64, u8p, C.c_int64, u8p, C.c_int, C.c_float, i32p, i32p, i32p, i32p,
+                                        C.c_int]
+
+    # -- counters
+    def comparisons(self) -> int:
+        return int(self.lib.oracle_comparisons())
+
+    def reset_comparisons(self):
+        self.lib.oracle_comparisons_reset()
+
+    # -- primitives
+    def descriptor_distance(self, a, b) -> int:
+        a, b = as_u8(a), as_u8(b)
+        return int(self.lib.oracle_descriptor_distance(_p(a, u8p), _p(b, u8p)))
+
+    def grid(self, f: HostFrame):
+        cs = np.zeros(f.grid_cols * f.grid_rows + 1, dtype=np.int32)
+        ci = np.full(max(f.n, 1), -1, dtype=np.int32)
+        s = f.struct()
+        self.lib.oracle_grid_build(C.byref(s), _p(cs, i32p), _p(ci, i32p))
+        return cs, ci
+
+    def features_in_area(self, f: HostFrame, x, y, r, min_level=-1, max_level=-1, grid=None):
+        cs, ci = grid if grid is not None else self.grid(f)
+        out = np.empty(max(f.n, 1), dtype=np.int32)
+        s = f.struct()
+        n = self.lib.oracle_features_in_area(C.byref(s), _p(cs, i32p), _p(ci, i32p), float(x), float(y), float(r),
+                                             int(min_level), int(max_level), _p(out, i32p))
+        return out[:n].copy()
+
+    def compute_three_maxima(self, sizes):
+        sizes = as_i32(sizes)
+        ind = np.zeros(3, dtype=np.int32)
+        self.lib.oracle_compute_three_maxima(_p(sizes, i32p), int(sizes.shape[0]), _p(ind, i32p))
+        return ind
+
+    # -- searches
+    def search_for_initialization(self, f1: HostFrame, f2: HostFrame, prev_matched, window_size, nnratio, check_ori):
+        prev = as_f32(prev_matched).copy()
+        m = np.empty(f1.n, dtype=np.int32)
+        s1, s2 = f1.struct(), f2.struct()
+        n = self.lib.oracle_search_for_initialization(C.byref(s1), C.byref(s2), _p(prev, f32p), int(window_size),
+                                                      float(nnratio), int(check_ori), _p(m, i32p))
+        return int(n), m, prev
+
+    def search_by_projection_local(self, f: HostFrame, mps: HostMapPoints, th, far_points, th_far, nnratio,
+                                   kp_prior_obs, kp_mp):
+        kp_mp = as_i32(kp_mp).copy()
+        prior = as_i32(kp_prior_obs)
+        sf, sm = f.struct(), mps.struct()
+        n = self.lib.oracle_search_by_projection_local(C.byref(sf), C.byref(sm), float(th), int(far_points),
+                                                       float(th_far), float(nnratio), _p(prior, i32p), _p(kp_mp, i32p))
+        return int(n), kp_mp
+
+    def voc_transform(self, voc: HostVoc, desc, levelsup):
+        desc = as_u8(desc).reshape(-1, 32)
+        n = desc.shape[0]
+        w = np.empty(n, dtype=np.uint32)
+        nid = np.empty(n, dtype=np.uint32)
+        wt = np.empty(n, dtype=np.float64)
+        sv = voc.struct()
+        self.lib.oracle_voc_transform(C.byref(sv), n, _p(desc, u8p), int(levelsup), _p(w, u32p), _p(nid, u32p),
+                                      _p(wt, f64p))
+        return w, nid, wt
+
+    def bowvector(self, word_id, weight):
+        n = word_id.shape[0]
+        words = np.empty(max(n, 1), dtype=np.uint32)
+        vals = np.empty(max(n, 1), dtype=np.float64)
+        m = self.lib.oracle_bowvector(n, _p(word_id, u32p), _p(weight, f64p), _p(words, u32p), _p(vals, f64p))
+        return words[:m].copy(), vals[:m].copy()
+
+    def featvec(self, node_id, weight):
+        n = node_id.shape[0]
+        nodes = np.empty(max(n, 1), dtype=np.uint32)
+        offs = np.empty(n + 1, dtype=np.int32)
+        feats = np.empty(max(n, 1), dtype=np.uint32)
+        m = self.lib.oracle_featvec(n, _p(node_id, u32p), _p(weight, f64p), _p(nodes, u32p), _p(offs, i32p),
+                                    _p(feats, u32p))
+        return nodes[:m].copy(), offs[:m + 1].copy(), feats[:offs[m]].copy()
+
+    def search_by_bow_kf_f(self, kf: HostFrame, f: HostFrame, kf_mp_valid, nnratio, check_ori):
+        valid = as_u8(kf_mp_valid)
+        out = np.empty(f.n, dtype=np.int32)
+        a, b = kf.struct(), f.struct()
+        n = self.lib.oracle_search_by_bow_kf_f(C.byref(a), C.byref(b), _p(valid, u8p), float(nnratio), int(check_ori),
+                                               _p(out, i32p))
+        return int(n), out
+
+    def search_by_bow_kf_kf(self, kf1: HostFrame, kf2: HostFrame, v1, v2, nnratio, check_ori):
+        v1, v2 = as_u8(v1), as_u8(v2)
+        out = np.empty(kf1.n, dtype=np.int32)
+        a, b = kf1.struct(), kf2.struct()
+        n = self.lib.oracle_search_by_bow_kf_kf(C.byref(a), C.byref(b), _p(v1, u8p), _p(v2, u8p), float(nnratio),
+                                                int(check_ori), _p(out, i32p))
+        return int(n), out
+
+    def search_for_triangulation_batch(self, s: HostKfSet, kf1, kf2, ep, f12, only_stereo=0, coarse=0, check_ori=0,
+                                       n_threads=1):
+        kf1, kf2 = as_i32(kf1), as_i32(kf2)
+        ep, f12 = as_f32(ep), as_f32(f12)
+        P = kf1.shape[0]
+        m = np.empty((P, s.n_feat), dtype=np.int32)
+        nm = np.empty(P, dtype=np.int32)
+        ss = s.struct()
+        self.lib.oracle_search_for_triangulation_batch(C.byref(ss), P, _p(kf1, i32p), _p(kf2, i32p), _p(ep, f32p),
+                                                       _p(f12, f32p), int(only_stereo), int(coarse), int(check_ori),
+                                                       _p(m, i32p), _p(nm, i32p), int(n_threads))
+        return nm, m
+
+    def knn2_ratio(self, q, db, th_low=50, nnratio=0.8, n_threads=1):
+        q, db = as_u8(q).reshape(-1, 32), as_u8(db).reshape(-1, 32)
+        nq = q.shape[0]
+        bi = np.empty(nq, dtype=np.int32)
+        bd = np.empty(nq, dtype=np.int32)
+        sd = np.empty(nq, dtype=np.int32)
+        mt = np.empty(nq, dtype=np.int32)
+        self.lib.oracle_knn2_ratio(nq, _p(q, u8p), db.shape[0], _p(db, u8p), int(th_low), float(nnratio), _p(bi, i32p),
+                                   _p(bd, i32p), _p(sd, i32p), _p(mt, i32p), int(n_threads))
+        return bi, bd, sd, mt
+
+
+class Reference:
+    """The reference's own ORBmatcher.cc / DBoW2 (oracle/_ref/libref_orbmatcher*.so)."""
+
+    kind = "reference"
+
+    @staticmethod
+    def available(fast: bool = False) -> bool:
+        name = "libref_orbmatcher_fast.so" if fast else "libref_orbmatcher.so"
+        return os.path.exists(os.path.join(_HERE, "_ref", name))
+
+    def __init__(self, fast: bool = False):
+        name = "libref_orbmatcher_fast.so" if fast else "libref_orbmatcher.so"
+        path = os.path.join(_HERE, "_ref", name)
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path}: run `make -C oracle ref` where /root/reference is mounted")
+        self.lib = L = C.CDLL(path)
+        FH, MP, KS, VH = C.POINTER(FrameHostStruct), C.POINTER(MapPointsHostStruct), C.POINTER(KfSetHostStruct), \
+            C.POINTER(VocHostStruct)
+        L.ref_descriptor_distance.argtypes = [u8p, u8p]
+        L.ref_compute_three_maxima.argtypes = [i32p, C.c_int, i32p]
+        L.ref_features_in_area.argtypes = [FH, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, i32p]
+        L.ref_grid.argtypes = [FH, i32p, i32p]
+        L.ref_search_for_initialization.argtypes = [FH, FH, f32p, C.c_int, C.c_float, C.c_int, i32p]
+        L.ref_search_by_projection_local.argtypes = [FH, MP, C.c_float, C.c_int, C.c_float, C.c_float, i32p, i32p]
+        L.ref_search_by_bow_kf_f.argtypes = [FH, FH, u8p, C.c_float, C.c_int, i32p]
+        L.ref_search_by_bow_kf_kf.argtypes = [FH, FH, u8p, u8p, C.c_float, C.c_int, i32p]
+        L.ref_triangulation_geometry.argtypes = [f32p, f32p, f32p, f32p, f32p, f32p]
+        L.ref_search_for_triangulation.argtypes = [KS, C.c_int, C.c_int, f32p, f32p, f32p, f32p, C.c_int, C.c_int,
+                                                   C.c_int, C.c_float, i32p]
+        L.ref_search_for_triangulation_batch.argtypes = [KS, C.c_int, i32p, i32p, f32p, f32p, f32p, C.c_int, C.c_int,
+                                                         C.c_int, C.c_float, i32p, i32p, C.c_int]
+        L.ref_knn2_ratio.argtypes = [C.c_int64, u8p, C.c_int64, u8p, C.c_int, C.c_float, i32p, i32p, i32p, i32p, C.c_int]
+        L.ref_voc_create.restype = C.c_void_p
+        L.ref_voc_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
+        L.ref_voc_from_flat.restype = C.c_void_p
+        L.ref_voc_from_flat.argtypes = [VH]
+        L.ref_voc_destroy.argtypes = [C.c_void_p]
+        L.ref_voc_n_nodes.argtypes = [C.c_void_p]
+        L.ref_voc_n_children.argtypes = [C.c_void_p]
+        L.ref_voc_n_words.argtypes = [C.c_void_p]
+        L.ref_voc_export.argtypes = [C.c_void_p, u8p, i32p, u32p, f64p, u32p]
+        L.ref_voc_transform.argtypes = [C.c_void_p, C.c_int, u8p, C.c_int, u32p, u32p, f64p, u32p, f64p, i32p, u32p,
+                                        i32p, u32p]
+
+    def descriptor_distance(self, a, b) -> int:
+        a, b = as_u8(a), as_u8(b)
+        return int(self.lib.ref_descriptor_distance(_p(a, u8p), _p(b, u8p)))
+
+    def compute_three_maxima(self, sizes):
+        sizes = as_i32(sizes)
+        ind = np.zeros(3, dtype=np.int32)
+        self.lib.ref_compute_three_maxima(_p(sizes, i32p), int(sizes.shape[0]), _p(ind, i32p))
+        return ind
+
+    def grid(self, f: HostFrame):
+        cs = np.zeros(f.grid_cols * f.grid_rows + 1, dtype=np.int32)
+        ci = np.full(max(f.n, 1), -1, dtype=np.int32)
+        s = f.struct()
+        self.lib.ref_grid(C.byref(s), _p(cs, i32p), _p(ci, i32p))
+        return cs, ci
+
+    def features_in_area(self, f: HostFrame, x, y, r, min_level=-1, max_level=-1):
+        out = np.empty(max(f.n, 1), dtype=np.int32)
+        s = f.struct()
+        n = self.lib.ref_features_in_area(C.byref(s), float(x), float(y), float(r), int(min_level), int(max_level),
+                                          _p(out, i32p))
+        return out[:n].copy()
+
+    def search_for_initialization(self, f1, f2, prev_matched, window_size, nnratio, check_ori):
+        prev = as_f32(prev_matched).copy()
+        m = np.empty(f1.n, dtype=np.int32)
+        s1, s2 = f1.struct(), f2.struct()
+        n = self.lib.ref_search_for_initialization(C.byref(s1), C.byref(s2), _p(prev, f32p), int(window_size),
+                                                   float(nnratio), int(check_ori), _p(m, i32p))
+        return int(n), m, prev
+
+    def search_by_projection_local(self, f, mps, th, far_points, th_far, nnratio, kp_prior_obs, kp_mp):
+        kp_mp = as_i32(kp_mp).copy()
+        prior = as_i32(kp_prior_obs)
+        sf, sm = f.struct(), mps.struct()
+        n = self.lib.ref_search_by_projection_local(C.byref(sf), C.byref(sm), float(th), int(far_points), float(th_far),
+                                                    float(nnratio), _p(prior, i32p), _p(kp_mp, i32p))
+        return int(n), kp_mp
+
+    def search_by_bow_kf_f(self, kf, f, kf_mp_valid, nnratio, check_ori):
+        valid = as_u8(kf_mp_valid)
+        out = np.empty(f.n, dtype=np.int32)
+        a, b = kf.struct(), f.struct()
+        n = self.lib.ref_search_by_bow_kf_f(C.byref(a), C.byref(b), _p(valid, u8p), float(nnratio), int(check_ori),
+                                            _p(out, i32p))
+        return int(n), out
+
+    def search_by_bow_kf_kf(self, kf1, kf2, v1, v2, nnratio, check_ori):
+        v1, v2 = as_u8(v1), as_u8(v2)
+        out = np.empty(kf1.n, dtype=np.int32)
+        a, b = kf1.struct(), kf2.struct()
+        n = self.lib.ref_search_by_bow_kf_kf(C.byref(a), C.byref(b), _p(v1, u8p), _p(v2, u8p), float(nnratio),
+                                             int(check_ori), _p(out, i32p))
+        return int(n), out
+
+    def triangulation_geometry(self, T1w, T2w, K1, K2):
+        """ep[2], f12[9] from poses ([R row-major | t], 12 floats) the way ORBmatcher.cc:1053-1071 +
+        Pinhole.cpp:194-197 compute them in this build."""
+        T1w, T2w, K1, K2 = as_f32(T1w), as_f32(T2w), as_f32(K1), as_f32(K2)
+        ep = np.empty(2, dtype=np.float32)
+        f12 = np.empty(9, dtype=np.float32)
+        self.lib.ref_triangulation_geometry(_p(T1w, f32p), _p(T2w, f32p), _p(K1, f32p), _p(K2, f32p), _p(ep, f32p),
+                                            _p(f12, f32p))
+        return ep, f12
+
+    def search_for_triangulation_batch(self, s: HostKfSet, kf1, kf2, T1w, T2w, K, only_stereo=0, coarse=0, check_ori=0,
+                                       nnratio=0.6, n_threads=1):
+        kf1, kf2 = as_i32(kf1), as_i32(kf2)
+        T1w, T2w, K = as_f32(T1w), as_f32(T2w), as_f32(K)
+        P = kf1.shape[0]
+        m = np.empty((P, s.n_feat), dtype=np.int32)
+        nm = np.empty(P, dtype=np.int32)
+        ss = s.struct()
+        self.lib.ref_search_for_triangulation_batch(C.byref(ss), P, _p(kf1, i32p), _p(kf2, i32p), _p(T1w, f32p),
+                                                    _p(T2w, f32p), _p(K, f32p), int(only_stereo), int(coarse),
+                                                    int(check_ori), float(nnratio), _p(m, i32p), _p(nm, i32p),
+                                                    int(n_threads))
+        return nm, m
+
+    def knn2_ratio(self, q, db, th_low=50, nnratio=0.8, n_threads=1):
+        q, db = as_u8(q).reshape(-1, 32), as_u8(db).reshape(-1, 32)
+        nq = q.shape[0]
+        bi = np.empty(nq, dtype=np.int32)
+        bd = np.empty(nq, dtype=np.int32)
+        sd = np.empty(nq, dtype=np.int32)
+        mt = np.empty(nq, dtype=np.int32)
+        self.lib.ref_knn2_ratio(nq, _p(q, u8p), db.shape[0], _p(db, u8p), int(th_low), float(nnratio), _p(bi, i32p),
+                                _p(bd, i32p), _p(sd, i32p), _p(mt, i32p), int(n_threads))
+        return bi, bd, sd, mt
+
+    # -- vocabulary
+    def voc_create(self, training_desc, k, L, seed) -> "RefVocHandle":
+        """training_desc [n_images, n_per_image, 32] -> TemplatedVocabulary::create (TemplatedVocabulary.h:560)"""
+        d = as_u8(training_desc)
+        h = self.lib.ref_voc_create(int(k), int(L), int(d.shape[0]), int(d.shape[1]), _p(d, u8p), int(seed))
+        return RefVocHandle(self, h, k, L)
+
+    def voc_from_flat(self, voc: HostVoc) -> "RefVocHandle":
+        s = voc.struct()
+        return RefVocHandle(self, self.lib.ref_voc_from_flat(C.byref(s)), voc.k, voc.L)
+
+
+class RefVocHandle:
+    def __init__(self, ref: Reference, h, k, L):
+        self.ref, self.h, self.k, self.L = ref, h, k, L
+
+    def __del__(self):
+        try:
+            self.ref.lib.ref_voc_destroy(self.h)
+        except Exception:
+            pass
+
+    def export(self) -> HostVoc:
+        L = self.ref.lib
+        n = L.ref_voc_n_nodes(self.h)
+        nc = L.ref_voc_n_children(self.h)
+        desc = np.zeros((n, 32), dtype=np.uint8)
+        off = np.zeros(n + 1, dtype=np.int32)
+        ch = np.zeros(max(nc, 1), dtype=np.uint32)
+        w = np.zeros(n, dtype=np.float64)
+        wid = np.zeros(n, dtype=np.uint32)
+        L.ref_voc_export(self.h, _p(desc, u8p), _p(off, i32p), _p(ch, u32p), _p(w, f64p), _p(wid, u32p))
+        return HostVoc(self.k, self.L, desc, off, ch[:nc], w, wid)
+
+    def transform(self, desc, levelsup):
+        desc = as_u8(desc).reshape(-1, 32)
+        n = desc.shape[0]
+        w = np.empty(n, dtype=np.uint32)
+        nid = np.empty(n, dtype=np.uint32)
+        wt = np.empty(n, dtype=np.float64)
+        bw = np.empty(max(n, 1), dtype=np.uint32)
+        bv = np.empty(max(n, 1), dtype=np.float64)
+        nn = C.c_int32(0)
+        fn = np.empty(max(n, 1), dtype=np.uint32)
+        fo = np.empty(n + 1, dtype=np.int32)
+        ff = np.empty(max(n, 1), dtype=np.uint32)
+        nw = self.ref.lib.ref_voc_transform(self.h, n, _p(desc, u8p), int(levelsup), _p(w, u32p), _p(nid, u32p),
+                                            _p(wt, f64p), _p(bw, u32p), _p(bv, f64p), C.byref(nn), _p(fn, u32p),
+                                            _p(fo, i32p), _p(ff, u32p))
+        m = nn.value
+        return dict(word_id=w, node_id=nid, weight=wt, bow_words=bw[:nw].copy(), bow_values=bv[:nw].copy(),
+                    fv_node_ids=fn[:m].copy(), fv_offsets=fo[:m + 1].copy(), fv_features=ff[:fo[m]].copy())

@@ -1,0 +1,535 @@
+// ORACLE (test infrastructure, NOT product code) -- flat-array entry points around the
+// reference's OWN matcher and vocabulary code.
+//
+// This translation unit is linked with the UNMODIFIED reference sources
+//   /root/reference/src/ORBmatcher.cc
+//   /root/reference/Thirdparty/DBoW2/DBoW2/{FORB,BowVector,FeatureVector,ScoringObject}.cpp
+//   /root/reference/Thirdparty/DBoW2/DUtils/{Random,Timestamp}.cpp
+// (compiled where they lie, see oracle/Makefile) into oracle/_ref/libref_orbmatcher.so.
+// It builds stub Frame / KeyFrame / MapPoint objects (oracle/shim/orbslam_stubs.h) from the
+// same flat structs the product ABI takes, calls ORB_SLAM3::ORBmatcher / ORBVocabulary, and
+// flattens the STL results.  It is what pins the C restatement (orb_oracle.c) and the golden
+// vectors (tests/golden/) to the reference's real behaviour.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#include "orbmatch_b200.h"
+
+#include "ORBmatcher.h" // the reference's include/ORBmatcher.h (stubs resolve MapPoint.h/KeyFrame.h/Frame.h)
+
+#include "Thirdparty/DBoW2/DBoW2/FORB.h"
+// The fork added `std::vector<std::pair<TDescriptor, F>> vocabulary;` (TemplatedVocabulary.h:435)
+// with F = FORB abstract, which does not compile as shipped.  Giving that one pair type an
+// (empty) explicit specialisation lets the header compile unmodified; the member is unused.
+namespace std
+{
+    template <>
+    struct pair<cv::Mat, DBoW2::FORB>
+    {
+    };
+}
+#include "Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h"
+#include "Thirdparty/DBoW2/DUtils/Random.h"
+
+using namespace ORB_SLAM3;
+
+namespace
+{
+    struct TaggedMapPoint : public MapPoint
+    {
+        int tag = -1;
+    };
+
+    void fill_feature_set(FeatureSet &s, const orbgpu_frame_host *h)
+    {
+        s.N = h->n;
+        s.mvKeysUn.resize(h->n);
+        for (int i = 0; i < h->n; i++)
+        {
+            cv::KeyPoint kp;
+            kp.pt.x = h->kp_xy[2 * i];
+            kp.pt.y = h->kp_xy[2 * i + 1];
+            kp.octave = h->octave[i];
+            kp.angle = h->angle[i];
+            s.mvKeysUn[i] = kp;
+        }
+        s.mvKeys = s.mvKeysUn;
+        s.mvuRight.assign(h->n, -1.f);
+        if (h->u_right)
+            for (int i = 0; i < h->n; i++) s.mvuRight[i] = h->u_right[i];
+        s.mDescriptors.create(h->n > 0 ? h->n : 1, 32, CV_8U);
+        if (h->n > 0) std::memcpy(s.mDescriptors.data, h->desc, (size_t)h->n * 32);
+        s.mnScaleLevels = h->n_levels;
+        s.mvScaleFactors.assign(h->scale_factors, h->scale_factors + h->n_levels);
+        s.mvLevelSigma2.assign(h->level_sigma2, h->level_sigma2 + h->n_levels);
+        s.mvInvLevelSigma2.resize(h->n_levels);
+        for (int i = 0; i < h->n_levels; i++) s.mvInvLevelSigma2[i] = 1.0f / s.mvLevelSigma2[i];
+        s.mfLogScaleFactor = h->n_levels > 1 ? std::log(h->scale_factors[1]) : 1.f;
+        s.mfGridElementWidthInv = h->grid_inv_w;
+        s.mfGridElementHeightInv = h->grid_inv_h;
+        s.mvpMapPoints.assign(h->n, nullptr);
+        s.AssignFeaturesToGrid(h->min_x, h->min_y);
+        s.mFeatVec.clear();
+        for (int a = 0; a < h->fv_n_nodes; a++)
+            for (int j = h->fv_offsets[a]; j < h->fv_offsets[a + 1]; j++)
+                s.mFeatVec.addFeature(h->fv_node_ids[a], h->fv_features[j]);
+    }
+    void fill_frame(Frame &F, const orbgpu_frame_host *h)
+    {
+        fill_feature_set(F, h);
+        F.mnMinX = h->min_x; F.mnMinY = h->min_y; F.mnMaxX = h->max_x; F.mnMaxY = h->max_y;
+        F.mvbOutlier.assign(h->n, false);
+    }
+    void fill_keyframe(KeyFrame &K, const orbgpu_frame_host *h)
+    {
+        fill_feature_set(K, h);
+        K.mnMinX = (int)h->min_x; K.mnMinY = (int)h->min_y; K.mnMaxX = (int)h->max_x; K.mnMaxY = (int)h->max_y;
+    }
+
+    struct ExposedMatcher : public ORBmatcher
+    {
+        ExposedMatcher() : ORBmatcher(0.6f, true) {}
+        void three(std::vector<int> *h, int L, int &a, int &b, int &c) { ComputeThreeMaxima(h, L, a, b, c); }
+    };
+
+    typedef DBoW2::TemplatedVocabulary<DBoW2::FORB::TDescriptor, DBoW2::FORB> RefVocBase;
+    struct RefVoc : public RefVocBase
+    {
+        RefVoc(int k, int L) : RefVocBase(k, L, DBoW2::TF_IDF, DBoW2::L1_NORM) {}
+        using RefVocBase::m_nodes;
+        using RefVocBase::m_words;
+        using RefVocBase::m_k;
+        using RefVocBase::m_L;
+        void descend(const cv::Mat &f, DBoW2::WordId &id, DBoW2::WordValue &w, DBoW2::NodeId *nid, int levelsup) const
+        {
+            RefVocBase::transform(f, id, w, nid, levelsup);
+        }
+    };
+} // namespace
+
+extern "C"
+{
+    int ref_descriptor_distance(const uint8_t *a, const uint8_t *b)
+    {
+        cv::Mat ma(1, 32, CV_8U, (void *)a), mb(1, 32, CV_8U, (void *)b);
+        return ORBmatcher::DescriptorDistance(ma, mb);
+    }
+
+    void ref_compute_three_maxima(const int32_t *histo_sizes, int L, int32_t *ind)
+    {
+        std::vector<std::vector<int>> h(L);
+        for (int i = 0; i < L; i++) h[i].assign(histo_sizes[i], 0);
+        ExposedMatcher m;
+        int a = -1, b = -1, c = -1;
+        m.three(h.data(), L, a, b, c);
+        ind[0] = a; ind[1] = b; ind[2] = c;
+    }
+
+    // Frame::GetFeaturesInArea as restated in the stub (a second, independent restatement)
+    int ref_features_in_area(const orbgpu_frame_host *f, float x, float y, float r, int min_level, int max_level,
+                             int32_t *out_idx)
+    {
+        Frame F;
+        fill_frame(F, f);
+        std::vector<size_t> v = F.GetFeaturesInArea(x, y, r, min_level, max_level);
+        for (size_t i = 0; i < v.size(); i++) out_idx[i] = (int32_t)v[i];
+        return (int)v.size();
+    }
+
+    void ref_grid(const orbgpu_frame_host *f, int32_t *cell_start, int32_t *cell_items)
+    {
+        Frame F;
+        fill_frame(F, f);
+        int acc = 0;
+        for (int ix = 0; ix < FRAME_GRID_COLS; ix++)
+            for (int iy = 0; iy < FRAME_GRID_ROWS; iy++)
+            {
+                cell_start[ix * FRAME_GRID_ROWS + iy] = acc;
+                for (size_t j = 0; j < F.mGrid[ix][iy].size(); j++) cell_items[acc++] = (int32_t)F.mGrid[ix][iy][j];
+            }
+        cell_start[FRAME_GRID_COLS * FRAME_GRID_ROWS] = acc;
+    }
+
+    int ref_search_for_initialization(const orbgpu_frame_host *f1, const orbgpu_frame_host *f2, float *prev_matched_xy,
+                                      int window_size, float nnratio, int check_ori, int32_t *matches12)
+    {
+        Frame F1, F2;
+        fill_frame(F1, f1);
+        fill_frame(F2, f2);
+        std::vector<cv::Point2f> prev(f1->n);
+        for (int i = 0; i < f1->n; i++) prev[i] = cv::Point2f(prev_matched_xy[2 * i], prev_matched_xy[2 * i + 1]);
+        std::vector<int> m12;
+        ORBmatcher matcher(nnratio, check_ori != 0);
+        const int n = matcher.SearchForInitialization(F1, F2, prev, m12, window_size);
+        for (int i = 0; i < f1->n; i++)
+        {
+            matches12[i] = m12[i];
+            prev_matched_xy[2 * i] = prev[i].x;
+            prev_matched_xy[2 * i + 1] = prev[i].y;
+        }
+        return n;
+    }
+
+    int ref_search_by_projection_local(const orbgpu_frame_host *f, const orbgpu_mappoints_host *mps, float th,
+                                       int far_points, float th_far_points, float nnratio, const int32_t *kp_prior_obs,
+                                       int32_t *kp_mp)
+    {
+        Frame F;
+        fill_frame(F, f);
+        std::vector<TaggedMapPoint> pts(mps->n);
+        std::vector<MapPoint *> vp(mps->n);
+        for (int i = 0; i < mps->n; i++)
+        {
+            TaggedMapPoint &p = pts[i];
+            p.tag = i;
+            p.descriptor_.create(1, 32, CV_8U);
+            std::memcpy(p.descriptor_.data, mps->desc + 32 * (size_t)i, 32);
+            p.mTrackProjX = mps->proj_xy[2 * i];
+            p.mTrackProjY = mps->proj_xy[2 * i + 1];
+            p.mTrackProjXR = mps->proj_xr ? mps->proj_xr[i] : 0.f;
+            p.mnTrackScaleLevel = mps->scale_level[i];
+            p.mTrackViewCos = mps->view_cos[i];
+            p.mTrackDepth = mps->depth[i];
+            p.mbTrackInView = mps->in_view[i] != 0;
+            p.mbTrackInViewR = false;
+            p.bad_ = mps->bad[i] != 0;
+            p.nObs_ = mps->n_obs[i];
+            vp[i] = &p;
+        }
+        // map points the frame already holds on entry (not part of vpMapPoints)
+        std::vector<TaggedMapPoint> prior(f->n);
+        for (int i = 0; i < f->n; i++)
+        {
+            prior[i].tag = -2 - i;
+            prior[i].nObs_ = kp_prior_obs[i];
+            if (kp_mp[i] >= 0 || kp_prior_obs[i] > 0) F.mvpMapPoints[i] = &prior[i];
+        }
+        ORBmatcher matcher(nnratio, true);
+        const int n = matcher.SearchByProjection(F, vp, th, far_points != 0, th_far_points);
+        for (int i = 0; i < f->n; i++)
+        {
+            MapPoint *p = F.mvpMapPoints[i];
+            if (!p) kp_mp[i] = -1;
+            else
+            {
+                const int tag = static_cast<TaggedMapPoint *>(p)->tag;
+                if (tag >= 0) kp_mp[i] = tag; /* else: keeps the caller's prior value */
+            }
+        }
+        return n;
+    }
+
+    int ref_search_by_bow_kf_f(const orbgpu_frame_host *kf, const orbgpu_frame_host *f, const uint8_t *kf_mp_valid,
+                               float nnratio, int check_ori, int32_t *match_f2kf)
+    {
+        KeyFrame K;
+        Frame F;
+        fill_keyframe(K, kf);
+        fill_frame(F, f);
+        std::vector<TaggedMapPoint> pts(kf->n);
+        for (int i = 0; i < kf->n; i++)
+        {
+            pts[i].tag = i;
+            if (kf_mp_valid[i]) K.mvpMapPoints[i] = &pts[i];
+        }
+        std::vector<MapPoint *> out;
+        ORBmatcher matcher(nnratio, check_ori != 0);
+        const int n = matcher.SearchByBoW(&K, F, out);
+        for (int i = 0; i < f->n; i++) match_f2kf[i] = out[i] ? static_cast<TaggedMapPoint *>(out[i])->tag : -1;
+        return n;
+    }
+
+    int ref_search_by_bow_kf_kf(const orbgpu_frame_host *kf1, const orbgpu_frame_host *kf2, const uint8_t *kf1_mp_valid,
+                                const uint8_t *kf2_mp_valid, float nnratio, int check_ori, int32_t *match_12)
+    {
+        KeyFrame K1, K2;
+        fill_keyframe(K1, kf1);
+        fill_keyframe(K2, kf2);
+        std::vector<TaggedMapPoint> p1(kf1->n), p2(kf2->n);
+        for (int i = 0; i < kf1->n; i++)
+        {
+            p1[i].tag = i;
+            if (kf1_mp_valid[i]) K1.mvpMapPoints[i] = &p1[i];
+        }
+        for (int i = 0; i < kf2->n; i++)
+        {
+            p2[i].tag = i;
+            if (kf2_mp_valid[i]) K2.mvpMapPoints[i] = &p2[i];
+        }
+        std::vector<MapPoint *> out;
+        ORBmatcher matcher(nnratio, check_ori != 0);
+        const int n = matcher.SearchByBoW(&K1, &K2, out);
+        for (int i = 0; i < kf1->n; i++) match_12[i] = out[i] ? static_cast<TaggedMapPoint *>(out[i])->tag : -1;
+        return n;
+    }
+
+    // ---- triangulation ------------------------------------------------------------------
+    static void pose_from_flat(const float *T, Sophus::SE3f &out)
+    { // T = [R row-major (9) | t (3)]
+        Eigen::Matrix3f R;
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) R(r, c) = T[3 * r + c];
+        out = Sophus::SE3f(R, Eigen::Vector3f(T[9], T[10], T[11]));
+    }
+
+    // The host-side pose algebra exactly as ORBmatcher.cc:1053-1071 + Pinhole.cpp:194-197 run it
+    // in this build: ep (epipole of camera 1 in image 2) and F12 (row-major).  Its outputs are the
+    // inputs of both orbgpu_search_for_triangulation_batch and oracle_search_for_triangulation.
+    void ref_triangulation_geometry(const float *T1w, const float *T2w, const float *K1, const float *K2, float *ep,
+                                    float *f12)
+    {
+        KeyFrame A, B;
+        pose_from_flat(T1w, A.mTcw);
+        pose_from_flat(T2w, B.mTcw);
+        Pinhole c1(K1[0], K1[1], K1[2], K1[3]), c2(K2[0], K2[1], K2[2], K2[3]);
+        Sophus::SE3f T1 = A.GetPose();
+        Sophus::SE3f T2 = B.GetPose();
+        Sophus::SE3f Tw2 = B.GetPoseInverse();
+        Eigen::Vector3f Cw = A.GetCameraCenter();
+        Eigen::Vector3f C2 = T2 * Cw;
+        Eigen::Vector2f e = c2.project(C2);
+        Sophus::SE3f T12 = T1 * Tw2;
+        Eigen::Matrix3f R12 = T12.rotationMatrix();
+        Eigen::Vector3f t12 = T12.translation();
+        Eigen::Matrix3f F = c1.fundamental(&c2, R12, t12);
+        ep[0] = e(0); ep[1] = e(1);
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) f12[3 * r + c] = F(r, c);
+    }
+
+    static void fill_kf_from_set(KeyFrame &K, const orbgpu_kfset_host *s, int kf, std::vector<TaggedMapPoint> &pts)
+    {
+        const int n = s->n_feat;
+        K.N = n;
+        K.mvKeysUn.resize(n);
+        const float *xy = s->kp_xy + (size_t)kf * n * 2;
+        for (int i = 0; i < n; i++)
+        {
+            cv::KeyPoint kp;
+            kp.pt.x = xy[2 * i]; kp.pt.y = xy[2 * i + 1];
+            kp.octave = s->octave[(size_t)kf * n + i];
+            kp.angle = s->angle[(size_t)kf * n + i];
+            K.mvKeysUn[i] = kp;
+        }
+        K.mvKeys = K.mvKeysUn;
+        K.mvuRight.assign(n, -1.f);
+        if (s->u_right)
+            for (int i = 0; i < n; i++) K.mvuRight[i] = s->u_right[(size_t)kf * n + i];
+        K.mDescriptors = cv::Mat(n, 32, CV_8U, (void *)(s->desc + (size_t)kf * n * 32));
+        K.mnScaleLevels = s->n_levels;
+        K.mvScaleFactors.assign(s->scale_factors, s->scale_factors + s->n_levels);
+        K.mvLevelSigma2.assign(s->level_sigma2, s->level_sigma2 + s->n_levels);
+        pts.resize(n);
+        K.mvpMapPoints.assign(n, nullptr);
+        for (int i = 0; i < n; i++)
+            if (s->has_mp[(size_t)kf * n + i]) K.mvpMapPoints[i] = &pts[i];
+        K.mFeatVec.clear();
+        for (int i = 0; i < n; i++)
+        {
+            const uint32_t nid = s->node_id[(size_t)kf * n + i];
+            if (nid != 0xFFFFFFFFu) K.mFeatVec.addFeature(nid, (unsigned)i);
+        }
+    }
+
+    int ref_search_for_triangulation(const orbgpu_kfset_host *s, int kf1, int kf2, const float *T1w, const float *T2w,
+                                     const float *K1, const float *K2, int only_stereo, int coarse, int check_ori,
+                                     float nnratio, int32_t *matches12)
+    {
+        KeyFrame A, B;
+        std::vector<TaggedMapPoint> pa, pb;
+        fill_kf_from_set(A, s, kf1, pa);
+        fill_kf_from_set(B, s, kf2, pb);
+        pose_from_flat(T1w, A.mTcw);
+        pose_from_flat(T2w, B.mTcw);
+        Pinhole c1(K1[0], K1[1], K1[2], K1[3]), c2(K2[0], K2[1], K2[2], K2[3]);
+        A.mpCamera = &c1;
+        B.mpCamera = &c2;
+        std::vector<std::pair<size_t, size_t>> pairs;
+        ORBmatcher matcher(nnratio, check_ori != 0);
+        const int n = matcher.SearchForTriangulation(&A, &B, pairs, only_stereo != 0, coarse != 0);
+        for (int i = 0; i < s->n_feat; i++) matches12[i] = -1;
+        for (size_t i = 0; i < pairs.size(); i++) matches12[pairs[i].first] = (int32_t)pairs[i].second;
+        return n;
+    }
+
+    // all pairs across n_threads host threads (the reference itself is single-threaded per call;
+    // LocalMapping.cc:556-630 runs one call per neighbour keyframe)
+    void ref_search_for_triangulation_batch(const orbgpu_kfset_host *s, int n_pairs, const int32_t *kf1, const int32_t *kf2,
+                                            const float *T1w, const float *T2w, const float *K, int only_stereo, int coarse,
+                                            int check_ori, float nnratio, int32_t *matches12, int32_t *nmatches,
+                                            int n_threads)
+    {
+        if (n_threads < 1) n_threads = 1;
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; t++)
+            th.emplace_back([=]() {
+                const int p0 = (int)((int64_t)n_pairs * t / n_threads), p1 = (int)((int64_t)n_pairs * (t + 1) / n_threads);
+                for (int p = p0; p < p1; p++)
+                    nmatches[p] = ref_search_for_triangulation(s, kf1[p], kf2[p], T1w + 12 * (size_t)p, T2w + 12 * (size_t)p, K,
+                                                               K, only_stereo, coarse, check_ori, nnratio,
+                                                               matches12 + (size_t)p * s->n_feat);
+            });
+        for (auto &x : th) x.join();
+    }
+
+    // brute-force 2-NN + ratio over the reference's DescriptorDistance (the function itself is
+    // "defined by this repo": SearchByNN does not exist in this fork)
+    void ref_knn2_ratio(int64_t nq, const uint8_t *q, int64_t nd, const uint8_t *db, int th_low, float nnratio,
+                        int32_t *best_idx, int32_t *best_dist, int32_t *second_dist, int32_t *match, int n_threads)
+    {
+        if (n_threads < 1) n_threads = 1;
+        cv::Mat Q((int)nq, 32, CV_8U, (void *)q), D((int)nd, 32, CV_8U, (void *)db);
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; t++)
+            th.emplace_back([&, t]() {
+                const int64_t q0 = nq * t / n_threads, q1 = nq * (t + 1) / n_threads;
+                for (int64_t i = q0; i < q1; i++)
+                {
+                    const cv::Mat &dq = Q.row((int)i);
+                    int bestDist1 = 256, bestIdx = -1, bestDist2 = 256;
+                    for (int64_t d = 0; d < nd; d++)
+                    {
+                        const cv::Mat &dd = D.row((int)d);
+                        const int dist = ORBmatcher::DescriptorDistance(dq, dd);
+                        if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx = (int)d; }
+                        else if (dist < bestDist2) { bestDist2 = dist; }
+                    }
+                    int m = -1;
+                    if (bestDist1 <= th_low)
+                        if (static_cast<float>(bestDist1) < nnratio * static_cast<float>(bestDist2)) m = bestIdx;
+                    if (best_idx) best_idx[i] = bestIdx;
+                    if (best_dist) best_dist[i] = bestDist1;
+                    if (second_dist) second_dist[i] = bestDist2;
+                    if (match) match[i] = m;
+                }
+            });
+        for (auto &x : th) x.join();
+    }
+
+    // ---- vocabulary -----------------------------------------------------------------------
+    void *ref_voc_create(int k, int L, int n_images, int n_per_image, const uint8_t *desc, int seed)
+    {
+        DUtils::Random::SeedRandOnce(seed);
+        DUtils::Random::SeedRand(seed);
+        std::vector<std::vector<cv::Mat>> training(n_images);
+        for (int im = 0; im < n_images; im++)
+        {
+            training[im].resize(n_per_image);
+            for (int j = 0; j < n_per_image; j++)
+            {
+                cv::Mat m(1, 32, CV_8U);
+                std::memcpy(m.data, desc + ((size_t)im * n_per_image + j) * 32, 32);
+                training[im][j] = m;
+            }
+        }
+        RefVoc *v = new RefVoc(k, L);
+        v->create(training, k, L);
+        return v;
+    }
+
+    void *ref_voc_from_flat(const orbgpu_voc_host *h)
+    {
+        RefVoc *v = new RefVoc(h->k, h->L);
+        v->m_nodes.clear();
+        v->m_nodes.resize(h->n_nodes);
+        size_t n_words = 0;
+        for (int i = 0; i < h->n_nodes; i++)
+        {
+            auto &nd = v->m_nodes[i];
+            nd.id = i;
+            nd.weight = h->weight[i];
+            nd.word_id = h->word_id[i];
+            nd.descriptor.create(1, 32, CV_8U);
+            std::memcpy(nd.descriptor.data, h->node_desc + 32 * (size_t)i, 32);
+            for (int c = h->child_offsets[i]; c < h->child_offsets[i + 1]; c++)
+            {
+                nd.children.push_back(h->child_ids[c]);
+                v->m_nodes[h->child_ids[c]].parent = i;
+            }
+            if (i > 0 && nd.children.empty()) n_words = std::max(n_words, (size_t)h->word_id[i] + 1);
+        }
+        v->m_words.assign(n_words, nullptr);
+        for (int i = 1; i < h->n_nodes; i++)
+            if (v->m_nodes[i].children.empty()) v->m_words[h->word_id[i]] = &v->m_nodes[i];
+        return v;
+    }
+
+    void ref_voc_destroy(void *p) { delete static_cast<RefVoc *>(p); }
+    int ref_voc_n_nodes(void *p) { return (int)static_cast<RefVoc *>(p)->m_nodes.size(); }
+    int ref_voc_n_children(void *p)
+    {
+        size_t n = 0;
+        for (auto &nd : static_cast<RefVoc *>(p)->m_nodes) n += nd.children.size();
+        return (int)n;
+    }
+    int ref_voc_n_words(void *p) { return (int)static_cast<RefVoc *>(p)->m_words.size(); }
+    // export into caller-allocated flat arrays (layout of orbgpu_voc_host)
+    void ref_voc_export(void *p, uint8_t *node_desc, int32_t *child_offsets, uint32_t *child_ids, double *weight,
+                        uint32_t *word_id)
+    {
+        RefVoc *v = static_cast<RefVoc *>(p);
+        int acc = 0;
+        for (size_t i = 0; i < v->m_nodes.size(); i++)
+        {
+            auto &nd = v->m_nodes[i];
+            child_offsets[i] = acc;
+            for (auto c : nd.children) child_ids[acc++] = c;
+            weight[i] = nd.weight;
+            word_id[i] = nd.word_id;
+            if (!nd.descriptor.empty()) std::memcpy(node_desc + 32 * i, nd.descriptor.data, 32);
+            else std::memset(node_desc + 32 * i, 0, 32);
+        }
+        child_offsets[v->m_nodes.size()] = acc;
+    }
+
+    // TemplatedVocabulary::transform(features, BowVector&, FeatureVector&, levelsup) -- the batch
+    // call Frame::ComputeBoW makes (Frame.cc:1005-1008) -- plus the per-feature descent outputs.
+    // Returns n_words; bow arrays capacity n, featvec capacities n / n+1 / n.
+    int ref_voc_transform(void *p, int n, const uint8_t *desc, int levelsup, uint32_t *word_id, uint32_t *node_id,
+                          double *weight, uint32_t *bow_words, double *bow_values, int32_t *fv_n_nodes,
+                          uint32_t *fv_node_ids, int32_t *fv_offsets, uint32_t *fv_features)
+    {
+        RefVoc *v = static_cast<RefVoc *>(p);
+        std::vector<cv::Mat> feats(n);
+        for (int i = 0; i < n; i++) feats[i] = cv::Mat(1, 32, CV_8U, (void *)(desc + 32 * (size_t)i));
+        for (int i = 0; i < n; i++)
+        {
+            DBoW2::WordId id = 0;
+            DBoW2::WordValue w = 0;
+            DBoW2::NodeId nid = 0;
+            v->descend(feats[i], id, w, &nid, levelsup);
+            if (word_id) word_id[i] = id;
+            if (node_id) node_id[i] = nid;
+            if (weight) weight[i] = w;
+        }
+        DBoW2::BowVector bv;
+        DBoW2::FeatureVector fv;
+        v->transform(feats, bv, fv, levelsup);
+        int nw = 0;
+        for (auto &kv : bv)
+        {
+            if (bow_words) bow_words[nw] = kv.first;
+            if (bow_values) bow_values[nw] = kv.second;
+            nw++;
+        }
+        int nn = 0, acc = 0;
+        for (auto &kv : fv)
+        {
+            if (fv_node_ids) fv_node_ids[nn] = kv.first;
+            if (fv_offsets) fv_offsets[nn] = acc;
+            for (auto f : kv.second)
+            {
+                if (fv_features) fv_features[acc] = f;
+                acc++;
+            }
+            nn++;
+        }
+        if (fv_offsets) fv_offsets[nn] = acc;
+        if (fv_n_nodes) *fv_n_nodes = nn;
+        return nw;
+    }
+}
