@@ -1,0 +1,318 @@
+// voc.cu -- DBoW2 vocabulary descent on the device.
+//
+// Replaces TemplatedVocabulary::transform (TemplatedVocabulary.h:1127-1194 batch, :1216-1258 per
+// feature descent with FORB::distance, FORB.cpp:92-112), BowVector::addWeight/normalize
+// (BowVector.cpp:35-85) and FeatureVector::addFeature (FeatureVector.cpp:32-46).
+//
+//   voc_transform_kernel  one warp per feature; lanes over the children of the current node; the
+//                         child with the lexicographically smallest (distance, child position) wins,
+//                         i.e. strict '<' / first child on ties (:1237-1248).
+//   featvec_build_kernel  one block per frame: bitonic sort of (node id, feature id) keys -> CSR with
+//                         ascending node ids and ascending feature ids inside a node (the iteration
+//                         order of the std::map<NodeId, vector<uint>> the reference walks).
+//   bow_build_kernel      same sort on (word id, feature id); weight of a word = idf added `count`
+//                         times in feature order (repeated double +=, not count*idf), then divided by
+//                         the L1 norm accumulated in ascending word-id order.
+#include <algorithm>
+#include <cstring>
+
+#include "internal.cuh"
+
+namespace {
+
+constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
+constexpr int SORT_THREADS = 1024;
+
+__global__ void voc_transform_kernel(int n, const uint4 *__restrict__ desc, const uint4 *__restrict__ node_desc,
+                                     const int32_t *__restrict__ child_offsets, const uint32_t *__restrict__ child_ids,
+                                     const double *__restrict__ node_weight, const uint32_t *__restrict__ node_word, int L,
+                                     int levelsup, uint32_t *__restrict__ word_id, uint32_t *__restrict__ node_id,
+                                     double *__restrict__ weight, unsigned long long *__restrict__ counters)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const int lane = lane_id();
+    const uint4 fa = desc[2 * i], fb = desc[2 * i + 1];
+    const int nid_level = L - levelsup; // :1223
+    uint32_t nid = 0;                   // root when nid_level <= 0 (:1224-1225)
+    uint32_t final_id = 0;
+    int level = 0, ncmp = 0;
+    int c0 = child_offsets[0], c1 = child_offsets[1];
+    while (c1 > c0) { // do { ... } while (!isLeaf) -- the root of a non-empty vocabulary has children
+        ++level;
+        uint32_t best = KEY_NONE;
+        for (int c = c0 + lane; c < c1; c += 32) {
+            const uint32_t id = child_ids[c];
+            const uint32_t d = (uint32_t)ham256(fa, fb, node_desc[2 * id], node_desc[2 * id + 1]);
+            best = min(best, (d << 20) | (uint32_t)(c - c0));
+        }
+        best = __reduce_min_sync(FULL_MASK, best);
+        final_id = child_ids[c0 + (best & 0xFFFFF)];
+        ncmp += c1 - c0;
+        if (level == nid_level) nid = final_id; // :1250-1251
+        c0 = child_offsets[final_id];
+        c1 = child_offsets[final_id + 1];
+    }
+    if (lane == 0) {
+        word_id[i] = node_word[final_id];
+        weight[i] = node_weight[final_id];
+        node_id[i] = nid;
+        atomicAdd(&counters[0], (unsigned long long)ncmp);
+    }
+}
+
+// in-place ascending bitonic sort of `cap` (power of two) 64-bit keys by one block
+__device__ void block_bitonic_sort(unsigned long long *keys, int cap)
+{
+    for (int k = 2; k <= cap; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < cap; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = keys[i], b = keys[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) {
+                        keys[i] = b;
+                        keys[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// block-wide exclusive scan of one int per thread (blockDim.x == SORT_THREADS)
+__device__ int block_exclusive_scan(int v, int *warp_sums, int &total)
+{
+    const int t = threadIdx.x;
+    int incl = v;
+    for (int off = 1; off < 32; off <<= 1) {
+        const int u = __shfl_up_sync(FULL_MASK, incl, off);
+        if ((t & 31) >= off) incl += u;
+    }
+    if ((t & 31) == 31) warp_sums[t >> 5] = incl;
+    __syncthreads();
+    if (t < 32) {
+        int w = warp_sums[t];
+        for (int off = 1; off < 32; off <<= 1) {
+            const int u = __shfl_up_sync(FULL_MASK, w, off);
+            if (t >= off) w += u;
+        }
+        warp_sums[t] = w;
+    }
+    __syncthreads();
+    const int prefix = ((t >> 5) > 0 ? warp_sums[(t >> 5) - 1] : 0) + incl - v;
+    total = warp_sums[31];
+    __syncthreads();
+    return prefix;
+}
+
+// groups the sorted keys (high 32 bits = group id) into CSR: ids[], offsets[], and returns counts.
+// Each thread handles a contiguous run of `per` sorted positions.
+__device__ void csr_from_sorted(const unsigned long long *keys, int m, uint32_t *ids, int32_t *offsets, int *warp_sums,
+                                int &n_groups)
+{
+    const int t = threadIdx.x;
+    const int per = (m + SORT_THREADS - 1) / SORT_THREADS;
+    const int s = min(m, t * per), e = min(m, s + per);
+    int heads = 0;
+    for (int i = s; i < e; i++)
+        if (i == 0 || (uint32_t)(keys[i] >> 32) != (uint32_t)(keys[i - 1] >> 32)) heads++;
+    int total;
+    int g = block_exclusive_scan(heads, warp_sums, total);
+    for (int i = s; i < e; i++)
+        if (i == 0 || (uint32_t)(keys[i] >> 32) != (uint32_t)(keys[i - 1] >> 32)) {
+            ids[g] = (uint32_t)(keys[i] >> 32);
+            offsets[g] = i;
+            g++;
+        }
+    if (t == 0) offsets[total] = m;
+    n_groups = total;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+featvec_build_kernel(int n, int cap, const uint32_t *__restrict__ node_id, const double *__restrict__ weight,
+                     unsigned long long *__restrict__ keys, uint32_t *__restrict__ fv_node_ids, int32_t *__restrict__ fv_offsets,
+                     uint32_t *__restrict__ fv_features, int32_t *__restrict__ meta)
+{
+    __shared__ int warp_sums[32];
+    __shared__ int s_max;
+    const int t = threadIdx.x;
+    if (t == 0) s_max = 0;
+    int valid = 0;
+    for (int i = t; i < cap; i += SORT_THREADS) {
+        unsigned long long k = ~0ull;
+        if (i < n && weight[i] > 0.0) { // stopped words are dropped (:1157)
+            k = ((unsigned long long)node_id[i] << 32) | (unsigned)i;
+            valid++;
+        }
+        keys[i] = k;
+    }
+    __syncthreads();
+    int m;
+    block_exclusive_scan(valid, warp_sums, m);
+    block_bitonic_sort(keys, cap);
+    for (int i = t; i < m; i += SORT_THREADS) fv_features[i] = (uint32_t)(keys[i] & 0xFFFFFFFFull);
+    int n_nodes;
+    csr_from_sorted(keys, m, fv_node_ids, fv_offsets, warp_sums, n_nodes);
+    int mx = 0;
+    for (int g = t; g < n_nodes; g += SORT_THREADS) mx = max(mx, fv_offsets[g + 1] - fv_offsets[g]);
+    if (mx) atomicMax(&s_max, mx);
+    __syncthreads();
+    if (t == 0) {
+        meta[0] = n_nodes;
+        meta[1] = m;
+        meta[2] = s_max;
+    }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+bow_build_kernel(int n, int cap, const uint32_t *__restrict__ word_id, const double *__restrict__ weight,
+                 unsigned long long *__restrict__ keys, uint32_t *__restrict__ bow_words, int32_t *__restrict__ tmp_offsets,
+                 double *__restrict__ bow_values, int32_t *__restrict__ meta)
+{
+    __shared__ int warp_sums[32];
+    __shared__ double s_norm;
+    const int t = threadIdx.x;
+    int valid = 0;
+    for (int i = t; i < cap; i += SORT_THREADS) {
+        unsigned long long k = ~0ull;
+        if (i < n && weight[i] > 0.0) {
+            k = ((unsigned long long)word_id[i] << 32) | (unsigned)i;
+            valid++;
+        }
+        keys[i] = k;
+    }
+    __syncthreads();
+    int m;
+    block_exclusive_scan(valid, warp_sums, m);
+    block_bitonic_sort(keys, cap);
+    int n_words;
+    csr_from_sorted(keys, m, bow_words, tmp_offsets, warp_sums, n_words);
+    // BowVector::addWeight (BowVector.cpp:35-50): first insert, then += per further feature
+    for (int g = t; g < n_words; g += SORT_THREADS) {
+        const int s = tmp_offsets[g], e = tmp_offsets[g + 1];
+        double v = weight[(uint32_t)(keys[s] & 0xFFFFFFFFull)];
+        for (int i = s + 1; i < e; i++) v = __dadd_rn(v, weight[(uint32_t)(keys[i] & 0xFFFFFFFFull)]);
+        bow_values[g] = v;
+    }
+    __syncthreads();
+    // BowVector::normalize(L1) (BowVector.cpp:63-85): norm accumulated in ascending word id
+    if (t == 0) {
+        double norm = 0.0;
+        for (int g = 0; g < n_words; g++) norm = __dadd_rn(norm, fabs(bow_values[g]));
+        s_norm = norm;
+    }
+    __syncthreads();
+    if (s_norm > 0.0)
+        for (int g = t; g < n_words; g += SORT_THREADS) bow_values[g] = __ddiv_rn(bow_values[g], s_norm);
+    if (t == 0) meta[3] = n_words;
+}
+
+} // namespace
+
+extern "C" int orbgpu_voc_upload(orbgpu_ctx *ctx, const orbgpu_voc_host *h, orbgpu_voc **out)
+{
+    ARG_TRY(ctx && h && out);
+    ARG_TRY(h->n_nodes >= 1 && h->node_desc && h->child_offsets && h->child_ids && h->weight && h->word_id);
+    CU_TRY(cudaSetDevice(ctx->device));
+    const int nn = h->n_nodes;
+    const int nc = h->child_offsets[nn];
+    ARG_TRY(nc >= 0);
+    for (int i = 0; i < nn; i++) ARG_TRY(h->child_offsets[i + 1] >= h->child_offsets[i] && h->child_offsets[i + 1] - h->child_offsets[i] < (1 << 20));
+    for (int c = 0; c < nc; c++) ARG_TRY(h->child_ids[c] > 0 && h->child_ids[c] < (uint32_t)nn);
+    orbgpu_voc *v = new orbgpu_voc();
+    v->device = ctx->device;
+    v->k = h->k; v->L = h->L; v->n_nodes = nn;
+    CU_TRY(cudaMalloc(&v->node_desc, (size_t)nn * 32));
+    CU_TRY(cudaMalloc(&v->child_offsets, (size_t)(nn + 1) * 4));
+    CU_TRY(cudaMalloc(&v->child_ids, (size_t)std::max(nc, 1) * 4));
+    CU_TRY(cudaMalloc(&v->weight, (size_t)nn * 8));
+    CU_TRY(cudaMalloc(&v->word_id, (size_t)nn * 4));
+    CU_TRY(cudaMemcpyAsync(v->node_desc, h->node_desc, (size_t)nn * 32, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(v->child_offsets, h->child_offsets, (size_t)(nn + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (nc) CU_TRY(cudaMemcpyAsync(v->child_ids, h->child_ids, (size_t)nc * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(v->weight, h->weight, (size_t)nn * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(v->word_id, h->word_id, (size_t)nn * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    *out = v;
+    return ORBGPU_OK;
+}
+
+extern "C" void orbgpu_voc_destroy(orbgpu_voc *v)
+{
+    if (!v) return;
+    cudaSetDevice(v->device);
+    cudaFree(v->node_desc); cudaFree(v->child_offsets); cudaFree(v->child_ids); cudaFree(v->weight); cudaFree(v->word_id);
+    delete v;
+}
+
+extern "C" int orbgpu_transform(orbgpu_ctx *ctx, const orbgpu_voc *voc, orbgpu_frame *f, int32_t levelsup, int32_t store_featvec,
+                                uint32_t *word_id, uint32_t *node_id, double *weight)
+{
+    ARG_TRY(ctx && voc && f);
+    int rc = ctx_begin(ctx);
+    if (rc) return rc;
+    const int n = f->n;
+    if (n == 0) return ORBGPU_OK;
+    rc = arena_reserve(ctx, align256((size_t)(n + 1) * 4) + 256);
+    if (rc) return rc;
+    int32_t *tmp_off = (int32_t *)arena_take(ctx, (size_t)(n + 1) * 4);
+    voc_transform_kernel<<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>(n, f->desc, voc->node_desc, voc->child_offsets, voc->child_ids,
+                                                                       voc->weight, voc->word_id, voc->L, levelsup, f->word_id,
+                                                                       f->node_id, f->weight, ctx->d_counters);
+    LAUNCH_COUNT(ctx);
+    f->has_transform = true;
+    if (store_featvec) {
+        featvec_build_kernel<<<1, SORT_THREADS, 0, ctx->stream>>>(n, f->sort_cap, f->node_id, f->weight, f->sort_keys, f->fv_node_ids,
+                                                                 f->fv_offsets, f->fv_features, f->fv_meta);
+        bow_build_kernel<<<1, SORT_THREADS, 0, ctx->stream>>>(n, f->sort_cap, f->word_id, f->weight, f->sort_keys, f->bow_words, tmp_off,
+                                                             f->bow_values, f->fv_meta);
+        ctx->launches += 2;
+    }
+    CU_TRY(cudaGetLastError());
+    if (word_id) CU_TRY(cudaMemcpyAsync(word_id, f->word_id, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (node_id) CU_TRY(cudaMemcpyAsync(node_id, f->node_id, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (weight) CU_TRY(cudaMemcpyAsync(weight, f->weight, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    int32_t meta[4] = {0, 0, 0, 0};
+    if (store_featvec) CU_TRY(cudaMemcpyAsync(meta, f->fv_meta, sizeof(meta), cudaMemcpyDeviceToHost, ctx->stream));
+    rc = ctx_fetch_comparisons(ctx);
+    if (rc) return rc;
+    if (store_featvec) {
+        f->fv_n_nodes = meta[0];
+        f->fv_total = meta[1];
+        f->fv_max_node = meta[2];
+        f->bow_n = meta[3];
+    }
+    return ORBGPU_OK;
+}
+
+extern "C" int orbgpu_bowvector_download(orbgpu_ctx *ctx, const orbgpu_frame *f, int32_t *n_words, uint32_t *words, double *values)
+{
+    ARG_TRY(ctx && f && n_words);
+    CU_TRY(cudaSetDevice(ctx->device));
+    *n_words = f->bow_n;
+    if (f->bow_n > 0) {
+        if (words) CU_TRY(cudaMemcpyAsync(words, f->bow_words, (size_t)f->bow_n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (values) CU_TRY(cudaMemcpyAsync(values, f->bow_values, (size_t)f->bow_n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    return ORBGPU_OK;
+}
+
+extern "C" int orbgpu_featvec_download(orbgpu_ctx *ctx, const orbgpu_frame *f, int32_t *n_nodes, uint32_t *node_ids, int32_t *offsets,
+                                       uint32_t *features)
+{
+    ARG_TRY(ctx && f && n_nodes);
+    CU_TRY(cudaSetDevice(ctx->device));
+    *n_nodes = f->fv_n_nodes;
+    if (node_ids && f->fv_n_nodes > 0)
+        CU_TRY(cudaMemcpyAsync(node_ids, f->fv_node_ids, (size_t)f->fv_n_nodes * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (offsets) CU_TRY(cudaMemcpyAsync(offsets, f->fv_offsets, (size_t)(f->fv_n_nodes + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (features && f->fv_total > 0)
+        CU_TRY(cudaMemcpyAsync(features, f->fv_features, (size_t)f->fv_total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    return ORBGPU_OK;
+}

@@ -1,0 +1,402 @@
+"""Host-side mirror of the reference's matcher interface over the CUDA C-ABI library.
+
+`ORBmatcher(nnratio, checkOri)` keeps the reference's constructor and method names
+(include/ORBmatcher.h:37-84); methods take the flat host views of `_abi` (the members the
+reference reads) or device handles, and return the reference's outputs in index form
+(MapPoint* -> index, NULL -> -1).  Everything runs on the GPU through liborbmatch_b200.so:
+if the library or a B200 is missing this module raises -- there is NO CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+from ._abi import (FrameHostStruct, HostFrame, HostKfSet, HostMapPoints, HostVoc, KfSetHostStruct, MapPointsHostStruct,
+                   VocHostStruct, as_f32, as_i32, as_u8, f32p, f64p, i32p, i64p, u8p, u32p)
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liborbmatch_b200.so")
+_lib = None
+
+TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30  # ORBmatcher.cc:34-36
+
+
+class OrbGpuError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load_library():
+    """Loads the CUDA extension; raises when it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise OrbGpuError(f"{_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(or make -C orb_slam3_comments_ghr_b200/csrc). There is no CPU fallback.")
+    L = C.CDLL(_LIB_PATH)
+    vp = C.c_void_p
+    FH, MP, KS, VH = C.POINTER(FrameHostStruct), C.POINTER(MapPointsHostStruct), C.POINTER(KfSetHostStruct), C.POINTER(VocHostStruct)
+    L.orbgpu_last_error.restype = C.c_char_p
+    L.orbgpu_version.restype = C.c_char_p
+    L.orbgpu_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.orbgpu_create_on_stream.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    L.orbgpu_destroy.argtypes = [vp]
+    L.orbgpu_destroy.restype = None
+    L.orbgpu_synchronize.argtypes = [vp]
+    L.orbgpu_stream.argtypes = [vp]
+    L.orbgpu_stream.restype = vp
+    L.orbgpu_launch_count.argtypes = [vp]
+    L.orbgpu_launch_count.restype = C.c_int64
+    L.orbgpu_last_comparisons.argtypes = [vp]
+    L.orbgpu_last_comparisons.restype = C.c_int64
+    L.orbgpu_descriptor_distance.argtypes = [vp, C.c_int64, u8p, u8p, i32p]
+    L.orbgpu_frame_upload.argtypes = [vp, FH, C.POINTER(vp)]
+    L.orbgpu_frame_destroy.argtypes = [vp]
+    L.orbgpu_frame_destroy.restype = None
+    L.orbgpu_frame_n.argtypes = [vp]
+    L.orbgpu_frame_grid_download.argtypes = [vp, vp, i32p, i32p]
+    L.orbgpu_features_in_area.argtypes = [vp, vp, C.c_int32, f32p, f32p, f32p, i32p, i32p, i32p, i32p, C.c_int64, i64p]
+    L.orbgpu_search_for_initialization.argtypes = [vp, vp, vp, f32p, C.c_int32, C.c_float, C.c_int32, i32p, i32p]
+    L.orbgpu_search_by_projection_local.argtypes = [vp, vp, MP, C.c_float, C.c_int32, C.c_float, C.c_float, i32p, i32p, i32p]
+    L.orbgpu_voc_upload.argtypes = [vp, VH, C.POINTER(vp)]
+    L.orbgpu_voc_destroy.argtypes = [vp]
+    L.orbgpu_voc_destroy.restype = None
+    L.orbgpu_transform.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, u32p, u32p, f64p]
+    L.orbgpu_bowvector_download.argtypes = [vp, vp, i32p, u32p, f64p]
+    L.orbgpu_featvec_download.argtypes = [vp, vp, i32p, u32p, i32p, u32p]
+    L.orbgpu_search_by_bow_kf_f.argtypes = [vp, vp, vp, u8p, C.c_float, C.c_int32, i32p, i32p]
+    L.orbgpu_search_by_bow_kf_kf.argtypes = [vp, vp, vp, u8p, u8p, C.c_float, C.c_int32, i32p, i32p]
+    L.orbgpu_kfset_upload.argtypes = [vp, KS, C.POINTER(vp)]
+    L.orbgpu_kfset_destroy.argtypes = [vp]
+    L.orbgpu_kfset_destroy.restype = None
+    L.orbgpu_search_for_triangulation_batch.argtypes = [vp, vp, C.c_int32, i32p, i32p, f32p, f32p, C.c_int32, C.c_int32, C.c_int32,
+                                                        i32p, i32p]
+    L.orbgpu_search_for_triangulation_batch_dev.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp]
+    L.orbgpu_db_upload.argtypes = [vp, C.c_int64, u8p, C.POINTER(vp)]
+    L.orbgpu_db_from_dev.argtypes = [vp, C.c_int64, vp, C.POINTER(vp)]
+    L.orbgpu_db_destroy.argtypes = [vp]
+    L.orbgpu_db_destroy.restype = None
+    L.orbgpu_knn2_ratio.argtypes = [vp, vp, C.c_int64, u8p, C.c_int32, C.c_float, i32p, i32p, i32p, i32p]
+    L.orbgpu_knn2_ratio_dev.argtypes = [vp, vp, C.c_int64, vp, C.c_int32, C.c_float, vp, vp, vp, vp]
+    L.orbgpu_knn2_set_engine.argtypes = [vp, C.c_int32]
+    L.orbgpu_compute_three_maxima.argtypes = [vp, i32p, C.c_int32, i32p]
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise OrbGpuError(f"orbgpu error {rc}: {load_library().orbgpu_last_error().decode()}")
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t) if a is not None else C.cast(None, t)
+
+
+class Context:
+    """One CUDA stream + workspace (orbgpu_ctx).  Use one per calling thread."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        L = load_library()
+        self._h = C.c_void_p()
+        if stream is None:
+            _check(L.orbgpu_create(int(device), C.byref(self._h)))
+        else:
+            _check(L.orbgpu_create_on_stream(int(device), C.c_void_p(stream), C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            load_library().orbgpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def synchronize(self):
+        _check(load_library().orbgpu_synchronize(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(load_library().orbgpu_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(load_library().orbgpu_launch_count(self._h))
+
+    @property
+    def last_comparisons(self) -> int:
+        return int(load_library().orbgpu_last_comparisons(self._h))
+
+    def set_knn_engine(self, engine: int):
+        _check(load_library().orbgpu_knn2_set_engine(self._h, int(engine)))
+
+    # ---- a1
+    def descriptor_distance(self, a, b) -> np.ndarray:
+        a, b = as_u8(a).reshape(-1, 32), as_u8(b).reshape(-1, 32)
+        out = np.empty(a.shape[0], dtype=np.int32)
+        _check(load_library().orbgpu_descriptor_distance(self._h, a.shape[0], _p(a, u8p), _p(b, u8p), _p(out, i32p)))
+        return out
+
+    def compute_three_maxima(self, sizes) -> np.ndarray:
+        sizes = as_i32(sizes)
+        ind = np.zeros(3, dtype=np.int32)
+        _check(load_library().orbgpu_compute_three_maxima(self._h, _p(sizes, i32p), int(sizes.shape[0]), _p(ind, i32p)))
+        return ind
+
+    # ---- uploads
+    def upload_frame(self, f: HostFrame) -> "DeviceFrame":
+        return DeviceFrame(self, f)
+
+    def upload_vocabulary(self, v: HostVoc) -> "DeviceVoc":
+        return DeviceVoc(self, v)
+
+    def upload_kfset(self, s: HostKfSet) -> "DeviceKfSet":
+        return DeviceKfSet(self, s)
+
+    def upload_database(self, db) -> "DeviceDb":
+        return DeviceDb(self, host=db)
+
+    def database_from_device(self, ptr: int, nd: int, keepalive=None) -> "DeviceDb":
+        return DeviceDb(self, dev_ptr=ptr, nd=nd, keepalive=keepalive)
+
+
+class DeviceFrame:
+    """Device copy of a Frame/KeyFrame (descriptors as uint4 pairs + CSR cell grid)."""
+
+    def __init__(self, ctx: Context, f: HostFrame):
+        self.ctx, self.host = ctx, f
+        self._h = C.c_void_p()
+        s = f.struct()
+        _check(load_library().orbgpu_frame_upload(ctx.handle, C.byref(s), C.byref(self._h)))
+        self.n = f.n
+
+    def __del__(self):
+        try:
+            if self._h:
+                load_library().orbgpu_frame_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def grid(self):
+        cs = np.zeros(self.host.grid_cols * self.host.grid_rows + 1, dtype=np.int32)
+        ci = np.full(max(self.n, 1), -1, dtype=np.int32)
+        _check(load_library().orbgpu_frame_grid_download(self.ctx.handle, self._h, _p(cs, i32p), _p(ci, i32p)))
+        return cs, ci
+
+    def features_in_area(self, x, y, r, min_level, max_level):
+        """batched Frame::GetFeaturesInArea -> (offsets[nq+1], idx[total]) in reference order"""
+        x, y, r = as_f32(np.atleast_1d(x)), as_f32(np.atleast_1d(y)), as_f32(np.atleast_1d(r))
+        nq = x.shape[0]
+        mn = as_i32(np.broadcast_to(np.asarray(min_level), (nq,)))
+        mx = as_i32(np.broadcast_to(np.asarray(max_level), (nq,)))
+        cap = max(1, nq * max(self.n, 1))
+        off = np.zeros(nq + 1, dtype=np.int32)
+        idx = np.empty(cap, dtype=np.int32)
+        total = C.c_int64(0)
+        _check(load_library().orbgpu_features_in_area(self.ctx.handle, self._h, nq, _p(x, f32p), _p(y, f32p), _p(r, f32p), _p(mn, i32p),
+                                                      _p(mx, i32p), _p(off, i32p), _p(idx, i32p), cap, C.byref(total)))
+        return off, idx[:total.value].copy()
+
+    def transform(self, voc: "DeviceVoc", levelsup: int = 4, store_featvec: bool = True):
+        """TemplatedVocabulary::transform on the device -> (word_id, node_id, weight) per feature"""
+        n = self.n
+        w = np.empty(n, dtype=np.uint32)
+        nid = np.empty(n, dtype=np.uint32)
+        wt = np.empty(n, dtype=np.float64)
+        _check(load_library().orbgpu_transform(self.ctx.handle, voc.handle, self._h, int(levelsup), int(store_featvec), _p(w, u32p),
+                                               _p(nid, u32p), _p(wt, f64p)))
+        return w, nid, wt
+
+    def bowvector(self):
+        n = max(self.n, 1)
+        words = np.empty(n, dtype=np.uint32)
+        vals = np.empty(n, dtype=np.float64)
+        m = C.c_int32(0)
+        _check(load_library().orbgpu_bowvector_download(self.ctx.handle, self._h, C.byref(m), _p(words, u32p), _p(vals, f64p)))
+        return words[:m.value].copy(), vals[:m.value].copy()
+
+    def featvec(self):
+        n = max(self.n, 1)
+        nodes = np.empty(n, dtype=np.uint32)
+        offs = np.empty(n + 1, dtype=np.int32)
+        feats = np.empty(n, dtype=np.uint32)
+        m = C.c_int32(0)
+        _check(load_library().orbgpu_featvec_download(self.ctx.handle, self._h, C.byref(m), _p(nodes, u32p), _p(offs, i32p),
+                                                      _p(feats, u32p)))
+        k = m.value
+        return nodes[:k].copy(), offs[:k + 1].copy(), feats[:offs[k] if k > 0 else 0].copy()
+
+
+class DeviceVoc:
+    def __init__(self, ctx: Context, v: HostVoc):
+        self.ctx, self.host = ctx, v
+        self._h = C.c_void_p()
+        s = v.struct()
+        _check(load_library().orbgpu_voc_upload(ctx.handle, C.byref(s), C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                load_library().orbgpu_voc_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+
+class DeviceKfSet:
+    def __init__(self, ctx: Context, s: HostKfSet):
+        self.ctx, self.host = ctx, s
+        self._h = C.c_void_p()
+        st = s.struct()
+        _check(load_library().orbgpu_kfset_upload(ctx.handle, C.byref(st), C.byref(self._h)))
+        self.n_kf, self.n_feat = s.n_kf, s.n_feat
+
+    def __del__(self):
+        try:
+            if self._h:
+                load_library().orbgpu_kfset_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+
+class DeviceDb:
+    def __init__(self, ctx: Context, host=None, dev_ptr: int = 0, nd: int = 0, keepalive=None):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        self._keep = keepalive
+        if host is not None:
+            d = as_u8(host).reshape(-1, 32)
+            self.nd = d.shape[0]
+            _check(load_library().orbgpu_db_upload(ctx.handle, self.nd, _p(d, u8p), C.byref(self._h)))
+        else:
+            self.nd = int(nd)
+            _check(load_library().orbgpu_db_from_dev(ctx.handle, self.nd, C.c_void_p(dev_ptr), C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                load_library().orbgpu_db_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+
+class ORBmatcher:
+    """Drop-in mirror of ORB_SLAM3::ORBmatcher (include/ORBmatcher.h:34-99) on the GPU."""
+
+    TH_HIGH, TH_LOW, HISTO_LENGTH = TH_HIGH, TH_LOW, HISTO_LENGTH
+
+    def __init__(self, nnratio: float = 0.6, checkOri: bool = True, ctx: Optional[Context] = None):
+        self.mfNNratio = float(nnratio)
+        self.mbCheckOrientation = bool(checkOri)
+        self.ctx = ctx if ctx is not None else Context(0)
+
+    # ORBmatcher.h:40
+    def DescriptorDistance(self, a, b):
+        return self.ctx.descriptor_distance(a, b)
+
+    # ORBmatcher.h:69 -> (nmatches, vnMatches12, vbPrevMatched)
+    def SearchForInitialization(self, F1: DeviceFrame, F2: DeviceFrame, vbPrevMatched, windowSize: int = 10):
+        prev = as_f32(vbPrevMatched).copy().reshape(-1, 2)
+        m = np.empty(F1.n, dtype=np.int32)
+        nm = C.c_int32(0)
+        _check(load_library().orbgpu_search_for_initialization(self.ctx.handle, F1.handle, F2.handle, _p(prev, f32p), int(windowSize),
+                                                               self.mfNNratio, int(self.mbCheckOrientation), _p(m, i32p), C.byref(nm)))
+        return nm.value, m, prev
+
+    # ORBmatcher.h:44 -> (nmatches, F.mvpMapPoints as indices into vpMapPoints)
+    def SearchByProjection(self, F: DeviceFrame, vpMapPoints: HostMapPoints, th: float = 3.0, bFarPoints: bool = False,
+                           thFarPoints: float = 50.0, kp_prior_obs=None, kp_mp=None):
+        n = F.n
+        prior = as_i32(kp_prior_obs) if kp_prior_obs is not None else np.zeros(n, dtype=np.int32)
+        out = as_i32(kp_mp).copy() if kp_mp is not None else np.full(n, -1, dtype=np.int32)
+        nm = C.c_int32(0)
+        s = vpMapPoints.struct()
+        _check(load_library().orbgpu_search_by_projection_local(self.ctx.handle, F.handle, C.byref(s), float(th), int(bFarPoints),
+                                                                float(thFarPoints), self.mfNNratio, _p(prior, i32p), _p(out, i32p),
+                                                                C.byref(nm)))
+        return nm.value, out
+
+    # ORBmatcher.h:65 -> (nmatches, vpMapPointMatches as KF feature indices, indexed by F feature)
+    def SearchByBoW(self, KF: DeviceFrame, F: DeviceFrame, kf_mp_valid, f_mp_valid=None):
+        v1 = as_u8(kf_mp_valid)
+        nm = C.c_int32(0)
+        if f_mp_valid is None:  # KeyFrame <-> Frame
+            out = np.empty(F.n, dtype=np.int32)
+            _check(load_library().orbgpu_search_by_bow_kf_f(self.ctx.handle, KF.handle, F.handle, _p(v1, u8p), self.mfNNratio,
+                                                            int(self.mbCheckOrientation), _p(out, i32p), C.byref(nm)))
+        else:  # KeyFrame <-> KeyFrame (ORBmatcher.h:66)
+            v2 = as_u8(f_mp_valid)
+            out = np.empty(KF.n, dtype=np.int32)
+            _check(load_library().orbgpu_search_by_bow_kf_kf(self.ctx.handle, KF.handle, F.handle, _p(v1, u8p), _p(v2, u8p),
+                                                             self.mfNNratio, int(self.mbCheckOrientation), _p(out, i32p), C.byref(nm)))
+        return nm.value, out
+
+    # ORBmatcher.h:72, batched over pairs -> (nmatches[P], vMatches12[P, n_feat])
+    def SearchForTriangulation(self, kfs: DeviceKfSet, kf1, kf2, ep, f12, bOnlyStereo: bool = False, bCoarse: bool = False):
+        kf1, kf2 = as_i32(kf1), as_i32(kf2)
+        ep, f12 = as_f32(ep), as_f32(f12)
+        P = kf1.shape[0]
+        m = np.empty((P, kfs.n_feat), dtype=np.int32)
+        nm = np.empty(P, dtype=np.int32)
+        _check(load_library().orbgpu_search_for_triangulation_batch(self.ctx.handle, kfs.handle, P, _p(kf1, i32p), _p(kf2, i32p),
+                                                                    _p(ep, f32p), _p(f12, f32p), int(bOnlyStereo), int(bCoarse),
+                                                                    int(self.mbCheckOrientation), _p(m, i32p), _p(nm, i32p)))
+        return nm, m
+
+    def SearchForTriangulation_dev(self, kfs: DeviceKfSet, n_pairs, kf1_ptr, kf2_ptr, ep_ptr, f12_ptr, matches_ptr, nmatches_ptr,
+                                   bOnlyStereo=False, bCoarse=False):
+        vp = C.c_void_p
+        _check(load_library().orbgpu_search_for_triangulation_batch_dev(self.ctx.handle, kfs.handle, int(n_pairs), vp(kf1_ptr), vp(kf2_ptr),
+                                                                        vp(ep_ptr), vp(f12_ptr), int(bOnlyStereo), int(bCoarse),
+                                                                        int(self.mbCheckOrientation), vp(matches_ptr), vp(nmatches_ptr)))
+
+    # brute-force 2-NN + ratio test ("SearchByNN" of BASELINE.json) -> best_idx, best_dist, second_dist, match
+    def SearchByNN(self, db: DeviceDb, q, th_low: int = TH_LOW):
+        q = as_u8(q).reshape(-1, 32)
+        nq = q.shape[0]
+        bi = np.empty(nq, dtype=np.int32)
+        bd = np.empty(nq, dtype=np.int32)
+        sd = np.empty(nq, dtype=np.int32)
+        mt = np.empty(nq, dtype=np.int32)
+        _check(load_library().orbgpu_knn2_ratio(self.ctx.handle, db.handle, nq, _p(q, u8p), int(th_low), self.mfNNratio, _p(bi, i32p),
+                                                _p(bd, i32p), _p(sd, i32p), _p(mt, i32p)))
+        return bi, bd, sd, mt
+
+    def SearchByNN_dev(self, db: DeviceDb, nq: int, q_ptr: int, best_idx_ptr: int, best_dist_ptr: int, second_ptr: int, match_ptr: int,
+                       th_low: int = TH_LOW):
+        vp = C.c_void_p
+        _check(load_library().orbgpu_knn2_ratio_dev(self.ctx.handle, db.handle, int(nq), vp(q_ptr), int(th_low), self.mfNNratio,
+                                                    vp(best_idx_ptr), vp(best_dist_ptr), vp(second_ptr), vp(match_ptr)))

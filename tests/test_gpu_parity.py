@@ -1,0 +1,232 @@
+"""GPU parity tests (run with -m gpu on a B200): every search goes through the C-ABI library
+(liborbmatch_b200.so) and must be BIT-EXACT against the CPU oracle on the same seeded inputs and
+against the golden vectors generated from the reference itself."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLD, attach_featvec, digest, golden_cases, golden_outputs, golden_voc
+from orb_slam3_comments_ghr_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from orb_slam3_comments_ghr_b200 import matcher
+    return matcher.Context(0)
+
+
+@pytest.fixture(scope="module")
+def M():
+    from orb_slam3_comments_ghr_b200 import matcher
+    return matcher
+
+
+def test_descriptor_distance(ctx, oracle):
+    z = np.load(f"{GOLD}/descriptor_distance.npz")
+    assert np.array_equal(ctx.descriptor_distance(z["a"], z["b"]), z["dist"])
+    rng = np.random.default_rng(0)
+    a, b = synth.random_descriptors(rng, 100000), synth.random_descriptors(rng, 100000)
+    assert np.array_equal(ctx.descriptor_distance(a, b), np.unpackbits(a ^ b, axis=1).sum(axis=1))
+
+
+def test_three_maxima(ctx):
+    z = np.load(f"{GOLD}/three_maxima.npz")
+    for h, ind in zip(z["histo"], z["ind"]):
+        assert np.array_equal(ctx.compute_three_maxima(h), ind)
+
+
+@pytest.mark.parametrize("seed", [101, 102])
+def test_grid_and_area(ctx, oracle, seed):
+    rng = np.random.default_rng(seed)
+    f = synth.make_frame(rng, 2000)
+    f.kp_xy[:40, 0] = np.arange(40, dtype=np.float32) * 5.0 + 5.0
+    f.kp_xy[40:44] = np.array([[639.75, 479.75], [0, 0], [636.0, 476.0], [635.0, 475.0]], dtype=np.float32)
+    d = ctx.upload_frame(f)
+    cs, ci = d.grid()
+    ocs, oci = oracle.grid(f)
+    assert np.array_equal(cs, ocs) and np.array_equal(ci[:cs[-1]], oci[:ocs[-1]])
+    nq = 500
+    x, y = rng.uniform(-50, 700, nq).astype(np.float32), rng.uniform(-50, 530, nq).astype(np.float32)
+    r = rng.choice(np.array([1.0, 2.5, 7.5, 40.0, 100.0, 1000.0], dtype=np.float32), nq)
+    lv = rng.integers(0, 8, nq)
+    kind = rng.integers(0, 5, nq)
+    mn = np.select([kind == 0, kind == 1, kind == 2, kind == 3, kind == 4], [-1, lv - 1, lv, 0, lv]).astype(np.int32)
+    mx = np.select([kind == 0, kind == 1, kind == 2, kind == 3, kind == 4], [-1, lv, lv, lv, -1]).astype(np.int32)
+    off, idx = d.features_in_area(x, y, r, mn, mx)
+    for q in range(nq):
+        exp = oracle.features_in_area(f, x[q], y[q], r[q], mn[q], mx[q], grid=(ocs, oci))
+        assert np.array_equal(idx[off[q]:off[q + 1]], exp), q
+
+
+@pytest.mark.parametrize("name", ["init_s11", "init_s12_n5000"])
+def test_init_golden(ctx, M, name):
+    g = golden_outputs()
+    c = golden_cases()[name]()
+    m = M.ORBmatcher(c.nnratio, bool(c.check_ori), ctx)
+    n, m12, prev = m.SearchForInitialization(ctx.upload_frame(c.f1), ctx.upload_frame(c.f2), c.prev_matched, c.window_size)
+    assert n == int(g[name + "/nmatches"]) and np.array_equal(m12, g[name + "/matches12"]) and np.array_equal(prev, g[name + "/prev"])
+
+
+@pytest.mark.parametrize("seed,n,ratio,ori", [(201, 1000, 0.9, 1), (202, 1000, 0.6, 0), (203, 300, 0.9, 1), (204, 2500, 0.95, 1), (205, 1, 0.9, 1)])
+def test_init_oracle(ctx, M, oracle, seed, n, ratio, ori):
+    c = synth.make_init_case(seed, n=n)
+    m = M.ORBmatcher(ratio, bool(ori), ctx)
+    got = m.SearchForInitialization(ctx.upload_frame(c.f1), ctx.upload_frame(c.f2), c.prev_matched, c.window_size)
+    oracle.reset_comparisons()
+    exp = oracle.search_for_initialization(c.f1, c.f2, c.prev_matched, c.window_size, ratio, ori)
+    assert got[0] == exp[0] and np.array_equal(got[1], exp[1]) and np.array_equal(got[2], exp[2])
+    assert ctx.last_comparisons == oracle.comparisons()
+
+
+@pytest.mark.parametrize("name", ["proj_s21_th1", "proj_s22_th3", "proj_s23_far"])
+def test_projection_golden(ctx, M, name):
+    g = golden_outputs()
+    c = golden_cases()[name]()
+    m = M.ORBmatcher(c.nnratio, True, ctx)
+    n, k = m.SearchByProjection(ctx.upload_frame(c.frame), c.mps, c.th, bool(c.far_points), c.th_far, c.kp_prior_obs, c.kp_mp)
+    assert n == int(g[name + "/nmatches"]) and np.array_equal(k, g[name + "/kp_mp"])
+
+
+@pytest.mark.parametrize("seed,th,far", [(301, 1.0, 0), (302, 3.0, 0), (303, 15.0, 1), (304, 2.0, 1)])
+def test_projection_oracle(ctx, M, oracle, seed, th, far):
+    c = synth.make_projection_case(seed, th=th, far_points=far)
+    m = M.ORBmatcher(c.nnratio, True, ctx)
+    got = m.SearchByProjection(ctx.upload_frame(c.frame), c.mps, th, bool(far), 40.0, c.kp_prior_obs, c.kp_mp)
+    oracle.reset_comparisons()
+    exp = oracle.search_by_projection_local(c.frame, c.mps, th, far, 40.0, c.nnratio, c.kp_prior_obs, c.kp_mp)
+    assert got[0] == exp[0] and np.array_equal(got[1], exp[1])
+    assert ctx.last_comparisons == oracle.comparisons()
+
+
+@pytest.mark.parametrize("levelsup", [2, 4])
+def test_transform_and_bow_golden(ctx, M, levelsup):
+    g = golden_outputs()
+    voc = golden_voc()
+    dv = ctx.upload_vocabulary(voc)
+    bc = synth.make_bow_case(31, voc, 2000)
+    dev = {}
+    for side, fr in (("kf", bc.kf), ("f", bc.f)):
+        d = ctx.upload_frame(fr)
+        w, nid, wt = d.transform(dv, levelsup, True)
+        p = f"bow_s31/l{levelsup}/{side}/"
+        assert np.array_equal(w, g[p + "word_id"]) and np.array_equal(nid, g[p + "node_id"]) and np.array_equal(wt, g[p + "weight"])
+        bw, bv = d.bowvector()
+        assert np.array_equal(bw, g[p + "bow_words"]) and np.array_equal(bv, g[p + "bow_values"])
+        fn, fo, ff = d.featvec()
+        assert np.array_equal(fn, g[p + "fv_node_ids"]) and np.array_equal(fo, g[p + "fv_offsets"]) and np.array_equal(ff, g[p + "fv_features"])
+        dev[side] = d
+    n, m = M.ORBmatcher(0.7, True, ctx).SearchByBoW(dev["kf"], dev["f"], bc.kf_mp_valid)
+    assert n == int(g[f"bow_s31/l{levelsup}/kf_f/nmatches"]) and np.array_equal(m, g[f"bow_s31/l{levelsup}/kf_f/match"])
+    n, m = M.ORBmatcher(0.9, True, ctx).SearchByBoW(dev["kf"], dev["f"], bc.kf_mp_valid, bc.f_mp_valid)
+    assert n == int(g[f"bow_s31/l{levelsup}/kf_kf/nmatches"]) and np.array_equal(m, g[f"bow_s31/l{levelsup}/kf_kf/match"])
+
+
+@pytest.mark.parametrize("levelsup", [0, 1, 2, 3, 4, 6])
+def test_transform_random_vocabulary(ctx, oracle, levelsup):
+    voc = synth.random_vocabulary(7, k=6, L=4, ragged=True)
+    dv = ctx.upload_vocabulary(voc)
+    rng = np.random.default_rng(levelsup)
+    desc = synth.descriptors_near_words(rng, voc, 700)
+    fr = synth.make_frame(rng, 700)
+    fr.desc[:] = desc
+    d = ctx.upload_frame(fr)
+    w, nid, wt = d.transform(dv, levelsup, True)
+    oracle.reset_comparisons()
+    ow, onid, owt = oracle.voc_transform(voc, desc, levelsup)
+    assert ctx.last_comparisons == oracle.comparisons()
+    assert np.array_equal(w, ow) and np.array_equal(nid, onid) and np.array_equal(wt, owt)
+    bw, bv = d.bowvector()
+    obw, obv = oracle.bowvector(ow, owt)
+    assert np.array_equal(bw, obw) and np.array_equal(bv, obv)
+    fn, fo, ff = d.featvec()
+    ofn, ofo, off_ = oracle.featvec(onid, owt)
+    assert np.array_equal(fn, ofn) and np.array_equal(fo, ofo) and np.array_equal(ff, off_)
+
+
+@pytest.mark.parametrize("seed,levelsup,ratio", [(401, 2, 0.7), (402, 3, 0.75), (403, 4, 0.9)])
+def test_bow_host_featvec(ctx, M, oracle, seed, levelsup, ratio):
+    """FeatureVectors supplied by the host (flattened std::map), as the drop-in adapter does"""
+    voc = golden_voc()
+    bc = synth.make_bow_case(seed, voc, 1200)
+    kf = attach_featvec(oracle, voc, bc.kf, levelsup)
+    f = attach_featvec(oracle, voc, bc.f, levelsup)
+    dkf, df = ctx.upload_frame(kf), ctx.upload_frame(f)
+    for ori in (0, 1):
+        m = M.ORBmatcher(ratio, bool(ori), ctx)
+        got = m.SearchByBoW(dkf, df, bc.kf_mp_valid)
+        oracle.reset_comparisons()
+        exp = oracle.search_by_bow_kf_f(kf, f, bc.kf_mp_valid, ratio, ori)
+        assert got[0] == exp[0] and np.array_equal(got[1], exp[1])
+        assert ctx.last_comparisons == oracle.comparisons()
+        got = m.SearchByBoW(dkf, df, bc.kf_mp_valid, bc.f_mp_valid)
+        exp = oracle.search_by_bow_kf_kf(kf, f, bc.kf_mp_valid, bc.f_mp_valid, ratio, ori)
+        assert got[0] == exp[0] and np.array_equal(got[1], exp[1])
+
+
+@pytest.mark.parametrize("check_ori", [0, 1])
+def test_triangulation_golden(ctx, M, check_ori):
+    g = golden_outputs()
+    tc = synth.fill_geometry(synth.make_triangulation_case(41, n_pairs=8, n_feat=2000))
+    ks = ctx.upload_kfset(tc.kfs)
+    nm, m = M.ORBmatcher(0.6, bool(check_ori), ctx).SearchForTriangulation(ks, tc.kf1, tc.kf2, g["tri_s41/ep"], g["tri_s41/f12"])
+    assert np.array_equal(nm, g[f"tri_s41/ori{check_ori}/nmatches"])
+    assert np.array_equal(m, g[f"tri_s41/ori{check_ori}/matches"].astype(np.int32))
+
+
+@pytest.mark.parametrize("seed,n_pairs,n_feat,coarse,ori", [(501, 6, 1500, 0, 0), (502, 6, 1500, 0, 1), (503, 6, 1500, 1, 1), (504, 96, 2000, 0, 0), (505, 3, 64, 0, 1)])
+def test_triangulation_oracle(ctx, M, oracle, seed, n_pairs, n_feat, coarse, ori):
+    tc = synth.fill_geometry(synth.make_triangulation_case(seed, n_pairs=n_pairs, n_feat=n_feat))
+    ks = ctx.upload_kfset(tc.kfs)
+    nm, m = M.ORBmatcher(0.6, bool(ori), ctx).SearchForTriangulation(ks, tc.kf1, tc.kf2, tc.ep, tc.f12, False, bool(coarse))
+    oracle.reset_comparisons()
+    enm, em = oracle.search_for_triangulation_batch(tc.kfs, tc.kf1, tc.kf2, tc.ep, tc.f12, 0, coarse, ori, n_threads=os.cpu_count() or 1)
+    assert np.array_equal(nm, enm) and np.array_equal(m, em)
+    assert ctx.last_comparisons == oracle.comparisons()
+
+
+@pytest.mark.parametrize("engine", [1, 2])
+def test_knn2_golden(ctx, M, engine):
+    g = golden_outputs()
+    kc = synth.make_knn_case(51, 512, 20000)
+    ctx.set_knn_engine(engine)
+    got = M.ORBmatcher(kc.nnratio, True, ctx).SearchByNN(ctx.upload_database(kc.db), kc.q, kc.th_low)
+    ctx.set_knn_engine(0)
+    for a, name in zip(got, ("best_idx", "best_dist", "second_dist", "match")):
+        assert np.array_equal(a, g["knn_s51/" + name]), name
+
+
+@pytest.mark.parametrize("engine", [1, 2])
+@pytest.mark.parametrize("nq,nd", [(1, 1), (3, 2), (1000, 257), (4097, 70001), (300, 3)])
+def test_knn2_oracle_ragged(ctx, M, oracle, engine, nq, nd):
+    kc = synth.make_knn_case(nq * 7 + nd, nq, nd)
+    ctx.set_knn_engine(engine)
+    got = M.ORBmatcher(0.8, True, ctx).SearchByNN(ctx.upload_database(kc.db), kc.q, 50)
+    ctx.set_knn_engine(0)
+    exp = oracle.knn2_ratio(kc.q, kc.db, 50, 0.8, n_threads=os.cpu_count() or 1)
+    for a, e, name in zip(got, exp, ("best_idx", "best_dist", "second_dist", "match")):
+        assert np.array_equal(a, e), name
+    assert ctx.last_comparisons == nq * nd
+
+
+def test_knn2_properties_large(ctx, M):
+    """size-independent properties at a size the oracle cannot finish: planted queries must find their
+    source row (or an earlier exact duplicate), best <= second, idempotence."""
+    rng = np.random.default_rng(77)
+    nd, nq = 1 << 20, 1 << 14
+    db = synth.random_descriptors(rng, nd)
+    src = rng.integers(0, nd, nq)
+    q = db[src] ^ synth.flip_mask(rng, nq, 5)
+    m = M.ORBmatcher(0.8, True, ctx)
+    d = ctx.upload_database(db)
+    bi, bd, sd, mt = m.SearchByNN(d, q, 50)
+    true_d = np.unpackbits(q ^ db[src], axis=1).sum(axis=1)
+    assert (bd <= true_d).all() and (bd <= sd).all()
+    same = bi == src
+    assert same.mean() > 0.999
+    got_d = np.unpackbits(q ^ db[bi], axis=1).sum(axis=1)
+    assert np.array_equal(got_d, bd)
+    again = m.SearchByNN(d, q, 50)
+    assert all(np.array_equal(a, b) for a, b in zip((bi, bd, sd, mt), again))

@@ -1,0 +1,103 @@
+"""CPU, only where oracle/_ref exists: the C restatement equals the reference's own
+ORBmatcher.cc / DBoW2 (compiled unmodified) on fresh seeds and on the edge cases."""
+import numpy as np
+import pytest
+
+from helpers import attach_featvec, golden_voc
+from orb_slam3_comments_ghr_b200 import synth
+from orb_slam3_comments_ghr_b200._abi import HostFrame, HostMapPoints
+
+pytestmark = pytest.mark.ref
+
+
+@pytest.mark.parametrize("seed", [101, 102, 103])
+def test_grid_and_area(oracle, reference, seed):
+    rng = np.random.default_rng(seed)
+    f = synth.make_frame(rng, 1500)
+    # exact cell-boundary and out-of-image keypoints
+    f.kp_xy[:40, 0] = np.arange(40, dtype=np.float32) * 5.0 + 5.0  # x*0.1 = k+0.5 -> round-half-away ties
+    f.kp_xy[40:44] = np.array([[639.75, 479.75], [0, 0], [636.0, 476.0], [635.0, 475.0]], dtype=np.float32)
+    cs_o, ci_o = oracle.grid(f)
+    cs_r, ci_r = reference.grid(f)
+    assert np.array_equal(cs_o, cs_r) and np.array_equal(ci_o, ci_r)
+    for _ in range(200):
+        x, y = rng.uniform(-50, 700), rng.uniform(-50, 530)
+        r = float(rng.choice([1.0, 2.5, 7.5, 40.0, 100.0, 1000.0]))
+        lv = int(rng.integers(0, 8))
+        mn, mx = [(-1, -1), (lv - 1, lv), (lv, lv), (0, lv), (lv, -1)][int(rng.integers(0, 5))]
+        a = oracle.features_in_area(f, x, y, r, mn, mx, grid=(cs_o, ci_o))
+        b = reference.features_in_area(f, x, y, r, mn, mx)
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("seed,n,ratio,ori", [(201, 1000, 0.9, 1), (202, 1000, 0.6, 0), (203, 300, 0.9, 1), (204, 2500, 0.95, 1)])
+def test_init(oracle, reference, seed, n, ratio, ori):
+    c = synth.make_init_case(seed, n=n)
+    a = oracle.search_for_initialization(c.f1, c.f2, c.prev_matched, c.window_size, ratio, ori)
+    b = reference.search_for_initialization(c.f1, c.f2, c.prev_matched, c.window_size, ratio, ori)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+@pytest.mark.parametrize("seed,th,far", [(301, 1.0, 0), (302, 3.0, 0), (303, 15.0, 1), (304, 2.0, 1)])
+def test_projection(oracle, reference, seed, th, far):
+    c = synth.make_projection_case(seed, th=th, far_points=far)
+    a = oracle.search_by_projection_local(c.frame, c.mps, th, far, 40.0, c.nnratio, c.kp_prior_obs, c.kp_mp)
+    b = reference.search_by_projection_local(c.frame, c.mps, th, far, 40.0, c.nnratio, c.kp_prior_obs, c.kp_mp)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("levelsup", [0, 1, 2, 3, 4, 6])
+def test_transform_random_vocabulary(oracle, reference, levelsup):
+    voc = synth.random_vocabulary(7, k=6, L=4, ragged=True)
+    hv = reference.voc_from_flat(voc)
+    rng = np.random.default_rng(levelsup)
+    d = synth.descriptors_near_words(rng, voc, 700)
+    r = hv.transform(d, levelsup)
+    w, nid, wt = oracle.voc_transform(voc, d, levelsup)
+    assert np.array_equal(w, r["word_id"]) and np.array_equal(nid, r["node_id"]) and np.array_equal(wt, r["weight"])
+    bw, bv = oracle.bowvector(w, wt)
+    assert np.array_equal(bw, r["bow_words"]) and np.array_equal(bv, r["bow_values"])
+    fn, fo, ff = oracle.featvec(nid, wt)
+    assert np.array_equal(fn, r["fv_node_ids"]) and np.array_equal(fo, r["fv_offsets"]) and np.array_equal(ff, r["fv_features"])
+    assert (wt == 0).any(), "the random vocabulary must exercise stopped words"
+
+
+@pytest.mark.parametrize("seed,levelsup,ratio", [(401, 2, 0.7), (402, 3, 0.75), (403, 4, 0.9)])
+def test_bow(oracle, reference, seed, levelsup, ratio):
+    voc = golden_voc()
+    bc = synth.make_bow_case(seed, voc, 1200)
+    kf = attach_featvec(oracle, voc, bc.kf, levelsup)
+    f = attach_featvec(oracle, voc, bc.f, levelsup)
+    for ori in (0, 1):
+        a = oracle.search_by_bow_kf_f(kf, f, bc.kf_mp_valid, ratio, ori)
+        b = reference.search_by_bow_kf_f(kf, f, bc.kf_mp_valid, ratio, ori)
+        assert a[0] == b[0] and np.array_equal(a[1], b[1])
+        a = oracle.search_by_bow_kf_kf(kf, f, bc.kf_mp_valid, bc.f_mp_valid, ratio, ori)
+        b = reference.search_by_bow_kf_kf(kf, f, bc.kf_mp_valid, bc.f_mp_valid, ratio, ori)
+        assert a[0] == b[0] and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("seed,coarse,ori", [(501, 0, 0), (502, 0, 1), (503, 1, 1)])
+def test_triangulation(oracle, reference, seed, coarse, ori):
+    tc = synth.fill_geometry(synth.make_triangulation_case(seed, n_pairs=6, n_feat=1500))
+    for p in range(6):
+        ep, f12 = reference.triangulation_geometry(tc.T1w[p], tc.T2w[p], tc.K, tc.K)
+        assert np.array_equal(ep, tc.ep[p]) and np.array_equal(f12, tc.f12[p])
+    a = oracle.search_for_triangulation_batch(tc.kfs, tc.kf1, tc.kf2, tc.ep, tc.f12, 0, coarse, ori, n_threads=2)
+    b = reference.search_for_triangulation_batch(tc.kfs, tc.kf1, tc.kf2, tc.T1w, tc.T2w, tc.K, 0, coarse, ori, 0.6, n_threads=2)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_edge_cases(oracle, reference):
+    rng = np.random.default_rng(9)
+    # empty frames / no candidates / single candidate (INT_MAX second best in init)
+    f1 = synth.make_frame(rng, 3)
+    f2 = synth.make_frame(rng, 1)
+    f1.octave[:] = 0
+    f2.octave[:] = 0
+    f2.kp_xy[0] = f1.kp_xy[0]
+    f2.desc[0] = f1.desc[0]
+    a = oracle.search_for_initialization(f1, f2, f1.kp_xy.copy(), 100, 0.9, 1)
+    b = reference.search_for_initialization(f1, f2, f1.kp_xy.copy(), 100, 0.9, 1)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+    assert a[0] >= 1
