@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- Hamming comparisons/s of the descriptor-matching hot path on B200.
+
+Headline workload (BASELINE.json configs[4], the largest single-GPU configuration): brute-force
+2-NN Hamming search with ratio test, 256k query descriptors vs a 4M-descriptor database
+(relocalization scale).  One "step" = one full pass: every query against every database row,
+best / second-best reduction, ratio test, match indices out.
+
+  python bench.py --gpus N --steps K --warmup W            (torchrun launches N ranks for N > 1)
+  python bench.py --impl reference ...                     reference CPU implementation on host cores
+
+Multi-GPU: queries are sharded contiguously by row over the ranks (database replicated), each rank
+searches its rows, and ONE NCCL all-gather of the match indices assembles the result ("strong"
+scaling: the total work is fixed by the config).  The secondary workload `--workload c4` is the
+batched SearchForTriangulation (4096 keyframe pairs x 2000 features), reported in frame pairs/s.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NQ_FULL, ND_FULL = 262144, 4194304      # BASELINE.json: "256k query vs 4M database descriptors"
+C4_PAIRS, C4_FEAT = 4096, 2000          # BASELINE.json: "4096 keyframe pairs x 2000 features"
+TH_LOW, NNRATIO = 50, 0.8
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_knn_baseline(nd: int, want_seconds: float = 12.0, prefer_reference: bool = True):
+    """the reference's CPU path (oracle/_ref when present, else the C port) on a bounded query sample
+    of the same workload, all host threads; returns (value cmp/s, dict)."""
+    from oracle.pyoracle import Oracle, Reference
+    cores = os.cpu_count() or 1
+    if prefer_reference and Reference.available(fast=True):
+        impl, kind = Reference(fast=True), "reference"
+    else:
+        impl, kind = Oracle(), "port"
+    rng = np.random.default_rng(1)
+    db = rng.integers(0, 256, size=(nd, 32), dtype=np.uint8)
+    nq0 = max(cores, 8)
+    q = rng.integers(0, 256, size=(nq0, 32), dtype=np.uint8)
+    t = time.perf_counter()
+    impl.knn2_ratio(q, db, TH_LOW, NNRATIO, cores)
+    t0 = time.perf_counter() - t
+    nq = int(min(65536, max(nq0, nq0 * want_seconds / max(t0, 1e-3))))
+    nq = max(cores, (nq // cores) * cores)
+    q = rng.integers(0, 256, size=(nq, 32), dtype=np.uint8)
+    t = time.perf_counter()
+    impl.knn2_ratio(q, db, TH_LOW, NNRATIO, cores)
+    dt = time.perf_counter() - t
+    val = nq * nd / dt
+    return val, {"value": val, "unit": "hamming_comparisons/s", "cores": cores, "kind": kind,
+                 "sample": f"{nq} of {NQ_FULL} queries x {nd} database rows, {dt:.1f} s, {cores} threads"}
+
+
+def cpu_tri_baseline(case, want_seconds: float = 10.0):
+    from oracle.pyoracle import Oracle, Reference
+    cores = os.cpu_count() or 1
+    P = case.kf1.shape[0]
+    if Reference.available(fast=True):
+        impl, kind = Reference(fast=True), "reference"
+        run = lambda n: impl.search_for_triangulation_batch(case.kfs, case.kf1[:n], case.kf2[:n], case.T1w[:n], case.T2w[:n], case.K, 0, 0, 0, 0.6, cores)
+    else:
+        impl, kind = Oracle(), "port"
+        run = lambda n: impl.search_for_triangulation_batch(case.kfs, case.kf1[:n], case.kf2[:n], case.ep[:n], case.f12[:n], 0, 0, 0, cores)
+    n0 = min(P, max(cores, 16))
+    t = time.perf_counter(); run(n0); t0 = time.perf_counter() - t
+    n = int(min(P, max(n0, n0 * want_seconds / max(t0, 1e-3))))
+    t = time.perf_counter(); run(n); dt = time.perf_counter() - t
+    val = n / dt
+    return val, {"value": val, "unit": "frame_pairs/s", "cores": cores, "kind": kind,
+                 "sample": f"{n} of {C4_PAIRS} keyframe pairs x {case.kfs.n_feat} features, {dt:.1f} s, {cores} threads"}
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation on the box's host cores, same metric
+    and config; each step is a bounded sample of the workload.  Rank 0 only."""
+    if rank != 0:
+        return
+    nd = args.nd
+    vals, info = [], None
+    for s in range(args.warmup + args.steps):
+        per = max(4.0, min(20.0, 150.0 / max(1, args.warmup + args.steps)))
+        if args.workload == "c5":
+            v, info = cpu_knn_baseline(nd, want_seconds=per)
+        else:
+            from orb_slam3_comments_ghr_b200 import synth
+            case = synth.fill_geometry(synth.make_triangulation_case(9, n_pairs=256, n_feat=C4_FEAT))
+            v, info = cpu_tri_baseline(case, want_seconds=per)
+        if s >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    info["value"] = value
+    line = {"impl": "reference", "metric": "hamming_comparisons_per_s" if args.workload == "c5" else "frame_pairs_matched_per_s",
+            "value": value, "unit": info["unit"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": workload_config(args), "cpu_baseline": info,
+            "e2e": {"value": value, "unit": info["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    if args.workload == "c5":
+        return {"workload": f"C5 brute-force 2-NN Hamming + ratio test: {args.nq} queries x {args.nd} database descriptors (256-bit), "
+                            f"th_low={TH_LOW}, nnratio={NNRATIO}", "nq": args.nq, "nd": args.nd,
+                "sharding": "queries by row, database replicated, one all-gather of match indices",
+                "l2": "L2 flushed (512 MiB write) between timed steps; database (128 MiB) also exceeds L2"}
+    return {"workload": f"C4 batched SearchForTriangulation: {args.pairs} keyframe pairs x {C4_FEAT} features, epipolar check, checkOri=false",
+            "pairs": args.pairs, "n_feat": C4_FEAT, "sharding": "pairs by index, keyframe set per rank, one all-gather of match indices",
+            "l2": "L2 flushed (512 MiB write) between timed steps"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5", choices=["c5", "c4"])
+    ap.add_argument("--nq", type=int, default=NQ_FULL)
+    ap.add_argument("--nd", type=int, default=ND_FULL)
+    ap.add_argument("--pairs", type=int, default=C4_PAIRS)
+    ap.add_argument("--engine", type=int, default=0, help="knn2 engine: 0 auto, 1 POPC, 2 mma.sync b1, 3 tcgen05")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from orb_slam3_comments_ghr_b200 import matcher, synth
+    from orb_slam3_comments_ghr_b200.sharding import all_gather_rows, shard_bounds
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = matcher.Context(local_rank, stream=torch.cuda.current_stream().cuda_stream)
+    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def flush_l2():
+        flush_buf.fill_(1)
+
+    def barrier_sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    K, W = args.steps, args.warmup
+    extra = {}
+    if args.workload == "c5":
+        nq_total, nd = args.nq, args.nd
+        lo, hi = shard_bounds(nq_total, rank, world)
+        nq = hi - lo
+        g = torch.Generator(device=dev)
+        g.manual_seed(20261018)
+        db = torch.randint(0, 256, (nd, 32), dtype=torch.uint8, device=dev, generator=g)
+        q_all = torch.randint(0, 256, (nq_total, 32), dtype=torch.uint8, device=dev, generator=g)
+        n_pl = nq_total // 10  # 10 % planted: database rows with ~1/16 of the bits flipped
+        who = torch.randperm(nq_total, device=dev, generator=g)[:n_pl]
+        src = torch.randint(0, nd, (n_pl,), device=dev, generator=g)
+        mask = torch.randint(0, 256, (n_pl, 32), dtype=torch.uint8, device=dev, generator=g)
+        for _ in range(3):
+            mask &= torch.randint(0, 256, (n_pl, 32), dtype=torch.uint8, device=dev, generator=g)
+        q_all[who] = db[src] ^ mask
+        q = q_all[lo:hi].contiguous()
+        res = torch.empty((4, max(nq, 1)), dtype=torch.int32, device=dev)
+        m = matcher.ORBmatcher(NNRATIO, True, ctx)
+        ctx.set_knn_engine(args.engine)
+        ddb = ctx.database_from_device(db.data_ptr(), nd, keepalive=db)
+
+        def step():
+            m.SearchByNN_dev(ddb, nq, q.data_ptr(), res[0].data_ptr(), res[1].data_ptr(), res[2].data_ptr(), res[3].data_ptr(), TH_LOW)
+            if world > 1:
+                return all_gather_rows(res.t().contiguous(), nq_total)
+            return res
+
+        units_total = float(nq_total) * float(nd)
+        metric, unit = "hamming_comparisons_per_s", "hamming_comparisons/s"
+    else:
+        P_total = args.pairs
+        lo, hi = shard_bounds(P_total, rank, world)
+        P = hi - lo
+        case = synth.fill_geometry(synth.make_triangulation_case(20261018 + rank, n_pairs=max(P, 1), n_feat=C4_FEAT))
+        ks = ctx.upload_kfset(case.kfs)
+        m = matcher.ORBmatcher(0.6, False, ctx)
+        kf1, kf2 = torch.from_numpy(case.kf1).to(dev), torch.from_numpy(case.kf2).to(dev)
+        ep, f12 = torch.from_numpy(case.ep).to(dev), torch.from_numpy(case.f12).to(dev)
+        out = torch.empty((max(P, 1), C4_FEAT), dtype=torch.int32, device=dev)
+        nmt = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
+
+        def step():
+            m.SearchForTriangulation_dev(ks, P, kf1.data_ptr(), kf2.data_ptr(), ep.data_ptr(), f12.data_ptr(), out.data_ptr(), nmt.data_ptr())
+            if world > 1:
+                return all_gather_rows(out, P_total)
+            return out
+
+        units_total = float(P_total)
+        metric, unit = "frame_pairs_matched_per_s", "frame_pairs/s"
+
+    # ---- device-resident timing: W warm-up steps, then exactly K timed steps
+    for _ in range(W):
+        step()
+    barrier_sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    total_ms = 0.0
+    barrier_sync()
+    for _ in range(K):
+        flush_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        e1.synchronize()
+        total_ms += e0.elapsed_time(e1)
+    barrier_sync()
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else {}
+    total_ms = max_over_ranks(total_ms)
+    ms_per_step = total_ms / max(K, 1)
+    value = units_total / (ms_per_step * 1e-3)
+    if args.workload == "c5":
+        ctx.synchronize()
+        extra["comparisons_per_step"] = int(units_total)
+        extra["matches_rank0"] = int((res[3][:nq] >= 0).sum().item())
+
+    # ---- end to end through the host-pointer C-ABI (what a reference-side caller uses)
+    e2e = None
+    if not args.no_e2e:
+        Ke = min(K, 2)
+        if args.workload == "c5":
+            db_h = db.cpu().pin_memory().numpy()
+            q_h = q.cpu().pin_memory().numpy()
+            h2d = db_h.nbytes + q_h.nbytes
+            d2h = 4 * 4 * nq
+
+            def e2e_step():
+                hdb = ctx.upload_database(db_h)  # database H2D is part of the step
+                r = m.SearchByNN(hdb, q_h, TH_LOW)
+                del hdb
+                return r
+        else:
+            h2d = case.kf1.nbytes * 2 + case.ep.nbytes + case.f12.nbytes
+            d2h = P * C4_FEAT * 4 + P * 4
+
+            def e2e_step():
+                return m.SearchForTriangulation(ks, case.kf1, case.kf2, case.ep, case.f12)
+        e2e_step()
+        barrier_sync()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / Ke
+        dt = max_over_ranks(dt)
+        e2e = {"value": units_total / dt, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": dt * 1e3, "steps": Ke,
+               "note": "host-pointer C-ABI call; C5 re-uploads the 128 MiB database every step" if args.workload == "c5" else
+                       "host-pointer C-ABI call; keyframe set resident (uploaded once like the reference's KeyFrames)"}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        engine = args.engine if args.engine else (3 if getattr(matcher, "TC_DEFAULT", False) else 1)
+        per_gpu_units = units_total / world
+        kern_s = ms_per_step * 1e-3
+        if args.workload == "c5":
+            if engine == 3:
+                flops = per_gpu_units * 512.0  # 256 MACs per 256-bit comparison on the +-1 fp8 contraction
+                peak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+                roof = {"bound": "tensor", "achieved": flops / kern_s / 1e12, "peak": peak, "unit": "TFLOP/s",
+                        "frac": flops / kern_s / 1e12 / peak, "traffic": None,
+                        "note": "fp8 dense peak taken as 2x the measured bf16 cuBLAS burst of MEASURED_PEAKS.json"}
+            else:
+                popc = per_gpu_units * 8.0  # 8 POPC32 per comparison
+                sm_mhz = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+                peak = 148 * 16 * sm_mhz * 1e6 / 1e12
+                roof = {"bound": "int-popc", "achieved": popc / kern_s / 1e12, "peak": peak, "unit": "TPOPC32/s",
+                        "frac": popc / kern_s / 1e12 / peak, "traffic": None,
+                        "note": "integer-pipe roofline: 16 POPC/clk/SM x 148 SMs at the SM clock sampled during the run"}
+        else:
+            # algorithmic bytes per pair: 32 B x map-point-free descriptors of both keyframes (~50 %), CSR
+            # feature ids + node ids, match row out
+            bytes_pair = 2 * (0.5 * C4_FEAT * 32 + 0.5 * C4_FEAT * 4 + 100 * 8) + C4_FEAT * 4 + 4 + 44
+            gb = per_gpu_units * bytes_pair / 1e9
+            peak = float(peaks.get("hbm_gbs", 6650.0))
+            roof = {"bound": "hbm", "achieved": gb / kern_s, "peak": peak, "unit": "GB/s", "frac": gb / kern_s / peak, "traffic": None}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                if args.workload == "c5":
+                    _, cpu = cpu_knn_baseline(args.nd)
+                else:
+                    _, cpu = cpu_tri_baseline(case)
+            except Exception as e:  # the baseline is a reported number, never a reason to lose the bench line
+                cpu = {"value": None, "error": repr(e)}
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+                "cpu_baseline": cpu, "engine": engine, **extra}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -18,8 +18,8 @@
 
 #include "internal.cuh"
 
-int knn2_tc_run(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const uint4 *q, uint64_t *part_best,
-                uint32_t *part_second, int *n_splits_out, int64_t part_stride); // knn2_tc.cu
+int knn2_tc_run(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const uint4 *q, int32_t th_low, float nnratio, int32_t *best_idx,
+                int32_t *best_dist, int32_t *second_dist, int32_t *match); // knn2_tc.cu
 bool knn2_tc_supported();
 
 namespace {
@@ -343,7 +343,7 @@ static KnnPlan knn2_plan(const orbgpu_ctx *ctx, int64_t nq, int64_t nd)
     p.chunk = chunk;
     p.splits = std::max<int64_t>(1, (nd + chunk - 1) / chunk);
     p.stride = std::max<int64_t>(nq, 1);
-    p.cap_splits = (p.engine == 3) ? std::max<int64_t>(p.splits, 64) : p.splits; // the tensor engine picks its own split count (<= 64)
+    p.cap_splits = p.splits;
     p.part_bytes = align256(p.cap_splits * p.stride * 8) + align256(p.cap_splits * p.stride * 4);
     return p;
 }
@@ -358,6 +358,8 @@ static int knn2_launch(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const u
     if (!part_best || !part_second) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
     ctx->last_comparisons = nq * nd;
     if (nq == 0) return ORBGPU_OK;
+    if (p.engine == 3 && nd > 0) // tensor engine: expansion + tcgen05 search + its own merge
+        return knn2_tc_run(ctx, db, nq, q, th_low, nnratio, best_idx, best_dist, second_dist, match);
     int n_splits = (int)p.splits;
     if (nd > 0) {
         if (p.engine == 1) {
@@ -369,9 +371,6 @@ static int knn2_launch(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const u
             knn2_mma_b1_kernel<<<grid, MMA_WARPS * 32, 0, ctx->stream>>>((const uint32_t *)q, nq, (const uint32_t *)db->desc, nd,
                                                                          p.chunk, part_best, part_second, p.stride);
             LAUNCH_COUNT(ctx);
-        } else {
-            int rc = knn2_tc_run(ctx, db, nq, q, part_best, part_second, &n_splits, p.stride);
-            if (rc) return rc;
         }
         CU_TRY(cudaGetLastError());
     } else {
