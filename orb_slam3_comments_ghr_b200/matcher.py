@@ -21,6 +21,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liborbmatc
 _lib = None
 
 TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30  # ORBmatcher.cc:34-36
+TC_DEFAULT = True  # engine 0 (auto) resolves to the tcgen05 engine for nq >= 128 and nd >= 1024
 
 
 class OrbGpuError(RuntimeError):
