@@ -1,0 +1,322 @@
+// ORBmatcher.hpp -- C++ drop-in adapter: the reference's ORB_SLAM3::ORBmatcher call signatures
+// (include/ORBmatcher.h:37-84) on top of the C ABI of include/orbmatch_b200.h.
+//
+// It only packs the members the reference matcher reads into the flat host structs, calls the
+// GPU library, and scatters the results back into the caller's STL containers in the reference's
+// layouts (vnMatches12, vpMapPointMatches, vMatchedPairs, F.mvpMapPoints).  No matching logic lives
+// here and there is no CPU fallback: a failing GPU call throws std::runtime_error.
+//
+// The class is a template over the reference's own Frame / KeyFrame / MapPoint types so that it
+// compiles inside ORB-SLAM3 unchanged:
+//     #include <orbmatch_b200/ORBmatcher.hpp>
+//     using ORBmatcherGPU = orbgpu::ORBmatcherT<ORB_SLAM3::Frame, ORB_SLAM3::KeyFrame, ORB_SLAM3::MapPoint>;
+// and against the oracle's stub types for the parity tests (tests/cpp/adapter_parity.cc).
+//
+// Covered overloads: SearchForInitialization, SearchByProjection(Frame&,
+// vector<MapPoint*>&), SearchByBoW x2, SearchForTriangulation (monocular pinhole), DescriptorDistance.
+#pragma once
+
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include <orbmatch_b200.h> // compile with -I<repo>/include
+
+namespace orbgpu
+{
+    inline void check(int rc)
+    {
+        if (rc != ORBGPU_OK) throw std::runtime_error(std::string("orbmatch_b200: ") + orbgpu_last_error());
+    }
+
+    // one context (stream + workspace) per calling thread: the reference calls the matcher from the
+    // Tracking, LocalMapping and LoopClosing threads concurrently (System.cc:234,254)
+    inline orbgpu_ctx *thread_context(int device = 0)
+    {
+        struct Holder
+        {
+            orbgpu_ctx *ctx = nullptr;
+            ~Holder() { if (ctx) orbgpu_destroy(ctx); }
+        };
+        thread_local Holder h;
+        if (!h.ctx) check(orbgpu_create(device, &h.ctx));
+        return h.ctx;
+    }
+
+    // flat copy of the members of a Frame / KeyFrame that the matcher reads
+    struct PackedFrame
+    {
+        std::vector<uint8_t> desc;
+        std::vector<float> xy, angle, u_right, sf, s2;
+        std::vector<int32_t> octave;
+        std::vector<uint32_t> fv_nodes, fv_feats;
+        std::vector<int32_t> fv_off;
+        orbgpu_frame_host h;
+
+        template <class FS>
+        void pack(const FS &F, float minX, float minY, float maxX, float maxY, bool with_uright)
+        {
+            const int n = F.N;
+            desc.resize((size_t)n * 32);
+            xy.resize((size_t)n * 2);
+            angle.resize(n);
+            octave.resize(n);
+            for (int i = 0; i < n; i++)
+            {
+                std::memcpy(&desc[(size_t)i * 32], F.mDescriptors.row(i).template ptr<uint8_t>(), 32);
+                xy[2 * i] = F.mvKeysUn[i].pt.x;
+                xy[2 * i + 1] = F.mvKeysUn[i].pt.y;
+                octave[i] = F.mvKeysUn[i].octave;
+                angle[i] = F.mvKeysUn[i].angle;
+            }
+            u_right.clear();
+            if (with_uright) u_right.assign(F.mvuRight.begin(), F.mvuRight.end());
+            sf.assign(F.mvScaleFactors.begin(), F.mvScaleFactors.end());
+            s2.assign(F.mvLevelSigma2.begin(), F.mvLevelSigma2.end());
+            fv_nodes.clear(); fv_feats.clear(); fv_off.clear();
+            for (const auto &kv : F.mFeatVec) // std::map<NodeId, vector<uint>>: ascending node id, ascending feature id
+            {
+                fv_nodes.push_back(kv.first);
+                fv_off.push_back((int32_t)fv_feats.size());
+                fv_feats.insert(fv_feats.end(), kv.second.begin(), kv.second.end());
+            }
+            fv_off.push_back((int32_t)fv_feats.size());
+            std::memset(&h, 0, sizeof(h));
+            h.n = n;
+            h.desc = desc.data(); h.kp_xy = xy.data(); h.octave = octave.data(); h.angle = angle.data();
+            h.u_right = u_right.empty() ? nullptr : u_right.data();
+            h.min_x = minX; h.min_y = minY; h.max_x = maxX; h.max_y = maxY;
+            h.grid_inv_w = F.mfGridElementWidthInv; h.grid_inv_h = F.mfGridElementHeightInv;
+            h.grid_cols = ORBGPU_FRAME_GRID_COLS; h.grid_rows = ORBGPU_FRAME_GRID_ROWS;
+            h.n_levels = (int32_t)sf.size();
+            h.scale_factors = sf.data(); h.level_sigma2 = s2.data();
+            h.fv_n_nodes = (int32_t)fv_nodes.size();
+            h.fv_node_ids = fv_nodes.data(); h.fv_offsets = fv_off.data(); h.fv_features = fv_feats.data();
+        }
+    };
+
+    struct DeviceFrameGuard
+    {
+        orbgpu_frame *f = nullptr;
+        DeviceFrameGuard(orbgpu_ctx *ctx, const orbgpu_frame_host &h) { check(orbgpu_frame_upload(ctx, &h, &f)); }
+        ~DeviceFrameGuard() { orbgpu_frame_destroy(f); }
+        DeviceFrameGuard(const DeviceFrameGuard &) = delete;
+        DeviceFrameGuard &operator=(const DeviceFrameGuard &) = delete;
+    };
+
+    template <class FrameT, class KeyFrameT, class MapPointT>
+    class ORBmatcherT
+    {
+    public:
+        // ORBmatcher.h:37
+        ORBmatcherT(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+
+        // ORBmatcher.h:40 (ORBmatcher.cc:2388-2408)
+        template <class Mat>
+        static int DescriptorDistance(const Mat &a, const Mat &b)
+        {
+            int32_t d = 0;
+            check(orbgpu_descriptor_distance(thread_context(), 1, a.template ptr<uint8_t>(), b.template ptr<uint8_t>(), &d));
+            return d;
+        }
+
+        // ORBmatcher.h:69 (ORBmatcher.cc:735-878)
+        template <class Point2f>
+        int SearchForInitialization(FrameT &F1, FrameT &F2, std::vector<Point2f> &vbPrevMatched, std::vector<int> &vnMatches12,
+                                    int windowSize = 10)
+        {
+            orbgpu_ctx *ctx = thread_context();
+            PackedFrame p1, p2;
+            p1.pack(F1, F1.mnMinX, F1.mnMinY, F1.mnMaxX, F1.mnMaxY, false);
+            p2.pack(F2, F2.mnMinX, F2.mnMinY, F2.mnMaxX, F2.mnMaxY, false);
+            DeviceFrameGuard d1(ctx, p1.h), d2(ctx, p2.h);
+            const int n1 = F1.N;
+            std::vector<float> prev((size_t)n1 * 2);
+            for (int i = 0; i < n1; i++) { prev[2 * i] = vbPrevMatched[i].x; prev[2 * i + 1] = vbPrevMatched[i].y; }
+            std::vector<int32_t> m12(n1 > 0 ? n1 : 1);
+            int32_t nmatches = 0;
+            check(orbgpu_search_for_initialization(ctx, d1.f, d2.f, prev.data(), windowSize, mfNNratio, mbCheckOrientation ? 1 : 0,
+                                                   m12.data(), &nmatches));
+            vnMatches12.assign(m12.begin(), m12.begin() + n1); // vnMatches12 = vector<int>(N1, -1) then filled (:739)
+            for (int i = 0; i < n1; i++) { vbPrevMatched[i].x = prev[2 * i]; vbPrevMatched[i].y = prev[2 * i + 1]; }
+            return nmatches;
+        }
+
+        // ORBmatcher.h:44 (ORBmatcher.cc:44-242), monocular / RGB-D path (F.Nleft == -1)
+        int SearchByProjection(FrameT &F, const std::vector<MapPointT *> &vpMapPoints, const float th = 3, const bool bFarPoints = false,
+                               const float thFarPoints = 50.0f)
+        {
+            if (F.Nleft != -1) throw std::runtime_error("orbmatch_b200: stereo-fisheye (Nleft != -1) path is not on the GPU hot path");
+            orbgpu_ctx *ctx = thread_context();
+            PackedFrame pf;
+            bool any_right = false;
+            for (int i = 0; i < F.N && !any_right; i++) any_right = F.mvuRight[i] > 0;
+            pf.pack(F, F.mnMinX, F.mnMinY, F.mnMaxX, F.mnMaxY, any_right);
+            DeviceFrameGuard df(ctx, pf.h);
+            const int M = (int)vpMapPoints.size();
+            std::vector<uint8_t> desc((size_t)M * 32), in_view(M), bad(M);
+            std::vector<float> proj((size_t)M * 2), xr(M), cosv(M), depth(M);
+            std::vector<int32_t> level(M), nobs(M);
+            for (int i = 0; i < M; i++)
+            {
+                MapPointT *p = vpMapPoints[i];
+                in_view[i] = p->mbTrackInView ? 1 : 0;
+                bad[i] = p->isBad() ? 1 : 0;
+                proj[2 * i] = p->mTrackProjX; proj[2 * i + 1] = p->mTrackProjY;
+                xr[i] = p->mTrackProjXR; cosv[i] = p->mTrackViewCos; depth[i] = p->mTrackDepth;
+                level[i] = p->mnTrackScaleLevel; nobs[i] = p->Observations();
+                std::memcpy(&desc[(size_t)i * 32], p->GetDescriptor().template ptr<uint8_t>(), 32);
+            }
+            orbgpu_mappoints_host mh;
+            std::memset(&mh, 0, sizeof(mh));
+            mh.n = M; mh.desc = desc.data(); mh.proj_xy = proj.data(); mh.proj_xr = xr.data(); mh.scale_level = level.data();
+            mh.view_cos = cosv.data(); mh.depth = depth.data(); mh.in_view = in_view.data(); mh.bad = bad.data(); mh.n_obs = nobs.data();
+            std::vector<int32_t> prior(F.N > 0 ? F.N : 1, 0), kp_mp(F.N > 0 ? F.N : 1, -1);
+            for (int i = 0; i < F.N; i++)
+                if (F.mvpMapPoints[i]) prior[i] = F.mvpMapPoints[i]->Observations();
+            int32_t nmatches = 0;
+            check(orbgpu_search_by_projection_local(ctx, df.f, &mh, th, bFarPoints ? 1 : 0, thFarPoints, mfNNratio, prior.data(),
+                                                    kp_mp.data(), &nmatches));
+            for (int i = 0; i < F.N; i++)
+                if (kp_mp[i] >= 0) F.mvpMapPoints[i] = vpMapPoints[kp_mp[i]]; // :156
+            return nmatches;
+        }
+
+        // ORBmatcher.h:65 (ORBmatcher.cc:262-496)
+        int SearchByBoW(KeyFrameT *pKF, FrameT &F, std::vector<MapPointT *> &vpMapPointMatches)
+        {
+            orbgpu_ctx *ctx = thread_context();
+            const std::vector<MapPointT *> vpMapPointsKF = pKF->GetMapPointMatches();
+            PackedFrame pk, pf;
+            pk.pack(*pKF, (float)pKF->mnMinX, (float)pKF->mnMinY, (float)pKF->mnMaxX, (float)pKF->mnMaxY, false);
+            pf.pack(F, F.mnMinX, F.mnMinY, F.mnMaxX, F.mnMaxY, false);
+            DeviceFrameGuard dk(ctx, pk.h), df(ctx, pf.h);
+            std::vector<uint8_t> valid(pKF->N > 0 ? pKF->N : 1, 0);
+            for (int i = 0; i < pKF->N; i++) valid[i] = (vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad()) ? 1 : 0; // :311-315
+            std::vector<int32_t> m(F.N > 0 ? F.N : 1, -1);
+            int32_t nmatches = 0;
+            check(orbgpu_search_by_bow_kf_f(ctx, dk.f, df.f, valid.data(), mfNNratio, mbCheckOrientation ? 1 : 0, m.data(), &nmatches));
+            vpMapPointMatches = std::vector<MapPointT *>(F.N, static_cast<MapPointT *>(NULL)); // :268
+            for (int i = 0; i < F.N; i++)
+                if (m[i] >= 0) vpMapPointMatches[i] = vpMapPointsKF[m[i]]; // :398
+            return nmatches;
+        }
+
+        // ORBmatcher.h:66 (ORBmatcher.cc:890-1043)
+        int SearchByBoW(KeyFrameT *pKF1, KeyFrameT *pKF2, std::vector<MapPointT *> &vpMatches12)
+        {
+            orbgpu_ctx *ctx = thread_context();
+            const std::vector<MapPointT *> vp1 = pKF1->GetMapPointMatches(), vp2 = pKF2->GetMapPointMatches();
+            PackedFrame p1, p2;
+            p1.pack(*pKF1, (float)pKF1->mnMinX, (float)pKF1->mnMinY, (float)pKF1->mnMaxX, (float)pKF1->mnMaxY, false);
+            p2.pack(*pKF2, (float)pKF2->mnMinX, (float)pKF2->mnMinY, (float)pKF2->mnMaxX, (float)pKF2->mnMaxY, false);
+            DeviceFrameGuard d1(ctx, p1.h), d2(ctx, p2.h);
+            std::vector<uint8_t> v1(pKF1->N > 0 ? pKF1->N : 1, 0), v2(pKF2->N > 0 ? pKF2->N : 1, 0);
+            for (int i = 0; i < pKF1->N; i++) v1[i] = (vp1[i] && !vp1[i]->isBad()) ? 1 : 0;
+            for (int i = 0; i < pKF2->N; i++) v2[i] = (vp2[i] && !vp2[i]->isBad()) ? 1 : 0;
+            std::vector<int32_t> m(pKF1->N > 0 ? pKF1->N : 1, -1);
+            int32_t nmatches = 0;
+            check(orbgpu_search_by_bow_kf_kf(ctx, d1.f, d2.f, v1.data(), v2.data(), mfNNratio, mbCheckOrientation ? 1 : 0, m.data(), &nmatches));
+            vpMatches12 = std::vector<MapPointT *>(vp1.size(), static_cast<MapPointT *>(NULL)); // :904
+            for (int i = 0; i < pKF1->N; i++)
+                if (m[i] >= 0) vpMatches12[i] = vp2[m[i]]; // :989
+            return nmatches;
+        }
+
+        // ORBmatcher.h:72 (ORBmatcher.cc:1045-1328), monocular pinhole path (mpCamera2 == NULL).
+        // The pose algebra (epipole, R12, t12, F12) is evaluated HERE with the host's own Sophus / Eigen, exactly as the
+        // reference does at :1053-1071 and Pinhole.cpp:194-197, and handed to the GPU as inputs.
+        template <class Vec3 = void>
+        int SearchForTriangulation(KeyFrameT *pKF1, KeyFrameT *pKF2, std::vector<std::pair<size_t, size_t>> &vMatchedPairs,
+                                   const bool bOnlyStereo, const bool bCoarse = false)
+        {
+            if (pKF1->mpCamera2 || pKF2->mpCamera2) throw std::runtime_error("orbmatch_b200: two-camera rigs are not on the GPU hot path");
+            orbgpu_ctx *ctx = thread_context();
+            auto T1w = pKF1->GetPose();
+            auto T2w = pKF2->GetPose();
+            auto Tw2 = pKF2->GetPoseInverse();
+            auto Cw = pKF1->GetCameraCenter();
+            auto C2 = T2w * Cw;
+            auto epv = pKF2->mpCamera->project(C2);
+            auto T12 = T1w * Tw2;
+            auto R12 = T12.rotationMatrix();
+            auto t12 = T12.translation();
+            // Pinhole.cpp:194-197
+            auto t12x = hat(t12, R12);
+            auto K1 = pKF1->mpCamera->toK_();
+            auto K2 = pKF2->mpCamera->toK_();
+            auto F12 = K1.transpose().inverse() * t12x * R12 * K2.inverse();
+            float ep[2] = {epv(0), epv(1)}, f12[9];
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) f12[3 * r + c] = F12(r, c);
+
+            // a kfset has a uniform feature count: the smaller keyframe is padded with features that carry a map
+            // point (has_mp = 1) and no vocabulary node, which the search skips (:1129, :1165)
+            const int n = pKF1->N > pKF2->N ? pKF1->N : pKF2->N;
+            std::vector<uint8_t> desc((size_t)2 * n * 32, 0), has_mp((size_t)2 * n, 1);
+            std::vector<float> xy((size_t)4 * n), angle((size_t)2 * n), ur((size_t)2 * n);
+            std::vector<int32_t> octave((size_t)2 * n);
+            std::vector<uint32_t> node((size_t)2 * n, 0xFFFFFFFFu);
+            KeyFrameT *kfs[2] = {pKF1, pKF2};
+            bool any_right = false;
+            for (int k = 0; k < 2; k++)
+            {
+                KeyFrameT *K = kfs[k];
+                for (int i = 0; i < K->N; i++)
+                {
+                    const size_t o = (size_t)k * n + i;
+                    std::memcpy(&desc[o * 32], K->mDescriptors.row(i).template ptr<uint8_t>(), 32);
+                    xy[2 * o] = K->mvKeysUn[i].pt.x; xy[2 * o + 1] = K->mvKeysUn[i].pt.y;
+                    octave[o] = K->mvKeysUn[i].octave; angle[o] = K->mvKeysUn[i].angle;
+                    has_mp[o] = K->GetMapPoint(i) ? 1 : 0;
+                    ur[o] = K->mvuRight[i];
+                    any_right = any_right || K->mvuRight[i] >= 0;
+                }
+                for (const auto &kv : K->mFeatVec)
+                    for (unsigned f : kv.second) node[(size_t)k * n + f] = kv.first;
+            }
+            std::vector<float> sf(pKF2->mvScaleFactors.begin(), pKF2->mvScaleFactors.end()), s2(pKF2->mvLevelSigma2.begin(), pKF2->mvLevelSigma2.end());
+            orbgpu_kfset_host sh;
+            std::memset(&sh, 0, sizeof(sh));
+            sh.n_kf = 2; sh.n_feat = n; sh.desc = desc.data(); sh.kp_xy = xy.data(); sh.octave = octave.data(); sh.angle = angle.data();
+            sh.has_mp = has_mp.data(); sh.u_right = any_right ? ur.data() : nullptr; sh.node_id = node.data();
+            sh.n_levels = (int32_t)sf.size(); sh.scale_factors = sf.data(); sh.level_sigma2 = s2.data();
+            orbgpu_kfset *set = nullptr;
+            check(orbgpu_kfset_upload(ctx, &sh, &set));
+            const int32_t k1 = 0, k2 = 1;
+            std::vector<int32_t> m(n > 0 ? n : 1, -1);
+            int32_t nmatches = 0;
+            const int rc = orbgpu_search_for_triangulation_batch(ctx, set, 1, &k1, &k2, ep, f12, bOnlyStereo ? 1 : 0, bCoarse ? 1 : 0,
+                                                                 mbCheckOrientation ? 1 : 0, m.data(), &nmatches);
+            orbgpu_kfset_destroy(set);
+            check(rc);
+            vMatchedPairs.clear(); // :1317-1325
+            vMatchedPairs.reserve(nmatches);
+            for (int i = 0; i < pKF1->N; i++)
+                if (m[i] >= 0) vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)m[i]));
+            return nmatches;
+        }
+
+    protected:
+        // Sophus::SO3f::hat(t12) written against the matrix type of R12 (so that no Sophus header is needed here)
+        template <class V, class Mtx>
+        static Mtx hat(const V &w, const Mtx &like)
+        {
+            Mtx O = like;
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) O(r, c) = 0.f;
+            O(0, 1) = -w(2); O(0, 2) = w(1);
+            O(1, 0) = w(2);  O(1, 2) = -w(0);
+            O(2, 0) = -w(1); O(2, 1) = w(0);
+            return O;
+        }
+
+        float mfNNratio;
+        bool mbCheckOrientation;
+    };
+} // namespace orbgpu
