@@ -138,6 +138,12 @@ struct orbgpu_kfset {
     uint32_t *kf_node_ids = nullptr; // [n_kf][n_feat]
     int32_t *kf_node_off = nullptr;  // [n_kf][n_feat+1]
     int32_t *kf_feat = nullptr;      // [n_kf][n_feat] feature ids grouped by node, ascending inside
+    // node-ordered copies of the map-point-free features: one contiguous, coalesced read per keyframe
+    uint4 *desc_csr = nullptr;       // [n_kf][n_feat][2] descriptors in CSR slot order
+    int4 *kp_csr = nullptr;          // [n_kf][n_feat] {x bits, y bits, octave, feature id} in CSR slot order
+    int32_t *kf_n_free = nullptr;    // [n_kf] number of CSR slots
+    int max_free = 0;                // max over keyframes (sizes the shared-memory staging)
+    int max_nodes = 0;
 };
 
 struct orbgpu_db {

@@ -8,11 +8,18 @@
 // (:1180) makes the LAST such candidate win ties, and node lists are ascending in feature id, so the
 // winner is the lexicographic minimum of (dist, -idx2).
 //
-// HBM layout: all keyframes of a batch live in one kfset (descriptors as packed uint4 pairs,
-// float2 keypoints, octave, angle, map-point mask, node id per feature) plus a per-keyframe CSR of
-// the map-point-free features grouped by node (built once at upload by a per-keyframe bitonic sort).
-// One CTA per pair; one warp per shared node; the n1 x n2 candidate pairs of a node are flattened
-// over the lanes; survivors (rare: planted matches) reduce into shared memory with atomicMin.
+// HBM layout: all keyframes of a batch live in one kfset.  At upload a per-keyframe bitonic sort builds
+// the CSR (by node id) of the map-point-free features AND node-ordered copies of their descriptors
+// (`desc_csr`) and keypoints (`kp_csr`), so that a pair reads two contiguous spans.
+// One CTA per pair:
+//   phase A  cp.async the two descriptor spans into shared memory (coalesced 16-byte chunks, all loads
+//            in flight at once; 16-byte chunk index XOR-swizzled so that 32-byte rows read by
+//            consecutive lanes are bank-conflict free);
+//   phase B  one warp per shared node (binary-search join of the two sorted node lists); the n1 x n2
+//            candidate pairs of the node are flattened over the lanes; XOR+POPC from shared memory;
+//            survivors (rare: planted matches) run the fp32 gates and atomicMin a packed key into
+//            shared memory;
+//   phase C  optional rotation histogram + cull, coalesced write of the match row, match count.
 #include <algorithm>
 #include <cstring>
 
@@ -24,18 +31,21 @@ constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
 constexpr uint32_t NODE_NONE = 0xFFFFFFFFu;
 constexpr int TRI_THREADS = 256;
 
-// one block per keyframe: CSR (by node id) of the features WITHOUT a map point
+// one block per keyframe: CSR (by node id) of the features WITHOUT a map point + node-ordered copies
 __global__ void __launch_bounds__(1024)
 kfset_csr_kernel(int n_feat, int cap, const uint32_t *__restrict__ node_id, const uint8_t *__restrict__ has_mp,
+                 const uint4 *__restrict__ desc, const float2 *__restrict__ xy, const int32_t *__restrict__ octave,
                  int32_t *__restrict__ kf_n_nodes, uint32_t *__restrict__ kf_node_ids, int32_t *__restrict__ kf_node_off,
-                 int32_t *__restrict__ kf_feat)
+                 int32_t *__restrict__ kf_feat, uint4 *__restrict__ desc_csr, int4 *__restrict__ kp_csr,
+                 int32_t *__restrict__ kf_n_free, int32_t *__restrict__ max_free)
 {
     extern __shared__ unsigned long long keys[]; // [cap]
-    __shared__ int s_m, s_groups;
+    __shared__ int s_m;
+    __shared__ int warp_sums[32];
     const int kf = blockIdx.x, t = threadIdx.x;
     const uint32_t *nid = node_id + (size_t)kf * n_feat;
     const uint8_t *mp = has_mp + (size_t)kf * n_feat;
-    if (t == 0) { s_m = 0; s_groups = 0; }
+    if (t == 0) s_m = 0;
     __syncthreads();
     int valid = 0;
     for (int i = t; i < cap; i += blockDim.x) {
@@ -63,17 +73,22 @@ kfset_csr_kernel(int n_feat, int cap, const uint32_t *__restrict__ node_id, cons
     uint32_t *ids = kf_node_ids + (size_t)kf * n_feat;
     int32_t *off = kf_node_off + (size_t)kf * (n_feat + 1);
     int32_t *feat = kf_feat + (size_t)kf * n_feat;
-    // group heads -> ordinal by counting heads before i (serial per thread chunk + block scan via atomics on ordered chunks)
-    // simple two-pass: thread t owns a contiguous chunk
+    // node-ordered copies
+    for (int i = t; i < m; i += blockDim.x) {
+        const int f = (int)(keys[i] & 0xFFFFFFFFull);
+        feat[i] = f;
+        const size_t src = (size_t)kf * n_feat + f, dst = (size_t)kf * n_feat + i;
+        desc_csr[2 * dst] = desc[2 * src];
+        desc_csr[2 * dst + 1] = desc[2 * src + 1];
+        const float2 p = xy[src];
+        kp_csr[dst] = make_int4(__float_as_int(p.x), __float_as_int(p.y), octave[src], f);
+    }
+    // group heads: thread t owns a contiguous chunk of the sorted keys
     const int per = (m + blockDim.x - 1) / blockDim.x;
     const int s = min(m, t * per), e = min(m, s + per);
     int heads = 0;
-    for (int i = s; i < e; i++) {
-        feat[i] = (int32_t)(keys[i] & 0xFFFFFFFFull);
+    for (int i = s; i < e; i++)
         if (i == 0 || (uint32_t)(keys[i] >> 32) != (uint32_t)(keys[i - 1] >> 32)) heads++;
-    }
-    // exclusive scan of heads over threads
-    __shared__ int warp_sums[32];
     int incl = heads;
     for (int o = 1; o < 32; o <<= 1) {
         const int u = __shfl_up_sync(FULL_MASK, incl, o);
@@ -101,14 +116,14 @@ kfset_csr_kernel(int n_feat, int cap, const uint32_t *__restrict__ node_id, cons
     if (t == 0) {
         off[total] = m;
         kf_n_nodes[kf] = total;
+        kf_n_free[kf] = m;
+        atomicMax(max_free, m);
+        atomicMax(max_free + 1, total);
     }
 }
 
 struct KfSetView {
     int n_kf, n_feat;
-    const uint4 *desc;
-    const float2 *xy;
-    const int32_t *octave;
     const float *angle;
     const float *u_right;
     const float *scale_factors;
@@ -116,7 +131,9 @@ struct KfSetView {
     const int32_t *kf_n_nodes;
     const uint32_t *kf_node_ids;
     const int32_t *kf_node_off;
-    const int32_t *kf_feat;
+    const uint4 *desc_csr;
+    const int4 *kp_csr;
+    const int32_t *kf_n_free;
 };
 
 // Pinhole::epipolarConstrain (Pinhole.cpp:203-218) with the pair's F12 (row-major)
@@ -132,104 +149,173 @@ __device__ __forceinline__ bool epipolar_ok(const float *F, float x1, float y1, 
     return (double)dsqr < __dmul_rn(3.84, (double)unc); // double compare (:218)
 }
 
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+// 16-byte chunk c (= 2*row + half) -> swizzled chunk: rows 4..7 of every 8 swap their halves, so that 8 consecutive
+// rows read with LDS.128 touch all 32 banks exactly once
+__device__ __forceinline__ int swz(int c) { return c ^ ((c >> 3) & 1); }
+
+constexpr int SURV_CAP = 2048;
+
+// epipole gate (:1191-1203) + epipolar test (:1246) of one surviving candidate, then the (dist, -idx2) reduction
+__device__ __forceinline__ void gate_survivor(uint32_t ent, const int4 *__restrict__ kp1, const int4 *__restrict__ kp2,
+                                              const float *ur1, const float *ur2, const float *sEp, const float *sF,
+                                              const float *__restrict__ scale_factors, const float *__restrict__ level_sigma2,
+                                              int coarse, uint32_t *sBest)
+{
+    const int c1 = (int)(ent & 0x1FFF), c2 = (int)((ent >> 13) & 0x1FFF), dist = (int)(ent >> 26);
+    const int4 q2 = kp2[c2];
+    const int4 q1 = kp1[c1];
+    const float x2 = __int_as_float(q2.x), y2 = __int_as_float(q2.y);
+    bool st1 = false, st2 = false;
+    if (ur1) {
+        st1 = ur1[q1.w] >= 0.f;
+        st2 = ur2[q2.w] >= 0.f;
+    }
+    if (!st1 && !st2) {
+        const float dx = __fsub_rn(sEp[0], x2), dy = __fsub_rn(sEp[1], y2);
+        if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, scale_factors[q2.z])) return;
+    }
+    if (!coarse && !epipolar_ok(sF, __int_as_float(q1.x), __int_as_float(q1.y), x2, y2, level_sigma2[q2.z])) return;
+    atomicMin(&sBest[c1], ((uint32_t)dist << 20) | (0xFFFFFu - (uint32_t)q2.w));
+}
+
+template <bool HAS_RIGHT>
 __global__ void __launch_bounds__(TRI_THREADS)
-triangulation_pairs_kernel(KfSetView s, int n_pairs, const int32_t *__restrict__ kf1, const int32_t *__restrict__ kf2,
+triangulation_pairs_kernel(KfSetView s, int n_pairs, int max_free, int max_nodes, const int32_t *__restrict__ kf1, const int32_t *__restrict__ kf2,
                            const float *__restrict__ ep, const float *__restrict__ f12, int only_stereo, int coarse, int check_ori,
                            int32_t *__restrict__ matches12, int32_t *__restrict__ nmatches, unsigned long long *__restrict__ counters)
 {
-    extern __shared__ uint32_t sm_best[]; // [n_feat] keys, then [n_feat] bytes of histogram bins
+    extern __shared__ uint4 sm_raw[];
+    uint4 *sD1 = sm_raw;                      // [max_free][2] swizzled
+    uint4 *sD2 = sm_raw + 2 * (size_t)max_free;
+    uint32_t *sBest = (uint32_t *)(sm_raw + 4 * (size_t)max_free); // [max_free] key per CSR slot of keyframe 1
+    int4 *sNode = (int4 *)(sBest + max_free);                      // [max_nodes] {s1, n1f, s2, n2f} of the joined nodes
+    uint8_t *sBin = (uint8_t *)(sNode + max_nodes);                // [max_free]
     __shared__ int hist[ORBGPU_HISTO_LENGTH];
     __shared__ int ind[3];
     __shared__ float sF[9];
     __shared__ float sEp[2];
-    __shared__ int s_count;
+    __shared__ int s_count, s_nsurv;
+    __shared__ uint32_t sSurv[SURV_CAP];
     const int p = blockIdx.x;
     if (p >= n_pairs) return;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarps = TRI_THREADS / 32;
     const int n = s.n_feat;
-    uint8_t *sm_bin = (uint8_t *)(sm_best + n);
     const int k1 = kf1[p], k2 = kf2[p];
-    for (int i = t; i < n; i += TRI_THREADS) sm_best[i] = KEY_NONE;
+    const int m1 = s.kf_n_free[k1], m2 = s.kf_n_free[k2];
+    const uint4 *g1 = s.desc_csr + (size_t)k1 * n * 2, *g2 = s.desc_csr + (size_t)k2 * n * 2;
+    // ---- phase A: stage both descriptor spans (all chunks in flight)
+    for (int c = t; c < 2 * m1; c += TRI_THREADS) cp_async16(&sD1[swz(c)], &g1[c]);
+    for (int c = t; c < 2 * m2; c += TRI_THREADS) cp_async16(&sD2[swz(c)], &g2[c]);
+    asm volatile("cp.async.commit_group;\n" ::);
+    int32_t *row = matches12 + (size_t)p * n;
+    for (int i = t; i < n; i += TRI_THREADS) row[i] = -1; // :1092 vMatches12(N, -1)
+    for (int i = t; i < m1; i += TRI_THREADS) sBest[i] = KEY_NONE;
     if (t < ORBGPU_HISTO_LENGTH) hist[t] = 0;
     if (t < 9) sF[t] = f12[9 * (size_t)p + t];
     if (t < 2) sEp[t] = ep[2 * (size_t)p + t];
-    if (t == 0) s_count = 0;
-    __syncthreads();
-
-    const uint4 *desc1 = s.desc + (size_t)k1 * n * 2, *desc2 = s.desc + (size_t)k2 * n * 2;
-    const float2 *xy1 = s.xy + (size_t)k1 * n, *xy2 = s.xy + (size_t)k2 * n;
-    const int32_t *oct2 = s.octave + (size_t)k2 * n;
+    if (t == 0) { s_count = 0; s_nsurv = 0; }
+    const int4 *kp1 = s.kp_csr + (size_t)k1 * n, *kp2 = s.kp_csr + (size_t)k2 * n;
     const float *ur1 = s.u_right ? s.u_right + (size_t)k1 * n : nullptr, *ur2 = s.u_right ? s.u_right + (size_t)k2 * n : nullptr;
     const int nn1 = s.kf_n_nodes[k1], nn2 = s.kf_n_nodes[k2];
     const uint32_t *ids1 = s.kf_node_ids + (size_t)k1 * n, *ids2 = s.kf_node_ids + (size_t)k2 * n;
     const int32_t *off1 = s.kf_node_off + (size_t)k1 * (n + 1), *off2 = s.kf_node_off + (size_t)k2 * (n + 1);
-    const int32_t *feat1 = s.kf_feat + (size_t)k1 * n, *feat2 = s.kf_feat + (size_t)k2 * n;
 
-    unsigned long long ncmp = 0;
-    for (int a = warp; a < nn1; a += nwarps) {
+    // ---- join: thread a looks node a of keyframe 1 up in keyframe 2's sorted node list (merge-join :1113-1292)
+    for (int a = t; a < nn1; a += TRI_THREADS) {
         const uint32_t nid = ids1[a];
-        int lo = 0, hi = nn2; // merge-join (:1113-1292) == lookup in the other sorted node list
+        int lo = 0, hi = nn2;
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
             if (ids2[mid] < nid) lo = mid + 1; else hi = mid;
         }
-        if (lo >= nn2 || ids2[lo] != nid) continue;
-        const int s1 = off1[a], n1f = off1[a + 1] - s1;
-        const int s2 = off2[lo], n2f = off2[lo + 1] - s2;
-        const int total = n1f * n2f;
-        for (int tp = lane; tp < total; tp += 32) {
-            const int i1 = tp / n2f, i2 = tp - i1 * n2f;
-            const int idx1 = feat1[s1 + i1], idx2 = feat2[s2 + i2];
-            const bool st1 = ur1 ? (ur1[idx1] >= 0.f) : false; // :1134
-            const bool st2 = ur2 ? (ur2[idx2] >= 0.f) : false; // :1168
-            if (only_stereo && (!st1 || !st2)) continue;       // :1136-1138, :1170-1172
-            const int dist = ham256(desc1[2 * idx1], desc1[2 * idx1 + 1], desc2[2 * idx2], desc2[2 * idx2 + 1]);
-            ncmp++;
-            if (dist > ORBGPU_TH_LOW) continue; // :1180 (bestDist starts at TH_LOW)
-            const float2 p2 = xy2[idx2];
-            const int o2 = oct2[idx2];
-            if (!st1 && !st2) { // :1191-1203 epipole gate
-                const float dx = __fsub_rn(sEp[0], p2.x), dy = __fsub_rn(sEp[1], p2.y);
-                if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, s.scale_factors[o2])) continue;
-            }
-            if (!coarse) { // :1246
-                const float2 p1 = xy1[idx1];
-                if (!epipolar_ok(sF, p1.x, p1.y, p2.x, p2.y, s.level_sigma2[o2])) continue;
-            }
-            atomicMin(&sm_best[idx1], ((uint32_t)dist << 20) | (0xFFFFFu - (uint32_t)idx2));
+        int4 e = make_int4(0, 0, 0, 0);
+        if (lo < nn2 && ids2[lo] == nid) {
+            const int s1 = off1[a], s2 = off2[lo];
+            e = make_int4(s1, off1[a + 1] - s1, s2, off2[lo + 1] - s2);
         }
+        sNode[a] = e;
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
+
+    // ---- phase B
+    unsigned long long ncmp = 0;
+    for (int a = warp; a < nn1; a += nwarps) {
+        const int4 e = sNode[a];
+        const int s1 = e.x, n1f = e.y, s2 = e.z, n2f = e.w;
+        if (n2f == 0 || n1f == 0 || (only_stereo && !HAS_RIGHT)) continue;
+        // the n1f x n2f candidate pairs of the node are flattened over the lanes: pair index tp = lane, lane+32, ...
+        // (i1, i2) = (tp / n2f, tp % n2f) is advanced incrementally (one division per node); trip counts are
+        // warp-uniform so that the warp stays converged from one node to the next
+        const int total = n1f * n2f;
+        const int q32 = 32 / n2f, r32 = 32 - q32 * n2f;
+        int i1 = lane / n2f, i2 = lane - i1 * n2f;
+        for (int tp0 = 0; tp0 < total; tp0 += 32) {
+            bool ok = (tp0 + lane) < total;
+            const int c1 = s1 + (ok ? i1 : 0), c2 = s2 + (ok ? i2 : 0); // CSR slots
+            if (HAS_RIGHT) {
+                const bool st1 = ur1[kp1[c1].w] >= 0.f, st2 = ur2[kp2[c2].w] >= 0.f; // :1134, :1168
+                if (only_stereo && (!st1 || !st2)) ok = false;                        // :1136-1138, :1170-1172
+            }
+            // first 128 bits; a random pair is already above TH_LOW here 99 % of the time
+            int dist = ham128(sD1[swz(2 * c1)], sD2[swz(2 * c2)]);
+            ncmp += ok ? 1 : 0;
+            if (__any_sync(FULL_MASK, ok && dist <= ORBGPU_TH_LOW)) {
+                dist += ham128(sD1[swz(2 * c1 + 1)], sD2[swz(2 * c2 + 1)]);
+                if (ok && dist <= ORBGPU_TH_LOW) { // :1180 (bestDist starts at TH_LOW); rare: planted matches only
+                    // the fp32 gates need keypoint data from global memory: defer them so that all survivors of the
+                    // pair are gated in parallel instead of one lane at a time
+                    const int slot = atomicAdd(&s_nsurv, 1);
+                    const uint32_t ent = (uint32_t)c1 | ((uint32_t)c2 << 13) | ((uint32_t)dist << 26);
+                    if (slot < SURV_CAP) sSurv[slot] = ent;
+                    else gate_survivor(ent, kp1, kp2, ur1, ur2, sEp, sF, s.scale_factors, s.level_sigma2, coarse, sBest);
+                }
+            }
+            i1 += q32;
+            i2 += r32;
+            if (i2 >= n2f) { i2 -= n2f; i1++; }
+        }
+        __syncwarp();
     }
     __syncthreads();
+    {
+        const int ns = min(s_nsurv, SURV_CAP);
+        for (int i = t; i < ns; i += TRI_THREADS)
+            gate_survivor(sSurv[i], kp1, kp2, ur1, ur2, sEp, sF, s.scale_factors, s.level_sigma2, coarse, sBest);
+    }
+    __syncthreads();
+    // ---- phase C
     const float *ang1 = s.angle + (size_t)k1 * n, *ang2 = s.angle + (size_t)k2 * n;
     int mine = 0;
     if (check_ori) { // :1266-1277
-        for (int i = t; i < n; i += TRI_THREADS) {
-            const uint32_t key = sm_best[i];
+        for (int c = t; c < m1; c += TRI_THREADS) {
+            const uint32_t key = sBest[c];
             int bin = 255;
             if (key != KEY_NONE) {
                 const int idx2 = (int)(0xFFFFFu - (key & 0xFFFFFu));
-                bin = rot_bin(ang1[i], ang2[idx2]);
+                bin = rot_bin(ang1[kp1[c].w], ang2[idx2]);
                 if (bin >= 0 && bin < ORBGPU_HISTO_LENGTH) atomicAdd(&hist[bin], 1); else bin = 254;
             }
-            sm_bin[i] = (uint8_t)bin;
+            sBin[c] = (uint8_t)bin;
         }
         __syncthreads();
         if (t == 0) three_maxima(hist, ORBGPU_HISTO_LENGTH, ind[0], ind[1], ind[2]);
         __syncthreads();
     }
-    int32_t *row = matches12 + (size_t)p * n;
-    for (int i = t; i < n; i += TRI_THREADS) {
-        const uint32_t key = sm_best[i];
-        int m = -1;
-        if (key != KEY_NONE) {
-            m = (int)(0xFFFFFu - (key & 0xFFFFFu));
-            if (check_ori) { // :1295-1314
-                const int b = sm_bin[i];
-                if (b < ORBGPU_HISTO_LENGTH && b != ind[0] && b != ind[1] && b != ind[2]) m = -1;
-            }
+    for (int c = t; c < m1; c += TRI_THREADS) {
+        const uint32_t key = sBest[c];
+        if (key == KEY_NONE) continue;
+        if (check_ori) { // :1295-1314
+            const int b = sBin[c];
+            if (b < ORBGPU_HISTO_LENGTH && b != ind[0] && b != ind[1] && b != ind[2]) continue;
         }
-        if (m >= 0) mine++;
-        row[i] = m;
+        row[kp1[c].w] = (int)(0xFFFFFu - (key & 0xFFFFFu));
+        mine++;
     }
     for (int o = 16; o; o >>= 1) {
         mine += __shfl_xor_sync(FULL_MASK, mine, o);
@@ -247,9 +333,10 @@ KfSetView kfset_view(const orbgpu_kfset *s)
 {
     KfSetView v;
     v.n_kf = s->n_kf; v.n_feat = s->n_feat;
-    v.desc = s->desc; v.xy = s->xy; v.octave = s->octave; v.angle = s->angle; v.u_right = s->u_right;
+    v.angle = s->angle; v.u_right = s->u_right;
     v.scale_factors = s->scale_factors; v.level_sigma2 = s->level_sigma2;
-    v.kf_n_nodes = s->kf_n_nodes; v.kf_node_ids = s->kf_node_ids; v.kf_node_off = s->kf_node_off; v.kf_feat = s->kf_feat;
+    v.kf_n_nodes = s->kf_n_nodes; v.kf_node_ids = s->kf_node_ids; v.kf_node_off = s->kf_node_off;
+    v.desc_csr = s->desc_csr; v.kp_csr = s->kp_csr; v.kf_n_free = s->kf_n_free;
     return v;
 }
 
@@ -262,6 +349,7 @@ extern "C" void orbgpu_kfset_destroy(orbgpu_kfset *s)
     cudaFree(s->desc); cudaFree(s->xy); cudaFree(s->octave); cudaFree(s->angle); cudaFree(s->has_mp); cudaFree(s->u_right);
     cudaFree(s->node_id); cudaFree(s->scale_factors); cudaFree(s->level_sigma2);
     cudaFree(s->kf_n_nodes); cudaFree(s->kf_node_ids); cudaFree(s->kf_node_off); cudaFree(s->kf_feat);
+    cudaFree(s->desc_csr); cudaFree(s->kp_csr); cudaFree(s->kf_n_free);
     delete s;
 }
 
@@ -295,15 +383,25 @@ extern "C" int orbgpu_kfset_upload(orbgpu_ctx *ctx, const orbgpu_kfset_host *h, 
     CU_TRY(cudaMalloc((void **)&s->kf_node_ids, T * 4));
     CU_TRY(cudaMalloc((void **)&s->kf_node_off, (size_t)h->n_kf * (h->n_feat + 1) * 4));
     CU_TRY(cudaMalloc((void **)&s->kf_feat, T * 4));
+    CU_TRY(cudaMalloc((void **)&s->desc_csr, T * 32));
+    CU_TRY(cudaMalloc((void **)&s->kp_csr, T * 16));
+    CU_TRY(cudaMalloc((void **)&s->kf_n_free, (size_t)h->n_kf * 4 + 256));
+    int32_t *d_max = s->kf_n_free + h->n_kf;
+    CU_TRY(cudaMemsetAsync(d_max, 0, 8, ctx->stream));
     int cap = 1;
     while (cap < h->n_feat) cap <<= 1;
     const size_t smem = (size_t)cap * 8;
     CU_TRY(cudaFuncSetAttribute(kfset_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kfset_csr_kernel<<<h->n_kf, 1024, smem, ctx->stream>>>(h->n_feat, cap, s->node_id, s->has_mp, s->kf_n_nodes, s->kf_node_ids,
-                                                          s->kf_node_off, s->kf_feat);
+    kfset_csr_kernel<<<h->n_kf, 1024, smem, ctx->stream>>>(h->n_feat, cap, s->node_id, s->has_mp, s->desc, s->xy, s->octave, s->kf_n_nodes,
+                                                          s->kf_node_ids, s->kf_node_off, s->kf_feat, s->desc_csr, s->kp_csr, s->kf_n_free,
+                                                          d_max);
     LAUNCH_COUNT(ctx);
     CU_TRY(cudaGetLastError());
+    int32_t mx[2] = {0, 0};
+    CU_TRY(cudaMemcpyAsync(mx, d_max, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(cudaStreamSynchronize(ctx->stream));
+    s->max_free = ((mx[0] > 0 ? mx[0] : 1) + 3) & ~3; // multiple of 4: keeps the int4 node table 16-byte aligned
+    s->max_nodes = mx[1] > 0 ? mx[1] : 1;
     *out = s;
     return ORBGPU_OK;
 }
@@ -318,11 +416,13 @@ extern "C" int orbgpu_search_for_triangulation_batch_dev(orbgpu_ctx *ctx, const 
     CU_TRY(cudaSetDevice(ctx->device));
     CU_TRY(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     if (n_pairs == 0) return ORBGPU_OK;
-    const size_t smem = (size_t)s->n_feat * 5 + 16;
-    if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(triangulation_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    triangulation_pairs_kernel<<<n_pairs, TRI_THREADS, smem, ctx->stream>>>(kfset_view(s), n_pairs, kf1_dev, kf2_dev, ep_dev, f12_dev,
-                                                                           only_stereo, coarse, check_ori, matches12_dev, nmatches_dev,
-                                                                           ctx->d_counters);
+    // 2 x max_free descriptors (32 B) + key (4 B) + histogram bin (1 B) per CSR slot
+    const size_t smem = (size_t)s->max_free * (64 + 4 + 1) + (size_t)s->max_nodes * 16 + 64;
+    if (smem > 227 * 1024) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "keyframes too large for the shared-memory staging");
+    auto kern = s->u_right ? triangulation_pairs_kernel<true> : triangulation_pairs_kernel<false>;
+    if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<n_pairs, TRI_THREADS, smem, ctx->stream>>>(kfset_view(s), n_pairs, s->max_free, s->max_nodes, kf1_dev, kf2_dev, ep_dev, f12_dev,
+                                                     only_stereo, coarse, check_ori, matches12_dev, nmatches_dev, ctx->d_counters);
     LAUNCH_COUNT(ctx);
     CU_TRY(cudaGetLastError());
     return ORBGPU_OK;
