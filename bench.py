@@ -188,7 +188,7 @@ def main():
     ap.add_argument("--nq", type=int, default=NQ_FULL)
     ap.add_argument("--nd", type=int, default=ND_FULL)
     ap.add_argument("--pairs", type=int, default=C4_PAIRS)
-    ap.add_argument("--engine", type=int, default=0, help="knn2 engine: 0 auto, 1 POPC, 2 mma.sync b1, 3 tcgen05")
+    ap.add_argument("--engine", type=int, default=0, help="knn2 engine: 0 auto, 1 POPC, 2 mma.sync b1, 3 tcgen05 1-CTA, 4 tcgen05 2-CTA")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -351,11 +351,11 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        engine = args.engine if args.engine else (3 if getattr(matcher, "TC_DEFAULT", False) else 1)
+        engine = args.engine if args.engine else (4 if getattr(matcher, "TC_DEFAULT", False) else 1)
         per_gpu_units = units_total / world
         kern_s = ms_per_step * 1e-3
         if args.workload == "c5":
-            if engine == 3:
+            if engine >= 3:
                 flops = per_gpu_units * 512.0  # 256 MACs per 256-bit comparison on the +-1 fp8 contraction
                 peak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
                 roof = {"bound": "tensor", "achieved": flops / kern_s / 1e12, "peak": peak, "unit": "TFLOP/s",

@@ -228,7 +228,8 @@ int orbgpu_knn2_ratio_dev(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, cons
                           float nnratio, int32_t *best_idx_dev, int32_t *best_dist_dev, int32_t *second_dist_dev,
                           int32_t *match_dev);
 /* selects the all-pairs engine: 0 = auto, 1 = LOP3+POPC CUDA-core kernel,
- * 2 = mma.sync b1 and.popc, 3 = tcgen05 (+-1 fp8 contraction, TMEM accumulators). */
+ * 2 = mma.sync b1 and.popc, 3 = tcgen05 (+-1 fp8 contraction, TMEM accumulators) one CTA per SM,
+ * 4 = tcgen05 with cta_group::2 SM pairs (what auto resolves to for nq >= 128 and nd >= 1024). */
 int orbgpu_knn2_set_engine(orbgpu_ctx *ctx, int32_t engine);
 
 /* ---- a10: ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:2341-2383) exposed for testing:

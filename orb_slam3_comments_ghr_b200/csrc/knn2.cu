@@ -13,13 +13,14 @@
 //      with cp.async double buffering, broadcast LDS.128 reads.
 //   2  mma.sync m16n8k256 b1 and.popc (ptxas lowers it to IMMA on sm_100a; kept for the bake-off
 //      BASELINE.json asks for).
-//   3  tcgen05 +-1 fp8 contraction with TMEM accumulators (knn2_tc.cu).
+//   3  tcgen05 +-1 fp8 contraction with TMEM accumulators, one CTA per SM (knn2_tc.cu).
+//   4  the same with cta_group::2 (SM pairs, M = 256, N = 256 per MMA) -- the default.
 #include <algorithm>
 
 #include "internal.cuh"
 
 int knn2_tc_run(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const uint4 *q, int32_t th_low, float nnratio, int32_t *best_idx,
-                int32_t *best_dist, int32_t *second_dist, int32_t *match); // knn2_tc.cu
+                int32_t *best_dist, int32_t *second_dist, int32_t *match, bool two_cta); // knn2_tc.cu
 bool knn2_tc_supported();
 
 namespace {
@@ -271,8 +272,8 @@ __global__ void descriptor_distance_kernel(const uint4 *__restrict__ a, const ui
 
 extern "C" int orbgpu_knn2_set_engine(orbgpu_ctx *ctx, int32_t engine)
 {
-    ARG_TRY(ctx != nullptr && engine >= 0 && engine <= 3);
-    if (engine == 3 && !knn2_tc_supported())
+    ARG_TRY(ctx != nullptr && engine >= 0 && engine <= 4);
+    if (engine >= 3 && !knn2_tc_supported())
         return orbgpu_fail(ORBGPU_ERR_INVALID, "tcgen05 engine not built into this library");
     ctx->knn_engine = engine;
     return ORBGPU_OK;
@@ -328,9 +329,9 @@ static KnnPlan knn2_plan(const orbgpu_ctx *ctx, int64_t nq, int64_t nd)
 {
     KnnPlan p;
     p.engine = ctx->knn_engine;
-    if (p.engine == 0) p.engine = knn2_tc_supported() ? 3 : 1;
+    if (p.engine == 0) p.engine = knn2_tc_supported() ? 4 : 1; // auto: 2-CTA tcgen05 engine
     // the tensor engine works on 128-query x 256-database tiles: tiny problems go to the POPC kernel
-    if (p.engine == 3 && (nd < 1024 || nq < 128)) p.engine = 1;
+    if (p.engine >= 3 && (nd < 1024 || nq < 128)) p.engine = 1;
     const int64_t per_tile = (p.engine == 2) ? MMA_WARPS * 16 * MMA_MT : KNN_THREADS * KNN_QPT;
     p.qtiles = std::max<int64_t>(1, (nq + per_tile - 1) / per_tile);
     // enough CTAs for ~4 waves over the SMs; chunk-relative indices must fit the packed key
@@ -358,8 +359,8 @@ static int knn2_launch(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const u
     if (!part_best || !part_second) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
     ctx->last_comparisons = nq * nd;
     if (nq == 0) return ORBGPU_OK;
-    if (p.engine == 3 && nd > 0) // tensor engine: expansion + tcgen05 search + its own merge
-        return knn2_tc_run(ctx, db, nq, q, th_low, nnratio, best_idx, best_dist, second_dist, match);
+    if (p.engine >= 3 && nd > 0) // tensor engines: expansion + tcgen05 search + their own merge (4 = cta_group::2)
+        return knn2_tc_run(ctx, db, nq, q, th_low, nnratio, best_idx, best_dist, second_dist, match, p.engine == 4);
     int n_splits = (int)p.splits;
     if (nd > 0) {
         if (p.engine == 1) {

@@ -136,6 +136,7 @@ struct TcParams {
     uint16_t *out_second; // [n_splits][nq_pad]
     int32_t *out_stage;   // [n_splits][nq_pad] first database row of the winning stage
     int64_t out_stride;
+    int dbg;              // development aid (ORBGPU_TC_DEBUG): 1 = skip the top-2 arithmetic, 2 = also skip the TMEM loads
 };
 
 __device__ __forceinline__ __half2 u2h2(uint32_t u) { return *reinterpret_cast<__half2 *>(&u); }
@@ -190,8 +191,8 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 const int s0 = split * P.stages_per_split, s1 = min(P.total_stages, s0 + P.stages_per_split);
                 for (int s = s0; s < s1; s++) {
                     mbar_wait(smem_u32(&b_empty[sb]), pb ^ 1);
-                    mbar_expect_tx(smem_u32(&b_full[sb]), STAGE_BYTES);
-                    for (int kb = 0; kb < NUM_KB; kb++)
+                    mbar_expect_tx(smem_u32(&b_full[sb]), (P.dbg & 16) ? TILE_BYTES : STAGE_BYTES);
+                    for (int kb = 0; kb < ((P.dbg & 16) ? 1 : NUM_KB); kb++)
                         tma_load_2d(smem_u32(sB + sb * STAGE_BYTES + kb * TILE_BYTES), &map_db, smem_u32(&b_full[sb]), kb * KB_BYTES, s * BN);
                     if (++sb == NS) { sb = 0; pb ^= 1; }
                 }
@@ -218,7 +219,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                         const uint64_t bd = make_desc(smem_u32(sB + sb * STAGE_BYTES + kb * TILE_BYTES));
 #pragma unroll
                         for (int k = 0; k < KB_BYTES / 32; k++) // UMMA K = 32 bytes; advance start address by 32 B >> 4 = 2
-                            tc_mma_f8(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), IDESC, (kb | k) ? 1u : 0u);
+                            tc_mma_f8(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), (P.dbg & 4) ? (((uint32_t)(64 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24)) : ((P.dbg & 8) ? (((uint32_t)(BN >> 3) << 17) | ((uint32_t)(64 >> 4) << 24)) : IDESC), (kb | k) ? 1u : 0u);
                     }
                     tc_commit(smem_u32(&b_empty[sb])); // smem stage reusable once these MMAs retire
                     tc_commit(smem_u32(&t_full[ta]));  // accumulator ready for the epilogue
@@ -252,9 +253,14 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 pt[pi] ^= 1;
                 tc_fence_after();
                 uint32_t r0[32], r1[32];
-                tc_ld_64cols_packed(lane_base + buf * BN, r0);
-                tc_ld_64cols_packed(lane_base + buf * BN + 64, r1);
-                tc_wait_ld();
+                if (!(P.dbg & 2)) {
+                    tc_ld_64cols_packed(lane_base + buf * BN, r0);
+                    tc_ld_64cols_packed(lane_base + buf * BN + 64, r1);
+                    tc_wait_ld();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) { r0[i] = 0; r1[i] = 0; }
+                }
                 // accumulator buffer can be overwritten as soon as the registers hold it
                 tc_fence_before();
                 __syncwarp();
@@ -272,6 +278,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                         r1[i] = *reinterpret_cast<uint32_t *>(&v1);
                     }
                 }
+                if (!(P.dbg & 1)) {
 #pragma unroll
                 for (int i = 0; i < 32; i++) {
                     const __half2 v = u2h2(r0[i]);
@@ -286,6 +293,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     m1 = __hmax2(m1, v);
                     m2 = __hmax2(m2, lo);
                 }
+                } else { m1 = __hmax2(m1, u2h2(r0[0] ^ r1[31])); }
                 const float cm = fmaxf(__low2float(m1), __high2float(m1));
                 if (cm > gmax) { // strictly better: this is the FIRST stage (of this warpgroup) reaching the new maximum
                     gmax = cm;
@@ -341,6 +349,272 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
 }
 
+// =============================================================================================
+// 2-CTA variant (cta_group::2): a cluster of two CTAs (one SM pair) computes a 256-query x 128-row tile per
+// MMA.  Each CTA holds its own 128 query rows (A) and HALF of every database stage (64 rows of B); the
+// leader CTA issues tcgen05.mma.cta_group::2 (M = 256) and the accumulators land in both CTAs' TMEM
+// (rows 0-127 in the leader, 128-255 in the peer).  Versus the 1-CTA kernel this halves the L2->SMEM
+// traffic per SM (16 KB instead of 32 KB per stage) and the shared-memory operand reads per MMA
+// (A 4 KB + B 2 KB instead of 4 + 4), which is what limited the 1-CTA kernel (ncu: 59 % tensor pipe,
+// l1tex tc wavefronts at 59 %, ~5.6 KB/clk of L2 reads chip-wide).
+constexpr int BN2 = 256;                        // database rows per stage of the 2-CTA kernel (UMMA N = 256)
+constexpr int NS2 = 4;                          // B pipeline stages (this CTA's 128 rows = 32 KB each)
+constexpr int NA2 = 2;                          // accumulator buffers (2 x 256 columns = 512)
+constexpr int SMEM2_BYTES = 2 * STAGE_BYTES + NS2 * STAGE_BYTES + 4096 + 1024;
+constexpr uint32_t IDESC2 = ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24); // M = 256, N = 256
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    // relaxed: the accumulator values are already in registers (tcgen05.wait::ld) and the tcgen05 fences order the
+    // TMEM accesses; a release at cluster scope would cost a MEMBAR.ALL.GPU + ERRBAR per stage (ncu: 40 % of samples)
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion is signalled on a barrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_f8_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// top-2 update of one 64-column chunk (32 packed half2 registers); columns >= valid are padding -> -inf
+__device__ __forceinline__ void epi_consume(uint32_t (&r)[32], int base_col, int valid, __half2 &m1, __half2 &m2)
+{
+    const __half2 NEG_INF2 = __half2half2(__ushort_as_half((unsigned short)0xFC00));
+    if (base_col + 64 > valid) {
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            const int c = base_col + 2 * i;
+            __half2 v = u2h2(r[i]);
+            if (c >= valid) v = NEG_INF2; else if (c + 1 >= valid) v = __halves2half2(__low2half(v), __low2half(NEG_INF2));
+            r[i] = *reinterpret_cast<uint32_t *>(&v);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        const __half2 v = u2h2(r[i]);
+        const __half2 lo = __hmin2(m1, v);
+        m1 = __hmax2(m1, v);
+        m2 = __hmax2(m2, lo);
+    }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+knn2_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, TcParams P)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;                        // [2][STAGE_BYTES]    this CTA's 128 query rows
+    uint8_t *sB = smem + 2 * STAGE_BYTES;      // [NS2][STAGE_BYTES]  this CTA's 128 rows of every 256-row stage
+    uint64_t *bars = (uint64_t *)(smem + 2 * STAGE_BYTES + NS2 * STAGE_BYTES);
+    uint64_t *b_full = bars, *b_empty = bars + NS2, *a_full = bars + 2 * NS2, *a_empty = a_full + 2, *t_full = a_empty + 2,
+             *t_empty = t_full + NA2;
+    uint32_t *tmem_slot = (uint32_t *)(t_empty + NA2);
+    uint32_t *sMerge = tmem_slot + 4;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int n_qt2 = (P.n_qtiles + 1) / 2;           // query-tile PAIRS
+    const int n_items = n_qt2 * P.n_splits;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < NS2; i++) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1); }
+        for (int i = 0; i < NA2; i++) { mbar_init(smem_u32(&t_full[i]), 1); mbar_init(smem_u32(&t_empty[i]), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_db) : "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all(); // barriers of both CTAs are initialised before any remote arrive / TMA signal
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs): own A tile + own 128 rows of every B stage =================
+        if (lane == 0) {
+            uint32_t sb = 0, pb = 0;
+            int it_local = 0;
+            for (int item = cluster_id; item < n_items; item += n_clusters, it_local++) {
+                const int qt = 2 * (item % n_qt2) + (int)rank, split = item / n_qt2;
+                const int abuf = it_local & 1;
+                mbar_wait(smem_u32(&a_empty[abuf]), ((it_local >> 1) & 1) ^ 1);
+                const uint32_t afull_leader = mapa(smem_u32(&a_full[abuf]), 0);
+                if (leader) mbar_expect_tx(smem_u32(&a_full[abuf]), 2 * STAGE_BYTES); // both CTAs' A tiles
+                for (int kb = 0; kb < NUM_KB; kb++)
+                    tma_load_2d_2sm(smem_u32(sA + abuf * STAGE_BYTES + kb * TILE_BYTES), &map_q, afull_leader, kb * KB_BYTES, qt * BM);
+                const int s0 = split * P.stages_per_split, s1 = min(P.total_stages, s0 + P.stages_per_split);
+                for (int s = s0; s < s1; s++) {
+                    mbar_wait(smem_u32(&b_empty[sb]), pb ^ 1);
+                    const uint32_t bfull_leader = mapa(smem_u32(&b_full[sb]), 0);
+                    if (leader) mbar_expect_tx(smem_u32(&b_full[sb]), 2 * STAGE_BYTES); // both halves
+                    for (int kb = 0; kb < NUM_KB; kb++)
+                        tma_load_2d_2sm(smem_u32(sB + sb * STAGE_BYTES + kb * TILE_BYTES), &map_db, bfull_leader, kb * KB_BYTES,
+                                        s * BN2 + (int)rank * (BN2 / 2));
+                    if (++sb == NS2) { sb = 0; pb ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (leader && lane == 0) {
+            uint32_t sb = 0, pb = 0, ta = 0, pt = 0;
+            int it_local = 0;
+            for (int item = cluster_id; item < n_items; item += n_clusters, it_local++) {
+                const int split = item / n_qt2;
+                const int abuf = it_local & 1;
+                mbar_wait(smem_u32(&a_full[abuf]), (it_local >> 1) & 1);
+                const int s0 = split * P.stages_per_split, s1 = min(P.total_stages, s0 + P.stages_per_split);
+                for (int s = s0; s < s1; s++) {
+                    mbar_wait(smem_u32(&t_empty[ta]), pt ^ 1); // both CTAs' epilogues drained this accumulator buffer
+                    mbar_wait(smem_u32(&b_full[sb]), pb);       // both halves of the stage landed
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + ta * BN2;
+#pragma unroll
+                    for (int kb = 0; kb < NUM_KB; kb++) {
+                        const uint64_t ad = make_desc(smem_u32(sA + abuf * STAGE_BYTES + kb * TILE_BYTES));
+                        const uint64_t bd = make_desc(smem_u32(sB + sb * STAGE_BYTES + kb * TILE_BYTES));
+#pragma unroll
+                        for (int k = 0; k < KB_BYTES / 32; k++)
+                            tc_mma_f8_2sm(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), IDESC2, (kb | k) ? 1u : 0u);
+                    }
+                    tc_commit_2sm(smem_u32(&b_empty[sb])); // frees the stage in BOTH CTAs
+                    tc_commit_2sm(smem_u32(&t_full[ta]));  // accumulator ready in BOTH CTAs
+                    if (++sb == NS2) { sb = 0; pb ^= 1; }
+                    if (++ta == NA2) { ta = 0; pt ^= 1; }
+                }
+                tc_commit_2sm(smem_u32(&a_empty[abuf]));
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ================= epilogue (both CTAs): thread == query row == TMEM lane; warpgroup g owns buffer g =================
+        const int wg = (warp - EPI_WARP0) >> 2;
+        const int wq = warp & 3;
+        const int row = wq * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16) + wg * BN2;
+        const __half2 NEG_INF2 = __half2half2(__ushort_as_half((unsigned short)0xFC00));
+        const uint32_t tempty_leader = mapa(smem_u32(&t_empty[wg]), 0);
+        uint32_t pt = 0;
+        int stage_counter = 0;
+        for (int item = cluster_id; item < n_items; item += n_clusters) {
+            const int qt = 2 * (item % n_qt2) + (int)rank, split = item / n_qt2;
+            const int s0 = split * P.stages_per_split, s1 = min(P.total_stages, s0 + P.stages_per_split);
+            __half2 m1 = NEG_INF2, m2 = NEG_INF2;
+            float gmax = -1e30f;
+            int best_stage = -1;
+            for (int s = s0; s < s1; s++, stage_counter++) {
+                if ((stage_counter & 1) != wg) continue;
+                mbar_wait(smem_u32(&t_full[wg]), pt);
+                pt ^= 1;
+                tc_fence_after();
+                const int valid = (int)min((int64_t)BN2, P.nd - (int64_t)s * BN2);
+                uint32_t r0[32], r1[32];
+                tc_ld_64cols_packed(lane_base, r0);
+                tc_ld_64cols_packed(lane_base + 64, r1);
+                tc_wait_ld();
+                epi_consume(r0, 0, valid, m1, m2);
+                tc_ld_64cols_packed(lane_base + 128, r0);
+                epi_consume(r1, 64, valid, m1, m2);
+                tc_ld_64cols_packed(lane_base + 192, r1);
+                tc_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_leader); // the leader's barrier counts both CTAs (8 warps)
+                epi_consume(r0, 128, valid, m1, m2);
+                epi_consume(r1, 192, valid, m1, m2);
+                const float cm = fmaxf(__low2float(m1), __high2float(m1));
+                if (cm > gmax) { // strictly better: FIRST stage (of this warpgroup) reaching the new maximum
+                    gmax = cm;
+                    best_stage = s;
+                }
+            }
+            if (wg == 1) {
+                sMerge[row * 4 + 0] = *reinterpret_cast<uint32_t *>(&m1);
+                sMerge[row * 4 + 1] = *reinterpret_cast<uint32_t *>(&m2);
+                sMerge[row * 4 + 2] = __float_as_uint(gmax);
+                sMerge[row * 4 + 3] = (uint32_t)best_stage;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (wg == 0) {
+                const __half2 o1 = u2h2(sMerge[row * 4 + 0]), o2 = u2h2(sMerge[row * 4 + 1]);
+                const float og = __uint_as_float(sMerge[row * 4 + 2]);
+                const int os = (int)sMerge[row * 4 + 3];
+                float v[8] = {__low2float(m1), __high2float(m1), __low2float(m2), __high2float(m2),
+                              __low2float(o1), __high2float(o1), __low2float(o2), __high2float(o2)};
+                float t1 = -1e30f, t2 = -1e30f;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float x = v[i];
+                    const float lo = fminf(t1, x);
+                    t1 = fmaxf(t1, x);
+                    t2 = fmaxf(t2, lo);
+                }
+                int bs = best_stage;
+                if (og > gmax || (og == gmax && os >= 0 && (bs < 0 || os < bs))) bs = os;
+                const int64_t q = (int64_t)qt * BM + row;
+                if (q < P.nq) {
+                    const uint16_t hb = (t1 < -1000.f) ? (uint16_t)0xFFFF : (uint16_t)(128 - (int)t1 / 2);
+                    const uint16_t hs = (t2 < -1000.f) ? (uint16_t)0xFFFF : (uint16_t)(128 - (int)t2 / 2);
+                    const int64_t o = (int64_t)split * P.out_stride + q;
+                    P.out_best[o] = hb;
+                    P.out_second[o] = hs;
+                    P.out_stage[o] = (bs < 0) ? -1 : bs * BN2;
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+    }
+    // ---- teardown: nobody leaves while the pair may still signal its barriers or write its TMEM
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // bits -> fp8 (+1 = 0x38, -1 = 0xB8); one thread per 32-bit word -> 32 output bytes.  Rows >= n are zero (padding).
 __global__ void expand_kernel(const uint32_t *__restrict__ in, int64_t n, int64_t n_pad, uint4 *__restrict__ out)
 {
@@ -364,7 +638,7 @@ __global__ void expand_kernel(const uint32_t *__restrict__ in, int64_t n, int64_
 }
 
 // one warp per query: merge the per-split partials, then recover the first index attaining the minimum
-__global__ void knn2_tc_merge_kernel(const uint4 *__restrict__ q, const uint4 *__restrict__ db, int64_t nq, int64_t nd, int n_splits,
+__global__ void knn2_tc_merge_kernel(const uint4 *__restrict__ q, const uint4 *__restrict__ db, int64_t nq, int64_t nd, int n_splits, int bn,
                                      int64_t stride, const uint16_t *__restrict__ pb, const uint16_t *__restrict__ ps,
                                      const int32_t *__restrict__ pstage, int th_low, float nnratio, int32_t *__restrict__ best_idx,
                                      int32_t *__restrict__ best_dist, int32_t *__restrict__ second_dist, int32_t *__restrict__ match)
@@ -390,7 +664,7 @@ __global__ void knn2_tc_merge_kernel(const uint4 *__restrict__ q, const uint4 *_
         const int64_t st = pstage[(int64_t)win * stride + qi];
         const uint4 qa = q[2 * qi], qb = q[2 * qi + 1];
         int found = 0x7FFFFFFF;
-        for (int j = lane; j < BN; j += 32) {
+        for (int j = lane; j < bn; j += 32) {
             const int64_t r = st + j;
             if (r >= 0 && r < nd && ham256(qa, qb, db[2 * r], db[2 * r + 1]) == bd) found = min(found, (int)r);
         }
@@ -425,13 +699,13 @@ PFN_encodeTiled get_encode()
 }
 
 // rows x 256 bytes, box = 128 bytes x 128 rows, SWIZZLE_128B
-int make_map(CUtensorMap *m, void *base, uint64_t rows)
+int make_map(CUtensorMap *m, void *base, uint64_t rows, uint32_t box_rows)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return orbgpu_fail(ORBGPU_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[2] = {(cuuint64_t)ROW_BYTES, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ROW_BYTES};
-    cuuint32_t box[2] = {(cuuint32_t)KB_BYTES, (cuuint32_t)BM};
+    cuuint32_t box[2] = {(cuuint32_t)KB_BYTES, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -445,17 +719,20 @@ bool knn2_tc_supported() { return true; }
 
 // q, outputs: device pointers.  Runs expansion + tcgen05 search + merge on ctx->stream.
 int knn2_tc_run(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const uint4 *q, int32_t th_low, float nnratio, int32_t *best_idx,
-                int32_t *best_dist, int32_t *second_dist, int32_t *match)
+                int32_t *best_dist, int32_t *second_dist, int32_t *match, bool two_cta)
 {
     const int64_t nd = db->nd;
-    const int64_t nq_pad = (nq + BM - 1) / BM * BM, nd_pad = (nd + BN - 1) / BN * BN;
+    const int bn = two_cta ? BN2 : BN; // database rows per stage
+    const int64_t nq_pad = (nq + 2 * BM - 1) / (2 * BM) * (2 * BM), nd_pad = (nd + bn - 1) / bn * bn;
     const int n_qtiles = (int)(nq_pad / BM);
-    const int total_stages = (int)(nd_pad / BN);
+    const int total_stages = (int)(nd_pad / bn);
     // database splits: each split (expanded: rows x 256 B) should stay L2 resident while every query tile sweeps it
-    int stages_per_split = std::min(total_stages, 1024); // 1024 stages = 128k rows = 32 MiB expanded
+    int stages_per_split = std::min(total_stages, (128 * 1024) / bn); // 128k rows = 32 MiB expanded per split
     int n_splits = (total_stages + stages_per_split - 1) / stages_per_split;
     // not enough items to fill the machine: split finer
-    while (n_splits * n_qtiles < 2 * ctx->sm_count && stages_per_split > 8) {
+    const int n_units = two_cta ? (n_qtiles + 1) / 2 : n_qtiles; // work items per split
+    const int n_workers = two_cta ? ctx->sm_count / 2 : ctx->sm_count;
+    while (n_splits * n_units < 2 * n_workers && stages_per_split > 8) {
         stages_per_split = (stages_per_split + 1) / 2;
         n_splits = (total_stages + stages_per_split - 1) / stages_per_split;
     }
@@ -482,23 +759,30 @@ int knn2_tc_run(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const uint4 *q
     expand_kernel<<<(unsigned)((nq_pad * 8 + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t *)q, nq, nq_pad, (uint4 *)x_q);
     ctx->launches += 2;
     CUtensorMap mq, mdb;
-    int rc = make_map(&mq, x_q, (uint64_t)nq_pad);
+    int rc = make_map(&mq, x_q, (uint64_t)nq_pad, BM);
     if (rc) return rc;
-    rc = make_map(&mdb, x_db, (uint64_t)nd_pad);
+    rc = make_map(&mdb, x_db, (uint64_t)nd_pad, BN); // 128-row boxes: a whole 1-CTA stage / this CTA's half of a 2-CTA stage
     if (rc) return rc;
     TcParams P;
     P.nq = nq; P.nd = nd; P.n_qtiles = n_qtiles; P.n_splits = n_splits; P.stages_per_split = stages_per_split;
     P.total_stages = total_stages; P.out_best = pb; P.out_second = ps; P.out_stage = pst; P.out_stride = nq_pad;
+    P.dbg = getenv("ORBGPU_TC_DEBUG") ? atoi(getenv("ORBGPU_TC_DEBUG")) : 0;
     static bool attr_set = false;
     if (!attr_set) {
         CU_TRY(cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CU_TRY(cudaFuncSetAttribute(knn2_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
         attr_set = true;
     }
-    const int grid = std::min(n_qtiles * n_splits, ctx->sm_count);
-    knn2_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(mq, mdb, P);
+    if (two_cta) {
+        const int grid = 2 * std::min(n_units * n_splits, n_workers); // whole clusters
+        knn2_tc2_kernel<<<grid, NUM_THREADS, SMEM2_BYTES, ctx->stream>>>(mq, mdb, P);
+    } else {
+        const int grid = std::min(n_qtiles * n_splits, ctx->sm_count);
+        knn2_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(mq, mdb, P);
+    }
     LAUNCH_COUNT(ctx);
     CU_TRY(cudaGetLastError());
-    knn2_tc_merge_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, ctx->stream>>>(q, db->desc, nq, nd, n_splits, nq_pad, pb, ps, pst, th_low,
+    knn2_tc_merge_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, ctx->stream>>>(q, db->desc, nq, nd, n_splits, bn, nq_pad, pb, ps, pst, th_low,
                                                                                 nnratio, best_idx, best_dist, second_dist, match);
     LAUNCH_COUNT(ctx);
     CU_TRY(cudaGetLastError());

@@ -187,7 +187,7 @@ def test_triangulation_oracle(ctx, M, oracle, seed, n_pairs, n_feat, coarse, ori
     assert ctx.last_comparisons == oracle.comparisons()
 
 
-@pytest.mark.parametrize("engine", [1, 2, 3])
+@pytest.mark.parametrize("engine", [1, 2, 3, 4])
 def test_knn2_golden(ctx, M, engine):
     g = golden_outputs()
     kc = synth.make_knn_case(51, 512, 20000)
@@ -198,7 +198,7 @@ def test_knn2_golden(ctx, M, engine):
         assert np.array_equal(a, g["knn_s51/" + name]), name
 
 
-@pytest.mark.parametrize("engine", [1, 2, 3])
+@pytest.mark.parametrize("engine", [1, 2, 3, 4])
 @pytest.mark.parametrize("nq,nd", [(1, 1), (3, 2), (1000, 257), (4097, 70001), (300, 3), (128, 1024), (129, 1025), (1000, 4097)])
 def test_knn2_oracle_ragged(ctx, M, oracle, engine, nq, nd):
     kc = synth.make_knn_case(nq * 7 + nd, nq, nd)
@@ -211,7 +211,8 @@ def test_knn2_oracle_ragged(ctx, M, oracle, engine, nq, nd):
     assert ctx.last_comparisons == nq * nd
 
 
-def test_knn2_tc_ties_and_duplicates(ctx, M, oracle):
+@pytest.mark.parametrize("engine", [3, 4])
+def test_knn2_tc_ties_and_duplicates(ctx, M, oracle, engine):
     """tensor engine: exact duplicates and equal distances across stages / splits must resolve to the FIRST index"""
     rng = np.random.default_rng(5)
     nd, nq = 40000, 640
@@ -221,7 +222,7 @@ def test_knn2_tc_ties_and_duplicates(ctx, M, oracle):
         rows = np.sort(rng.choice(nd, size=4, replace=False))
         near = q[i] ^ synth.flip_mask(rng, 1, 5)[0]
         db[rows] = near
-    ctx.set_knn_engine(3)
+    ctx.set_knn_engine(engine)
     got = M.ORBmatcher(0.8, True, ctx).SearchByNN(ctx.upload_database(db), q, 50)
     ctx.set_knn_engine(0)
     exp = oracle.knn2_ratio(q, db, 50, 0.8, n_threads=os.cpu_count() or 1)
