@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--nd", type=int, default=ND_FULL)
     ap.add_argument("--pairs", type=int, default=C4_PAIRS)
     ap.add_argument("--engine", type=int, default=0, help="knn2 engine: 0 auto, 1 POPC, 2 mma.sync b1, 3 tcgen05 1-CTA, 4 tcgen05 2-CTA")
+    ap.add_argument("--tri-engine", type=int, default=0, help="C4 kernel: 0 auto, 1 CTA per pair, 2 persistent bulk-copy pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -267,6 +268,7 @@ def main():
         P = hi - lo
         case = synth.fill_geometry(synth.make_triangulation_case(20261018 + rank, n_pairs=max(P, 1), n_feat=C4_FEAT))
         ks = ctx.upload_kfset(case.kfs)
+        ctx.set_triangulation_engine(args.tri_engine)
         m = matcher.ORBmatcher(0.6, False, ctx)
         kf1, kf2 = torch.from_numpy(case.kf1).to(dev), torch.from_numpy(case.kf2).to(dev)
         ep, f12 = torch.from_numpy(case.ep).to(dev), torch.from_numpy(case.f12).to(dev)

@@ -214,6 +214,11 @@ int orbgpu_search_for_triangulation_batch_dev(orbgpu_ctx *ctx, const orbgpu_kfse
                                               int32_t only_stereo, int32_t coarse, int32_t check_ori, int32_t *matches12_dev,
                                               int32_t *nmatches_dev);
 
+/* selects the batched-triangulation kernel: 0 = auto, 1 = one CTA per pair (cp.async staging; the only one
+ * that handles mvuRight / bOnlyStereo), 2 = persistent CTAs, producer warp + double-buffered bulk copies
+ * (cp.async.bulk + mbarrier) of per-keyframe stream blobs (what auto resolves to for monocular sets). */
+int orbgpu_triangulation_set_engine(orbgpu_ctx *ctx, int32_t engine);
+
 /* ---- brute-force 2-NN + ratio test (north_star "SearchByNN"; not in this fork: semantics are the
  * inner loop of SearchByBoW, ORBmatcher.cc:327-355 + accept rule :392-395).
  * For each query: best = first db index attaining the minimum distance, second = second

@@ -43,6 +43,7 @@ struct orbgpu_ctx {
     unsigned long long *d_counters = nullptr; // [8] device counters: [0] comparisons, [1] overflow flag, ...
     unsigned long long *h_counters = nullptr; // pinned mirror
     int knn_engine = 0;
+    int tri_engine = 0; // 0 auto, 1 CTA-per-pair kernel, 2 persistent bulk-copy pipelined kernel
     // tcgen05 engine scratch (expanded database), owned by the context
     void *knn_expanded = nullptr;
     size_t knn_expanded_bytes = 0;
@@ -144,6 +145,13 @@ struct orbgpu_kfset {
     int32_t *kf_n_free = nullptr;    // [n_kf] number of CSR slots
     int max_free = 0;                // max over keyframes (sizes the shared-memory staging)
     int max_nodes = 0;
+    // per-keyframe stream blob: [lo halves][node offsets][node ids], fetched with ONE bulk copy; aux = per-slot
+    // 32-byte record {hi half, keypoint} read only for prefilter survivors
+    uint4 *aux = nullptr;            // [n_kf][n_feat][2]
+    unsigned char *blob = nullptr;   // [n_kf][blob_stride]
+    size_t blob_stride = 0;
+    int32_t *blob_bytes = nullptr;   // [n_kf] bytes to copy (multiple of 16)
+    int max_blob = 0;                // max over keyframes
 };
 
 struct orbgpu_db {

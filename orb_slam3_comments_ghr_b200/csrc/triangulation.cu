@@ -37,7 +37,8 @@ kfset_csr_kernel(int n_feat, int cap, const uint32_t *__restrict__ node_id, cons
                  const uint4 *__restrict__ desc, const float2 *__restrict__ xy, const int32_t *__restrict__ octave,
                  int32_t *__restrict__ kf_n_nodes, uint32_t *__restrict__ kf_node_ids, int32_t *__restrict__ kf_node_off,
                  int32_t *__restrict__ kf_feat, uint4 *__restrict__ desc_csr, int4 *__restrict__ kp_csr,
-                 int32_t *__restrict__ kf_n_free, int32_t *__restrict__ max_free)
+                 int32_t *__restrict__ kf_n_free, int32_t *__restrict__ max_free, unsigned char *__restrict__ blob,
+                 size_t blob_stride, int32_t *__restrict__ blob_bytes, uint4 *__restrict__ aux)
 {
     extern __shared__ unsigned long long keys[]; // [cap]
     __shared__ int s_m;
@@ -73,15 +74,25 @@ kfset_csr_kernel(int n_feat, int cap, const uint32_t *__restrict__ node_id, cons
     uint32_t *ids = kf_node_ids + (size_t)kf * n_feat;
     int32_t *off = kf_node_off + (size_t)kf * (n_feat + 1);
     int32_t *feat = kf_feat + (size_t)kf * n_feat;
+    // stream blob of this keyframe (one bulk copy per keyframe in triangulation_stream_kernel):
+    // [lo halves m x 16 B][node offsets (nn+1) x 4 B][node ids nn x 4 B]; the hi halves travel with the keypoint
+    // in the 32-byte aux record of the slot, which only prefilter survivors ever read
+    uint4 *b_lo = (uint4 *)(blob + (size_t)kf * blob_stride);
+    int32_t *b_off = (int32_t *)(b_lo + m);
     // node-ordered copies
     for (int i = t; i < m; i += blockDim.x) {
         const int f = (int)(keys[i] & 0xFFFFFFFFull);
         feat[i] = f;
         const size_t src = (size_t)kf * n_feat + f, dst = (size_t)kf * n_feat + i;
-        desc_csr[2 * dst] = desc[2 * src];
-        desc_csr[2 * dst + 1] = desc[2 * src + 1];
+        const uint4 lo = desc[2 * src], hi = desc[2 * src + 1];
+        desc_csr[2 * dst] = lo;
+        desc_csr[2 * dst + 1] = hi;
+        b_lo[i] = lo;
         const float2 p = xy[src];
-        kp_csr[dst] = make_int4(__float_as_int(p.x), __float_as_int(p.y), octave[src], f);
+        const int4 kp = make_int4(__float_as_int(p.x), __float_as_int(p.y), octave[src], f);
+        kp_csr[dst] = kp;
+        aux[2 * dst] = hi;
+        aux[2 * dst + 1] = make_uint4((unsigned)kp.x, (unsigned)kp.y, (unsigned)kp.z, (unsigned)kp.w);
     }
     // group heads: thread t owns a contiguous chunk of the sorted keys
     const int per = (m + blockDim.x - 1) / blockDim.x;
@@ -107,18 +118,25 @@ kfset_csr_kernel(int n_feat, int cap, const uint32_t *__restrict__ node_id, cons
     __syncthreads();
     int g = ((t >> 5) > 0 ? warp_sums[(t >> 5) - 1] : 0) + incl - heads;
     const int total = warp_sums[31];
+    uint32_t *b_ids = (uint32_t *)(b_off + total + 1);
     for (int i = s; i < e; i++)
         if (i == 0 || (uint32_t)(keys[i] >> 32) != (uint32_t)(keys[i - 1] >> 32)) {
             ids[g] = (uint32_t)(keys[i] >> 32);
             off[g] = i;
+            b_ids[g] = (uint32_t)(keys[i] >> 32);
+            b_off[g] = i;
             g++;
         }
     if (t == 0) {
         off[total] = m;
+        b_off[total] = m;
         kf_n_nodes[kf] = total;
         kf_n_free[kf] = m;
+        const int bytes = (16 * m + 8 * total + 4 + 15) & ~15;
+        blob_bytes[kf] = bytes;
         atomicMax(max_free, m);
         atomicMax(max_free + 1, total);
+        atomicMax(max_free + 2, bytes);
     }
 }
 
@@ -329,6 +347,301 @@ triangulation_pairs_kernel(KfSetView s, int n_pairs, int max_free, int max_nodes
     if (t == 0) nmatches[p] = s_count;
 }
 
+
+// =========================================================================================
+// Engine 2: persistent, pipelined kernel for monocular keyframe sets.
+//
+//   grid  = 2 CTAs per SM (or n_pairs if fewer), each walks pairs p = blockIdx.x, += gridDim.x
+//   warp CW (producer): per pair, reads the pair's metadata and issues ONE cp.async.bulk per keyframe
+//            (its stream blob: lo halves | node offsets | node ids, ~17 KB) into a 2-stage ring;
+//            full[]/empty[] mbarriers with complete_tx byte counting
+//   warps 0..CW-1 (compute), per pair:
+//     row init -> wait full -> join (binary search of the node ids in shared memory)
+//     -> compare: lane owns a kf1 CSR slot and walks its node's kf2 candidates: 128-bit prefilter
+//        (1 LDS.128, 4 XOR, 4 POPC); a candidate whose lo half is already <= TH_LOW (2 % of them) is kept
+//        in a register (first two per thread) or appended to a shared list  -> release the stage
+//     -> gating (converged, one candidate per thread): fetch the two 32-byte aux records {hi half, keypoint}
+//        from global memory, finish the distance, fp32 gates, atomicMin of the (dist, -idx2) key
+//     -> winners write the match row.
+//   The second CTA of the SM overlaps the serial phases and the global latency of the gating step.
+constexpr int TS_SURV = 2048;
+constexpr uint32_t ENT_NONE = 0xFFFFFFFFu;
+struct TsMeta {
+    int k1, k2, m1, m2, nn1, nn2, pad0, pad1;
+    float geo[12]; // f12[9], ep[2]
+};
+
+__device__ __forceinline__ uint32_t ts_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ts_mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void ts_mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ts_mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void ts_mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "TS_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra TS_WAIT_DONE;\n\t"
+        "bra TS_WAIT_LOOP;\n\t"
+        "TS_WAIT_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void ts_bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void ts_bar_compute(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+
+struct TsParams {
+    const unsigned char *blob;
+    size_t blob_stride;
+    const int32_t *blob_bytes;
+    const int32_t *kf_n_free;
+    const int32_t *kf_n_nodes;
+    const uint4 *aux; // [n_kf][n_feat][2] {hi half, keypoint {x, y, octave, feature id}} in CSR slot order
+    const float *angle;
+    const float *scale_factors;
+    const float *level_sigma2;
+    int n_feat, n_levels, cap_bytes, max_free, n_pairs;
+    const int32_t *kf1, *kf2;
+    const float *ep, *f12;
+    int coarse, check_ori;
+    int32_t *matches12, *nmatches;
+    unsigned long long *counters;
+};
+
+// One prefilter survivor ent = c1 | c2 << 13 | dlo << 26: finish the distance (:1180), epipole gate (:1191-1203,
+// monocular), epipolar test (:1246), then the (dist, -idx2) reduction.  Returns the key (KEY_NONE when rejected)
+// and w = c1 | feature id of slot c1 << 13 for the output step.
+__device__ __forceinline__ uint32_t ts_gate(uint32_t ent, const uint4 *__restrict__ aux1, const uint4 *__restrict__ aux2,
+                                            const float *geo, const float *sScale, const float *sSigma, int coarse,
+                                            uint32_t *best, uint32_t &w)
+{
+    const int c1 = (int)(ent & 0x1FFF), c2 = (int)((ent >> 13) & 0x1FFF);
+    const uint4 h1 = aux1[2 * c1], q1 = aux1[2 * c1 + 1];
+    const uint4 h2 = aux2[2 * c2], q2 = aux2[2 * c2 + 1];
+    w = (uint32_t)c1 | (q1.w << 13);
+    const int dist = (int)(ent >> 26) + ham128(h1, h2);
+    if (dist > ORBGPU_TH_LOW) return KEY_NONE;
+    const float x2 = __uint_as_float(q2.x), y2 = __uint_as_float(q2.y);
+    const float dx = __fsub_rn(geo[9], x2), dy = __fsub_rn(geo[10], y2);
+    if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, sScale[q2.z])) return KEY_NONE;
+    if (!coarse && !epipolar_ok(geo, __uint_as_float(q1.x), __uint_as_float(q1.y), x2, y2, sSigma[q2.z])) return KEY_NONE;
+    const uint32_t key = ((uint32_t)dist << 20) | (0xFFFFFu - q2.w);
+    atomicMin(&best[c1], key);
+    return key;
+}
+
+template <int CW>
+__global__ void __launch_bounds__(CW * 32 + 32, 2) triangulation_stream_kernel(const TsParams P)
+{
+    constexpr int CT = CW * 32;
+    extern __shared__ __align__(128) unsigned char ts_smem[];
+    __shared__ __align__(8) unsigned long long bars[4]; // full[2], empty[2]
+    __shared__ TsMeta meta[2];
+    __shared__ float sGeo[12];
+    __shared__ int nsurv;
+    __shared__ float sScale[64], sSigma[64];
+    __shared__ int hist[ORBGPU_HISTO_LENGTH];
+    __shared__ int ind[3];
+
+    const int cap = P.cap_bytes;
+    unsigned char *stage0 = ts_smem;                           // [2 stages][2 keyframes][cap]
+    uint32_t *sCand = (uint32_t *)(ts_smem + 4 * (size_t)cap); // [max_free] s2 | n2f << 16 of every kf1 CSR slot
+    uint32_t *sBest = sCand + P.max_free;                      // [2][max_free] (parity of the pair)
+    uint32_t *sSurv = sBest + 2 * P.max_free;                  // [TS_SURV] entry, then its key
+    uint32_t *sSurvW = sSurv + TS_SURV;                        // [TS_SURV] c1 | feature id << 13
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int n = P.n_feat;
+    const int n_my = (P.n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t full0 = ts_smem_u32(&bars[0]), empty0 = ts_smem_u32(&bars[2]);
+
+    if (t == 0) {
+        ts_mbar_init(full0, 1);
+        ts_mbar_init(full0 + 8, 1);
+        ts_mbar_init(empty0, CW);
+        ts_mbar_init(empty0 + 8, CW);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        nsurv = 0;
+    }
+    if (t < 64) {
+        sScale[t] = t < P.n_levels ? P.scale_factors[t] : 0.f;
+        sSigma[t] = t < P.n_levels ? P.level_sigma2[t] : 0.f;
+    }
+    __syncthreads();
+
+    if (warp == CW) {
+        // ---------------- producer warp
+        for (int i = 0; i < n_my; i++) {
+            const int st = i & 1;
+            if (i >= 2) ts_mbar_wait(empty0 + 8 * st, ((i >> 1) - 1) & 1);
+            const int p = blockIdx.x + i * gridDim.x;
+            const int k1 = P.kf1[p], k2 = P.kf2[p];
+            if (lane < 9) meta[st].geo[lane] = P.f12[9 * (size_t)p + lane];
+            else if (lane < 11) meta[st].geo[lane] = P.ep[2 * (size_t)p + lane - 9];
+            __syncwarp();
+            if (lane == 0) {
+                const int b1 = P.blob_bytes[k1], b2 = P.blob_bytes[k2];
+                meta[st].k1 = k1; meta[st].k2 = k2;
+                meta[st].m1 = P.kf_n_free[k1]; meta[st].m2 = P.kf_n_free[k2];
+                meta[st].nn1 = P.kf_n_nodes[k1]; meta[st].nn2 = P.kf_n_nodes[k2];
+                const uint32_t bar = full0 + 8 * st;
+                ts_mbar_expect_tx(bar, (uint32_t)(b1 + b2));
+                unsigned char *dst = stage0 + (size_t)st * 2 * cap;
+                ts_bulk_load(ts_smem_u32(dst), P.blob + (size_t)k1 * P.blob_stride, (uint32_t)b1, bar);
+                ts_bulk_load(ts_smem_u32(dst + cap), P.blob + (size_t)k2 * P.blob_stride, (uint32_t)b2, bar);
+            }
+            __syncwarp();
+        }
+        return;
+    }
+
+    // ---------------- compute warps
+    unsigned long long ncmp = 0;
+    for (int i = 0; i < n_my; i++) {
+        const int st = i & 1;
+        const int p = blockIdx.x + i * gridDim.x;
+        int32_t *row = P.matches12 + (size_t)p * n;
+        // ---- vMatches12(N, -1) (:1092)
+        if ((n & 3) == 0) {
+            int4 *row4 = (int4 *)row;
+            for (int x = t; x < (n >> 2); x += CT) row4[x] = make_int4(-1, -1, -1, -1);
+        } else {
+            for (int x = t; x < n; x += CT) row[x] = -1;
+        }
+        if (t == 0) P.nmatches[p] = 0;
+        ts_mbar_wait(full0 + 8 * st, (i >> 1) & 1);
+        const TsMeta &M = meta[st];
+        const int k1 = M.k1, k2 = M.k2, m1 = M.m1, m2 = M.m2, nn1 = M.nn1, nn2 = M.nn2;
+        const unsigned char *A = stage0 + (size_t)st * 2 * cap, *B = A + cap;
+        const uint4 *lo1 = (const uint4 *)A;
+        const int32_t *off1 = (const int32_t *)(lo1 + m1);
+        const uint32_t *ids1 = (const uint32_t *)(off1 + nn1 + 1);
+        const uint4 *lo2 = (const uint4 *)B;
+        const int32_t *off2 = (const int32_t *)(lo2 + m2);
+        const uint32_t *ids2 = (const uint32_t *)(off2 + nn2 + 1);
+        uint32_t *best = sBest + st * P.max_free;
+        // ---- join: node a of keyframe 1 looked up in keyframe 2's sorted node list (merge-join :1113-1292)
+        for (int a = t; a < nn1; a += CT) {
+            const uint32_t nid = ids1[a];
+            int lo = 0, hi = nn2;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (ids2[mid] < nid) lo = mid + 1; else hi = mid;
+            }
+            uint32_t e = 0;
+            if (lo < nn2 && ids2[lo] == nid) {
+                const int s2 = off2[lo];
+                e = (uint32_t)s2 | ((uint32_t)(off2[lo + 1] - s2) << 16);
+            }
+            const int s1 = off1[a], e1 = off1[a + 1];
+            for (int c = s1; c < e1; c++) { sCand[c] = e; best[c] = KEY_NONE; }
+        }
+        if (t < 11) sGeo[t] = M.geo[t];
+        ts_bar_compute(CT);
+        // ---- compare: lane owns CSR slot c1 of keyframe 1
+        uint32_t ent0 = ENT_NONE, ent1 = ENT_NONE;
+        for (int c1 = t; c1 < m1; c1 += CT) {
+            const uint32_t cand = sCand[c1];
+            const int n2f = (int)(cand >> 16);
+            const uint4 a_lo = lo1[c1];
+            const uint4 *pb = lo2 + (cand & 0xFFFF), *pe = pb + n2f;
+            ncmp += (unsigned)n2f;
+            for (; pb < pe; ++pb) {
+                const int dlo = ham128(a_lo, *pb);
+                if (dlo <= ORBGPU_TH_LOW) { // a random pair is already above TH_LOW here 99.6 % of the time
+                    const uint32_t e = (uint32_t)c1 | ((uint32_t)(pb - lo2) << 13) | ((uint32_t)dlo << 26);
+                    if (ent0 == ENT_NONE) ent0 = e;
+                    else if (ent1 == ENT_NONE) ent1 = e;
+                    else {
+                        const int slot = atomicAdd(&nsurv, 1);
+                        if (slot < TS_SURV) sSurv[slot] = e;
+                        else { // list full (adversarial inputs only): gate in place, output by slot owners below
+                            uint32_t w;
+                            ts_gate(e, P.aux + (size_t)k1 * n * 2, P.aux + (size_t)k2 * n * 2, sGeo, sScale, sSigma, P.coarse, best, w);
+                        }
+                    }
+                }
+            }
+        }
+        // this warp is done with the stage: let the producer refill it
+        __syncwarp();
+        if (lane == 0) ts_mbar_arrive(empty0 + 8 * st);
+        ts_bar_compute(CT);
+        // ---- gating (converged): registers first, then the shared list
+        const int ns_all = nsurv, ns = min(ns_all, TS_SURV);
+        const uint4 *aux1 = P.aux + (size_t)k1 * n * 2, *aux2 = P.aux + (size_t)k2 * n * 2;
+        uint32_t key0 = KEY_NONE, key1 = KEY_NONE, w0 = 0, w1 = 0;
+        if (ent0 != ENT_NONE) key0 = ts_gate(ent0, aux1, aux2, sGeo, sScale, sSigma, P.coarse, best, w0);
+        if (ent1 != ENT_NONE) key1 = ts_gate(ent1, aux1, aux2, sGeo, sScale, sSigma, P.coarse, best, w1);
+        for (int e = t; e < ns; e += CT) {
+            uint32_t w;
+            sSurv[e] = ts_gate(sSurv[e], aux1, aux2, sGeo, sScale, sSigma, P.coarse, best, w);
+            sSurvW[e] = w;
+        }
+        if (P.check_ori && t < ORBGPU_HISTO_LENGTH) hist[t] = 0;
+        ts_bar_compute(CT);
+        if (t == 0) nsurv = 0;
+        // ---- output
+        const float *ang1 = P.angle + (size_t)k1 * n, *ang2 = P.angle + (size_t)k2 * n;
+        int mine = 0;
+        // calls fn(f1, idx2) for every winning (slot, candidate) this thread is responsible for
+        auto for_each_winner = [&](auto &&fn) {
+            if (ns_all <= TS_SURV) { // the thread that gated the winning candidate reports it
+                if (key0 != KEY_NONE && best[w0 & 0x1FFF] == key0) fn((int)(w0 >> 13), (int)(0xFFFFFu - (key0 & 0xFFFFFu)));
+                if (key1 != KEY_NONE && best[w1 & 0x1FFF] == key1) fn((int)(w1 >> 13), (int)(0xFFFFFu - (key1 & 0xFFFFFu)));
+                for (int e = t; e < ns; e += CT) {
+                    const uint32_t key = sSurv[e], w = sSurvW[e];
+                    if (key != KEY_NONE && best[w & 0x1FFF] == key) fn((int)(w >> 13), (int)(0xFFFFFu - (key & 0xFFFFFu)));
+                }
+            } else { // some candidates were gated in place: slot owners report
+                for (int c = t; c < m1; c += CT) {
+                    const uint32_t key = best[c];
+                    if (key != KEY_NONE) fn((int)aux1[2 * c + 1].w, (int)(0xFFFFFu - (key & 0xFFFFFu)));
+                }
+            }
+        };
+        if (P.check_ori) { // :1266-1277, :1295-1314
+            for_each_winner([&](int f1, int idx2) {
+                const int bin = rot_bin(ang1[f1], ang2[idx2]);
+                if (bin >= 0 && bin < ORBGPU_HISTO_LENGTH) atomicAdd(&hist[bin], 1);
+            });
+            ts_bar_compute(CT);
+            if (t == 0) three_maxima(hist, ORBGPU_HISTO_LENGTH, ind[0], ind[1], ind[2]);
+            ts_bar_compute(CT);
+            for_each_winner([&](int f1, int idx2) {
+                const int bin = rot_bin(ang1[f1], ang2[idx2]);
+                if (bin >= 0 && bin < ORBGPU_HISTO_LENGTH && bin != ind[0] && bin != ind[1] && bin != ind[2]) return;
+                row[f1] = idx2;
+                mine++;
+            });
+        } else {
+            for_each_winner([&](int f1, int idx2) {
+                row[f1] = idx2;
+                mine++;
+            });
+        }
+        for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(FULL_MASK, mine, o);
+        if (lane == 0 && mine) atomicAdd(&P.nmatches[p], mine);
+    }
+    for (int o = 16; o; o >>= 1) ncmp += __shfl_xor_sync(FULL_MASK, ncmp, o);
+    if (lane == 0 && ncmp) atomicAdd(&P.counters[0], ncmp);
+}
+
 KfSetView kfset_view(const orbgpu_kfset *s)
 {
     KfSetView v;
@@ -350,6 +663,7 @@ extern "C" void orbgpu_kfset_destroy(orbgpu_kfset *s)
     cudaFree(s->node_id); cudaFree(s->scale_factors); cudaFree(s->level_sigma2);
     cudaFree(s->kf_n_nodes); cudaFree(s->kf_node_ids); cudaFree(s->kf_node_off); cudaFree(s->kf_feat);
     cudaFree(s->desc_csr); cudaFree(s->kp_csr); cudaFree(s->kf_n_free);
+    cudaFree(s->blob); cudaFree(s->blob_bytes); cudaFree(s->aux);
     delete s;
 }
 
@@ -386,23 +700,35 @@ extern "C" int orbgpu_kfset_upload(orbgpu_ctx *ctx, const orbgpu_kfset_host *h, 
     CU_TRY(cudaMalloc((void **)&s->desc_csr, T * 32));
     CU_TRY(cudaMalloc((void **)&s->kp_csr, T * 16));
     CU_TRY(cudaMalloc((void **)&s->kf_n_free, (size_t)h->n_kf * 4 + 256));
+    s->blob_stride = ((size_t)h->n_feat * 24 + 4 + 127) & ~size_t(127);
+    CU_TRY(cudaMalloc((void **)&s->blob, s->blob_stride * h->n_kf));
+    CU_TRY(cudaMalloc((void **)&s->aux, T * 32));
+    CU_TRY(cudaMalloc((void **)&s->blob_bytes, (size_t)h->n_kf * 4));
     int32_t *d_max = s->kf_n_free + h->n_kf;
-    CU_TRY(cudaMemsetAsync(d_max, 0, 8, ctx->stream));
+    CU_TRY(cudaMemsetAsync(d_max, 0, 12, ctx->stream));
     int cap = 1;
     while (cap < h->n_feat) cap <<= 1;
     const size_t smem = (size_t)cap * 8;
     CU_TRY(cudaFuncSetAttribute(kfset_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kfset_csr_kernel<<<h->n_kf, 1024, smem, ctx->stream>>>(h->n_feat, cap, s->node_id, s->has_mp, s->desc, s->xy, s->octave, s->kf_n_nodes,
                                                           s->kf_node_ids, s->kf_node_off, s->kf_feat, s->desc_csr, s->kp_csr, s->kf_n_free,
-                                                          d_max);
+                                                          d_max, s->blob, s->blob_stride, s->blob_bytes, s->aux);
     LAUNCH_COUNT(ctx);
     CU_TRY(cudaGetLastError());
-    int32_t mx[2] = {0, 0};
-    CU_TRY(cudaMemcpyAsync(mx, d_max, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    int32_t mx[3] = {0, 0, 0};
+    CU_TRY(cudaMemcpyAsync(mx, d_max, 12, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     s->max_free = ((mx[0] > 0 ? mx[0] : 1) + 3) & ~3; // multiple of 4: keeps the int4 node table 16-byte aligned
     s->max_nodes = mx[1] > 0 ? mx[1] : 1;
+    s->max_blob = mx[2] > 0 ? mx[2] : 16;
     *out = s;
+    return ORBGPU_OK;
+}
+
+extern "C" int orbgpu_triangulation_set_engine(orbgpu_ctx *ctx, int32_t engine)
+{
+    ARG_TRY(ctx && engine >= 0 && engine <= 2);
+    ctx->tri_engine = engine;
     return ORBGPU_OK;
 }
 
@@ -416,6 +742,37 @@ extern "C" int orbgpu_search_for_triangulation_batch_dev(orbgpu_ctx *ctx, const 
     CU_TRY(cudaSetDevice(ctx->device));
     CU_TRY(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     if (n_pairs == 0) return ORBGPU_OK;
+    // engine 2: persistent pipelined kernel (monocular sets; bOnlyStereo on a monocular set matches nothing and is
+    // left to the per-pair kernel)
+    {
+        constexpr int CW = 16; // 16 compute warps + 1 producer warp, two CTAs per SM
+        const int cap = (s->max_blob + 127) & ~127;
+        const size_t smem2 = 4 * (size_t)cap + (size_t)s->max_free * 12 + (size_t)TS_SURV * 8;
+        const bool can = !s->u_right && !only_stereo && smem2 + 2048 <= 227 * 1024 && s->max_free <= 8192;
+        if (ctx->tri_engine == 2 && !can)
+            return orbgpu_fail(ORBGPU_ERR_INVALID, "triangulation engine 2 needs a monocular keyframe set that fits the shared-memory ring");
+        if (can && ctx->tri_engine != 1) {
+            TsParams P;
+            P.blob = s->blob; P.blob_stride = s->blob_stride; P.blob_bytes = s->blob_bytes;
+            P.kf_n_free = s->kf_n_free; P.kf_n_nodes = s->kf_n_nodes; P.aux = s->aux; P.angle = s->angle;
+            P.scale_factors = s->scale_factors; P.level_sigma2 = s->level_sigma2;
+            P.n_feat = s->n_feat; P.n_levels = s->n_levels; P.cap_bytes = cap; P.max_free = s->max_free; P.n_pairs = n_pairs;
+            P.kf1 = kf1_dev; P.kf2 = kf2_dev; P.ep = ep_dev; P.f12 = f12_dev;
+            P.coarse = coarse; P.check_ori = check_ori;
+            P.matches12 = matches12_dev; P.nmatches = nmatches_dev; P.counters = ctx->d_counters;
+            auto kern2 = triangulation_stream_kernel<CW>;
+            CU_TRY(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            int per_sm = 1;
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern2, CW * 32 + 32, smem2));
+            if (per_sm < 1) per_sm = 1;
+            if (per_sm > 2) per_sm = 2;
+            const int grid = n_pairs < ctx->sm_count * per_sm ? n_pairs : ctx->sm_count * per_sm;
+            kern2<<<grid, CW * 32 + 32, smem2, ctx->stream>>>(P);
+            LAUNCH_COUNT(ctx);
+            CU_TRY(cudaGetLastError());
+            return ORBGPU_OK;
+        }
+    }
     // 2 x max_free descriptors (32 B) + key (4 B) + histogram bin (1 B) per CSR slot
     const size_t smem = (size_t)s->max_free * (64 + 4 + 1) + (size_t)s->max_nodes * 16 + 64;
     if (smem > 227 * 1024) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "keyframes too large for the shared-memory staging");

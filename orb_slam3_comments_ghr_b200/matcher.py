@@ -86,6 +86,7 @@ def load_library():
     L.orbgpu_knn2_ratio.argtypes = [vp, vp, C.c_int64, u8p, C.c_int32, C.c_float, i32p, i32p, i32p, i32p]
     L.orbgpu_knn2_ratio_dev.argtypes = [vp, vp, C.c_int64, vp, C.c_int32, C.c_float, vp, vp, vp, vp]
     L.orbgpu_knn2_set_engine.argtypes = [vp, C.c_int32]
+    L.orbgpu_triangulation_set_engine.argtypes = [vp, C.c_int32]
     L.orbgpu_compute_three_maxima.argtypes = [vp, i32p, C.c_int32, i32p]
     _lib = L
     return L
@@ -144,6 +145,9 @@ class Context:
 
     def set_knn_engine(self, engine: int):
         _check(load_library().orbgpu_knn2_set_engine(self._h, int(engine)))
+
+    def set_triangulation_engine(self, engine: int):
+        _check(load_library().orbgpu_triangulation_set_engine(self._h, int(engine)))
 
     # ---- a1
     def descriptor_distance(self, a, b) -> np.ndarray:

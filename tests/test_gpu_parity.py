@@ -166,23 +166,52 @@ def test_bow_host_featvec(ctx, M, oracle, seed, levelsup, ratio):
         assert got[0] == exp[0] and np.array_equal(got[1], exp[1])
 
 
+@pytest.mark.parametrize("engine", [1, 2])
 @pytest.mark.parametrize("check_ori", [0, 1])
-def test_triangulation_golden(ctx, M, check_ori):
+def test_triangulation_golden(ctx, M, check_ori, engine):
     g = golden_outputs()
     tc = synth.fill_geometry(synth.make_triangulation_case(41, n_pairs=8, n_feat=2000))
     ks = ctx.upload_kfset(tc.kfs)
+    ctx.set_triangulation_engine(engine)
     nm, m = M.ORBmatcher(0.6, bool(check_ori), ctx).SearchForTriangulation(ks, tc.kf1, tc.kf2, g["tri_s41/ep"], g["tri_s41/f12"])
+    ctx.set_triangulation_engine(0)
     assert np.array_equal(nm, g[f"tri_s41/ori{check_ori}/nmatches"])
     assert np.array_equal(m, g[f"tri_s41/ori{check_ori}/matches"].astype(np.int32))
 
 
-@pytest.mark.parametrize("seed,n_pairs,n_feat,coarse,ori", [(501, 6, 1500, 0, 0), (502, 6, 1500, 0, 1), (503, 6, 1500, 1, 1), (504, 96, 2000, 0, 0), (505, 3, 64, 0, 1)])
-def test_triangulation_oracle(ctx, M, oracle, seed, n_pairs, n_feat, coarse, ori):
+@pytest.mark.parametrize("engine", [1, 2])
+@pytest.mark.parametrize("seed,n_pairs,n_feat,coarse,ori", [(501, 6, 1500, 0, 0), (502, 6, 1500, 0, 1), (503, 6, 1500, 1, 1), (504, 96, 2000, 0, 0), (505, 3, 64, 0, 1),
+                                                            (506, 700, 500, 0, 0), (507, 450, 300, 0, 1), (508, 1, 2000, 0, 0)])
+def test_triangulation_oracle(ctx, M, oracle, seed, n_pairs, n_feat, coarse, ori, engine):
     tc = synth.fill_geometry(synth.make_triangulation_case(seed, n_pairs=n_pairs, n_feat=n_feat))
     ks = ctx.upload_kfset(tc.kfs)
+    ctx.set_triangulation_engine(engine)
     nm, m = M.ORBmatcher(0.6, bool(ori), ctx).SearchForTriangulation(ks, tc.kf1, tc.kf2, tc.ep, tc.f12, False, bool(coarse))
+    ctx.set_triangulation_engine(0)
     oracle.reset_comparisons()
     enm, em = oracle.search_for_triangulation_batch(tc.kfs, tc.kf1, tc.kf2, tc.ep, tc.f12, 0, coarse, ori, n_threads=os.cpu_count() or 1)
+    assert np.array_equal(nm, enm) and np.array_equal(m, em)
+    assert ctx.last_comparisons == oracle.comparisons()
+
+
+@pytest.mark.parametrize("engine", [1, 2])
+@pytest.mark.parametrize("n_distinct,coarse,ori", [(1, 1, 0), (3, 1, 1), (5, 0, 0), (2, 0, 1)])
+def test_triangulation_dense_ties(ctx, M, oracle, engine, n_distinct, coarse, ori):
+    """adversarial: only a handful of distinct descriptors, so almost every candidate of a node survives
+    dist <= TH_LOW with equal distances -- exercises the last-wins tie-break (:1180), the survivor list
+    beyond one entry per thread and its overflow path."""
+    tc = synth.fill_geometry(synth.make_triangulation_case(900 + n_distinct, n_pairs=5, n_feat=1200, n_nodes=12))
+    rng = np.random.default_rng(n_distinct)
+    base = synth.random_descriptors(rng, n_distinct)
+    pick = rng.integers(0, n_distinct, size=tc.kfs.desc.shape[:2])
+    tc.kfs.desc[:] = base[pick] ^ synth.flip_mask(rng, pick.size, np.full(pick.size, 6)).reshape(*pick.shape, 32)
+    ks = ctx.upload_kfset(tc.kfs)
+    ctx.set_triangulation_engine(engine)
+    nm, m = M.ORBmatcher(0.6, bool(ori), ctx).SearchForTriangulation(ks, tc.kf1, tc.kf2, tc.ep, tc.f12, False, bool(coarse))
+    ctx.set_triangulation_engine(0)
+    oracle.reset_comparisons()
+    enm, em = oracle.search_for_triangulation_batch(tc.kfs, tc.kf1, tc.kf2, tc.ep, tc.f12, 0, coarse, ori, n_threads=os.cpu_count() or 1)
+    assert int(enm.sum()) > 0
     assert np.array_equal(nm, enm) and np.array_equal(m, em)
     assert ctx.last_comparisons == oracle.comparisons()
 
