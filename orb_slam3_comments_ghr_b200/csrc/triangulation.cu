@@ -349,26 +349,32 @@ triangulation_pairs_kernel(KfSetView s, int n_pairs, int max_free, int max_nodes
 
 
 // =========================================================================================
-// Engine 2: persistent, pipelined kernel for monocular keyframe sets.
+// Engine 2: persistent, warp-specialised pipeline for monocular keyframe sets.
 //
-//   grid  = 2 CTAs per SM (or n_pairs if fewer), each walks pairs p = blockIdx.x, += gridDim.x
-//   warp CW (producer): per pair, reads the pair's metadata and issues ONE cp.async.bulk per keyframe
-//            (its stream blob: lo halves | node offsets | node ids, ~17 KB) into a 2-stage ring;
-//            full[]/empty[] mbarriers with complete_tx byte counting
-//   warps 0..CW-1 (compute), per pair:
-//     row init -> wait full -> join (binary search of the node ids in shared memory)
-//     -> compare: lane owns a kf1 CSR slot and walks its node's kf2 candidates: 128-bit prefilter
-//        (1 LDS.128, 4 XOR, 4 POPC); a candidate whose lo half is already <= TH_LOW (2 % of them) is kept
-//        in a register (first two per thread) or appended to a shared list  -> release the stage
-//     -> gating (converged, one candidate per thread): fetch the two 32-byte aux records {hi half, keypoint}
-//        from global memory, finish the distance, fp32 gates, atomicMin of the (dist, -idx2) key
-//     -> winners write the match row.
-//   The second CTA of the SM overlaps the serial phases and the global latency of the gating step.
-constexpr int TS_SURV = 2048;
+// One CTA per SM walks pairs p = blockIdx.x, += gridDim.x through a ring of S stages (S = 2..4, as shared memory
+// allows).  A stage holds the two keyframes' stream blobs (lo halves | node offsets | node ids, ~17 KB each), the
+// join table, the per-slot best keys and the candidate list of ONE pair.  Four roles, chained by mbarriers:
+//
+//   producer (1 warp)  waits empty[st]; reads the pair's metadata; ONE cp.async.bulk per keyframe -> full[st] (tx bytes)
+//   join     (NJ warps) waits full[st]; node a of keyframe 1 binary-searched in keyframe 2's node list (merge-join
+//                      :1113-1292); writes sCand[c1] = (first candidate, count) for every slot -> joined[st]
+//   compare  (NC warps) waits joined[st]; warps grab 32-slot chunks dynamically; lane owns CSR slot c1 of keyframe 1
+//                      and walks its node's candidates: 1 LDS.128 + 4 XOR + 4 POPC on the lo halves; a candidate
+//                      whose lo half is already <= TH_LOW (2 % of them) goes to the stage's list -> compared[st]
+//   post     (NG warps) fills the match row with -1 while waiting for compared[st]; one list entry per thread:
+//                      fetches the two 32-byte aux records {hi half, keypoint} (L2-prefetched by the compare warps),
+//                      finishes the distance, fp32 gates, atomicMin of the (dist, -idx2) key; winners write the
+//                      match row -> empty[st]
+//
+// The compare warps never meet a CTA-wide barrier: while they stream pair i, the post warps finish pair i-1, the join
+// warps prepare pair i+1 and the bulk copies of pair i+2 are in flight.
+constexpr int TS_SURV = 1024;
 constexpr uint32_t ENT_NONE = 0xFFFFFFFFu;
-struct TsMeta {
-    int k1, k2, m1, m2, nn1, nn2, pad0, pad1;
-    float geo[12]; // f12[9], ep[2]
+struct TsStageCtl {
+    int k1, k2, m1, m2, nn1, nn2;
+    int n_list;     // candidates appended so far
+    int next_chunk; // dynamic 32-slot chunk counter of the compare warps
+    float geo[12];  // f12[9], ep[2]
 };
 
 __device__ __forceinline__ uint32_t ts_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -397,13 +403,31 @@ __device__ __forceinline__ void ts_mbar_wait(uint32_t bar, uint32_t parity)
         "}" ::"r"(bar), "r"(parity)
         : "memory");
 }
+// for the roles that normally wait (producer, join, post): poll with a short sleep so that the compare warps keep the issue slots
+__device__ __forceinline__ void ts_mbar_wait_relaxed(uint32_t bar, uint32_t parity)
+{
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        __nanosleep(64);
+    }
+}
 __device__ __forceinline__ void ts_bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
-__device__ __forceinline__ void ts_bar_compute(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+__device__ __forceinline__ void ts_bar_post(int nthreads) { asm volatile("bar.sync 2, %0;" ::"r"(nthreads) : "memory"); }
 
 struct TsParams {
     const unsigned char *blob;
@@ -415,7 +439,7 @@ struct TsParams {
     const float *angle;
     const float *scale_factors;
     const float *level_sigma2;
-    int n_feat, n_levels, cap_bytes, max_free, n_pairs;
+    int n_feat, n_levels, cap_bytes, max_free, n_pairs, n_stages, stage_bytes;
     const int32_t *kf1, *kf2;
     const float *ep, *f12;
     int coarse, check_ori;
@@ -423,18 +447,18 @@ struct TsParams {
     unsigned long long *counters;
 };
 
-// One prefilter survivor ent = c1 | c2 << 13 | dlo << 26: finish the distance (:1180), epipole gate (:1191-1203,
-// monocular), epipolar test (:1246), then the (dist, -idx2) reduction.  Returns the key (KEY_NONE when rejected)
-// and w = c1 | feature id of slot c1 << 13 for the output step.
-__device__ __forceinline__ uint32_t ts_gate(uint32_t ent, const uint4 *__restrict__ aux1, const uint4 *__restrict__ aux2,
-                                            const float *geo, const float *sScale, const float *sSigma, int coarse,
-                                            uint32_t *best, uint32_t &w)
+// One prefilter survivor ent = c1 | c2 << 13: finish the distance (:1180; lo halves from the stage, hi halves from the
+// aux records), epipole gate (:1191-1203, monocular), epipolar test (:1246), then the (dist, -idx2) reduction.
+// Returns the key (KEY_NONE when rejected) and w = c1 | feature id of slot c1 << 13 for the output step.
+__device__ __forceinline__ uint32_t ts_gate(uint32_t ent, const uint4 *lo1, const uint4 *lo2, const uint4 *__restrict__ aux1,
+                                            const uint4 *__restrict__ aux2, const float *geo, const float *sScale,
+                                            const float *sSigma, int coarse, uint32_t *best, uint32_t &w)
 {
     const int c1 = (int)(ent & 0x1FFF), c2 = (int)((ent >> 13) & 0x1FFF);
     const uint4 h1 = aux1[2 * c1], q1 = aux1[2 * c1 + 1];
     const uint4 h2 = aux2[2 * c2], q2 = aux2[2 * c2 + 1];
     w = (uint32_t)c1 | (q1.w << 13);
-    const int dist = (int)(ent >> 26) + ham128(h1, h2);
+    const int dist = ham128(lo1[c1], lo2[c2]) + ham128(h1, h2);
     if (dist > ORBGPU_TH_LOW) return KEY_NONE;
     const float x2 = __uint_as_float(q2.x), y2 = __uint_as_float(q2.y);
     const float dx = __fsub_rn(geo[9], x2), dy = __fsub_rn(geo[10], y2);
@@ -445,38 +469,33 @@ __device__ __forceinline__ uint32_t ts_gate(uint32_t ent, const uint4 *__restric
     return key;
 }
 
-template <int CW>
-__global__ void __launch_bounds__(CW * 32 + 32, 2) triangulation_stream_kernel(const TsParams P)
+template <int NC, int NG, int NJ>
+__global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stream_kernel(const TsParams P)
 {
-    constexpr int CT = CW * 32;
+    constexpr int GT = NG * 32, JT = NJ * 32;
     extern __shared__ __align__(128) unsigned char ts_smem[];
-    __shared__ __align__(8) unsigned long long bars[4]; // full[2], empty[2]
-    __shared__ TsMeta meta[2];
-    __shared__ float sGeo[12];
-    __shared__ int nsurv;
+    __shared__ __align__(8) unsigned long long bars[4][4]; // [stage][full, joined, compared, empty]
+    __shared__ TsStageCtl ctl[4];
     __shared__ float sScale[64], sSigma[64];
     __shared__ int hist[ORBGPU_HISTO_LENGTH];
     __shared__ int ind[3];
 
-    const int cap = P.cap_bytes;
-    unsigned char *stage0 = ts_smem;                           // [2 stages][2 keyframes][cap]
-    uint32_t *sCand = (uint32_t *)(ts_smem + 4 * (size_t)cap); // [max_free] s2 | n2f << 16 of every kf1 CSR slot
-    uint32_t *sBest = sCand + P.max_free;                      // [2][max_free] (parity of the pair)
-    uint32_t *sSurv = sBest + 2 * P.max_free;                  // [TS_SURV] entry, then its key
-    uint32_t *sSurvW = sSurv + TS_SURV;                        // [TS_SURV] c1 | feature id << 13
-
+    const int S = P.n_stages, cap = P.cap_bytes, mf = P.max_free;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int n = P.n_feat;
     const int n_my = (P.n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const uint32_t full0 = ts_smem_u32(&bars[0]), empty0 = ts_smem_u32(&bars[2]);
+    const uint32_t bar0 = ts_smem_u32(&bars[0][0]);
+    auto bar_of = [&](int st, int which) { return bar0 + (uint32_t)(st * 4 + which) * 8u; };
+    enum { B_FULL = 0, B_JOINED = 1, B_COMPARED = 2, B_EMPTY = 3 };
 
     if (t == 0) {
-        ts_mbar_init(full0, 1);
-        ts_mbar_init(full0 + 8, 1);
-        ts_mbar_init(empty0, CW);
-        ts_mbar_init(empty0 + 8, CW);
+        for (int st = 0; st < 4; st++) {
+            ts_mbar_init(bar_of(st, B_FULL), 1);
+            ts_mbar_init(bar_of(st, B_JOINED), NJ);
+            ts_mbar_init(bar_of(st, B_COMPARED), NC);
+            ts_mbar_init(bar_of(st, B_EMPTY), NG);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        nsurv = 0;
     }
     if (t < 64) {
         sScale[t] = t < P.n_levels ? P.scale_factors[t] : 0.f;
@@ -484,132 +503,190 @@ __global__ void __launch_bounds__(CW * 32 + 32, 2) triangulation_stream_kernel(c
     }
     __syncthreads();
 
-    if (warp == CW) {
+    // per-stage carve-up of the dynamic shared memory
+    auto stage_base = [&](int st) { return ts_smem + (size_t)st * P.stage_bytes; };
+    // [A cap][B cap][sCand mf][sBest mf][list TS_SURV][listW TS_SURV]
+
+    if (warp == NC + NG + NJ) {
         // ---------------- producer warp
-        for (int i = 0; i < n_my; i++) {
-            const int st = i & 1;
-            if (i >= 2) ts_mbar_wait(empty0 + 8 * st, ((i >> 1) - 1) & 1);
+        for (int i = 0, st = 0, round = 0; i < n_my; i++) {
+            if (round > 0) ts_mbar_wait_relaxed(bar_of(st, B_EMPTY), (round - 1) & 1);
             const int p = blockIdx.x + i * gridDim.x;
             const int k1 = P.kf1[p], k2 = P.kf2[p];
-            if (lane < 9) meta[st].geo[lane] = P.f12[9 * (size_t)p + lane];
-            else if (lane < 11) meta[st].geo[lane] = P.ep[2 * (size_t)p + lane - 9];
+            TsStageCtl &C = ctl[st];
+            if (lane < 9) C.geo[lane] = P.f12[9 * (size_t)p + lane];
+            else if (lane < 11) C.geo[lane] = P.ep[2 * (size_t)p + lane - 9];
             __syncwarp();
             if (lane == 0) {
                 const int b1 = P.blob_bytes[k1], b2 = P.blob_bytes[k2];
-                meta[st].k1 = k1; meta[st].k2 = k2;
-                meta[st].m1 = P.kf_n_free[k1]; meta[st].m2 = P.kf_n_free[k2];
-                meta[st].nn1 = P.kf_n_nodes[k1]; meta[st].nn2 = P.kf_n_nodes[k2];
-                const uint32_t bar = full0 + 8 * st;
+                C.k1 = k1; C.k2 = k2;
+                C.m1 = P.kf_n_free[k1]; C.m2 = P.kf_n_free[k2];
+                C.nn1 = P.kf_n_nodes[k1]; C.nn2 = P.kf_n_nodes[k2];
+                C.n_list = 0; C.next_chunk = 0;
+                const uint32_t bar = bar_of(st, B_FULL);
                 ts_mbar_expect_tx(bar, (uint32_t)(b1 + b2));
-                unsigned char *dst = stage0 + (size_t)st * 2 * cap;
+                unsigned char *dst = stage_base(st);
                 ts_bulk_load(ts_smem_u32(dst), P.blob + (size_t)k1 * P.blob_stride, (uint32_t)b1, bar);
                 ts_bulk_load(ts_smem_u32(dst + cap), P.blob + (size_t)k2 * P.blob_stride, (uint32_t)b2, bar);
             }
             __syncwarp();
+            if (++st == S) { st = 0; round++; }
         }
         return;
     }
 
-    // ---------------- compute warps
-    unsigned long long ncmp = 0;
-    for (int i = 0; i < n_my; i++) {
-        const int st = i & 1;
+    if (warp >= NC + NG) {
+        // ---------------- join warps
+        const int jt = (warp - (NC + NG)) * 32 + lane;
+        for (int i = 0, st = 0, round = 0; i < n_my; i++) {
+            ts_mbar_wait_relaxed(bar_of(st, B_FULL), round & 1);
+            const TsStageCtl &C = ctl[st];
+            const int m1 = C.m1, m2 = C.m2, nn1 = C.nn1, nn2 = C.nn2;
+            unsigned char *base = stage_base(st);
+            const int32_t *off1 = (const int32_t *)((const uint4 *)base + m1);
+            const uint32_t *ids1 = (const uint32_t *)(off1 + nn1 + 1);
+            const int32_t *off2 = (const int32_t *)((const uint4 *)(base + cap) + m2);
+            const uint32_t *ids2 = (const uint32_t *)(off2 + nn2 + 1);
+            uint32_t *sCand = (uint32_t *)(base + 2 * (size_t)cap), *sBest = sCand + mf;
+            for (int a = jt; a < nn1; a += JT) {
+                const uint32_t nid = ids1[a];
+                int lo = 0, hi = nn2;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (ids2[mid] < nid) lo = mid + 1; else hi = mid;
+                }
+                uint32_t e = 0;
+                if (lo < nn2 && ids2[lo] == nid) {
+                    const int s2 = off2[lo];
+                    e = (uint32_t)s2 | ((uint32_t)(off2[lo + 1] - s2) << 16);
+                }
+                const int s1 = off1[a], e1 = off1[a + 1];
+                for (int c = s1; c < e1; c++) { sCand[c] = e; sBest[c] = KEY_NONE; }
+            }
+            __syncwarp();
+            if (lane == 0) ts_mbar_arrive(bar_of(st, B_JOINED));
+            if (++st == S) { st = 0; round++; }
+        }
+        return;
+    }
+
+    if (warp < NC) {
+        // ---------------- compare warps
+        unsigned long long ncmp = 0;
+        for (int i = 0, st = 0, round = 0; i < n_my; i++) {
+            ts_mbar_wait(bar_of(st, B_JOINED), round & 1);
+            TsStageCtl &C = ctl[st];
+            const int k1 = C.k1, k2 = C.k2, m1 = C.m1;
+            unsigned char *base = stage_base(st);
+            const uint4 *lo1 = (const uint4 *)base, *lo2 = (const uint4 *)(base + cap);
+            const uint32_t *sCand = (const uint32_t *)(base + 2 * (size_t)cap);
+            uint32_t *sBest = (uint32_t *)sCand + mf, *sList = sBest + mf;
+            const uint4 *aux1 = P.aux + (size_t)k1 * n * 2, *aux2 = P.aux + (size_t)k2 * n * 2;
+            // 32-slot chunks are dealt round-robin to the warps, rotated from pair to pair so that the odd chunk does
+            // not always land on the same warps
+            for (int chunk = (warp + NC - (i % NC)) % NC; chunk * 32 < m1; chunk += NC) {
+                const int c1 = chunk * 32 + lane;
+                uint32_t cand = 0;
+                uint4 a_lo = make_uint4(0, 0, 0, 0);
+                if (c1 < m1) {
+                    cand = sCand[c1];
+                    a_lo = lo1[c1];
+                }
+                const int n2f = (int)(cand >> 16), s2 = (int)(cand & 0xFFFF);
+                ncmp += (unsigned)n2f;
+                const int maxn = __reduce_max_sync(FULL_MASK, n2f);
+                for (int j0 = 0; j0 < maxn; j0 += 32) { // one pass unless a node holds more than 32 candidates
+                    // branch-free inner loop: bit j of mask = candidate j0+j passes the 128-bit prefilter
+                    const int nb = min(max(n2f - j0, 0), 32);
+                    const uint4 *pb = lo2 + s2 + j0, *pe = pb + nb;
+                    uint32_t mask = 0, bit = 1;
+#pragma unroll 2
+                    for (; pb < pe; ++pb) {
+                        if (ham128(a_lo, *pb) <= ORBGPU_TH_LOW) mask |= bit; // a random pair fails here 99.6 % of the time
+                        bit <<= 1;
+                    }
+                    __syncwarp();
+                    const int cnt = __popc(mask);
+                    if (__ballot_sync(FULL_MASK, cnt != 0) == 0) continue;
+                    // one list reservation per warp: exclusive prefix sum of the hit counts
+                    int incl = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int u = __shfl_up_sync(FULL_MASK, incl, o);
+                        if (lane >= o) incl += u;
+                    }
+                    int slot0 = 0;
+                    if (lane == 31) slot0 = atomicAdd(&C.n_list, incl);
+                    slot0 = __shfl_sync(FULL_MASK, slot0, 31);
+                    int slot = slot0 + incl - cnt;
+                    while (mask) {
+                        const int c2 = s2 + j0 + __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const uint32_t e = (uint32_t)c1 | ((uint32_t)c2 << 13);
+                        if (slot < TS_SURV) {
+                            sList[slot] = e;
+                            // the post warps will read the two aux records: start pulling them into L2 now
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(aux1 + 2 * c1));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(aux2 + 2 * c2));
+                        } else { // list full (adversarial inputs only): gate in place, output by slot owners
+                            uint32_t w;
+                            ts_gate(e, lo1, lo2, aux1, aux2, C.geo, sScale, sSigma, P.coarse, sBest, w);
+                        }
+                        slot++;
+                    }
+                    __syncwarp();
+                }
+            }
+            __syncwarp();
+            if (lane == 0) ts_mbar_arrive(bar_of(st, B_COMPARED));
+            if (++st == S) { st = 0; round++; }
+        }
+        for (int o = 16; o; o >>= 1) ncmp += __shfl_xor_sync(FULL_MASK, ncmp, o);
+        if (lane == 0 && ncmp) atomicAdd(&P.counters[0], ncmp);
+        return;
+    }
+
+    // ---------------- post warps
+    const int gt = (warp - NC) * 32 + lane;
+    for (int i = 0, st = 0, round = 0; i < n_my; i++) {
         const int p = blockIdx.x + i * gridDim.x;
         int32_t *row = P.matches12 + (size_t)p * n;
         // ---- vMatches12(N, -1) (:1092)
         if ((n & 3) == 0) {
             int4 *row4 = (int4 *)row;
-            for (int x = t; x < (n >> 2); x += CT) row4[x] = make_int4(-1, -1, -1, -1);
+            for (int x = gt; x < (n >> 2); x += GT) row4[x] = make_int4(-1, -1, -1, -1);
         } else {
-            for (int x = t; x < n; x += CT) row[x] = -1;
+            for (int x = gt; x < n; x += GT) row[x] = -1;
         }
-        if (t == 0) P.nmatches[p] = 0;
-        ts_mbar_wait(full0 + 8 * st, (i >> 1) & 1);
-        const TsMeta &M = meta[st];
-        const int k1 = M.k1, k2 = M.k2, m1 = M.m1, m2 = M.m2, nn1 = M.nn1, nn2 = M.nn2;
-        const unsigned char *A = stage0 + (size_t)st * 2 * cap, *B = A + cap;
-        const uint4 *lo1 = (const uint4 *)A;
-        const int32_t *off1 = (const int32_t *)(lo1 + m1);
-        const uint32_t *ids1 = (const uint32_t *)(off1 + nn1 + 1);
-        const uint4 *lo2 = (const uint4 *)B;
-        const int32_t *off2 = (const int32_t *)(lo2 + m2);
-        const uint32_t *ids2 = (const uint32_t *)(off2 + nn2 + 1);
-        uint32_t *best = sBest + st * P.max_free;
-        // ---- join: node a of keyframe 1 looked up in keyframe 2's sorted node list (merge-join :1113-1292)
-        for (int a = t; a < nn1; a += CT) {
-            const uint32_t nid = ids1[a];
-            int lo = 0, hi = nn2;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (ids2[mid] < nid) lo = mid + 1; else hi = mid;
-            }
-            uint32_t e = 0;
-            if (lo < nn2 && ids2[lo] == nid) {
-                const int s2 = off2[lo];
-                e = (uint32_t)s2 | ((uint32_t)(off2[lo + 1] - s2) << 16);
-            }
-            const int s1 = off1[a], e1 = off1[a + 1];
-            for (int c = s1; c < e1; c++) { sCand[c] = e; best[c] = KEY_NONE; }
-        }
-        if (t < 11) sGeo[t] = M.geo[t];
-        ts_bar_compute(CT);
-        // ---- compare: lane owns CSR slot c1 of keyframe 1
-        uint32_t ent0 = ENT_NONE, ent1 = ENT_NONE;
-        for (int c1 = t; c1 < m1; c1 += CT) {
-            const uint32_t cand = sCand[c1];
-            const int n2f = (int)(cand >> 16);
-            const uint4 a_lo = lo1[c1];
-            const uint4 *pb = lo2 + (cand & 0xFFFF), *pe = pb + n2f;
-            ncmp += (unsigned)n2f;
-            for (; pb < pe; ++pb) {
-                const int dlo = ham128(a_lo, *pb);
-                if (dlo <= ORBGPU_TH_LOW) { // a random pair is already above TH_LOW here 99.6 % of the time
-                    const uint32_t e = (uint32_t)c1 | ((uint32_t)(pb - lo2) << 13) | ((uint32_t)dlo << 26);
-                    if (ent0 == ENT_NONE) ent0 = e;
-                    else if (ent1 == ENT_NONE) ent1 = e;
-                    else {
-                        const int slot = atomicAdd(&nsurv, 1);
-                        if (slot < TS_SURV) sSurv[slot] = e;
-                        else { // list full (adversarial inputs only): gate in place, output by slot owners below
-                            uint32_t w;
-                            ts_gate(e, P.aux + (size_t)k1 * n * 2, P.aux + (size_t)k2 * n * 2, sGeo, sScale, sSigma, P.coarse, best, w);
-                        }
-                    }
-                }
-            }
-        }
-        // this warp is done with the stage: let the producer refill it
-        __syncwarp();
-        if (lane == 0) ts_mbar_arrive(empty0 + 8 * st);
-        ts_bar_compute(CT);
-        // ---- gating (converged): registers first, then the shared list
-        const int ns_all = nsurv, ns = min(ns_all, TS_SURV);
+        if (gt == 0) P.nmatches[p] = 0;
+        ts_mbar_wait_relaxed(bar_of(st, B_COMPARED), round & 1);
+        const TsStageCtl &C = ctl[st];
+        const int k1 = C.k1, k2 = C.k2, m1 = C.m1;
+        const int ns_all = C.n_list, ns = min(ns_all, TS_SURV);
+        unsigned char *base = stage_base(st);
+        const uint4 *lo1 = (const uint4 *)base, *lo2 = (const uint4 *)(base + cap);
+        uint32_t *best = (uint32_t *)(base + 2 * (size_t)cap) + mf, *sList = best + mf, *sListW = sList + TS_SURV;
         const uint4 *aux1 = P.aux + (size_t)k1 * n * 2, *aux2 = P.aux + (size_t)k2 * n * 2;
-        uint32_t key0 = KEY_NONE, key1 = KEY_NONE, w0 = 0, w1 = 0;
-        if (ent0 != ENT_NONE) key0 = ts_gate(ent0, aux1, aux2, sGeo, sScale, sSigma, P.coarse, best, w0);
-        if (ent1 != ENT_NONE) key1 = ts_gate(ent1, aux1, aux2, sGeo, sScale, sSigma, P.coarse, best, w1);
-        for (int e = t; e < ns; e += CT) {
+        // ---- gating: one list entry per thread
+        for (int e = gt; e < ns; e += GT) {
             uint32_t w;
-            sSurv[e] = ts_gate(sSurv[e], aux1, aux2, sGeo, sScale, sSigma, P.coarse, best, w);
-            sSurvW[e] = w;
+            sList[e] = ts_gate(sList[e], lo1, lo2, aux1, aux2, C.geo, sScale, sSigma, P.coarse, best, w);
+            sListW[e] = w;
         }
-        if (P.check_ori && t < ORBGPU_HISTO_LENGTH) hist[t] = 0;
-        ts_bar_compute(CT);
-        if (t == 0) nsurv = 0;
+        if (P.check_ori && gt < ORBGPU_HISTO_LENGTH) hist[gt] = 0;
+        ts_bar_post(GT);
         // ---- output
         const float *ang1 = P.angle + (size_t)k1 * n, *ang2 = P.angle + (size_t)k2 * n;
         int mine = 0;
         // calls fn(f1, idx2) for every winning (slot, candidate) this thread is responsible for
         auto for_each_winner = [&](auto &&fn) {
             if (ns_all <= TS_SURV) { // the thread that gated the winning candidate reports it
-                if (key0 != KEY_NONE && best[w0 & 0x1FFF] == key0) fn((int)(w0 >> 13), (int)(0xFFFFFu - (key0 & 0xFFFFFu)));
-                if (key1 != KEY_NONE && best[w1 & 0x1FFF] == key1) fn((int)(w1 >> 13), (int)(0xFFFFFu - (key1 & 0xFFFFFu)));
-                for (int e = t; e < ns; e += CT) {
-                    const uint32_t key = sSurv[e], w = sSurvW[e];
+                for (int e = gt; e < ns; e += GT) {
+                    const uint32_t key = sList[e], w = sListW[e];
                     if (key != KEY_NONE && best[w & 0x1FFF] == key) fn((int)(w >> 13), (int)(0xFFFFFu - (key & 0xFFFFFu)));
                 }
-            } else { // some candidates were gated in place: slot owners report
-                for (int c = t; c < m1; c += CT) {
+            } else { // some candidates were gated in place by the compare warps: slot owners report
+                for (int c = gt; c < m1; c += GT) {
                     const uint32_t key = best[c];
                     if (key != KEY_NONE) fn((int)aux1[2 * c + 1].w, (int)(0xFFFFFu - (key & 0xFFFFFu)));
                 }
@@ -620,9 +697,9 @@ __global__ void __launch_bounds__(CW * 32 + 32, 2) triangulation_stream_kernel(c
                 const int bin = rot_bin(ang1[f1], ang2[idx2]);
                 if (bin >= 0 && bin < ORBGPU_HISTO_LENGTH) atomicAdd(&hist[bin], 1);
             });
-            ts_bar_compute(CT);
-            if (t == 0) three_maxima(hist, ORBGPU_HISTO_LENGTH, ind[0], ind[1], ind[2]);
-            ts_bar_compute(CT);
+            ts_bar_post(GT);
+            if (gt == 0) three_maxima(hist, ORBGPU_HISTO_LENGTH, ind[0], ind[1], ind[2]);
+            ts_bar_post(GT);
             for_each_winner([&](int f1, int idx2) {
                 const int bin = rot_bin(ang1[f1], ang2[idx2]);
                 if (bin >= 0 && bin < ORBGPU_HISTO_LENGTH && bin != ind[0] && bin != ind[1] && bin != ind[2]) return;
@@ -637,9 +714,10 @@ __global__ void __launch_bounds__(CW * 32 + 32, 2) triangulation_stream_kernel(c
         }
         for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(FULL_MASK, mine, o);
         if (lane == 0 && mine) atomicAdd(&P.nmatches[p], mine);
+        __syncwarp();
+        if (lane == 0) ts_mbar_arrive(bar_of(st, B_EMPTY));
+        if (++st == S) { st = 0; round++; }
     }
-    for (int o = 16; o; o >>= 1) ncmp += __shfl_xor_sync(FULL_MASK, ncmp, o);
-    if (lane == 0 && ncmp) atomicAdd(&P.counters[0], ncmp);
 }
 
 KfSetView kfset_view(const orbgpu_kfset *s)
@@ -742,13 +820,15 @@ extern "C" int orbgpu_search_for_triangulation_batch_dev(orbgpu_ctx *ctx, const 
     CU_TRY(cudaSetDevice(ctx->device));
     CU_TRY(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     if (n_pairs == 0) return ORBGPU_OK;
-    // engine 2: persistent pipelined kernel (monocular sets; bOnlyStereo on a monocular set matches nothing and is
-    // left to the per-pair kernel)
+    // engine 2: persistent warp-specialised pipeline (monocular sets; bOnlyStereo on a monocular set matches nothing
+    // and is left to the per-pair kernel)
     {
-        constexpr int CW = 16; // 16 compute warps + 1 producer warp, two CTAs per SM
+        constexpr int NC = 16, NG = 4, NJ = 2; // compare / post / join warps (+ 1 producer warp = 736 threads)
         const int cap = (s->max_blob + 127) & ~127;
-        const size_t smem2 = 4 * (size_t)cap + (size_t)s->max_free * 12 + (size_t)TS_SURV * 8;
-        const bool can = !s->u_right && !only_stereo && smem2 + 2048 <= 227 * 1024 && s->max_free <= 8192;
+        const size_t stage_bytes = (2 * (size_t)cap + (size_t)s->max_free * 8 + (size_t)TS_SURV * 8 + 127) & ~size_t(127);
+        int n_stages = (int)((227 * 1024 - 2048) / stage_bytes);
+        if (n_stages > 4) n_stages = 4;
+        const bool can = !s->u_right && !only_stereo && n_stages >= 2 && s->max_free <= 8192;
         if (ctx->tri_engine == 2 && !can)
             return orbgpu_fail(ORBGPU_ERR_INVALID, "triangulation engine 2 needs a monocular keyframe set that fits the shared-memory ring");
         if (can && ctx->tri_engine != 1) {
@@ -757,17 +837,15 @@ extern "C" int orbgpu_search_for_triangulation_batch_dev(orbgpu_ctx *ctx, const 
             P.kf_n_free = s->kf_n_free; P.kf_n_nodes = s->kf_n_nodes; P.aux = s->aux; P.angle = s->angle;
             P.scale_factors = s->scale_factors; P.level_sigma2 = s->level_sigma2;
             P.n_feat = s->n_feat; P.n_levels = s->n_levels; P.cap_bytes = cap; P.max_free = s->max_free; P.n_pairs = n_pairs;
+            P.n_stages = n_stages; P.stage_bytes = (int)stage_bytes;
             P.kf1 = kf1_dev; P.kf2 = kf2_dev; P.ep = ep_dev; P.f12 = f12_dev;
             P.coarse = coarse; P.check_ori = check_ori;
             P.matches12 = matches12_dev; P.nmatches = nmatches_dev; P.counters = ctx->d_counters;
-            auto kern2 = triangulation_stream_kernel<CW>;
+            auto kern2 = triangulation_stream_kernel<NC, NG, NJ>;
+            const size_t smem2 = stage_bytes * n_stages;
             CU_TRY(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            int per_sm = 1;
-            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern2, CW * 32 + 32, smem2));
-            if (per_sm < 1) per_sm = 1;
-            if (per_sm > 2) per_sm = 2;
-            const int grid = n_pairs < ctx->sm_count * per_sm ? n_pairs : ctx->sm_count * per_sm;
-            kern2<<<grid, CW * 32 + 32, smem2, ctx->stream>>>(P);
+            const int grid = n_pairs < ctx->sm_count ? n_pairs : ctx->sm_count;
+            kern2<<<grid, (NC + NG + NJ + 1) * 32, smem2, ctx->stream>>>(P);
             LAUNCH_COUNT(ctx);
             CU_TRY(cudaGetLastError());
             return ORBGPU_OK;
