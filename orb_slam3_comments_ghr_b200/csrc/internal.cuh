@@ -43,6 +43,7 @@ struct orbgpu_ctx {
     unsigned long long *d_counters = nullptr; // [8] device counters: [0] comparisons, [1] overflow flag, ...
     unsigned long long *h_counters = nullptr; // pinned mirror
     int knn_engine = 0;
+    void *tri_timeline = nullptr; // debug time-stamp buffer (null = off)
     int tri_engine = 0; // 0 auto, 1 CTA-per-pair kernel, 2 persistent bulk-copy pipelined kernel
     // tcgen05 engine scratch (expanded database), owned by the context
     void *knn_expanded = nullptr;

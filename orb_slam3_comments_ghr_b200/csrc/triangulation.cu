@@ -356,24 +356,31 @@ triangulation_pairs_kernel(KfSetView s, int n_pairs, int max_free, int max_nodes
 // join table, the per-slot best keys and the candidate list of ONE pair.  Four roles, chained by mbarriers:
 //
 //   producer (1 warp)  waits empty[st]; reads the pair's metadata; ONE cp.async.bulk per keyframe -> full[st] (tx bytes)
-//   join     (NJ warps) waits full[st]; node a of keyframe 1 binary-searched in keyframe 2's node list (merge-join
-//                      :1113-1292); writes sCand[c1] = (first candidate, count) for every slot -> joined[st]
-//   compare  (NC warps) waits joined[st]; warps grab 32-slot chunks dynamically; lane owns CSR slot c1 of keyframe 1
-//                      and walks its node's candidates: 1 LDS.128 + 4 XOR + 4 POPC on the lo halves; a candidate
-//                      whose lo half is already <= TH_LOW (2 % of them) goes to the stage's list -> compared[st]
-//   post     (NG warps) fills the match row with -1 while waiting for compared[st]; one list entry per thread:
-//                      fetches the two 32-byte aux records {hi half, keypoint} (L2-prefetched by the compare warps),
-//                      finishes the distance, fp32 gates, atomicMin of the (dist, -idx2) key; winners write the
-//                      match row -> empty[st]
+//   join     (NJ warps) waits full[st]; fills the pair's match row with -1; node a of keyframe 1 binary-searched in
+//                      keyframe 2's node list (merge-join :1113-1292); writes sCand[c1] = (first candidate, count)
+//                      for every slot -> joined[st]
+//   compare  (NC warps) waits joined[st]; 32-slot chunks dealt round-robin; lane owns CSR slot c1 of keyframe 1 and
+//                      walks its node's candidates with a branch-free loop: 1 LDS.128 + 4 XOR + 4 POPC on the lo
+//                      halves, bit j of a per-slot mask = candidate j is already <= TH_LOW (2 % of them are).
+//                      Slots with a non-zero mask are compacted into the stage's list (one ballot per chunk) and
+//                      the aux records of their candidates are prefetched into L2 -> compared[st]
+//   post     (NG warps) waits compared[st]; one listed slot per thread: fetches the 32-byte aux records {hi half,
+//                      keypoint} of the flagged candidates, finishes the distances, fp32 gates, keeps the
+//                      (dist, -idx2) minimum and writes the match -> empty[st]
 //
 // The compare warps never meet a CTA-wide barrier: while they stream pair i, the post warps finish pair i-1, the join
 // warps prepare pair i+1 and the bulk copies of pair i+2 are in flight.
-constexpr int TS_SURV = 1024;
+constexpr int TS_OVF = 256; // (slot, candidate) entries of nodes with more than 32 candidates
 constexpr uint32_t ENT_NONE = 0xFFFFFFFFu;
+#ifdef TS_NO_PREFETCH
+#define TS_PREFETCH(...) ((void)0)
+#else
+#define TS_PREFETCH(...) asm volatile(__VA_ARGS__)
+#endif
 struct TsStageCtl {
     int k1, k2, m1, m2, nn1, nn2;
-    int n_list;     // candidates appended so far
-    int next_chunk; // dynamic 32-slot chunk counter of the compare warps
+    int n_list;     // slots with a non-zero mask listed so far
+    int n_ovf;      // entries in the overflow list
     float geo[12];  // f12[9], ep[2]
 };
 
@@ -445,40 +452,41 @@ struct TsParams {
     int coarse, check_ori;
     int32_t *matches12, *nmatches;
     unsigned long long *counters;
+    long long *timeline; // debug: [n_my of CTA 0][8] SM-clock stamps, or null
 };
 
-// One prefilter survivor ent = c1 | c2 << 13: finish the distance (:1180; lo halves from the stage, hi halves from the
-// aux records), epipole gate (:1191-1203, monocular), epipolar test (:1246), then the (dist, -idx2) reduction.
-// Returns the key (KEY_NONE when rejected) and w = c1 | feature id of slot c1 << 13 for the output step.
-__device__ __forceinline__ uint32_t ts_gate(uint32_t ent, const uint4 *lo1, const uint4 *lo2, const uint4 *__restrict__ aux1,
-                                            const uint4 *__restrict__ aux2, const float *geo, const float *sScale,
-                                            const float *sSigma, int coarse, uint32_t *best, uint32_t &w)
+// One prefilter survivor (slot c1 of keyframe 1 with its aux record {h1, q1} already loaded, slot c2 of keyframe 2):
+// finish the distance (:1180; lo halves from the stage, hi halves from the aux records), epipole gate (:1191-1203,
+// monocular), epipolar test (:1246).  Returns the (dist, -idx2) key, KEY_NONE when rejected.
+__device__ __forceinline__ uint32_t ts_gate_loaded(const uint4 a_lo, const uint4 h1, const uint4 q1, const uint4 b_lo, const uint4 h2,
+                                                   const uint4 q2, const float *geo, const float *sScale, const float *sSigma,
+                                                   int coarse)
 {
-    const int c1 = (int)(ent & 0x1FFF), c2 = (int)((ent >> 13) & 0x1FFF);
-    const uint4 h1 = aux1[2 * c1], q1 = aux1[2 * c1 + 1];
-    const uint4 h2 = aux2[2 * c2], q2 = aux2[2 * c2 + 1];
-    w = (uint32_t)c1 | (q1.w << 13);
-    const int dist = ham128(lo1[c1], lo2[c2]) + ham128(h1, h2);
+    const int dist = ham128(a_lo, b_lo) + ham128(h1, h2);
     if (dist > ORBGPU_TH_LOW) return KEY_NONE;
     const float x2 = __uint_as_float(q2.x), y2 = __uint_as_float(q2.y);
     const float dx = __fsub_rn(geo[9], x2), dy = __fsub_rn(geo[10], y2);
     if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, sScale[q2.z])) return KEY_NONE;
     if (!coarse && !epipolar_ok(geo, __uint_as_float(q1.x), __uint_as_float(q1.y), x2, y2, sSigma[q2.z])) return KEY_NONE;
-    const uint32_t key = ((uint32_t)dist << 20) | (0xFFFFFu - q2.w);
-    atomicMin(&best[c1], key);
-    return key;
+    return ((uint32_t)dist << 20) | (0xFFFFFu - q2.w);
+}
+__device__ __forceinline__ uint32_t ts_gate(const uint4 a_lo, const uint4 h1, const uint4 q1, int c2, const uint4 *lo2,
+                                            const uint4 *__restrict__ aux2, const float *geo, const float *sScale,
+                                            const float *sSigma, int coarse)
+{
+    return ts_gate_loaded(a_lo, h1, q1, lo2[c2], aux2[2 * c2], aux2[2 * c2 + 1], geo, sScale, sSigma, coarse);
 }
 
 template <int NC, int NG, int NJ>
 __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stream_kernel(const TsParams P)
 {
-    constexpr int GT = NG * 32, JT = NJ * 32;
+    constexpr int JT = NJ * 32;
     extern __shared__ __align__(128) unsigned char ts_smem[];
     __shared__ __align__(8) unsigned long long bars[4][4]; // [stage][full, joined, compared, empty]
     __shared__ TsStageCtl ctl[4];
     __shared__ float sScale[64], sSigma[64];
-    __shared__ int hist[ORBGPU_HISTO_LENGTH];
-    __shared__ int ind[3];
+    __shared__ int hist2[2][ORBGPU_HISTO_LENGTH + 2];
+    __shared__ int ind2[2][4];
 
     const int S = P.n_stages, cap = P.cap_bytes, mf = P.max_free;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -486,6 +494,7 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
     const int n_my = (P.n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const uint32_t bar0 = ts_smem_u32(&bars[0][0]);
     auto bar_of = [&](int st, int which) { return bar0 + (uint32_t)(st * 4 + which) * 8u; };
+    auto stamp = [&](int i, int ev) { if (P.timeline && blockIdx.x == 0) P.timeline[i * 8 + ev] = clock64(); };
     enum { B_FULL = 0, B_JOINED = 1, B_COMPARED = 2, B_EMPTY = 3 };
 
     if (t == 0) {
@@ -493,7 +502,7 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
             ts_mbar_init(bar_of(st, B_FULL), 1);
             ts_mbar_init(bar_of(st, B_JOINED), NJ);
             ts_mbar_init(bar_of(st, B_COMPARED), NC);
-            ts_mbar_init(bar_of(st, B_EMPTY), NG);
+            ts_mbar_init(bar_of(st, B_EMPTY), NG / 2);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -505,29 +514,46 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
 
     // per-stage carve-up of the dynamic shared memory
     auto stage_base = [&](int st) { return ts_smem + (size_t)st * P.stage_bytes; };
-    // [A cap][B cap][sCand mf][sBest mf][list TS_SURV][listW TS_SURV]
+    // [A cap][B cap][sCand mf][sMask mf][sBest mf][sList mf][sOvf TS_OVF]
 
     if (warp == NC + NG + NJ) {
-        // ---------------- producer warp
+        // ---------------- producer warp: the metadata of the next pair is fetched while the ring is still full, so
+        // that only the bulk copies themselves follow the empty[] signal
+        struct Next { int k1, k2, b1, b2, m1, m2, nn1, nn2; float g; };
+        auto fetch = [&](int i) {
+            Next x;
+            x.g = 0.f;
+            x.k1 = x.k2 = x.b1 = x.b2 = x.m1 = x.m2 = x.nn1 = x.nn2 = 0;
+            if (i < n_my) {
+                const int p = blockIdx.x + i * gridDim.x;
+                x.k1 = P.kf1[p]; x.k2 = P.kf2[p];
+                if (lane < 9) x.g = P.f12[9 * (size_t)p + lane];
+                else if (lane < 11) x.g = P.ep[2 * (size_t)p + lane - 9];
+                x.b1 = P.blob_bytes[x.k1]; x.b2 = P.blob_bytes[x.k2];
+                x.m1 = P.kf_n_free[x.k1]; x.m2 = P.kf_n_free[x.k2];
+                x.nn1 = P.kf_n_nodes[x.k1]; x.nn2 = P.kf_n_nodes[x.k2];
+            }
+            return x;
+        };
+        Next nx = fetch(0);
         for (int i = 0, st = 0, round = 0; i < n_my; i++) {
+            const Next cur = nx;
+            nx = fetch(i + 1);
             if (round > 0) ts_mbar_wait_relaxed(bar_of(st, B_EMPTY), (round - 1) & 1);
-            const int p = blockIdx.x + i * gridDim.x;
-            const int k1 = P.kf1[p], k2 = P.kf2[p];
+            if (lane == 0) stamp(i, 0);
             TsStageCtl &C = ctl[st];
-            if (lane < 9) C.geo[lane] = P.f12[9 * (size_t)p + lane];
-            else if (lane < 11) C.geo[lane] = P.ep[2 * (size_t)p + lane - 9];
+            if (lane < 11) C.geo[lane] = cur.g;
             __syncwarp();
             if (lane == 0) {
-                const int b1 = P.blob_bytes[k1], b2 = P.blob_bytes[k2];
-                C.k1 = k1; C.k2 = k2;
-                C.m1 = P.kf_n_free[k1]; C.m2 = P.kf_n_free[k2];
-                C.nn1 = P.kf_n_nodes[k1]; C.nn2 = P.kf_n_nodes[k2];
-                C.n_list = 0; C.next_chunk = 0;
+                C.k1 = cur.k1; C.k2 = cur.k2;
+                C.m1 = cur.m1; C.m2 = cur.m2;
+                C.nn1 = cur.nn1; C.nn2 = cur.nn2;
+                C.n_list = 0; C.n_ovf = 0;
                 const uint32_t bar = bar_of(st, B_FULL);
-                ts_mbar_expect_tx(bar, (uint32_t)(b1 + b2));
+                ts_mbar_expect_tx(bar, (uint32_t)(cur.b1 + cur.b2));
                 unsigned char *dst = stage_base(st);
-                ts_bulk_load(ts_smem_u32(dst), P.blob + (size_t)k1 * P.blob_stride, (uint32_t)b1, bar);
-                ts_bulk_load(ts_smem_u32(dst + cap), P.blob + (size_t)k2 * P.blob_stride, (uint32_t)b2, bar);
+                ts_bulk_load(ts_smem_u32(dst), P.blob + (size_t)cur.k1 * P.blob_stride, (uint32_t)cur.b1, bar);
+                ts_bulk_load(ts_smem_u32(dst + cap), P.blob + (size_t)cur.k2 * P.blob_stride, (uint32_t)cur.b2, bar);
             }
             __syncwarp();
             if (++st == S) { st = 0; round++; }
@@ -539,7 +565,19 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
         // ---------------- join warps
         const int jt = (warp - (NC + NG)) * 32 + lane;
         for (int i = 0, st = 0, round = 0; i < n_my; i++) {
+            {   // vMatches12(N, -1) (:1092): ordered before the post warps' match writes through joined[] -> compared[]
+                const int p = blockIdx.x + i * gridDim.x;
+                int32_t *row = P.matches12 + (size_t)p * n;
+                if ((n & 3) == 0) {
+                    int4 *row4 = (int4 *)row;
+                    for (int x = jt; x < (n >> 2); x += JT) row4[x] = make_int4(-1, -1, -1, -1);
+                } else {
+                    for (int x = jt; x < n; x += JT) row[x] = -1;
+                }
+                if (jt == 0) P.nmatches[p] = 0;
+            }
             ts_mbar_wait_relaxed(bar_of(st, B_FULL), round & 1);
+            if (jt == 0) stamp(i, 1);
             const TsStageCtl &C = ctl[st];
             const int m1 = C.m1, m2 = C.m2, nn1 = C.nn1, nn2 = C.nn2;
             unsigned char *base = stage_base(st);
@@ -547,7 +585,7 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
             const uint32_t *ids1 = (const uint32_t *)(off1 + nn1 + 1);
             const int32_t *off2 = (const int32_t *)((const uint4 *)(base + cap) + m2);
             const uint32_t *ids2 = (const uint32_t *)(off2 + nn2 + 1);
-            uint32_t *sCand = (uint32_t *)(base + 2 * (size_t)cap), *sBest = sCand + mf;
+            uint32_t *sCand = (uint32_t *)(base + 2 * (size_t)cap), *sBest = sCand + 2 * mf;
             for (int a = jt; a < nn1; a += JT) {
                 const uint32_t nid = ids1[a];
                 int lo = 0, hi = nn2;
@@ -564,6 +602,7 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
                 for (int c = s1; c < e1; c++) { sCand[c] = e; sBest[c] = KEY_NONE; }
             }
             __syncwarp();
+            if (jt == 0) stamp(i, 2);
             if (lane == 0) ts_mbar_arrive(bar_of(st, B_JOINED));
             if (++st == S) { st = 0; round++; }
         }
@@ -575,17 +614,18 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
         unsigned long long ncmp = 0;
         for (int i = 0, st = 0, round = 0; i < n_my; i++) {
             ts_mbar_wait(bar_of(st, B_JOINED), round & 1);
+            if (t == 0) stamp(i, 3);
             TsStageCtl &C = ctl[st];
             const int k1 = C.k1, k2 = C.k2, m1 = C.m1;
             unsigned char *base = stage_base(st);
             const uint4 *lo1 = (const uint4 *)base, *lo2 = (const uint4 *)(base + cap);
             const uint32_t *sCand = (const uint32_t *)(base + 2 * (size_t)cap);
-            uint32_t *sBest = (uint32_t *)sCand + mf, *sList = sBest + mf;
+            uint32_t *sMask = (uint32_t *)sCand + mf, *sBest = sMask + mf, *sList = sBest + mf, *sOvf = sList + mf;
             const uint4 *aux1 = P.aux + (size_t)k1 * n * 2, *aux2 = P.aux + (size_t)k2 * n * 2;
             // 32-slot chunks are dealt round-robin to the warps, rotated from pair to pair so that the odd chunk does
             // not always land on the same warps
-            for (int chunk = (warp + NC - (i % NC)) % NC; chunk * 32 < m1; chunk += NC) {
-                const int c1 = chunk * 32 + lane;
+            for (int c0 = ((warp + NC - (i % NC)) % NC) * 32; c0 < m1; c0 += NC * 32) {
+                const int c1 = c0 + lane;
                 uint32_t cand = 0;
                 uint4 a_lo = make_uint4(0, 0, 0, 0);
                 if (c1 < m1) {
@@ -594,50 +634,45 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
                 }
                 const int n2f = (int)(cand >> 16), s2 = (int)(cand & 0xFFFF);
                 ncmp += (unsigned)n2f;
-                const int maxn = __reduce_max_sync(FULL_MASK, n2f);
-                for (int j0 = 0; j0 < maxn; j0 += 32) { // one pass unless a node holds more than 32 candidates
-                    // branch-free inner loop: bit j of mask = candidate j0+j passes the 128-bit prefilter
-                    const int nb = min(max(n2f - j0, 0), 32);
-                    const uint4 *pb = lo2 + s2 + j0, *pe = pb + nb;
-                    uint32_t mask = 0, bit = 1;
+                // branch-free inner loop: bit j of mask = candidate j passes the 128-bit prefilter
+                const uint4 *pb = lo2 + s2, *pe = pb + min(n2f, 32);
+                uint32_t mask = 0, bit = 1;
 #pragma unroll 2
-                    for (; pb < pe; ++pb) {
-                        if (ham128(a_lo, *pb) <= ORBGPU_TH_LOW) mask |= bit; // a random pair fails here 99.6 % of the time
-                        bit <<= 1;
-                    }
-                    __syncwarp();
-                    const int cnt = __popc(mask);
-                    if (__ballot_sync(FULL_MASK, cnt != 0) == 0) continue;
-                    // one list reservation per warp: exclusive prefix sum of the hit counts
-                    int incl = cnt;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int u = __shfl_up_sync(FULL_MASK, incl, o);
-                        if (lane >= o) incl += u;
-                    }
-                    int slot0 = 0;
-                    if (lane == 31) slot0 = atomicAdd(&C.n_list, incl);
-                    slot0 = __shfl_sync(FULL_MASK, slot0, 31);
-                    int slot = slot0 + incl - cnt;
-                    while (mask) {
-                        const int c2 = s2 + j0 + __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const uint32_t e = (uint32_t)c1 | ((uint32_t)c2 << 13);
-                        if (slot < TS_SURV) {
-                            sList[slot] = e;
-                            // the post warps will read the two aux records: start pulling them into L2 now
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(aux1 + 2 * c1));
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(aux2 + 2 * c2));
-                        } else { // list full (adversarial inputs only): gate in place, output by slot owners
-                            uint32_t w;
-                            ts_gate(e, lo1, lo2, aux1, aux2, C.geo, sScale, sSigma, P.coarse, sBest, w);
-                        }
-                        slot++;
-                    }
-                    __syncwarp();
+                for (; pb < pe; ++pb) {
+                    if (ham128(a_lo, *pb) <= ORBGPU_TH_LOW) mask |= bit; // a random pair fails here 99.6 % of the time
+                    bit <<= 1;
                 }
+                __syncwarp();
+                // list the slots that have candidates left (one reservation per chunk), start pulling their aux records
+                const unsigned bal = __ballot_sync(FULL_MASK, mask != 0);
+                if (bal) {
+                    int slot0 = 0;
+                    if (lane == 0) slot0 = atomicAdd(&C.n_list, __popc(bal));
+                    slot0 = __shfl_sync(FULL_MASK, slot0, 0);
+                    if (mask) {
+                        sMask[c1] = mask;
+                        sList[slot0 + __popc(bal & lanemask_lt())] = (uint32_t)c1;
+                        TS_PREFETCH("prefetch.global.L2 [%0];" ::"l"(aux1 + 2 * c1));
+                        do {
+                            TS_PREFETCH("prefetch.global.L2 [%0];" ::"l"(aux2 + 2 * (s2 + __ffs(mask) - 1)));
+                            mask &= mask - 1;
+                        } while (mask);
+                    }
+                }
+                // a node with more than 32 candidates (rare with a real vocabulary): the rest goes through the overflow list
+                for (int j = 32; j < n2f; j++) {
+                    if (ham128(a_lo, lo2[s2 + j]) > ORBGPU_TH_LOW) continue;
+                    const int slot = atomicAdd(&C.n_ovf, 1);
+                    if (slot < TS_OVF) sOvf[slot] = (uint32_t)c1 | ((uint32_t)(s2 + j) << 13);
+                    else { // list full (adversarial inputs only): gate in place
+                        const uint32_t key = ts_gate(a_lo, aux1[2 * c1], aux1[2 * c1 + 1], s2 + j, lo2, aux2, C.geo, sScale, sSigma, P.coarse);
+                        if (key != KEY_NONE) atomicMin(&sBest[c1], key);
+                    }
+                }
+                __syncwarp();
             }
             __syncwarp();
+            if (t == 0) stamp(i, 4);
             if (lane == 0) ts_mbar_arrive(bar_of(st, B_COMPARED));
             if (++st == S) { st = 0; round++; }
         }
@@ -646,77 +681,104 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
         return;
     }
 
-    // ---------------- post warps
-    const int gt = (warp - NC) * 32 + lane;
-    for (int i = 0, st = 0, round = 0; i < n_my; i++) {
+    // ---------------- post warps: two groups of NG/2 warps take alternate pairs, so that each group has two compare
+    // periods to cover the round trips of its pair's gating step
+    constexpr int GT = (NG / 2) * 32;
+    const int grp = (warp - NC) / (NG / 2), gt = (warp - NC - grp * (NG / 2)) * 32 + lane;
+    const int bar_id = 2 + grp;
+    auto bar_post = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(GT) : "memory"); };
+    int *hist = hist2[grp], *ind = ind2[grp];
+    for (int i = 0, st = 0, round = 0; i < n_my; i++, st = (st + 1 == S ? 0 : st + 1), round += (st == 0)) {
+        if ((i & 1) != grp) continue;
         const int p = blockIdx.x + i * gridDim.x;
         int32_t *row = P.matches12 + (size_t)p * n;
-        // ---- vMatches12(N, -1) (:1092)
-        if ((n & 3) == 0) {
-            int4 *row4 = (int4 *)row;
-            for (int x = gt; x < (n >> 2); x += GT) row4[x] = make_int4(-1, -1, -1, -1);
-        } else {
-            for (int x = gt; x < n; x += GT) row[x] = -1;
-        }
-        if (gt == 0) P.nmatches[p] = 0;
+        if (P.check_ori && gt < ORBGPU_HISTO_LENGTH) hist[gt] = 0;
+        if (gt == 0 && grp == 0) stamp(i, 5);
         ts_mbar_wait_relaxed(bar_of(st, B_COMPARED), round & 1);
+        if (gt == 0 && grp == 0) stamp(i, 6);
         const TsStageCtl &C = ctl[st];
-        const int k1 = C.k1, k2 = C.k2, m1 = C.m1;
-        const int ns_all = C.n_list, ns = min(ns_all, TS_SURV);
+        const int k1 = C.k1, k2 = C.k2, m1 = C.m1, ns = C.n_list;
+        const int n_ovf_all = C.n_ovf, n_ovf = min(n_ovf_all, TS_OVF);
+        // a slot's candidates are all in its mask unless its node has more than 32: then (and for the rotation
+        // histogram) the per-slot minimum goes through sBest and the slot owners write the row after a barrier
+        const bool via_best = n_ovf_all > 0 || P.check_ori;
         unsigned char *base = stage_base(st);
         const uint4 *lo1 = (const uint4 *)base, *lo2 = (const uint4 *)(base + cap);
-        uint32_t *best = (uint32_t *)(base + 2 * (size_t)cap) + mf, *sList = best + mf, *sListW = sList + TS_SURV;
+        const uint32_t *sCand = (const uint32_t *)(base + 2 * (size_t)cap), *sMask = sCand + mf;
+        uint32_t *best = (uint32_t *)sMask + mf;
+        const uint32_t *sList = best + mf, *sOvf = sList + mf;
         const uint4 *aux1 = P.aux + (size_t)k1 * n * 2, *aux2 = P.aux + (size_t)k2 * n * 2;
-        // ---- gating: one list entry per thread
-        for (int e = gt; e < ns; e += GT) {
-            uint32_t w;
-            sList[e] = ts_gate(sList[e], lo1, lo2, aux1, aux2, C.geo, sScale, sSigma, P.coarse, best, w);
-            sListW[e] = w;
-        }
-        if (P.check_ori && gt < ORBGPU_HISTO_LENGTH) hist[gt] = 0;
-        ts_bar_post(GT);
-        // ---- output
-        const float *ang1 = P.angle + (size_t)k1 * n, *ang2 = P.angle + (size_t)k2 * n;
         int mine = 0;
-        // calls fn(f1, idx2) for every winning (slot, candidate) this thread is responsible for
-        auto for_each_winner = [&](auto &&fn) {
-            if (ns_all <= TS_SURV) { // the thread that gated the winning candidate reports it
-                for (int e = gt; e < ns; e += GT) {
-                    const uint32_t key = sList[e], w = sListW[e];
-                    if (key != KEY_NONE && best[w & 0x1FFF] == key) fn((int)(w >> 13), (int)(0xFFFFFu - (key & 0xFFFFFu)));
-                }
-            } else { // some candidates were gated in place by the compare warps: slot owners report
+        // ---- one listed slot per thread: finish the distances, gates, minimum
+        for (int e = gt; e < ns; e += GT) {
+            const int c1 = (int)sList[e];
+            uint32_t mask = sMask[c1];
+            const int s2 = (int)(sCand[c1] & 0xFFFF);
+            // the records of the slot and of its first two candidates are requested together: one round trip for
+            // nearly every slot (a third candidate is rare)
+            const int ca = s2 + __ffs(mask) - 1;
+            mask &= mask - 1;
+            const bool two = mask != 0;
+            const int cb = two ? s2 + __ffs(mask) - 1 : ca;
+            mask &= mask - 1;
+            const uint4 h1 = aux1[2 * c1], q1 = aux1[2 * c1 + 1];
+            const uint4 ha = aux2[2 * ca], qa = aux2[2 * ca + 1];
+            const uint4 hb = aux2[2 * cb], qb = aux2[2 * cb + 1];
+            const uint4 a_lo = lo1[c1];
+            uint32_t key = ts_gate_loaded(a_lo, h1, q1, lo2[ca], ha, qa, C.geo, sScale, sSigma, P.coarse);
+            if (two) key = min(key, ts_gate_loaded(a_lo, h1, q1, lo2[cb], hb, qb, C.geo, sScale, sSigma, P.coarse));
+            while (mask) {
+                const int c2 = s2 + __ffs(mask) - 1;
+                mask &= mask - 1;
+                key = min(key, ts_gate(a_lo, h1, q1, c2, lo2, aux2, C.geo, sScale, sSigma, P.coarse));
+            }
+            if (key == KEY_NONE) continue;
+            if (via_best) atomicMin(&best[c1], key);
+            else {
+                row[q1.w] = (int)(0xFFFFFu - (key & 0xFFFFFu));
+                mine++;
+            }
+        }
+        if (via_best) {
+            for (int e = gt; e < n_ovf; e += GT) {
+                const uint32_t en = sOvf[e];
+                const int c1 = (int)(en & 0x1FFF);
+                const uint32_t key = ts_gate(lo1[c1], aux1[2 * c1], aux1[2 * c1 + 1], (int)((en >> 13) & 0x1FFF), lo2, aux2, C.geo, sScale,
+                                             sSigma, P.coarse);
+                if (key != KEY_NONE) atomicMin(&best[c1], key);
+            }
+            bar_post();
+            // ---- output by slot owners
+            const float *ang1 = P.angle + (size_t)k1 * n, *ang2 = P.angle + (size_t)k2 * n;
+            if (P.check_ori) { // :1266-1277, :1295-1314
                 for (int c = gt; c < m1; c += GT) {
                     const uint32_t key = best[c];
-                    if (key != KEY_NONE) fn((int)aux1[2 * c + 1].w, (int)(0xFFFFFu - (key & 0xFFFFFu)));
+                    if (key == KEY_NONE) continue;
+                    const int bin = rot_bin(ang1[aux1[2 * c + 1].w], ang2[(int)(0xFFFFFu - (key & 0xFFFFFu))]);
+                    if (bin >= 0 && bin < ORBGPU_HISTO_LENGTH) atomicAdd(&hist[bin], 1);
                 }
+                bar_post();
+                if (gt == 0) three_maxima(hist, ORBGPU_HISTO_LENGTH, ind[0], ind[1], ind[2]);
+                bar_post();
             }
-        };
-        if (P.check_ori) { // :1266-1277, :1295-1314
-            for_each_winner([&](int f1, int idx2) {
-                const int bin = rot_bin(ang1[f1], ang2[idx2]);
-                if (bin >= 0 && bin < ORBGPU_HISTO_LENGTH) atomicAdd(&hist[bin], 1);
-            });
-            ts_bar_post(GT);
-            if (gt == 0) three_maxima(hist, ORBGPU_HISTO_LENGTH, ind[0], ind[1], ind[2]);
-            ts_bar_post(GT);
-            for_each_winner([&](int f1, int idx2) {
-                const int bin = rot_bin(ang1[f1], ang2[idx2]);
-                if (bin >= 0 && bin < ORBGPU_HISTO_LENGTH && bin != ind[0] && bin != ind[1] && bin != ind[2]) return;
+            for (int c = gt; c < m1; c += GT) {
+                const uint32_t key = best[c];
+                if (key == KEY_NONE) continue;
+                const int f1 = (int)aux1[2 * c + 1].w, idx2 = (int)(0xFFFFFu - (key & 0xFFFFFu));
+                if (P.check_ori) {
+                    const int bin = rot_bin(ang1[f1], ang2[idx2]);
+                    if (bin >= 0 && bin < ORBGPU_HISTO_LENGTH && bin != ind[0] && bin != ind[1] && bin != ind[2]) continue;
+                }
                 row[f1] = idx2;
                 mine++;
-            });
-        } else {
-            for_each_winner([&](int f1, int idx2) {
-                row[f1] = idx2;
-                mine++;
-            });
+            }
+            bar_post(); // hist / ind are reused by the next pair
         }
         for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(FULL_MASK, mine, o);
         if (lane == 0 && mine) atomicAdd(&P.nmatches[p], mine);
         __syncwarp();
+        if (gt == 0 && grp == 0) stamp(i, 7);
         if (lane == 0) ts_mbar_arrive(bar_of(st, B_EMPTY));
-        if (++st == S) { st = 0; round++; }
     }
 }
 
@@ -803,6 +865,14 @@ extern "C" int orbgpu_kfset_upload(orbgpu_ctx *ctx, const orbgpu_kfset_host *h, 
     return ORBGPU_OK;
 }
 
+// development aid (not in the public header): device buffer receiving CTA 0's pipeline time stamps
+extern "C" int orbgpu_debug_triangulation_timeline(orbgpu_ctx *ctx, void *dev_buf)
+{
+    ARG_TRY(ctx);
+    ctx->tri_timeline = dev_buf;
+    return ORBGPU_OK;
+}
+
 extern "C" int orbgpu_triangulation_set_engine(orbgpu_ctx *ctx, int32_t engine)
 {
     ARG_TRY(ctx && engine >= 0 && engine <= 2);
@@ -823,12 +893,12 @@ extern "C" int orbgpu_search_for_triangulation_batch_dev(orbgpu_ctx *ctx, const 
     // engine 2: persistent warp-specialised pipeline (monocular sets; bOnlyStereo on a monocular set matches nothing
     // and is left to the per-pair kernel)
     {
-        constexpr int NC = 16, NG = 4, NJ = 2; // compare / post / join warps (+ 1 producer warp = 736 threads)
+        constexpr int NC = 16, NG = 12, NJ = 2; // compare / post (two groups) / join warps (+ 1 producer warp = 992 threads)
         const int cap = (s->max_blob + 127) & ~127;
-        const size_t stage_bytes = (2 * (size_t)cap + (size_t)s->max_free * 8 + (size_t)TS_SURV * 8 + 127) & ~size_t(127);
+        const size_t stage_bytes = (2 * (size_t)cap + (size_t)s->max_free * 16 + (size_t)TS_OVF * 4 + 127) & ~size_t(127);
         int n_stages = (int)((227 * 1024 - 2048) / stage_bytes);
         if (n_stages > 4) n_stages = 4;
-        const bool can = !s->u_right && !only_stereo && n_stages >= 2 && s->max_free <= 8192;
+        const bool can = !s->u_right && !only_stereo && n_stages >= 3 && s->max_free <= 8192; // each post group holds a stage
         if (ctx->tri_engine == 2 && !can)
             return orbgpu_fail(ORBGPU_ERR_INVALID, "triangulation engine 2 needs a monocular keyframe set that fits the shared-memory ring");
         if (can && ctx->tri_engine != 1) {
@@ -841,6 +911,7 @@ extern "C" int orbgpu_search_for_triangulation_batch_dev(orbgpu_ctx *ctx, const 
             P.kf1 = kf1_dev; P.kf2 = kf2_dev; P.ep = ep_dev; P.f12 = f12_dev;
             P.coarse = coarse; P.check_ori = check_ori;
             P.matches12 = matches12_dev; P.nmatches = nmatches_dev; P.counters = ctx->d_counters;
+            P.timeline = (long long *)ctx->tri_timeline;
             auto kern2 = triangulation_stream_kernel<NC, NG, NJ>;
             const size_t smem2 = stage_bytes * n_stages;
             CU_TRY(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
