@@ -43,33 +43,94 @@ __global__ void init_candidates_kernel(FrameView f1, FrameView f2, const float2 
     }
 }
 
-__global__ void __launch_bounds__(256)
+// Ordered pass: one CTA.  All threads first compact the non-empty candidate lists into shared memory (block scan of
+// the counts) together with vMatchedDistance / vnMatches21, so that the single warp that replays the reference's
+// loop order only touches shared memory: ~100 cycles per level-0 keypoint instead of several L2 round trips.
+constexpr int INIT_THREADS = 1024;
+constexpr int INIT_LIST_CAP = 24 * 1024; // staged list entries (96 KB); larger cases replay from global memory
+__global__ void __launch_bounds__(INIT_THREADS)
 init_resolve_kernel(FrameView f1, FrameView f2, float2 *__restrict__ prev, const uint32_t *__restrict__ lists, int stride,
-                    const int32_t *__restrict__ counts, float nnratio, int check_ori, int32_t *__restrict__ vMatchedDistance,
-                    int32_t *__restrict__ vnMatches21, int32_t *__restrict__ bin_of, int32_t *__restrict__ matches12,
-                    int32_t *__restrict__ nmatches_out)
+                    const int32_t *__restrict__ counts, float nnratio, int check_ori, int32_t *__restrict__ bin_of,
+                    int32_t *__restrict__ matches12, int32_t *__restrict__ nmatches_out)
 {
+    extern __shared__ int init_smem[];
+    int *vMatchedDistance = init_smem;           // [n2]
+    int *vnMatches21 = vMatchedDistance + f2.n;  // [n2]
+    int *sAct = vnMatches21 + f2.n;              // [n1] active (non-empty) F1 keypoints, ascending
+    int *sOff = sAct + f1.n;                     // [n1] start of their lists
+    uint32_t *sLists = (uint32_t *)(sOff + f1.n); // [INIT_LIST_CAP]
     __shared__ int hist[ORBGPU_HISTO_LENGTH];
     __shared__ int ind[3];
-    __shared__ int s_nmatches, s_removed;
-    const int t = threadIdx.x, lane = t & 31;
-    for (int i = t; i < f2.n; i += blockDim.x) {
+    __shared__ int s_nmatches, s_removed, s_nact, s_total;
+    __shared__ int warp_cnt[32], warp_act[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int i = t; i < f2.n; i += INIT_THREADS) {
         vMatchedDistance[i] = INT_MAX; // :752
         vnMatches21[i] = -1;           // :754
     }
-    for (int i = t; i < f1.n; i += blockDim.x) {
+    for (int i = t; i < f1.n; i += INIT_THREADS) {
         matches12[i] = -1; // :739
         bin_of[i] = -1;
     }
     if (t < ORBGPU_HISTO_LENGTH) hist[t] = 0;
     if (t == 0) { s_nmatches = 0; s_removed = 0; }
+    // ---- block scan over contiguous chunks of F1 keypoints: list offsets and the compact index of the active ones
+    const int per = (f1.n + INIT_THREADS - 1) / INIT_THREADS;
+    const int lo = min(f1.n, t * per), hi = min(f1.n, lo + per);
+    int my_cnt = 0, my_act = 0;
+    for (int i = lo; i < hi; i++) {
+        const int c = counts[i];
+        my_cnt += c;
+        my_act += c > 0;
+    }
+    int inc_cnt = my_cnt, inc_act = my_act;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(FULL_MASK, inc_cnt, o), b = __shfl_up_sync(FULL_MASK, inc_act, o);
+        if (lane >= o) { inc_cnt += a; inc_act += b; }
+    }
+    if (lane == 31) { warp_cnt[warp] = inc_cnt; warp_act[warp] = inc_act; }
     __syncthreads();
+    if (warp == 0) {
+        int a = warp_cnt[lane], b = warp_act[lane];
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(FULL_MASK, a, o), v = __shfl_up_sync(FULL_MASK, b, o);
+            if (lane >= o) { a += u; b += v; }
+        }
+        warp_cnt[lane] = a; warp_act[lane] = b;
+        if (lane == 31) { s_total = a; s_nact = b; }
+    }
+    __syncthreads();
+    const bool staged = s_total <= INIT_LIST_CAP;
+    {
+        int off = (warp ? warp_cnt[warp - 1] : 0) + inc_cnt - my_cnt;
+        int k = (warp ? warp_act[warp - 1] : 0) + inc_act - my_act;
+        for (int i = lo; i < hi; i++) {
+            const int c = counts[i];
+            if (c > 0) {
+                sAct[k] = i;
+                sOff[k] = staged ? off : i * stride;
+                k++;
+                off += c;
+            }
+        }
+    }
+    __syncthreads();
+    const int nact = s_nact;
+    if (staged) { // one warp per active keypoint copies its list
+        for (int k = warp; k < nact; k += INIT_THREADS / 32) {
+            const int i1 = sAct[k], c = counts[i1];
+            const uint32_t *src = lists + (size_t)i1 * stride;
+            for (int p = lane; p < c; p += 32) sLists[sOff[k] + p] = src[p];
+        }
+    }
+    __syncthreads();
+    const uint32_t *L = staged ? sLists : lists;
     if (t < 32) {
         int nmatches = 0;
-        for (int i1 = 0; i1 < f1.n; i1++) {
-            const int cnt = counts[i1];
-            if (cnt == 0) continue; // level > 0 (:762) or empty window (:771)
-            const uint32_t *lst = lists + (size_t)i1 * stride;
+        for (int k = 0; k < nact; k++) { // keypoints with level > 0 (:762) or an empty window (:771) are not listed
+            const int i1 = sAct[k];
+            const int cnt = (k + 1 < nact && staged) ? sOff[k + 1] - sOff[k] : counts[i1];
+            const uint32_t *lst = L + sOff[k];
             uint32_t b1 = KEY_NONE, b2 = KEY_NONE;
             for (int base = 0; base < cnt; base += 32) {
                 const int p = base + lane;
@@ -97,14 +158,8 @@ init_resolve_kernel(FrameView f1, FrameView f2, float2 *__restrict__ prev, const
                             matches12[i1] = bestIdx2;
                             vnMatches21[bestIdx2] = i1;
                             vMatchedDistance[bestIdx2] = bestDist;
+                            bin_of[i1] = bestIdx2; // partner at accept time (for the rotation histogram)
                             nmatches++;
-                            if (check_ori) { // :826-840
-                                const int bin = rot_bin(f1.angle[i1], f2.angle[bestIdx2]);
-                                if (bin >= 0 && bin < ORBGPU_HISTO_LENGTH) {
-                                    hist[bin]++;
-                                    bin_of[i1] = bin;
-                                }
-                            }
                         }
                     }
                 }
@@ -114,19 +169,31 @@ init_resolve_kernel(FrameView f1, FrameView f2, float2 *__restrict__ prev, const
         if (lane == 0) s_nmatches = nmatches;
     }
     __syncthreads();
-    if (check_ori) { // :846-869
+    if (check_ori) {
+        // :826-840 -- every keypoint that was accepted goes into its bin, also when it is displaced later (:813-817 do
+        // not touch rotHist).  The replay left the accepted partner in bin_of; the angles are fetched here, in parallel.
+        for (int i1 = t; i1 < f1.n; i1 += INIT_THREADS) {
+            const int i2 = bin_of[i1];
+            int bin = -1;
+            if (i2 >= 0) {
+                bin = rot_bin(f1.angle[i1], f2.angle[i2]);
+                if (bin >= 0 && bin < ORBGPU_HISTO_LENGTH) atomicAdd(&hist[bin], 1); else bin = -1;
+            }
+            bin_of[i1] = bin;
+        }
+        __syncthreads();
         if (t == 0) three_maxima(hist, ORBGPU_HISTO_LENGTH, ind[0], ind[1], ind[2]);
         __syncthreads();
-        for (int i1 = t; i1 < f1.n; i1 += blockDim.x) {
+        for (int i1 = t; i1 < f1.n; i1 += INIT_THREADS) { // :846-869
             const int b = bin_of[i1];
             if (b >= 0 && b != ind[0] && b != ind[1] && b != ind[2] && matches12[i1] >= 0) {
                 matches12[i1] = -1;
                 atomicAdd(&s_removed, 1);
             }
         }
-        __syncthreads();
     }
-    for (int i1 = t; i1 < f1.n; i1 += blockDim.x) { // :873-875
+    __syncthreads();
+    for (int i1 = t; i1 < f1.n; i1 += INIT_THREADS) { // :873-875
         const int m = matches12[i1];
         if (m >= 0) prev[i1] = f2.xy[m];
     }
@@ -149,20 +216,23 @@ extern "C" int orbgpu_search_for_initialization(orbgpu_ctx *ctx, const orbgpu_fr
     if (n1 == 0) return ORBGPU_OK;
     const int stride = n2 > 0 ? n2 : 1;
     const size_t b1 = align256((size_t)n1 * 4), b2 = align256((size_t)(n2 + 1) * 4);
-    rc = arena_reserve(ctx, align256((size_t)n1 * 8) + align256((size_t)n1 * stride * 4) + 3 * b1 + 2 * b2 + 256);
+    rc = arena_reserve(ctx, align256((size_t)n1 * 8) + align256((size_t)n1 * stride * 4) + 3 * b1 + 256);
+    (void)b2;
     if (rc) return rc;
     float2 *d_prev = (float2 *)arena_take(ctx, (size_t)n1 * 8);
     uint32_t *lists = (uint32_t *)arena_take(ctx, (size_t)n1 * stride * 4);
     int32_t *counts = (int32_t *)arena_take(ctx, n1 * 4), *bin_of = (int32_t *)arena_take(ctx, n1 * 4),
             *d_m12 = (int32_t *)arena_take(ctx, n1 * 4);
-    int32_t *vmd = (int32_t *)arena_take(ctx, (n2 + 1) * 4), *vn21 = (int32_t *)arena_take(ctx, (n2 + 1) * 4);
     int32_t *d_nm = (int32_t *)arena_take(ctx, 256);
     CU_TRY(cudaMemcpyAsync(d_prev, prev_matched_xy, (size_t)n1 * 8, cudaMemcpyHostToDevice, ctx->stream));
     const FrameView v1 = frame_view(f1), v2 = frame_view(f2);
     init_candidates_kernel<<<(n1 * 32 + 255) / 256, 256, 0, ctx->stream>>>(v1, v2, d_prev, (float)window_size, lists, stride, counts,
                                                                           ctx->d_counters);
-    init_resolve_kernel<<<1, 256, 0, ctx->stream>>>(v1, v2, d_prev, lists, stride, counts, nnratio, check_ori, vmd, vn21, bin_of,
-                                                    d_m12, d_nm);
+    const size_t smem = ((size_t)2 * n2 + (size_t)2 * n1 + INIT_LIST_CAP) * 4;
+    if (smem > 220 * 1024) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "frames too large for the shared-memory replay state");
+    CU_TRY(cudaFuncSetAttribute(init_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    init_resolve_kernel<<<1, INIT_THREADS, smem, ctx->stream>>>(v1, v2, d_prev, lists, stride, counts, nnratio, check_ori, bin_of, d_m12,
+                                                                d_nm);
     ctx->launches += 2;
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(matches12, d_m12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -66,61 +66,101 @@ __global__ void proj_candidates_kernel(FrameView f, MapPointsView mp, float th, 
     if (lane == 0) counts[m] = cnt;
 }
 
-// one warp replays the map points in vpMapPoints order
-__global__ void __launch_bounds__(256)
+// Ordered pass.  The reference walks vpMapPoints in order and skips a keypoint whose current map point has
+// Observations() > 0 (:102-104), so map point m sees the assignments of the map points before it.  A keypoint k is
+// therefore unavailable to m iff it was locked on entry (prior Observations() > 0) or some m' < m with
+// Observations() > 0 chose it: lock[k] = min such m' (-1 when locked on entry).  The choices and the lock times
+// define each other through a triangular system (m only depends on m' < m); it is solved by fixed-point iteration --
+// every round re-decides all map points in parallel against the previous round's lock times; map point 0 is right
+// after round 0, and by induction one more map point prefix is right after every round, so the fixed point is the
+// reference's sequential result (typically reached in 2-3 rounds: windows rarely chain).
+// One CTA: lock times live in shared memory, a thread owns map points m = t, t+T, ...
+constexpr int RESOLVE_THREADS = 1024;
+__global__ void __launch_bounds__(RESOLVE_THREADS)
 proj_resolve_kernel(FrameView f, MapPointsView mp, const uint32_t *__restrict__ lists, int stride,
-                    const int32_t *__restrict__ counts, float nnratio, int32_t *__restrict__ cur_obs,
-                    int32_t *__restrict__ kp_mp, int32_t *__restrict__ nmatches_out, unsigned long long *__restrict__ counters)
+                    const int32_t *__restrict__ counts, float nnratio, const int32_t *__restrict__ prior_obs,
+                    int32_t *__restrict__ choice, int32_t *__restrict__ kp_mp, int32_t *__restrict__ nmatches_out,
+                    unsigned long long *__restrict__ counters)
 {
-    const int lane = threadIdx.x & 31;
-    if (threadIdx.x >= 32) return;
-    int nmatches = 0;
-    unsigned long long ncmp = 0;
-    for (int m = 0; m < mp.n; m++) {
-        const int cnt = counts[m];
-        if (cnt == 0) continue; // filtered (:55-62) or empty window (:84)
-        const uint32_t *lst = lists + (size_t)m * stride;
-        uint32_t b1 = KEY_NONE, b2 = KEY_NONE;
-        int nvalid = 0;
-        for (int base = 0; base < cnt; base += 32) {
-            const int p = base + lane;
-            if (p < cnt) {
-                const uint32_t e = lst[p];
-                const int idx = (int)(e & 0xFFFFF);
-                if (!(cur_obs[idx] > 0)) { // :102-104
-                    top2_push(b1, b2, (e & 0xFFF00000u) | (uint32_t)p);
-                    nvalid++;
+    extern __shared__ int lock_time[]; // [f.n]
+    __shared__ int s_changed, s_nmatches;
+    __shared__ unsigned long long s_ncmp;
+    const int t = threadIdx.x;
+    for (int k = t; k < f.n; k += RESOLVE_THREADS) lock_time[k] = prior_obs[k] > 0 ? -1 : 0x7FFFFFFF;
+    for (int m = t; m < mp.n; m += RESOLVE_THREADS) choice[m] = -2; // "not decided yet"
+    if (t == 0) s_changed = 0;
+    __syncthreads();
+    for (;;) {
+        int nm = 0;
+        unsigned long long ncmp = 0;
+        bool changed = false;
+        for (int m = t; m < mp.n; m += RESOLVE_THREADS) {
+            const int cnt = counts[m];
+            int pick = -1;
+            if (cnt > 0) { // else filtered (:55-62) or empty window (:84)
+                const uint32_t *lst = lists + (size_t)m * stride;
+                int bestDist = 256, bestDist2 = 256, bestIdx = -1, idx2 = -1; // :89-93
+                for (int p = 0; p < cnt; p++) {
+                    const uint32_t e = lst[p];
+                    const int idx = (int)(e & 0xFFFFF), dist = (int)(e >> 20);
+                    if (lock_time[idx] < m) continue; // :102-104
+                    ncmp++;                           // DescriptorDistance is only called past the skip rule
+                    if (dist < bestDist) {            // :125-141
+                        bestDist2 = bestDist; idx2 = bestIdx;
+                        bestDist = dist; bestIdx = idx;
+                    } else if (dist < bestDist2) {
+                        bestDist2 = dist; idx2 = idx;
+                    }
+                }
+                if (bestIdx >= 0 && bestDist <= ORBGPU_TH_HIGH) { // :147
+                    const int bestLevel = f.octave[bestIdx], bestLevel2 = idx2 >= 0 ? f.octave[idx2] : -1;
+                    const float lim = __fmul_rn(nnratio, (float)bestDist2);
+                    if (!(bestLevel == bestLevel2 && (float)bestDist > lim)) pick = bestIdx; // :151-154
                 }
             }
-        }
-        ncmp += nvalid; // DescriptorDistance is only called for candidates that pass the skip rule
-        uint32_t m1, m2;
-        warp_top2(b1, b2, m1, m2);
-        if (m1 != KEY_NONE && lane == 0) {
-            const int bestDist = (int)(m1 >> 20);
-            if (bestDist <= ORBGPU_TH_HIGH) { // :147
-                const int bestIdx = (int)(lst[m1 & 0xFFFFF] & 0xFFFFF);
-                const int bestLevel = f.octave[bestIdx];
-                int bestDist2 = 256, bestLevel2 = -1;
-                if (m2 != KEY_NONE) {
-                    bestDist2 = (int)(m2 >> 20);
-                    bestLevel2 = f.octave[lst[m2 & 0xFFFFF] & 0xFFFFF];
-                }
-                const float lim = __fmul_rn(nnratio, (float)bestDist2);
-                const bool reject = (bestLevel == bestLevel2) && ((float)bestDist > lim);  // :151
-                if (!reject && (bestLevel != bestLevel2 || (float)bestDist <= lim)) {       // :154
-                    kp_mp[bestIdx] = m;                                                    // :156
-                    cur_obs[bestIdx] = mp.n_obs[m];
-                    nmatches++;
-                }
+            if (pick != choice[m]) {
+                choice[m] = pick;
+                changed = true;
             }
+            nm += pick >= 0;
         }
-        __syncwarp();
-    }
-    for (int off = 16; off; off >>= 1) ncmp += __shfl_xor_sync(FULL_MASK, ncmp, off);
-    if (lane == 0) {
-        *nmatches_out = nmatches;
-        counters[0] = ncmp;
+        if (changed) s_changed = 1;
+        __syncthreads();
+        const bool again = s_changed != 0;
+        __syncthreads();
+        if (!again) { // fixed point: publish
+            if (t == 0) { s_nmatches = 0; s_ncmp = 0; }
+            __syncthreads();
+            for (int o = 16; o; o >>= 1) {
+                nm += __shfl_xor_sync(FULL_MASK, nm, o);
+                ncmp += __shfl_xor_sync(FULL_MASK, ncmp, o);
+            }
+            if ((t & 31) == 0) {
+                if (nm) atomicAdd(&s_nmatches, nm);
+                if (ncmp) atomicAdd(&s_ncmp, ncmp);
+            }
+            // F.mvpMapPoints[bestIdx] = pMP (:156): the last map point that chose a keypoint keeps it
+            for (int m = t; m < mp.n; m += RESOLVE_THREADS)
+                if (choice[m] >= 0) kp_mp[choice[m]] = -1; // whatever the keypoint held on entry is replaced
+            __syncthreads();
+            for (int m = t; m < mp.n; m += RESOLVE_THREADS)
+                if (choice[m] >= 0) atomicMax(&kp_mp[choice[m]], m);
+            __syncthreads();
+            if (t == 0) {
+                *nmatches_out = s_nmatches;
+                counters[0] = s_ncmp;
+            }
+            return;
+        }
+        // lock times of this round's choices
+        if (t == 0) s_changed = 0;
+        for (int k = t; k < f.n; k += RESOLVE_THREADS) lock_time[k] = prior_obs[k] > 0 ? -1 : 0x7FFFFFFF;
+        __syncthreads();
+        for (int m = t; m < mp.n; m += RESOLVE_THREADS) {
+            const int c = choice[m];
+            if (c >= 0 && mp.n_obs[m] > 0) atomicMin(&lock_time[c], m);
+        }
+        __syncthreads();
     }
 }
 
@@ -153,7 +193,7 @@ extern "C" int orbgpu_search_by_projection_local(orbgpu_ctx *ctx, const orbgpu_f
     const int stride = n;
     rc = stage_reserve(ctx, up_bytes);
     if (rc) return rc;
-    rc = arena_reserve(ctx, up_bytes + align256((size_t)M * stride * 4) + align256((size_t)M * 4) + 512);
+    rc = arena_reserve(ctx, up_bytes + align256((size_t)M * stride * 4) + 2 * align256((size_t)M * 4) + 512);
     if (rc) return rc;
     char *H = ctx->h_stage;
     memcpy(H + o_desc, mps->desc, (size_t)M * 32);
@@ -170,8 +210,9 @@ extern "C" int orbgpu_search_by_projection_local(orbgpu_ctx *ctx, const orbgpu_f
     char *D = (char *)arena_take(ctx, up_bytes);
     uint32_t *lists = (uint32_t *)arena_take(ctx, (size_t)M * stride * 4);
     int32_t *counts = (int32_t *)arena_take(ctx, (size_t)M * 4);
+    int32_t *choice = (int32_t *)arena_take(ctx, (size_t)M * 4);
     int32_t *d_nm = (int32_t *)arena_take(ctx, 256);
-    if (!D || !lists || !counts || !d_nm) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
+    if (!D || !lists || !counts || !choice || !d_nm) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
     CU_TRY(cudaMemcpyAsync(D, H, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
     MapPointsView mv;
     mv.n = M;
@@ -183,7 +224,12 @@ extern "C" int orbgpu_search_by_projection_local(orbgpu_ctx *ctx, const orbgpu_f
     const FrameView v = frame_view(f);
     proj_candidates_kernel<<<(M * 32 + 255) / 256, 256, 0, ctx->stream>>>(v, mv, th, far_points, th_far_points, lists, stride, counts,
                                                                          ctx->d_counters);
-    proj_resolve_kernel<<<1, 32, 0, ctx->stream>>>(v, mv, lists, stride, counts, nnratio, cur_obs, d_kpmp, d_nm, ctx->d_counters);
+    const size_t lock_bytes = (size_t)n * sizeof(int);
+    if (lock_bytes > 200 * 1024) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "frame too large for the shared-memory lock table");
+    if (lock_bytes > 48 * 1024)
+        CU_TRY(cudaFuncSetAttribute(proj_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lock_bytes));
+    proj_resolve_kernel<<<1, RESOLVE_THREADS, lock_bytes, ctx->stream>>>(v, mv, lists, stride, counts, nnratio, cur_obs, choice, d_kpmp,
+                                                                        d_nm, ctx->d_counters);
     ctx->launches += 2;
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(kp_mp, d_kpmp, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
