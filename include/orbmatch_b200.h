@@ -154,6 +154,43 @@ int orbgpu_search_by_projection_local(orbgpu_ctx *ctx, const orbgpu_frame *f, co
                                       float th, int32_t far_points, float th_far_points, float nnratio,
                                       const int32_t *kp_prior_obs, int32_t *kp_mp, int32_t *nmatches);
 
+/* ---- a6: the projection-gated searches that do their own projection: SearchByProjection(Cur, Last) (ORBmatcher.cc:1957-2191),
+ * SearchByProjection(Cur, KF, sAlreadyFound) (:2203-2330), SearchByProjection(KF, Sim3, ...) x2 (:498-733),
+ * Fuse x2 (:1330-1682), SearchBySim3 (:1684-1955).  They share one skeleton after the per-point prologue
+ * (SE3/Sim3 transform, camera projection, frustum / distance / viewing-angle gates, PredictScale): a window search
+ * around (u, v) with an octave filter, optional per-candidate gates, best-only selection (strict <, first
+ * candidate in GetFeaturesInArea order wins) and an acceptance threshold.  The prologue is evaluated by the caller
+ * with its own Sophus / Eigen (include/orbmatch_b200/ORBmatcher.hpp), because that arithmetic is not vendored in the
+ * reference; everything from the window on runs here. */
+typedef struct orbgpu_projpoints_host {
+    int32_t n;
+    const uint8_t *desc;       /* [n][32] MapPoint::GetDescriptor() */
+    const float *uv;           /* [n][2]  projection into the target frame */
+    const float *radius;       /* [n]     th * mvScaleFactors[level] */
+    const int32_t *min_level;  /* [n]     minLevel of Frame::GetFeaturesInArea (Frame.cc:868, :919); the KeyFrame callers' */
+    const int32_t *max_level;  /* [n]     `kpLevel < nPredictedLevel-1 || kpLevel > nPredictedLevel` is (level-1, level) */
+    const float *ur;           /* [n] or NULL: predicted right-image coordinate uv(0) - mbf*invz (stereo / chi2 gates) */
+    const uint8_t *active;     /* [n] 0: dropped by the caller's prologue gates */
+    const uint8_t *locks;      /* [n] or NULL (all 1): once this point takes a keypoint, later points skip that keypoint */
+    const float *angle;        /* [n] or NULL: angle of the source keypoint (rotation histogram) */
+} orbgpu_projpoints_host;
+typedef struct orbgpu_projsearch_params {
+    float max_dist;       /* accept iff (float)bestDist <= max_dist (TH_HIGH, ORBdist, TH_LOW*ratioHamming, TH_LOW) */
+    int32_t ordered;      /* 1: points in order, a keypoint that is locked (kp_locked on entry, or taken by an earlier locking
+                             point) is skipped (:2046-2049, :580-581); 0: every point independently (Fuse, SearchBySim3) */
+    int32_t stereo_gate;  /* 1: skip a candidate with u_right > 0 and |ur - u_right| > radius (:2052-2059) */
+    int32_t chi2_gate;    /* 1: Fuse reprojection gate (:1463-1492): e2*invSigma2[level] > 7.8 (u_right >= 0) / 5.99 */
+    int32_t check_ori;    /* 1: rotation-histogram cull over the accepted matches (:2163-2186) */
+    const float *inv_level_sigma2; /* [frame n_levels] mvInvLevelSigma2, needed when chi2_gate */
+} orbgpu_projsearch_params;
+/* kp_locked [frame n] in (may be NULL): keypoints unavailable on entry.
+ * best_idx / best_dist [n] out: accepted keypoint of every point (-1 none) BEFORE the histogram cull, and its distance.
+ * kp_owner [frame n] out (may be NULL): index of the LAST point that took each keypoint, -1 when none or culled
+ * (what the reference leaves in CurrentFrame.mvpMapPoints / vpMatched).  nmatches: accepted minus culled entries. */
+int orbgpu_search_projected(orbgpu_ctx *ctx, const orbgpu_frame *f, const orbgpu_projpoints_host *pts,
+                            const orbgpu_projsearch_params *prm, const uint8_t *kp_locked, int32_t *best_idx,
+                            int32_t *best_dist, int32_t *kp_owner, int32_t *nmatches);
+
 /* ---- a11/a12: TemplatedVocabulary::transform (TemplatedVocabulary.h:1127-1194, 1216-1258) */
 int orbgpu_voc_upload(orbgpu_ctx *ctx, const orbgpu_voc_host *v, orbgpu_voc **out);
 void orbgpu_voc_destroy(orbgpu_voc *v);

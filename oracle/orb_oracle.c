@@ -324,6 +324,103 @@ int oracle_search_by_projection_local(const orbgpu_frame_host *f, const orbgpu_m
     return nmatches;
 }
 
+/* The common search core of the self-projecting overloads, sequential restatement:
+ *   SearchByProjection(Cur, Last)            ORBmatcher.cc:2026-2101  (window :2031-2041, skip :2046-2049, stereo :2052-2059,
+ *                                            best-only :2062-2068, accept :2071-2074, histogram :2076-2088, cull :2163-2186)
+ *   SearchByProjection(Cur, KF, found)       :2262-2320  (skip `if (CurrentFrame.mvpMapPoints[*vit]) continue`)
+ *   SearchByProjection(KF, Sim3, ...)        :566-614    (skip `if (vpMatched[idx]) continue`, level filter :583-584)
+ *   Fuse                                     :1452-1510  (level filter :1461-1462, chi2 gate :1463-1492)
+ *   Fuse (Sim3), SearchBySim3                :1636-1650, :1780-1800 / :1870-1890
+ * The per-point prologue (pose transform, projection, frustum gates, PredictScale) is an input. */
+int oracle_search_projected(const orbgpu_frame_host *f, const orbgpu_projpoints_host *pts, const orbgpu_projsearch_params *prm,
+                            const uint8_t *kp_locked, int32_t *best_idx, int32_t *best_dist, int32_t *kp_owner)
+{
+    int nmatches = 0;
+    int32_t *cs = (int32_t *)malloc(sizeof(int32_t) * (size_t)(f->grid_cols * f->grid_rows + 1));
+    int32_t *ci = (int32_t *)malloc(sizeof(int32_t) * (size_t)(f->n + 1));
+    int32_t *vIndices = (int32_t *)malloc(sizeof(int32_t) * (size_t)(f->n + 1));
+    uint8_t *locked = (uint8_t *)calloc((size_t)f->n + 1, 1);
+    int32_t *owner = (int32_t *)malloc(sizeof(int32_t) * (size_t)(f->n + 1));
+    /* rotHist[bin] holds keypoint indices in acceptance order; one flat array of (bin, keypoint) is enough */
+    int32_t *hist_bin = (int32_t *)malloc(sizeof(int32_t) * (size_t)(pts->n + 1));
+    int32_t *hist_kp = (int32_t *)malloc(sizeof(int32_t) * (size_t)(pts->n + 1));
+    int32_t histo[ORBGPU_HISTO_LENGTH];
+    int n_hist = 0;
+    const float factor = 1.0f / ORBGPU_HISTO_LENGTH;
+    memset(histo, 0, sizeof(histo));
+    oracle_grid_build(f, cs, ci);
+    for (int i = 0; i < f->n; i++) {
+        locked[i] = kp_locked ? kp_locked[i] : 0;
+        owner[i] = -1;
+    }
+    for (int m = 0; m < pts->n; m++) {
+        best_idx[m] = -1;
+        best_dist[m] = 256;
+        if (!pts->active[m]) continue;
+        const float u = pts->uv[2 * m], v = pts->uv[2 * m + 1], radius = pts->radius[m];
+        const int nc = oracle_features_in_area(f, cs, ci, u, v, radius, pts->min_level[m], pts->max_level[m], vIndices);
+        if (nc == 0) continue;
+        const uint8_t *dMP = pts->desc + 32 * (size_t)m;
+        int bestDist = 256, bestIdx = -1;
+        for (int c = 0; c < nc; c++) {
+            const int idx = vIndices[c];
+            if (prm->ordered && locked[idx]) continue;
+            if (prm->stereo_gate && f->u_right && f->u_right[idx] > 0) {
+                const float er = fabsf(pts->ur[m] - f->u_right[idx]);
+                if (er > radius) continue;
+            }
+            if (prm->chi2_gate) {
+                const float ex = u - f->kp_xy[2 * idx], ey = v - f->kp_xy[2 * idx + 1];
+                const float inv = prm->inv_level_sigma2[f->octave[idx]];
+                if (f->u_right && f->u_right[idx] >= 0) {
+                    const float er = pts->ur[m] - f->u_right[idx];
+                    const float e2 = ex * ex + ey * ey + er * er;
+                    if (e2 * inv > 7.8) continue;
+                } else {
+                    const float e2 = ex * ex + ey * ey;
+                    if (e2 * inv > 5.99) continue;
+                }
+            }
+            const int dist = oracle_descriptor_distance(dMP, f->desc + 32 * (size_t)idx);
+            if (dist < bestDist) {
+                bestDist = dist;
+                bestIdx = idx;
+            }
+        }
+        if (bestIdx >= 0 && (float)bestDist <= prm->max_dist) {
+            best_idx[m] = bestIdx;
+            best_dist[m] = bestDist;
+            owner[bestIdx] = m;
+            if (!pts->locks || pts->locks[m]) locked[bestIdx] = 1;
+            nmatches++;
+            if (prm->check_ori) {
+                float rot = pts->angle[m] - f->angle[bestIdx];
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)roundf(rot * factor);
+                if (bin == ORBGPU_HISTO_LENGTH) bin = 0;
+                if (bin >= 0 && bin < ORBGPU_HISTO_LENGTH) {
+                    histo[bin]++;
+                    hist_bin[n_hist] = bin;
+                    hist_kp[n_hist] = bestIdx;
+                    n_hist++;
+                }
+            }
+        }
+    }
+    if (prm->check_ori) {
+        int32_t ind[3];
+        oracle_compute_three_maxima(histo, ORBGPU_HISTO_LENGTH, ind);
+        for (int e = 0; e < n_hist; e++)
+            if (hist_bin[e] != ind[0] && hist_bin[e] != ind[1] && hist_bin[e] != ind[2]) {
+                owner[hist_kp[e]] = -1;
+                nmatches--;
+            }
+    }
+    if (kp_owner) memcpy(kp_owner, owner, sizeof(int32_t) * (size_t)f->n);
+    free(cs); free(ci); free(vIndices); free(locked); free(owner); free(hist_bin); free(hist_kp);
+    return nmatches;
+}
+
 /* TemplatedVocabulary.h:1216-1258 */
 void oracle_voc_transform(const orbgpu_voc_host *v, int32_t n, const uint8_t *desc, int levelsup, uint32_t *word_id,
                           uint32_t *node_id, double *weight)

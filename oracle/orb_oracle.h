@@ -50,6 +50,10 @@ int oracle_search_by_projection_local(const orbgpu_frame_host *f, const orbgpu_m
                                       int far_points, float th_far_points, float nnratio, const int32_t *kp_prior_obs,
                                       int32_t *kp_mp);
 
+/* search core of the self-projecting overloads (row a6: ORBmatcher.cc:498-733, 1330-1955, 1957-2330); returns nmatches */
+int oracle_search_projected(const orbgpu_frame_host *f, const orbgpu_projpoints_host *pts, const orbgpu_projsearch_params *prm,
+                            const uint8_t *kp_locked, int32_t *best_idx, int32_t *best_dist, int32_t *kp_owner);
+
 /* TemplatedVocabulary.h:1216-1258 per feature */
 void oracle_voc_transform(const orbgpu_voc_host *v, int32_t n, const uint8_t *desc, int levelsup, uint32_t *word_id,
                           uint32_t *node_id, double *weight);

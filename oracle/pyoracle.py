@@ -14,7 +14,8 @@ from typing import Optional
 
 import numpy as np
 
-from orb_slam3_comments_ghr_b200._abi import (FrameHostStruct, HostFrame, HostKfSet, HostMapPoints, HostVoc,
+from orb_slam3_comments_ghr_b200._abi import (FrameHostStruct, HostFrame, HostKfSet, HostMapPoints, HostProjPoints, HostVoc,
+                                              ProjPointsHostStruct, ProjSearchParamsStruct, proj_params,
                                               KfSetHostStruct, MapPointsHostStruct, VocHostStruct, as_f32, as_i32,
                                               as_u8, f32p, f64p, i32p, u8p, u32p)
 
@@ -52,6 +53,8 @@ class Oracle:
                                                        C.c_int, C.c_float, C.c_int, i32p]
         L.oracle_search_by_projection_local.argtypes = [C.POINTER(FrameHostStruct), C.POINTER(MapPointsHostStruct),
                                                         C.c_float, C.c_int, C.c_float, C.c_float, i32p, i32p]
+        L.oracle_search_projected.argtypes = [C.POINTER(FrameHostStruct), C.POINTER(ProjPointsHostStruct),
+                                              C.POINTER(ProjSearchParamsStruct), u8p, i32p, i32p, i32p]
         L.oracle_voc_transform.argtypes = [C.POINTER(VocHostStruct), C.c_int32, u8p, C.c_int, u32p, u32p, f64p]
         L.oracle_bowvector.argtypes = [C.c_int32, u32p, f64p, u32p, f64p]
         L.oracle_featvec.argtypes = [C.c_int32, u32p, f64p, u32p, i32p, u32p]
@@ -116,6 +119,19 @@ class Oracle:
         n = self.lib.oracle_search_by_projection_local(C.byref(sf), C.byref(sm), float(th), int(far_points),
                                                        float(th_far), float(nnratio), _p(prior, i32p), _p(kp_mp, i32p))
         return int(n), kp_mp
+
+    def search_projected(self, f: HostFrame, pts: HostProjPoints, max_dist, ordered, kp_locked=None, stereo_gate=False,
+                         chi2_gate=False, check_ori=False, inv_level_sigma2=None):
+        prm = proj_params(max_dist, ordered, stereo_gate, chi2_gate, check_ori, inv_level_sigma2)
+        sf, sp = f.struct(), pts.struct()
+        kl = as_u8(kp_locked) if kp_locked is not None else None
+        bi = np.full(max(pts.n, 1), -1, dtype=np.int32)
+        bd = np.full(max(pts.n, 1), 256, dtype=np.int32)
+        own = np.full(max(f.n, 1), -1, dtype=np.int32)
+        n = self.lib.oracle_search_projected(C.byref(sf), C.byref(sp), C.byref(prm),
+                                             _p(kl, u8p) if kl is not None else C.cast(None, u8p), _p(bi, i32p), _p(bd, i32p),
+                                             _p(own, i32p))
+        return int(n), bi[:pts.n], bd[:pts.n], own[:f.n]
 
     def voc_transform(self, voc: HostVoc, desc, levelsup):
         desc = as_u8(desc).reshape(-1, 32)

@@ -94,6 +94,32 @@ class MapPointsHostStruct(C.Structure):
     ]
 
 
+class ProjPointsHostStruct(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32),
+        ("desc", u8p),
+        ("uv", f32p),
+        ("radius", f32p),
+        ("min_level", i32p),
+        ("max_level", i32p),
+        ("ur", f32p),
+        ("active", u8p),
+        ("locks", u8p),
+        ("angle", f32p),
+    ]
+
+
+class ProjSearchParamsStruct(C.Structure):
+    _fields_ = [
+        ("max_dist", C.c_float),
+        ("ordered", C.c_int32),
+        ("stereo_gate", C.c_int32),
+        ("chi2_gate", C.c_int32),
+        ("check_ori", C.c_int32),
+        ("inv_level_sigma2", f32p),
+    ]
+
+
 class KfSetHostStruct(C.Structure):
     _fields_ = [
         ("n_kf", C.c_int32), ("n_feat", C.c_int32),
@@ -300,6 +326,64 @@ class HostMapPoints:
         s.n_obs = _ptr(self.n_obs, i32p)
         s._keep = self
         return s
+
+
+@dataclass
+class HostProjPoints:
+    """Points already projected into the target frame: the inputs of the search core shared by the self-projecting
+    overloads (SearchByProjection Cur/Last, Cur/KF, KF/Sim3; Fuse; SearchBySim3)."""
+    desc: np.ndarray
+    uv: np.ndarray
+    radius: np.ndarray
+    min_level: np.ndarray
+    max_level: np.ndarray
+    active: np.ndarray
+    ur: Optional[np.ndarray] = None
+    locks: Optional[np.ndarray] = None
+    angle: Optional[np.ndarray] = None
+
+    def __post_init__(self):
+        self.desc = as_u8(self.desc).reshape(-1, 32)
+        self.uv = as_f32(self.uv).reshape(-1, 2)
+        self.radius = as_f32(self.radius)
+        self.min_level = as_i32(self.min_level)
+        self.max_level = as_i32(self.max_level)
+        self.active = as_u8(self.active)
+        if self.ur is not None:
+            self.ur = as_f32(self.ur)
+        if self.locks is not None:
+            self.locks = as_u8(self.locks)
+        if self.angle is not None:
+            self.angle = as_f32(self.angle)
+
+    @property
+    def n(self) -> int:
+        return int(self.desc.shape[0])
+
+    def struct(self) -> ProjPointsHostStruct:
+        s = ProjPointsHostStruct()
+        s.n = self.n
+        s.desc = _ptr(self.desc, u8p)
+        s.uv = _ptr(self.uv, f32p)
+        s.radius = _ptr(self.radius, f32p)
+        s.min_level = _ptr(self.min_level, i32p)
+        s.max_level = _ptr(self.max_level, i32p)
+        s.ur = _ptr(self.ur, f32p)
+        s.active = _ptr(self.active, u8p)
+        s.locks = _ptr(self.locks, u8p)
+        s.angle = _ptr(self.angle, f32p)
+        s._keep = self
+        return s
+
+
+def proj_params(max_dist, ordered, stereo_gate=0, chi2_gate=0, check_ori=0, inv_level_sigma2=None) -> ProjSearchParamsStruct:
+    p = ProjSearchParamsStruct()
+    p.max_dist = float(max_dist)
+    p.ordered, p.stereo_gate, p.chi2_gate, p.check_ori = int(ordered), int(stereo_gate), int(chi2_gate), int(check_ori)
+    inv = as_f32(inv_level_sigma2) if inv_level_sigma2 is not None else None
+    p.inv_level_sigma2 = _ptr(inv, f32p)
+    p._keep = inv
+    return p
 
 
 @dataclass

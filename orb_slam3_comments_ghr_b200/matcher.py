@@ -14,8 +14,8 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-from ._abi import (FrameHostStruct, HostFrame, HostKfSet, HostMapPoints, HostVoc, KfSetHostStruct, MapPointsHostStruct,
-                   VocHostStruct, as_f32, as_i32, as_u8, f32p, f64p, i32p, i64p, u8p, u32p)
+from ._abi import (FrameHostStruct, HostFrame, HostKfSet, HostMapPoints, HostProjPoints, HostVoc, KfSetHostStruct, MapPointsHostStruct,
+                   ProjPointsHostStruct, ProjSearchParamsStruct, proj_params, VocHostStruct, as_f32, as_i32, as_u8, f32p, f64p, i32p, i64p, u8p, u32p)
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liborbmatch_b200.so")
 _lib = None
@@ -86,6 +86,8 @@ def load_library():
     L.orbgpu_knn2_ratio.argtypes = [vp, vp, C.c_int64, u8p, C.c_int32, C.c_float, i32p, i32p, i32p, i32p]
     L.orbgpu_knn2_ratio_dev.argtypes = [vp, vp, C.c_int64, vp, C.c_int32, C.c_float, vp, vp, vp, vp]
     L.orbgpu_knn2_set_engine.argtypes = [vp, C.c_int32]
+    L.orbgpu_search_projected.argtypes = [vp, vp, C.POINTER(ProjPointsHostStruct), C.POINTER(ProjSearchParamsStruct), u8p, i32p, i32p,
+                                          i32p, i32p]
     L.orbgpu_triangulation_set_engine.argtypes = [vp, C.c_int32]
     L.orbgpu_compute_three_maxima.argtypes = [vp, i32p, C.c_int32, i32p]
     _lib = L
@@ -353,6 +355,22 @@ class ORBmatcher:
                                                                 float(thFarPoints), self.mfNNratio, _p(prior, i32p), _p(out, i32p),
                                                                 C.byref(nm)))
         return nm.value, out
+
+    # search core of the self-projecting overloads (ORBmatcher.h:48-60, 78-84): points already projected by the caller
+    # -> (nmatches, best_idx per point, best_dist per point, owner point per keypoint)
+    def SearchProjected(self, F: DeviceFrame, pts: HostProjPoints, max_dist: float, ordered: bool, kp_locked=None,
+                        stereo_gate: bool = False, chi2_gate: bool = False, inv_level_sigma2=None):
+        prm = proj_params(max_dist, ordered, stereo_gate, chi2_gate, self.mbCheckOrientation and pts.angle is not None, inv_level_sigma2)
+        s = pts.struct()
+        kl = as_u8(kp_locked) if kp_locked is not None else None
+        bi = np.full(max(pts.n, 1), -1, dtype=np.int32)
+        bd = np.full(max(pts.n, 1), 256, dtype=np.int32)
+        own = np.full(max(F.n, 1), -1, dtype=np.int32)
+        nm = C.c_int32(0)
+        _check(load_library().orbgpu_search_projected(self.ctx.handle, F.handle, C.byref(s), C.byref(prm),
+                                                      _p(kl, u8p) if kl is not None else C.cast(None, u8p), _p(bi, i32p), _p(bd, i32p),
+                                                      _p(own, i32p), C.byref(nm)))
+        return nm.value, bi[:pts.n], bd[:pts.n], own[:F.n]
 
     # ORBmatcher.h:65 -> (nmatches, vpMapPointMatches as KF feature indices, indexed by F feature)
     def SearchByBoW(self, KF: DeviceFrame, F: DeviceFrame, kf_mp_valid, f_mp_valid=None):

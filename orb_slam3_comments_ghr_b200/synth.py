@@ -14,7 +14,7 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-from ._abi import HostFrame, HostKfSet, HostMapPoints, HostVoc, orb_scale_tables
+from ._abi import HostFrame, HostKfSet, HostMapPoints, HostProjPoints, HostVoc, orb_scale_tables
 
 IMG_W, IMG_H = 640.0, 480.0
 # orbbec335L_rgbd.yaml:11-14
@@ -168,6 +168,54 @@ def make_projection_case(seed: int, n_kp: int = 2000, n_mp: int = 5000, th: floa
     prior[pre] = rng.integers(0, 4, int(pre.sum()))
     kp_mp = np.full(n_kp, -1, dtype=np.int32)
     return ProjectionCase(frame, mps, prior, kp_mp, th=th, far_points=far_points)
+
+
+def make_projected_case(seed: int, n_kp: int = 2000, n_pts: int = 3000, th: float = 7.0, stereo: bool = False,
+                        level_mode: str = "pm1", planted_frac: float = 0.5, lock_frac: float = 0.9):
+    """Inputs of the search core shared by the self-projecting overloads (row a6): points already projected into a
+    frame.  planted points sit on keypoints (+N(0,2 px)) with a bit-flipped copy of the keypoint's descriptor, several
+    per keypoint so that the ordered skip rule matters; the others are random in-image.  level_mode: 'pm1' = window
+    [l-1, l+1] (Cur/Last, :2041), 'fwd' = (l, -1) (:2035), 'bwd' = (0, l) (:2038), 'pred' = (l-1, l) (KeyFrame callers)."""
+    rng = np.random.default_rng(seed)
+    frame = make_frame(rng, n_kp)
+    n_levels = frame.scale_factors.shape[0]
+    if stereo:
+        ur = quantise(np.maximum(frame.kp_xy[:, 0] - rng.uniform(2, 40, n_kp), 0.25)).astype(np.float32)
+        ur[rng.random(n_kp) >= 0.6] = np.float32(-1.0)  # keypoints without a stereo match (mvuRight = -1)
+        frame = HostFrame(frame.desc, frame.kp_xy, frame.octave, frame.angle, u_right=ur,
+                          scale_factors=frame.scale_factors, level_sigma2=frame.level_sigma2)
+    desc = random_descriptors(rng, n_pts)
+    uv = random_keypoints(rng, n_pts).astype(np.float32)
+    level = random_octaves(rng, n_pts)
+    n_pl = int(planted_frac * n_pts)
+    tgt = rng.integers(0, n_kp, n_pl)
+    who = rng.permutation(n_pts)[:n_pl]
+    desc[who] = planted_copies(rng, frame.desc[tgt])
+    uv[who] = quantise(frame.kp_xy[tgt] + rng.normal(0, 2.0, size=(n_pl, 2)))
+    level[who] = np.clip(frame.octave[tgt] + rng.integers(-1, 2, n_pl), 0, n_levels - 1)
+    radius = (np.float32(th) * frame.scale_factors[level]).astype(np.float32)
+    if level_mode == "pm1":
+        lo, hi = level - 1, level + 1
+    elif level_mode == "fwd":
+        lo, hi = level, np.full(n_pts, -1)
+    elif level_mode == "bwd":
+        lo, hi = np.zeros(n_pts, dtype=np.int64), level
+    else:
+        lo, hi = level - 1, level
+    pur = None
+    if stereo:
+        pur = (uv[:, 0] - rng.uniform(2, 40, n_pts)).astype(np.float32)
+        has = frame.u_right[tgt] > 0
+        pur[who[has]] = frame.u_right[tgt[has]] + rng.normal(0, 3.0, int(has.sum())).astype(np.float32)
+    active = (rng.random(n_pts) < 0.9).astype(np.uint8)
+    locks = (rng.random(n_pts) < lock_frac).astype(np.uint8)
+    angle = quantise(rng.uniform(0, 360, n_pts) % 360.0).astype(np.float32)
+    angle[who] = quantise((frame.angle[tgt] + 20.0 + rng.normal(0, 4.0, n_pl)) % 360.0)
+    odd = who[rng.random(n_pl) < 0.15]  # wrong rotation: these matches fall outside the three dominant bins
+    angle[odd] = quantise(rng.uniform(0, 360, odd.size) % 360.0)
+    pts = HostProjPoints(desc, uv, radius, lo, hi, active, ur=pur, locks=locks, angle=angle)
+    kp_locked = (rng.random(n_kp) < 0.1).astype(np.uint8)
+    return frame, pts, kp_locked
 
 
 # ---------------------------------------------------------------- vocabulary

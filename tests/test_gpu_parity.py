@@ -166,6 +166,51 @@ def test_bow_host_featvec(ctx, M, oracle, seed, levelsup, ratio):
         assert got[0] == exp[0] and np.array_equal(got[1], exp[1])
 
 
+# search core of the self-projecting overloads (row a6)
+PROJECTED_MODES = [  # name, level_mode, ordered, stereo, stereo_gate, chi2_gate, max_dist, th, ori
+    ("cur_last", "pm1", 1, False, 0, 0, 100.0, 7.0, 1),
+    ("cur_last_fwd_stereo", "fwd", 1, True, 1, 0, 100.0, 15.0, 1),
+    ("cur_last_bwd", "bwd", 1, False, 0, 0, 100.0, 15.0, 0),
+    ("reloc", "pm1", 1, False, 0, 0, 64.0, 10.0, 1),
+    ("sim3", "pred", 1, False, 0, 0, 50.0 * 0.9, 8.0, 0),
+    ("fuse_mono", "pred", 0, False, 0, 1, 50.0, 3.0, 0),
+    ("fuse_stereo", "pred", 0, True, 0, 1, 50.0, 3.0, 0),
+    ("by_sim3", "pred", 0, False, 0, 0, 100.0, 7.5, 0),
+]
+
+
+@pytest.mark.parametrize("mode", PROJECTED_MODES, ids=[m[0] for m in PROJECTED_MODES])
+@pytest.mark.parametrize("seed", [71, 72])
+def test_search_projected_oracle(ctx, M, oracle, mode, seed):
+    name, level_mode, ordered, stereo, sgate, chi2, max_dist, th, ori = mode
+    frame, pts, kp_locked = synth.make_projected_case(seed, th=th, stereo=stereo, level_mode=level_mode,
+                                                      lock_frac=1.0 if name in ("reloc", "sim3") else 0.85)
+    inv = (1.0 / frame.level_sigma2).astype(np.float32)
+    df = ctx.upload_frame(frame)
+    got = M.ORBmatcher(0.9, bool(ori), ctx).SearchProjected(df, pts, max_dist, bool(ordered), kp_locked if ordered else None,
+                                                           stereo_gate=bool(sgate), chi2_gate=bool(chi2), inv_level_sigma2=inv)
+    oracle.reset_comparisons()
+    exp = oracle.search_projected(frame, pts, max_dist, ordered, kp_locked if ordered else None, sgate, chi2, ori, inv)
+    assert exp[0] > 50, "the case must produce matches"
+    assert got[0] == exp[0]
+    for a, b, what in zip(got[1:], exp[1:], ("best_idx", "best_dist", "kp_owner")):
+        assert np.array_equal(a, b), what
+    assert ctx.last_comparisons == oracle.comparisons()
+
+
+def test_search_projected_edge_cases(ctx, M, oracle):
+    frame, pts, kp_locked = synth.make_projected_case(5, n_kp=300, n_pts=0)
+    df = ctx.upload_frame(frame)
+    got = M.ORBmatcher(0.9, True, ctx).SearchProjected(df, pts, 100.0, True, kp_locked)
+    assert got[0] == 0 and got[1].size == 0 and np.all(got[3] == -1)
+    # every point on the same keypoint: a chain of takes and skips
+    frame, pts, kp_locked = synth.make_projected_case(6, n_kp=64, n_pts=400, th=40.0, planted_frac=1.0, lock_frac=0.5)
+    df = ctx.upload_frame(frame)
+    got = M.ORBmatcher(0.9, True, ctx).SearchProjected(df, pts, 100.0, True, kp_locked)
+    exp = oracle.search_projected(frame, pts, 100.0, 1, kp_locked, 0, 0, 1, None)
+    assert got[0] == exp[0] and all(np.array_equal(a, b) for a, b in zip(got[1:], exp[1:]))
+
+
 @pytest.mark.parametrize("engine", [1, 2])
 @pytest.mark.parametrize("check_ori", [0, 1])
 def test_triangulation_golden(ctx, M, check_ori, engine):
