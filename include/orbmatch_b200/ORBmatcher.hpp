@@ -12,8 +12,13 @@
 //     using ORBmatcherGPU = orbgpu::ORBmatcherT<ORB_SLAM3::Frame, ORB_SLAM3::KeyFrame, ORB_SLAM3::MapPoint>;
 // and against the oracle's stub types for the parity tests (tests/cpp/adapter_parity.cc).
 //
-// Covered overloads: SearchForInitialization, SearchByProjection(Frame&,
-// vector<MapPoint*>&), SearchByBoW x2, SearchForTriangulation (monocular pinhole), DescriptorDistance.
+// Covered overloads: SearchForInitialization, SearchByProjection x5 (local map points;
+// Cur/Last; Cur/KF relocalisation; KF/Sim3 with and without the keyframe list), SearchByBoW x2, SearchForTriangulation
+// (monocular pinhole), Fuse x2, SearchBySim3, DescriptorDistance.  The overloads that project on their own evaluate
+// the per-point prologue (pose transform, projection, frustum / distance / viewing gates, PredictScale) HERE, with
+// the host's own Sophus / Eigen and in the reference's operation order; the window search, the Hamming distances, the
+// ordered "keypoint already taken" rule, the acceptance threshold and the rotation histogram run on the GPU
+// (orbgpu_search_projected).  The stereo-fisheye branches (Nleft != -1, bRight) are not on the GPU hot path.
 #pragma once
 
 #include <cstdint>
@@ -22,6 +27,7 @@
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <utility>
 #include <vector>
 
@@ -108,6 +114,55 @@ namespace orbgpu
         DeviceFrameGuard(const DeviceFrameGuard &) = delete;
         DeviceFrameGuard &operator=(const DeviceFrameGuard &) = delete;
     };
+
+
+    // points already projected into the target frame (inputs of orbgpu_search_projected); index m == source index
+    struct ProjBatch
+    {
+        std::vector<uint8_t> desc, active, locks;
+        std::vector<float> uv, radius, ur, angle;
+        std::vector<int32_t> lo, hi;
+        explicit ProjBatch(int n) : desc((size_t)n * 32, 0), active(n, 0), locks(n, 1), uv((size_t)n * 2, 0.f), radius(n, 0.f), ur(n, 0.f),
+                                    angle(n, 0.f), lo(n, -1), hi(n, -1) {}
+        template <class Mat>
+        void set(int m, const Mat &d, float u, float v, float r, int min_level, int max_level)
+        {
+            std::memcpy(&desc[(size_t)m * 32], d.template ptr<uint8_t>(), 32);
+            uv[2 * m] = u; uv[2 * m + 1] = v; radius[m] = r; lo[m] = min_level; hi[m] = max_level; active[m] = 1;
+        }
+        orbgpu_projpoints_host host() const
+        {
+            orbgpu_projpoints_host h;
+            std::memset(&h, 0, sizeof(h));
+            h.n = (int32_t)active.size();
+            h.desc = desc.data(); h.uv = uv.data(); h.radius = radius.data(); h.min_level = lo.data(); h.max_level = hi.data();
+            h.ur = ur.data(); h.active = active.data(); h.locks = locks.data(); h.angle = angle.data();
+            return h;
+        }
+    };
+    struct ProjResult
+    {
+        std::vector<int32_t> best_idx, best_dist, kp_owner;
+        int32_t nmatches = 0;
+    };
+    inline ProjResult run_projected(orbgpu_ctx *ctx, const orbgpu_frame *f, int n_kp, const ProjBatch &b, float max_dist, bool ordered,
+                                    bool stereo_gate, bool chi2_gate, bool check_ori, const std::vector<float> *inv_sigma2,
+                                    const std::vector<uint8_t> *kp_locked)
+    {
+        ProjResult r;
+        const int M = (int)b.active.size();
+        r.best_idx.assign(M > 0 ? M : 1, -1);
+        r.best_dist.assign(M > 0 ? M : 1, 256);
+        r.kp_owner.assign(n_kp > 0 ? n_kp : 1, -1);
+        orbgpu_projsearch_params prm;
+        std::memset(&prm, 0, sizeof(prm));
+        prm.max_dist = max_dist; prm.ordered = ordered; prm.stereo_gate = stereo_gate; prm.chi2_gate = chi2_gate; prm.check_ori = check_ori;
+        prm.inv_level_sigma2 = inv_sigma2 ? inv_sigma2->data() : nullptr;
+        const orbgpu_projpoints_host h = b.host();
+        check(orbgpu_search_projected(ctx, f, &h, &prm, kp_locked ? kp_locked->data() : nullptr, r.best_idx.data(), r.best_dist.data(),
+                                      r.kp_owner.data(), &r.nmatches));
+        return r;
+    }
 
     template <class FrameT, class KeyFrameT, class MapPointT>
     class ORBmatcherT
@@ -302,7 +357,368 @@ namespace orbgpu
             return nmatches;
         }
 
+        // ORBmatcher.h:48 (ORBmatcher.cc:1957-2191), monocular / RGB-D path (Nleft == -1)
+        int SearchByProjection(FrameT &CurrentFrame, const FrameT &LastFrame, const float th, const bool bMono)
+        {
+            if (CurrentFrame.Nleft != -1 || LastFrame.Nleft != -1)
+                throw std::runtime_error("orbmatch_b200: stereo-fisheye (Nleft != -1) path is not on the GPU hot path");
+            orbgpu_ctx *ctx = thread_context();
+            const auto Tcw = CurrentFrame.GetPose();
+            const auto twc = Tcw.inverse().translation();
+            const auto Tlw = LastFrame.GetPose();
+            const auto tlc = Tlw * twc;
+            const bool bForward = tlc(2) > CurrentFrame.mb && !bMono;   // :1971
+            const bool bBackward = -tlc(2) > CurrentFrame.mb && !bMono; // :1972
+            ProjBatch b(LastFrame.N);
+            for (int i = 0; i < LastFrame.N; i++)
+            {
+                MapPointT *pMP = LastFrame.mvpMapPoints[i];
+                if (!pMP || LastFrame.mvbOutlier[i]) continue;
+                const auto x3Dw = pMP->GetWorldPos();
+                const auto x3Dc = Tcw * x3Dw;
+                const float invzc = 1.0 / x3Dc(2); // :2005
+                if (invzc < 0) continue;
+                const auto uv = CurrentFrame.mpCamera->project(x3Dc);
+                if (uv(0) < CurrentFrame.mnMinX || uv(0) > CurrentFrame.mnMaxX) continue;
+                if (uv(1) < CurrentFrame.mnMinY || uv(1) > CurrentFrame.mnMaxY) continue;
+                const int nLastOctave = LastFrame.mvKeys[i].octave;
+                const float radius = th * CurrentFrame.mvScaleFactors[nLastOctave];
+                int lo, hi; // :2031-2041
+                if (bForward) { lo = nLastOctave; hi = -1; }
+                else if (bBackward) { lo = 0; hi = nLastOctave; }
+                else { lo = nLastOctave - 1; hi = nLastOctave + 1; }
+                b.set(i, pMP->GetDescriptor(), uv(0), uv(1), radius, lo, hi);
+                b.ur[i] = uv(0) - CurrentFrame.mbf * invzc; // :2056
+                b.locks[i] = pMP->Observations() > 0 ? 1 : 0; // what a later point's :2046-2049 test will see
+                b.angle[i] = LastFrame.mvKeysUn[i].angle;
+            }
+            PackedFrame pf;
+            bool any_right = false;
+            for (int i = 0; i < CurrentFrame.N && !any_right; i++) any_right = CurrentFrame.mvuRight[i] > 0;
+            pf.pack(CurrentFrame, CurrentFrame.mnMinX, CurrentFrame.mnMinY, CurrentFrame.mnMaxX, CurrentFrame.mnMaxY, any_right);
+            DeviceFrameGuard df(ctx, pf.h);
+            std::vector<uint8_t> locked(CurrentFrame.N > 0 ? CurrentFrame.N : 1, 0);
+            for (int i = 0; i < CurrentFrame.N; i++)
+                locked[i] = (CurrentFrame.mvpMapPoints[i] && CurrentFrame.mvpMapPoints[i]->Observations() > 0) ? 1 : 0;
+            const ProjResult r = run_projected(ctx, df.f, CurrentFrame.N, b, (float)ORBGPU_TH_HIGH, true, any_right, false,
+                                               mbCheckOrientation, nullptr, &locked);
+            scatter_owners(r, CurrentFrame.mvpMapPoints, [&](int m) { return LastFrame.mvpMapPoints[m]; });
+            return r.nmatches;
+        }
+
+        // ORBmatcher.h:52 (ORBmatcher.cc:2203-2330)
+        int SearchByProjection(FrameT &CurrentFrame, KeyFrameT *pKF, const std::set<MapPointT *> &sAlreadyFound, const float th,
+                               const int ORBdist)
+        {
+            orbgpu_ctx *ctx = thread_context();
+            const auto Tcw = CurrentFrame.GetPose();
+            const auto Ow = Tcw.inverse().translation();
+            const std::vector<MapPointT *> vpMPs = pKF->GetMapPointMatches();
+            ProjBatch b((int)vpMPs.size());
+            for (size_t i = 0; i < vpMPs.size(); i++)
+            {
+                MapPointT *pMP = vpMPs[i];
+                if (!pMP || pMP->isBad() || sAlreadyFound.count(pMP)) continue;
+                const auto x3Dw = pMP->GetWorldPos();
+                const auto x3Dc = Tcw * x3Dw;
+                const auto uv = CurrentFrame.mpCamera->project(x3Dc);
+                if (uv(0) < CurrentFrame.mnMinX || uv(0) > CurrentFrame.mnMaxX) continue;
+                if (uv(1) < CurrentFrame.mnMinY || uv(1) > CurrentFrame.mnMaxY) continue;
+                const auto PO = x3Dw - Ow;
+                const float dist3D = PO.norm();
+                const float maxDistance = pMP->GetMaxDistanceInvariance();
+                const float minDistance = pMP->GetMinDistanceInvariance();
+                if (dist3D < minDistance || dist3D > maxDistance) continue;
+                const int nPredictedLevel = pMP->PredictScale(dist3D, &CurrentFrame);
+                const float radius = th * CurrentFrame.mvScaleFactors[nPredictedLevel];
+                b.set((int)i, pMP->GetDescriptor(), uv(0), uv(1), radius, nPredictedLevel - 1, nPredictedLevel + 1);
+                b.angle[i] = pKF->mvKeysUn[i].angle;
+            }
+            PackedFrame pf;
+            pf.pack(CurrentFrame, CurrentFrame.mnMinX, CurrentFrame.mnMinY, CurrentFrame.mnMaxX, CurrentFrame.mnMaxY, false);
+            DeviceFrameGuard df(ctx, pf.h);
+            std::vector<uint8_t> locked(CurrentFrame.N > 0 ? CurrentFrame.N : 1, 0);
+            for (int i = 0; i < CurrentFrame.N; i++) locked[i] = CurrentFrame.mvpMapPoints[i] ? 1 : 0; // :2262-2263
+            const ProjResult r = run_projected(ctx, df.f, CurrentFrame.N, b, (float)ORBdist, true, false, false, mbCheckOrientation, nullptr,
+                                               &locked);
+            scatter_owners(r, CurrentFrame.mvpMapPoints, [&](int m) { return vpMPs[m]; });
+            return r.nmatches;
+        }
+
+        // ORBmatcher.h:56 (ORBmatcher.cc:498-620)
+        template <class Sim3T>
+        int SearchByProjection(KeyFrameT *pKF, Sim3T &Scw, const std::vector<MapPointT *> &vpPoints, std::vector<MapPointT *> &vpMatched,
+                               int th, float ratioHamming = 1.0)
+        {
+            const ProjResult r = sim3_projection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming);
+            for (int k = 0; k < pKF->N; k++)
+                if (r.kp_owner[k] >= 0) vpMatched[k] = vpPoints[r.kp_owner[k]]; // :614
+            return r.nmatches;
+        }
+
+        // ORBmatcher.h:60 (ORBmatcher.cc:622-733): same search, also records the keyframe each point came from
+        template <class Sim3T>
+        int SearchByProjection(KeyFrameT *pKF, Sim3T &Scw, const std::vector<MapPointT *> &vpPoints,
+                               const std::vector<KeyFrameT *> &vpPointsKFs, std::vector<MapPointT *> &vpMatched,
+                               std::vector<KeyFrameT *> &vpMatchedKF, int th, float ratioHamming = 1.0)
+        {
+            const ProjResult r = sim3_projection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming, true);
+            for (int k = 0; k < pKF->N; k++)
+                if (r.kp_owner[k] >= 0)
+                {
+                    vpMatched[k] = vpPoints[r.kp_owner[k]];       // :726
+                    vpMatchedKF[k] = vpPointsKFs[r.kp_owner[k]];  // :727
+                }
+            return r.nmatches;
+        }
+
+        // ORBmatcher.h:81 (ORBmatcher.cc:1330-1545), left camera (bRight == false)
+        int Fuse(KeyFrameT *pKF, const std::vector<MapPointT *> &vpMapPoints, const float th = 3.0, const bool bRight = false)
+        {
+            if (bRight) throw std::runtime_error("orbmatch_b200: two-camera rigs (bRight) are not on the GPU hot path");
+            orbgpu_ctx *ctx = thread_context();
+            const auto Tcw = pKF->GetPose();
+            const auto Ow = pKF->GetCameraCenter();
+            const float bf = pKF->mbf;
+            const int nMPs = (int)vpMapPoints.size();
+            ProjBatch b(nMPs);
+            for (int i = 0; i < nMPs; i++)
+            {
+                MapPointT *pMP = vpMapPoints[i];
+                if (!pMP || pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
+                const auto p3Dw = pMP->GetWorldPos();
+                const auto p3Dc = Tcw * p3Dw;
+                if (p3Dc(2) < 0.0f) continue;
+                const float invz = 1 / p3Dc(2);
+                const auto uv = pKF->mpCamera->project(p3Dc);
+                if (!pKF->IsInImage(uv(0), uv(1))) continue;
+                const float ur = uv(0) - bf * invz;
+                const float maxDistance = pMP->GetMaxDistanceInvariance();
+                const float minDistance = pMP->GetMinDistanceInvariance();
+                const auto PO = p3Dw - Ow;
+                const float dist3D = PO.norm();
+                if (dist3D < minDistance || dist3D > maxDistance) continue;
+                const auto Pn = pMP->GetNormal();
+                if (PO.dot(Pn) < 0.5 * dist3D) continue;
+                const int nPredictedLevel = pMP->PredictScale(dist3D, pKF);
+                const float radius = th * pKF->mvScaleFactors[nPredictedLevel];
+                b.set(i, pMP->GetDescriptor(), uv(0), uv(1), radius, nPredictedLevel - 1, nPredictedLevel);
+                b.ur[i] = ur;
+            }
+            PackedFrame pk;
+            bool any_right = false;
+            for (int i = 0; i < pKF->N && !any_right; i++) any_right = pKF->mvuRight[i] >= 0;
+            pk.pack(*pKF, (float)pKF->mnMinX, (float)pKF->mnMinY, (float)pKF->mnMaxX, (float)pKF->mnMaxY, any_right);
+            DeviceFrameGuard dk(ctx, pk.h);
+            const std::vector<float> inv(pKF->mvInvLevelSigma2.begin(), pKF->mvInvLevelSigma2.end());
+            const ProjResult r = run_projected(ctx, dk.f, pKF->N, b, (float)ORBGPU_TH_LOW, false, false, true, false, &inv, nullptr);
+            // the map mutations stay on the host, applied in the reference's order (:1502-1523)
+            int nFused = 0;
+            for (int i = 0; i < nMPs; i++)
+            {
+                const int bestIdx = r.best_idx[i];
+                if (bestIdx < 0) continue;
+                MapPointT *pMP = vpMapPoints[i];
+                if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue; // an earlier entry of the list may have changed it
+                MapPointT *pMPinKF = pKF->GetMapPoint(bestIdx);
+                if (pMPinKF)
+                {
+                    if (!pMPinKF->isBad())
+                    {
+                        if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+                        else pMPinKF->Replace(pMP);
+                    }
+                }
+                else
+                {
+                    pMP->AddObservation(pKF, bestIdx);
+                    pKF->AddMapPoint(pMP, bestIdx);
+                }
+                nFused++;
+            }
+            return nFused;
+        }
+
+        // ORBmatcher.h:84 (ORBmatcher.cc:1547-1682)
+        template <class Sim3T>
+        int Fuse(KeyFrameT *pKF, Sim3T &Scw, const std::vector<MapPointT *> &vpPoints, float th, std::vector<MapPointT *> &vpReplacePoint)
+        {
+            orbgpu_ctx *ctx = thread_context();
+            typedef decltype(pKF->GetPose()) SE3T;
+            const SE3T Tcw = SE3T(Scw.rotationMatrix(), Scw.translation() / Scw.scale());
+            const auto Ow = Tcw.inverse().translation();
+            const std::set<MapPointT *> spAlreadyFound = pKF->GetMapPoints();
+            const int nPoints = (int)vpPoints.size();
+            ProjBatch b(nPoints);
+            for (int iMP = 0; iMP < nPoints; iMP++)
+            {
+                MapPointT *pMP = vpPoints[iMP];
+                if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+                float u, v, dist3D;
+                if (!project_checked(pKF, Tcw, Ow, pMP, u, v, dist3D)) continue;
+                const int nPredictedLevel = pMP->PredictScale(dist3D, pKF);
+                const float radius = th * pKF->mvScaleFactors[nPredictedLevel];
+                b.set(iMP, pMP->GetDescriptor(), u, v, radius, nPredictedLevel - 1, nPredictedLevel);
+            }
+            PackedFrame pk;
+            pk.pack(*pKF, (float)pKF->mnMinX, (float)pKF->mnMinY, (float)pKF->mnMaxX, (float)pKF->mnMaxY, false);
+            DeviceFrameGuard dk(ctx, pk.h);
+            const ProjResult r = run_projected(ctx, dk.f, pKF->N, b, (float)ORBGPU_TH_LOW, false, false, false, false, nullptr, nullptr);
+            int nFused = 0;
+            for (int iMP = 0; iMP < nPoints; iMP++) // :1657-1672
+            {
+                const int bestIdx = r.best_idx[iMP];
+                if (bestIdx < 0) continue;
+                MapPointT *pMP = vpPoints[iMP];
+                MapPointT *pMPinKF = pKF->GetMapPoint(bestIdx);
+                if (pMPinKF)
+                {
+                    if (!pMPinKF->isBad()) vpReplacePoint[iMP] = pMPinKF;
+                }
+                else
+                {
+                    pMP->AddObservation(pKF, bestIdx);
+                    pKF->AddMapPoint(pMP, bestIdx);
+                }
+                nFused++;
+            }
+            return nFused;
+        }
+
+        // ORBmatcher.h:78 (ORBmatcher.cc:1684-1955)
+        template <class Sim3T>
+        int SearchBySim3(KeyFrameT *pKF1, KeyFrameT *pKF2, std::vector<MapPointT *> &vpMatches12, const Sim3T &S12, const float th)
+        {
+            orbgpu_ctx *ctx = thread_context();
+            const float fx = pKF1->fx, fy = pKF1->fy, cx = pKF1->cx, cy = pKF1->cy;
+            const auto T1w = pKF1->GetPose();
+            const auto T2w = pKF2->GetPose();
+            const Sim3T S21 = S12.inverse();
+            const std::vector<MapPointT *> vpMapPoints1 = pKF1->GetMapPointMatches(), vpMapPoints2 = pKF2->GetMapPointMatches();
+            const int N1 = (int)vpMapPoints1.size(), N2 = (int)vpMapPoints2.size();
+            std::vector<bool> vbAlreadyMatched1(N1, false), vbAlreadyMatched2(N2, false);
+            for (int i = 0; i < N1; i++) // :1711-1722
+            {
+                MapPointT *pMP = vpMatches12[i];
+                if (!pMP) continue;
+                vbAlreadyMatched1[i] = true;
+                const int idx2 = std::get<0>(pMP->GetIndexInKeyFrame(pKF2));
+                if (idx2 >= 0 && idx2 < N2) vbAlreadyMatched2[idx2] = true;
+            }
+            // one direction: the map points of `from` (already transformed into its camera by Tfw) through S into `to`
+            auto direction = [&](KeyFrameT *to, const std::vector<MapPointT *> &pts, const std::vector<bool> &done, const decltype(T1w) &Tfw,
+                                 const Sim3T &S, int n_from) {
+                ProjBatch b(n_from);
+                for (int i = 0; i < n_from; i++)
+                {
+                    MapPointT *pMP = pts[i];
+                    if (!pMP || done[i] || pMP->isBad()) continue;
+                    const auto p3Dw = pMP->GetWorldPos();
+                    const auto p3Dfrom = Tfw * p3Dw;
+                    const auto p3Dto = S * p3Dfrom;
+                    if (p3Dto(2) < 0.0) continue;
+                    const float invz = 1.0 / p3Dto(2);
+                    const float x = p3Dto(0) * invz, y = p3Dto(1) * invz;
+                    const float u = fx * x + cx, v = fy * y + cy;
+                    if (!to->IsInImage(u, v)) continue;
+                    const float maxDistance = pMP->GetMaxDistanceInvariance(), minDistance = pMP->GetMinDistanceInvariance();
+                    const float dist3D = p3Dto.norm();
+                    if (dist3D < minDistance || dist3D > maxDistance) continue;
+                    const int nPredictedLevel = pMP->PredictScale(dist3D, to);
+                    const float radius = th * to->mvScaleFactors[nPredictedLevel];
+                    b.set(i, pMP->GetDescriptor(), u, v, radius, nPredictedLevel - 1, nPredictedLevel);
+                }
+                PackedFrame pk;
+                pk.pack(*to, (float)to->mnMinX, (float)to->mnMinY, (float)to->mnMaxX, (float)to->mnMaxY, false);
+                DeviceFrameGuard dk(ctx, pk.h);
+                return run_projected(ctx, dk.f, to->N, b, (float)ORBGPU_TH_HIGH, false, false, false, false, nullptr, nullptr).best_idx;
+            };
+            const std::vector<int32_t> vnMatch1 = direction(pKF2, vpMapPoints1, vbAlreadyMatched1, T1w, S21, N1);
+            const std::vector<int32_t> vnMatch2 = direction(pKF1, vpMapPoints2, vbAlreadyMatched2, T2w, S12, N2);
+            int nFound = 0; // :1936-1950
+            for (int i1 = 0; i1 < N1; i1++)
+            {
+                const int idx2 = vnMatch1[i1];
+                if (idx2 >= 0 && vnMatch2[idx2] == i1)
+                {
+                    vpMatches12[i1] = vpMapPoints2[idx2];
+                    nFound++;
+                }
+            }
+            return nFound;
+        }
+
     protected:
+        // writes the GPU's owner table into the caller's map-point slots: a keypoint some point took ends up holding the
+        // last taker, or NULL when the rotation histogram culled it (ORBmatcher.cc:2074 + :2163-2186, :2290 + :2310-2325)
+        template <class Get>
+        static void scatter_owners(const ProjResult &r, std::vector<MapPointT *> &slots, Get &&point_of)
+        {
+            for (size_t m = 0; m < r.best_idx.size(); m++)
+                if (r.best_idx[m] >= 0) slots[r.best_idx[m]] = static_cast<MapPointT *>(NULL);
+            for (size_t k = 0; k < slots.size(); k++)
+                if (r.kp_owner[k] >= 0) slots[k] = point_of(r.kp_owner[k]);
+        }
+
+        // prologue shared by the Sim3 searches (ORBmatcher.cc:524-557, :646-684, :1581-1611): false when a gate drops the point
+        // inline_pinhole: the 8-argument overload projects with fx*x*invz + cx written out (:647-652) instead of mpCamera->project
+        template <class SE3T, class Vec3>
+        static bool project_checked(KeyFrameT *pKF, const SE3T &Tcw, const Vec3 &Ow, MapPointT *pMP, float &u, float &v, float &dist,
+                                    bool inline_pinhole = false)
+        {
+            const auto p3Dw = pMP->GetWorldPos();
+            const auto p3Dc = Tcw * p3Dw;
+            if (p3Dc(2) < 0.0) return false;
+            auto uv = pKF->mpCamera->project(p3Dc);
+            if (inline_pinhole)
+            {
+                const float invz = 1 / p3Dc(2);
+                const float x = p3Dc(0) * invz, y = p3Dc(1) * invz;
+                uv(0) = pKF->fx * x + pKF->cx;
+                uv(1) = pKF->fy * y + pKF->cy;
+            }
+            if (!pKF->IsInImage(uv(0), uv(1))) return false;
+            const float maxDistance = pMP->GetMaxDistanceInvariance();
+            const float minDistance = pMP->GetMinDistanceInvariance();
+            const auto PO = p3Dw - Ow;
+            dist = PO.norm();
+            if (dist < minDistance || dist > maxDistance) return false;
+            const auto Pn = pMP->GetNormal();
+            if (PO.dot(Pn) < 0.5 * dist) return false;
+            u = uv(0); v = uv(1);
+            return true;
+        }
+
+        template <class Sim3T>
+        ProjResult sim3_projection(KeyFrameT *pKF, Sim3T &Scw, const std::vector<MapPointT *> &vpPoints,
+                                   const std::vector<MapPointT *> &vpMatched, int th, float ratioHamming, bool inline_pinhole = false)
+        {
+            orbgpu_ctx *ctx = thread_context();
+            typedef decltype(pKF->GetPose()) SE3T;
+            const SE3T Tcw = SE3T(Scw.rotationMatrix(), Scw.translation() / Scw.scale()); // :507
+            const auto Ow = Tcw.inverse().translation();
+            std::set<MapPointT *> spAlreadyFound(vpMatched.begin(), vpMatched.end());
+            spAlreadyFound.erase(static_cast<MapPointT *>(NULL));
+            const int n = (int)vpPoints.size();
+            ProjBatch b(n);
+            for (int iMP = 0; iMP < n; iMP++)
+            {
+                MapPointT *pMP = vpPoints[iMP];
+                if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+                float u, v, dist;
+                if (!project_checked(pKF, Tcw, Ow, pMP, u, v, dist, inline_pinhole)) continue;
+                const int nPredictedLevel = pMP->PredictScale(dist, pKF);
+                const float radius = th * pKF->mvScaleFactors[nPredictedLevel];
+                b.set(iMP, pMP->GetDescriptor(), u, v, radius, nPredictedLevel - 1, nPredictedLevel);
+            }
+            PackedFrame pk;
+            pk.pack(*pKF, (float)pKF->mnMinX, (float)pKF->mnMinY, (float)pKF->mnMaxX, (float)pKF->mnMaxY, false);
+            DeviceFrameGuard dk(ctx, pk.h);
+            std::vector<uint8_t> locked(pKF->N > 0 ? pKF->N : 1, 0);
+            for (int k = 0; k < pKF->N; k++) locked[k] = vpMatched[k] ? 1 : 0; // :580-581
+            return run_projected(ctx, dk.f, pKF->N, b, ORBGPU_TH_LOW * ratioHamming, true, false, false, false, nullptr, &locked);
+        }
+
         // Sophus::SO3f::hat(t12) written against the matrix type of R12 (so that no Sophus header is needed here)
         template <class V, class Mtx>
         static Mtx hat(const V &w, const Mtx &like)

@@ -225,6 +225,12 @@ class Reference:
         L.ref_grid.argtypes = [FH, i32p, i32p]
         L.ref_search_for_initialization.argtypes = [FH, FH, f32p, C.c_int, C.c_float, C.c_int, i32p]
         L.ref_search_by_projection_local.argtypes = [FH, MP, C.c_float, C.c_int, C.c_float, C.c_float, i32p, i32p]
+        PP = C.POINTER(ProjPointsHostStruct)
+        L.ref_projected_cur_last.argtypes = [FH, PP, C.c_float, C.c_int, C.c_float, u8p, C.c_int, i32p]
+        L.ref_projected_reloc.argtypes = [FH, PP, C.c_float, C.c_int, u8p, C.c_int, i32p]
+        L.ref_projected_sim3.argtypes = [FH, PP, C.c_int, C.c_float, u8p, i32p]
+        L.ref_projected_fuse.argtypes = [FH, PP, C.c_float, C.c_float, i32p]
+        L.ref_projected_fuse_sim3.argtypes = [FH, PP, C.c_float, i32p]
         L.ref_search_by_bow_kf_f.argtypes = [FH, FH, u8p, C.c_float, C.c_int, i32p]
         L.ref_search_by_bow_kf_kf.argtypes = [FH, FH, u8p, u8p, C.c_float, C.c_int, i32p]
         L.ref_triangulation_geometry.argtypes = [f32p, f32p, f32p, f32p, f32p, f32p]
@@ -284,6 +290,38 @@ class Reference:
         n = self.lib.ref_search_by_projection_local(C.byref(sf), C.byref(sm), float(th), int(far_points), float(th_far),
                                                     float(nnratio), _p(prior, i32p), _p(kp_mp, i32p))
         return int(n), kp_mp
+
+    # the reference's self-projecting overloads on degenerate geometry (see ref_adapter.cc): everything from the window on
+    def projected_cur_last(self, cur: HostFrame, pts: HostProjPoints, th, mode, mbf, kp_locked, check_ori):
+        own = np.full(max(cur.n, 1), -1, dtype=np.int32)
+        a, b, kl = cur.struct(), pts.struct(), as_u8(kp_locked)
+        n = self.lib.ref_projected_cur_last(C.byref(a), C.byref(b), float(th), int(mode), float(mbf), _p(kl, u8p), int(check_ori),
+                                            _p(own, i32p))
+        return int(n), own[:cur.n]
+
+    def projected_reloc(self, cur: HostFrame, pts: HostProjPoints, th, orb_dist, kp_locked, check_ori):
+        own = np.full(max(cur.n, 1), -1, dtype=np.int32)
+        a, b, kl = cur.struct(), pts.struct(), as_u8(kp_locked)
+        n = self.lib.ref_projected_reloc(C.byref(a), C.byref(b), float(th), int(orb_dist), _p(kl, u8p), int(check_ori), _p(own, i32p))
+        return int(n), own[:cur.n]
+
+    def projected_sim3(self, kf: HostFrame, pts: HostProjPoints, th, ratio_hamming, kp_locked):
+        own = np.full(max(kf.n, 1), -1, dtype=np.int32)
+        a, b, kl = kf.struct(), pts.struct(), as_u8(kp_locked)
+        n = self.lib.ref_projected_sim3(C.byref(a), C.byref(b), int(th), float(ratio_hamming), _p(kl, u8p), _p(own, i32p))
+        return int(n), own[:kf.n]
+
+    def projected_fuse(self, kf: HostFrame, pts: HostProjPoints, th, bf):
+        bi = np.full(max(pts.n, 1), -1, dtype=np.int32)
+        a, b = kf.struct(), pts.struct()
+        n = self.lib.ref_projected_fuse(C.byref(a), C.byref(b), float(th), float(bf), _p(bi, i32p))
+        return int(n), bi[:pts.n]
+
+    def projected_fuse_sim3(self, kf: HostFrame, pts: HostProjPoints, th):
+        bi = np.full(max(pts.n, 1), -1, dtype=np.int32)
+        a, b = kf.struct(), pts.struct()
+        n = self.lib.ref_projected_fuse_sim3(C.byref(a), C.byref(b), float(th), _p(bi, i32p))
+        return int(n), bi[:pts.n]
 
     def search_by_bow_kf_f(self, kf, f, kf_mp_valid, nnratio, check_ori):
         valid = as_u8(kf_mp_valid)

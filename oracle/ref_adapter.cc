@@ -223,6 +223,209 @@ extern "C"
         return n;
     }
 
+    // ------------------------------------------------------------------------------------------------------------
+    // Self-projecting overloads driven from flat "already projected" points.  The geometry is
+    // degenerate on purpose: identity pose, pinhole fx = fy = 1, cx = cy = 0 and world points (u, v, 1), so that the
+    // reference's OWN prologue (Tcw * x3Dw, mpCamera->project, PredictScale, ...) reproduces the given (u, v), radius
+    // and level exactly (1*u + 0*v + 0*1 + 0 and 1*u/1 + 0 are exact in fp32).  What is pinned here is everything
+    // from the window on; the general-pose prologue runs in tests/cpp/adapter_parity.cc.
+    namespace
+    {
+        struct ProjWorld
+        {
+            std::vector<TaggedMapPoint> pts, locked;
+            Pinhole cam{1.f, 1.f, 0.f, 0.f};
+        };
+        // level of point m as the generator defined it from (min_level, max_level) and the window mode
+        int level_of(const orbgpu_projpoints_host *p, int m, int mode)
+        {
+            if (mode == 1) return p->min_level[m];      // fwd: (l, -1)
+            if (mode == 2) return p->max_level[m];      // bwd: (0, l)
+            if (mode == 3) return p->max_level[m];      // pred: (l-1, l)
+            return p->min_level[m] + 1;                 // pm1: (l-1, l+1)
+        }
+        void make_points(ProjWorld &w, const orbgpu_projpoints_host *p, int mode, const float *scale_log, int n_levels)
+        {
+            (void)scale_log; (void)n_levels;
+            w.pts.resize(p->n);
+            for (int i = 0; i < p->n; i++)
+            {
+                TaggedMapPoint &mp = w.pts[i];
+                mp.tag = i;
+                mp.descriptor_.create(1, 32, CV_8U);
+                std::memcpy(mp.descriptor_.data, p->desc + 32 * (size_t)i, 32);
+                mp.worldPos_ = Eigen::Vector3f(p->uv[2 * i], p->uv[2 * i + 1], 1.f);
+                mp.nObs_ = (!p->locks || p->locks[i]) ? 1 : 0;
+                mp.bad_ = false;
+                // distance gates and PredictScale (MapPoint.cc:695-738): dist = |PO| with Ow = 0
+                const float dist = mp.worldPos_.norm();
+                mp.normal_ = Eigen::Vector3f(mp.worldPos_(0) / dist, mp.worldPos_(1) / dist, mp.worldPos_(2) / dist);
+                mp.mfMinDistance = 0.f;
+                mp.mfMaxDistance = (float)((double)dist * std::pow(1.2, (double)level_of(p, i, mode) - 0.5));
+            }
+        }
+        void lock_keypoints(ProjWorld &w, std::vector<MapPoint *> &slots, const uint8_t *kp_locked, int n)
+        {
+            w.locked.resize(n);
+            for (int k = 0; k < n; k++)
+            {
+                w.locked[k].tag = -2;
+                w.locked[k].nObs_ = 1;
+                if (kp_locked && kp_locked[k]) slots[k] = &w.locked[k];
+            }
+        }
+        void read_owners(const std::vector<MapPoint *> &slots, int32_t *kp_owner)
+        {
+            for (size_t k = 0; k < slots.size(); k++)
+            {
+                const int tag = slots[k] ? static_cast<TaggedMapPoint *>(slots[k])->tag : -1;
+                kp_owner[k] = tag >= 0 ? tag : -1;
+            }
+        }
+    } // namespace
+
+    // ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) (ORBmatcher.cc:1957-2191); mode 0 pm1 / 1 fwd / 2 bwd
+    int ref_projected_cur_last(const orbgpu_frame_host *cur, const orbgpu_projpoints_host *p, float th, int mode, float mbf,
+                               const uint8_t *kp_locked, int check_ori, int32_t *kp_owner)
+    {
+        ProjWorld w;
+        Frame C, L;
+        fill_frame(C, cur);
+        C.mpCamera = &w.cam;
+        C.mb = 0.5f;
+        C.mbf = mbf;
+        make_points(w, p, mode, nullptr, 0);
+        lock_keypoints(w, C.mvpMapPoints, kp_locked, cur->n);
+        L.N = p->n;
+        L.mvKeys.resize(p->n);
+        L.mvKeysUn.resize(p->n);
+        L.mvpMapPoints.assign(p->n, nullptr);
+        L.mvbOutlier.assign(p->n, false);
+        for (int i = 0; i < p->n; i++)
+        {
+            cv::KeyPoint kp;
+            kp.octave = level_of(p, i, mode);
+            kp.angle = p->angle ? p->angle[i] : 0.f;
+            L.mvKeys[i] = kp;
+            L.mvKeysUn[i] = kp;
+            if (p->active[i]) L.mvpMapPoints[i] = &w.pts[i];
+        }
+        // tlc = Tlw * twc with twc = 0: the sign of its z against mb selects forward / backward (:1969-1972)
+        const float tz = mode == 1 ? 1.f : (mode == 2 ? -1.f : 0.f);
+        L.mTcw = Sophus::SE3f(Eigen::Matrix3f::Identity(), Eigen::Vector3f(0.f, 0.f, tz));
+        ORBmatcher matcher(0.9f, check_ori != 0);
+        const int n = matcher.SearchByProjection(C, L, th, false);
+        read_owners(C.mvpMapPoints, kp_owner);
+        return n;
+    }
+
+    // ORBmatcher::SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist) (:2203-2330)
+    int ref_projected_reloc(const orbgpu_frame_host *cur, const orbgpu_projpoints_host *p, float th, int orb_dist,
+                            const uint8_t *kp_locked, int check_ori, int32_t *kp_owner)
+    {
+        ProjWorld w;
+        Frame C;
+        KeyFrame K;
+        fill_frame(C, cur);
+        C.mpCamera = &w.cam;
+        make_points(w, p, 0, nullptr, 0);
+        lock_keypoints(w, C.mvpMapPoints, kp_locked, cur->n);
+        K.N = p->n;
+        K.mvKeysUn.resize(p->n);
+        K.mvpMapPoints.assign(p->n, nullptr);
+        std::set<MapPoint *> found;
+        for (int i = 0; i < p->n; i++)
+        {
+            K.mvKeysUn[i].angle = p->angle ? p->angle[i] : 0.f;
+            K.mvpMapPoints[i] = &w.pts[i];
+            if (!p->active[i]) found.insert(&w.pts[i]); // sAlreadyFound skips it (:2222)
+        }
+        ORBmatcher matcher(0.9f, check_ori != 0);
+        const int n = matcher.SearchByProjection(C, &K, found, th, orb_dist);
+        read_owners(C.mvpMapPoints, kp_owner);
+        return n;
+    }
+
+    // ORBmatcher::SearchByProjection(KeyFrame*, Sim3f&, vpPoints, vpMatched, th, ratioHamming) (:498-620)
+    int ref_projected_sim3(const orbgpu_frame_host *kf, const orbgpu_projpoints_host *p, int th, float ratio_hamming,
+                           const uint8_t *kp_locked, int32_t *kp_owner)
+    {
+        ProjWorld w;
+        KeyFrame K;
+        fill_keyframe(K, kf);
+        K.mpCamera = &w.cam;
+        make_points(w, p, 3, nullptr, 0);
+        std::vector<MapPoint *> vp(p->n), vpMatched(kf->n, nullptr);
+        for (int i = 0; i < p->n; i++)
+        {
+            vp[i] = &w.pts[i];
+            w.pts[i].bad_ = !p->active[i];
+        }
+        lock_keypoints(w, vpMatched, kp_locked, kf->n);
+        Sophus::Sim3f Scw;
+        ORBmatcher matcher(0.9f, true);
+        const int n = matcher.SearchByProjection(&K, Scw, vp, vpMatched, th, ratio_hamming);
+        read_owners(vpMatched, kp_owner);
+        return n;
+    }
+
+    // ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th, bRight=false) (:1330-1545): best_idx per point from the
+    // side effects (AddObservation :1519-1520, or Replace on the point the keypoint already holds :1505-1515)
+    int ref_projected_fuse(const orbgpu_frame_host *kf, const orbgpu_projpoints_host *p, float th, float bf, int32_t *best_idx)
+    {
+        ProjWorld w;
+        KeyFrame K;
+        fill_keyframe(K, kf);
+        K.mpCamera = &w.cam;
+        K.mbf = bf;
+        make_points(w, p, 3, nullptr, 0);
+        std::vector<MapPoint *> vp(p->n);
+        for (int i = 0; i < p->n; i++)
+        {
+            w.pts[i].nObs_ = 0;
+            vp[i] = p->active[i] ? &w.pts[i] : nullptr;
+            best_idx[i] = -1;
+        }
+        g_replace_log().clear();
+        ORBmatcher matcher(0.9f, true);
+        const int n = matcher.Fuse(&K, vp, th, false);
+        for (int i = 0; i < p->n; i++)
+            if (w.pts[i].observations_.count(&K)) best_idx[i] = std::get<0>(w.pts[i].observations_[&K]);
+        for (const auto &e : g_replace_log()) // pMP->Replace(pMPinKF) or pMPinKF->Replace(pMP) (:1508-1511): the one that
+        {                                     // observes the keyframe is the point held by the keypoint
+            TaggedMapPoint *a = static_cast<TaggedMapPoint *>(e.first), *b = static_cast<TaggedMapPoint *>(e.second);
+            TaggedMapPoint *held = a->observations_.count(&K) ? a : b, *fused = held == a ? b : a;
+            best_idx[fused->tag] = std::get<0>(held->observations_[&K]);
+        }
+        return n;
+    }
+
+    // ORBmatcher::Fuse(KeyFrame*, Sim3f&, vpPoints, th, vpReplacePoint) (:1547-1682)
+    int ref_projected_fuse_sim3(const orbgpu_frame_host *kf, const orbgpu_projpoints_host *p, float th, int32_t *best_idx)
+    {
+        ProjWorld w;
+        KeyFrame K;
+        fill_keyframe(K, kf);
+        K.mpCamera = &w.cam;
+        make_points(w, p, 3, nullptr, 0);
+        std::vector<MapPoint *> vp(p->n), repl(p->n, nullptr);
+        for (int i = 0; i < p->n; i++)
+        {
+            vp[i] = &w.pts[i];
+            w.pts[i].bad_ = !p->active[i];
+            best_idx[i] = -1;
+        }
+        Sophus::Sim3f Scw;
+        ORBmatcher matcher(0.9f, true);
+        const int n = matcher.Fuse(&K, Scw, vp, th, repl);
+        for (int i = 0; i < p->n; i++)
+        {
+            if (w.pts[i].observations_.count(&K)) best_idx[i] = std::get<0>(w.pts[i].observations_[&K]);
+            if (repl[i]) best_idx[i] = std::get<0>(static_cast<TaggedMapPoint *>(repl[i])->observations_[&K]);
+        }
+        return n;
+    }
+
     int ref_search_by_bow_kf_f(const orbgpu_frame_host *kf, const orbgpu_frame_host *f, const uint8_t *kf_mp_valid,
                                float nnratio, int check_ori, int32_t *match_f2kf)
     {

@@ -97,6 +97,14 @@ namespace ORB_SLAM3
         }
     };
 
+    class MapPoint;
+    // (held, incoming) pairs of MapPoint::Replace calls, so that the harness can recover Fuse's per-point result
+    inline std::vector<std::pair<MapPoint *, MapPoint *>> &g_replace_log()
+    {
+        static thread_local std::vector<std::pair<MapPoint *, MapPoint *>> log;
+        return log;
+    }
+
     class MapPoint
     {
     public:
@@ -124,7 +132,7 @@ namespace ORB_SLAM3
         float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; } // MapPoint.cc:674-678
         int PredictScale(const float &currentDist, KeyFrame *pKF);        // MapPoint.cc:695-713
         int PredictScale(const float &currentDist, Frame *pF);            // MapPoint.cc:722-738
-        void Replace(MapPoint *) {}
+        void Replace(MapPoint *pMP) { g_replace_log().push_back(std::make_pair(this, pMP)); }
         void AddObservation(KeyFrame *pKF, int idx) { observations_[pKF] = std::make_tuple(idx, -1); nObs_++; }
         bool IsInKeyFrame(KeyFrame *pKF) { return observations_.count(pKF) > 0; }
         std::tuple<int, int> GetIndexInKeyFrame(KeyFrame *pKF)

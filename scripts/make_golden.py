@@ -42,6 +42,64 @@ def golden_cases():
     }
 
 
+def projected_cases():
+    """row a6 (self-projecting overloads): name -> (builder of (frame, pts, kp_locked), reference call spec).  Shared with the
+    tests.  The image-bounds gate of the reference's prologue is applied to `active` here (see tests/test_oracle_vs_ref.py)."""
+    def build(seed, th, level_mode, stereo, lock_frac, in_image, off=None):
+        frame, pts, kl = synth.make_projected_case(seed, n_kp=1500, n_pts=2000, th=th, stereo=stereo, level_mode=level_mode,
+                                                   lock_frac=lock_frac)
+        if off is not None:
+            pts.ur = (pts.uv[:, 0] - np.float32(off)).astype(np.float32)
+        u, v = pts.uv[:, 0], pts.uv[:, 1]
+        if in_image:
+            ok = (u >= frame.min_x) & (u < frame.max_x) & (v >= frame.min_y) & (v < frame.max_y)
+        else:
+            ok = ~((u < frame.min_x) | (u > frame.max_x) | (v < frame.min_y) | (v > frame.max_y))
+        pts.active = (pts.active.astype(bool) & ok).astype(np.uint8)
+        return frame, pts, kl
+    return {
+        # name: (builder, kind, reference args, search_projected kwargs)
+        "curlast_pm1": (lambda: build(91, 7.0, "pm1", False, 0.85, False, 40.0), "cur_last", dict(th=7.0, mode=0, mbf=40.0, check_ori=1),
+                        dict(max_dist=100.0, ordered=1, stereo_gate=1, check_ori=1)),
+        "curlast_fwd_stereo": (lambda: build(92, 15.0, "fwd", True, 0.85, False, 40.0), "cur_last", dict(th=15.0, mode=1, mbf=40.0, check_ori=1),
+                               dict(max_dist=100.0, ordered=1, stereo_gate=1, check_ori=1)),
+        "curlast_bwd": (lambda: build(93, 15.0, "bwd", False, 0.85, False, 40.0), "cur_last", dict(th=15.0, mode=2, mbf=40.0, check_ori=0),
+                        dict(max_dist=100.0, ordered=1, stereo_gate=1, check_ori=0)),
+        "reloc": (lambda: build(94, 10.0, "pm1", False, 1.0, False), "reloc", dict(th=10.0, orb_dist=64, check_ori=1),
+                  dict(max_dist=64.0, ordered=1, check_ori=1)),
+        "sim3": (lambda: build(95, 8.0, "pred", False, 1.0, True), "sim3", dict(th=8, ratio_hamming=0.9),
+                 dict(max_dist=float(np.float32(50) * np.float32(0.9)), ordered=1)),
+        "fuse_stereo": (lambda: build(96, 3.0, "pred", True, 1.0, True, 40.0), "fuse", dict(th=3.0, bf=40.0),
+                        dict(max_dist=50.0, ordered=0, chi2_gate=1)),
+        "fuse_sim3": (lambda: build(97, 4.0, "pred", False, 1.0, True), "fuse_sim3", dict(th=4.0), dict(max_dist=50.0, ordered=0)),
+    }
+
+
+def make_projected_golden(ref):
+    out = {}
+    for name, (mk, kind, rargs, _) in projected_cases().items():
+        frame, pts, kl = mk()
+        out[name + "/in"] = np.frombuffer(bytes.fromhex(digest(frame.desc, frame.kp_xy, pts.desc, pts.uv, pts.radius, pts.active, kl)), dtype=np.uint8)
+        if kind == "cur_last":
+            n, own = ref.projected_cur_last(frame, pts, rargs["th"], rargs["mode"], rargs["mbf"], kl, rargs["check_ori"])
+            out[name + "/kp_owner"] = own
+        elif kind == "reloc":
+            n, own = ref.projected_reloc(frame, pts, rargs["th"], rargs["orb_dist"], kl, rargs["check_ori"])
+            out[name + "/kp_owner"] = own
+        elif kind == "sim3":
+            n, own = ref.projected_sim3(frame, pts, rargs["th"], rargs["ratio_hamming"], kl)
+            out[name + "/kp_owner"] = own
+        elif kind == "fuse":
+            n, bi = ref.projected_fuse(frame, pts, rargs["th"], rargs["bf"])
+            out[name + "/best_idx"] = bi
+        else:
+            n, bi = ref.projected_fuse_sim3(frame, pts, rargs["th"])
+            out[name + "/best_idx"] = bi
+        out[name + "/nmatches"] = np.int32(n)
+        print("projected", name, "nmatches", n)
+    np.savez_compressed(os.path.join(GOLD, "projected_outputs.npz"), **out)
+
+
 def vocabulary_training_set(seed=5, n_images=200, n_per_image=500, n_centers=20000):
     rng = np.random.default_rng(seed)
     centers = synth.random_descriptors(rng, n_centers)
@@ -152,9 +210,13 @@ def main():
     print("knn matches", int((mt >= 0).sum()))
 
     np.savez_compressed(os.path.join(GOLD, "reference_outputs.npz"), **out)
+    make_projected_golden(ref)
     for fn in sorted(os.listdir(GOLD)):
         print(fn, os.path.getsize(os.path.join(GOLD, fn)))
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "projected":  # only the row-a6 fixtures
+        make_projected_golden(Reference())
+    else:
+        main()

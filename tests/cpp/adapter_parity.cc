@@ -80,6 +80,126 @@ static void plant(FeatureSet &dst, int i, const FeatureSet &src, int j, int flip
 static void finish_frame(Frame &F) { F.mnMinX = 0; F.mnMinY = 0; F.mnMaxX = 640; F.mnMaxY = 480; F.mvbOutlier.assign(F.N, false); F.AssignFeaturesToGrid(0, 0); }
 static void finish_kf(KeyFrame &K) { K.mnMinX = 0; K.mnMinY = 0; K.mnMaxX = 640; K.mnMaxY = 480; K.AssignFeaturesToGrid(0, 0); }
 
+
+// ---- a scene with real geometry for the overloads that project on their own.  Built twice from the
+// same seed: the reference runs on one copy, the GPU adapter on the other (Fuse mutates key frames and map points).
+struct TagPoint : public MapPoint
+{
+    int tag = -1;
+};
+struct Scene
+{
+    Pinhole cam{368.05096f, 368.05399f, 317.11264f, 236.39537f};
+    Frame Cur, Last;
+    KeyFrame K, K2;
+    std::vector<TagPoint> pts, held, held2, twins;
+    std::vector<int> pair_m, pair_tgt, pair_j; // landmark m: keypoint tgt of Cur/K and keypoint j of K2
+    std::vector<MapPoint *> vp;
+    std::vector<KeyFrame *> vpKFs;
+    Sophus::Sim3f Scw, S12;
+};
+static Eigen::Matrix3f rot_y(float a)
+{
+    Eigen::Matrix3f R = Eigen::Matrix3f::Identity();
+    R(0, 0) = std::cos(a); R(0, 2) = std::sin(a); R(2, 0) = -std::sin(a); R(2, 2) = std::cos(a);
+    return R;
+}
+static int tag_of(MapPoint *p) { return p ? static_cast<TagPoint *>(p)->tag : -1; }
+static std::vector<int> tags(const std::vector<MapPoint *> &v)
+{
+    std::vector<int> t(v.size());
+    for (size_t i = 0; i < v.size(); i++) t[i] = tag_of(v[i]);
+    return t;
+}
+// world point that projects onto (u, v) at depth z in a camera with pose Tcw
+static Eigen::Vector3f backproject(const Pinhole &cam, const Sophus::SE3f &Tcw, float u, float v, float z)
+{
+    Eigen::Vector3f Xc((u - cam.mvParameters[2]) / cam.mvParameters[0] * z, (v - cam.mvParameters[3]) / cam.mvParameters[1] * z, z);
+    return Tcw.inverse() * Xc;
+}
+static void build_scene(Scene &S, uint64_t seed, bool stereo)
+{
+    rng.seed(seed);
+    const int N = 2000, M = 3000;
+    const Sophus::SE3f Tcw(rot_y(0.02f), Eigen::Vector3f(0.10f, -0.03f, 0.05f));
+    S.Scw = Sophus::Sim3f(1.08f, rot_y(0.02f), Eigen::Vector3f(0.10f, -0.03f, 0.05f) * 1.08f); // same camera through a Sim3
+    for (FeatureSet *f : {(FeatureSet *)&S.Cur, (FeatureSet *)&S.K, (FeatureSet *)&S.K2})
+    {
+        random_features(*f, N);
+        f->mpCamera = &S.cam;
+        f->fx = S.cam.mvParameters[0]; f->fy = S.cam.mvParameters[1]; f->cx = S.cam.mvParameters[2]; f->cy = S.cam.mvParameters[3];
+        f->mbf = 40.f; f->mb = 0.11f;
+        f->mTcw = Tcw;
+    }
+    S.K.mDescriptors = S.Cur.mDescriptors.clone(); S.K.mvKeysUn = S.Cur.mvKeysUn; S.K.mvKeys = S.Cur.mvKeys;
+    if (stereo)
+        for (int i = 0; i < N; i++)
+            if (uni(0, 1) < 0.6f) { S.Cur.mvuRight[i] = quant(std::max(0.25f, S.Cur.mvKeysUn[i].pt.x - uni(2, 40))); S.K.mvuRight[i] = S.Cur.mvuRight[i]; }
+    // second key frame for SearchBySim3: another pose, features planted from the same landmarks below
+    S.K2.mTcw = Sophus::SE3f(rot_y(-0.03f), Eigen::Vector3f(-0.25f, 0.02f, 0.04f));
+    S.pts.resize(M); S.vp.resize(M); S.vpKFs.resize(M);
+    S.Last.N = M; S.Last.mvKeys.resize(M); S.Last.mvKeysUn.resize(M); S.Last.mvpMapPoints.assign(M, nullptr); S.Last.mvbOutlier.assign(M, false);
+    S.Last.mTcw = Sophus::SE3f(rot_y(0.018f), Eigen::Vector3f(0.10f, -0.03f, stereo ? 0.45f : 0.04f)); // stereo: a clear forward motion
+    scale_tables(S.Last);
+    for (int i = 0; i < M; i++)
+    {
+        TagPoint &p = S.pts[i];
+        p.tag = i;
+        const bool planted = uni(0, 1) < 0.6f;
+        const int tgt = (int)(rng() % N);
+        const cv::KeyPoint &kp = S.Cur.mvKeysUn[tgt];
+        const float u = planted ? kp.pt.x + uni(-2.5f, 2.5f) : uni(-20, 660), v = planted ? kp.pt.y + uni(-2.5f, 2.5f) : uni(-20, 500);
+        const float z = uni(2.f, 12.f);
+        p.worldPos_ = backproject(S.cam, Tcw, u, v, z);
+        p.descriptor_.create(1, 32, CV_8U);
+        for (int b = 0; b < 32; b++) p.descriptor_.ptr<uint8_t>()[b] = planted ? S.Cur.mDescriptors.ptr<uint8_t>(tgt)[b] : (uint8_t)(rng() & 0xFF);
+        if (planted) for (int f = 0; f < (int)(rng() % 30); f++) { int bit = (int)(rng() % 256); p.descriptor_.ptr<uint8_t>()[bit >> 3] ^= (uint8_t)(1 << (bit & 7)); }
+        const Eigen::Vector3f Ow = Tcw.inverse().translation(), PO = p.worldPos_ - Ow;
+        const float dist = PO.norm();
+        const int lvl = planted ? std::min(7, kp.octave + (int)(rng() % 2)) : octave();
+        p.mfMaxDistance = dist * std::pow(1.2f, (float)lvl - uni(0.2f, 0.8f));
+        p.mfMinDistance = p.mfMaxDistance / std::pow(1.2f, 7.f) * uni(0.5f, 1.0f);
+        Eigen::Vector3f nrm = PO / dist;
+        if (uni(0, 1) < 0.05f) nrm = Eigen::Vector3f(-nrm(0), nrm(1), -nrm(2)); // viewing-angle gate
+        p.normal_ = nrm;
+        p.nObs_ = uni(0, 1) < 0.12f ? 0 : 1 + (int)(rng() % 4);
+        p.bad_ = uni(0, 1) < 0.03f;
+        S.vp[i] = &p;
+        S.vpKFs[i] = (i & 1) ? &S.K : &S.K2;
+        cv::KeyPoint lk;
+        lk.octave = lvl; lk.angle = quant(std::fmod((planted ? kp.angle : uni(0, 360)) + 25.f + uni(-6, 6) + 720.f, 360.f));
+        if (planted && uni(0, 1) < 0.15f) lk.angle = quant(uni(0, 359.5f));
+        S.Last.mvKeys[i] = lk; S.Last.mvKeysUn[i] = lk;
+        if (uni(0, 1) < 0.9f) S.Last.mvpMapPoints[i] = &p;
+        S.Last.mvbOutlier[i] = uni(0, 1) < 0.05f;
+        // the same landmark seen by K2 (for SearchBySim3)
+        if (planted && uni(0, 1) < 0.5f)
+        {
+            const Eigen::Vector2f u2 = S.cam.project(S.K2.mTcw * p.worldPos_);
+            if (u2(0) > 1 && u2(0) < 638 && u2(1) > 1 && u2(1) < 478)
+            {
+                const int j = (int)(rng() % N);
+                plant(S.K2, j, S.Cur, tgt, (int)(rng() % 30), 0, 0, 10.f);
+                S.K2.mvKeysUn[j].pt.x = quant(u2(0) + uni(-1.5f, 1.5f)); S.K2.mvKeysUn[j].pt.y = quant(u2(1) + uni(-1.5f, 1.5f));
+                S.K2.mvKeysUn[j].octave = kp.octave; S.K2.mvKeys[j] = S.K2.mvKeysUn[j];
+                S.pair_m.push_back(i); S.pair_tgt.push_back(tgt); S.pair_j.push_back(j);
+            }
+        }
+    }
+    finish_frame(S.Cur); finish_kf(S.K); finish_kf(S.K2);
+    // what the frames / key frames hold on entry
+    S.held.resize(N); S.held2.resize(N);
+    for (int i = 0; i < N; i++)
+    {
+        S.held[i].tag = 100000 + i; S.held2[i].tag = 200000 + i;
+        S.held[i].nObs_ = (int)(rng() % 3); S.held2[i].nObs_ = (int)(rng() % 3);
+        S.held[i].bad_ = uni(0, 1) < 0.05f;
+        if (uni(0, 1) < 0.12f) { S.Cur.mvpMapPoints[i] = &S.held[i]; S.K.mvpMapPoints[i] = &S.held[i]; S.held[i].observations_[&S.K] = std::make_tuple(i, -1); }
+    }
+    // SearchBySim3 walks the map points of both key frames: give K the landmarks at their planted keypoints
+    S.S12 = Sophus::Sim3f(1.0f, (S.K.mTcw * S.K2.mTcw.inverse()).rotationMatrix(), (S.K.mTcw * S.K2.mTcw.inverse()).translation());
+}
+
 static int fails = 0;
 #define EXPECT(cond, what)                                            \
     do {                                                              \
@@ -215,6 +335,108 @@ int main()
             std::printf("SearchForTriangulation checkOri=%d: ref %d gpu %d\n", ori, nA, nB);
             EXPECT(nA == nB && vA == vB && nA > 20, "SearchForTriangulation vMatchedPairs / return value");
         }
+    }
+    // ---- row a6: the overloads that project on their own, on real geometry
+    for (int stereo = 0; stereo < 2; stereo++)
+    {
+        {
+            Scene A, B;
+            build_scene(A, 77 + stereo, stereo != 0); build_scene(B, 77 + stereo, stereo != 0);
+            ORBmatcher ref(0.9f, true);
+            GpuMatcher gpu(0.9f, true);
+            const float th = stereo ? 15.f : 7.f;
+            const int nA = ref.SearchByProjection(A.Cur, A.Last, th, !stereo), nB = gpu.SearchByProjection(B.Cur, B.Last, th, !stereo);
+            std::printf("SearchByProjection(Cur, Last) stereo=%d: ref %d gpu %d\n", stereo, nA, nB);
+            EXPECT(nA == nB && tags(A.Cur.mvpMapPoints) == tags(B.Cur.mvpMapPoints) && nA > 100, "SearchByProjection(Frame&, const Frame&) mvpMapPoints / return value");
+        }
+        {
+            Scene A, B;
+            build_scene(A, 79 + stereo, false); build_scene(B, 79 + stereo, false);
+            for (Scene *S : {&A, &B})
+                for (int i = 0; i < 2000; i++) S->K.mvpMapPoints[i] = i < (int)S->vp.size() && (i % 3) ? S->vp[i] : nullptr; // the KF's map points
+            std::set<MapPoint *> fA, fB;
+            for (int i = 0; i < 2000; i += 7) { fA.insert(A.vp[i]); fB.insert(B.vp[i]); }
+            ORBmatcher ref(0.9f, stereo != 0);
+            GpuMatcher gpu(0.9f, stereo != 0);
+            const int nA = ref.SearchByProjection(A.Cur, &A.K, fA, 10.f, 64), nB = gpu.SearchByProjection(B.Cur, &B.K, fB, 10.f, 64);
+            std::printf("SearchByProjection(Cur, KF, found) ori=%d: ref %d gpu %d\n", stereo, nA, nB);
+            EXPECT(nA == nB && tags(A.Cur.mvpMapPoints) == tags(B.Cur.mvpMapPoints) && nA > 100, "SearchByProjection(Frame&, KeyFrame*, set) mvpMapPoints / return value");
+        }
+    }
+    {
+        Scene A, B;
+        build_scene(A, 81, false); build_scene(B, 81, false);
+        std::vector<MapPoint *> mA(2000, nullptr), mB(2000, nullptr);
+        for (int i = 0; i < 2000; i += 9) { mA[i] = &A.held2[i]; mB[i] = &B.held2[i]; }
+        mA[5] = A.vp[17]; mB[5] = B.vp[17]; // a point of the list that is already matched
+        ORBmatcher ref(0.9f, true);
+        GpuMatcher gpu(0.9f, true);
+        const int nA = ref.SearchByProjection(&A.K, A.Scw, A.vp, mA, 8, 0.9f), nB = gpu.SearchByProjection(&B.K, B.Scw, B.vp, mB, 8, 0.9f);
+        std::printf("SearchByProjection(KF, Sim3): ref %d gpu %d\n", nA, nB);
+        EXPECT(nA == nB && tags(mA) == tags(mB) && nA > 100, "SearchByProjection(KeyFrame*, Sim3f&, ...) vpMatched / return value");
+        std::vector<MapPoint *> qA(2000, nullptr), qB(2000, nullptr);
+        std::vector<KeyFrame *> kA(2000, nullptr), kB(2000, nullptr);
+        const int n2A = ref.SearchByProjection(&A.K, A.Scw, A.vp, A.vpKFs, qA, kA, 6, 1.0f), n2B = gpu.SearchByProjection(&B.K, B.Scw, B.vp, B.vpKFs, qB, kB, 6, 1.0f);
+        bool kfs_same = true;
+        for (int i = 0; i < 2000; i++) kfs_same = kfs_same && ((kA[i] == nullptr) == (kB[i] == nullptr)) && ((kA[i] == &A.K) == (kB[i] == &B.K));
+        std::printf("SearchByProjection(KF, Sim3, KFs): ref %d gpu %d\n", n2A, n2B);
+        EXPECT(n2A == n2B && tags(qA) == tags(qB) && kfs_same && n2A > 100, "SearchByProjection(KeyFrame*, Sim3f&, ..., KFs) vpMatched / vpMatchedKF / return value");
+    }
+    for (int stereo = 0; stereo < 2; stereo++)
+    {
+        Scene A, B;
+        build_scene(A, 83 + stereo, stereo != 0); build_scene(B, 83 + stereo, stereo != 0);
+        for (Scene *S : {&A, &B}) { S->vp[11] = nullptr; S->vp[40] = S->vp[39]; } // a NULL entry and a duplicate
+        ORBmatcher ref(0.9f, true);
+        GpuMatcher gpu(0.9f, true);
+        g_replace_log().clear();
+        const int nA = ref.Fuse(&A.K, A.vp, 3.0f, false);
+        std::vector<std::pair<int, int>> logA, logB;
+        for (auto &e : g_replace_log()) logA.push_back(std::make_pair(tag_of(e.first), tag_of(e.second)));
+        g_replace_log().clear();
+        const int nB = gpu.Fuse(&B.K, B.vp, 3.0f, false);
+        for (auto &e : g_replace_log()) logB.push_back(std::make_pair(tag_of(e.first), tag_of(e.second)));
+        std::printf("Fuse stereo=%d: ref %d gpu %d (%zu replacements)\n", stereo, nA, nB, logA.size());
+        EXPECT(nA == nB && tags(A.K.mvpMapPoints) == tags(B.K.mvpMapPoints) && logA == logB && nA > 100, "Fuse(KeyFrame*, vector<MapPoint*>) map-point table / Replace calls / return value");
+    }
+    {
+        Scene A, B;
+        build_scene(A, 85, false); build_scene(B, 85, false);
+        std::vector<MapPoint *> rA(A.vp.size(), nullptr), rB(B.vp.size(), nullptr);
+        ORBmatcher ref(0.9f, true);
+        GpuMatcher gpu(0.9f, true);
+        const int nA = ref.Fuse(&A.K, A.Scw, A.vp, 4.0f, rA), nB = gpu.Fuse(&B.K, B.Scw, B.vp, 4.0f, rB);
+        std::printf("Fuse(Sim3): ref %d gpu %d\n", nA, nB);
+        EXPECT(nA == nB && tags(rA) == tags(rB) && tags(A.K.mvpMapPoints) == tags(B.K.mvpMapPoints) && nA > 100, "Fuse(KeyFrame*, Sim3f&, ...) vpReplacePoint / map-point table / return value");
+    }
+    {
+        Scene A, B;
+        build_scene(A, 86, false); build_scene(B, 86, false);
+        for (Scene *S : {&A, &B})
+        {   // K holds each landmark at its keypoint; K2 holds a twin map point (same position and descriptor) at the keypoint
+            // the landmark projects to there, so that the two directions can agree; the rest is clutter
+            for (int i = 0; i < 2000; i++) { S->K.mvpMapPoints[i] = nullptr; S->K2.mvpMapPoints[i] = nullptr; }
+            S->twins.resize(S->pair_m.size());
+            for (size_t k = 0; k < S->pair_m.size(); k++)
+            {
+                S->twins[k] = S->pts[S->pair_m[k]];
+                S->twins[k].tag = 300000 + S->pair_m[k];
+                S->twins[k].bad_ = false;
+                S->K.mvpMapPoints[S->pair_tgt[k]] = S->vp[S->pair_m[k]];
+                S->K2.mvpMapPoints[S->pair_j[k]] = &S->twins[k];
+            }
+            for (int m = 0; m < 600; m++)
+            {
+                const int i = (m * 37) % 2000;
+                if (!S->K.mvpMapPoints[i]) S->K.mvpMapPoints[i] = S->vp[(m * 5 + 1) % (int)S->vp.size()];
+            }
+        }
+        std::vector<MapPoint *> mA(2000, nullptr), mB(2000, nullptr);
+        ORBmatcher ref(0.9f, true);
+        GpuMatcher gpu(0.9f, true);
+        const int nA = ref.SearchBySim3(&A.K, &A.K2, mA, A.S12, 7.5f), nB = gpu.SearchBySim3(&B.K, &B.K2, mB, B.S12, 7.5f);
+        std::printf("SearchBySim3: ref %d gpu %d\n", nA, nB);
+        EXPECT(nA == nB && tags(mA) == tags(mB) && nA > 50, "SearchBySim3 vpMatches12 / return value");
     }
     {
         cv::Mat a(1, 32, CV_8U), b(1, 32, CV_8U);

@@ -36,6 +36,15 @@ def golden_cases():
     return gc()
 
 
+def projected_cases():
+    from make_golden import projected_cases as pc
+    return pc()
+
+
+def projected_golden():
+    return np.load(os.path.join(GOLD, "projected_outputs.npz"))
+
+
 def attach_featvec(oracle, voc, frame, levelsup):
     w, nid, wt = oracle.voc_transform(voc, frame.desc, levelsup)
     fn, fo, ff = oracle.featvec(nid, wt)

@@ -198,6 +198,26 @@ def test_search_projected_oracle(ctx, M, oracle, mode, seed):
     assert ctx.last_comparisons == oracle.comparisons()
 
 
+@pytest.mark.parametrize("name", ["curlast_pm1", "curlast_fwd_stereo", "curlast_bwd", "reloc", "sim3", "fuse_stereo", "fuse_sim3"])
+def test_search_projected_golden(ctx, M, name):
+    """GPU against the committed outputs of the reference's own self-projecting overloads (tests/golden/projected_outputs.npz)"""
+    from helpers import projected_cases, projected_golden
+    g = projected_golden()
+    mk, kind, _, kw = projected_cases()[name]
+    frame, pts, kl = mk()
+    kw = dict(kw)
+    inv = (np.float32(1.0) / frame.level_sigma2).astype(np.float32) if kw.get("chi2_gate") else None
+    ordered = kw["ordered"]
+    n, bi, bd, own = M.ORBmatcher(0.9, bool(kw.get("check_ori", 0)), ctx).SearchProjected(
+        ctx.upload_frame(frame), pts, kw["max_dist"], bool(ordered), kl if ordered else None, stereo_gate=bool(kw.get("stereo_gate", 0)),
+        chi2_gate=bool(kw.get("chi2_gate", 0)), inv_level_sigma2=inv)
+    assert n == int(g[name + "/nmatches"])
+    if name + "/kp_owner" in g:
+        assert np.array_equal(own, g[name + "/kp_owner"])
+    else:
+        assert np.array_equal(bi, g[name + "/best_idx"])
+
+
 def test_search_projected_edge_cases(ctx, M, oracle):
     frame, pts, kp_locked = synth.make_projected_case(5, n_kp=300, n_pts=0)
     df = ctx.upload_frame(frame)

@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from helpers import GOLD, attach_featvec, digest, golden_cases, golden_outputs, golden_voc
+from helpers import GOLD, attach_featvec, digest, golden_cases, golden_outputs, golden_voc, projected_cases, projected_golden
 from orb_slam3_comments_ghr_b200 import synth
 
 
@@ -89,3 +89,22 @@ def test_knn2(oracle):
     assert np.array_equal(bi, g["knn_s51/best_idx"]) and np.array_equal(bd, g["knn_s51/best_dist"])
     assert np.array_equal(sd, g["knn_s51/second_dist"]) and np.array_equal(mt, g["knn_s51/match"])
     assert oracle.comparisons() >= 0
+
+
+@pytest.mark.parametrize("name", ["curlast_pm1", "curlast_fwd_stereo", "curlast_bwd", "reloc", "sim3", "fuse_stereo", "fuse_sim3"])
+def test_search_projected(oracle, name):
+    """row a6: the search core against the reference's own SearchByProjection(Cur,Last) / (Cur,KF) / (KF,Sim3) / Fuse x2 outputs"""
+    g = projected_golden()
+    mk, kind, _, kw = projected_cases()[name]
+    frame, pts, kl = mk()
+    assert np.array_equal(digest(frame.desc, frame.kp_xy, pts.desc, pts.uv, pts.radius, pts.active, kl), g[name + "/in"]), "generator drift"
+    kw = dict(kw)
+    if kw.get("chi2_gate"):
+        kw["inv_level_sigma2"] = (np.float32(1.0) / frame.level_sigma2).astype(np.float32)
+    ordered = kw.pop("ordered")
+    n, bi, bd, own = oracle.search_projected(frame, pts, kw.pop("max_dist"), ordered, kl if ordered else None, **kw)
+    assert n == int(g[name + "/nmatches"]) and n > 100
+    if name + "/kp_owner" in g:
+        assert np.array_equal(own, g[name + "/kp_owner"])
+    else:
+        assert np.array_equal(bi, g[name + "/best_idx"])

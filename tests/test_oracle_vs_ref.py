@@ -101,3 +101,70 @@ def test_edge_cases(oracle, reference):
     b = reference.search_for_initialization(f1, f2, f1.kp_xy.copy(), 100, 0.9, 1)
     assert a[0] == b[0] and np.array_equal(a[1], b[1])
     assert a[0] >= 1
+
+
+# ---- row a6: the search core of the self-projecting overloads against the reference's OWN functions.  The harness
+# (oracle/ref_adapter.cc) gives them identity poses and a unit pinhole so that their prologue reproduces the given
+# projections exactly; everything from GetFeaturesInArea on is the reference's code.
+def _frustum(pts, frame, is_in_image):
+    """the image-bounds gate belongs to the caller's prologue: Frame callers use u < min || u > max (:2013-2016,
+    :2226-2229), KeyFrame callers IsInImage: min <= u < max (KeyFrame.cc:910-913)"""
+    u, v = pts.uv[:, 0], pts.uv[:, 1]
+    if is_in_image:
+        ok = (u >= frame.min_x) & (u < frame.max_x) & (v >= frame.min_y) & (v < frame.max_y)
+    else:
+        ok = ~((u < frame.min_x) | (u > frame.max_x) | (v < frame.min_y) | (v > frame.max_y))
+    pts.active = (pts.active.astype(bool) & ok).astype(np.uint8)
+    return pts
+
+
+@pytest.mark.parametrize("seed", [81, 82])
+@pytest.mark.parametrize("mode,level_mode,stereo", [(0, "pm1", False), (1, "fwd", True), (2, "bwd", False), (0, "pm1", True)])
+@pytest.mark.parametrize("ori", [0, 1])
+def test_projected_cur_last(oracle, reference, seed, mode, level_mode, stereo, ori):
+    th, mbf = (15.0 if stereo else 7.0), 40.0
+    frame, pts, kl = synth.make_projected_case(seed, n_kp=1200, n_pts=1500, th=th, stereo=stereo, level_mode=level_mode, lock_frac=0.85)
+    pts.ur = (pts.uv[:, 0] - np.float32(mbf)).astype(np.float32)  # what the reference derives from mbf * invzc (:2056)
+    exp_n, _ = reference.projected_cur_last(frame, pts, th, mode, mbf, kl, ori)
+    pts = _frustum(pts, frame, False)
+    exp_n, exp_own = reference.projected_cur_last(frame, pts, th, mode, mbf, kl, ori)
+    got = oracle.search_projected(frame, pts, 100.0, 1, kl, stereo_gate=1, check_ori=ori)
+    assert exp_n > 100
+    assert got[0] == exp_n and np.array_equal(got[3], exp_own)
+
+
+@pytest.mark.parametrize("seed", [83, 84])
+@pytest.mark.parametrize("ori", [0, 1])
+def test_projected_reloc(oracle, reference, seed, ori):
+    frame, pts, kl = synth.make_projected_case(seed, n_kp=1200, n_pts=1500, th=10.0, level_mode="pm1", lock_frac=1.0)
+    pts = _frustum(pts, frame, False)
+    exp_n, exp_own = reference.projected_reloc(frame, pts, 10.0, 64, kl, ori)
+    got = oracle.search_projected(frame, pts, 64.0, 1, kl, check_ori=ori)
+    assert exp_n > 100
+    assert got[0] == exp_n and np.array_equal(got[3], exp_own)
+
+
+@pytest.mark.parametrize("seed,ratio", [(85, 1.0), (86, 0.9)])
+def test_projected_sim3(oracle, reference, seed, ratio):
+    frame, pts, kl = synth.make_projected_case(seed, n_kp=1200, n_pts=1500, th=8.0, level_mode="pred", lock_frac=1.0)
+    pts = _frustum(pts, frame, True)
+    exp_n, exp_own = reference.projected_sim3(frame, pts, 8, ratio, kl)
+    got = oracle.search_projected(frame, pts, float(np.float32(50) * np.float32(ratio)), 1, kl)
+    assert exp_n > 100
+    assert got[0] == exp_n and np.array_equal(got[3], exp_own)
+
+
+@pytest.mark.parametrize("seed,stereo", [(87, False), (88, True)])
+def test_projected_fuse(oracle, reference, seed, stereo):
+    bf = 40.0
+    frame, pts, _ = synth.make_projected_case(seed, n_kp=1200, n_pts=1500, th=3.0, stereo=stereo, level_mode="pred")
+    pts.ur = (pts.uv[:, 0] - np.float32(bf)).astype(np.float32)  # ur = uv(0) - bf * invz (:1398)
+    inv = (np.float32(1.0) / frame.level_sigma2).astype(np.float32)
+    pts = _frustum(pts, frame, True)
+    exp_n, exp_bi = reference.projected_fuse(frame, pts, 3.0, bf)
+    got = oracle.search_projected(frame, pts, 50.0, 0, None, chi2_gate=1, inv_level_sigma2=inv)
+    assert exp_n > 100
+    assert got[0] == exp_n and np.array_equal(got[1], exp_bi)
+    exp_n, exp_bi = reference.projected_fuse_sim3(frame, pts, 3.0)
+    got = oracle.search_projected(frame, pts, 50.0, 0, None)
+    assert got[0] == exp_n and np.array_equal(got[1], exp_bi)
