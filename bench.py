@@ -312,6 +312,9 @@ def main():
         ctx.synchronize()
         extra["comparisons_per_step"] = int(units_total)
         extra["matches_rank0"] = int((res[3][:nq] >= 0).sum().item())
+    else:
+        extra["comparisons_per_step_rank0"] = ctx.fetch_comparisons()  # DescriptorDistance-equivalents, counted on the device
+        extra["matches_rank0"] = int(nmt[:P].sum().item())
 
     # ---- end to end through the host-pointer C-ABI (what a reference-side caller uses)
     e2e = None
@@ -331,9 +334,12 @@ def main():
         else:
             h2d = case.kf1.nbytes * 2 + case.ep.nbytes + case.f12.nbytes
             d2h = P * C4_FEAT * 4 + P * 4
+            pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+            h_kf1, h_kf2, h_ep, h_f12 = pin(case.kf1), pin(case.kf2), pin(case.ep), pin(case.f12)
+            h_out = (torch.empty((P, C4_FEAT), dtype=torch.int32).pin_memory().numpy(), torch.empty(P, dtype=torch.int32).pin_memory().numpy())
 
             def e2e_step():
-                return m.SearchForTriangulation(ks, case.kf1, case.kf2, case.ep, case.f12)
+                return m.SearchForTriangulation(ks, h_kf1, h_kf2, h_ep, h_f12, out=h_out)
         e2e_step()
         barrier_sync()
         t0 = time.perf_counter()
@@ -354,6 +360,13 @@ def main():
         except Exception:
             pass
         engine = args.engine if args.engine else (4 if getattr(matcher, "TC_DEFAULT", False) else 1)
+        if args.workload == "c4":
+            engine = args.tri_engine if args.tri_engine else 2  # auto = persistent warp-specialised pipeline (monocular sets)
+        traffic = {}
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        except Exception:
+            pass
         per_gpu_units = units_total / world
         kern_s = ms_per_step * 1e-3
         if args.workload == "c5":
@@ -361,22 +374,36 @@ def main():
                 flops = per_gpu_units * 512.0  # 256 MACs per 256-bit comparison on the +-1 fp8 contraction
                 peak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
                 roof = {"bound": "tensor", "achieved": flops / kern_s / 1e12, "peak": peak, "unit": "TFLOP/s",
-                        "frac": flops / kern_s / 1e12 / peak, "traffic": None,
-                        "note": "fp8 dense peak taken as 2x the measured bf16 cuBLAS burst of MEASURED_PEAKS.json"}
+                        "frac": flops / kern_s / 1e12 / peak, "traffic": traffic.get("c5"),
+                        "frac_of_nominal_fp8": flops / kern_s / 1e12 / 4500.0,
+                        "note": "fp8 dense peak taken as 2x the measured bf16 cuBLAS burst of MEASURED_PEAKS.json (no fp8 figure is "
+                                "measured there); against the nominal 4.5 PFLOP/s see frac_of_nominal_fp8.  512 flop per 256-bit comparison"}
             else:
                 popc = per_gpu_units * 8.0  # 8 POPC32 per comparison
                 sm_mhz = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
                 peak = 148 * 16 * sm_mhz * 1e6 / 1e12
                 roof = {"bound": "int-popc", "achieved": popc / kern_s / 1e12, "peak": peak, "unit": "TPOPC32/s",
-                        "frac": popc / kern_s / 1e12 / peak, "traffic": None,
+                        "frac": popc / kern_s / 1e12 / peak, "traffic": traffic.get("c5"),
                         "note": "integer-pipe roofline: 16 POPC/clk/SM x 148 SMs at the SM clock sampled during the run"}
         else:
+            # C4 is bucketed all-pairs work: SURVEY.md 8(d) names the integer pipe as the binding bound (8 POPC32 per
+            # Hamming comparison, 16 POPC32/clk/SM) and HBM as the close second; both are reported, the binding one first
+            cmp_step = float(extra.get("comparisons_per_step_rank0", 0))
+            sm_mhz = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+            popc_peak = 148 * 16 * sm_mhz * 1e6 / 1e12
+            popc = cmp_step * 8.0 / kern_s / 1e12
+            roof = {"bound": "int-popc", "achieved": popc, "peak": popc_peak, "unit": "TPOPC32/s", "frac": popc / popc_peak,
+                    "traffic": traffic.get("c4"),
+                    "note": "8 POPC32 per 256-bit comparison x comparisons counted on the device; peak = 16 POPC32/clk/SM x 148 SMs at the "
+                            "SM clock sampled during the run.  The 128-bit prefilter executes ~4.2 POPC32 per comparison, which is why "
+                            "the fraction can approach 1 while the XU pipe is not saturated"}
             # algorithmic bytes per pair: 32 B x map-point-free descriptors of both keyframes (~50 %), CSR
             # feature ids + node ids, match row out
             bytes_pair = 2 * (0.5 * C4_FEAT * 32 + 0.5 * C4_FEAT * 4 + 100 * 8) + C4_FEAT * 4 + 4 + 44
             gb = per_gpu_units * bytes_pair / 1e9
             peak = float(peaks.get("hbm_gbs", 6650.0))
-            roof = {"bound": "hbm", "achieved": gb / kern_s, "peak": peak, "unit": "GB/s", "frac": gb / kern_s / peak, "traffic": None}
+            extra["roofline_hbm"] = {"bound": "hbm", "achieved": gb / kern_s, "peak": peak, "unit": "GB/s", "frac": gb / kern_s / peak,
+                                     "traffic": traffic.get("c4")}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -106,6 +106,8 @@ int64_t orbgpu_launch_count(orbgpu_ctx *ctx);
 /* number of Hamming comparisons (DescriptorDistance-equivalents) the last search call
  * executed, counted on the device exactly where the reference calls DescriptorDistance. */
 int64_t orbgpu_last_comparisons(orbgpu_ctx *ctx);
+/* same, after synchronising the stream (the *_dev entry points return without synchronising) */
+int orbgpu_fetch_comparisons(orbgpu_ctx *ctx, int64_t *out);
 
 /* ---- a1: ORBmatcher::DescriptorDistance (ORBmatcher.cc:2388-2408), FORB::distance (FORB.cpp:92-112)
  * batched: out[i] = hamming(a[i], b[i]).  Host pointers. */

@@ -226,6 +226,8 @@ class Reference:
         L.ref_search_for_initialization.argtypes = [FH, FH, f32p, C.c_int, C.c_float, C.c_int, i32p]
         L.ref_search_by_projection_local.argtypes = [FH, MP, C.c_float, C.c_int, C.c_float, C.c_float, i32p, i32p]
         PP = C.POINTER(ProjPointsHostStruct)
+        if not hasattr(L, "ref_projected_cur_last"):
+            raise RuntimeError(f"{path} predates the row-a6 harnesses: rebuild with `make -C oracle ref`")
         L.ref_projected_cur_last.argtypes = [FH, PP, C.c_float, C.c_int, C.c_float, u8p, C.c_int, i32p]
         L.ref_projected_reloc.argtypes = [FH, PP, C.c_float, C.c_int, u8p, C.c_int, i32p]
         L.ref_projected_sim3.argtypes = [FH, PP, C.c_int, C.c_float, u8p, i32p]

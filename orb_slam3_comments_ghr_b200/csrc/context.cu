@@ -130,6 +130,17 @@ int ctx_fetch_comparisons(orbgpu_ctx *ctx)
     return ORBGPU_OK;
 }
 
+// public: synchronise the context's stream and return the comparison counter of the last search (device-pointer entry
+// points do not synchronise on their own)
+extern "C" int orbgpu_fetch_comparisons(orbgpu_ctx *ctx, int64_t *out)
+{
+    ARG_TRY(ctx && out);
+    int rc = ctx_fetch_comparisons(ctx);
+    if (rc) return rc;
+    *out = ctx->last_comparisons;
+    return ORBGPU_OK;
+}
+
 int stage_reserve(orbgpu_ctx *ctx, size_t bytes)
 {
     if (bytes <= ctx->h_stage_bytes) return ORBGPU_OK;

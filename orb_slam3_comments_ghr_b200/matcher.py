@@ -145,6 +145,13 @@ class Context:
     def last_comparisons(self) -> int:
         return int(load_library().orbgpu_last_comparisons(self._h))
 
+    def fetch_comparisons(self) -> int:
+        out = C.c_int64(0)
+        L = load_library()
+        L.orbgpu_fetch_comparisons.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        _check(L.orbgpu_fetch_comparisons(self._h, C.byref(out)))
+        return int(out.value)
+
     def set_knn_engine(self, engine: int):
         _check(load_library().orbgpu_knn2_set_engine(self._h, int(engine)))
 
@@ -388,10 +395,20 @@ class ORBmatcher:
         return nm.value, out
 
     # ORBmatcher.h:72, batched over pairs -> (nmatches[P], vMatches12[P, n_feat])
-    def SearchForTriangulation(self, kfs: DeviceKfSet, kf1, kf2, ep, f12, bOnlyStereo: bool = False, bCoarse: bool = False):
+    def SearchForTriangulation(self, kfs: DeviceKfSet, kf1, kf2, ep, f12, bOnlyStereo: bool = False, bCoarse: bool = False, out=None):
+        """out: optional caller-owned (vMatches12[P, n_feat] int32, nmatches[P] int32) host buffers -- pinned memory makes the
+        device-to-host copies asynchronous DMA transfers."""
         kf1, kf2 = as_i32(kf1), as_i32(kf2)
         ep, f12 = as_f32(ep), as_f32(f12)
         P = kf1.shape[0]
+        if out is not None:
+            m, nm = out
+            assert m.dtype == np.int32 and m.shape == (P, kfs.n_feat) and m.flags["C_CONTIGUOUS"]
+            assert nm.dtype == np.int32 and nm.shape == (P,)
+            _check(load_library().orbgpu_search_for_triangulation_batch(self.ctx.handle, kfs.handle, P, _p(kf1, i32p), _p(kf2, i32p),
+                                                                        _p(ep, f32p), _p(f12, f32p), int(bOnlyStereo), int(bCoarse),
+                                                                        int(self.mbCheckOrientation), _p(m, i32p), _p(nm, i32p)))
+            return nm, m
         m = np.empty((P, kfs.n_feat), dtype=np.int32)
         nm = np.empty(P, dtype=np.int32)
         _check(load_library().orbgpu_search_for_triangulation_batch(self.ctx.handle, kfs.handle, P, _p(kf1, i32p), _p(kf2, i32p),
