@@ -264,6 +264,8 @@ int orbgpu_triangulation_set_engine(orbgpu_ctx *ctx, int32_t engine);
  * smallest distance of the multiset (256 when nd < 2).  match = best_idx when
  * best <= th_low && (float)best < nnratio*(float)second, else -1. */
 int orbgpu_db_upload(orbgpu_ctx *ctx, int64_t nd, const uint8_t *db_desc, orbgpu_db **out);
+/* refresh an uploaded database in place (nd <= the size it was created with): one H2D copy, no allocation */
+int orbgpu_db_update(orbgpu_ctx *ctx, orbgpu_db *db, int64_t nd, const uint8_t *db_desc);
 int orbgpu_db_from_dev(orbgpu_ctx *ctx, int64_t nd, const void *db_desc_dev, orbgpu_db **out); /* borrows the pointer */
 void orbgpu_db_destroy(orbgpu_db *db);
 int orbgpu_knn2_ratio(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const uint8_t *q_desc, int32_t th_low, float nnratio,

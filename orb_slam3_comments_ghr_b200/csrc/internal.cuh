@@ -157,7 +157,7 @@ struct orbgpu_kfset {
 
 struct orbgpu_db {
     int device = 0;
-    int64_t nd = 0;
+    int64_t nd = 0, capacity = 0;
     const uint4 *desc = nullptr; // [nd][2]
     bool owned = false;
 };

@@ -286,6 +286,7 @@ extern "C" int orbgpu_db_upload(orbgpu_ctx *ctx, int64_t nd, const uint8_t *db_d
     orbgpu_db *d = new orbgpu_db();
     d->device = ctx->device;
     d->nd = nd;
+    d->capacity = nd;
     d->owned = true;
     void *p = nullptr;
     CU_TRY(cudaMalloc(&p, std::max<int64_t>(nd, 1) * 32));
@@ -293,6 +294,17 @@ extern "C" int orbgpu_db_upload(orbgpu_ctx *ctx, int64_t nd, const uint8_t *db_d
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     d->desc = (const uint4 *)p;
     *out = d;
+    return ORBGPU_OK;
+}
+
+// re-uploads descriptors into an owned database without reallocating (nd must not exceed the size it was created with)
+extern "C" int orbgpu_db_update(orbgpu_ctx *ctx, orbgpu_db *db, int64_t nd, const uint8_t *db_desc)
+{
+    ARG_TRY(ctx && db && db->owned && nd >= 0 && nd <= db->capacity && (nd == 0 || db_desc));
+    CU_TRY(cudaSetDevice(ctx->device));
+    if (nd > 0) CU_TRY(cudaMemcpyAsync((void *)db->desc, db_desc, nd * 32, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    db->nd = nd;
     return ORBGPU_OK;
 }
 

@@ -314,6 +314,14 @@ class DeviceDb:
             self.nd = int(nd)
             _check(load_library().orbgpu_db_from_dev(ctx.handle, self.nd, C.c_void_p(dev_ptr), C.byref(self._h)))
 
+    def update(self, host):
+        """re-upload the descriptors in place (no reallocation)"""
+        d = as_u8(host).reshape(-1, 32)
+        L = load_library()
+        L.orbgpu_db_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, u8p]
+        _check(L.orbgpu_db_update(self.ctx.handle, self._h, d.shape[0], _p(d, u8p)))
+        self.nd = d.shape[0]
+
     def __del__(self):
         try:
             if self._h:
