@@ -254,10 +254,12 @@ def main():
         ctx.set_knn_engine(args.engine)
         ddb = ctx.database_from_device(db.data_ptr(), nd, keepalive=db)
 
+        gathered = torch.empty((nq_total, 4), dtype=torch.int32, device=dev) if world > 1 else None
+
         def step():
             m.SearchByNN_dev(ddb, nq, q.data_ptr(), res[0].data_ptr(), res[1].data_ptr(), res[2].data_ptr(), res[3].data_ptr(), TH_LOW)
             if world > 1:
-                return all_gather_rows(res.t().contiguous(), nq_total)
+                return all_gather_rows(res.t().contiguous(), nq_total, out=gathered)
             return res
 
         units_total = float(nq_total) * float(nd)
@@ -275,10 +277,12 @@ def main():
         out = torch.empty((max(P, 1), C4_FEAT), dtype=torch.int32, device=dev)
         nmt = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
 
+        gathered = torch.empty((P_total, C4_FEAT), dtype=torch.int32, device=dev) if world > 1 else None
+
         def step():
             m.SearchForTriangulation_dev(ks, P, kf1.data_ptr(), kf2.data_ptr(), ep.data_ptr(), f12.data_ptr(), out.data_ptr(), nmt.data_ptr())
             if world > 1:
-                return all_gather_rows(out, P_total)
+                return all_gather_rows(out, P_total, out=gathered)
             return out
 
         units_total = float(P_total)

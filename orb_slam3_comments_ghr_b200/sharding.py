@@ -21,13 +21,19 @@ def max_shard(n: int, world: int) -> int:
     return (n + world - 1) // world
 
 
-def all_gather_rows(local: torch.Tensor, n_total: int) -> torch.Tensor:
-    """local: [rows_of_this_rank, ...] -> [n_total, ...] on every rank with a single all-gather
-    (shards are padded to the largest shard and trimmed afterwards)."""
+def all_gather_rows(local: torch.Tensor, n_total: int, out: torch.Tensor = None) -> torch.Tensor:
+    """local: [rows_of_this_rank, ...] -> [n_total, ...] on every rank with a single all-gather.
+    Equal shards (n_total divisible by the world size) gather straight into `out` (a caller-owned [n_total, ...]
+    buffer, allocated when omitted) with no staging copy; ragged shards are padded to the largest shard and trimmed."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return local
     world, rank = dist.get_world_size(), dist.get_rank()
     cap = max_shard(n_total, world)
+    if n_total % world == 0:
+        if out is None:
+            out = torch.empty((n_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous())
+        return out
     pad = torch.zeros((cap,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
     out = torch.empty((world * cap,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)

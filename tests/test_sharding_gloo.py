@@ -41,9 +41,15 @@ def _worker(rank, world, port, nq, nd, ret):
     plo, phi = shard_bounds(5, rank, world)
     nm, m = o.search_for_triangulation_batch(tc.kfs, tc.kf1[plo:phi], tc.kf2[plo:phi], tc.ep[plo:phi], tc.f12[plo:phi])
     fullm = all_gather_rows(torch.from_numpy(m), 5)
+    # equal shards: the direct path into a caller-owned buffer
+    elo, ehi = shard_bounds(300, rank, world)
+    buf = torch.empty((300, 4), dtype=local.dtype)
+    eq = all_gather_rows(torch.from_numpy(np.stack(o.knn2_ratio(kc.q[elo:ehi], kc.db, 50, 0.8, 1), axis=1)), 300, out=buf)
     if rank == 0:
         ret["knn"] = full.numpy()
         ret["tri"] = fullm.numpy()
+        ret["knn_eq"] = eq.numpy()
+        ret["eq_in_place"] = eq.data_ptr() == buf.data_ptr()
     dist.barrier()
     dist.destroy_process_group()
 
@@ -58,6 +64,7 @@ def test_world2_allgather_matches_single_rank(oracle):
     kc = synth.make_knn_case(61, nq, nd)
     exp = np.stack(oracle.knn2_ratio(kc.q, kc.db, 50, 0.8, 1), axis=1)
     assert np.array_equal(ret["knn"], exp)
+    assert np.array_equal(ret["knn_eq"], exp[:300]) and ret["eq_in_place"]
     tc = synth.fill_geometry(synth.make_triangulation_case(62, n_pairs=5, n_feat=256))
     nm, m = oracle.search_for_triangulation_batch(tc.kfs, tc.kf1, tc.kf2, tc.ep, tc.f12)
     assert np.array_equal(ret["tri"], m)
