@@ -278,6 +278,30 @@ int orbgpu_knn2_ratio_dev(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, cons
  * 4 = tcgen05 with cta_group::2 SM pairs (what auto resolves to for nq >= 128 and nd >= 1024). */
 int orbgpu_knn2_set_engine(orbgpu_ctx *ctx, int32_t engine);
 
+/* ---- 8(f) rank 2: KeyFrameDatabase candidate scoring -- the query BowVector against every key frame's BowVector.
+ * common_words[kf] = number of words shared with the query (the inverted-file walk of KeyFrameDatabase.cc:928-943:
+ * mnRelocWords / mnLoopWords / mnMergeWords); scores[kf] = L1Scoring::score(query, kf) (ScoringObject.cpp:23-68), double,
+ * summed in ascending word order.  The caller casts to float (`float si = mpVoc->score(...)`, :970) and applies the
+ * candidate policy (:949-1031).  The database is the CSR of the key frames' BowVectors (words ascending per key frame). */
+typedef struct orbgpu_bowdb orbgpu_bowdb;
+typedef struct orbgpu_bowdb_host {
+    int32_t n_kf;
+    const int32_t *offsets;  /* [n_kf+1] */
+    const uint32_t *words;   /* [offsets[n_kf]] */
+    const double *values;    /* [offsets[n_kf]] */
+} orbgpu_bowdb_host;
+int orbgpu_bowdb_upload(orbgpu_ctx *ctx, const orbgpu_bowdb_host *h, orbgpu_bowdb **out);
+void orbgpu_bowdb_destroy(orbgpu_bowdb *d);
+int orbgpu_bow_score_l1(orbgpu_ctx *ctx, const orbgpu_bowdb *db, int32_t nq_words, const uint32_t *q_words,
+                        const double *q_values, int32_t *common_words, double *scores);
+
+/* ---- 8(f) rank 4: batched MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:444-535).  Map point p observes the
+ * descriptors desc[offsets[p] .. offsets[p+1]) (observation order, left then right index per key frame, :465-477).
+ * best_idx[p] = the row with the smallest median distance to the others (first wins ties, :510-514), -1 for an empty
+ * list; best_median[p] (may be NULL) = that median.  The caller clones vDescriptors[best_idx] into mDescriptor (:518). */
+int orbgpu_compute_distinctive_descriptors(orbgpu_ctx *ctx, int32_t n_mp, const int32_t *offsets, const uint8_t *desc,
+                                           int32_t *best_idx, int32_t *best_median);
+
 /* ---- a10: ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:2341-2383) exposed for testing:
  * histo[30] bin sizes -> ind[3]. Runs on the device. */
 int orbgpu_compute_three_maxima(orbgpu_ctx *ctx, const int32_t *histo, int32_t L, int32_t *ind);

@@ -421,6 +421,72 @@ int oracle_search_projected(const orbgpu_frame_host *f, const orbgpu_projpoints_
     return nmatches;
 }
 
+/* KeyFrameDatabase candidate scoring: common words per key frame (the inverted-file walk of
+ * KeyFrameDatabase.cc:928-943 counts one per (query word, key frame holding it)) and L1Scoring::score
+ * (Thirdparty/DBoW2/DBoW2/ScoringObject.cpp:23-68) of the query against every key frame. */
+void oracle_bow_score_l1(const orbgpu_bowdb_host *db, int32_t nq, const uint32_t *q_words, const double *q_values,
+                         int32_t *common_words, double *scores)
+{
+    for (int kf = 0; kf < db->n_kf; kf++) {
+        int a = 0, b = db->offsets[kf];
+        const int b_end = db->offsets[kf + 1];
+        double score = 0;
+        int n_common = 0;
+        while (a < nq && b < b_end) {
+            const double vi = q_values[a], wi = db->values[b];
+            if (q_words[a] == db->words[b]) {
+                score += fabs(vi - wi) - fabs(vi) - fabs(wi);
+                n_common++;
+                ++a; ++b;
+            } else if (q_words[a] < db->words[b]) {
+                while (a < nq && q_words[a] < db->words[b]) ++a; /* v1.lower_bound(v2_it->first) */
+            } else {
+                while (b < b_end && db->words[b] < q_words[a]) ++b; /* v2.lower_bound(v1_it->first) */
+            }
+        }
+        common_words[kf] = n_common;
+        scores[kf] = -score / 2.0;
+    }
+}
+
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:444-535) for a batch of map points whose observation
+ * descriptors are given as a CSR.  The real MapPoint.cc cannot be compiled here (OpenCV / Eigen / Boost / g2o), so this is a
+ * restatement only; tests/test_oracle_golden.py cross-checks it with an independent numpy evaluation. */
+static int cmp_int(const void *a, const void *b) { return *(const int *)a - *(const int *)b; }
+void oracle_compute_distinctive_descriptors(int32_t n_mp, const int32_t *offsets, const uint8_t *desc, int32_t *best_idx,
+                                            int32_t *best_median)
+{
+    for (int p = 0; p < n_mp; p++) {
+        const int s = offsets[p], N = offsets[p + 1] - s;
+        best_idx[p] = -1;
+        if (best_median) best_median[p] = -1;
+        if (N <= 0) continue; /* :455-456, :481-482 */
+        float *Distances = (float *)malloc(sizeof(float) * (size_t)N * (size_t)N); /* float Distances[N][N] (:487) */
+        int *vDists = (int *)malloc(sizeof(int) * (size_t)N);
+        for (int i = 0; i < N; i++) {
+            Distances[(size_t)i * N + i] = 0;
+            for (int j = i + 1; j < N; j++) {
+                const int distij = oracle_descriptor_distance(desc + 32 * (size_t)(s + i), desc + 32 * (size_t)(s + j));
+                Distances[(size_t)i * N + j] = (float)distij;
+                Distances[(size_t)j * N + i] = (float)distij;
+            }
+        }
+        int BestMedian = 0x7FFFFFFF, BestIdx = 0;
+        for (int i = 0; i < N; i++) {
+            for (int j = 0; j < N; j++) vDists[j] = (int)Distances[(size_t)i * N + j];
+            qsort(vDists, (size_t)N, sizeof(int), cmp_int);
+            const int median = vDists[(size_t)(0.5 * (N - 1))];
+            if (median < BestMedian) {
+                BestMedian = median;
+                BestIdx = i;
+            }
+        }
+        best_idx[p] = BestIdx;
+        if (best_median) best_median[p] = BestMedian;
+        free(Distances); free(vDists);
+    }
+}
+
 /* TemplatedVocabulary.h:1216-1258 */
 void oracle_voc_transform(const orbgpu_voc_host *v, int32_t n, const uint8_t *desc, int levelsup, uint32_t *word_id,
                           uint32_t *node_id, double *weight)

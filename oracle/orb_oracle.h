@@ -54,6 +54,14 @@ int oracle_search_by_projection_local(const orbgpu_frame_host *f, const orbgpu_m
 int oracle_search_projected(const orbgpu_frame_host *f, const orbgpu_projpoints_host *pts, const orbgpu_projsearch_params *prm,
                             const uint8_t *kp_locked, int32_t *best_idx, int32_t *best_dist, int32_t *kp_owner);
 
+/* KeyFrameDatabase.cc:928-943 (common words) + ScoringObject.cpp:23-68 (L1Scoring::score), query vs every key frame */
+void oracle_bow_score_l1(const orbgpu_bowdb_host *db, int32_t nq, const uint32_t *q_words, const double *q_values,
+                         int32_t *common_words, double *scores);
+
+/* MapPoint.cc:444-535 batched over a CSR of observation descriptors (restatement only: MapPoint.cc does not compile here) */
+void oracle_compute_distinctive_descriptors(int32_t n_mp, const int32_t *offsets, const uint8_t *desc, int32_t *best_idx,
+                                            int32_t *best_median);
+
 /* TemplatedVocabulary.h:1216-1258 per feature */
 void oracle_voc_transform(const orbgpu_voc_host *v, int32_t n, const uint8_t *desc, int levelsup, uint32_t *word_id,
                           uint32_t *node_id, double *weight);

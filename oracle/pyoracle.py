@@ -14,7 +14,7 @@ from typing import Optional
 
 import numpy as np
 
-from orb_slam3_comments_ghr_b200._abi import (FrameHostStruct, HostFrame, HostKfSet, HostMapPoints, HostProjPoints, HostVoc,
+from orb_slam3_comments_ghr_b200._abi import (BowDbHostStruct, HostBowDb, FrameHostStruct, HostFrame, HostKfSet, HostMapPoints, HostProjPoints, HostVoc,
                                               ProjPointsHostStruct, ProjSearchParamsStruct, proj_params,
                                               KfSetHostStruct, MapPointsHostStruct, VocHostStruct, as_f32, as_i32,
                                               as_u8, f32p, f64p, i32p, u8p, u32p)
@@ -119,6 +119,28 @@ class Oracle:
         n = self.lib.oracle_search_by_projection_local(C.byref(sf), C.byref(sm), float(th), int(far_points),
                                                        float(th_far), float(nnratio), _p(prior, i32p), _p(kp_mp, i32p))
         return int(n), kp_mp
+
+    def compute_distinctive_descriptors(self, offsets, desc):
+        off = as_i32(offsets)
+        d = as_u8(desc).reshape(-1, 32)
+        n = off.shape[0] - 1
+        bi = np.full(max(n, 1), -1, dtype=np.int32)
+        bm = np.full(max(n, 1), -1, dtype=np.int32)
+        self.lib.oracle_compute_distinctive_descriptors.argtypes = [C.c_int32, i32p, u8p, i32p, i32p]
+        self.lib.oracle_compute_distinctive_descriptors.restype = None
+        self.lib.oracle_compute_distinctive_descriptors(n, _p(off, i32p), _p(d, u8p), _p(bi, i32p), _p(bm, i32p))
+        return bi[:n], bm[:n]
+
+    def bow_score_l1(self, db: HostBowDb, q_words, q_values):
+        qw = np.ascontiguousarray(q_words, dtype=np.uint32)
+        qv = np.ascontiguousarray(q_values, dtype=np.float64)
+        common = np.zeros(max(db.n_kf, 1), dtype=np.int32)
+        scores = np.zeros(max(db.n_kf, 1), dtype=np.float64)
+        self.lib.oracle_bow_score_l1.argtypes = [C.POINTER(BowDbHostStruct), C.c_int32, u32p, f64p, i32p, f64p]
+        self.lib.oracle_bow_score_l1.restype = None
+        s = db.struct()
+        self.lib.oracle_bow_score_l1(C.byref(s), qw.shape[0], _p(qw, u32p), _p(qv, f64p), _p(common, i32p), _p(scores, f64p))
+        return common[:db.n_kf], scores[:db.n_kf]
 
     def search_projected(self, f: HostFrame, pts: HostProjPoints, max_dist, ordered, kp_locked=None, stereo_gate=False,
                          chi2_gate=False, check_ori=False, inv_level_sigma2=None):
@@ -292,6 +314,17 @@ class Reference:
         n = self.lib.ref_search_by_projection_local(C.byref(sf), C.byref(sm), float(th), int(far_points), float(th_far),
                                                     float(nnratio), _p(prior, i32p), _p(kp_mp, i32p))
         return int(n), kp_mp
+
+    def bow_score_l1(self, db: HostBowDb, q_words, q_values):
+        qw = np.ascontiguousarray(q_words, dtype=np.uint32)
+        qv = np.ascontiguousarray(q_values, dtype=np.float64)
+        common = np.zeros(max(db.n_kf, 1), dtype=np.int32)
+        scores = np.zeros(max(db.n_kf, 1), dtype=np.float64)
+        self.lib.ref_bow_score_l1.argtypes = [C.POINTER(BowDbHostStruct), C.c_int32, u32p, f64p, i32p, f64p]
+        self.lib.ref_bow_score_l1.restype = None
+        s = db.struct()
+        self.lib.ref_bow_score_l1(C.byref(s), qw.shape[0], _p(qw, u32p), _p(qv, f64p), _p(common, i32p), _p(scores, f64p))
+        return common[:db.n_kf], scores[:db.n_kf]
 
     # the reference's self-projecting overloads on degenerate geometry (see ref_adapter.cc): everything from the window on
     def projected_cur_last(self, cur: HostFrame, pts: HostProjPoints, th, mode, mbf, kp_locked, check_ori):

@@ -22,6 +22,7 @@
 #include "ORBmatcher.h" // the reference's include/ORBmatcher.h (stubs resolve MapPoint.h/KeyFrame.h/Frame.h)
 
 #include "Thirdparty/DBoW2/DBoW2/FORB.h"
+#include "Thirdparty/DBoW2/DBoW2/ScoringObject.h"
 // The fork added `std::vector<std::pair<TDescriptor, F>> vocabulary;` (TemplatedVocabulary.h:435)
 // with F = FORB abstract, which does not compile as shipped.  Giving that one pair type an
 // (empty) explicit specialisation lets the header compile unmodified; the member is unused.
@@ -424,6 +425,29 @@ extern "C"
             if (repl[i]) best_idx[i] = std::get<0>(static_cast<TaggedMapPoint *>(repl[i])->observations_[&K]);
         }
         return n;
+    }
+
+    // DBoW2::L1Scoring::score (the reference's ScoringObject.cpp, compiled unmodified) of the query against every key
+    // frame of a CSR database; common words counted from the same std::map objects (KeyFrameDatabase.cc:928-943 walks an
+    // inverted file over exactly these (word, key frame) incidences)
+    void ref_bow_score_l1(const orbgpu_bowdb_host *db, int32_t nq, const uint32_t *q_words, const double *q_values,
+                          int32_t *common_words, double *scores)
+    {
+        DBoW2::BowVector q;
+        for (int i = 0; i < nq; i++) q.insert(std::make_pair(q_words[i], q_values[i]));
+        DBoW2::L1Scoring l1;
+        for (int kf = 0; kf < db->n_kf; kf++)
+        {
+            DBoW2::BowVector v;
+            int n_common = 0;
+            for (int j = db->offsets[kf]; j < db->offsets[kf + 1]; j++)
+            {
+                v.insert(std::make_pair(db->words[j], db->values[j]));
+                n_common += (int)q.count(db->words[j]);
+            }
+            common_words[kf] = n_common;
+            scores[kf] = l1.score(q, v);
+        }
     }
 
     int ref_search_by_bow_kf_f(const orbgpu_frame_host *kf, const orbgpu_frame_host *f, const uint8_t *kf_mp_valid,

@@ -120,6 +120,10 @@ class ProjSearchParamsStruct(C.Structure):
     ]
 
 
+class BowDbHostStruct(C.Structure):
+    _fields_ = [("n_kf", C.c_int32), ("offsets", i32p), ("words", u32p), ("values", f64p)]
+
+
 class KfSetHostStruct(C.Structure):
     _fields_ = [
         ("n_kf", C.c_int32), ("n_feat", C.c_int32),
@@ -384,6 +388,32 @@ def proj_params(max_dist, ordered, stereo_gate=0, chi2_gate=0, check_ori=0, inv_
     p.inv_level_sigma2 = _ptr(inv, f32p)
     p._keep = inv
     return p
+
+
+@dataclass
+class HostBowDb:
+    """CSR of the key frames' BowVectors (words ascending inside a key frame): the database KeyFrameDatabase indexes."""
+    offsets: np.ndarray
+    words: np.ndarray
+    values: np.ndarray
+
+    def __post_init__(self):
+        self.offsets = as_i32(self.offsets)
+        self.words = as_u32(self.words)
+        self.values = np.ascontiguousarray(self.values, dtype=np.float64)
+
+    @property
+    def n_kf(self) -> int:
+        return int(self.offsets.shape[0] - 1)
+
+    def struct(self) -> BowDbHostStruct:
+        s = BowDbHostStruct()
+        s.n_kf = self.n_kf
+        s.offsets = _ptr(self.offsets, i32p)
+        s.words = _ptr(self.words, u32p)
+        s.values = _ptr(self.values, f64p)
+        s._keep = self
+        return s
 
 
 @dataclass

@@ -14,7 +14,7 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-from ._abi import (FrameHostStruct, HostFrame, HostKfSet, HostMapPoints, HostProjPoints, HostVoc, KfSetHostStruct, MapPointsHostStruct,
+from ._abi import (BowDbHostStruct, HostBowDb, FrameHostStruct, HostFrame, HostKfSet, HostMapPoints, HostProjPoints, HostVoc, KfSetHostStruct, MapPointsHostStruct,
                    ProjPointsHostStruct, ProjSearchParamsStruct, proj_params, VocHostStruct, as_f32, as_i32, as_u8, f32p, f64p, i32p, i64p, u8p, u32p)
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liborbmatch_b200.so")
@@ -181,6 +181,21 @@ class Context:
     def upload_kfset(self, s: HostKfSet) -> "DeviceKfSet":
         return DeviceKfSet(self, s)
 
+    # MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:444-535) for a batch of map points -> (best_idx, best_median)
+    def compute_distinctive_descriptors(self, offsets, desc):
+        off = as_i32(offsets)
+        d = as_u8(desc).reshape(-1, 32)
+        n = off.shape[0] - 1
+        bi = np.full(max(n, 1), -1, dtype=np.int32)
+        bm = np.full(max(n, 1), -1, dtype=np.int32)
+        L = load_library()
+        L.orbgpu_compute_distinctive_descriptors.argtypes = [C.c_void_p, C.c_int32, i32p, u8p, i32p, i32p]
+        _check(L.orbgpu_compute_distinctive_descriptors(self._h, n, _p(off, i32p), _p(d, u8p), _p(bi, i32p), _p(bm, i32p)))
+        return bi[:n], bm[:n]
+
+    def upload_bow_database(self, db: HostBowDb) -> "DeviceBowDb":
+        return DeviceBowDb(self, db)
+
     def upload_database(self, db) -> "DeviceDb":
         return DeviceDb(self, host=db)
 
@@ -299,6 +314,39 @@ class DeviceKfSet:
     @property
     def handle(self):
         return self._h
+
+
+class DeviceBowDb:
+    """Device CSR of the key frames' BowVectors; score() = KeyFrameDatabase's common-word count and L1Scoring::score of a query
+    BowVector against every key frame (KeyFrameDatabase.cc:928-943, :970; ScoringObject.cpp:23-68)."""
+
+    def __init__(self, ctx: Context, db: HostBowDb):
+        self.ctx, self.n_kf = ctx, db.n_kf
+        self._h = C.c_void_p()
+        L = load_library()
+        L.orbgpu_bowdb_upload.argtypes = [C.c_void_p, C.POINTER(BowDbHostStruct), C.POINTER(C.c_void_p)]
+        L.orbgpu_bowdb_destroy.argtypes = [C.c_void_p]
+        L.orbgpu_bowdb_destroy.restype = None
+        L.orbgpu_bow_score_l1.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, u32p, f64p, i32p, f64p]
+        s = db.struct()
+        _check(L.orbgpu_bowdb_upload(ctx.handle, C.byref(s), C.byref(self._h)))
+
+    def score(self, q_words, q_values):
+        qw = np.ascontiguousarray(q_words, dtype=np.uint32)
+        qv = np.ascontiguousarray(q_values, dtype=np.float64)
+        common = np.zeros(max(self.n_kf, 1), dtype=np.int32)
+        scores = np.zeros(max(self.n_kf, 1), dtype=np.float64)
+        _check(load_library().orbgpu_bow_score_l1(self.ctx.handle, self._h, qw.shape[0], _p(qw, u32p), _p(qv, f64p), _p(common, i32p),
+                                                  _p(scores, f64p)))
+        return common[:self.n_kf], scores[:self.n_kf]
+
+    def __del__(self):
+        try:
+            if self._h:
+                load_library().orbgpu_bowdb_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
 
 
 class DeviceDb:

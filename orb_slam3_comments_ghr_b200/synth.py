@@ -14,7 +14,7 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-from ._abi import HostFrame, HostKfSet, HostMapPoints, HostProjPoints, HostVoc, orb_scale_tables
+from ._abi import HostBowDb, HostFrame, HostKfSet, HostMapPoints, HostProjPoints, HostVoc, orb_scale_tables
 
 IMG_W, IMG_H = 640.0, 480.0
 # orbbec335L_rgbd.yaml:11-14
@@ -216,6 +216,52 @@ def make_projected_case(seed: int, n_kp: int = 2000, n_pts: int = 3000, th: floa
     pts = HostProjPoints(desc, uv, radius, lo, hi, active, ur=pur, locks=locks, angle=angle)
     kp_locked = (rng.random(n_kp) < 0.1).astype(np.uint8)
     return frame, pts, kp_locked
+
+
+def make_distinctive_case(seed: int, n_mp: int = 3000, max_obs: int = 40):
+    """Observation descriptors of n_mp map points (CSR): noisy copies of a per-point prototype, a few outliers, some points with
+    1-2 observations (median index 0), a few empty lists, duplicates (distance 0 ties) and one long list."""
+    rng = np.random.default_rng(seed)
+    offs, descs = [0], []
+    for p in range(n_mp):
+        n = 0 if p % 211 == 7 else int(rng.integers(1, max_obs + 1))
+        if p == n_mp // 2:
+            n = 1500  # longer than the shared-memory staging of the kernel
+        proto = random_descriptors(rng, 1)
+        d = np.repeat(proto, n, axis=0) ^ flip_mask(rng, n, rng.choice(np.array([3, 4, 5]), size=n)) if n else np.zeros((0, 32), np.uint8)
+        if n > 3:
+            d[rng.integers(0, n)] = random_descriptors(rng, 1)[0]      # an outlier observation
+            if p % 5 == 0:
+                d[rng.integers(0, n)] = d[rng.integers(0, n)]         # exact duplicates
+        descs.append(d)
+        offs.append(offs[-1] + n)
+    return np.array(offs, dtype=np.int32), np.concatenate(descs, axis=0)
+
+
+def make_bowdb_case(seed: int, n_kf: int = 2000, n_words_voc: int = 10000, words_per_kf: int = 800):
+    """A key-frame database of L1-normalised BowVectors over a vocabulary of n_words_voc words plus a query that shares many
+    words with a few key frames (the relocalisation / loop candidates) and few with the rest; sizes vary per key frame and a
+    few are empty or disjoint from the query."""
+    rng = np.random.default_rng(seed)
+    offs, words, vals = [0], [], []
+    pop = rng.zipf(1.3, size=n_words_voc).astype(np.float64)  # popular words, as in a real vocabulary
+    pop /= pop.sum()
+
+    def bow(n):
+        w = np.unique(rng.choice(n_words_voc, size=n, p=pop))
+        v = rng.gamma(2.0, 1.0, size=w.shape[0])
+        return w.astype(np.uint32), v / v.sum()
+
+    qw, qv = bow(words_per_kf + 200)
+    for k in range(n_kf):
+        n = int(rng.integers(1, 2 * words_per_kf)) if k % 97 else 0
+        w, v = bow(n) if n else (np.zeros(0, np.uint32), np.zeros(0))
+        if k % 50 == 3 and w.size:  # a near-duplicate of the query: perturbed weights on a subset of its words
+            keep = rng.random(qw.shape[0]) < 0.8
+            w, v = qw[keep].copy(), qv[keep] * rng.uniform(0.5, 1.5, int(keep.sum()))
+            v = v / v.sum()
+        words.append(w); vals.append(v); offs.append(offs[-1] + w.shape[0])
+    return HostBowDb(np.array(offs), np.concatenate(words), np.concatenate(vals)), qw, qv
 
 
 # ---------------------------------------------------------------- vocabulary

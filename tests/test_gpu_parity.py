@@ -343,3 +343,58 @@ def test_knn2_properties_large(ctx, M):
     assert np.array_equal(got_d, bd)
     again = m.SearchByNN(d, q, 50)
     assert all(np.array_equal(a, b) for a, b in zip((bi, bd, sd, mt), again))
+
+
+def test_triangulation_full_size_properties(ctx, M, oracle):
+    """BASELINE.json config C4 at full size (4096 key-frame pairs x 2000 features): the two engines agree on every match row,
+    count and comparison counter; a 64-pair sample equals the oracle; every reported match satisfies the reference's
+    acceptance conditions (both features without a map point, same vocabulary node, distance <= TH_LOW); idempotence."""
+    P = 4096
+    tc = synth.fill_geometry(synth.make_triangulation_case(20261018, n_pairs=P, n_feat=2000))
+    ks = ctx.upload_kfset(tc.kfs)
+    mm = M.ORBmatcher(0.6, False, ctx)
+    res = {}
+    for eng in (1, 2):
+        ctx.set_triangulation_engine(eng)
+        nm, m = mm.SearchForTriangulation(ks, tc.kf1, tc.kf2, tc.ep, tc.f12)
+        res[eng] = (nm.copy(), m.copy(), ctx.last_comparisons)
+    ctx.set_triangulation_engine(0)
+    nm2, m2 = mm.SearchForTriangulation(ks, tc.kf1, tc.kf2, tc.ep, tc.f12)
+    assert np.array_equal(res[1][0], res[2][0]) and np.array_equal(res[1][1], res[2][1]) and res[1][2] == res[2][2]
+    assert np.array_equal(nm2, res[2][0]) and np.array_equal(m2, res[2][1])
+    nm, m, _ = res[2]
+    assert np.array_equal(nm, (m >= 0).sum(axis=1)) and nm.sum() > 100 * P
+    sel = np.arange(0, P, 64)
+    enm, em = oracle.search_for_triangulation_batch(tc.kfs, tc.kf1[sel], tc.kf2[sel], tc.ep[sel], tc.f12[sel], 0, 0, 0,
+                                                    n_threads=os.cpu_count() or 1)
+    assert np.array_equal(nm[sel], enm) and np.array_equal(m[sel], em)
+    p, i1 = np.nonzero(m >= 0)
+    i2 = m[p, i1]
+    k1, k2 = tc.kf1[p], tc.kf2[p]
+    assert not tc.kfs.has_mp[k1, i1].any() and not tc.kfs.has_mp[k2, i2].any()
+    assert np.array_equal(tc.kfs.node_id[k1, i1], tc.kfs.node_id[k2, i2])
+    d = np.unpackbits(tc.kfs.desc[k1, i1] ^ tc.kfs.desc[k2, i2], axis=1).sum(axis=1)
+    assert d.max() <= 50
+
+
+@pytest.mark.parametrize("seed,n_kf", [(121, 3000), (122, 257), (123, 1)])
+def test_bow_score_l1(ctx, oracle, seed, n_kf):
+    """8(f) rank 2: KeyFrameDatabase candidate scoring -- bit-exact doubles (the sum runs in word order per key frame)"""
+    db, qw, qv = synth.make_bowdb_case(seed, n_kf=n_kf)
+    ddb = ctx.upload_bow_database(db)
+    gc, gs = ddb.score(qw, qv)
+    ec, es = oracle.bow_score_l1(db, qw, qv)
+    assert np.array_equal(gc, ec) and np.array_equal(gs.view(np.uint64), es.view(np.uint64))
+    gc, gs = ddb.score(qw[:0], qv[:0])
+    assert not gc.any() and not gs.any()
+
+
+@pytest.mark.parametrize("seed,n_mp,max_obs", [(141, 3000, 40), (142, 50, 300), (143, 1, 1)])
+def test_compute_distinctive_descriptors(ctx, oracle, seed, n_mp, max_obs):
+    """8(f) rank 4: batched MapPoint::ComputeDistinctiveDescriptors"""
+    offs, desc = synth.make_distinctive_case(seed, n_mp=n_mp, max_obs=max_obs)
+    gi, gm = ctx.compute_distinctive_descriptors(offs, desc)
+    oracle.reset_comparisons()
+    ei, em = oracle.compute_distinctive_descriptors(offs, desc)
+    assert np.array_equal(gi, ei) and np.array_equal(gm, em)
+    assert ctx.last_comparisons == oracle.comparisons()

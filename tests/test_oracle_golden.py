@@ -108,3 +108,22 @@ def test_search_projected(oracle, name):
         assert np.array_equal(own, g[name + "/kp_owner"])
     else:
         assert np.array_equal(bi, g[name + "/best_idx"])
+
+
+def test_compute_distinctive_descriptors_vs_numpy(oracle):
+    """8(f) rank 4: MapPoint.cc does not compile here, so the restatement is cross-checked with an independent numpy evaluation of
+    MapPoint.cc:487-515 (all-pairs popcount, np.sort, index int(0.5*(N-1)), first minimum)."""
+    offs, desc = synth.make_distinctive_case(131, n_mp=400, max_obs=30)
+    bi, bm = oracle.compute_distinctive_descriptors(offs, desc)
+    bits = np.unpackbits(desc, axis=1).astype(np.int32)
+    for p in range(offs.shape[0] - 1):
+        s, e = offs[p], offs[p + 1]
+        if e == s:
+            assert bi[p] == -1
+            continue
+        if e - s > 200:
+            continue
+        b = bits[s:e]
+        dist = (b[:, None, :] != b[None, :, :]).sum(axis=2)
+        med = np.sort(dist, axis=1)[:, int(0.5 * (e - s - 1))]
+        assert bi[p] == int(np.argmin(med)) and bm[p] == int(med.min())

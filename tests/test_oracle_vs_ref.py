@@ -168,3 +168,16 @@ def test_projected_fuse(oracle, reference, seed, stereo):
     exp_n, exp_bi = reference.projected_fuse_sim3(frame, pts, 3.0)
     got = oracle.search_projected(frame, pts, 50.0, 0, None)
     assert got[0] == exp_n and np.array_equal(got[1], exp_bi)
+
+
+@pytest.mark.parametrize("seed", [111, 112])
+def test_bow_score_l1(oracle, reference, seed):
+    """8(f) rank 2: the restated L1Scoring::score / common-word count against the reference's ScoringObject.cpp"""
+    db, qw, qv = synth.make_bowdb_case(seed, n_kf=600)
+    ec, es = reference.bow_score_l1(db, qw, qv)
+    gc, gs = oracle.bow_score_l1(db, qw, qv)
+    assert np.array_equal(gc, ec) and np.array_equal(gs.view(np.uint64), es.view(np.uint64))
+    assert es.max() > 0.3 and (ec == 0).any()
+    ec, es = reference.bow_score_l1(db, qw[:0], qv[:0])  # empty query
+    gc, gs = oracle.bow_score_l1(db, qw[:0], qv[:0])
+    assert np.array_equal(gc, ec) and np.array_equal(gs.view(np.uint64), es.view(np.uint64))
