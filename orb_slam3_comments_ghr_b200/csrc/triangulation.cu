@@ -397,37 +397,25 @@ __device__ __forceinline__ void ts_mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void ts_mbar_wait(uint32_t bar, uint32_t parity)
+// Blocking wait: try_wait with a suspend-time hint parks the warp in hardware instead of re-polling -- the polls of the
+// waiting roles (post, join, producer and the compare warps between pairs) were 40 % of all issued instructions and took
+// issue slots from the compare loop.
+__device__ __forceinline__ void ts_mbar_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns)
 {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "TS_WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra TS_WAIT_DONE;\n\t"
         "bra TS_WAIT_LOOP;\n\t"
         "TS_WAIT_DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity)
+        "}" ::"r"(bar), "r"(parity), "r"(hint_ns)
         : "memory");
 }
-// for the roles that normally wait (producer, join, post): poll with a short sleep so that the compare warps keep the issue slots
-__device__ __forceinline__ void ts_mbar_wait_relaxed(uint32_t bar, uint32_t parity)
-{
-    for (;;) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (ok) return;
-        __nanosleep(64);
-    }
-}
+__device__ __forceinline__ void ts_mbar_wait(uint32_t bar, uint32_t parity) { ts_mbar_wait_hint(bar, parity, 4000u); }
+// the roles that normally wait (producer, join, post)
+__device__ __forceinline__ void ts_mbar_wait_relaxed(uint32_t bar, uint32_t parity) { ts_mbar_wait_hint(bar, parity, 20000u); }
 __device__ __forceinline__ void ts_bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -485,6 +473,7 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
     __shared__ __align__(8) unsigned long long bars[4][4]; // [stage][full, joined, compared, empty]
     __shared__ TsStageCtl ctl[4];
     __shared__ float sScale[64], sSigma[64];
+    __shared__ int sBucket[64]; // join warps: slots per candidate-count bucket, then the buckets' bases
     __shared__ int hist2[2][ORBGPU_HISTO_LENGTH + 2];
     __shared__ int ind2[2][4];
 
@@ -514,7 +503,7 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
 
     // per-stage carve-up of the dynamic shared memory
     auto stage_base = [&](int st) { return ts_smem + (size_t)st * P.stage_bytes; };
-    // [A cap][B cap][sCand mf][sMask mf][sBest mf][sList mf][sOvf TS_OVF]
+    // [A cap][B cap][sCand mf x4][sMask mf x4][sBest mf x4][sList mf x2][sPerm mf x2][sOvf TS_OVF x4][sNodeE max_nodes x4]
 
     if (warp == NC + NG + NJ) {
         // ---------------- producer warp: the metadata of the next pair is fetched while the ring is still full, so
@@ -586,6 +575,10 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
             const int32_t *off2 = (const int32_t *)((const uint4 *)(base + cap) + m2);
             const uint32_t *ids2 = (const uint32_t *)(off2 + nn2 + 1);
             uint32_t *sCand = (uint32_t *)(base + 2 * (size_t)cap), *sBest = sCand + 2 * mf;
+            uint16_t *sPerm = (uint16_t *)(sBest + mf) + mf;          // after the (16-bit) slot list
+            uint32_t *sNodeE = (uint32_t *)(sPerm + mf) + TS_OVF;     // after the overflow list: per node (s2 | n2f << 16)
+            if (jt < 64) sBucket[jt] = 0;
+            asm volatile("bar.sync 4, %0;" ::"r"(JT) : "memory");
             for (int a = jt; a < nn1; a += JT) {
                 const uint32_t nid = ids1[a];
                 int lo = 0, hi = nn2;
@@ -598,9 +591,37 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
                     const int s2 = off2[lo];
                     e = (uint32_t)s2 | ((uint32_t)(off2[lo + 1] - s2) << 16);
                 }
-                const int s1 = off1[a], e1 = off1[a + 1];
-                for (int c = s1; c < e1; c++) { sCand[c] = e; sBest[c] = KEY_NONE; }
+                sNodeE[a] = e;
+                atomicAdd(&sBucket[min((int)(e >> 16), 63)], off1[a + 1] - off1[a]);
             }
+            asm volatile("bar.sync 4, %0;" ::"r"(JT) : "memory");
+            // compare order: nodes bucketed by their candidate count (descending), so that the 32 slots a compare warp
+            // takes at a time walk candidate lists of (nearly) the same length.  Counting sort: slots per bucket above,
+            // exclusive scan over the 64 buckets by one warp, then every node reserves its range in its bucket (the order
+            // of equal-count nodes is irrelevant: results do not depend on the compare order).
+            if (jt < 32) {
+                const int v0 = sBucket[63 - 2 * jt], v1 = sBucket[62 - 2 * jt];
+                int incl = v0 + v1;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(FULL_MASK, incl, o);
+                    if (jt >= o) incl += u;
+                }
+                const int excl = incl - v0 - v1;
+                sBucket[63 - 2 * jt] = excl;
+                sBucket[62 - 2 * jt] = excl + v0;
+            }
+            asm volatile("bar.sync 4, %0;" ::"r"(JT) : "memory");
+            for (int a = jt; a < nn1; a += JT) {
+                const uint32_t e = sNodeE[a];
+                const int s1 = off1[a], e1 = off1[a + 1];
+                const int pos = atomicAdd(&sBucket[min((int)(e >> 16), 63)], e1 - s1);
+                for (int c = s1; c < e1; c++) {
+                    sCand[c] = e;
+                    sBest[c] = KEY_NONE;
+                    sPerm[pos + (c - s1)] = (uint16_t)c;
+                }
+            }
+            asm volatile("bar.sync 4, %0;" ::"r"(JT) : "memory"); // sBucket is reused by the next pair
             __syncwarp();
             if (jt == 0) stamp(i, 2);
             if (lane == 0) ts_mbar_arrive(bar_of(st, B_JOINED));
@@ -620,15 +641,19 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
             unsigned char *base = stage_base(st);
             const uint4 *lo1 = (const uint4 *)base, *lo2 = (const uint4 *)(base + cap);
             const uint32_t *sCand = (const uint32_t *)(base + 2 * (size_t)cap);
-            uint32_t *sMask = (uint32_t *)sCand + mf, *sBest = sMask + mf, *sList = sBest + mf, *sOvf = sList + mf;
+            uint32_t *sMask = (uint32_t *)sCand + mf, *sBest = sMask + mf;
+            uint16_t *sList = (uint16_t *)(sBest + mf);
+            const uint16_t *sPerm = sList + mf;
+            uint32_t *sOvf = (uint32_t *)(sPerm + mf);
             const uint4 *aux1 = P.aux + (size_t)k1 * n * 2, *aux2 = P.aux + (size_t)k2 * n * 2;
             // 32-slot chunks are dealt round-robin to the warps, rotated from pair to pair so that the odd chunk does
             // not always land on the same warps
             for (int c0 = ((warp + NC - (i % NC)) % NC) * 32; c0 < m1; c0 += NC * 32) {
-                const int c1 = c0 + lane;
+                int c1 = c0 + lane;
                 uint32_t cand = 0;
                 uint4 a_lo = make_uint4(0, 0, 0, 0);
                 if (c1 < m1) {
+                    c1 = sPerm[c1]; // position in compare order -> CSR slot
                     cand = sCand[c1];
                     a_lo = lo1[c1];
                 }
@@ -651,7 +676,7 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
                     slot0 = __shfl_sync(FULL_MASK, slot0, 0);
                     if (mask) {
                         sMask[c1] = mask;
-                        sList[slot0 + __popc(bal & lanemask_lt())] = (uint32_t)c1;
+                        sList[slot0 + __popc(bal & lanemask_lt())] = (uint16_t)c1;
                         TS_PREFETCH("prefetch.global.L2 [%0];" ::"l"(aux1 + 2 * c1));
                         do {
                             TS_PREFETCH("prefetch.global.L2 [%0];" ::"l"(aux2 + 2 * (s2 + __ffs(mask) - 1)));
@@ -706,7 +731,8 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
         const uint4 *lo1 = (const uint4 *)base, *lo2 = (const uint4 *)(base + cap);
         const uint32_t *sCand = (const uint32_t *)(base + 2 * (size_t)cap), *sMask = sCand + mf;
         uint32_t *best = (uint32_t *)sMask + mf;
-        const uint32_t *sList = best + mf, *sOvf = sList + mf;
+        const uint16_t *sList = (const uint16_t *)(best + mf);
+        const uint32_t *sOvf = (const uint32_t *)(sList + 2 * mf);
         const uint4 *aux1 = P.aux + (size_t)k1 * n * 2, *aux2 = P.aux + (size_t)k2 * n * 2;
         int mine = 0;
         // ---- one listed slot per thread: finish the distances, gates, minimum
@@ -893,9 +919,9 @@ extern "C" int orbgpu_search_for_triangulation_batch_dev(orbgpu_ctx *ctx, const 
     // engine 2: persistent warp-specialised pipeline (monocular sets; bOnlyStereo on a monocular set matches nothing
     // and is left to the per-pair kernel)
     {
-        constexpr int NC = 16, NG = 12, NJ = 2; // compare / post (two groups) / join warps (+ 1 producer warp = 992 threads)
+        constexpr int NC = 16, NG = 12, NJ = 3; // compare / post (two groups) / join warps (+ 1 producer warp = 1024 threads)
         const int cap = (s->max_blob + 127) & ~127;
-        const size_t stage_bytes = (2 * (size_t)cap + (size_t)s->max_free * 16 + (size_t)TS_OVF * 4 + 127) & ~size_t(127);
+        const size_t stage_bytes = (2 * (size_t)cap + (size_t)s->max_free * 16 + (size_t)TS_OVF * 4 + (size_t)s->max_nodes * 4 + 127) & ~size_t(127);
         int n_stages = (int)((227 * 1024 - 2048) / stage_bytes);
         if (n_stages > 4) n_stages = 4;
         const bool can = !s->u_right && !only_stereo && n_stages >= 3 && s->max_free <= 8192; // each post group holds a stage
