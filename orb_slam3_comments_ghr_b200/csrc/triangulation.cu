@@ -356,7 +356,7 @@ triangulation_pairs_kernel(KfSetView s, int n_pairs, int max_free, int max_nodes
 // join table, the per-slot best keys and the candidate list of ONE pair.  Four roles, chained by mbarriers:
 //
 //   producer (1 warp)  waits empty[st]; reads the pair's metadata; ONE cp.async.bulk per keyframe -> full[st] (tx bytes)
-//   join     (NJ warps) waits full[st]; fills the pair's match row with -1; node a of keyframe 1 binary-searched in
+//   join     (NJ warps) waits full[st]; node a of keyframe 1 binary-searched in
 //                      keyframe 2's node list (merge-join :1113-1292); writes sCand[c1] = (first candidate, count)
 //                      for every slot -> joined[st]
 //   compare  (NC warps) waits joined[st]; 32-slot chunks dealt round-robin; lane owns CSR slot c1 of keyframe 1 and
@@ -554,17 +554,6 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
         // ---------------- join warps
         const int jt = (warp - (NC + NG)) * 32 + lane;
         for (int i = 0, st = 0, round = 0; i < n_my; i++) {
-            {   // vMatches12(N, -1) (:1092): ordered before the post warps' match writes through joined[] -> compared[]
-                const int p = blockIdx.x + i * gridDim.x;
-                int32_t *row = P.matches12 + (size_t)p * n;
-                if ((n & 3) == 0) {
-                    int4 *row4 = (int4 *)row;
-                    for (int x = jt; x < (n >> 2); x += JT) row4[x] = make_int4(-1, -1, -1, -1);
-                } else {
-                    for (int x = jt; x < n; x += JT) row[x] = -1;
-                }
-                if (jt == 0) P.nmatches[p] = 0;
-            }
             ts_mbar_wait_relaxed(bar_of(st, B_FULL), round & 1);
             if (jt == 0) stamp(i, 1);
             const TsStageCtl &C = ctl[st];
@@ -717,7 +706,16 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
         if ((i & 1) != grp) continue;
         const int p = blockIdx.x + i * gridDim.x;
         int32_t *row = P.matches12 + (size_t)p * n;
+        // vMatches12(N, -1) (:1092), while the pair is still being compared
+        if ((n & 3) == 0) {
+            int4 *row4 = (int4 *)row;
+            for (int x = gt; x < (n >> 2); x += GT) row4[x] = make_int4(-1, -1, -1, -1);
+        } else {
+            for (int x = gt; x < n; x += GT) row[x] = -1;
+        }
+        if (gt == 0) P.nmatches[p] = 0;
         if (P.check_ori && gt < ORBGPU_HISTO_LENGTH) hist[gt] = 0;
+        bar_post(); // the row is initialised before any thread of the group writes a match into it
         if (gt == 0 && grp == 0) stamp(i, 5);
         ts_mbar_wait_relaxed(bar_of(st, B_COMPARED), round & 1);
         if (gt == 0 && grp == 0) stamp(i, 6);
