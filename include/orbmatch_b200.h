@@ -302,6 +302,18 @@ int orbgpu_bow_score_l1(orbgpu_ctx *ctx, const orbgpu_bowdb *db, int32_t nq_word
 int orbgpu_compute_distinctive_descriptors(orbgpu_ctx *ctx, int32_t n_mp, const int32_t *offsets, const uint8_t *desc,
                                            int32_t *best_idx, int32_t *best_median);
 
+/* ---- 8(f) rank 3: coarse stage of Frame::ComputeStereoMatches (Frame.cc:1139-1216): per left keypoint the right keypoint of
+ * its row band (right keypoints are listed in rows [floor(y-r), ceil(y+r)], r = 2*scaleFactor[octave], :1143-1156) with the
+ * smallest descriptor distance among those within one octave and with uR in [uL - mbf/mb, uL] (:1194-1200); bestDist starts
+ * at TH_HIGH, strict <, first candidate (ascending right index) wins; accepted iff bestDist < (TH_HIGH+TH_LOW)/2 (:1214).
+ * best_idx_r[i] = accepted right keypoint or -1; best_dist[i] = bestDist (TH_HIGH when no candidate).  Rows outside
+ * [0, n_rows) -- undefined behaviour in the reference -- are ignored.  The SAD sub-pixel refinement (:1216-1290) reads the
+ * image pyramids and stays with the caller. */
+int orbgpu_stereo_coarse_match(orbgpu_ctx *ctx, int32_t n_left, const uint8_t *desc_l, const float *kp_xy_l, const int32_t *octave_l,
+                               int32_t n_right, const uint8_t *desc_r, const float *kp_xy_r, const int32_t *octave_r,
+                               const float *scale_factors, int32_t n_levels, int32_t n_rows, float mb, float mbf,
+                               int32_t *best_idx_r, int32_t *best_dist);
+
 /* ---- a10: ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:2341-2383) exposed for testing:
  * histo[30] bin sizes -> ind[3]. Runs on the device. */
 int orbgpu_compute_three_maxima(orbgpu_ctx *ctx, const int32_t *histo, int32_t L, int32_t *ind);

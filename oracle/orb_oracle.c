@@ -487,6 +487,67 @@ void oracle_compute_distinctive_descriptors(int32_t n_mp, const int32_t *offsets
     }
 }
 
+/* Coarse stage of Frame::ComputeStereoMatches (src/Frame.cc:1139-1216).  Frame.cc cannot be compiled here (OpenCV image
+ * pyramids), so this is a restatement only, cross-checked with numpy in tests/test_oracle_golden.py.  Rows outside
+ * [0, n_rows) are undefined behaviour in the reference (vRowIndices[yi]) and are ignored here. */
+void oracle_stereo_coarse_match(int32_t n_left, const uint8_t *desc_l, const float *kp_xy_l, const int32_t *octave_l, int32_t n_right,
+                                const uint8_t *desc_r, const float *kp_xy_r, const int32_t *octave_r, const float *scale_factors,
+                                int32_t n_rows, float mb, float mbf, int32_t *best_idx_r, int32_t *best_dist)
+{
+    const int thOrbDist = (ORBGPU_TH_HIGH + ORBGPU_TH_LOW) / 2; /* :1139 */
+    int32_t *cnt = (int32_t *)calloc((size_t)n_rows + 1, sizeof(int32_t));
+    int32_t *start = (int32_t *)calloc((size_t)n_rows + 2, sizeof(int32_t));
+    for (int pass = 0; pass < 2; pass++) { /* vRowIndices as a CSR: count, then fill in ascending iR (:1147-1156) */
+        int32_t *items = NULL;
+        if (pass == 1) {
+            for (int r = 0; r < n_rows; r++) start[r + 1] = start[r] + cnt[r];
+            items = (int32_t *)malloc(sizeof(int32_t) * (size_t)(start[n_rows] + 1));
+            memset(cnt, 0, sizeof(int32_t) * (size_t)n_rows);
+        }
+        for (int iR = 0; iR < n_right; iR++) {
+            const float kpY = kp_xy_r[2 * iR + 1];
+            const float r = 2.0f * scale_factors[octave_r[iR]];
+            const int maxr = (int)ceilf(kpY + r), minr = (int)floorf(kpY - r);
+            for (int yi = minr; yi <= maxr; yi++) {
+                if (yi < 0 || yi >= n_rows) continue;
+                if (pass == 1) items[start[yi] + cnt[yi]] = iR;
+                cnt[yi]++;
+            }
+        }
+        if (pass == 1) {
+            const float minZ = mb, minD = 0, maxD = mbf / minZ; /* :1160-1163 */
+            for (int iL = 0; iL < n_left; iL++) {
+                best_idx_r[iL] = -1;
+                best_dist[iL] = ORBGPU_TH_HIGH;
+                const int levelL = octave_l[iL];
+                const float vL = kp_xy_l[2 * iL + 1], uL = kp_xy_l[2 * iL];
+                if (vL < 0 || (int)vL >= n_rows) continue;
+                const int row = (int)vL;
+                if (cnt[row] == 0) continue; /* :1180 */
+                const float minU = uL - maxD, maxU = uL - minD;
+                if (maxU < 0) continue; /* :1186 */
+                int bestDist = ORBGPU_TH_HIGH, bestIdxR = 0;
+                for (int iC = 0; iC < cnt[row]; iC++) {
+                    const int iR = items[start[row] + iC];
+                    if (octave_r[iR] < levelL - 1 || octave_r[iR] > levelL + 1) continue; /* :1197 */
+                    const float uR = kp_xy_r[2 * iR];
+                    if (uR >= minU && uR <= maxU) {
+                        const int dist = oracle_descriptor_distance(desc_l + 32 * (size_t)iL, desc_r + 32 * (size_t)iR);
+                        if (dist < bestDist) {
+                            bestDist = dist;
+                            bestIdxR = iR;
+                        }
+                    }
+                }
+                best_dist[iL] = bestDist;
+                if (bestDist < thOrbDist) best_idx_r[iL] = bestIdxR; /* :1214 */
+            }
+            free(items);
+        }
+    }
+    free(cnt); free(start);
+}
+
 /* TemplatedVocabulary.h:1216-1258 */
 void oracle_voc_transform(const orbgpu_voc_host *v, int32_t n, const uint8_t *desc, int levelsup, uint32_t *word_id,
                           uint32_t *node_id, double *weight)

@@ -62,6 +62,11 @@ void oracle_bow_score_l1(const orbgpu_bowdb_host *db, int32_t nq, const uint32_t
 void oracle_compute_distinctive_descriptors(int32_t n_mp, const int32_t *offsets, const uint8_t *desc, int32_t *best_idx,
                                             int32_t *best_median);
 
+/* Frame.cc:1139-1216, coarse stage of ComputeStereoMatches (restatement only: Frame.cc does not compile here) */
+void oracle_stereo_coarse_match(int32_t n_left, const uint8_t *desc_l, const float *kp_xy_l, const int32_t *octave_l, int32_t n_right,
+                                const uint8_t *desc_r, const float *kp_xy_r, const int32_t *octave_r, const float *scale_factors,
+                                int32_t n_rows, float mb, float mbf, int32_t *best_idx_r, int32_t *best_dist);
+
 /* TemplatedVocabulary.h:1216-1258 per feature */
 void oracle_voc_transform(const orbgpu_voc_host *v, int32_t n, const uint8_t *desc, int levelsup, uint32_t *word_id,
                           uint32_t *node_id, double *weight);

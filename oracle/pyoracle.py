@@ -120,6 +120,18 @@ class Oracle:
                                                        float(th_far), float(nnratio), _p(prior, i32p), _p(kp_mp, i32p))
         return int(n), kp_mp
 
+    def stereo_coarse_match(self, left: HostFrame, right: HostFrame, n_rows, mb, mbf):
+        nl = left.n
+        bi = np.full(max(nl, 1), -1, dtype=np.int32)
+        bd = np.full(max(nl, 1), 100, dtype=np.int32)
+        self.lib.oracle_stereo_coarse_match.argtypes = [C.c_int32, u8p, f32p, i32p, C.c_int32, u8p, f32p, i32p, f32p, C.c_int32,
+                                                        C.c_float, C.c_float, i32p, i32p]
+        self.lib.oracle_stereo_coarse_match.restype = None
+        self.lib.oracle_stereo_coarse_match(nl, _p(left.desc, u8p), _p(left.kp_xy, f32p), _p(left.octave, i32p), right.n,
+                                            _p(right.desc, u8p), _p(right.kp_xy, f32p), _p(right.octave, i32p),
+                                            _p(left.scale_factors, f32p), int(n_rows), float(mb), float(mbf), _p(bi, i32p), _p(bd, i32p))
+        return bi[:nl], bd[:nl]
+
     def compute_distinctive_descriptors(self, offsets, desc):
         off = as_i32(offsets)
         d = as_u8(desc).reshape(-1, 32)

@@ -181,6 +181,20 @@ class Context:
     def upload_kfset(self, s: HostKfSet) -> "DeviceKfSet":
         return DeviceKfSet(self, s)
 
+    # coarse stage of Frame::ComputeStereoMatches (Frame.cc:1139-1216) -> (best right keypoint or -1, bestDist) per left keypoint
+    def stereo_coarse_match(self, left: HostFrame, right: HostFrame, n_rows: int, mb: float, mbf: float):
+        nl, nr = left.n, right.n
+        bi = np.full(max(nl, 1), -1, dtype=np.int32)
+        bd = np.full(max(nl, 1), TH_HIGH, dtype=np.int32)
+        L = load_library()
+        L.orbgpu_stereo_coarse_match.argtypes = [C.c_void_p, C.c_int32, u8p, f32p, i32p, C.c_int32, u8p, f32p, i32p, f32p, C.c_int32,
+                                                 C.c_int32, C.c_float, C.c_float, i32p, i32p]
+        _check(L.orbgpu_stereo_coarse_match(self._h, nl, _p(left.desc, u8p), _p(left.kp_xy, f32p), _p(left.octave, i32p), nr,
+                                            _p(right.desc, u8p), _p(right.kp_xy, f32p), _p(right.octave, i32p),
+                                            _p(left.scale_factors, f32p), left.scale_factors.shape[0], int(n_rows), float(mb), float(mbf),
+                                            _p(bi, i32p), _p(bd, i32p)))
+        return bi[:nl], bd[:nl]
+
     # MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:444-535) for a batch of map points -> (best_idx, best_median)
     def compute_distinctive_descriptors(self, offsets, desc):
         off = as_i32(offsets)

@@ -218,6 +218,29 @@ def make_projected_case(seed: int, n_kp: int = 2000, n_pts: int = 3000, th: floa
     return frame, pts, kp_locked
 
 
+def make_stereo_case(seed: int, n: int = 2000, planted_frac: float = 0.7):
+    """A rectified stereo pair: right keypoints are left keypoints shifted by a disparity in [0, mbf/mb] on (nearly) the same
+    row, with bit-flipped descriptors and octave within +-1; plus clutter, keypoints on the image border rows and ties."""
+    rng = np.random.default_rng(seed)
+    left, right = make_frame(rng, n), make_frame(rng, n)
+    mb, mbf = 0.11, 40.0
+    n_pl = int(planted_frac * n)
+    src = rng.permutation(n)[:n_pl]
+    dst = rng.permutation(n)[:n_pl]
+    right.desc[dst] = planted_copies(rng, left.desc[src])
+    disp = rng.uniform(-5, mbf / mb + 20, n_pl)  # some outside [0, maxD]
+    right.kp_xy[dst, 0] = quantise(np.clip(left.kp_xy[src, 0] - disp, 0, IMG_W - 0.25))
+    right.kp_xy[dst, 1] = quantise(np.clip(left.kp_xy[src, 1] + rng.normal(0, 1.5, n_pl), 0, IMG_H - 0.25))
+    right.octave[dst] = np.clip(left.octave[src] + rng.integers(-2, 3, n_pl), 0, 7)
+    k = min(8, n)
+    left.kp_xy[:k, 1] = np.array([0.0, 0.25, 479.75, 479.0, 1.0, 478.5, 0.75, 2.0], dtype=np.float32)[:k]  # border rows
+    right.desc[dst[:20]] = left.desc[src[:20]]  # exact copies: distance-0 ties with duplicates below
+    right.desc[(dst[:20] + 1) % n] = left.desc[src[:20]]
+    right.kp_xy[(dst[:20] + 1) % n] = right.kp_xy[dst[:20]]
+    right.octave[(dst[:20] + 1) % n] = right.octave[dst[:20]]
+    return left, right, IMG_H, mb, mbf
+
+
 def make_distinctive_case(seed: int, n_mp: int = 3000, max_obs: int = 40):
     """Observation descriptors of n_mp map points (CSR): noisy copies of a per-point prototype, a few outliers, some points with
     1-2 observations (median index 0), a few empty lists, duplicates (distance 0 ties) and one long list."""

@@ -398,3 +398,16 @@ def test_compute_distinctive_descriptors(ctx, oracle, seed, n_mp, max_obs):
     ei, em = oracle.compute_distinctive_descriptors(offs, desc)
     assert np.array_equal(gi, ei) and np.array_equal(gm, em)
     assert ctx.last_comparisons == oracle.comparisons()
+
+
+@pytest.mark.parametrize("seed,n", [(161, 2000), (162, 333), (163, 1)])
+def test_stereo_coarse_match(ctx, oracle, seed, n):
+    """8(f) rank 3: coarse stage of Frame::ComputeStereoMatches"""
+    left, right, n_rows, mb, mbf = synth.make_stereo_case(seed, n=n)
+    gi, gd = ctx.stereo_coarse_match(left, right, n_rows, mb, mbf)
+    oracle.reset_comparisons()
+    ei, ed = oracle.stereo_coarse_match(left, right, n_rows, mb, mbf)
+    assert np.array_equal(gi, ei) and np.array_equal(gd, ed)
+    assert ctx.last_comparisons == oracle.comparisons()
+    if n >= 333:
+        assert (gi >= 0).sum() > n // 10

@@ -127,3 +127,27 @@ def test_compute_distinctive_descriptors_vs_numpy(oracle):
         dist = (b[:, None, :] != b[None, :, :]).sum(axis=2)
         med = np.sort(dist, axis=1)[:, int(0.5 * (e - s - 1))]
         assert bi[p] == int(np.argmin(med)) and bm[p] == int(med.min())
+
+
+def test_stereo_coarse_match_vs_numpy(oracle):
+    """8(f) rank 3: Frame.cc does not compile here; the restatement of Frame.cc:1139-1216 is cross-checked with an independent
+    numpy evaluation (row bands, octave and disparity filters, first minimum, acceptance threshold)."""
+    left, right, n_rows, mb, mbf = synth.make_stereo_case(151, n=600)
+    bi, bd = oracle.stereo_coarse_match(left, right, n_rows, mb, mbf)
+    r = np.float32(2.0) * left.scale_factors[right.octave]
+    maxr = np.ceil(right.kp_xy[:, 1] + r).astype(int)
+    minr = np.floor(right.kp_xy[:, 1] - r).astype(int)
+    max_d = np.float32(mbf) / np.float32(mb)
+    dist = np.unpackbits(left.desc[:, None, :] ^ right.desc[None, :, :], axis=2).sum(axis=2)
+    n_acc = 0
+    for i in range(left.n):
+        row = int(left.kp_xy[i, 1])
+        ok = (minr <= row) & (row <= maxr) & (np.abs(right.octave - left.octave[i]) <= 1)
+        ok &= (right.kp_xy[:, 0] >= left.kp_xy[i, 0] - max_d) & (right.kp_xy[:, 0] <= left.kp_xy[i, 0])
+        d = np.where(ok, dist[i], 1000)
+        j = int(np.argmin(d))  # first minimum == ascending right index
+        best = int(d[j]) if d[j] < 100 else 100
+        assert bd[i] == best
+        assert bi[i] == (j if best < 75 else -1)
+        n_acc += bi[i] >= 0
+    assert n_acc > 100
