@@ -77,6 +77,7 @@ extern "C" int orbgpu_bowdb_upload(orbgpu_ctx *ctx, const orbgpu_bowdb_host *h, 
     for (int i = 0; i < h->n_kf; i++) ARG_TRY(h->offsets[i] <= h->offsets[i + 1]);
     CU_TRY(cudaSetDevice(ctx->device));
     orbgpu_bowdb *d = new orbgpu_bowdb();
+    OwnedHandle<orbgpu_bowdb, orbgpu_bowdb_destroy> owner(d);
     d->device = ctx->device; d->n_kf = h->n_kf; d->total = total;
     CU_TRY(cudaMalloc((void **)&d->offsets, (size_t)(h->n_kf + 1) * 4));
     CU_TRY(cudaMalloc((void **)&d->words, (size_t)(total > 0 ? total : 1) * 4));
@@ -87,7 +88,7 @@ extern "C" int orbgpu_bowdb_upload(orbgpu_ctx *ctx, const orbgpu_bowdb_host *h, 
         CU_TRY(cudaMemcpyAsync(d->values, h->values, (size_t)total * 8, cudaMemcpyHostToDevice, ctx->stream));
     }
     CU_TRY(cudaStreamSynchronize(ctx->stream));
-    *out = d;
+    *out = owner.release();
     return ORBGPU_OK;
 }
 

@@ -191,6 +191,7 @@ extern "C" int orbgpu_frame_upload(orbgpu_ctx *ctx, const orbgpu_frame_host *h, 
     ARG_TRY(h->n == 0 || (h->desc && h->kp_xy && h->octave && h->angle));
     ARG_TRY(h->n_levels > 0 && h->n_levels <= 64 && h->scale_factors && h->level_sigma2);
     ARG_TRY(h->fv_n_nodes >= 0 && h->fv_n_nodes <= h->n);
+    for (int i = 0; i < h->n; i++) ARG_TRY(h->octave[i] >= 0 && h->octave[i] < h->n_levels); // indexes the scale tables
     CU_TRY(cudaSetDevice(ctx->device));
     const int n = h->n, nl = h->n_levels, ncell = h->grid_cols * h->grid_rows;
     const size_t N = (size_t)(n > 0 ? n : 1);
@@ -198,6 +199,7 @@ extern "C" int orbgpu_frame_upload(orbgpu_ctx *ctx, const orbgpu_frame_host *h, 
     ARG_TRY(fv_total >= 0 && fv_total <= n);
 
     orbgpu_frame *f = new orbgpu_frame();
+    OwnedHandle<orbgpu_frame, orbgpu_frame_destroy> owner(f);
     f->device = ctx->device;
     f->n = n;
     f->n_levels = nl;
@@ -229,7 +231,7 @@ extern "C" int orbgpu_frame_upload(orbgpu_ctx *ctx, const orbgpu_frame_host *h, 
 
     // pack the host arrays into pinned staging in slab layout -> ONE H2D copy
     int rc = stage_reserve(ctx, upload_bytes);
-    if (rc) { orbgpu_frame_destroy(f); return rc; }
+    if (rc) return rc; // the owner guard releases the frame
     char *H = ctx->h_stage;
     if (n > 0) {
         memcpy(H + o_desc, h->desc, (size_t)n * 32);
@@ -256,7 +258,7 @@ extern "C" int orbgpu_frame_upload(orbgpu_ctx *ctx, const orbgpu_frame_host *h, 
     LAUNCH_COUNT(ctx);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(ctx->stream)); // staging buffer is reusable after this
-    *out = f;
+    *out = owner.release();
     return ORBGPU_OK;
 }
 

@@ -20,6 +20,18 @@ int orbgpu_fail(int code, const std::string &msg);
             return orbgpu_fail(ORBGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
     } while (0)
 
+// owns a freshly created handle until the creating entry point succeeds: an early `return` (CU_TRY / ARG_TRY) releases
+// whatever was allocated so far through the handle's own destroy function
+template <class T, void (*Destroy)(T *)>
+struct OwnedHandle {
+    T *p;
+    explicit OwnedHandle(T *q) : p(q) {}
+    ~OwnedHandle() { if (p) Destroy(p); }
+    OwnedHandle(const OwnedHandle &) = delete;
+    OwnedHandle &operator=(const OwnedHandle &) = delete;
+    T *release() { T *q = p; p = nullptr; return q; }
+};
+
 #define ARG_TRY(cond)                                                                                       \
     do {                                                                                                    \
         if (!(cond)) return orbgpu_fail(ORBGPU_ERR_INVALID, std::string("invalid argument: ") + #cond);     \

@@ -288,12 +288,13 @@ extern "C" int orbgpu_db_upload(orbgpu_ctx *ctx, int64_t nd, const uint8_t *db_d
     d->nd = nd;
     d->capacity = nd;
     d->owned = true;
+    OwnedHandle<orbgpu_db, orbgpu_db_destroy> owner(d);
     void *p = nullptr;
     CU_TRY(cudaMalloc(&p, std::max<int64_t>(nd, 1) * 32));
+    d->desc = (const uint4 *)p;
     if (nd > 0) CU_TRY(cudaMemcpyAsync(p, db_desc, nd * 32, cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(cudaStreamSynchronize(ctx->stream));
-    d->desc = (const uint4 *)p;
-    *out = d;
+    *out = owner.release();
     return ORBGPU_OK;
 }
 

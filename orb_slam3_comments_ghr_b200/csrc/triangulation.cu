@@ -837,8 +837,11 @@ extern "C" int orbgpu_kfset_upload(orbgpu_ctx *ctx, const orbgpu_kfset_host *h, 
     ARG_TRY(h->n_kf > 0 && h->n_feat > 0 && h->n_feat <= 8192 && h->n_feat < (1 << 20));
     ARG_TRY(h->desc && h->kp_xy && h->octave && h->angle && h->has_mp && h->node_id && h->scale_factors && h->level_sigma2);
     ARG_TRY(h->n_levels > 0 && h->n_levels <= 64);
+    for (size_t i = 0, T0 = (size_t)h->n_kf * h->n_feat; i < T0; i++)
+        ARG_TRY(h->octave[i] >= 0 && h->octave[i] < h->n_levels); // indexes the scale tables in the gates
     CU_TRY(cudaSetDevice(ctx->device));
     orbgpu_kfset *s = new orbgpu_kfset();
+    OwnedHandle<orbgpu_kfset, orbgpu_kfset_destroy> owner(s);
     s->device = ctx->device;
     s->n_kf = h->n_kf; s->n_feat = h->n_feat; s->n_levels = h->n_levels;
     const size_t T = (size_t)h->n_kf * h->n_feat;
@@ -885,7 +888,7 @@ extern "C" int orbgpu_kfset_upload(orbgpu_ctx *ctx, const orbgpu_kfset_host *h, 
     s->max_free = ((mx[0] > 0 ? mx[0] : 1) + 3) & ~3; // multiple of 4: keeps the int4 node table 16-byte aligned
     s->max_nodes = mx[1] > 0 ? mx[1] : 1;
     s->max_blob = mx[2] > 0 ? mx[2] : 16;
-    *out = s;
+    *out = owner.release();
     return ORBGPU_OK;
 }
 

@@ -224,6 +224,7 @@ extern "C" int orbgpu_voc_upload(orbgpu_ctx *ctx, const orbgpu_voc_host *h, orbg
     for (int i = 0; i < nn; i++) ARG_TRY(h->child_offsets[i + 1] >= h->child_offsets[i] && h->child_offsets[i + 1] - h->child_offsets[i] < (1 << 20));
     for (int c = 0; c < nc; c++) ARG_TRY(h->child_ids[c] > 0 && h->child_ids[c] < (uint32_t)nn);
     orbgpu_voc *v = new orbgpu_voc();
+    OwnedHandle<orbgpu_voc, orbgpu_voc_destroy> owner(v);
     v->device = ctx->device;
     v->k = h->k; v->L = h->L; v->n_nodes = nn;
     CU_TRY(cudaMalloc(&v->node_desc, (size_t)nn * 32));
@@ -237,7 +238,7 @@ extern "C" int orbgpu_voc_upload(orbgpu_ctx *ctx, const orbgpu_voc_host *h, orbg
     CU_TRY(cudaMemcpyAsync(v->weight, h->weight, (size_t)nn * 8, cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(cudaMemcpyAsync(v->word_id, h->word_id, (size_t)nn * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(cudaStreamSynchronize(ctx->stream));
-    *out = v;
+    *out = owner.release();
     return ORBGPU_OK;
 }
 
