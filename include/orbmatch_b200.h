@@ -253,6 +253,14 @@ int orbgpu_search_for_triangulation_batch_dev(orbgpu_ctx *ctx, const orbgpu_kfse
                                               int32_t only_stereo, int32_t coarse, int32_t check_ori, int32_t *matches12_dev,
                                               int32_t *nmatches_dev);
 
+/* Same search with the result in the reference's vMatchedPairs form (ORBmatcher.cc:1317-1325): for pair p the matches are
+ * pairs[2*j], pairs[2*j+1] = (idx1, idx2), j in [pair_offsets[p], pair_offsets[p+1]), ascending idx1.  pair_offsets has
+ * n_pairs+1 entries; cap = capacity of pairs in (idx1, idx2) entries; *total = entries produced (ORBGPU_ERR_OVERFLOW and the
+ * first cap entries when it exceeds cap).  Only the pairs cross the bus: about 1/20 of the dense rows. */
+int orbgpu_search_for_triangulation_batch_pairs(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs, const int32_t *kf1,
+                                                const int32_t *kf2, const float *ep, const float *f12, int32_t only_stereo,
+                                                int32_t coarse, int32_t check_ori, int32_t *pair_offsets, int32_t *pairs, int64_t cap,
+                                                int64_t *total);
 /* selects the batched-triangulation kernel: 0 = auto, 1 = one CTA per pair (cp.async staging; the only one
  * that handles mvuRight / bOnlyStereo), 2 = persistent CTAs, producer warp + double-buffered bulk copies
  * (cp.async.bulk + mbarrier) of per-keyframe stream blobs (what auto resolves to for monocular sets). */

@@ -806,6 +806,57 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
     }
 }
 
+// ---- compact form of the result: the reference's vMatchedPairs (:1317-1325), pairs (idx1, idx2) in ascending idx1
+__global__ void tri_offsets_kernel(int n_pairs, const int32_t *__restrict__ nmatches, int32_t *__restrict__ offsets)
+{
+    // exclusive scan by one block of 1024 threads over contiguous chunks
+    __shared__ int warp_sum[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int per = (n_pairs + 1023) / 1024, lo = min(n_pairs, t * per), hi = min(n_pairs, lo + per);
+    int mine = 0;
+    for (int i = lo; i < hi; i++) mine += nmatches[i];
+    int incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(FULL_MASK, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warp_sum[lane];
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(FULL_MASK, w, o);
+            if (lane >= o) w += u;
+        }
+        warp_sum[lane] = w;
+    }
+    __syncthreads();
+    int run = (warp ? warp_sum[warp - 1] : 0) + incl - mine;
+    for (int i = lo; i < hi; i++) {
+        offsets[i] = run;
+        run += nmatches[i];
+    }
+    if (t == 1023) offsets[n_pairs] = warp_sum[31];
+}
+
+__global__ void tri_compact_kernel(int n_pairs, int n_feat, const int32_t *__restrict__ matches12, const int32_t *__restrict__ offsets,
+                                   int2 *__restrict__ pairs, long long cap)
+{
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; // one warp per key-frame pair
+    if (p >= n_pairs) return;
+    const int lane = lane_id();
+    const int32_t *row = matches12 + (size_t)p * n_feat;
+    long long out = offsets[p];
+    for (int b = 0; b < n_feat; b += 32) {
+        const int i = b + lane;
+        const int m = i < n_feat ? row[i] : -1;
+        const unsigned bal = __ballot_sync(FULL_MASK, m >= 0);
+        const long long pos = out + __popc(bal & lanemask_lt());
+        if (m >= 0 && pos < cap) pairs[pos] = make_int2(i, m);
+        out += __popc(bal);
+    }
+}
+
 KfSetView kfset_view(const orbgpu_kfset *s)
 {
     KfSetView v;
@@ -996,4 +1047,59 @@ extern "C" int orbgpu_search_for_triangulation_batch(orbgpu_ctx *ctx, const orbg
     CU_TRY(cudaMemcpyAsync(matches12, d_m, P * s->n_feat * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(cudaMemcpyAsync(nmatches, d_nm, P * 4, cudaMemcpyDeviceToHost, ctx->stream));
     return ctx_fetch_comparisons(ctx);
+}
+
+// same search, result in the reference's vMatchedPairs form: pairs[pair_offsets[p] .. pair_offsets[p+1]) = (idx1, idx2) of pair p,
+// ascending idx1.  The dense rows stay on the device; only the pairs travel back (about 1/20 of the bytes).
+extern "C" int orbgpu_search_for_triangulation_batch_pairs(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs, const int32_t *kf1,
+                                                           const int32_t *kf2, const float *ep, const float *f12, int32_t only_stereo,
+                                                           int32_t coarse, int32_t check_ori, int32_t *pair_offsets, int32_t *pairs,
+                                                           int64_t cap, int64_t *total)
+{
+    ARG_TRY(ctx && s && n_pairs >= 0 && pair_offsets && total && cap >= 0 && (cap == 0 || pairs));
+    ARG_TRY(n_pairs == 0 || (kf1 && kf2 && ep && f12));
+    int rc = ctx_begin(ctx);
+    if (rc) return rc;
+    *total = 0;
+    pair_offsets[0] = 0;
+    if (n_pairs == 0) return ORBGPU_OK;
+    for (int p = 0; p < n_pairs; p++) ARG_TRY(kf1[p] >= 0 && kf1[p] < s->n_kf && kf2[p] >= 0 && kf2[p] < s->n_kf);
+    const size_t P = (size_t)n_pairs;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+    const size_t o_k1 = take(P * 4), o_k2 = take(P * 4), o_ep = take(P * 8), o_f = take(P * 36);
+    const size_t up = off;
+    rc = stage_reserve(ctx, up);
+    if (rc) return rc;
+    rc = arena_reserve(ctx, up + align256(P * s->n_feat * 4) + 2 * align256((P + 1) * 4) + align256((size_t)cap * 8 + 8));
+    if (rc) return rc;
+    char *H = ctx->h_stage;
+    memcpy(H + o_k1, kf1, P * 4);
+    memcpy(H + o_k2, kf2, P * 4);
+    memcpy(H + o_ep, ep, P * 8);
+    memcpy(H + o_f, f12, P * 36);
+    char *D = (char *)arena_take(ctx, up);
+    int32_t *d_m = (int32_t *)arena_take(ctx, P * s->n_feat * 4), *d_nm = (int32_t *)arena_take(ctx, (P + 1) * 4),
+            *d_off = (int32_t *)arena_take(ctx, (P + 1) * 4);
+    int2 *d_pairs = (int2 *)arena_take(ctx, (size_t)cap * 8 + 8);
+    if (!D || !d_m || !d_nm || !d_off || !d_pairs) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
+    CU_TRY(cudaMemcpyAsync(D, H, up, cudaMemcpyHostToDevice, ctx->stream));
+    rc = orbgpu_search_for_triangulation_batch_dev(ctx, s, n_pairs, (const int32_t *)(D + o_k1), (const int32_t *)(D + o_k2),
+                                                   (const float *)(D + o_ep), (const float *)(D + o_f), only_stereo, coarse, check_ori,
+                                                   d_m, d_nm);
+    if (rc) return rc;
+    tri_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(n_pairs, d_nm, d_off);
+    tri_compact_kernel<<<(unsigned)((P * 32 + 255) / 256), 256, 0, ctx->stream>>>(n_pairs, s->n_feat, d_m, d_off, d_pairs, (long long)cap);
+    ctx->launches += 2;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(pair_offsets, d_off, (P + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = ctx_fetch_comparisons(ctx); // synchronises: the total is known
+    if (rc) return rc;
+    *total = pair_offsets[n_pairs];
+    const int64_t n_copy = *total < cap ? *total : cap;
+    if (n_copy > 0) {
+        CU_TRY(cudaMemcpyAsync(pairs, d_pairs, (size_t)n_copy * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return *total <= cap ? ORBGPU_OK : orbgpu_fail(ORBGPU_ERR_OVERFLOW, "pairs capacity too small: see *total");
 }

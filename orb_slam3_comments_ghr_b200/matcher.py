@@ -486,6 +486,24 @@ class ORBmatcher:
                                                                     int(self.mbCheckOrientation), _p(m, i32p), _p(nm, i32p)))
         return nm, m
 
+    # same search, vMatchedPairs form: (pair_offsets[P+1], pairs[total, 2]) -- only the matched pairs cross the bus
+    def SearchForTriangulationPairs(self, kfs: DeviceKfSet, kf1, kf2, ep, f12, bOnlyStereo: bool = False, bCoarse: bool = False,
+                                    out=None):
+        kf1, kf2 = as_i32(kf1), as_i32(kf2)
+        ep, f12 = as_f32(ep), as_f32(f12)
+        P = kf1.shape[0]
+        if out is None:
+            out = (np.empty(P + 1, dtype=np.int32), np.empty((P * kfs.n_feat, 2), dtype=np.int32))
+        offs, pairs = out
+        total = C.c_int64(0)
+        L = load_library()
+        L.orbgpu_search_for_triangulation_batch_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, i32p, i32p, f32p, f32p, C.c_int32,
+                                                                  C.c_int32, C.c_int32, i32p, i32p, C.c_int64, C.POINTER(C.c_int64)]
+        _check(L.orbgpu_search_for_triangulation_batch_pairs(self.ctx.handle, kfs.handle, P, _p(kf1, i32p), _p(kf2, i32p), _p(ep, f32p),
+                                                             _p(f12, f32p), int(bOnlyStereo), int(bCoarse), int(self.mbCheckOrientation),
+                                                             _p(offs, i32p), _p(pairs, i32p), pairs.shape[0], C.byref(total)))
+        return offs, pairs[:total.value]
+
     def SearchForTriangulation_dev(self, kfs: DeviceKfSet, n_pairs, kf1_ptr, kf2_ptr, ep_ptr, f12_ptr, matches_ptr, nmatches_ptr,
                                    bOnlyStereo=False, bCoarse=False):
         vp = C.c_void_p

@@ -411,3 +411,19 @@ def test_stereo_coarse_match(ctx, oracle, seed, n):
     assert ctx.last_comparisons == oracle.comparisons()
     if n >= 333:
         assert (gi >= 0).sum() > n // 10
+
+
+@pytest.mark.parametrize("seed,n_pairs,n_feat,ori", [(171, 37, 1500, 0), (172, 300, 600, 1), (173, 1, 64, 0)])
+def test_triangulation_pairs_form(ctx, M, seed, n_pairs, n_feat, ori):
+    """the vMatchedPairs form equals the dense rows: (idx1, idx2) ascending in idx1, per pair (ORBmatcher.cc:1317-1325)"""
+    tc = synth.fill_geometry(synth.make_triangulation_case(seed, n_pairs=n_pairs, n_feat=n_feat))
+    ks = ctx.upload_kfset(tc.kfs)
+    mm = M.ORBmatcher(0.6, bool(ori), ctx)
+    nm, m = mm.SearchForTriangulation(ks, tc.kf1, tc.kf2, tc.ep, tc.f12)
+    offs, pairs = mm.SearchForTriangulationPairs(ks, tc.kf1, tc.kf2, tc.ep, tc.f12)
+    assert np.array_equal(np.diff(offs), nm) and offs[0] == 0 and offs[-1] == pairs.shape[0]
+    p, i1 = np.nonzero(m >= 0)
+    assert np.array_equal(pairs[:, 0], i1) and np.array_equal(pairs[:, 1], m[p, i1])
+    if pairs.shape[0] > 0:
+      with pytest.raises(M.OrbGpuError):  # capacity too small is reported, not truncated silently
+        mm.SearchForTriangulationPairs(ks, tc.kf1, tc.kf2, tc.ep, tc.f12, out=(np.empty(n_pairs + 1, np.int32), np.empty((max(pairs.shape[0] - 1, 0), 2), np.int32)))
