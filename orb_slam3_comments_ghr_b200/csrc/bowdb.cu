@@ -115,7 +115,7 @@ extern "C" int orbgpu_bow_score_l1(orbgpu_ctx *ctx, const orbgpu_bowdb *db, int3
         CU_TRY(cudaMemcpyAsync(d_qv, q_values, (size_t)nq_words * 8, cudaMemcpyHostToDevice, ctx->stream));
         CU_TRY(cudaMemcpyAsync(d_qw, q_words, (size_t)nq_words * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
-    if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(bow_score_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 32 * 1024) CU_TRY(cudaFuncSetAttribute(bow_score_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bow_score_l1_kernel<<<(db->n_kf + BOW_THREADS - 1) / BOW_THREADS, BOW_THREADS, smem, ctx->stream>>>(
         db->n_kf, db->offsets, db->words, db->values, nq_words, d_qw, d_qv, d_cm, d_sc);
     LAUNCH_COUNT(ctx);

@@ -1004,7 +1004,8 @@ extern "C" int orbgpu_search_for_triangulation_batch_dev(orbgpu_ctx *ctx, const 
     const size_t smem = (size_t)s->max_free * (64 + 4 + 1) + (size_t)s->max_nodes * 16 + 64;
     if (smem > 227 * 1024) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "keyframes too large for the shared-memory staging");
     auto kern = s->u_right ? triangulation_pairs_kernel<true> : triangulation_pairs_kernel<false>;
-    if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // always opt in: the kernel also has ~8.5 KB of static shared memory, so dynamic sizes just under 48 KB need it too
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<n_pairs, TRI_THREADS, smem, ctx->stream>>>(kfset_view(s), n_pairs, s->max_free, s->max_nodes, kf1_dev, kf2_dev, ep_dev, f12_dev,
                                                      only_stereo, coarse, check_ori, matches12_dev, nmatches_dev, ctx->d_counters);
     LAUNCH_COUNT(ctx);

@@ -427,3 +427,55 @@ def test_triangulation_pairs_form(ctx, M, seed, n_pairs, n_feat, ori):
     if pairs.shape[0] > 0:
       with pytest.raises(M.OrbGpuError):  # capacity too small is reported, not truncated silently
         mm.SearchForTriangulationPairs(ks, tc.kf1, tc.kf2, tc.ep, tc.f12, out=(np.empty(n_pairs + 1, np.int32), np.empty((max(pairs.shape[0] - 1, 0), 2), np.int32)))
+
+
+@pytest.mark.parametrize("seed,only_stereo,coarse,ori", [(521, 0, 0, 0), (522, 1, 0, 1), (523, 1, 1, 0), (524, 0, 0, 1)])
+def test_triangulation_stereo(ctx, M, oracle, seed, only_stereo, coarse, ori):
+    """key frames with mvuRight: served by the per-pair kernel (engine 1; auto must route there), engine 2 refuses"""
+    from helpers import add_stereo
+    tc = add_stereo(synth.fill_geometry(synth.make_triangulation_case(seed, n_pairs=40, n_feat=1200)), seed)
+    ks = ctx.upload_kfset(tc.kfs)
+    mm = M.ORBmatcher(0.6, bool(ori), ctx)
+    oracle.reset_comparisons()
+    enm, em = oracle.search_for_triangulation_batch(tc.kfs, tc.kf1, tc.kf2, tc.ep, tc.f12, only_stereo, coarse, ori, n_threads=os.cpu_count() or 1)
+    for eng in (0, 1):
+        ctx.set_triangulation_engine(eng)
+        nm, m = mm.SearchForTriangulation(ks, tc.kf1, tc.kf2, tc.ep, tc.f12, bool(only_stereo), bool(coarse))
+        assert np.array_equal(nm, enm) and np.array_equal(m, em)
+        assert ctx.last_comparisons == oracle.comparisons()
+    ctx.set_triangulation_engine(2)
+    with pytest.raises(M.OrbGpuError):
+        mm.SearchForTriangulation(ks, tc.kf1, tc.kf2, tc.ep, tc.f12, bool(only_stereo), bool(coarse))
+    ctx.set_triangulation_engine(0)
+    # bOnlyStereo on a monocular set matches nothing (every feature fails :1136 / :1170)
+    tm = synth.fill_geometry(synth.make_triangulation_case(seed, n_pairs=5, n_feat=600))
+    nm, m = mm.SearchForTriangulation(ctx.upload_kfset(tm.kfs), tm.kf1, tm.kf2, tm.ep, tm.f12, True, False)
+    assert not nm.any() and (m == -1).all()
+
+
+@pytest.mark.parametrize("seed,th", [(321, 1.0), (322, 3.0)])
+def test_projection_stereo(ctx, M, oracle, seed, th):
+    from helpers import stereo_projection_case
+    c = stereo_projection_case(seed, th)
+    got = M.ORBmatcher(c.nnratio, True, ctx).SearchByProjection(ctx.upload_frame(c.frame), c.mps, th, False, 50.0, c.kp_prior_obs, c.kp_mp)
+    oracle.reset_comparisons()
+    exp = oracle.search_by_projection_local(c.frame, c.mps, th, 0, 50.0, c.nnratio, c.kp_prior_obs, c.kp_mp)
+    assert got[0] == exp[0] and np.array_equal(got[1], exp[1])
+    assert ctx.last_comparisons == oracle.comparisons()
+
+
+def test_large_frames_shared_memory_opt_in(ctx, M, oracle):
+    """frames with more than 12 k keypoints: the lock tables of the ordered passes exceed the 48 KB default shared memory"""
+    frame, pts, kl = synth.make_projected_case(181, n_kp=14000, n_pts=4000, th=7.0)
+    got = M.ORBmatcher(0.9, True, ctx).SearchProjected(ctx.upload_frame(frame), pts, 100.0, True, kl)
+    exp = oracle.search_projected(frame, pts, 100.0, 1, kl, check_ori=1)
+    assert got[0] == exp[0] and all(np.array_equal(a, b) for a, b in zip(got[1:], exp[1:]))
+    c = synth.make_projection_case(182, n_kp=13000, n_mp=6000, th=3.0)
+    g2 = M.ORBmatcher(c.nnratio, True, ctx).SearchByProjection(ctx.upload_frame(c.frame), c.mps, 3.0, False, 50.0, c.kp_prior_obs, c.kp_mp)
+    e2 = oracle.search_by_projection_local(c.frame, c.mps, 3.0, 0, 50.0, c.nnratio, c.kp_prior_obs, c.kp_mp)
+    assert g2[0] == e2[0] and np.array_equal(g2[1], e2[1])
+    ci = synth.make_init_case(183, n=6000)
+    f1, f2 = ctx.upload_frame(ci.f1), ctx.upload_frame(ci.f2)
+    n, m12, prev = M.ORBmatcher(ci.nnratio, True, ctx).SearchForInitialization(f1, f2, ci.prev_matched, ci.window_size)
+    en, em, ep = oracle.search_for_initialization(ci.f1, ci.f2, ci.prev_matched, ci.window_size, ci.nnratio, 1)
+    assert n == en and np.array_equal(m12, em) and np.array_equal(prev, ep)

@@ -3,7 +3,7 @@ ORBmatcher.cc / DBoW2 (compiled unmodified) on fresh seeds and on the edge cases
 import numpy as np
 import pytest
 
-from helpers import attach_featvec, golden_voc
+from helpers import add_stereo, attach_featvec, golden_voc, stereo_projection_case
 from orb_slam3_comments_ghr_b200 import synth
 from orb_slam3_comments_ghr_b200._abi import HostFrame, HostMapPoints
 
@@ -181,3 +181,20 @@ def test_bow_score_l1(oracle, reference, seed):
     ec, es = reference.bow_score_l1(db, qw[:0], qv[:0])  # empty query
     gc, gs = oracle.bow_score_l1(db, qw[:0], qv[:0])
     assert np.array_equal(gc, ec) and np.array_equal(gs.view(np.uint64), es.view(np.uint64))
+
+
+@pytest.mark.parametrize("seed,only_stereo,coarse,ori", [(511, 0, 0, 0), (512, 1, 0, 1), (513, 1, 1, 0), (514, 0, 0, 1)])
+def test_triangulation_stereo(oracle, reference, seed, only_stereo, coarse, ori):
+    """mvuRight >= 0 features: bOnlyStereo filter (:1134-1138, :1168-1172) and the epipole gate only for mono-mono pairs (:1191)"""
+    tc = add_stereo(synth.fill_geometry(synth.make_triangulation_case(seed, n_pairs=6, n_feat=1500)), seed)
+    a = oracle.search_for_triangulation_batch(tc.kfs, tc.kf1, tc.kf2, tc.ep, tc.f12, only_stereo, coarse, ori, n_threads=2)
+    b = reference.search_for_triangulation_batch(tc.kfs, tc.kf1, tc.kf2, tc.T1w, tc.T2w, tc.K, only_stereo, coarse, ori, 0.6, n_threads=2)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[0].sum() > 50
+
+
+@pytest.mark.parametrize("seed,th", [(311, 1.0), (312, 3.0)])
+def test_projection_stereo(oracle, reference, seed, th):
+    c = stereo_projection_case(seed, th)
+    a = oracle.search_by_projection_local(c.frame, c.mps, th, 0, 40.0, c.nnratio, c.kp_prior_obs, c.kp_mp)
+    b = reference.search_by_projection_local(c.frame, c.mps, th, 0, 40.0, c.nnratio, c.kp_prior_obs, c.kp_mp)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and a[0] > 100
