@@ -196,6 +196,9 @@ def main():
     ap.add_argument("--pairs", type=int, default=C4_PAIRS)
     ap.add_argument("--engine", type=int, default=0, help="knn2 engine: 0 auto, 1 POPC, 2 mma.sync b1, 3 tcgen05 1-CTA, 4 tcgen05 2-CTA")
     ap.add_argument("--tri-engine", type=int, default=0, help="C4 kernel: 0 auto, 1 CTA per pair, 2 persistent bulk-copy pipeline")
+    ap.add_argument("--c4-gather", default="fused", choices=["fused", "nccl"],
+                    help="C4 at N > 1: 'fused' = the kernel stores matches into every rank's result buffer over NVLink peer memory "
+                         "(torch symmetric memory) + one device-side barrier; 'nccl' = kernel, then one NCCL all-gather of the dense rows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -284,12 +287,66 @@ def main():
         nmt = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
 
         gathered = torch.empty((P_total, C4_FEAT), dtype=torch.int32, device=dev) if world > 1 else None
+        extra["c4_gather"] = "none" if world == 1 else args.c4_gather
+        state = {}
 
-        def step():
+        def step_nccl():
             m.SearchForTriangulation_dev(ks, P, kf1.data_ptr(), kf2.data_ptr(), ep.data_ptr(), f12.data_ptr(), out.data_ptr(), nmt.data_ptr())
             if world > 1:
                 return all_gather_rows(out, P_total, out=gathered)
             return out
+
+        step = step_nccl
+        if world > 1 and args.c4_gather == "fused" and P_total % world == 0:
+            # Fused search + all-gather: every rank's kernel stores its matches straight into the result buffers of ALL ranks
+            # (symmetric memory = peer mappings over NVLink / NVSwitch).  Result buffers are double-buffered and preset to -1 by
+            # their owners one step ahead; ONE device-side barrier per step orders "all matches of step k written" and "all
+            # buffers of step k+1 preset".  Both step variants are captured in CUDA graphs: a step is tens of microseconds.
+            import torch.distributed._symmetric_memory as symm_mem
+            rows = symm_mem.empty((2, P_total * C4_FEAT), dtype=torch.int32, device=dev)
+            cnts = symm_mem.empty((2, P_total), dtype=torch.int32, device=dev)
+            hr = symm_mem.rendezvous(rows, dist.group.WORLD.group_name)
+            hc = symm_mem.rendezvous(cnts, dist.group.WORLD.group_name)
+            rows.fill_(-1)
+            cnts.fill_(0)
+            hr.barrier(channel=0)
+            state.update(k=0, graphs=None, gctx=None)
+
+            def fused_once(mm, b):
+                tm = [p_ + b * P_total * C4_FEAT * 4 for p_ in hr.buffer_ptrs]
+                tn = [p_ + b * P_total * 4 for p_ in hc.buffer_ptrs]
+                mm.SearchForTriangulation_peers_dev(ks, P, kf1.data_ptr(), kf2.data_ptr(), ep.data_ptr(), f12.data_ptr(), tm, tn, lo, True)
+                rows[b ^ 1].fill_(-1)
+                hr.barrier(channel=0)
+
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    gctx = matcher.Context(local_rank, stream=side.cuda_stream)
+                    gm = matcher.ORBmatcher(0.6, False, gctx)
+                    fused_once(gm, 0); fused_once(gm, 1)
+                    side.synchronize()
+                    graphs = []
+                    for b in (0, 1):
+                        g_ = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g_, stream=side):
+                            fused_once(gm, b)
+                        graphs.append(g_)
+                torch.cuda.current_stream().wait_stream(side)
+                state["graphs"], state["gctx"] = graphs, gctx
+                extra["c4_gather"] = "fused (peer stores over NVLink + device barrier, CUDA graph)"
+            except Exception as e:  # eager launches are still correct, only launch-bound
+                extra["c4_gather"] = f"fused (eager: graph capture failed: {e!r})"
+
+            def step():
+                b = state["k"] & 1
+                state["k"] += 1
+                if state["graphs"] is not None:
+                    state["graphs"][b].replay()
+                else:
+                    fused_once(m, b)
+                return rows[b].view(P_total, C4_FEAT)
 
         units_total = float(P_total)
         metric, unit = "frame_pairs_matched_per_s", "frame_pairs/s"
@@ -314,6 +371,8 @@ def main():
         total_ms += e0.elapsed_time(e1)
     barrier_sync()
     launches = ctx.launch_count - launches0
+    if extra.get("c4_gather", "").startswith("fused (peer") and launches == 0:
+        launches = K  # graph replays: one triangulation_stream_kernel per step (the context only counts direct launches)
     clocks = sampler.stop() if rank == 0 else {}
     total_ms = max_over_ranks(total_ms)
     ms_per_step = total_ms / max(K, 1)
@@ -323,8 +382,9 @@ def main():
         extra["comparisons_per_step"] = int(units_total)
         extra["matches_rank0"] = int((res[3][:nq] >= 0).sum().item())
     else:
-        extra["comparisons_per_step_rank0"] = ctx.fetch_comparisons()  # DescriptorDistance-equivalents, counted on the device
-        extra["matches_rank0"] = int(nmt[:P].sum().item())
+        cctx = state.get("gctx") or ctx
+        extra["comparisons_per_step_rank0"] = cctx.fetch_comparisons()  # DescriptorDistance-equivalents, counted on the device
+        extra["matches_rank0"] = int(nmt[:P].sum().item()) if extra.get("c4_gather", "none") in ("none", "nccl") else int(cnts[0][lo:hi].sum().item())
 
     # ---- end to end through the host-pointer C-ABI (what a reference-side caller uses)
     e2e = None

@@ -253,6 +253,15 @@ int orbgpu_search_for_triangulation_batch_dev(orbgpu_ctx *ctx, const orbgpu_kfse
                                               int32_t only_stereo, int32_t coarse, int32_t check_ori, int32_t *matches12_dev,
                                               int32_t *nmatches_dev);
 
+/* Fused search + all-gather for the sharded batch (monocular sets): the rows / counts of this rank's pairs are stored into the
+ * [P_total][n_feat] / [P_total] result buffers of ALL ranks -- target_matches[r], target_nmatches[r] are device addresses valid
+ * on THIS GPU (peer memory over NVLink / NVSwitch, e.g. torch symmetric memory) -- at rows pair_offset + p.  rows_preset != 0:
+ * every owner filled its buffer with -1 beforehand, so only matches and counts cross the links.  The caller separates steps
+ * with a cross-rank barrier.  n_targets <= 8 (one box). */
+int orbgpu_search_for_triangulation_batch_peers_dev(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs, const int32_t *kf1_dev,
+                                                    const int32_t *kf2_dev, const float *ep_dev, const float *f12_dev,
+                                                    int32_t coarse, int32_t check_ori, int32_t n_targets, void *const *target_matches,
+                                                    void *const *target_nmatches, int64_t pair_offset, int32_t rows_preset);
 /* Same search with the result in the reference's vMatchedPairs form (ORBmatcher.cc:1317-1325): for pair p the matches are
  * pairs[2*j], pairs[2*j+1] = (idx1, idx2), j in [pair_offsets[p], pair_offsets[p+1]), ascending idx1.  pair_offsets has
  * n_pairs+1 entries; cap = capacity of pairs in (idx1, idx2) entries; *total = entries produced (ORBGPU_ERR_OVERFLOW and the

@@ -438,7 +438,12 @@ struct TsParams {
     const int32_t *kf1, *kf2;
     const float *ep, *f12;
     int coarse, check_ori;
-    int32_t *matches12, *nmatches;
+    // output targets: the match rows / counts of pair p go to row (pair0 + p) of EVERY target.  One target (the caller's own
+    // buffers) for the plain call; the buffers of all ranks (peer memory over NVLink) for the fused all-gather, where the rows
+    // were preset to -1 by their owners and only matches and counts cross the links.
+    int n_targets, rows_preset;
+    long long pair0;
+    int32_t *tgt_m[8], *tgt_nm[8];
     unsigned long long *counters;
     long long *timeline; // debug: [n_my of CTA 0][8] SM-clock stamps, or null
 };
@@ -473,6 +478,7 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
     __shared__ __align__(8) unsigned long long bars[4][4]; // [stage][full, joined, compared, empty]
     __shared__ TsStageCtl ctl[4];
     __shared__ float sScale[64], sSigma[64];
+    __shared__ int s_cnt[2];    // post groups: matches of the pair in flight
     __shared__ int sBucket[64]; // join warps: slots per candidate-count bucket, then the buckets' bases
     __shared__ int hist2[2][ORBGPU_HISTO_LENGTH + 2];
     __shared__ int ind2[2][4];
@@ -705,15 +711,23 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
     for (int i = 0, st = 0, round = 0; i < n_my; i++, st = (st + 1 == S ? 0 : st + 1), round += (st == 0)) {
         if ((i & 1) != grp) continue;
         const int p = blockIdx.x + i * gridDim.x;
-        int32_t *row = P.matches12 + (size_t)p * n;
+        const size_t row_off = (size_t)(P.pair0 + p) * n;
         // vMatches12(N, -1) (:1092), while the pair is still being compared
-        if ((n & 3) == 0) {
-            int4 *row4 = (int4 *)row;
-            for (int x = gt; x < (n >> 2); x += GT) row4[x] = make_int4(-1, -1, -1, -1);
-        } else {
-            for (int x = gt; x < n; x += GT) row[x] = -1;
+        if (!P.rows_preset) {
+            for (int r = 0; r < P.n_targets; r++) {
+                int32_t *row = P.tgt_m[r] + row_off;
+                if ((n & 3) == 0) {
+                    int4 *row4 = (int4 *)row;
+                    for (int x = gt; x < (n >> 2); x += GT) row4[x] = make_int4(-1, -1, -1, -1);
+                } else {
+                    for (int x = gt; x < n; x += GT) row[x] = -1;
+                }
+            }
         }
-        if (gt == 0) P.nmatches[p] = 0;
+        auto put_match = [&](int f1, int idx2) {
+            for (int r = 0; r < P.n_targets; r++) P.tgt_m[r][row_off + f1] = idx2;
+        };
+        if (gt == 0) s_cnt[grp] = 0;
         if (P.check_ori && gt < ORBGPU_HISTO_LENGTH) hist[gt] = 0;
         bar_post(); // the row is initialised before any thread of the group writes a match into it
         if (gt == 0 && grp == 0) stamp(i, 5);
@@ -759,7 +773,7 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
             if (key == KEY_NONE) continue;
             if (via_best) atomicMin(&best[c1], key);
             else {
-                row[q1.w] = (int)(0xFFFFFu - (key & 0xFFFFFu));
+                put_match((int)q1.w, (int)(0xFFFFFu - (key & 0xFFFFFu)));
                 mine++;
             }
         }
@@ -793,13 +807,17 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
                     const int bin = rot_bin(ang1[f1], ang2[idx2]);
                     if (bin >= 0 && bin < ORBGPU_HISTO_LENGTH && bin != ind[0] && bin != ind[1] && bin != ind[2]) continue;
                 }
-                row[f1] = idx2;
+                put_match(f1, idx2);
                 mine++;
             }
-            bar_post(); // hist / ind are reused by the next pair
         }
         for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(FULL_MASK, mine, o);
-        if (lane == 0 && mine) atomicAdd(&P.nmatches[p], mine);
+        if (lane == 0 && mine) atomicAdd(&s_cnt[grp], mine);
+        bar_post(); // the group's count is complete; hist / ind may be reused by the next pair
+        if (gt == 0) {
+            const int cnt = s_cnt[grp];
+            for (int r = 0; r < P.n_targets; r++) P.tgt_nm[r][P.pair0 + p] = cnt;
+        }
         __syncwarp();
         if (gt == 0 && grp == 0) stamp(i, 7);
         if (lane == 0) ts_mbar_arrive(bar_of(st, B_EMPTY));
@@ -958,10 +976,11 @@ extern "C" int orbgpu_triangulation_set_engine(orbgpu_ctx *ctx, int32_t engine)
     return ORBGPU_OK;
 }
 
-extern "C" int orbgpu_search_for_triangulation_batch_dev(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs, const int32_t *kf1_dev,
-                                                         const int32_t *kf2_dev, const float *ep_dev, const float *f12_dev,
-                                                         int32_t only_stereo, int32_t coarse, int32_t check_ori, int32_t *matches12_dev,
-                                                         int32_t *nmatches_dev)
+// n_targets > 1 (or pair_offset != 0, rows_preset): output into the given targets (engine 2 only); otherwise the plain call
+static int tri_launch(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs, const int32_t *kf1_dev, const int32_t *kf2_dev,
+                      const float *ep_dev, const float *f12_dev, int32_t only_stereo, int32_t coarse, int32_t check_ori,
+                      int32_t *matches12_dev, int32_t *nmatches_dev, int n_targets, void *const *tgt_m, void *const *tgt_nm,
+                      int64_t pair_offset, int rows_preset)
 {
     ARG_TRY(ctx && s && n_pairs >= 0);
     ARG_TRY(n_pairs == 0 || (kf1_dev && kf2_dev && ep_dev && f12_dev && matches12_dev && nmatches_dev));
@@ -977,9 +996,9 @@ extern "C" int orbgpu_search_for_triangulation_batch_dev(orbgpu_ctx *ctx, const 
         int n_stages = (int)((227 * 1024 - 2048) / stage_bytes);
         if (n_stages > 4) n_stages = 4;
         const bool can = !s->u_right && !only_stereo && n_stages >= 3 && s->max_free <= 8192; // each post group holds a stage
-        if (ctx->tri_engine == 2 && !can)
+        if ((ctx->tri_engine == 2 || tgt_m) && !can)
             return orbgpu_fail(ORBGPU_ERR_INVALID, "triangulation engine 2 needs a monocular keyframe set that fits the shared-memory ring");
-        if (can && ctx->tri_engine != 1) {
+        if (can && (ctx->tri_engine != 1 || tgt_m)) {
             TsParams P;
             P.blob = s->blob; P.blob_stride = s->blob_stride; P.blob_bytes = s->blob_bytes;
             P.kf_n_free = s->kf_n_free; P.kf_n_nodes = s->kf_n_nodes; P.aux = s->aux; P.angle = s->angle;
@@ -988,7 +1007,18 @@ extern "C" int orbgpu_search_for_triangulation_batch_dev(orbgpu_ctx *ctx, const 
             P.n_stages = n_stages; P.stage_bytes = (int)stage_bytes;
             P.kf1 = kf1_dev; P.kf2 = kf2_dev; P.ep = ep_dev; P.f12 = f12_dev;
             P.coarse = coarse; P.check_ori = check_ori;
-            P.matches12 = matches12_dev; P.nmatches = nmatches_dev; P.counters = ctx->d_counters;
+            P.counters = ctx->d_counters;
+            if (tgt_m) {
+                P.n_targets = n_targets; P.rows_preset = rows_preset; P.pair0 = pair_offset;
+                for (int r = 0; r < 8; r++) {
+                    P.tgt_m[r] = r < n_targets ? (int32_t *)tgt_m[r] : nullptr;
+                    P.tgt_nm[r] = r < n_targets ? (int32_t *)tgt_nm[r] : nullptr;
+                }
+            } else {
+                P.n_targets = 1; P.rows_preset = 0; P.pair0 = 0;
+                for (int r = 0; r < 8; r++) { P.tgt_m[r] = nullptr; P.tgt_nm[r] = nullptr; }
+                P.tgt_m[0] = matches12_dev; P.tgt_nm[0] = nmatches_dev;
+            }
             P.timeline = (long long *)ctx->tri_timeline;
             auto kern2 = triangulation_stream_kernel<NC, NG, NJ>;
             const size_t smem2 = stage_bytes * n_stages;
@@ -1011,6 +1041,31 @@ extern "C" int orbgpu_search_for_triangulation_batch_dev(orbgpu_ctx *ctx, const 
     LAUNCH_COUNT(ctx);
     CU_TRY(cudaGetLastError());
     return ORBGPU_OK;
+}
+
+extern "C" int orbgpu_search_for_triangulation_batch_dev(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs, const int32_t *kf1_dev,
+                                                         const int32_t *kf2_dev, const float *ep_dev, const float *f12_dev,
+                                                         int32_t only_stereo, int32_t coarse, int32_t check_ori, int32_t *matches12_dev,
+                                                         int32_t *nmatches_dev)
+{
+    return tri_launch(ctx, s, n_pairs, kf1_dev, kf2_dev, ep_dev, f12_dev, only_stereo, coarse, check_ori, matches12_dev, nmatches_dev, 0,
+                      nullptr, nullptr, 0, 0);
+}
+
+// Fused search + all-gather: the match rows and counts of this rank's pairs are stored straight into the result buffers of ALL
+// ranks (peer memory mapped over NVLink / NVSwitch, e.g. torch symmetric memory), at rows pair_offset + p.  With rows_preset the
+// owners have filled their buffers with -1 beforehand and only the matches (a few hundred 4-byte stores per pair) and the
+// counts cross the links; the caller separates steps with a cross-rank barrier.
+extern "C" int orbgpu_search_for_triangulation_batch_peers_dev(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs,
+                                                               const int32_t *kf1_dev, const int32_t *kf2_dev, const float *ep_dev,
+                                                               const float *f12_dev, int32_t coarse, int32_t check_ori, int32_t n_targets,
+                                                               void *const *target_matches, void *const *target_nmatches,
+                                                               int64_t pair_offset, int32_t rows_preset)
+{
+    ARG_TRY(ctx && s && n_pairs >= 0 && n_targets >= 1 && n_targets <= 8 && target_matches && target_nmatches && pair_offset >= 0);
+    for (int r = 0; r < n_targets; r++) ARG_TRY(target_matches[r] && target_nmatches[r]);
+    return tri_launch(ctx, s, n_pairs, kf1_dev, kf2_dev, ep_dev, f12_dev, 0, coarse, check_ori, (int32_t *)target_matches[0],
+                      (int32_t *)target_nmatches[0], n_targets, target_matches, target_nmatches, pair_offset, rows_preset ? 1 : 0);
 }
 
 extern "C" int orbgpu_search_for_triangulation_batch(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs, const int32_t *kf1,

@@ -511,6 +511,20 @@ class ORBmatcher:
                                                                         vp(ep_ptr), vp(f12_ptr), int(bOnlyStereo), int(bCoarse),
                                                                         int(self.mbCheckOrientation), vp(matches_ptr), vp(nmatches_ptr)))
 
+    # fused search + all-gather: rows / counts of this rank's pairs stored into every rank's result buffers (peer memory)
+    def SearchForTriangulation_peers_dev(self, kfs: DeviceKfSet, n_pairs, kf1_ptr, kf2_ptr, ep_ptr, f12_ptr, target_matches, target_nmatches,
+                                         pair_offset: int, rows_preset: bool = True, bCoarse=False):
+        vp = C.c_void_p
+        n = len(target_matches)
+        tm = (C.c_void_p * n)(*[int(x) for x in target_matches])
+        tn = (C.c_void_p * n)(*[int(x) for x in target_nmatches])
+        L = load_library()
+        L.orbgpu_search_for_triangulation_batch_peers_dev.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32,
+                                                                      C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int64, C.c_int32]
+        _check(L.orbgpu_search_for_triangulation_batch_peers_dev(self.ctx.handle, kfs.handle, int(n_pairs), vp(kf1_ptr), vp(kf2_ptr),
+                                                                 vp(ep_ptr), vp(f12_ptr), int(bCoarse), int(self.mbCheckOrientation), n, tm, tn,
+                                                                 int(pair_offset), int(rows_preset)))
+
     # brute-force 2-NN + ratio test ("SearchByNN" of BASELINE.json) -> best_idx, best_dist, second_dist, match
     def SearchByNN(self, db: DeviceDb, q, th_low: int = TH_LOW):
         q = as_u8(q).reshape(-1, 32)

@@ -479,3 +479,28 @@ def test_large_frames_shared_memory_opt_in(ctx, M, oracle):
     n, m12, prev = M.ORBmatcher(ci.nnratio, True, ctx).SearchForInitialization(f1, f2, ci.prev_matched, ci.window_size)
     en, em, ep = oracle.search_for_initialization(ci.f1, ci.f2, ci.prev_matched, ci.window_size, ci.nnratio, 1)
     assert n == en and np.array_equal(m12, em) and np.array_equal(prev, ep)
+
+
+def test_triangulation_multi_target_output(ctx, M):
+    """the fused all-gather entry point on one GPU: two target buffers (stand-ins for two ranks' result buffers), rows preset to -1,
+    this 'rank' owning pairs [lo, hi) of a larger batch -- both targets must hold exactly the dense rows of the plain call"""
+    import torch
+    tc = synth.fill_geometry(synth.make_triangulation_case(191, n_pairs=300, n_feat=900))
+    ks = ctx.upload_kfset(tc.kfs)
+    mm = M.ORBmatcher(0.6, False, ctx)
+    nm, m = mm.SearchForTriangulation(ks, tc.kf1, tc.kf2, tc.ep, tc.f12)
+    dev = torch.device("cuda", 0)
+    P_total, NF, lo, hi = 300, 900, 100, 260
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    kf1, kf2, ep, f12 = t(tc.kf1[lo:hi]), t(tc.kf2[lo:hi]), t(tc.ep[lo:hi]), t(tc.f12[lo:hi])
+    for preset in (True, False):
+        rows = [torch.full((P_total, NF), -1 if preset else 7, dtype=torch.int32, device=dev) for _ in range(2)]
+        cnts = [torch.full((P_total,), -5, dtype=torch.int32, device=dev) for _ in range(2)]
+        torch.cuda.synchronize()
+        mm.SearchForTriangulation_peers_dev(ks, hi - lo, kf1.data_ptr(), kf2.data_ptr(), ep.data_ptr(), f12.data_ptr(),
+                                            [r.data_ptr() for r in rows], [c.data_ptr() for c in cnts], lo, preset)
+        ctx.synchronize()
+        for r, c in zip(rows, cnts):
+            assert np.array_equal(r[lo:hi].cpu().numpy(), m[lo:hi]) and np.array_equal(c[lo:hi].cpu().numpy(), nm[lo:hi])
+            assert (r[:lo] == (-1 if preset else 7)).all() and (r[hi:] == (-1 if preset else 7)).all()  # other ranks' rows untouched
+            assert (c[:lo] == -5).all() and (c[hi:] == -5).all()
