@@ -350,6 +350,28 @@ def main():
 
         units_total = float(P_total)
         metric, unit = "frame_pairs_matched_per_s", "frame_pairs/s"
+        if world == 1 and not args.no_e2e:
+            # the caller before this path: KeyFrame::ComputeBoW for the whole set on the device (vocabulary descent of every feature
+            # + CSR rebuild), reported next to the headline; run on a second copy of the set so that the timed search keeps its inputs
+            try:
+                from orb_slam3_comments_ghr_b200._abi import HostVoc
+                voc = HostVoc.load(os.path.join(ROOT, "tests", "golden", "voc_k10_L4.npz"))
+                dv = ctx.upload_vocabulary(voc)
+                nodes_host = case.kfs.node_id
+                case.kfs.node_id = None
+                ks2 = ctx.upload_kfset(case.kfs)
+                case.kfs.node_id = nodes_host
+                ks2.transform(dv, 2)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                ncmp = ks2.transform(dv, 2)
+                dt = time.perf_counter() - t0
+                extra["kfset_transform"] = {"features": int(case.kfs.desc.shape[0] * case.kfs.desc.shape[1]), "vocabulary": "k=10 L=4, levelsup=2",
+                                            "ms": dt * 1e3, "comparisons": int(ncmp), "comparisons_per_s": ncmp / dt,
+                                            "note": "vocabulary descent of every feature of the 8192 key frames + CSR / stream-blob rebuild, one call"}
+                del ks2
+            except Exception as e:
+                extra["kfset_transform"] = {"error": repr(e)}
 
     # ---- device-resident timing: W warm-up steps, then exactly K timed steps
     for _ in range(W):

@@ -233,13 +233,17 @@ typedef struct orbgpu_kfset_host {
     const float *angle;          /* [n_kf][n_feat] */
     const uint8_t *has_mp;       /* [n_kf][n_feat] GetMapPoint(i) != NULL */
     const float *u_right;        /* [n_kf][n_feat] mvuRight or NULL (mono) */
-    const uint32_t *node_id;     /* [n_kf][n_feat] FeatureVector node of each feature, 0xFFFFFFFF == none */
+    const uint32_t *node_id;     /* [n_kf][n_feat] FeatureVector node of each feature, 0xFFFFFFFF == none; NULL: see orbgpu_kfset_transform */
     int32_t n_levels;
     const float *scale_factors;  /* [n_levels] */
     const float *level_sigma2;   /* [n_levels] */
 } orbgpu_kfset_host;
 int orbgpu_kfset_upload(orbgpu_ctx *ctx, const orbgpu_kfset_host *s, orbgpu_kfset **out);
 void orbgpu_kfset_destroy(orbgpu_kfset *s);
+/* KeyFrame::ComputeBoW (KeyFrame.cc:102-117) for the whole set on the device: TemplatedVocabulary::transform of every feature
+ * (TemplatedVocabulary.h:1127-1194, 1216-1258) -> FeatureVector node ids (level L - levelsup, stopped words dropped), then the
+ * per-key-frame CSR is rebuilt.  A set uploaded with node_id == NULL has no FeatureVector until this is called. */
+int orbgpu_kfset_transform(orbgpu_ctx *ctx, const orbgpu_voc *voc, orbgpu_kfset *s, int32_t levelsup);
 /* Per pair p: keyframes (kf1[p], kf2[p]); geometry precomputed by the caller with the
  * reference's own host algebra (ORBmatcher.cc:1053-1071, Pinhole.cpp:194-197):
  *   ep[p][2]  epipole of camera 1 in image 2;  f12[p][9] row-major F12 = K1^-T [t12]x R12 K2^-1.

@@ -436,7 +436,8 @@ class HostKfSet:
         self.octave = as_i32(self.octave)
         self.angle = as_f32(self.angle)
         self.has_mp = as_u8(self.has_mp)
-        self.node_id = as_u32(self.node_id)
+        if self.node_id is not None:  # None: the FeatureVectors are computed on the device (DeviceKfSet.transform)
+            self.node_id = as_u32(self.node_id)
         if self.u_right is not None:
             self.u_right = as_f32(self.u_right)
         self.scale_factors = as_f32(self.scale_factors)

@@ -75,6 +75,9 @@ inline void arena_reset(orbgpu_ctx *ctx) { ctx->arena.used = 0; }
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 int ctx_begin(orbgpu_ctx *ctx); // set device, reset arena, zero counters
+struct orbgpu_voc;
+// voc.cu: FeatureVector node of n descriptors (0xFFFFFFFF for stopped words), comparisons added to counters[0]
+int launch_voc_transform_nodes(orbgpu_ctx *ctx, const orbgpu_voc *voc, long long n, const uint4 *desc, int levelsup, uint32_t *node_id);
 int ctx_fetch_comparisons(orbgpu_ctx *ctx); // sync + read counter[0] into last_comparisons
 
 #define LAUNCH_COUNT(ctx) ((ctx)->launches++)

@@ -900,11 +900,34 @@ extern "C" void orbgpu_kfset_destroy(orbgpu_kfset *s)
     delete s;
 }
 
+// (re)builds the per-key-frame CSR, the node-ordered copies, the stream blobs and the aux records from s->node_id / s->has_mp
+static int kfset_build_csr(orbgpu_ctx *ctx, orbgpu_kfset *s)
+{
+    int32_t *d_max = s->kf_n_free + s->n_kf;
+    CU_TRY(cudaMemsetAsync(d_max, 0, 12, ctx->stream));
+    int cap = 1;
+    while (cap < s->n_feat) cap <<= 1;
+    const size_t smem = (size_t)cap * 8;
+    CU_TRY(cudaFuncSetAttribute(kfset_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kfset_csr_kernel<<<s->n_kf, 1024, smem, ctx->stream>>>(s->n_feat, cap, s->node_id, s->has_mp, s->desc, s->xy, s->octave, s->kf_n_nodes,
+                                                          s->kf_node_ids, s->kf_node_off, s->kf_feat, s->desc_csr, s->kp_csr, s->kf_n_free,
+                                                          d_max, s->blob, s->blob_stride, s->blob_bytes, s->aux);
+    LAUNCH_COUNT(ctx);
+    CU_TRY(cudaGetLastError());
+    int32_t mx[3] = {0, 0, 0};
+    CU_TRY(cudaMemcpyAsync(mx, d_max, 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    s->max_free = ((mx[0] > 0 ? mx[0] : 1) + 3) & ~3; // multiple of 4: keeps the int4 node table 16-byte aligned
+    s->max_nodes = mx[1] > 0 ? mx[1] : 1;
+    s->max_blob = mx[2] > 0 ? mx[2] : 16;
+    return ORBGPU_OK;
+}
+
 extern "C" int orbgpu_kfset_upload(orbgpu_ctx *ctx, const orbgpu_kfset_host *h, orbgpu_kfset **out)
 {
     ARG_TRY(ctx && h && out);
     ARG_TRY(h->n_kf > 0 && h->n_feat > 0 && h->n_feat <= 8192 && h->n_feat < (1 << 20));
-    ARG_TRY(h->desc && h->kp_xy && h->octave && h->angle && h->has_mp && h->node_id && h->scale_factors && h->level_sigma2);
+    ARG_TRY(h->desc && h->kp_xy && h->octave && h->angle && h->has_mp && h->scale_factors && h->level_sigma2);
     ARG_TRY(h->n_levels > 0 && h->n_levels <= 64);
     for (size_t i = 0, T0 = (size_t)h->n_kf * h->n_feat; i < T0; i++)
         ARG_TRY(h->octave[i] >= 0 && h->octave[i] < h->n_levels); // indexes the scale tables in the gates
@@ -925,7 +948,11 @@ extern "C" int orbgpu_kfset_upload(orbgpu_ctx *ctx, const orbgpu_kfset_host *h, 
     UP(s->angle, h->angle, T * 4);
     UP(s->has_mp, h->has_mp, T);
     if (h->u_right) UP(s->u_right, h->u_right, T * 4);
-    UP(s->node_id, h->node_id, T * 4);
+    if (h->node_id) UP(s->node_id, h->node_id, T * 4);
+    else { // no FeatureVector yet: orbgpu_kfset_transform fills it on the device
+        CU_TRY(cudaMalloc((void **)&s->node_id, T * 4));
+        CU_TRY(cudaMemsetAsync(s->node_id, 0xFF, T * 4, ctx->stream));
+    }
     UP(s->scale_factors, h->scale_factors, (size_t)h->n_levels * 4);
     UP(s->level_sigma2, h->level_sigma2, (size_t)h->n_levels * 4);
 #undef UP
@@ -940,23 +967,8 @@ extern "C" int orbgpu_kfset_upload(orbgpu_ctx *ctx, const orbgpu_kfset_host *h, 
     CU_TRY(cudaMalloc((void **)&s->blob, s->blob_stride * h->n_kf));
     CU_TRY(cudaMalloc((void **)&s->aux, T * 32));
     CU_TRY(cudaMalloc((void **)&s->blob_bytes, (size_t)h->n_kf * 4));
-    int32_t *d_max = s->kf_n_free + h->n_kf;
-    CU_TRY(cudaMemsetAsync(d_max, 0, 12, ctx->stream));
-    int cap = 1;
-    while (cap < h->n_feat) cap <<= 1;
-    const size_t smem = (size_t)cap * 8;
-    CU_TRY(cudaFuncSetAttribute(kfset_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kfset_csr_kernel<<<h->n_kf, 1024, smem, ctx->stream>>>(h->n_feat, cap, s->node_id, s->has_mp, s->desc, s->xy, s->octave, s->kf_n_nodes,
-                                                          s->kf_node_ids, s->kf_node_off, s->kf_feat, s->desc_csr, s->kp_csr, s->kf_n_free,
-                                                          d_max, s->blob, s->blob_stride, s->blob_bytes, s->aux);
-    LAUNCH_COUNT(ctx);
-    CU_TRY(cudaGetLastError());
-    int32_t mx[3] = {0, 0, 0};
-    CU_TRY(cudaMemcpyAsync(mx, d_max, 12, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaStreamSynchronize(ctx->stream));
-    s->max_free = ((mx[0] > 0 ? mx[0] : 1) + 3) & ~3; // multiple of 4: keeps the int4 node table 16-byte aligned
-    s->max_nodes = mx[1] > 0 ? mx[1] : 1;
-    s->max_blob = mx[2] > 0 ? mx[2] : 16;
+    int rc = kfset_build_csr(ctx, s);
+    if (rc) return rc;
     *out = owner.release();
     return ORBGPU_OK;
 }
@@ -967,6 +979,21 @@ extern "C" int orbgpu_debug_triangulation_timeline(orbgpu_ctx *ctx, void *dev_bu
     ARG_TRY(ctx);
     ctx->tri_timeline = dev_buf;
     return ORBGPU_OK;
+}
+
+// TemplatedVocabulary::transform (TemplatedVocabulary.h:1127-1194, 1216-1258) for every feature of every key frame of the set,
+// on the device: node ids of the FeatureVectors (level L - levelsup; stopped words dropped), then the CSR / stream blobs are
+// rebuilt.  This is KeyFrame::ComputeBoW (KeyFrame.cc:102-117) for the whole batch, without a host round trip.
+extern "C" int orbgpu_kfset_transform(orbgpu_ctx *ctx, const orbgpu_voc *voc, orbgpu_kfset *s, int32_t levelsup)
+{
+    ARG_TRY(ctx && voc && s);
+    int rc = ctx_begin(ctx);
+    if (rc) return rc;
+    rc = launch_voc_transform_nodes(ctx, voc, (long long)s->n_kf * s->n_feat, s->desc, levelsup, s->node_id);
+    if (rc) return rc;
+    rc = kfset_build_csr(ctx, s);
+    if (rc) return rc;
+    return ctx_fetch_comparisons(ctx);
 }
 
 extern "C" int orbgpu_triangulation_set_engine(orbgpu_ctx *ctx, int32_t engine)

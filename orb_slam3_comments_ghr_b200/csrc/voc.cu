@@ -61,6 +61,45 @@ __global__ void voc_transform_kernel(int n, const uint4 *__restrict__ desc, cons
     }
 }
 
+// batched form for a key-frame set: only the FeatureVector node survives (NODE id at level L - levelsup, 0xFFFFFFFF for a
+// stopped word, w == 0, which the reference drops from the FeatureVector: TemplatedVocabulary.h:1157-1161)
+template <int G> // lanes per feature: the smallest power of two >= the branching factor, so that a warp descends 32/G features at once
+__global__ void voc_transform_nodes_kernel(long long n, const uint4 *__restrict__ desc, const uint4 *__restrict__ node_desc,
+                                           const int32_t *__restrict__ child_offsets, const uint32_t *__restrict__ child_ids,
+                                           const double *__restrict__ node_weight, int L, int levelsup, uint32_t *__restrict__ node_id,
+                                           unsigned long long *__restrict__ counters)
+{
+    const int lane = lane_id(), sub = lane & (G - 1);
+    const unsigned gmask = (G == 32) ? FULL_MASK : (((1u << G) - 1u) << (lane & ~(G - 1)));
+    const long long group0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 / G) + lane / G;
+    const long long n_groups = (((long long)gridDim.x * blockDim.x) >> 5) * (32 / G);
+    const int nid_level = L - levelsup;
+    unsigned long long ncmp = 0; // one atomic per group at the end: 16 M single-address atomics would serialise the kernel
+    for (long long i = group0; i < n; i += n_groups) { // persistent grid: group-uniform trip count
+        const uint4 fa = desc[2 * i], fb = desc[2 * i + 1];
+        uint32_t nid = 0, final_id = 0;
+        int level = 0;
+        int c0 = child_offsets[0], c1 = child_offsets[1];
+        while (c1 > c0) { // group-uniform
+            ++level;
+            uint32_t best = KEY_NONE;
+            for (int c = c0 + sub; c < c1; c += G) {
+                const uint32_t id = child_ids[c];
+                const uint32_t d = (uint32_t)ham256(fa, fb, node_desc[2 * id], node_desc[2 * id + 1]);
+                best = min(best, (d << 20) | (uint32_t)(c - c0));
+            }
+            best = __reduce_min_sync(gmask, best);
+            final_id = child_ids[c0 + (best & 0xFFFFF)];
+            ncmp += (unsigned)(c1 - c0);
+            if (level == nid_level) nid = final_id;
+            c0 = child_offsets[final_id];
+            c1 = child_offsets[final_id + 1];
+        }
+        if (sub == 0) node_id[i] = node_weight[final_id] > 0.0 ? nid : 0xFFFFFFFFu;
+    }
+    if (sub == 0 && ncmp) atomicAdd(&counters[0], ncmp);
+}
+
 // in-place ascending bitonic sort of `cap` (power of two) 64-bit keys by one block
 __device__ void block_bitonic_sort(unsigned long long *keys, int cap)
 {
@@ -212,6 +251,27 @@ bow_build_kernel(int n, int cap, const uint32_t *__restrict__ word_id, const dou
 }
 
 } // namespace
+
+int launch_voc_transform_nodes(orbgpu_ctx *ctx, const orbgpu_voc *voc, long long n, const uint4 *desc, int levelsup, uint32_t *node_id)
+{
+    if (n <= 0) return ORBGPU_OK;
+    const int G = voc->k <= 8 ? 8 : (voc->k <= 16 ? 16 : 32);
+    const long long warps = (n + 32 / G - 1) / (32 / G);
+    long long blocks = (warps * 32 + 255) / 256;
+    const long long resident = (long long)ctx->sm_count * 8; // 8 x 256 threads per SM; the kernel is a grid-stride loop
+    if (blocks > resident) blocks = resident;
+#define LAUNCH_NODES(GG)                                                                                                              \
+    voc_transform_nodes_kernel<GG><<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, desc, voc->node_desc, voc->child_offsets, voc->child_ids, \
+                                                                              voc->weight, voc->L, levelsup, node_id, ctx->d_counters)
+    if (G == 8) LAUNCH_NODES(8);
+    else if (G == 16) LAUNCH_NODES(16);
+    else LAUNCH_NODES(32);
+#undef LAUNCH_NODES
+    LAUNCH_COUNT(ctx);
+    CU_TRY(cudaGetLastError());
+    return ORBGPU_OK;
+}
+
 
 extern "C" int orbgpu_voc_upload(orbgpu_ctx *ctx, const orbgpu_voc_host *h, orbgpu_voc **out)
 {

@@ -317,6 +317,14 @@ class DeviceKfSet:
         _check(load_library().orbgpu_kfset_upload(ctx.handle, C.byref(st), C.byref(self._h)))
         self.n_kf, self.n_feat = s.n_kf, s.n_feat
 
+    def transform(self, voc: "DeviceVoc", levelsup: int):
+        """KeyFrame::ComputeBoW for the whole set on the device (FeatureVector node ids + CSR rebuild); returns the number of
+        descriptor comparisons of the vocabulary descent."""
+        L = load_library()
+        L.orbgpu_kfset_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        _check(L.orbgpu_kfset_transform(self.ctx.handle, voc.handle, self._h, int(levelsup)))
+        return self.ctx.last_comparisons
+
     def __del__(self):
         try:
             if self._h:

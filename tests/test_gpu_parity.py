@@ -504,3 +504,33 @@ def test_triangulation_multi_target_output(ctx, M):
             assert np.array_equal(r[lo:hi].cpu().numpy(), m[lo:hi]) and np.array_equal(c[lo:hi].cpu().numpy(), nm[lo:hi])
             assert (r[:lo] == (-1 if preset else 7)).all() and (r[hi:] == (-1 if preset else 7)).all()  # other ranks' rows untouched
             assert (c[:lo] == -5).all() and (c[hi:] == -5).all()
+
+
+@pytest.mark.parametrize("levelsup", [2, 3])
+def test_kfset_transform_then_triangulation(ctx, M, oracle, levelsup):
+    """KeyFrame::ComputeBoW for a whole key-frame set on the device: FeatureVector nodes from the vocabulary descent feed the
+    batched SearchForTriangulation without a host round trip; equals oracle transform + oracle search."""
+    voc = golden_voc()
+    rng = np.random.default_rng(201)
+    tc = synth.fill_geometry(synth.make_triangulation_case(201, n_pairs=24, n_feat=800))
+    nk, nf = tc.kfs.desc.shape[:2]
+    # descriptors near vocabulary words so that the key frames share nodes; planted pairs keep (nearly) equal descriptors
+    base = synth.descriptors_near_words(rng, voc, nk * nf).reshape(nk, nf, 32)
+    tc.kfs.desc[:] = base
+    tc.kfs.desc[tc.kf2] = np.where(rng.random((tc.kf2.shape[0], nf, 1)) < 0.5, tc.kfs.desc[tc.kf1] ^ synth.flip_mask(rng, tc.kf1.shape[0] * nf, np.full(tc.kf1.shape[0] * nf, 5)).reshape(-1, nf, 32), tc.kfs.desc[tc.kf2])
+    # oracle: per-feature descent -> node ids (stopped words dropped)
+    w, nid, wt = oracle.voc_transform(voc, tc.kfs.desc.reshape(-1, 32), levelsup)
+    node = np.where(wt > 0, nid, np.uint32(0xFFFFFFFF)).astype(np.uint32).reshape(nk, nf)
+    host_nodes = tc.kfs.node_id
+    tc.kfs.node_id = None
+    ks = ctx.upload_kfset(tc.kfs)
+    dv = ctx.upload_vocabulary(voc)
+    oracle.reset_comparisons()
+    oracle.voc_transform(voc, tc.kfs.desc.reshape(-1, 32), levelsup)
+    n_cmp = ks.transform(dv, levelsup)
+    assert n_cmp == oracle.comparisons()
+    nm, m = M.ORBmatcher(0.6, False, ctx).SearchForTriangulation(ks, tc.kf1, tc.kf2, tc.ep, tc.f12, False, True)
+    tc.kfs.node_id = node
+    enm, em = oracle.search_for_triangulation_batch(tc.kfs, tc.kf1, tc.kf2, tc.ep, tc.f12, 0, 1, 0, n_threads=os.cpu_count() or 1)
+    assert np.array_equal(nm, enm) and np.array_equal(m, em) and enm.sum() > 100
+    tc.kfs.node_id = host_nodes
