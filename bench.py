@@ -298,10 +298,10 @@ def main():
 
         step = step_nccl
         if world > 1 and args.c4_gather == "fused" and P_total % world == 0:
-            # Fused search + all-gather: every rank's kernel stores its matches straight into the result buffers of ALL ranks
-            # (symmetric memory = peer mappings over NVLink / NVSwitch).  Result buffers are double-buffered and preset to -1 by
-            # their owners one step ahead; ONE device-side barrier per step orders "all matches of step k written" and "all
-            # buffers of step k+1 preset".  Both step variants are captured in CUDA graphs: a step is tens of microseconds.
+            # Fused search + all-gather: every rank's kernel builds each match row in its own result buffer and ships the finished
+            # row to the result buffers of ALL other ranks (symmetric memory = peer mappings over NVLink / NVSwitch) with coalesced
+            # 128-bit stores while the next pairs are being compared.  Result buffers are double-buffered; ONE device-side barrier
+            # per step.  Both step variants are captured in CUDA graphs: a step is tens of microseconds of GPU work.
             import torch.distributed._symmetric_memory as symm_mem
             rows = symm_mem.empty((2, P_total * C4_FEAT), dtype=torch.int32, device=dev)
             cnts = symm_mem.empty((2, P_total), dtype=torch.int32, device=dev)
@@ -312,11 +312,13 @@ def main():
             hr.barrier(channel=0)
             state.update(k=0, graphs=None, gctx=None)
 
+            order = [rank] + [r_ for r_ in range(world) if r_ != rank]  # target 0 = this rank's own buffer
+
             def fused_once(mm, b):
-                tm = [p_ + b * P_total * C4_FEAT * 4 for p_ in hr.buffer_ptrs]
-                tn = [p_ + b * P_total * 4 for p_ in hc.buffer_ptrs]
-                mm.SearchForTriangulation_peers_dev(ks, P, kf1.data_ptr(), kf2.data_ptr(), ep.data_ptr(), f12.data_ptr(), tm, tn, lo, True)
-                rows[b ^ 1].fill_(-1)
+                tm = [hr.buffer_ptrs[r_] + b * P_total * C4_FEAT * 4 for r_ in order]
+                tn = [hc.buffer_ptrs[r_] + b * P_total * 4 for r_ in order]
+                # rows_preset = 2: the row is built in this rank's buffer and shipped whole to the peers (coalesced 128-bit stores)
+                mm.SearchForTriangulation_peers_dev(ks, P, kf1.data_ptr(), kf2.data_ptr(), ep.data_ptr(), f12.data_ptr(), tm, tn, lo, 2)
                 hr.barrier(channel=0)
 
             try:

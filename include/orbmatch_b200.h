@@ -259,9 +259,12 @@ int orbgpu_search_for_triangulation_batch_dev(orbgpu_ctx *ctx, const orbgpu_kfse
 
 /* Fused search + all-gather for the sharded batch (monocular sets): the rows / counts of this rank's pairs are stored into the
  * [P_total][n_feat] / [P_total] result buffers of ALL ranks -- target_matches[r], target_nmatches[r] are device addresses valid
- * on THIS GPU (peer memory over NVLink / NVSwitch, e.g. torch symmetric memory) -- at rows pair_offset + p.  rows_preset != 0:
- * every owner filled its buffer with -1 beforehand, so only matches and counts cross the links.  The caller separates steps
- * with a cross-rank barrier.  n_targets <= 8 (one box). */
+ * on THIS GPU (peer memory over NVLink / NVSwitch, e.g. torch symmetric memory) -- at rows pair_offset + p.
+ *   rows_preset 0: every target row is filled with -1 and receives the individual match stores;
+ *   rows_preset 1: every owner filled its buffer with -1 beforehand, only matches and counts cross the links;
+ *   rows_preset 2: target 0 must be THIS rank's buffer; the row is built there and then copied whole to the other targets
+ *                  with coalesced 128-bit stores (no preset; small scattered stores do not coalesce on the links).
+ * The caller separates steps with a cross-rank barrier.  n_targets <= 8 (one box). */
 int orbgpu_search_for_triangulation_batch_peers_dev(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs, const int32_t *kf1_dev,
                                                     const int32_t *kf2_dev, const float *ep_dev, const float *f12_dev,
                                                     int32_t coarse, int32_t check_ori, int32_t n_targets, void *const *target_matches,

@@ -441,7 +441,8 @@ struct TsParams {
     // output targets: the match rows / counts of pair p go to row (pair0 + p) of EVERY target.  One target (the caller's own
     // buffers) for the plain call; the buffers of all ranks (peer memory over NVLink) for the fused all-gather, where the rows
     // were preset to -1 by their owners and only matches and counts cross the links.
-    int n_targets, rows_preset;
+    int n_targets, rows_preset; // rows_preset 2: "copy rows" -- target 0 is this rank's own buffer, built as in the plain call; the
+                                // finished 8 KB row is then copied to the other targets with coalesced 128-bit stores (no preset needed)
     long long pair0;
     int32_t *tgt_m[8], *tgt_nm[8];
     unsigned long long *counters;
@@ -713,8 +714,9 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
         const int p = blockIdx.x + i * gridDim.x;
         const size_t row_off = (size_t)(P.pair0 + p) * n;
         // vMatches12(N, -1) (:1092), while the pair is still being compared
-        if (!P.rows_preset) {
-            for (int r = 0; r < P.n_targets; r++) {
+        const int n_scatter = P.rows_preset == 2 ? 1 : P.n_targets; // targets that receive individual match stores
+        if (P.rows_preset != 1) {
+            for (int r = 0; r < n_scatter; r++) {
                 int32_t *row = P.tgt_m[r] + row_off;
                 if ((n & 3) == 0) {
                     int4 *row4 = (int4 *)row;
@@ -725,7 +727,7 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
             }
         }
         auto put_match = [&](int f1, int idx2) {
-            for (int r = 0; r < P.n_targets; r++) P.tgt_m[r][row_off + f1] = idx2;
+            for (int r = 0; r < n_scatter; r++) P.tgt_m[r][row_off + f1] = idx2;
         };
         if (gt == 0) s_cnt[grp] = 0;
         if (P.check_ori && gt < ORBGPU_HISTO_LENGTH) hist[gt] = 0;
@@ -817,6 +819,17 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
         if (gt == 0) {
             const int cnt = s_cnt[grp];
             for (int r = 0; r < P.n_targets; r++) P.tgt_nm[r][P.pair0 + p] = cnt;
+        }
+        if (P.rows_preset == 2) { // the row is complete in this rank's buffer (all stores precede the barrier above): ship it whole
+            const int32_t *src = P.tgt_m[0] + row_off;
+            for (int r = 1; r < P.n_targets; r++) {
+                int32_t *dst = P.tgt_m[r] + row_off;
+                if ((n & 3) == 0) {
+                    for (int x = gt; x < (n >> 2); x += GT) ((int4 *)dst)[x] = __ldcg((const int4 *)src + x);
+                } else {
+                    for (int x = gt; x < n; x += GT) dst[x] = __ldcg(src + x);
+                }
+            }
         }
         __syncwarp();
         if (gt == 0 && grp == 0) stamp(i, 7);
@@ -1092,7 +1105,8 @@ extern "C" int orbgpu_search_for_triangulation_batch_peers_dev(orbgpu_ctx *ctx, 
     ARG_TRY(ctx && s && n_pairs >= 0 && n_targets >= 1 && n_targets <= 8 && target_matches && target_nmatches && pair_offset >= 0);
     for (int r = 0; r < n_targets; r++) ARG_TRY(target_matches[r] && target_nmatches[r]);
     return tri_launch(ctx, s, n_pairs, kf1_dev, kf2_dev, ep_dev, f12_dev, 0, coarse, check_ori, (int32_t *)target_matches[0],
-                      (int32_t *)target_nmatches[0], n_targets, target_matches, target_nmatches, pair_offset, rows_preset ? 1 : 0);
+                      (int32_t *)target_nmatches[0], n_targets, target_matches, target_nmatches, pair_offset,
+                      rows_preset == 2 ? 2 : (rows_preset ? 1 : 0));
 }
 
 extern "C" int orbgpu_search_for_triangulation_batch(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs, const int32_t *kf1,

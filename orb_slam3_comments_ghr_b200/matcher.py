@@ -521,7 +521,7 @@ class ORBmatcher:
 
     # fused search + all-gather: rows / counts of this rank's pairs stored into every rank's result buffers (peer memory)
     def SearchForTriangulation_peers_dev(self, kfs: DeviceKfSet, n_pairs, kf1_ptr, kf2_ptr, ep_ptr, f12_ptr, target_matches, target_nmatches,
-                                         pair_offset: int, rows_preset: bool = True, bCoarse=False):
+                                         pair_offset: int, rows_preset=True, bCoarse=False):
         vp = C.c_void_p
         n = len(target_matches)
         tm = (C.c_void_p * n)(*[int(x) for x in target_matches])

@@ -28,12 +28,16 @@ hr = symm_mem.rendezvous(rows, dist.group.WORLD.group_name)
 hc = symm_mem.rendezvous(cnts, dist.group.WORLD.group_name)
 rows.fill_(-1); cnts.fill_(0)
 hr.barrier(channel=0)
-def step(k):
+MODE = int(os.environ.get("PEER_MODE", "2"))   # 2: whole rows copied to the peers (default); 1: preset + individual match stores
+order = [rank] + [r for r in range(world) if r != rank]  # target 0 = this rank's own buffer
+def targets(b):
+    return [hr.buffer_ptrs[r] + b * P_total * NF * 4 for r in order], [hc.buffer_ptrs[r] + b * P_total * 4 for r in order]
+def step(k, mm=None):
     b = k & 1
-    tm = [p + b * P_total * NF * 4 for p in hr.buffer_ptrs]
-    tn = [p + b * P_total * 4 for p in hc.buffer_ptrs]
-    m.SearchForTriangulation_peers_dev(ks, P, kf1[lo:hi].data_ptr(), kf2[lo:hi].data_ptr(), ep[lo:hi].data_ptr(), f12[lo:hi].data_ptr(), tm, tn, lo, True)
-    rows[b ^ 1].fill_(-1)          # my copy of the NEXT step's buffer; every rank has done this when the barrier releases
+    tm, tn = targets(b)
+    (mm or m).SearchForTriangulation_peers_dev(ks, P, kf1[lo:hi].data_ptr(), kf2[lo:hi].data_ptr(), ep[lo:hi].data_ptr(), f12[lo:hi].data_ptr(), tm, tn, lo, MODE)
+    if MODE == 1:
+        rows[b ^ 1].fill_(-1)      # my copy of the NEXT step's buffer; every rank has done this when the barrier releases
     hr.barrier(channel=0)
     return rows[b].view(P_total, NF), cnts[b]
 ok = True
@@ -71,12 +75,7 @@ try:
         gctx = matcher.Context(lr, stream=side.cuda_stream)
         gm = matcher.ORBmatcher(0.6, False, gctx)
         def gstep(k):
-            b = k & 1
-            tm = [p + b * P_total * NF * 4 for p in hr.buffer_ptrs]
-            tn = [p + b * P_total * 4 for p in hc.buffer_ptrs]
-            gm.SearchForTriangulation_peers_dev(ks, P, kf1[lo:hi].data_ptr(), kf2[lo:hi].data_ptr(), ep[lo:hi].data_ptr(), f12[lo:hi].data_ptr(), tm, tn, lo, True)
-            rows[b ^ 1].fill_(-1)
-            hr.barrier(channel=0)
+            step(k, gm)
         gstep(0); gstep(1)
         side.synchronize()
         g = torch.cuda.CUDAGraph()
@@ -90,7 +89,7 @@ try:
 except Exception as e:
     print(f"rank {rank}: graph capture failed: {e!r}", flush=True)
 if rank == 0:
-    print(f"world {world}: fused peer-store all-gather {'OK' if ok else 'FAILED'}; step {t_fused*1e3:.1f} us fused vs {t_nccl*1e3:.1f} us kernel + NCCL all-gather "
+    print(f"world {world} mode {MODE}: fused peer-store all-gather {'OK' if ok else 'FAILED'}; step {t_fused*1e3:.1f} us fused vs {t_nccl*1e3:.1f} us kernel + NCCL all-gather "
           f"({P_total / t_fused / 1e3:.2f} vs {P_total / t_nccl / 1e3:.2f} M pairs/s); fused in a CUDA graph {t_fused_g*1e3:.1f} us "
           f"({P_total / t_fused_g / 1e3:.2f} M pairs/s)", flush=True)
 dist.barrier(); dist.destroy_process_group()

@@ -493,8 +493,8 @@ def test_triangulation_multi_target_output(ctx, M):
     P_total, NF, lo, hi = 300, 900, 100, 260
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     kf1, kf2, ep, f12 = t(tc.kf1[lo:hi]), t(tc.kf2[lo:hi]), t(tc.ep[lo:hi]), t(tc.f12[lo:hi])
-    for preset in (True, False):
-        rows = [torch.full((P_total, NF), -1 if preset else 7, dtype=torch.int32, device=dev) for _ in range(2)]
+    for preset in (True, False, 2):
+        rows = [torch.full((P_total, NF), -1 if preset is True else 7, dtype=torch.int32, device=dev) for _ in range(2)]
         cnts = [torch.full((P_total,), -5, dtype=torch.int32, device=dev) for _ in range(2)]
         torch.cuda.synchronize()
         mm.SearchForTriangulation_peers_dev(ks, hi - lo, kf1.data_ptr(), kf2.data_ptr(), ep.data_ptr(), f12.data_ptr(),
@@ -502,7 +502,8 @@ def test_triangulation_multi_target_output(ctx, M):
         ctx.synchronize()
         for r, c in zip(rows, cnts):
             assert np.array_equal(r[lo:hi].cpu().numpy(), m[lo:hi]) and np.array_equal(c[lo:hi].cpu().numpy(), nm[lo:hi])
-            assert (r[:lo] == (-1 if preset else 7)).all() and (r[hi:] == (-1 if preset else 7)).all()  # other ranks' rows untouched
+            other = -1 if preset is True else 7
+            assert (r[:lo] == other).all() and (r[hi:] == other).all()  # other ranks' rows untouched
             assert (c[:lo] == -5).all() and (c[hi:] == -5).all()
 
 
