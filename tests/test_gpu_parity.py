@@ -535,3 +535,44 @@ def test_kfset_transform_then_triangulation(ctx, M, oracle, levelsup):
     enm, em = oracle.search_for_triangulation_batch(tc.kfs, tc.kf1, tc.kf2, tc.ep, tc.f12, 0, 1, 0, n_threads=os.cpu_count() or 1)
     assert np.array_equal(nm, enm) and np.array_equal(m, em) and enm.sum() > 100
     tc.kfs.node_id = host_nodes
+
+
+def test_knn2_full_size_engines_agree(ctx, M):
+    """BASELINE.json config C5 at full size (262144 queries x 4194304 database rows, 1.1e12 comparisons): the tensor-core engine
+    (tcgen05, +-1 fp8 contraction) and the LOP3+POPC engine return identical best index / best / second / match vectors, and the
+    size-independent properties hold (planted queries find their source or an equal-distance earlier row, distances recompute)."""
+    import torch
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev); g.manual_seed(4242)
+    nq, nd = 262144, 4194304
+    db = torch.randint(0, 256, (nd, 32), dtype=torch.uint8, device=dev, generator=g)
+    q = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, device=dev, generator=g)
+    n_pl = nq // 10
+    who = torch.randperm(nq, device=dev, generator=g)[:n_pl]
+    src = torch.randint(0, nd, (n_pl,), device=dev, generator=g)
+    mask = torch.randint(0, 256, (n_pl, 32), dtype=torch.uint8, device=dev, generator=g)
+    for _ in range(3):
+        mask &= torch.randint(0, 256, (n_pl, 32), dtype=torch.uint8, device=dev, generator=g)
+    q[who] = db[src] ^ mask
+    mm = M.ORBmatcher(0.8, True, ctx)
+    ddb = ctx.database_from_device(db.data_ptr(), nd, keepalive=db)
+    res = {}
+    for eng in (4, 1):
+        ctx.set_knn_engine(eng)
+        out = torch.empty((4, nq), dtype=torch.int32, device=dev)
+        mm.SearchByNN_dev(ddb, nq, q.data_ptr(), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), 50)
+        ctx.synchronize()
+        res[eng] = out
+    ctx.set_knn_engine(0)
+    assert torch.equal(res[4], res[1])
+    bi, bd, sd, mt = [x.long() for x in res[4]]
+    assert bool((bd <= sd).all())
+    lut = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int32, device=dev)
+    got_d = lut[(q ^ db[bi]).long()].sum(dim=1)
+    assert torch.equal(got_d.long(), bd)
+    true_d = lut[(q[who] ^ db[src]).long()].sum(dim=1).long()
+    assert bool((bd[who] <= true_d).all())
+    assert float((bi[who] == src).float().mean()) > 0.999
+    acc = (bd <= 50) & (bd.float() < 0.8 * sd.float())
+    assert torch.equal(mt >= 0, acc) and torch.equal(mt[acc], bi[acc])
+    assert int(acc.sum()) >= int(0.95 * n_pl)
