@@ -246,7 +246,8 @@ def test_triangulation_golden(ctx, M, check_ori, engine):
 
 @pytest.mark.parametrize("engine", [1, 2])
 @pytest.mark.parametrize("seed,n_pairs,n_feat,coarse,ori", [(501, 6, 1500, 0, 0), (502, 6, 1500, 0, 1), (503, 6, 1500, 1, 1), (504, 96, 2000, 0, 0), (505, 3, 64, 0, 1),
-                                                            (506, 700, 500, 0, 0), (507, 450, 300, 0, 1), (508, 1, 2000, 0, 0)])
+                                                            (506, 700, 500, 0, 0), (507, 450, 300, 0, 1), (508, 1, 2000, 0, 0),
+                                                            (509, 40, 777, 0, 1), (510, 9, 1001, 0, 0), (511, 300, 2, 1, 0)])
 def test_triangulation_oracle(ctx, M, oracle, seed, n_pairs, n_feat, coarse, ori, engine):
     tc = synth.fill_geometry(synth.make_triangulation_case(seed, n_pairs=n_pairs, n_feat=n_feat))
     ks = ctx.upload_kfset(tc.kfs)
