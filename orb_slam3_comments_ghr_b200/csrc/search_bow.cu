@@ -13,7 +13,7 @@
 namespace {
 
 constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
-constexpr int BOW_MAX_WARPS = 8;
+constexpr int BOW_MAX_WARPS = 32;
 
 // MODE 0: KF <-> F   (match indexed by F feature, value = KF feature)
 // MODE 1: KF1 <-> KF2 (match indexed by KF1 feature, value = KF2 feature)
@@ -21,8 +21,12 @@ template <int MODE>
 __global__ void bow_match_kernel(FrameView kf, FrameView f, const uint8_t *__restrict__ kf_valid,
                                  const uint8_t *__restrict__ f_valid, float nnratio, int check_ori, int32_t *match,
                                  uint8_t *matched2, int32_t *__restrict__ bin_of, int *__restrict__ hist, int *__restrict__ nmatches,
-                                 unsigned long long *__restrict__ counters)
+                                 unsigned long long *__restrict__ counters, int stage_cap)
 {
+    // optional staging (dynamic shared memory, stage_cap descriptors): when the partner node fits, its descriptors and
+    // "already matched" flags are copied once and every keyframe feature of the node is replayed against shared memory --
+    // a large node (e.g. the single root bucket of levelsup >= L) is otherwise one global round trip per keyframe feature
+    extern __shared__ uint4 bow_smem[];
     __shared__ uint32_t wm1[BOW_MAX_WARPS], wm2[BOW_MAX_WARPS];
     __shared__ int s_b;
     const int a = blockIdx.x;
@@ -41,32 +45,69 @@ __global__ void bow_match_kernel(FrameView kf, FrameView f, const uint8_t *__res
     if (b < 0) return;
     const int s1 = kf.fv_offsets[a], e1 = kf.fv_offsets[a + 1];
     const int s2 = f.fv_offsets[b], n2 = f.fv_offsets[b + 1] - s2;
-    int my_matches = 0;
-    unsigned long long ncmp = 0;
-    for (int iKF = s1; iKF < e1; iKF++) {
-        const int idx1 = (int)kf.fv_features[iKF];
-        if (!kf_valid[idx1]) continue; // :311-315 / :937-941 (block-uniform)
-        const uint4 qa = kf.desc[2 * idx1], qb = kf.desc[2 * idx1 + 1];
-        uint32_t b1 = KEY_NONE, b2 = KEY_NONE;
+    const bool staged = n2 <= stage_cap && (e1 - s1) >= 4; // worth it only when several keyframe features share the copy
+    int *sIdx2 = (int *)(bow_smem + 2 * (size_t)stage_cap);   // [stage_cap] feature id of the partner's entry
+    float *sAng2 = (float *)(sIdx2 + stage_cap);               // [stage_cap] its angle
+    uint8_t *sTaken = (uint8_t *)(sAng2 + stage_cap);          // [stage_cap] already matched / not eligible
+    if (staged) {
         for (int p = t; p < n2; p += blockDim.x) {
             const int idx2 = (int)f.fv_features[s2 + p];
-            if (MODE == 0) {
-                if (match[idx2] >= 0) continue; // :335
-            } else {
-                if (matched2[idx2] || !f_valid[idx2]) continue; // :962-966
+            bow_smem[2 * p] = f.desc[2 * idx2];
+            bow_smem[2 * p + 1] = f.desc[2 * idx2 + 1];
+            sIdx2[p] = idx2;
+            sAng2[p] = f.angle[idx2];
+            sTaken[p] = (MODE == 0) ? (uint8_t)(match[idx2] >= 0) : (uint8_t)(matched2[idx2] || !f_valid[idx2]);
+        }
+        __syncthreads();
+    }
+    int my_matches = 0;
+    unsigned long long ncmp = 0;
+    // the keyframe feature of the NEXT iteration is fetched while the current one is scanned (three dependent global loads)
+    int n_idx1 = (int)kf.fv_features[s1];
+    bool n_valid = kf_valid[n_idx1] != 0;
+    uint4 n_qa = kf.desc[2 * n_idx1], n_qb = kf.desc[2 * n_idx1 + 1];
+    float n_ang = check_ori ? kf.angle[n_idx1] : 0.f;
+    for (int iKF = s1; iKF < e1; iKF++) {
+        const int idx1 = n_idx1;
+        const bool valid1 = n_valid;
+        const uint4 qa = n_qa, qb = n_qb;
+        const float ang1 = n_ang;
+        if (iKF + 1 < e1) {
+            n_idx1 = (int)kf.fv_features[iKF + 1];
+            n_valid = kf_valid[n_idx1] != 0;
+            n_qa = kf.desc[2 * n_idx1]; n_qb = kf.desc[2 * n_idx1 + 1];
+            if (check_ori) n_ang = kf.angle[n_idx1];
+        }
+        if (!valid1) continue; // :311-315 / :937-941 (block-uniform)
+        uint32_t b1 = KEY_NONE, b2 = KEY_NONE;
+        if (staged) {
+            for (int p = t; p < n2; p += blockDim.x) {
+                if (sTaken[p]) continue; // :335 / :962-966
+                const uint32_t d = (uint32_t)ham256(qa, qb, bow_smem[2 * p], bow_smem[2 * p + 1]);
+                top2_push(b1, b2, (d << 20) | (uint32_t)p);
+                ncmp++;
             }
-            const uint32_t d = (uint32_t)ham256(qa, qb, f.desc[2 * idx2], f.desc[2 * idx2 + 1]);
-            top2_push(b1, b2, (d << 20) | (uint32_t)p);
-            ncmp++;
+        } else {
+            for (int p = t; p < n2; p += blockDim.x) {
+                const int idx2 = (int)f.fv_features[s2 + p];
+                if (MODE == 0) {
+                    if (match[idx2] >= 0) continue; // :335
+                } else {
+                    if (matched2[idx2] || !f_valid[idx2]) continue; // :962-966
+                }
+                const uint32_t d = (uint32_t)ham256(qa, qb, f.desc[2 * idx2], f.desc[2 * idx2 + 1]);
+                top2_push(b1, b2, (d << 20) | (uint32_t)p);
+                ncmp++;
+            }
         }
         uint32_t m1, m2;
         warp_top2(b1, b2, m1, m2);
         if (nwarps > 1) {
             if (lane == 0) { wm1[warp] = m1; wm2[warp] = m2; }
             __syncthreads();
-            if (t == 0) {
-                m1 = KEY_NONE; m2 = KEY_NONE;
-                for (int w = 0; w < nwarps; w++) { top2_push(m1, m2, wm1[w]); top2_push(m1, m2, wm2[w]); }
+            if (warp == 0) { // the per-warp pairs are merged by one warp-wide top-2 (keys are unique or KEY_NONE)
+                const uint32_t c1 = lane < nwarps ? wm1[lane] : KEY_NONE, c2 = lane < nwarps ? wm2[lane] : KEY_NONE;
+                warp_top2(c1, c2, m1, m2);
             }
         }
         if (t == 0 && m1 != KEY_NONE) {
@@ -74,7 +115,7 @@ __global__ void bow_match_kernel(FrameView kf, FrameView f, const uint8_t *__res
             const int bestDist2 = (m2 == KEY_NONE) ? 256 : (int)(m2 >> 20);
             const bool th_ok = (MODE == 0) ? (bestDist1 <= ORBGPU_TH_LOW) : (bestDist1 < ORBGPU_TH_LOW); // :392 / :985
             if (th_ok && (float)bestDist1 < __fmul_rn(nnratio, (float)bestDist2)) {                     // :395 / :987
-                const int best2 = (int)f.fv_features[s2 + (m1 & 0xFFFFF)];
+                const int best2 = staged ? sIdx2[m1 & 0xFFFFF] : (int)f.fv_features[s2 + (m1 & 0xFFFFF)];
                 const int slot = (MODE == 0) ? best2 : idx1;
                 if (MODE == 0) {
                     match[best2] = idx1; // vpMapPointMatches[bestIdxF] = pMP (of KF feature idx1)
@@ -82,8 +123,9 @@ __global__ void bow_match_kernel(FrameView kf, FrameView f, const uint8_t *__res
                     match[idx1] = best2; // vpMatches12[idx1] = vpMapPoints2[bestIdx2]
                     matched2[best2] = 1;
                 }
+                if (staged) sTaken[m1 & 0xFFFFF] = 1;
                 if (check_ori) { // :405-419 / :992-1002
-                    const int bin = rot_bin(kf.angle[idx1], f.angle[best2]);
+                    const int bin = rot_bin(ang1, staged ? sAng2[m1 & 0xFFFFF] : f.angle[best2]);
                     if (bin >= 0 && bin < ORBGPU_HISTO_LENGTH) {
                         atomicAdd(&hist[bin], 1);
                         bin_of[slot] = bin;
@@ -144,14 +186,22 @@ int run_bow(orbgpu_ctx *ctx, int mode, const orbgpu_frame *kf, const orbgpu_fram
     if (kf->n) CU_TRY(cudaMemcpyAsync(d_kfv, kf_valid, kf->n, cudaMemcpyHostToDevice, ctx->stream));
     if (mode == 1 && f->n) CU_TRY(cudaMemcpyAsync(d_fv, f_valid, f->n, cudaMemcpyHostToDevice, ctx->stream));
     if (kf->fv_n_nodes > 0 && f->fv_n_nodes > 0) {
-        const int threads = f->fv_max_node <= 32 ? 32 : (f->fv_max_node <= 512 ? 128 : 256);
+        const int threads = f->fv_max_node <= 32 ? 32 : (f->fv_max_node <= 512 ? 128 : (f->fv_max_node <= 1024 ? 256 : 1024));
+        // staging capacity: the largest partner node, as far as shared memory goes (33 B per descriptor)
+        int stage_cap = f->fv_max_node > 64 ? f->fv_max_node : 0;
+        if (stage_cap > 4800) stage_cap = 4800;
+        stage_cap = (stage_cap + 15) & ~15;
+        const size_t smem = (size_t)stage_cap * 41; // 32 B descriptor + feature id + angle + flag
         const FrameView vk = frame_view(kf), vf = frame_view(f);
-        if (mode == 0)
-            bow_match_kernel<0><<<kf->fv_n_nodes, threads, 0, ctx->stream>>>(vk, vf, d_kfv, d_fv, nnratio, check_ori, d_match, d_m2, d_bin,
-                                                                            d_hist, d_nm, ctx->d_counters);
-        else
-            bow_match_kernel<1><<<kf->fv_n_nodes, threads, 0, ctx->stream>>>(vk, vf, d_kfv, d_fv, nnratio, check_ori, d_match, d_m2, d_bin,
-                                                                            d_hist, d_nm, ctx->d_counters);
+        if (mode == 0) {
+            CU_TRY(cudaFuncSetAttribute(bow_match_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 1024 ? smem : 1024)));
+            bow_match_kernel<0><<<kf->fv_n_nodes, threads, smem, ctx->stream>>>(vk, vf, d_kfv, d_fv, nnratio, check_ori, d_match, d_m2, d_bin,
+                                                                               d_hist, d_nm, ctx->d_counters, stage_cap);
+        } else {
+            CU_TRY(cudaFuncSetAttribute(bow_match_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 1024 ? smem : 1024)));
+            bow_match_kernel<1><<<kf->fv_n_nodes, threads, smem, ctx->stream>>>(vk, vf, d_kfv, d_fv, nnratio, check_ori, d_match, d_m2, d_bin,
+                                                                               d_hist, d_nm, ctx->d_counters, stage_cap);
+        }
         LAUNCH_COUNT(ctx);
         bow_cull_kernel<<<1, 256, 0, ctx->stream>>>(n_out, check_ori, d_match, d_bin, d_hist, d_nm);
         LAUNCH_COUNT(ctx);
