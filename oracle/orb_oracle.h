@@ -12,12 +12,12 @@
  * tests/test_oracle_vs_ref.py) and against the golden vectors generated from that build
  * (tests/golden/, scripts/make_golden.py).
  *
- * PARITY UNPINNED for two functions only: oracle_stereo_coarse_match (Frame.cc:1139-1216) and
- * oracle_compute_distinctive_descriptors (MapPoint.cc:444-535).  Frame.cc / MapPoint.cc need OpenCV, Eigen, Boost and
- * g2o headers that do not exist in this image, so the reference cannot be compiled for them; the restatements are
- * cross-checked against an independent numpy evaluation (tests/test_oracle_golden.py) instead.  Everything else --
- * including oracle_search_projected (the self-projecting overloads, via the harnesses of ref_adapter.cc) and
- * oracle_bow_score_l1 (ScoringObject.cpp) -- is pinned on the reference's own compiled code.
+ * PARITY UNPINNED for one function only: oracle_stereo_coarse_match (Frame.cc:1139-1216).  Frame.cc needs OpenCV image
+ * operations, Eigen, Boost and g2o headers that do not exist in this image, so the reference cannot be compiled for it; the
+ * restatement is cross-checked against an independent numpy evaluation (tests/test_oracle_golden.py) instead.  Everything
+ * else is pinned on the reference's own compiled code: oracle_search_projected (the self-projecting overloads, via the
+ * harnesses of ref_adapter.cc), oracle_bow_score_l1 (ScoringObject.cpp) and oracle_compute_distinctive_descriptors
+ * (src/MapPoint.cc compiled unmodified with its real include/MapPoint.h against shim_mp/, ref_mappoint_adapter.cc).
  *
  * The flat input structs are the ones of the product ABI (include/orbmatch_b200.h) so that
  * oracle and GPU consume byte-identical inputs.

@@ -338,6 +338,26 @@ class Reference:
         self.lib.ref_bow_score_l1(C.byref(s), qw.shape[0], _p(qw, u32p), _p(qv, f64p), _p(common, i32p), _p(scores, f64p))
         return common[:db.n_kf], scores[:db.n_kf]
 
+    @staticmethod
+    def mappoint_available() -> bool:
+        return os.path.exists(os.path.join(_HERE, "_ref", "libref_mappoint.so"))
+
+    def compute_distinctive_descriptors(self, offsets, desc, kf_bad=None):
+        """the reference's own MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc with the real include/MapPoint.h,
+        oracle/_ref/libref_mappoint.so): per map point the position of the kept descriptor (-1: none) and the descriptor."""
+        path = os.path.join(_HERE, "_ref", "libref_mappoint.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path}: run `make -C oracle ref` where /root/reference is mounted")
+        L = C.CDLL(path)
+        L.ref_compute_distinctive.argtypes = [C.c_int32, i32p, u8p, u8p, i32p, u8p]
+        off, d = as_i32(offsets), as_u8(desc)
+        n = off.shape[0] - 1
+        bad = as_u8(kf_bad) if kf_bad is not None else None
+        bi = np.full(max(n, 1), -1, dtype=np.int32)
+        out = np.zeros((max(n, 1), 32), dtype=np.uint8)
+        L.ref_compute_distinctive(n, _p(off, i32p), _p(d, u8p), _p(bad, u8p), _p(bi, i32p), _p(out, u8p))
+        return bi[:n], out[:n]
+
     # the reference's self-projecting overloads on degenerate geometry (see ref_adapter.cc): everything from the window on
     def projected_cur_last(self, cur: HostFrame, pts: HostProjPoints, th, mode, mbf, kp_locked, check_ori):
         own = np.full(max(cur.n, 1), -1, dtype=np.int32)

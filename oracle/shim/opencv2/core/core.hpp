@@ -79,6 +79,7 @@ namespace cv
             std::memcpy(m.data, data, (size_t)rows * cols * esz_);
             return m;
         }
+        void copyTo(Mat &dst) const { dst = clone(); }
         Mat row(int i) const
         {
             Mat m;

@@ -111,8 +111,8 @@ def test_search_projected(oracle, name):
 
 
 def test_compute_distinctive_descriptors_vs_numpy(oracle):
-    """8(f) rank 4: MapPoint.cc does not compile here, so the restatement is cross-checked with an independent numpy evaluation of
-    MapPoint.cc:487-515 (all-pairs popcount, np.sort, index int(0.5*(N-1)), first minimum)."""
+    """8(f) rank 4: besides the pin on the reference's MapPoint.cc (test_oracle_vs_ref.py), an independent numpy evaluation of
+    MapPoint.cc:487-515 (all-pairs popcount, np.sort, index int(0.5*(N-1)), first minimum) that also runs where oracle/_ref is absent."""
     offs, desc = synth.make_distinctive_case(131, n_mp=400, max_obs=30)
     bi, bm = oracle.compute_distinctive_descriptors(offs, desc)
     bits = np.unpackbits(desc, axis=1).astype(np.int32)

@@ -198,3 +198,50 @@ def test_projection_stereo(oracle, reference, seed, th):
     a = oracle.search_by_projection_local(c.frame, c.mps, th, 0, 40.0, c.nnratio, c.kp_prior_obs, c.kp_mp)
     b = reference.search_by_projection_local(c.frame, c.mps, th, 0, 40.0, c.nnratio, c.kp_prior_obs, c.kp_mp)
     assert a[0] == b[0] and np.array_equal(a[1], b[1]) and a[0] > 100
+
+
+def _clip_long_lists(offs, desc, cap):
+    """the reference keeps float Distances[N][N] on the stack (MapPoint.cc:492): lists are clipped to what 8 MB holds"""
+    keep, new_offs = [], [0]
+    for p in range(offs.shape[0] - 1):
+        s, e = int(offs[p]), min(int(offs[p + 1]), int(offs[p]) + cap)
+        keep.append(np.arange(s, e))
+        new_offs.append(new_offs[-1] + e - s)
+    return np.array(new_offs, dtype=np.int32), np.ascontiguousarray(desc[np.concatenate(keep)])
+
+
+@pytest.mark.parametrize("seed", [131, 132, 133])
+def test_compute_distinctive_descriptors(oracle, reference, seed):
+    """8(f) rank 4: the restatement against the reference's own MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc compiled
+    unmodified with its real MapPoint.h, oracle/_ref/libref_mappoint.so) -- same kept descriptor, same index among equal
+    medians (first), nothing selected for an empty list"""
+    if not reference.mappoint_available():
+        pytest.skip("oracle/_ref/libref_mappoint.so not built")
+    offs, desc = _clip_long_lists(*synth.make_distinctive_case(seed, n_mp=600, max_obs=40), cap=900)
+    ei, ed = reference.compute_distinctive_descriptors(offs, desc)
+    gi, gm = oracle.compute_distinctive_descriptors(offs, desc)
+    assert np.array_equal(gi, ei)
+    sel = gi >= 0
+    assert sel.sum() > 500 and (~sel).any()
+    assert np.array_equal(desc[offs[:-1][sel] + gi[sel]], ed[sel])
+    assert (np.diff(offs) > 800).any()  # the long list went through both
+
+
+def test_compute_distinctive_descriptors_bad_keyframes(oracle, reference):
+    """observations of bad key frames are skipped (:471): the reference on the full lists == the restatement on the filtered ones"""
+    if not reference.mappoint_available():
+        pytest.skip("oracle/_ref/libref_mappoint.so not built")
+    offs, desc = _clip_long_lists(*synth.make_distinctive_case(134, n_mp=300, max_obs=25), cap=200)
+    rng = np.random.default_rng(7)
+    bad = (rng.random(desc.shape[0]) < 0.3).astype(np.uint8)
+    bad[offs[5]:offs[6]] = 1  # a point whose observations are all bad keeps its (empty) descriptor
+    ei, ed = reference.compute_distinctive_descriptors(offs, desc, kf_bad=bad)
+    good = np.flatnonzero(bad == 0)
+    f_offs = np.searchsorted(good, offs).astype(np.int32)
+    gi, _ = oracle.compute_distinctive_descriptors(f_offs, np.ascontiguousarray(desc[good]))
+    for p in range(offs.shape[0] - 1):
+        if gi[p] < 0:
+            assert ei[p] == -1
+        else:
+            assert good[f_offs[p] + gi[p]] == offs[p] + ei[p]
+    assert ei[5] == -1
