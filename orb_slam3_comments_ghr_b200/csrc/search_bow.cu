@@ -15,13 +15,33 @@ namespace {
 constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
 constexpr int BOW_MAX_WARPS = 32;
 
+// Big node pairs (e.g. the single root bucket when levelsup >= L, which is what Frame.cc:1008's levelsup = 4 gives with an
+// L = 4 vocabulary: 1200 x 2000 features in one node) are not replayed feature by feature.  The "partner already matched"
+// rule (:335 / :962) is solved as a fixed point over LOCK TIMES, as in the projection searches: lock[p] = position of the
+// first keyframe feature that takes partner p.  Given the locks, every keyframe feature's outcome is independent (first two
+// entries of its sorted candidate list that are not locked by an earlier feature); the outcomes give new locks; iterate
+// until nothing changes.  The outcome of feature i depends only on features before i, so by induction the k-th iteration
+// has the first k features right and the fixed point is the sequential result -- in practice a handful of iterations.
+constexpr int BOW_BIG_N1 = 32, BOW_BIG_N2 = 256; // node pair taken by the fixed-point path: n1 >= .. && n2 >= ..
+constexpr int BOW_LIST_K = 8;                    // sorted candidate list per keyframe feature
+__device__ __forceinline__ bool bow_big(int n1, int n2) { return n1 >= BOW_BIG_N1 && n2 >= BOW_BIG_N2; }
+__device__ __forceinline__ int bow_partner(const FrameView &f, uint32_t nid)
+{ // lower_bound merge-join (:292-467) == look the node id up in the other sorted list
+    int lo = 0, hi = f.fv_n_nodes;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (f.fv_node_ids[mid] < nid) lo = mid + 1; else hi = mid;
+    }
+    return (lo < f.fv_n_nodes && f.fv_node_ids[lo] == nid) ? lo : -1;
+}
+
 // MODE 0: KF <-> F   (match indexed by F feature, value = KF feature)
 // MODE 1: KF1 <-> KF2 (match indexed by KF1 feature, value = KF2 feature)
 template <int MODE>
 __global__ void bow_match_kernel(FrameView kf, FrameView f, const uint8_t *__restrict__ kf_valid,
                                  const uint8_t *__restrict__ f_valid, float nnratio, int check_ori, int32_t *match,
                                  uint8_t *matched2, int32_t *__restrict__ bin_of, int *__restrict__ hist, int *__restrict__ nmatches,
-                                 unsigned long long *__restrict__ counters, int stage_cap)
+                                 unsigned long long *__restrict__ counters, int stage_cap, int skip_big)
 {
     // optional staging (dynamic shared memory, stage_cap descriptors): when the partner node fits, its descriptors and
     // "already matched" flags are copied once and every keyframe feature of the node is replayed against shared memory --
@@ -31,20 +51,13 @@ __global__ void bow_match_kernel(FrameView kf, FrameView f, const uint8_t *__res
     __shared__ int s_b;
     const int a = blockIdx.x;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
-    if (t == 0) { // lower_bound merge-join (:292-467) == look the node id up in the other sorted list
-        const uint32_t nid = kf.fv_node_ids[a];
-        int lo = 0, hi = f.fv_n_nodes;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (f.fv_node_ids[mid] < nid) lo = mid + 1; else hi = mid;
-        }
-        s_b = (lo < f.fv_n_nodes && f.fv_node_ids[lo] == nid) ? lo : -1;
-    }
+    if (t == 0) s_b = bow_partner(f, kf.fv_node_ids[a]);
     __syncthreads();
     const int b = s_b;
     if (b < 0) return;
     const int s1 = kf.fv_offsets[a], e1 = kf.fv_offsets[a + 1];
     const int s2 = f.fv_offsets[b], n2 = f.fv_offsets[b + 1] - s2;
+    if (skip_big && bow_big(e1 - s1, n2)) return; // bow_big_lists_kernel + bow_big_resolve_kernel take this node pair
     const bool staged = n2 <= stage_cap && (e1 - s1) >= 4; // worth it only when several keyframe features share the copy
     int *sIdx2 = (int *)(bow_smem + 2 * (size_t)stage_cap);   // [stage_cap] feature id of the partner's entry
     float *sAng2 = (float *)(sIdx2 + stage_cap);               // [stage_cap] its angle
@@ -141,6 +154,215 @@ __global__ void bow_match_kernel(FrameView kf, FrameView f, const uint8_t *__res
     if (t == 0 && my_matches) atomicAdd(nmatches, my_matches);
 }
 
+// ---- fixed-point path, step 1: one warp per keyframe feature of a big node pair lists its BOW_LIST_K best eligible partners,
+// ascending in (distance, position).  lists[q][k]: keys (dist << 20 | position in the partner node), KEY_NONE padded;
+// meta[q] = m | more << 8: the first m entries are exactly the m smallest keys, `more` = eligible partners exist beyond them.
+template <int MODE>
+__global__ void bow_big_lists_kernel(FrameView kf, FrameView f, const uint8_t *__restrict__ kf_valid, const uint8_t *__restrict__ f_valid,
+                                     uint32_t *__restrict__ lists, uint32_t *__restrict__ meta)
+{
+    const int q = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5); // position in the keyframe's FeatureVector
+    const int lane = threadIdx.x & 31;
+    if (q >= kf.fv_offsets[kf.fv_n_nodes]) return;
+    int lo = 0, hi = kf.fv_n_nodes - 1; // node of position q: last a with fv_offsets[a] <= q
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (kf.fv_offsets[mid] <= q) lo = mid; else hi = mid - 1;
+    }
+    const int a = lo;
+    const int b = bow_partner(f, kf.fv_node_ids[a]);
+    if (b < 0) return;
+    const int s2 = f.fv_offsets[b], n2 = f.fv_offsets[b + 1] - s2;
+    if (!bow_big(kf.fv_offsets[a + 1] - kf.fv_offsets[a], n2)) return;
+    const int idx1 = (int)kf.fv_features[q];
+    if (!kf_valid[idx1]) return; // :311-315 / :937-941
+    const uint4 qa = kf.desc[2 * idx1], qb = kf.desc[2 * idx1 + 1];
+    uint32_t b1 = KEY_NONE, b2 = KEY_NONE;
+    int cnt = 0;
+    for (int p = lane; p < n2; p += 32) {
+        const int idx2 = (int)f.fv_features[s2 + p];
+        if (MODE == 1 && !f_valid[idx2]) continue; // :962-966 (nothing is matched yet: :335 only bites through the locks)
+        const uint32_t d = (uint32_t)ham256(qa, qb, f.desc[2 * idx2], f.desc[2 * idx2 + 1]);
+        top2_push(b1, b2, (d << 20) | (uint32_t)p);
+        cnt++;
+    }
+    // pop the lanes' pairs in ascending order; the prefix stays exact until a lane that dropped keys runs empty
+    uint32_t out = KEY_NONE;
+    int m = 0, popped = 0;
+    for (int k = 0; k < BOW_LIST_K; k++) {
+        const uint32_t head = popped == 0 ? b1 : (popped == 1 ? b2 : KEY_NONE);
+        const uint32_t mn = __reduce_min_sync(FULL_MASK, head);
+        if (mn == KEY_NONE) break;
+        if (lane == k) out = mn;
+        m++;
+        if (head == mn) popped++;
+        if (__any_sync(FULL_MASK, head == mn && popped == 2 && cnt > 2)) break;
+    }
+    int total = cnt;
+    for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(FULL_MASK, total, o);
+    if (lane < BOW_LIST_K) lists[(size_t)q * BOW_LIST_K + lane] = out;
+    if (lane == 0) meta[q] = (uint32_t)m | ((total > m ? 1u : 0u) << 8);
+}
+
+// ---- step 2: one CTA per big node pair iterates outcomes <-> lock times to the fixed point, then writes the matches
+template <int MODE>
+__global__ void bow_big_resolve_kernel(FrameView kf, FrameView f, const uint8_t *__restrict__ kf_valid, const uint8_t *__restrict__ f_valid,
+                                       const uint32_t *__restrict__ lists, const uint32_t *__restrict__ meta, float nnratio, int check_ori,
+                                       int32_t *match, int32_t *__restrict__ bin_of, int *__restrict__ hist, int *__restrict__ nmatches,
+                                       unsigned long long *__restrict__ counters, int n1_cap, int n2_cap)
+{
+    extern __shared__ int big_smem[];
+    int *lock = big_smem;          // [n2_cap] position of the first keyframe feature that takes the partner
+    int *choice = lock + n2_cap;   // [n1_cap] partner taken by the feature, -1 none
+    int *queue = choice + n1_cap;  // [n1_cap] features whose list ran out: full rescan
+    __shared__ uint32_t wm1[BOW_MAX_WARPS], wm2[BOW_MAX_WARPS];
+    __shared__ int s_b, s_changed, s_nq, s_elig, s_carry, s_warp[BOW_MAX_WARPS];
+    __shared__ unsigned long long s_cmp;
+    const int a = blockIdx.x;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
+    if (t == 0) {
+        s_b = bow_partner(f, kf.fv_node_ids[a]);
+        s_elig = 0; s_carry = 0; s_cmp = 0;
+    }
+    __syncthreads();
+    const int b = s_b;
+    if (b < 0) return;
+    const int s1 = kf.fv_offsets[a], n1 = kf.fv_offsets[a + 1] - s1;
+    const int s2 = f.fv_offsets[b], n2 = f.fv_offsets[b + 1] - s2;
+    if (!bow_big(n1, n2)) return;
+    for (int p = t; p < n2; p += blockDim.x) lock[p] = INT_MAX;
+    for (int i = t; i < n1; i += blockDim.x) choice[i] = -2;
+    if (MODE == 1) { // partners that can be compared at all (:962-966)
+        int c = 0;
+        for (int p = t; p < n2; p += blockDim.x) c += f_valid[f.fv_features[s2 + p]] != 0;
+        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(FULL_MASK, c, o);
+        if (lane == 0 && c) atomicAdd(&s_elig, c);
+    }
+    __syncthreads();
+    const int n_elig = MODE == 1 ? s_elig : n2;
+
+    // accept test of :392-395 / :985-987 on the (best, second) keys
+    auto decide = [&](uint32_t k1, uint32_t k2) -> int {
+        if (k1 == KEY_NONE) return -1;
+        const int d1 = (int)(k1 >> 20), d2 = (k2 == KEY_NONE) ? 256 : (int)(k2 >> 20);
+        const bool th_ok = (MODE == 0) ? (d1 <= ORBGPU_TH_LOW) : (d1 < ORBGPU_TH_LOW);
+        return (th_ok && (float)d1 < __fmul_rn(nnratio, (float)d2)) ? (int)(k1 & 0xFFFFFu) : -1;
+    };
+
+    for (int iter = 0; iter <= n1 + 1; iter++) {
+        if (t == 0) { s_changed = 0; s_nq = 0; }
+        __syncthreads();
+        for (int i = t; i < n1; i += blockDim.x) {
+            const int idx1 = (int)kf.fv_features[s1 + i];
+            if (!kf_valid[idx1]) continue;
+            const uint32_t mt = meta[s1 + i];
+            const int m = (int)(mt & 0xFF);
+            uint32_t k1 = KEY_NONE, k2 = KEY_NONE;
+            for (int e = 0; e < m; e++) {
+                const uint32_t key = lists[(size_t)(s1 + i) * BOW_LIST_K + e];
+                if (lock[key & 0xFFFFFu] < i) continue; // taken by an earlier keyframe feature (:335 / :962)
+                if (k1 == KEY_NONE) k1 = key;
+                else { k2 = key; break; }
+            }
+            if (k2 == KEY_NONE && (mt >> 8)) { // the list does not reach the second free partner
+                queue[atomicAdd(&s_nq, 1)] = i;
+                continue;
+            }
+            const int c = decide(k1, k2);
+            if (c != choice[i]) { choice[i] = c; s_changed = 1; }
+        }
+        __syncthreads();
+        const int nq = s_nq;
+        for (int qi = 0; qi < nq; qi++) { // rare: block-wide scan of the whole partner node for one feature
+            const int i = queue[qi];
+            const int idx1 = (int)kf.fv_features[s1 + i];
+            const uint4 qa = kf.desc[2 * idx1], qb = kf.desc[2 * idx1 + 1];
+            uint32_t b1 = KEY_NONE, b2 = KEY_NONE;
+            for (int p = t; p < n2; p += blockDim.x) {
+                if (lock[p] < i) continue;
+                const int idx2 = (int)f.fv_features[s2 + p];
+                if (MODE == 1 && !f_valid[idx2]) continue;
+                const uint32_t d = (uint32_t)ham256(qa, qb, f.desc[2 * idx2], f.desc[2 * idx2 + 1]);
+                top2_push(b1, b2, (d << 20) | (uint32_t)p);
+            }
+            uint32_t m1, m2;
+            warp_top2(b1, b2, m1, m2);
+            if (lane == 0) { wm1[warp] = m1; wm2[warp] = m2; }
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t c1 = lane < nwarps ? wm1[lane] : KEY_NONE, c2 = lane < nwarps ? wm2[lane] : KEY_NONE;
+                warp_top2(c1, c2, m1, m2);
+                if (lane == 0) {
+                    const int c = decide(m1, m2);
+                    if (c != choice[i]) { choice[i] = c; s_changed = 1; }
+                }
+            }
+            __syncthreads();
+        }
+        if (!s_changed) break;
+        for (int p = t; p < n2; p += blockDim.x) lock[p] = INT_MAX;
+        __syncthreads();
+        for (int i = t; i < n1; i += blockDim.x)
+            if (choice[i] >= 0) atomicMin(&lock[choice[i]], i);
+        __syncthreads();
+    }
+
+    // ---- the fixed point: every accepted feature is the only holder of its partner.  Outputs as in the replay kernel;
+    // DescriptorDistance calls of the sequential scan: feature i compares the eligible partners not taken before it
+    int my_matches = 0;
+    unsigned long long ncmp = 0;
+    for (int base = 0; base < n1; base += blockDim.x) {
+        const int i = base + t;
+        int acc = 0, idx1 = -1;
+        bool valid = false;
+        if (i < n1) {
+            idx1 = (int)kf.fv_features[s1 + i];
+            valid = kf_valid[idx1] != 0;
+            acc = (valid && choice[i] >= 0) ? 1 : 0;
+        }
+        int incl = acc;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = lane < nwarps ? s_warp[lane] : 0;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(FULL_MASK, w, o);
+                if (lane >= o) w += u;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int before = s_carry + (warp ? s_warp[warp - 1] : 0) + incl - acc; // accepted features ahead of i
+        if (valid) ncmp += (unsigned long long)(n_elig - before);
+        if (acc) {
+            const int best2 = (int)f.fv_features[s2 + choice[i]];
+            const int slot = (MODE == 0) ? best2 : idx1;
+            if (MODE == 0) match[best2] = idx1; else match[idx1] = best2;
+            if (check_ori) { // :405-419 / :992-1002
+                const int bin = rot_bin(kf.angle[idx1], f.angle[best2]);
+                if (bin >= 0 && bin < ORBGPU_HISTO_LENGTH) {
+                    atomicAdd(&hist[bin], 1);
+                    bin_of[slot] = bin;
+                }
+            }
+            my_matches++;
+        }
+        __syncthreads();
+        if (t == 0) s_carry += s_warp[nwarps - 1];
+        __syncthreads();
+    }
+    for (int o = 16; o; o >>= 1) {
+        ncmp += __shfl_xor_sync(FULL_MASK, ncmp, o);
+        my_matches += __shfl_xor_sync(FULL_MASK, my_matches, o);
+    }
+    if (lane == 0 && ncmp) atomicAdd(&counters[0], ncmp);
+    if (lane == 0 && my_matches) atomicAdd(nmatches, my_matches);
+}
+
 __global__ void bow_cull_kernel(int n, int check_ori, int32_t *__restrict__ match, const int32_t *__restrict__ bin_of,
                                 const int *__restrict__ hist, int *__restrict__ nmatches)
 {
@@ -172,7 +394,10 @@ int run_bow(orbgpu_ctx *ctx, int mode, const orbgpu_frame *kf, const orbgpu_fram
     const int n_out = (mode == 0) ? f->n : kf->n; // size of the match vector
     if (n_out == 0) return ORBGPU_OK;
     const size_t ob = align256((size_t)n_out * 4);
-    rc = arena_reserve(ctx, 2 * ob + align256(kf->n + 1) + 2 * align256(f->n + 1) + 1024);
+    // fixed-point path for big node pairs (both sizes are known on the host as launch hints)
+    const bool big = kf->fv_max_node >= BOW_BIG_N1 && f->fv_max_node >= BOW_BIG_N2 && kf->fv_n_nodes > 0 && f->fv_n_nodes > 0;
+    rc = arena_reserve(ctx, 2 * ob + align256(kf->n + 1) + 2 * align256(f->n + 1) + 1024 +
+                                (big ? align256((size_t)kf->n * BOW_LIST_K * 4) + align256((size_t)kf->n * 4) : 0));
     if (rc) return rc;
     int32_t *d_match = (int32_t *)arena_take(ctx, (size_t)n_out * 4), *d_bin = (int32_t *)arena_take(ctx, (size_t)n_out * 4);
     uint8_t *d_kfv = (uint8_t *)arena_take(ctx, kf->n + 1), *d_fv = (uint8_t *)arena_take(ctx, f->n + 1),
@@ -196,13 +421,32 @@ int run_bow(orbgpu_ctx *ctx, int mode, const orbgpu_frame *kf, const orbgpu_fram
         if (mode == 0) {
             CU_TRY(cudaFuncSetAttribute(bow_match_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 1024 ? smem : 1024)));
             bow_match_kernel<0><<<kf->fv_n_nodes, threads, smem, ctx->stream>>>(vk, vf, d_kfv, d_fv, nnratio, check_ori, d_match, d_m2, d_bin,
-                                                                               d_hist, d_nm, ctx->d_counters, stage_cap);
+                                                                               d_hist, d_nm, ctx->d_counters, stage_cap, big ? 1 : 0);
         } else {
             CU_TRY(cudaFuncSetAttribute(bow_match_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 1024 ? smem : 1024)));
             bow_match_kernel<1><<<kf->fv_n_nodes, threads, smem, ctx->stream>>>(vk, vf, d_kfv, d_fv, nnratio, check_ori, d_match, d_m2, d_bin,
-                                                                               d_hist, d_nm, ctx->d_counters, stage_cap);
+                                                                               d_hist, d_nm, ctx->d_counters, stage_cap, big ? 1 : 0);
         }
         LAUNCH_COUNT(ctx);
+        if (big) {
+            uint32_t *d_lists = (uint32_t *)arena_take(ctx, (size_t)kf->n * BOW_LIST_K * 4), *d_meta = (uint32_t *)arena_take(ctx, (size_t)kf->n * 4);
+            const int n1_cap = kf->fv_max_node, n2_cap = f->fv_max_node;
+            const size_t smem_big = ((size_t)n2_cap + 2 * (size_t)n1_cap) * 4;
+            const int blocks = (int)(((size_t)kf->n * 32 + 255) / 256);
+            if (mode == 0) {
+                bow_big_lists_kernel<0><<<blocks, 256, 0, ctx->stream>>>(vk, vf, d_kfv, d_fv, d_lists, d_meta);
+                CU_TRY(cudaFuncSetAttribute(bow_big_resolve_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_big > 1024 ? smem_big : 1024)));
+                bow_big_resolve_kernel<0><<<kf->fv_n_nodes, 1024, smem_big, ctx->stream>>>(vk, vf, d_kfv, d_fv, d_lists, d_meta, nnratio, check_ori, d_match,
+                                                                                         d_bin, d_hist, d_nm, ctx->d_counters, n1_cap, n2_cap);
+            } else {
+                bow_big_lists_kernel<1><<<blocks, 256, 0, ctx->stream>>>(vk, vf, d_kfv, d_fv, d_lists, d_meta);
+                CU_TRY(cudaFuncSetAttribute(bow_big_resolve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_big > 1024 ? smem_big : 1024)));
+                bow_big_resolve_kernel<1><<<kf->fv_n_nodes, 1024, smem_big, ctx->stream>>>(vk, vf, d_kfv, d_fv, d_lists, d_meta, nnratio, check_ori, d_match,
+                                                                                         d_bin, d_hist, d_nm, ctx->d_counters, n1_cap, n2_cap);
+            }
+            LAUNCH_COUNT(ctx);
+            LAUNCH_COUNT(ctx);
+        }
         bow_cull_kernel<<<1, 256, 0, ctx->stream>>>(n_out, check_ori, d_match, d_bin, d_hist, d_nm);
         LAUNCH_COUNT(ctx);
         CU_TRY(cudaGetLastError());

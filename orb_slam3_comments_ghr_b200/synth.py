@@ -377,6 +377,39 @@ def make_bow_case(seed: int, voc: HostVoc, n: int = 2000, valid_frac: float = 0.
     return BowCase(kf, f, kf_valid, f_valid)
 
 
+def make_bow_conflict_case(seed: int, n1: int = 1200, n2: int = 1500, group: int = 10, layout: str = "root") -> BowCase:
+    """SearchByBoW stress for the "partner already matched" rule (:335 / :962): the frame holds groups of `group` near-duplicate
+    descriptors and many keyframe features sit near each group's prototype, so later keyframe features find their best
+    partners taken and walk down their candidate lists (past 8 entries for the big groups).  FeatureVectors are attached here:
+    layout "root" = one node holding everything (levelsup >= L), "mixed" = one big node, one mid-size node and small ones."""
+    rng = np.random.default_rng(seed)
+    n_groups = max(n2 // group, 1)
+    proto = random_descriptors(rng, n_groups)
+    f = make_frame(rng, n2)
+    gid2 = np.arange(n2) % n_groups
+    f.desc[:] = proto[gid2] ^ flip_mask(rng, n2, rng.choice(np.array([4, 5, 6]), size=n2))
+    kf = make_frame(rng, n1)
+    gid1 = rng.integers(0, n_groups, n1)
+    gid1[: n1 // 8] = 0  # one crowded group: more contenders than members
+    kf.desc[:] = proto[gid1] ^ flip_mask(rng, n1, rng.choice(np.array([5, 6, 7, 9]), size=n1))
+    kf.angle[:] = quantise((f.angle[rng.integers(0, n2, n1)] + 33.0 + rng.normal(0, 4.0, n1)) % 360.0)
+    kf_valid = (rng.random(n1) < 0.8).astype(np.uint8)
+    f_valid = (rng.random(n2) < 0.8).astype(np.uint8)
+
+    def featvec(n, cuts):
+        order = rng.permutation(n).astype(np.uint32)
+        bounds = [0] + [int(c * n) for c in cuts] + [n]
+        feats = np.concatenate([np.sort(order[bounds[i]:bounds[i + 1]]) for i in range(len(bounds) - 1)])  # ascending in a node
+        keep = [i for i in range(len(bounds) - 1) if bounds[i + 1] > bounds[i]]
+        return (np.array([10 + 3 * i for i in keep], dtype=np.uint32),
+                np.array([bounds[i] for i in keep] + [n], dtype=np.int32), feats)
+
+    cuts = [] if layout == "root" else [0.55, 0.8, 0.82, 0.9]
+    kf = kf.with_featvec(*featvec(n1, cuts))
+    f = f.with_featvec(*featvec(n2, cuts))
+    return BowCase(kf, f, kf_valid, f_valid)
+
+
 # ---------------------------------------------------------------- C4
 @dataclass
 class TriangulationCase:

@@ -166,6 +166,31 @@ def test_bow_host_featvec(ctx, M, oracle, seed, levelsup, ratio):
         assert got[0] == exp[0] and np.array_equal(got[1], exp[1])
 
 
+@pytest.mark.parametrize("seed,layout,ratio,n1,n2", [(601, "root", 0.95, 1200, 1500), (602, "mixed", 0.9, 1200, 1500), (603, "root", 0.7, 1200, 1500),
+                                                   (604, "root", 0.95, 40, 300), (605, "mixed", 1.0, 3000, 4000), (606, "root", 0.95, 31, 400)])
+def test_bow_conflicts(ctx, M, oracle, seed, layout, ratio, n1, n2):
+    """big node pairs go through the lock-time fixed point (bow_big_*_kernel): heavy contention for near-duplicate partners,
+    candidate lists that run out (full rescans), a crowded group with more contenders than members; (606) just under the
+    size that selects the path"""
+    bc = synth.make_bow_conflict_case(seed, n1=n1, n2=n2, layout=layout)
+    dkf, df = ctx.upload_frame(bc.kf), ctx.upload_frame(bc.f)
+    for ori in (0, 1):
+        m = M.ORBmatcher(ratio, bool(ori), ctx)
+        got = m.SearchByBoW(dkf, df, bc.kf_mp_valid)
+        oracle.reset_comparisons()
+        exp = oracle.search_by_bow_kf_f(bc.kf, bc.f, bc.kf_mp_valid, ratio, ori)
+        assert got[0] == exp[0] and np.array_equal(got[1], exp[1])
+        assert ctx.last_comparisons == oracle.comparisons()
+        got = m.SearchByBoW(dkf, df, bc.kf_mp_valid, bc.f_mp_valid)
+        oracle.reset_comparisons()
+        exp = oracle.search_by_bow_kf_kf(bc.kf, bc.f, bc.kf_mp_valid, bc.f_mp_valid, ratio, ori)
+        assert got[0] == exp[0] and np.array_equal(got[1], exp[1])
+        assert ctx.last_comparisons == oracle.comparisons()
+    # all-invalid keyframe: nothing to match, nothing compared
+    got = M.ORBmatcher(ratio, True, ctx).SearchByBoW(dkf, df, np.zeros_like(bc.kf_mp_valid))
+    assert got[0] == 0 and (got[1] == -1).all() and ctx.last_comparisons == 0
+
+
 # search core of the self-projecting overloads (row a6)
 PROJECTED_MODES = [  # name, level_mode, ordered, stereo, stereo_gate, chi2_gate, max_dist, th, ori
     ("cur_last", "pm1", 1, False, 0, 0, 100.0, 7.0, 1),

@@ -245,3 +245,17 @@ def test_compute_distinctive_descriptors_bad_keyframes(oracle, reference):
         else:
             assert good[f_offs[p] + gi[p]] == offs[p] + ei[p]
     assert ei[5] == -1
+
+
+@pytest.mark.parametrize("seed,layout,ratio", [(601, "root", 0.95), (602, "mixed", 0.9), (603, "root", 0.7)])
+def test_bow_conflicts(oracle, reference, seed, layout, ratio):
+    """the "partner already matched" rule under heavy contention (groups of near-duplicate partners): restatement == reference"""
+    bc = synth.make_bow_conflict_case(seed, layout=layout)
+    for ori in (0, 1):
+        exp = reference.search_by_bow_kf_f(bc.kf, bc.f, bc.kf_mp_valid, ratio, ori)
+        got = oracle.search_by_bow_kf_f(bc.kf, bc.f, bc.kf_mp_valid, ratio, ori)
+        assert got[0] == exp[0] and np.array_equal(got[1], exp[1])
+        exp = reference.search_by_bow_kf_kf(bc.kf, bc.f, bc.kf_mp_valid, bc.f_mp_valid, ratio, ori)
+        got = oracle.search_by_bow_kf_kf(bc.kf, bc.f, bc.kf_mp_valid, bc.f_mp_valid, ratio, ori)
+        assert got[0] == exp[0] and np.array_equal(got[1], exp[1])
+    assert exp[0] > 20
