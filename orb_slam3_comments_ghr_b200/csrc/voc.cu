@@ -7,12 +7,13 @@
 //   voc_transform_kernel  one warp per feature; lanes over the children of the current node; the
 //                         child with the lexicographically smallest (distance, child position) wins,
 //                         i.e. strict '<' / first child on ties (:1237-1248).
-//   featvec_build_kernel  one block per frame: bitonic sort of (node id, feature id) keys -> CSR with
-//                         ascending node ids and ascending feature ids inside a node (the iteration
-//                         order of the std::map<NodeId, vector<uint>> the reference walks).
-//   bow_build_kernel      same sort on (word id, feature id); weight of a word = idf added `count`
-//                         times in feature order (repeated double +=, not count*idf), then divided by
-//                         the L1 norm accumulated in ascending word-id order.
+//   featvec_bow_build_kernel  two blocks per frame, side by side, each a bitonic sort in shared memory:
+//     job 0 (featvec_build)  (node id, feature id) keys -> CSR with ascending node ids and ascending feature
+//                            ids inside a node (the iteration order of the std::map<NodeId, vector<uint>>
+//                            the reference walks);
+//     job 1 (bow_build)      same sort on (word id, feature id); weight of a word = idf added `count` times in
+//                            feature order (repeated double +=, not count*idf), then divided by the L1 norm
+//                            accumulated in ascending word-id order.
 #include <algorithm>
 #include <cstring>
 
@@ -171,10 +172,9 @@ __device__ void csr_from_sorted(const unsigned long long *keys, int m, uint32_t 
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(SORT_THREADS)
-featvec_build_kernel(int n, int cap, const uint32_t *__restrict__ node_id, const double *__restrict__ weight,
-                     unsigned long long *__restrict__ keys, uint32_t *__restrict__ fv_node_ids, int32_t *__restrict__ fv_offsets,
-                     uint32_t *__restrict__ fv_features, int32_t *__restrict__ meta)
+__device__ void featvec_build(int n, int cap, const uint32_t *__restrict__ node_id, const double *__restrict__ weight,
+                              unsigned long long *keys, uint32_t *__restrict__ fv_node_ids, int32_t *__restrict__ fv_offsets,
+                              uint32_t *__restrict__ fv_features, int32_t *__restrict__ meta)
 {
     __shared__ int warp_sums[32];
     __shared__ int s_max;
@@ -207,10 +207,9 @@ featvec_build_kernel(int n, int cap, const uint32_t *__restrict__ node_id, const
     }
 }
 
-__global__ void __launch_bounds__(SORT_THREADS)
-bow_build_kernel(int n, int cap, const uint32_t *__restrict__ word_id, const double *__restrict__ weight,
-                 unsigned long long *__restrict__ keys, uint32_t *__restrict__ bow_words, int32_t *__restrict__ tmp_offsets,
-                 double *__restrict__ bow_values, int32_t *__restrict__ meta)
+__device__ void bow_build(int n, int cap, const uint32_t *__restrict__ word_id, const double *__restrict__ weight,
+                          unsigned long long *keys, uint32_t *__restrict__ bow_words, int32_t *__restrict__ tmp_offsets,
+                          double *__restrict__ bow_values, int32_t *__restrict__ meta)
 {
     __shared__ int warp_sums[32];
     __shared__ double s_norm;
@@ -248,6 +247,21 @@ bow_build_kernel(int n, int cap, const uint32_t *__restrict__ word_id, const dou
     if (s_norm > 0.0)
         for (int g = t; g < n_words; g += SORT_THREADS) bow_values[g] = __ddiv_rn(bow_values[g], s_norm);
     if (t == 0) meta[3] = n_words;
+}
+
+// FeatureVector (block with job 0) and BowVector (job 1) of one frame, built side by side: two independent sorts of the same
+// features by node id / word id.  The keys are sorted in shared memory when they fit (`keys_global` null: 8 B per key, frames
+// up to 16 k features); otherwise in the frame's global scratch, one job per launch.
+__global__ void __launch_bounds__(SORT_THREADS)
+featvec_bow_build_kernel(int job_base, int n, int cap, const uint32_t *__restrict__ node_id, const uint32_t *__restrict__ word_id,
+                         const double *__restrict__ weight, unsigned long long *keys_global, uint32_t *__restrict__ fv_node_ids,
+                         int32_t *__restrict__ fv_offsets, uint32_t *__restrict__ fv_features, uint32_t *__restrict__ bow_words,
+                         int32_t *__restrict__ tmp_offsets, double *__restrict__ bow_values, int32_t *__restrict__ meta)
+{
+    extern __shared__ unsigned long long sort_smem[];
+    unsigned long long *keys = keys_global ? keys_global : sort_smem;
+    if (job_base + (int)blockIdx.x == 0) featvec_build(n, cap, node_id, weight, keys, fv_node_ids, fv_offsets, fv_features, meta);
+    else bow_build(n, cap, word_id, weight, keys, bow_words, tmp_offsets, bow_values, meta);
 }
 
 } // namespace
@@ -327,11 +341,21 @@ extern "C" int orbgpu_transform(orbgpu_ctx *ctx, const orbgpu_voc *voc, orbgpu_f
     LAUNCH_COUNT(ctx);
     f->has_transform = true;
     if (store_featvec) {
-        featvec_build_kernel<<<1, SORT_THREADS, 0, ctx->stream>>>(n, f->sort_cap, f->node_id, f->weight, f->sort_keys, f->fv_node_ids,
-                                                                 f->fv_offsets, f->fv_features, f->fv_meta);
-        bow_build_kernel<<<1, SORT_THREADS, 0, ctx->stream>>>(n, f->sort_cap, f->word_id, f->weight, f->sort_keys, f->bow_words, tmp_off,
-                                                             f->bow_values, f->fv_meta);
-        ctx->launches += 2;
+        const size_t smem = (size_t)f->sort_cap * 8;
+        if (smem <= 160 * 1024) {
+            CU_TRY(cudaFuncSetAttribute(featvec_bow_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 1024 ? smem : 1024)));
+            featvec_bow_build_kernel<<<2, SORT_THREADS, smem, ctx->stream>>>(0, n, f->sort_cap, f->node_id, f->word_id, f->weight, nullptr,
+                                                                           f->fv_node_ids, f->fv_offsets, f->fv_features, f->bow_words, tmp_off,
+                                                                           f->bow_values, f->fv_meta);
+            LAUNCH_COUNT(ctx);
+        } else {
+            for (int job = 0; job < 2; job++) {
+                featvec_bow_build_kernel<<<1, SORT_THREADS, 0, ctx->stream>>>(job, n, f->sort_cap, f->node_id, f->word_id, f->weight, f->sort_keys,
+                                                                            f->fv_node_ids, f->fv_offsets, f->fv_features, f->bow_words, tmp_off,
+                                                                            f->bow_values, f->fv_meta);
+                LAUNCH_COUNT(ctx);
+            }
+        }
     }
     CU_TRY(cudaGetLastError());
     if (word_id) CU_TRY(cudaMemcpyAsync(word_id, f->word_id, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
