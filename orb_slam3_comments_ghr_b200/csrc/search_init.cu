@@ -5,10 +5,14 @@
 //   phase 1 (parallel, one warp per F1 keypoint): enumerate the F2 window candidates in the
 //           reference's iteration order and compute their Hamming distances; store
 //           (dist<<20 | i2) lists.  This is where every DescriptorDistance call happens.
-//   phase 2 (ordered, one warp): walk the F1 keypoints in index order over the stored lists,
-//           applying the `vMatchedDistance[i2] <= dist` filter, the lexicographic (dist,
-//           position) top-2, thresholds, match displacement and the rotation histogram exactly
-//           as written.  Only integer compares and two fp32 multiplies per keypoint.
+//   phase 2 (one CTA): the ordered part -- the `vMatchedDistance[i2] <= dist` filter (:790), the
+//           lexicographic (dist, position) top-2, thresholds, match displacement (:813-817) and the
+//           rotation histogram.  Solved as a fixed point over the keypoints' ACCEPTS: the matched distance
+//           keypoint k sees at partner i2 is the smallest distance among the accepts onto i2 by keypoints
+//           before k, so with an inverse index (partner -> keypoints that list it) every keypoint is
+//           re-decided in parallel against the current accepts until a sweep changes nothing; keypoint k
+//           only depends on keypoints before it, so the fixed point is the sequential result.  Cases whose
+//           lists do not fit the shared-memory budget are replayed in order by one warp.
 #include <climits>
 
 #include "internal.cuh"
@@ -48,6 +52,7 @@ __global__ void init_candidates_kernel(FrameView f1, FrameView f2, const float2 
 // loop order only touches shared memory: ~100 cycles per level-0 keypoint instead of several L2 round trips.
 constexpr int INIT_THREADS = 1024;
 constexpr int INIT_LIST_CAP = 24 * 1024; // staged list entries (96 KB); larger cases replay from global memory
+constexpr int INIT_FP_CAP = INIT_LIST_CAP / 2; // fixed-point path: lists in the first half, the inverse index in the second
 __global__ void __launch_bounds__(INIT_THREADS)
 init_resolve_kernel(FrameView f1, FrameView f2, float2 *__restrict__ prev, const uint32_t *__restrict__ lists, int stride,
                     const int32_t *__restrict__ counts, float nnratio, int check_ori, int32_t *__restrict__ bin_of,
@@ -58,7 +63,9 @@ init_resolve_kernel(FrameView f1, FrameView f2, float2 *__restrict__ prev, const
     int *vnMatches21 = vMatchedDistance + f2.n;  // [n2]
     int *sAct = vnMatches21 + f2.n;              // [n1] active (non-empty) F1 keypoints, ascending
     int *sOff = sAct + f1.n;                     // [n1] start of their lists
-    uint32_t *sLists = (uint32_t *)(sOff + f1.n); // [INIT_LIST_CAP]
+    int *choice = sOff + f1.n;                   // [n1] fixed-point path: accept of active keypoint k (i2 << 9 | dist), -1 none
+    uint32_t *sLists = (uint32_t *)(choice + f1.n); // [INIT_LIST_CAP]
+    __shared__ int s_changed;
     __shared__ int hist[ORBGPU_HISTO_LENGTH];
     __shared__ int ind[3];
     __shared__ int s_nmatches, s_removed, s_nact, s_total;
@@ -125,7 +132,102 @@ init_resolve_kernel(FrameView f1, FrameView f2, float2 *__restrict__ prev, const
     }
     __syncthreads();
     const uint32_t *L = staged ? sLists : lists;
-    if (t < 32) {
+    const bool fixed_point = staged && s_total <= INIT_FP_CAP;
+    if (fixed_point) {
+        const int total = s_total, n2 = f2.n;
+        // accepts grouped by partner: partner i2 owns acc[accOff[i2] ...] with room for every keypoint that lists it
+        uint32_t *acc = sLists + INIT_FP_CAP; // [total] (k << 9 | dist)
+        int *accOff = vMatchedDistance, *accCnt = vnMatches21; // the replay state is not needed on this path
+        for (int i = t; i < n2; i += INIT_THREADS) accCnt[i] = 0;
+        for (int k = t; k < nact; k += INIT_THREADS) choice[k] = -1;
+        __syncthreads();
+        for (int e = t; e < total; e += INIT_THREADS) atomicAdd(&accCnt[sLists[e] & 0xFFFFF], 1);
+        __syncthreads();
+        { // exclusive scan of the partners' capacities over contiguous chunks
+            const int per2 = (n2 + INIT_THREADS - 1) / INIT_THREADS;
+            const int lo2 = min(n2, t * per2), hi2 = min(n2, lo2 + per2);
+            int mine = 0;
+            for (int i = lo2; i < hi2; i++) mine += accCnt[i];
+            int incl = mine;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int a = __shfl_up_sync(FULL_MASK, incl, o);
+                if (lane >= o) incl += a;
+            }
+            if (lane == 31) warp_cnt[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                int a = warp_cnt[lane];
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(FULL_MASK, a, o);
+                    if (lane >= o) a += u;
+                }
+                warp_cnt[lane] = a;
+            }
+            __syncthreads();
+            int run = (warp ? warp_cnt[warp - 1] : 0) + incl - mine;
+            for (int i = lo2; i < hi2; i++) {
+                accOff[i] = run;
+                run += accCnt[i];
+            }
+        }
+        __syncthreads();
+        for (int iter = 0; iter <= nact + 1; iter++) {
+            // the accepts of the previous sweep, by partner
+            for (int i = t; i < n2; i += INIT_THREADS) accCnt[i] = 0;
+            __syncthreads();
+            if (t == 0) s_changed = 0; // every thread has read the previous sweep's flag before the barrier above
+            for (int k = t; k < nact; k += INIT_THREADS) {
+                const int c = choice[k];
+                if (c >= 0) acc[accOff[c >> 9] + atomicAdd(&accCnt[c >> 9], 1)] = ((uint32_t)k << 9) | (uint32_t)(c & 0x1FF);
+            }
+            __syncthreads();
+            for (int k = warp; k < nact; k += INIT_THREADS / 32) {
+                const int s0 = sOff[k], cnt = (k + 1 < nact ? sOff[k + 1] : total) - s0;
+                uint32_t b1 = KEY_NONE, b2 = KEY_NONE;
+                for (int p = lane; p < cnt; p += 32) {
+                    const uint32_t e = sLists[s0 + p];
+                    const int dist = (int)(e >> 20), i2 = (int)(e & 0xFFFFF);
+                    int md = INT_MAX; // vMatchedDistance[i2] as keypoint k finds it (:752, :822): accepts by keypoints before k
+                    for (int x = accOff[i2], xe = x + accCnt[i2]; x < xe; x++) {
+                        const uint32_t v = acc[x];
+                        if ((int)(v >> 9) < k) md = min(md, (int)(v & 0x1FF));
+                    }
+                    if (!(md <= dist)) top2_push(b1, b2, ((uint32_t)dist << 20) | (uint32_t)p); // :790
+                }
+                uint32_t m1, m2;
+                warp_top2(b1, b2, m1, m2);
+                int c = -1;
+                if (m1 != KEY_NONE) {
+                    const int bestDist = (int)(m1 >> 20);
+                    const float second = (m2 == KEY_NONE) ? (float)INT_MAX : (float)(int)(m2 >> 20);
+                    if (bestDist <= ORBGPU_TH_LOW && (float)bestDist < __fmul_rn(second, nnratio)) // :807, :810
+                        c = (int)((sLists[s0 + (m1 & 0xFFFFF)] & 0xFFFFF) << 9) | bestDist;
+                }
+                if (lane == 0 && c != choice[k]) { // the sweep reads acc[], not choice[]
+                    choice[k] = c;
+                    s_changed = 1;
+                }
+            }
+            __syncthreads();
+            if (!s_changed) break; // acc[] holds exactly the final accepts
+        }
+        int kept = 0;
+        for (int k = t; k < nact; k += INIT_THREADS) {
+            const int c = choice[k];
+            if (c < 0) continue;
+            const int i2 = c >> 9, i1 = sAct[k];
+            bin_of[i1] = i2; // partner at accept time (for the rotation histogram), displaced or not
+            bool displaced = false; // :813-817: a later accept onto the same partner takes the match away
+            for (int x = accOff[i2], xe = x + accCnt[i2]; x < xe; x++)
+                if ((int)(acc[x] >> 9) > k) displaced = true;
+            if (!displaced) {
+                matches12[i1] = i2;
+                kept++;
+            }
+        }
+        for (int o = 16; o; o >>= 1) kept += __shfl_xor_sync(FULL_MASK, kept, o);
+        if (lane == 0 && kept) atomicAdd(&s_nmatches, kept);
+    } else if (t < 32) {
         int nmatches = 0;
         for (int k = 0; k < nact; k++) { // keypoints with level > 0 (:762) or an empty window (:771) are not listed
             const int i1 = sAct[k];
@@ -228,7 +330,7 @@ extern "C" int orbgpu_search_for_initialization(orbgpu_ctx *ctx, const orbgpu_fr
     const FrameView v1 = frame_view(f1), v2 = frame_view(f2);
     init_candidates_kernel<<<(n1 * 32 + 255) / 256, 256, 0, ctx->stream>>>(v1, v2, d_prev, (float)window_size, lists, stride, counts,
                                                                           ctx->d_counters);
-    const size_t smem = ((size_t)2 * n2 + (size_t)2 * n1 + INIT_LIST_CAP) * 4;
+    const size_t smem = ((size_t)2 * n2 + (size_t)3 * n1 + INIT_LIST_CAP) * 4;
     if (smem > 220 * 1024) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "frames too large for the shared-memory replay state");
     CU_TRY(cudaFuncSetAttribute(init_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     init_resolve_kernel<<<1, INIT_THREADS, smem, ctx->stream>>>(v1, v2, d_prev, lists, stride, counts, nnratio, check_ori, bin_of, d_m12,
