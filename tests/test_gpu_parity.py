@@ -70,7 +70,8 @@ def test_init_golden(ctx, M, name):
     assert n == int(g[name + "/nmatches"]) and np.array_equal(m12, g[name + "/matches12"]) and np.array_equal(prev, g[name + "/prev"])
 
 
-@pytest.mark.parametrize("seed,n,ratio,ori", [(201, 1000, 0.9, 1), (202, 1000, 0.6, 0), (203, 300, 0.9, 1), (204, 2500, 0.95, 1), (205, 1, 0.9, 1)])
+@pytest.mark.parametrize("seed,n,ratio,ori", [(201, 1000, 0.9, 1), (202, 1000, 0.6, 0), (203, 300, 0.9, 1), (204, 2500, 0.95, 1), (205, 1, 0.9, 1),
+                                              (206, 1800, 0.9, 1)])  # 1000: accept fixed point; 1800: staged ordered replay; 2500: replay from global
 def test_init_oracle(ctx, M, oracle, seed, n, ratio, ori):
     c = synth.make_init_case(seed, n=n)
     m = M.ORBmatcher(ratio, bool(ori), ctx)
@@ -79,6 +80,25 @@ def test_init_oracle(ctx, M, oracle, seed, n, ratio, ori):
     exp = oracle.search_for_initialization(c.f1, c.f2, c.prev_matched, c.window_size, ratio, ori)
     assert got[0] == exp[0] and np.array_equal(got[1], exp[1]) and np.array_equal(got[2], exp[2])
     assert ctx.last_comparisons == oracle.comparisons()
+
+
+@pytest.mark.parametrize("seed,n,n_proto,ratio", [(211, 800, 6, 1.0), (212, 1000, 40, 0.95), (213, 400, 2, 1.0)])
+def test_init_contention(ctx, M, oracle, seed, n, n_proto, ratio):
+    """the accept fixed point under contention: level-0 descriptors of both frames are noisy copies of a few prototypes, so many
+    key points accept the same partners with shrinking distances (vMatchedDistance chains, :790/:822) and displace each other
+    (:813-817); ratio 1.0 keeps ties alive"""
+    c = synth.make_init_case(seed, n=n)
+    rng = np.random.default_rng(seed)
+    proto = synth.random_descriptors(rng, n_proto)
+    for fr in (c.f1, c.f2):
+        l0 = np.flatnonzero(fr.octave == 0)
+        fr.desc[l0] = proto[rng.integers(0, n_proto, l0.size)] ^ synth.flip_mask(rng, l0.size, rng.choice(np.array([4, 5, 6, 9]), size=l0.size))
+    for ori in (0, 1):
+        m = M.ORBmatcher(ratio, bool(ori), ctx)
+        got = m.SearchForInitialization(ctx.upload_frame(c.f1), ctx.upload_frame(c.f2), c.prev_matched.copy(), c.window_size)
+        exp = oracle.search_for_initialization(c.f1, c.f2, c.prev_matched.copy(), c.window_size, ratio, ori)
+        assert got[0] == exp[0] and np.array_equal(got[1], exp[1]) and np.array_equal(got[2], exp[2])
+    assert exp[0] > 5
 
 
 @pytest.mark.parametrize("name", ["proj_s21_th1", "proj_s22_th3", "proj_s23_far"])
