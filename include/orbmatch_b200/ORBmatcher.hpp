@@ -180,6 +180,32 @@ namespace orbgpu
             return d;
         }
 
+        // SearchByNN: named in the matcher family but not present in this fork (no declaration in ORBmatcher.h) -- defined by this
+        // repo as the brute-force form of SearchByBoW's inner loop (ORBmatcher.cc:327-355) with its accept rule (:392-395):
+        // for every row of `queries` the nearest row of `database` (first index among equal distances) is accepted when
+        // best <= th && (float)best < mfNNratio * (float)second.  vnMatches = vector<int>(queries.rows, -1) then filled;
+        // returns the number of matches.  Both matrices are N x 32 CV_8U like Frame::mDescriptors.
+        template <class Mat>
+        int SearchByNN(const Mat &queries, const Mat &database, std::vector<int> &vnMatches, int th = 50 /* TH_LOW */)
+        {
+            orbgpu_ctx *ctx = thread_context();
+            const int nq = queries.rows, nd = database.rows;
+            vnMatches.assign((size_t)nq, -1);
+            if (nq == 0 || nd == 0) return 0;
+            orbgpu_db *db = nullptr;
+            check(orbgpu_db_upload(ctx, nd, database.template ptr<uint8_t>(), &db));
+            std::vector<int32_t> bi((size_t)nq), bd((size_t)nq), sd((size_t)nq), m((size_t)nq);
+            const int rc = orbgpu_knn2_ratio(ctx, db, nq, queries.template ptr<uint8_t>(), th, mfNNratio, bi.data(), bd.data(), sd.data(), m.data());
+            orbgpu_db_destroy(db);
+            check(rc);
+            int nmatches = 0;
+            for (int i = 0; i < nq; i++) {
+                vnMatches[(size_t)i] = m[(size_t)i];
+                nmatches += m[(size_t)i] >= 0;
+            }
+            return nmatches;
+        }
+
         // ORBmatcher.h:69 (ORBmatcher.cc:735-878)
         template <class Point2f>
         int SearchForInitialization(FrameT &F1, FrameT &F2, std::vector<Point2f> &vbPrevMatched, std::vector<int> &vnMatches12,

@@ -443,6 +443,34 @@ int main()
         for (int i = 0; i < 32; i++) { a.ptr<uint8_t>()[i] = (uint8_t)(rng() & 0xFF); b.ptr<uint8_t>()[i] = (uint8_t)(rng() & 0xFF); }
         EXPECT(ORBmatcher::DescriptorDistance(a, b) == GpuMatcher::DescriptorDistance(a, b), "DescriptorDistance");
     }
+    { // SearchByNN (defined by this repo): against a loop over the reference's own DescriptorDistance with SearchByBoW's accept rule
+        const int nq = 700, nd = 3000;
+        cv::Mat Q(nq, 32, CV_8U), D(nd, 32, CV_8U);
+        for (int i = 0; i < nd * 32; i++) D.ptr<uint8_t>()[i] = (uint8_t)(rng() & 0xFF);
+        for (int i = 0; i < nq * 32; i++) Q.ptr<uint8_t>()[i] = (uint8_t)(rng() & 0xFF);
+        for (int q = 0; q < nq; q += 2) { // planted: a database row with a few flipped bits; every 10th has an exact twin (ratio failure)
+            const int src = (q * 13) % nd;
+            std::memcpy(Q.ptr<uint8_t>(q), D.ptr<uint8_t>(src), 32);
+            for (int f = 0; f < (q % 7); f++) Q.ptr<uint8_t>(q)[(q + 5 * f) % 32] ^= (uint8_t)(1u << (f % 8));
+            if (q % 10 == 0) std::memcpy(D.ptr<uint8_t>((src + 1) % nd), D.ptr<uint8_t>(src), 32);
+        }
+        const float ratio = 0.8f;
+        std::vector<int> exp(nq, -1), got;
+        int nExp = 0;
+        for (int q = 0; q < nq; q++) {
+            int best = 256, second = 256, bi = -1;
+            for (int d = 0; d < nd; d++) {
+                const int dist = ORBmatcher::DescriptorDistance(Q.row(q), D.row(d));
+                if (dist < best) { second = best; best = dist; bi = d; }
+                else if (dist < second) second = dist;
+            }
+            if (best <= ORBmatcher::TH_LOW && (float)best < ratio * (float)second) { exp[q] = bi; nExp++; }
+        }
+        GpuMatcher gpu(ratio, true);
+        const int nGot = gpu.SearchByNN(Q, D, got);
+        std::printf("SearchByNN: ref %d gpu %d\n", nExp, nGot);
+        EXPECT(nGot == nExp && got == exp && nExp > 100, "SearchByNN vnMatches / return value");
+    }
     std::printf(fails ? "ADAPTER PARITY FAILED (%d)\n" : "ADAPTER PARITY OK (%d failures)\n", fails);
     return fails ? 1 : 0;
 }
