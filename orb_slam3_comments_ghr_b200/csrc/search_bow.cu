@@ -395,7 +395,8 @@ int run_bow(orbgpu_ctx *ctx, int mode, const orbgpu_frame *kf, const orbgpu_fram
     if (n_out == 0) return ORBGPU_OK;
     const size_t ob = align256((size_t)n_out * 4);
     // fixed-point path for big node pairs (both sizes are known on the host as launch hints)
-    const bool big = kf->fv_max_node >= BOW_BIG_N1 && f->fv_max_node >= BOW_BIG_N2 && kf->fv_n_nodes > 0 && f->fv_n_nodes > 0;
+    const bool big = kf->fv_max_node >= BOW_BIG_N1 && f->fv_max_node >= BOW_BIG_N2 && kf->fv_n_nodes > 0 && f->fv_n_nodes > 0 &&
+                     ((size_t)f->fv_max_node + 2 * (size_t)kf->fv_max_node) * 4 <= 200 * 1024; // else: replay kernel for every node
     rc = arena_reserve(ctx, 2 * ob + align256(kf->n + 1) + 2 * align256(f->n + 1) + 1024 +
                                 (big ? align256((size_t)kf->n * BOW_LIST_K * 4) + align256((size_t)kf->n * 4) : 0));
     if (rc) return rc;
