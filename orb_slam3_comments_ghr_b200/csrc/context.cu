@@ -73,6 +73,7 @@ extern "C" void orbgpu_destroy(orbgpu_ctx *ctx)
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -127,6 +128,35 @@ int ctx_fetch_comparisons(orbgpu_ctx *ctx)
                            ctx->stream));
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     ctx->last_comparisons = (int64_t)ctx->h_counters[0];
+    return ORBGPU_OK;
+}
+
+int ctx_download(orbgpu_ctx *ctx, const OutPiece *pieces, int n)
+{
+    size_t total = 0;
+    for (int i = 0; i < n; i++) total += (pieces[i].bytes + 63) & ~size_t(63);
+    if (total > ctx->h_out_bytes) {
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_out) CU_TRY(cudaFreeHost(ctx->h_out));
+        ctx->h_out = nullptr;
+        ctx->h_out_bytes = 0;
+        const size_t want = total + total / 4 + 4096;
+        CU_TRY(cudaMallocHost(&ctx->h_out, want));
+        ctx->h_out_bytes = want;
+    }
+    size_t off = 0;
+    for (int i = 0; i < n; i++) {
+        if (pieces[i].bytes && pieces[i].host)
+            CU_TRY(cudaMemcpyAsync(ctx->h_out + off, pieces[i].dev, pieces[i].bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        off += (pieces[i].bytes + 63) & ~size_t(63);
+    }
+    int rc = ctx_fetch_comparisons(ctx); // the one synchronisation
+    if (rc) return rc;
+    off = 0;
+    for (int i = 0; i < n; i++) {
+        if (pieces[i].bytes && pieces[i].host) memcpy(pieces[i].host, ctx->h_out + off, pieces[i].bytes);
+        off += (pieces[i].bytes + 63) & ~size_t(63);
+    }
     return ORBGPU_OK;
 }
 

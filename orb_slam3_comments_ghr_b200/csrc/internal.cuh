@@ -63,6 +63,8 @@ struct orbgpu_ctx {
     // pinned host staging (grow-only) used to pack uploads into one H2D copy
     char *h_stage = nullptr;
     size_t h_stage_bytes = 0;
+    char *h_out = nullptr; // pinned landing zone of ctx_download
+    size_t h_out_bytes = 0;
 };
 int stage_reserve(orbgpu_ctx *ctx, size_t bytes);
 
@@ -79,6 +81,15 @@ struct orbgpu_voc;
 // voc.cu: FeatureVector node of n descriptors (0xFFFFFFFF for stopped words), comparisons added to counters[0]
 int launch_voc_transform_nodes(orbgpu_ctx *ctx, const orbgpu_voc *voc, long long n, const uint4 *desc, int levelsup, uint32_t *node_id);
 int ctx_fetch_comparisons(orbgpu_ctx *ctx); // sync + read counter[0] into last_comparisons
+// Results of a host-pointer call: every piece is copied device -> pinned memory asynchronously, ONE synchronisation, then the
+// pieces go to the caller's (pageable) buffers.  A cudaMemcpyAsync straight into pageable memory blocks until it is done, so
+// each result array used to cost its own round trip.  Also reads the comparison counter like ctx_fetch_comparisons.
+struct OutPiece {
+    void *host;
+    const void *dev;
+    size_t bytes;
+};
+int ctx_download(orbgpu_ctx *ctx, const OutPiece *pieces, int n);
 
 #define LAUNCH_COUNT(ctx) ((ctx)->launches++)
 

@@ -452,9 +452,8 @@ int run_bow(orbgpu_ctx *ctx, int mode, const orbgpu_frame *kf, const orbgpu_fram
         LAUNCH_COUNT(ctx);
         CU_TRY(cudaGetLastError());
     }
-    CU_TRY(cudaMemcpyAsync(match_out, d_match, (size_t)n_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaMemcpyAsync(nmatches, d_nm, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    return ctx_fetch_comparisons(ctx);
+    const OutPiece out[2] = {{match_out, d_match, (size_t)n_out * 4}, {nmatches, d_nm, 4}};
+    return ctx_download(ctx, out, 2);
 }
 
 } // namespace

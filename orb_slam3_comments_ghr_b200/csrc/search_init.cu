@@ -337,8 +337,6 @@ extern "C" int orbgpu_search_for_initialization(orbgpu_ctx *ctx, const orbgpu_fr
                                                                 d_nm);
     ctx->launches += 2;
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpyAsync(matches12, d_m12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaMemcpyAsync(prev_matched_xy, d_prev, (size_t)n1 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaMemcpyAsync(nmatches, d_nm, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    return ctx_fetch_comparisons(ctx);
+    const OutPiece out[3] = {{matches12, d_m12, (size_t)n1 * 4}, {prev_matched_xy, d_prev, (size_t)n1 * 8}, {nmatches, d_nm, 4}};
+    return ctx_download(ctx, out, 3);
 }

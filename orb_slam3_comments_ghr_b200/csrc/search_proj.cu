@@ -232,7 +232,6 @@ extern "C" int orbgpu_search_by_projection_local(orbgpu_ctx *ctx, const orbgpu_f
                                                                         d_nm, ctx->d_counters);
     ctx->launches += 2;
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpyAsync(kp_mp, d_kpmp, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaMemcpyAsync(nmatches, d_nm, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    return ctx_fetch_comparisons(ctx);
+    const OutPiece out[2] = {{kp_mp, d_kpmp, (size_t)n * 4}, {nmatches, d_nm, 4}};
+    return ctx_download(ctx, out, 2);
 }

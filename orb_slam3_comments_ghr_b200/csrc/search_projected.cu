@@ -264,9 +264,7 @@ extern "C" int orbgpu_search_projected(orbgpu_ctx *ctx, const orbgpu_frame *f, c
                                                                         choice, d_bd, kp_owner ? d_owner : nullptr, d_nm, ctx->d_counters);
     ctx->launches += 2;
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpyAsync(best_idx, choice, (size_t)M * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaMemcpyAsync(best_dist, d_bd, (size_t)M * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (kp_owner) CU_TRY(cudaMemcpyAsync(kp_owner, d_owner, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaMemcpyAsync(nmatches, d_nm, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    return ctx_fetch_comparisons(ctx);
+    const OutPiece out[4] = {{best_idx, choice, (size_t)M * 4}, {best_dist, d_bd, (size_t)M * 4},
+                             {kp_owner, kp_owner ? d_owner : nullptr, (size_t)n * 4}, {nmatches, d_nm, 4}};
+    return ctx_download(ctx, out, 4);
 }

@@ -240,7 +240,15 @@ __device__ void bow_build(int n, int cap, const uint32_t *__restrict__ word_id, 
     // BowVector::normalize(L1) (BowVector.cpp:63-85): norm accumulated in ascending word id
     if (t == 0) {
         double norm = 0.0;
-        for (int g = 0; g < n_words; g++) norm = __dadd_rn(norm, fabs(bow_values[g]));
+        int g = 0;
+        for (; g + 8 <= n_words; g += 8) { // the loads are batched, the additions stay in word order
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = fabs(bow_values[g + u]);
+#pragma unroll
+            for (int u = 0; u < 8; u++) norm = __dadd_rn(norm, v[u]);
+        }
+        for (; g < n_words; g++) norm = __dadd_rn(norm, fabs(bow_values[g]));
         s_norm = norm;
     }
     __syncthreads();
@@ -358,12 +366,10 @@ extern "C" int orbgpu_transform(orbgpu_ctx *ctx, const orbgpu_voc *voc, orbgpu_f
         }
     }
     CU_TRY(cudaGetLastError());
-    if (word_id) CU_TRY(cudaMemcpyAsync(word_id, f->word_id, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (node_id) CU_TRY(cudaMemcpyAsync(node_id, f->node_id, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (weight) CU_TRY(cudaMemcpyAsync(weight, f->weight, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     int32_t meta[4] = {0, 0, 0, 0};
-    if (store_featvec) CU_TRY(cudaMemcpyAsync(meta, f->fv_meta, sizeof(meta), cudaMemcpyDeviceToHost, ctx->stream));
-    rc = ctx_fetch_comparisons(ctx);
+    const OutPiece out[4] = {{word_id, f->word_id, (size_t)n * 4}, {node_id, f->node_id, (size_t)n * 4}, {weight, f->weight, (size_t)n * 8},
+                             {store_featvec ? meta : nullptr, f->fv_meta, sizeof(meta)}};
+    rc = ctx_download(ctx, out, 4);
     if (rc) return rc;
     if (store_featvec) {
         f->fv_n_nodes = meta[0];
@@ -379,12 +385,8 @@ extern "C" int orbgpu_bowvector_download(orbgpu_ctx *ctx, const orbgpu_frame *f,
     ARG_TRY(ctx && f && n_words);
     CU_TRY(cudaSetDevice(ctx->device));
     *n_words = f->bow_n;
-    if (f->bow_n > 0) {
-        if (words) CU_TRY(cudaMemcpyAsync(words, f->bow_words, (size_t)f->bow_n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        if (values) CU_TRY(cudaMemcpyAsync(values, f->bow_values, (size_t)f->bow_n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    CU_TRY(cudaStreamSynchronize(ctx->stream));
-    return ORBGPU_OK;
+    const OutPiece out[2] = {{words, f->bow_words, (size_t)f->bow_n * 4}, {values, f->bow_values, (size_t)f->bow_n * 8}};
+    return ctx_download(ctx, out, 2);
 }
 
 extern "C" int orbgpu_featvec_download(orbgpu_ctx *ctx, const orbgpu_frame *f, int32_t *n_nodes, uint32_t *node_ids, int32_t *offsets,
@@ -393,11 +395,7 @@ extern "C" int orbgpu_featvec_download(orbgpu_ctx *ctx, const orbgpu_frame *f, i
     ARG_TRY(ctx && f && n_nodes);
     CU_TRY(cudaSetDevice(ctx->device));
     *n_nodes = f->fv_n_nodes;
-    if (node_ids && f->fv_n_nodes > 0)
-        CU_TRY(cudaMemcpyAsync(node_ids, f->fv_node_ids, (size_t)f->fv_n_nodes * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (offsets) CU_TRY(cudaMemcpyAsync(offsets, f->fv_offsets, (size_t)(f->fv_n_nodes + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (features && f->fv_total > 0)
-        CU_TRY(cudaMemcpyAsync(features, f->fv_features, (size_t)f->fv_total * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaStreamSynchronize(ctx->stream));
-    return ORBGPU_OK;
+    const OutPiece out[3] = {{node_ids, f->fv_node_ids, (size_t)f->fv_n_nodes * 4}, {offsets, f->fv_offsets, (size_t)(f->fv_n_nodes + 1) * 4},
+                             {features, f->fv_features, (size_t)f->fv_total * 4}};
+    return ctx_download(ctx, out, 3);
 }

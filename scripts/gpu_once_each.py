@@ -24,6 +24,8 @@ for it in range(2):
     dk.transform(dv, 2, True); df.transform(dv, 2, True)
     matcher.ORBmatcher(0.7, True, ctx).SearchByBoW(dk, df, bc.kf_mp_valid)
     matcher.ORBmatcher(0.9, True, ctx).SearchByBoW(dk, df, bc.kf_mp_valid, bc.f_mp_valid)
+    dk.transform(dv, 4, True); df.transform(dv, 4, True)  # one root bucket: the big-node fixed point
+    matcher.ORBmatcher(0.7, True, ctx).SearchByBoW(dk, df, bc.kf_mp_valid)
     matcher.ORBmatcher(0.9, True, ctx).SearchProjected(ctx.upload_frame(fr), pts, 100.0, True, kl)
     bdb.score(qw, qv)
     ctx.compute_distinctive_descriptors(offs, desc)
