@@ -120,8 +120,6 @@ extern "C" int orbgpu_bow_score_l1(orbgpu_ctx *ctx, const orbgpu_bowdb *db, int3
         db->n_kf, db->offsets, db->words, db->values, nq_words, d_qw, d_qv, d_cm, d_sc);
     LAUNCH_COUNT(ctx);
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpyAsync(common_words, d_cm, (size_t)db->n_kf * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaMemcpyAsync(scores, d_sc, (size_t)db->n_kf * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaStreamSynchronize(ctx->stream));
-    return ORBGPU_OK;
+    const OutPiece out[2] = {{common_words, d_cm, (size_t)db->n_kf * 4}, {scores, d_sc, (size_t)db->n_kf * 8}};
+    return ctx_download(ctx, out, 2);
 }

@@ -100,7 +100,6 @@ extern "C" int orbgpu_compute_distinctive_descriptors(orbgpu_ctx *ctx, int32_t n
     distinctive_kernel<<<n_mp, DD_THREADS, 0, ctx->stream>>>(n_mp, d_off, d_desc, d_bi, d_bm, ctx->d_counters);
     LAUNCH_COUNT(ctx);
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpyAsync(best_idx, d_bi, (size_t)n_mp * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (best_median) CU_TRY(cudaMemcpyAsync(best_median, d_bm, (size_t)n_mp * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    return ctx_fetch_comparisons(ctx);
+    const OutPiece out[2] = {{best_idx, d_bi, (size_t)n_mp * 4}, {best_median, d_bm, (size_t)n_mp * 4}};
+    return ctx_download(ctx, out, 2);
 }

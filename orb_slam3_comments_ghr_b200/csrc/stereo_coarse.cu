@@ -152,7 +152,6 @@ extern "C" int orbgpu_stereo_coarse_match(orbgpu_ctx *ctx, int32_t n_left, const
                                                                            n_rows, row_start, row_items, max_d, d_bi, d_bd, ctx->d_counters);
     ctx->launches += 4;
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpyAsync(best_idx_r, d_bi, (size_t)n_left * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaMemcpyAsync(best_dist, d_bd, (size_t)n_left * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    return ctx_fetch_comparisons(ctx);
+    const OutPiece out[2] = {{best_idx_r, d_bi, (size_t)n_left * 4}, {best_dist, d_bd, (size_t)n_left * 4}};
+    return ctx_download(ctx, out, 2);
 }
