@@ -13,6 +13,9 @@
 #include <algorithm>
 #include <cstring>
 
+#include <mutex>
+#include <vector>
+
 #include "internal.cuh"
 
 namespace {
@@ -24,12 +27,15 @@ __global__ void __launch_bounds__(GRID_THREADS)
 grid_build_kernel(int n, const float2 *__restrict__ xy, const int32_t *__restrict__ octave, const uint4 *__restrict__ desc,
                   float min_x, float min_y, float inv_w, float inv_h, int cols, int rows, int32_t *__restrict__ cell_of,
                   int32_t *__restrict__ cell_start, int32_t *__restrict__ cell_items, int4 *__restrict__ items,
-                  uint4 *__restrict__ desc_sorted)
+                  uint4 *__restrict__ desc_sorted, int cof_in_smem)
 {
-    extern __shared__ int32_t sm[]; // counts[ncell] then cursor reuse
+    extern __shared__ int32_t sm[]; // counts[ncell] then cursor reuse; then (cof_in_smem) the features' cells [n]
     __shared__ int32_t warp_sums[32];
     const int ncell = cols * rows;
     const int t = threadIdx.x;
+    // the ordered scatter below is one warp walking the features: from shared memory a step is ~100 cycles, from global
+    // memory an L2 round trip
+    int32_t *cof = cof_in_smem ? sm + ncell : cell_of;
     for (int c = t; c < ncell; c += GRID_THREADS) sm[c] = 0;
     __syncthreads();
     // PosInGrid (Frame.cc:973-989): round-half-away of (pt - min) * inv, reject outside the grid
@@ -43,6 +49,7 @@ grid_build_kernel(int n, const float2 *__restrict__ xy, const int32_t *__restric
             atomicAdd(&sm[c], 1);
         }
         cell_of[i] = c;
+        if (cof_in_smem) cof[i] = c;
     }
     __syncthreads();
     // exclusive scan of the per-cell counts
@@ -85,7 +92,7 @@ grid_build_kernel(int n, const float2 *__restrict__ xy, const int32_t *__restric
     if (t < 32) {
         for (int base = 0; base < n; base += 32) {
             const int i = base + t;
-            const int c = (i < n) ? cell_of[i] : -1;
+            const int c = (i < n) ? cof[i] : -1;
             const unsigned same = __match_any_sync(FULL_MASK, c);
             if (c >= 0) {
                 const int rank = __popc(same & lanemask_lt());
@@ -102,7 +109,7 @@ grid_build_kernel(int n, const float2 *__restrict__ xy, const int32_t *__restric
     for (int s = t; s < n_in; s += GRID_THREADS) {
         const int i = cell_items[s];
         const float2 p = xy[i];
-        const int iy = cell_of[i] % rows;
+        const int iy = cof[i] % rows;
         items[s] = make_int4(__float_as_int(p.x), __float_as_int(p.y), (octave[i] & 0xffff) | (iy << 16), i);
         desc_sorted[2 * s] = desc[2 * i];
         desc_sorted[2 * s + 1] = desc[2 * i + 1];
@@ -169,11 +176,55 @@ __global__ void area_fill_kernel(FrameView f, int nq, const float *x, const floa
 // exported to the search kernels (same translation-unit-local template is re-declared there)
 extern "C" int orbgpu_frame_n(const orbgpu_frame *f) { return f ? f->n : 0; }
 
+// Frame slabs are recycled: the drop-in adapter uploads its frames on every call, and a cudaMalloc / cudaFree pair per frame
+// costs more than the upload itself (cudaFree also synchronises the device).  Process-wide, per device, bounded.
+namespace {
+struct SlabPool {
+    struct Entry { int device; char *p; size_t bytes; };
+    std::mutex mu;
+    std::vector<Entry> free_list;
+    size_t held = 0;
+};
+SlabPool g_slabs;
+constexpr size_t SLAB_POOL_BYTES = size_t(256) << 20;
+constexpr size_t SLAB_POOL_ENTRIES = 32;
+
+char *slab_take(int device, size_t need, size_t *got)
+{
+    std::lock_guard<std::mutex> lock(g_slabs.mu);
+    int best = -1;
+    for (int i = 0; i < (int)g_slabs.free_list.size(); i++) {
+        const SlabPool::Entry &e = g_slabs.free_list[i];
+        if (e.device != device || e.bytes < need || e.bytes > 2 * need + (size_t(1) << 20)) continue;
+        if (best < 0 || e.bytes < g_slabs.free_list[best].bytes) best = i;
+    }
+    if (best < 0) return nullptr;
+    const SlabPool::Entry e = g_slabs.free_list[best];
+    g_slabs.free_list.erase(g_slabs.free_list.begin() + best);
+    g_slabs.held -= e.bytes;
+    *got = e.bytes;
+    return e.p;
+}
+bool slab_give(int device, char *p, size_t bytes)
+{
+    std::lock_guard<std::mutex> lock(g_slabs.mu);
+    if (g_slabs.free_list.size() >= SLAB_POOL_ENTRIES || g_slabs.held + bytes > SLAB_POOL_BYTES) return false;
+    g_slabs.free_list.push_back({device, p, bytes});
+    g_slabs.held += bytes;
+    return true;
+}
+} // namespace
+
 extern "C" void orbgpu_frame_destroy(orbgpu_frame *f)
 {
     if (!f) return;
     cudaSetDevice(f->device);
-    if (f->slab) cudaFree(f->slab);
+    if (f->slab) {
+        // work that still reads the frame (device-pointer entry points do not synchronise) must be over before the slab can be
+        // handed to the next upload -- the same guarantee cudaFree gives
+        cudaDeviceSynchronize();
+        if (!slab_give(f->device, f->slab, f->slab_bytes)) cudaFree(f->slab);
+    }
     delete f;
 }
 
@@ -218,7 +269,11 @@ extern "C" int orbgpu_frame_upload(orbgpu_ctx *ctx, const orbgpu_frame_host *h, 
                  o_w = take(N * 4), o_nid = take(N * 4), o_wt = take(N * 8), o_bw = take(N * 4), o_bv = take(N * 8),
                  o_cof = take(N * 4), o_sk = take((size_t)f->sort_cap * 8), o_meta = take(64);
     f->slab_bytes = off;
-    CU_TRY(cudaMalloc(&f->slab, f->slab_bytes));
+    f->slab = slab_take(ctx->device, off, &f->slab_bytes);
+    if (!f->slab) {
+        f->slab_bytes = off;
+        CU_TRY(cudaMalloc(&f->slab, f->slab_bytes));
+    }
     char *S = f->slab;
     f->desc = (uint4 *)(S + o_desc); f->xy = (float2 *)(S + o_xy); f->octave = (int32_t *)(S + o_oct);
     f->angle = (float *)(S + o_ang); f->u_right = h->u_right ? (float *)(S + o_ur) : nullptr;
@@ -252,9 +307,12 @@ extern "C" int orbgpu_frame_upload(orbgpu_ctx *ctx, const orbgpu_frame_host *h, 
         for (int a = 0; a < h->fv_n_nodes; a++) f->fv_max_node = std::max(f->fv_max_node, h->fv_offsets[a + 1] - h->fv_offsets[a]);
     }
     CU_TRY(cudaMemcpyAsync(S, H, upload_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    grid_build_kernel<<<1, GRID_THREADS, (size_t)ncell * 4, ctx->stream>>>(n, f->xy, f->octave, f->desc, f->min_x, f->min_y, f->inv_w,
-                                                                          f->inv_h, f->cols, f->rows, f->cell_of, f->cell_start,
-                                                                          f->cell_items, f->items, f->desc_sorted);
+    const int cof_in_smem = ((size_t)ncell + N) * 4 <= 160 * 1024;
+    const size_t grid_smem = cof_in_smem ? ((size_t)ncell + N) * 4 : (size_t)ncell * 4;
+    if (grid_smem > 32 * 1024) CU_TRY(cudaFuncSetAttribute(grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grid_smem));
+    grid_build_kernel<<<1, GRID_THREADS, grid_smem, ctx->stream>>>(n, f->xy, f->octave, f->desc, f->min_x, f->min_y, f->inv_w, f->inv_h,
+                                                                  f->cols, f->rows, f->cell_of, f->cell_start, f->cell_items, f->items,
+                                                                  f->desc_sorted, cof_in_smem);
     LAUNCH_COUNT(ctx);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(ctx->stream)); // staging buffer is reusable after this
