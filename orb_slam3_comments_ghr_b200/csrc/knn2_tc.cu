@@ -29,6 +29,10 @@
 #include "internal.cuh"
 
 namespace {
+// bisection switches used while bringing the pipeline up (1 = skip the top-2 arithmetic, 2 = also the TMEM loads, 4/8 = narrow MMA
+// shapes, 16 = one k-block per stage); compiled out
+constexpr int TC_DBG = 0;
+
 
 constexpr int BM = 128;            // queries per CTA tile (UMMA M, TMEM lanes)
 constexpr int BN = 128;            // database rows per stage (UMMA N)
@@ -136,7 +140,6 @@ struct TcParams {
     uint16_t *out_second; // [n_splits][nq_pad]
     int32_t *out_stage;   // [n_splits][nq_pad] first database row of the winning stage
     int64_t out_stride;
-    int dbg;              // development aid (ORBGPU_TC_DEBUG): 1 = skip the top-2 arithmetic, 2 = also skip the TMEM loads
 };
 
 __device__ __forceinline__ __half2 u2h2(uint32_t u) { return *reinterpret_cast<__half2 *>(&u); }
@@ -191,8 +194,8 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 const int s0 = split * P.stages_per_split, s1 = min(P.total_stages, s0 + P.stages_per_split);
                 for (int s = s0; s < s1; s++) {
                     mbar_wait(smem_u32(&b_empty[sb]), pb ^ 1);
-                    mbar_expect_tx(smem_u32(&b_full[sb]), (P.dbg & 16) ? TILE_BYTES : STAGE_BYTES);
-                    for (int kb = 0; kb < ((P.dbg & 16) ? 1 : NUM_KB); kb++)
+                    mbar_expect_tx(smem_u32(&b_full[sb]), (TC_DBG & 16) ? TILE_BYTES : STAGE_BYTES);
+                    for (int kb = 0; kb < ((TC_DBG & 16) ? 1 : NUM_KB); kb++)
                         tma_load_2d(smem_u32(sB + sb * STAGE_BYTES + kb * TILE_BYTES), &map_db, smem_u32(&b_full[sb]), kb * KB_BYTES, s * BN);
                     if (++sb == NS) { sb = 0; pb ^= 1; }
                 }
@@ -219,7 +222,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                         const uint64_t bd = make_desc(smem_u32(sB + sb * STAGE_BYTES + kb * TILE_BYTES));
 #pragma unroll
                         for (int k = 0; k < KB_BYTES / 32; k++) // UMMA K = 32 bytes; advance start address by 32 B >> 4 = 2
-                            tc_mma_f8(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), (P.dbg & 4) ? (((uint32_t)(64 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24)) : ((P.dbg & 8) ? (((uint32_t)(BN >> 3) << 17) | ((uint32_t)(64 >> 4) << 24)) : IDESC), (kb | k) ? 1u : 0u);
+                            tc_mma_f8(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), (TC_DBG & 4) ? (((uint32_t)(64 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24)) : ((TC_DBG & 8) ? (((uint32_t)(BN >> 3) << 17) | ((uint32_t)(64 >> 4) << 24)) : IDESC), (kb | k) ? 1u : 0u);
                     }
                     tc_commit(smem_u32(&b_empty[sb])); // smem stage reusable once these MMAs retire
                     tc_commit(smem_u32(&t_full[ta]));  // accumulator ready for the epilogue
@@ -253,7 +256,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 pt[pi] ^= 1;
                 tc_fence_after();
                 uint32_t r0[32], r1[32];
-                if (!(P.dbg & 2)) {
+                if (!(TC_DBG & 2)) {
                     tc_ld_64cols_packed(lane_base + buf * BN, r0);
                     tc_ld_64cols_packed(lane_base + buf * BN + 64, r1);
                     tc_wait_ld();
@@ -278,7 +281,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                         r1[i] = *reinterpret_cast<uint32_t *>(&v1);
                     }
                 }
-                if (!(P.dbg & 1)) {
+                if (!(TC_DBG & 1)) {
 #pragma unroll
                 for (int i = 0; i < 32; i++) {
                     const __half2 v = u2h2(r0[i]);
@@ -766,7 +769,6 @@ int knn2_tc_run(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const uint4 *q
     TcParams P;
     P.nq = nq; P.nd = nd; P.n_qtiles = n_qtiles; P.n_splits = n_splits; P.stages_per_split = stages_per_split;
     P.total_stages = total_stages; P.out_best = pb; P.out_second = ps; P.out_stage = pst; P.out_stride = nq_pad;
-    P.dbg = getenv("ORBGPU_TC_DEBUG") ? atoi(getenv("ORBGPU_TC_DEBUG")) : 0;
     static bool attr_set = false;
     if (!attr_set) {
         CU_TRY(cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
