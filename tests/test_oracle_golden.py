@@ -129,10 +129,11 @@ def test_compute_distinctive_descriptors_vs_numpy(oracle):
         assert bi[p] == int(np.argmin(med)) and bm[p] == int(med.min())
 
 
-def test_stereo_coarse_match_vs_numpy(oracle):
+@pytest.mark.parametrize("seed,n,min_acc", [(151, 600, 100), (152, 900, 150), (153, 37, 1), (154, 1, 0)])
+def test_stereo_coarse_match_vs_numpy(oracle, seed, n, min_acc):
     """8(f) rank 3: Frame.cc does not compile here; the restatement of Frame.cc:1139-1216 is cross-checked with an independent
     numpy evaluation (row bands, octave and disparity filters, first minimum, acceptance threshold)."""
-    left, right, n_rows, mb, mbf = synth.make_stereo_case(151, n=600)
+    left, right, n_rows, mb, mbf = synth.make_stereo_case(seed, n=n)
     bi, bd = oracle.stereo_coarse_match(left, right, n_rows, mb, mbf)
     r = np.float32(2.0) * left.scale_factors[right.octave]
     maxr = np.ceil(right.kp_xy[:, 1] + r).astype(int)
@@ -150,4 +151,4 @@ def test_stereo_coarse_match_vs_numpy(oracle):
         assert bd[i] == best
         assert bi[i] == (j if best < 75 else -1)
         n_acc += bi[i] >= 0
-    assert n_acc > 100
+    assert n_acc >= min_acc
