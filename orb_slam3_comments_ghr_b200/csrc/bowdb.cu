@@ -115,7 +115,7 @@ extern "C" int orbgpu_bow_score_l1(orbgpu_ctx *ctx, const orbgpu_bowdb *db, int3
         CU_TRY(cudaMemcpyAsync(d_qv, q_values, (size_t)nq_words * 8, cudaMemcpyHostToDevice, ctx->stream));
         CU_TRY(cudaMemcpyAsync(d_qw, q_words, (size_t)nq_words * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
-    if (smem > 32 * 1024) CU_TRY(cudaFuncSetAttribute(bow_score_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > ORBGPU_SMEM_OPTIN - 1024) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "query BowVector too large for the shared-memory staging");
     bow_score_l1_kernel<<<(db->n_kf + BOW_THREADS - 1) / BOW_THREADS, BOW_THREADS, smem, ctx->stream>>>(
         db->n_kf, db->offsets, db->words, db->values, nq_words, d_qw, d_qv, d_cm, d_sc);
     LAUNCH_COUNT(ctx);
@@ -123,3 +123,5 @@ extern "C" int orbgpu_bow_score_l1(orbgpu_ctx *ctx, const orbgpu_bowdb *db, int3
     const OutPiece out[2] = {{common_words, d_cm, (size_t)db->n_kf * 4}, {scores, d_sc, (size_t)db->n_kf * 8}};
     return ctx_download(ctx, out, 2);
 }
+
+int bowdb_device_init() { return set_max_dyn_smem(bow_score_l1_kernel); }

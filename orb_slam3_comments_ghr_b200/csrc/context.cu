@@ -1,6 +1,7 @@
 // context.cu -- context, arena, error reporting of liborbmatch_b200.so
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 #include "internal.cuh"
 
@@ -26,6 +27,41 @@ extern "C" int orbgpu_device_count(void)
     return n;
 }
 
+namespace {
+std::mutex g_live_mu;
+std::vector<orbgpu_ctx *> g_live;
+} // namespace
+bool ctx_record_event_if_alive(orbgpu_ctx *ctx, cudaEvent_t ev)
+{
+    std::lock_guard<std::mutex> lock(g_live_mu);
+    for (orbgpu_ctx *c : g_live)
+        if (c == ctx) return cudaEventRecord(ev, ctx->stream) == cudaSuccess;
+    return false;
+}
+bool ctx_sync_if_alive(orbgpu_ctx *ctx)
+{
+    std::lock_guard<std::mutex> lock(g_live_mu);
+    for (orbgpu_ctx *c : g_live)
+        if (c == ctx) return cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+    return false;
+}
+
+// raises every kernel's dynamic shared-memory limit to the opt-in maximum, once per device and process
+static int device_attrs_once(int device)
+{
+    static std::mutex mu;
+    static bool done[64] = {false};
+    std::lock_guard<std::mutex> lock(mu);
+    if (device < 64 && done[device]) return ORBGPU_OK;
+    int rc;
+    if ((rc = frame_device_init()) || (rc = knn2_tc_device_init()) || (rc = search_init_device_init()) ||
+        (rc = search_proj_device_init()) || (rc = search_projected_device_init()) || (rc = search_bow_device_init()) ||
+        (rc = triangulation_device_init()) || (rc = voc_device_init()) || (rc = bowdb_device_init()))
+        return rc;
+    if (device < 64) done[device] = true;
+    return ORBGPU_OK;
+}
+
 static int create_common(int device, cudaStream_t s, bool own, orbgpu_ctx **out)
 {
     ARG_TRY(out != nullptr);
@@ -41,7 +77,10 @@ static int create_common(int device, cudaStream_t s, bool own, orbgpu_ctx **out)
     if (prop.major < 10)
         return orbgpu_fail(ORBGPU_ERR_NO_DEVICE, std::string("device ") + prop.name +
                                                      " is not sm_100-class: this library is built for sm_100a only");
+    int rc = device_attrs_once(device);
+    if (rc) return rc;
     orbgpu_ctx *c = new orbgpu_ctx();
+    OwnedHandle<orbgpu_ctx, orbgpu_destroy> owner(c); // an early return below releases the stream and the partial allocations
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     if (own) {
@@ -53,7 +92,11 @@ static int create_common(int device, cudaStream_t s, bool own, orbgpu_ctx **out)
     CU_TRY(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
     CU_TRY(cudaMallocHost(&c->h_counters, 8 * sizeof(unsigned long long)));
     CU_TRY(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), c->stream));
-    *out = c;
+    {
+        std::lock_guard<std::mutex> lock(g_live_mu);
+        g_live.push_back(c);
+    }
+    *out = owner.release();
     return ORBGPU_OK;
 }
 
@@ -66,8 +109,13 @@ extern "C" int orbgpu_create_on_stream(int device, void *cuda_stream, orbgpu_ctx
 extern "C" void orbgpu_destroy(orbgpu_ctx *ctx)
 {
     if (!ctx) return;
+    {
+        std::lock_guard<std::mutex> lock(g_live_mu);
+        for (size_t i = 0; i < g_live.size(); i++)
+            if (g_live[i] == ctx) { g_live.erase(g_live.begin() + i); break; }
+    }
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream || !ctx->own_stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->arena.base) cudaFree(ctx->arena.base);
     if (ctx->knn_expanded) cudaFree(ctx->knn_expanded);
     if (ctx->d_counters) cudaFree(ctx->d_counters);

@@ -177,10 +177,13 @@ __global__ void area_fill_kernel(FrameView f, int nq, const float *x, const floa
 extern "C" int orbgpu_frame_n(const orbgpu_frame *f) { return f ? f->n : 0; }
 
 // Frame slabs are recycled: the drop-in adapter uploads its frames on every call, and a cudaMalloc / cudaFree pair per frame
-// costs more than the upload itself (cudaFree also synchronises the device).  Process-wide, per device, bounded.
+// costs more than the upload itself (cudaFree also synchronises the device).  Process-wide, per device, bounded.  A slab that is
+// given back carries an event recorded on its owner's stream; the next upload that takes it makes ITS stream wait on that event,
+// so neither side ever stops the device -- the other threads' streams (Tracking / LocalMapping / LoopClosing each own a context)
+// keep running.
 namespace {
 struct SlabPool {
-    struct Entry { int device; char *p; size_t bytes; };
+    struct Entry { int device; char *p; size_t bytes; cudaEvent_t ev; };
     std::mutex mu;
     std::vector<Entry> free_list;
     size_t held = 0;
@@ -189,7 +192,7 @@ SlabPool g_slabs;
 constexpr size_t SLAB_POOL_BYTES = size_t(256) << 20;
 constexpr size_t SLAB_POOL_ENTRIES = 32;
 
-char *slab_take(int device, size_t need, size_t *got)
+char *slab_take(int device, size_t need, size_t *got, cudaEvent_t *ev)
 {
     std::lock_guard<std::mutex> lock(g_slabs.mu);
     int best = -1;
@@ -203,13 +206,14 @@ char *slab_take(int device, size_t need, size_t *got)
     g_slabs.free_list.erase(g_slabs.free_list.begin() + best);
     g_slabs.held -= e.bytes;
     *got = e.bytes;
+    *ev = e.ev;
     return e.p;
 }
-bool slab_give(int device, char *p, size_t bytes)
+bool slab_give(int device, char *p, size_t bytes, cudaEvent_t ev)
 {
     std::lock_guard<std::mutex> lock(g_slabs.mu);
     if (g_slabs.free_list.size() >= SLAB_POOL_ENTRIES || g_slabs.held + bytes > SLAB_POOL_BYTES) return false;
-    g_slabs.free_list.push_back({device, p, bytes});
+    g_slabs.free_list.push_back({device, p, bytes, ev});
     g_slabs.held += bytes;
     return true;
 }
@@ -220,10 +224,19 @@ extern "C" void orbgpu_frame_destroy(orbgpu_frame *f)
     if (!f) return;
     cudaSetDevice(f->device);
     if (f->slab) {
-        // work that still reads the frame (device-pointer entry points do not synchronise) must be over before the slab can be
-        // handed to the next upload -- the same guarantee cudaFree gives
-        cudaDeviceSynchronize();
-        if (!slab_give(f->device, f->slab, f->slab_bytes)) cudaFree(f->slab);
+        // work that still reads the frame (device-pointer entry points do not synchronise) is ordered before the slab's next use
+        // by an event on the owner's stream; a frame whose owner is gone has nothing in flight (orbgpu_destroy synchronised)
+        cudaEvent_t ev = nullptr;
+        bool pooled = false;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+            if (!ctx_record_event_if_alive(f->owner, ev)) { cudaEventDestroy(ev); ev = nullptr; }
+            pooled = slab_give(f->device, f->slab, f->slab_bytes, ev);
+        }
+        if (!pooled) {
+            if (ev) cudaEventDestroy(ev);
+            ctx_sync_if_alive(f->owner);
+            cudaFree(f->slab);
+        }
     }
     delete f;
 }
@@ -262,22 +275,28 @@ extern "C" int orbgpu_frame_upload(orbgpu_ctx *ctx, const orbgpu_frame_host *h, 
     // slab layout: [uploaded part | device-only part]
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
-    const size_t o_desc = take(N * 32), o_xy = take(N * 8), o_oct = take(N * 4), o_ang = take(N * 4), o_ur = take(N * 4),
+    const size_t o_desc = take(N * 32), o_xy = take(N * 8), o_oct = take(N * 4), o_ang = take(N * 4), o_ur = take(N * 4), o_r0 = take(N * 4),
                  o_sf = take(nl * 4), o_s2 = take(nl * 4), o_fvn = take(N * 4), o_fvo = take((N + 1) * 4), o_fvf = take(N * 4);
     const size_t upload_bytes = off;
     const size_t o_cs = take((size_t)(ncell + 1) * 4), o_ci = take(N * 4), o_it = take(N * 16), o_ds = take(N * 32),
                  o_w = take(N * 4), o_nid = take(N * 4), o_wt = take(N * 8), o_bw = take(N * 4), o_bv = take(N * 8),
                  o_cof = take(N * 4), o_sk = take((size_t)f->sort_cap * 8), o_meta = take(64);
     f->slab_bytes = off;
-    f->slab = slab_take(ctx->device, off, &f->slab_bytes);
+    f->owner = ctx;
+    cudaEvent_t reuse_ev = nullptr;
+    f->slab = slab_take(ctx->device, off, &f->slab_bytes, &reuse_ev);
     if (!f->slab) {
         f->slab_bytes = off;
         CU_TRY(cudaMalloc(&f->slab, f->slab_bytes));
+    } else if (reuse_ev) { // the previous user's work on this slab comes first -- on the device, without stopping the host
+        const cudaError_t we = cudaStreamWaitEvent(ctx->stream, reuse_ev, 0);
+        cudaEventDestroy(reuse_ev);
+        CU_TRY(we);
     }
     char *S = f->slab;
     f->desc = (uint4 *)(S + o_desc); f->xy = (float2 *)(S + o_xy); f->octave = (int32_t *)(S + o_oct);
     f->angle = (float *)(S + o_ang); f->u_right = h->u_right ? (float *)(S + o_ur) : nullptr;
-    f->scale_factors = (float *)(S + o_sf); f->level_sigma2 = (float *)(S + o_s2);
+    f->scale_factors = (float *)(S + o_sf); f->level_sigma2 = (float *)(S + o_s2); f->rank0 = (int32_t *)(S + o_r0);
     f->fv_node_ids = (uint32_t *)(S + o_fvn); f->fv_offsets = (int32_t *)(S + o_fvo); f->fv_features = (uint32_t *)(S + o_fvf);
     f->cell_start = (int32_t *)(S + o_cs); f->cell_items = (int32_t *)(S + o_ci); f->items = (int4 *)(S + o_it);
     f->desc_sorted = (uint4 *)(S + o_ds); f->word_id = (uint32_t *)(S + o_w); f->node_id = (uint32_t *)(S + o_nid);
@@ -294,6 +313,10 @@ extern "C" int orbgpu_frame_upload(orbgpu_ctx *ctx, const orbgpu_frame_host *h, 
         memcpy(H + o_oct, h->octave, (size_t)n * 4);
         memcpy(H + o_ang, h->angle, (size_t)n * 4);
         if (h->u_right) memcpy(H + o_ur, h->u_right, (size_t)n * 4);
+        int32_t *r0 = (int32_t *)(H + o_r0);
+        int n0 = 0;
+        for (int i = 0; i < n; i++) r0[i] = h->octave[i] <= 0 ? n0++ : -1;
+        f->n_level0 = n0;
     }
     memcpy(H + o_sf, h->scale_factors, (size_t)nl * 4);
     memcpy(H + o_s2, h->level_sigma2, (size_t)nl * 4);
@@ -309,7 +332,6 @@ extern "C" int orbgpu_frame_upload(orbgpu_ctx *ctx, const orbgpu_frame_host *h, 
     CU_TRY(cudaMemcpyAsync(S, H, upload_bytes, cudaMemcpyHostToDevice, ctx->stream));
     const int cof_in_smem = ((size_t)ncell + N) * 4 <= 160 * 1024;
     const size_t grid_smem = cof_in_smem ? ((size_t)ncell + N) * 4 : (size_t)ncell * 4;
-    if (grid_smem > 32 * 1024) CU_TRY(cudaFuncSetAttribute(grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grid_smem));
     grid_build_kernel<<<1, GRID_THREADS, grid_smem, ctx->stream>>>(n, f->xy, f->octave, f->desc, f->min_x, f->min_y, f->inv_w, f->inv_h,
                                                                   f->cols, f->rows, f->cell_of, f->cell_start, f->cell_items, f->items,
                                                                   f->desc_sorted, cof_in_smem);
@@ -370,3 +392,5 @@ extern "C" int orbgpu_features_in_area(orbgpu_ctx *ctx, const orbgpu_frame *f, i
     }
     return ORBGPU_OK;
 }
+
+int frame_device_init() { return set_max_dyn_smem(grid_build_kernel); }

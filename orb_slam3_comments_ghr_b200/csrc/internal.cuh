@@ -67,6 +67,11 @@ struct orbgpu_ctx {
     size_t h_out_bytes = 0;
 };
 int stage_reserve(orbgpu_ctx *ctx, size_t bytes);
+// live-context registry (context.cu): objects that outlive a call (frame slabs) order their release after the owning context's
+// stream with an event instead of a device-wide synchronisation.  Returns false when the context is gone (its stream was
+// synchronised at orbgpu_destroy, so nothing can still be reading the object).
+bool ctx_record_event_if_alive(orbgpu_ctx *ctx, cudaEvent_t ev);
+bool ctx_sync_if_alive(orbgpu_ctx *ctx);
 
 // returns a 256-byte aligned device pointer valid until the next arena_reset; grows (with a
 // stream sync + realloc) when needed -- only ever called BEFORE any kernel of the API call
@@ -77,6 +82,32 @@ inline void arena_reset(orbgpu_ctx *ctx) { ctx->arena.used = 0; }
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 int ctx_begin(orbgpu_ctx *ctx); // set device, reset arena, zero counters
+
+// Per-device kernel attributes.  cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device, per-function limit: it is raised ONCE
+// per device, to the opt-in maximum, when the first context on that device is created (context.cu: device_attrs_once) -- never per
+// call, so two host threads cannot lower each other's limit between a set and a launch, and a second GPU in the same process gets
+// its own opt-in.  Every translation unit lists its kernels in <unit>_device_init().
+template <class K>
+inline int set_max_dyn_smem(K kern)
+{
+    int dev = 0, optin = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    CU_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    cudaFuncAttributes a;
+    CU_TRY(cudaFuncGetAttributes(&a, kern));
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)a.sharedSizeBytes));
+    return ORBGPU_OK;
+}
+constexpr size_t ORBGPU_SMEM_OPTIN = 227 * 1024; // sm_100: 232448 bytes per block (static + dynamic)
+int frame_device_init();
+int knn2_tc_device_init();
+int search_init_device_init();
+int search_proj_device_init();
+int search_projected_device_init();
+int search_bow_device_init();
+int triangulation_device_init();
+int voc_device_init();
+int bowdb_device_init();
 struct orbgpu_voc;
 // voc.cu: FeatureVector node of n descriptors (0xFFFFFFFF for stopped words), comparisons added to counters[0]
 int launch_voc_transform_nodes(orbgpu_ctx *ctx, const orbgpu_voc *voc, long long n, const uint4 *desc, int levelsup, uint32_t *node_id);
@@ -98,6 +129,7 @@ int ctx_download(orbgpu_ctx *ctx, const OutPiece *pieces, int n);
 
 struct orbgpu_frame {
     int device = 0;
+    orbgpu_ctx *owner = nullptr; // uploading context (only dereferenced through the live-context registry)
     char *slab = nullptr;      // one device allocation holding every array below
     size_t slab_bytes = 0;
     int32_t *cell_of = nullptr; // [n] temp: cell id per feature (-1 outside the grid)
@@ -114,6 +146,8 @@ struct orbgpu_frame {
     int32_t *octave = nullptr;  // [n]
     float *angle = nullptr;     // [n]
     float *u_right = nullptr;   // [n] or null
+    int32_t *rank0 = nullptr;   // [n] rank of the feature among the level-0 features (octave <= 0), -1 for the others
+    int n_level0 = 0;           // number of level-0 features (SearchForInitialization only looks at those, ORBmatcher.cc:762,768)
     float *scale_factors = nullptr; // [n_levels]
     float *level_sigma2 = nullptr;
     // CSR cell index (cell = ix*rows+iy), in-cell ascending feature id

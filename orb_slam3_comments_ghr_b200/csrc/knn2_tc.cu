@@ -769,12 +769,6 @@ int knn2_tc_run(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const uint4 *q
     TcParams P;
     P.nq = nq; P.nd = nd; P.n_qtiles = n_qtiles; P.n_splits = n_splits; P.stages_per_split = stages_per_split;
     P.total_stages = total_stages; P.out_best = pb; P.out_second = ps; P.out_stage = pst; P.out_stride = nq_pad;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CU_TRY(cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        CU_TRY(cudaFuncSetAttribute(knn2_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-        attr_set = true;
-    }
     if (two_cta) {
         const int grid = 2 * std::min(n_units * n_splits, n_workers); // whole clusters
         knn2_tc2_kernel<<<grid, NUM_THREADS, SMEM2_BYTES, ctx->stream>>>(mq, mdb, P);
@@ -789,4 +783,11 @@ int knn2_tc_run(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const uint4 *q
     LAUNCH_COUNT(ctx);
     CU_TRY(cudaGetLastError());
     return ORBGPU_OK;
+}
+
+int knn2_tc_device_init()
+{
+    int rc = set_max_dyn_smem(knn2_tc_kernel);
+    if (rc) return rc;
+    return set_max_dyn_smem(knn2_tc2_kernel);
 }

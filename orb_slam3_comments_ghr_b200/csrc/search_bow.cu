@@ -420,11 +420,9 @@ int run_bow(orbgpu_ctx *ctx, int mode, const orbgpu_frame *kf, const orbgpu_fram
         const size_t smem = (size_t)stage_cap * 41; // 32 B descriptor + feature id + angle + flag
         const FrameView vk = frame_view(kf), vf = frame_view(f);
         if (mode == 0) {
-            CU_TRY(cudaFuncSetAttribute(bow_match_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 1024 ? smem : 1024)));
             bow_match_kernel<0><<<kf->fv_n_nodes, threads, smem, ctx->stream>>>(vk, vf, d_kfv, d_fv, nnratio, check_ori, d_match, d_m2, d_bin,
                                                                                d_hist, d_nm, ctx->d_counters, stage_cap, big ? 1 : 0);
         } else {
-            CU_TRY(cudaFuncSetAttribute(bow_match_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 1024 ? smem : 1024)));
             bow_match_kernel<1><<<kf->fv_n_nodes, threads, smem, ctx->stream>>>(vk, vf, d_kfv, d_fv, nnratio, check_ori, d_match, d_m2, d_bin,
                                                                                d_hist, d_nm, ctx->d_counters, stage_cap, big ? 1 : 0);
         }
@@ -434,14 +432,13 @@ int run_bow(orbgpu_ctx *ctx, int mode, const orbgpu_frame *kf, const orbgpu_fram
             const int n1_cap = kf->fv_max_node, n2_cap = f->fv_max_node;
             const size_t smem_big = ((size_t)n2_cap + 2 * (size_t)n1_cap) * 4;
             const int blocks = (int)(((size_t)kf->n * 32 + 255) / 256);
+            if (smem_big > ORBGPU_SMEM_OPTIN - 4096) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "node too large for the shared-memory lock table");
             if (mode == 0) {
                 bow_big_lists_kernel<0><<<blocks, 256, 0, ctx->stream>>>(vk, vf, d_kfv, d_fv, d_lists, d_meta);
-                CU_TRY(cudaFuncSetAttribute(bow_big_resolve_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_big > 1024 ? smem_big : 1024)));
                 bow_big_resolve_kernel<0><<<kf->fv_n_nodes, 1024, smem_big, ctx->stream>>>(vk, vf, d_kfv, d_fv, d_lists, d_meta, nnratio, check_ori, d_match,
                                                                                          d_bin, d_hist, d_nm, ctx->d_counters, n1_cap, n2_cap);
             } else {
                 bow_big_lists_kernel<1><<<blocks, 256, 0, ctx->stream>>>(vk, vf, d_kfv, d_fv, d_lists, d_meta);
-                CU_TRY(cudaFuncSetAttribute(bow_big_resolve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_big > 1024 ? smem_big : 1024)));
                 bow_big_resolve_kernel<1><<<kf->fv_n_nodes, 1024, smem_big, ctx->stream>>>(vk, vf, d_kfv, d_fv, d_lists, d_meta, nnratio, check_ori, d_match,
                                                                                          d_bin, d_hist, d_nm, ctx->d_counters, n1_cap, n2_cap);
             }
@@ -496,4 +493,13 @@ extern "C" int orbgpu_search_by_bow_kf_kf(orbgpu_ctx *ctx, const orbgpu_frame *k
     ARG_TRY(ctx && kf1 && kf2 && nmatches && (kf1->n == 0 || (match_12 && kf1_mp_valid)) && (kf2->n == 0 || kf2_mp_valid));
     ARG_TRY(kf2->n < (1 << 20));
     return run_bow(ctx, 1, kf1, kf2, kf1_mp_valid, kf2_mp_valid, nnratio, check_ori, match_12, nmatches);
+}
+
+int search_bow_device_init()
+{
+    int rc;
+    if ((rc = set_max_dyn_smem(bow_match_kernel<0>)) || (rc = set_max_dyn_smem(bow_match_kernel<1>)) ||
+        (rc = set_max_dyn_smem(bow_big_resolve_kernel<0>)) || (rc = set_max_dyn_smem(bow_big_resolve_kernel<1>)))
+        return rc;
+    return ORBGPU_OK;
 }

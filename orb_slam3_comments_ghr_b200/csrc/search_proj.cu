@@ -226,8 +226,6 @@ extern "C" int orbgpu_search_by_projection_local(orbgpu_ctx *ctx, const orbgpu_f
                                                                          ctx->d_counters);
     const size_t lock_bytes = (size_t)n * sizeof(int);
     if (lock_bytes > 200 * 1024) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "frame too large for the shared-memory lock table");
-    if (lock_bytes > 32 * 1024) // static shared memory counts against the 48 KB default too
-        CU_TRY(cudaFuncSetAttribute(proj_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lock_bytes));
     proj_resolve_kernel<<<1, RESOLVE_THREADS, lock_bytes, ctx->stream>>>(v, mv, lists, stride, counts, nnratio, cur_obs, choice, d_kpmp,
                                                                         d_nm, ctx->d_counters);
     ctx->launches += 2;
@@ -235,3 +233,5 @@ extern "C" int orbgpu_search_by_projection_local(orbgpu_ctx *ctx, const orbgpu_f
     const OutPiece out[2] = {{kp_mp, d_kpmp, (size_t)n * 4}, {nmatches, d_nm, 4}};
     return ctx_download(ctx, out, 2);
 }
+
+int search_proj_device_init() { return set_max_dyn_smem(proj_resolve_kernel); }

@@ -257,8 +257,6 @@ extern "C" int orbgpu_search_projected(orbgpu_ctx *ctx, const orbgpu_frame *f, c
                                                                               (const float *)(D + o_sig), lists, stride, counts);
     const size_t lock_bytes = (size_t)n * sizeof(int);
     if (lock_bytes > 200 * 1024) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "frame too large for the shared-memory lock table");
-    if (lock_bytes > 32 * 1024) // static shared memory counts against the 48 KB default too
-        CU_TRY(cudaFuncSetAttribute(projected_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lock_bytes));
     projected_resolve_kernel<<<1, PR_THREADS, lock_bytes, ctx->stream>>>(v, pv, lists, stride, counts, prm->max_dist, prm->ordered,
                                                                         prm->check_ori, kp_locked ? (const uint8_t *)(D + o_kl) : nullptr,
                                                                         choice, d_bd, kp_owner ? d_owner : nullptr, d_nm, ctx->d_counters);
@@ -268,3 +266,5 @@ extern "C" int orbgpu_search_projected(orbgpu_ctx *ctx, const orbgpu_frame *f, c
                              {kp_owner, kp_owner ? d_owner : nullptr, (size_t)n * 4}, {nmatches, d_nm, 4}};
     return ctx_download(ctx, out, 4);
 }
+
+int search_projected_device_init() { return set_max_dyn_smem(projected_resolve_kernel); }

@@ -922,7 +922,6 @@ static int kfset_build_csr(orbgpu_ctx *ctx, orbgpu_kfset *s)
     int cap = 1;
     while (cap < s->n_feat) cap <<= 1;
     const size_t smem = (size_t)cap * 8;
-    CU_TRY(cudaFuncSetAttribute(kfset_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kfset_csr_kernel<<<s->n_kf, 1024, smem, ctx->stream>>>(s->n_feat, cap, s->node_id, s->has_mp, s->desc, s->xy, s->octave, s->kf_n_nodes,
                                                           s->kf_node_ids, s->kf_node_off, s->kf_feat, s->desc_csr, s->kp_csr, s->kf_n_free,
                                                           d_max, s->blob, s->blob_stride, s->blob_bytes, s->aux);
@@ -1063,7 +1062,6 @@ static int tri_launch(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs, c
             P.timeline = (long long *)ctx->tri_timeline;
             auto kern2 = triangulation_stream_kernel<NC, NG, NJ>;
             const size_t smem2 = stage_bytes * n_stages;
-            CU_TRY(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
             const int grid = n_pairs < ctx->sm_count ? n_pairs : ctx->sm_count;
             kern2<<<grid, (NC + NG + NJ + 1) * 32, smem2, ctx->stream>>>(P);
             LAUNCH_COUNT(ctx);
@@ -1075,8 +1073,6 @@ static int tri_launch(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs, c
     const size_t smem = (size_t)s->max_free * (64 + 4 + 1) + (size_t)s->max_nodes * 16 + 64;
     if (smem > 227 * 1024) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "keyframes too large for the shared-memory staging");
     auto kern = s->u_right ? triangulation_pairs_kernel<true> : triangulation_pairs_kernel<false>;
-    // always opt in: the kernel also has ~8.5 KB of static shared memory, so dynamic sizes just under 48 KB need it too
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<n_pairs, TRI_THREADS, smem, ctx->stream>>>(kfset_view(s), n_pairs, s->max_free, s->max_nodes, kf1_dev, kf2_dev, ep_dev, f12_dev,
                                                      only_stereo, coarse, check_ori, matches12_dev, nmatches_dev, ctx->d_counters);
     LAUNCH_COUNT(ctx);
@@ -1200,4 +1196,13 @@ extern "C" int orbgpu_search_for_triangulation_batch_pairs(orbgpu_ctx *ctx, cons
         CU_TRY(cudaStreamSynchronize(ctx->stream));
     }
     return *total <= cap ? ORBGPU_OK : orbgpu_fail(ORBGPU_ERR_OVERFLOW, "pairs capacity too small: see *total");
+}
+
+int triangulation_device_init()
+{
+    int rc;
+    if ((rc = set_max_dyn_smem(kfset_csr_kernel)) || (rc = set_max_dyn_smem(triangulation_stream_kernel<16, 12, 3>)) ||
+        (rc = set_max_dyn_smem(triangulation_pairs_kernel<true>)) || (rc = set_max_dyn_smem(triangulation_pairs_kernel<false>)))
+        return rc;
+    return ORBGPU_OK;
 }

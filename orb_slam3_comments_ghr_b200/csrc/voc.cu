@@ -351,7 +351,6 @@ extern "C" int orbgpu_transform(orbgpu_ctx *ctx, const orbgpu_voc *voc, orbgpu_f
     if (store_featvec) {
         const size_t smem = (size_t)f->sort_cap * 8;
         if (smem <= 160 * 1024) {
-            CU_TRY(cudaFuncSetAttribute(featvec_bow_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 1024 ? smem : 1024)));
             featvec_bow_build_kernel<<<2, SORT_THREADS, smem, ctx->stream>>>(0, n, f->sort_cap, f->node_id, f->word_id, f->weight, nullptr,
                                                                            f->fv_node_ids, f->fv_offsets, f->fv_features, f->bow_words, tmp_off,
                                                                            f->bow_values, f->fv_meta);
@@ -399,3 +398,5 @@ extern "C" int orbgpu_featvec_download(orbgpu_ctx *ctx, const orbgpu_frame *f, i
                              {features, f->fv_features, (size_t)f->fv_total * 4}};
     return ctx_download(ctx, out, 3);
 }
+
+int voc_device_init() { return set_max_dyn_smem(featvec_bow_build_kernel); }

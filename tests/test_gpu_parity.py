@@ -71,7 +71,7 @@ def test_init_golden(ctx, M, name):
 
 
 @pytest.mark.parametrize("seed,n,ratio,ori", [(201, 1000, 0.9, 1), (202, 1000, 0.6, 0), (203, 300, 0.9, 1), (204, 2500, 0.95, 1), (205, 1, 0.9, 1),
-                                              (206, 1800, 0.9, 1)])  # 1000: accept fixed point; 1800: staged ordered replay; 2500: replay from global
+                                              (206, 1800, 0.9, 1)])  # 1000: lists + inverse index in shared memory; 1800: inverse index in global memory; 2500: lists in global memory too
 def test_init_oracle(ctx, M, oracle, seed, n, ratio, ori):
     c = synth.make_init_case(seed, n=n)
     m = M.ORBmatcher(ratio, bool(ori), ctx)
@@ -508,6 +508,22 @@ def test_projection_stereo(ctx, M, oracle, seed, th):
     exp = oracle.search_by_projection_local(c.frame, c.mps, th, 0, 50.0, c.nnratio, c.kp_prior_obs, c.kp_mp)
     assert got[0] == exp[0] and np.array_equal(got[1], exp[1])
     assert ctx.last_comparisons == oracle.comparisons()
+
+
+@pytest.mark.parametrize("seed,n,all_level0", [(221, 7500, False), (222, 10000, False), (223, 9000, True), (224, 11000, True)])
+def test_init_large_monocular(ctx, M, oracle, seed, n, all_level0):
+    """monocular initialisation extracts 5 x nFeatures key points (Tracking.cc:667): 7.5 k - 10 k per frame.  With every key point
+    on level 0 the per-partner state (9000) and also the per-key-point state (11000) no longer fit shared memory and live in
+    global memory -- same fixed point, same results."""
+    c = synth.make_init_case(seed, n=n, window_size=60 if all_level0 else 100)
+    if all_level0:
+        c.f1.octave[:] = 0
+        c.f2.octave[:] = 0
+    got = M.ORBmatcher(0.9, True, ctx).SearchForInitialization(ctx.upload_frame(c.f1), ctx.upload_frame(c.f2), c.prev_matched, c.window_size)
+    oracle.reset_comparisons()
+    exp = oracle.search_for_initialization(c.f1, c.f2, c.prev_matched, c.window_size, 0.9, 1)
+    assert got[0] == exp[0] and np.array_equal(got[1], exp[1]) and np.array_equal(got[2], exp[2])
+    assert ctx.last_comparisons == oracle.comparisons() and exp[0] > 100
 
 
 def test_large_frames_shared_memory_opt_in(ctx, M, oracle):
