@@ -1,18 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- Hamming comparisons/s of the descriptor-matching hot path on B200.
+"""bench.py -- Hamming comparisons/s and frame pairs matched/s of the descriptor-matching hot path on B200.
 
-Headline workload (BASELINE.json configs[4], the largest single-GPU configuration): brute-force
-2-NN Hamming search with ratio test, 256k query descriptors vs a 4M-descriptor database
-(relocalization scale).  One "step" = one full pass: every query against every database row,
-best / second-best reduction, ratio test, match indices out.
+Headline workload (BASELINE.json configs[4], the largest single-GPU configuration): brute-force 2-NN Hamming search with
+ratio test, 256k query descriptors vs a 4M-descriptor database (relocalization scale).  One "step" = one full pass: every
+query against every database row, best / second-best reduction, ratio test, match indices out.
+
+The same JSON line carries a `secondary` block with the other half of BASELINE's metric and the single-frame configs:
+  secondary.c4        batched SearchForTriangulation, 4096 keyframe pairs x 2000 features (frame pairs/s), same keys as the
+                      main line (value, ms_per_step, clocks, roofline, roofline_hbm, cpu_baseline, e2e, gpu_launches)
+  secondary.reloc_2k  the real relocalisation shape: ONE frame (2000 queries) against the 4M database
+  secondary.c1/c2/c3  single frame pair latencies through the host-pointer C-ABI next to the reference CPU code (N = 1 only:
+                      single frame pairs do not shard)
 
   python bench.py --gpus N --steps K --warmup W            (torchrun launches N ranks for N > 1)
   python bench.py --impl reference ...                     reference CPU implementation on host cores
+  python bench.py --workload c4 ...                        C4 as the main line
 
-Multi-GPU: queries are sharded contiguously by row over the ranks (database replicated), each rank
-searches its rows, and ONE NCCL all-gather of the match indices assembles the result ("strong"
-scaling: the total work is fixed by the config).  The secondary workload `--workload c4` is the
-batched SearchForTriangulation (4096 keyframe pairs x 2000 features), reported in frame pairs/s.
+Multi-GPU: C5 queries are sharded contiguously by row over the ranks (database replicated), ONE NCCL all-gather of the match
+indices.  C4 pairs are sharded by index; the search kernel itself stores the compact vMatchedPairs of every finished pair into
+the buffers of all ranks over NVLink peer memory (torch symmetric memory) and the ranks meet through epoch flags.  Total work
+is fixed by the config -> "scaling": "strong".
 """
 from __future__ import annotations
 
@@ -32,6 +39,7 @@ sys.path.insert(0, ROOT)
 NQ_FULL, ND_FULL = 262144, 4194304      # BASELINE.json: "256k query vs 4M database descriptors"
 C4_PAIRS, C4_FEAT = 4096, 2000          # BASELINE.json: "4096 keyframe pairs x 2000 features"
 TH_LOW, NNRATIO = 50, 0.8
+C4_SEED = 20261018
 
 
 def env_int(name, default):
@@ -42,13 +50,14 @@ def env_int(name, default):
 
 
 # ------------------------------------------------------------------------------------------
-# clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
+# clocks sampling (B200_PROFILING.md "clocks DURING the timed region"): nvidia-smi runs beside the benchmark and every sample
+# carries its own timestamp; only samples inside [t0, t1] of the timed region are used
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device_index: int):
-        self.idx = device_index
+    def __init__(self, device_index: int, period_ms: int = 100):
+        self.idx, self.period = device_index, period_ms
         self.proc = None
         self.path = None
 
@@ -56,12 +65,24 @@ class ClockSampler:
         try:
             fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
             os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(self.period),
                                           "-i", str(self.idx)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def wait_first_sample(self, timeout=3.0):
+        """nvidia-smi needs a few hundred ms to start: the timed region begins once it is sampling"""
+        t = time.time()
+        while self.proc is not None and time.time() - t < timeout:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return True
+            except OSError:
+                pass
+            time.sleep(0.02)
+        return False
+
+    def stop(self, t0=None, t1=None):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -70,18 +91,22 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             pass
+        import datetime
         sm, mx, reasons = [], [], set()
         try:
             for line in open(self.path):
                 p = [x.strip() for x in line.split(",")]
-                if len(p) < 9:
+                if len(p) < 10:
                     continue
                 try:
-                    sm.append(float(p[1]))
-                    mx.append(float(p[2]))
+                    ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.05):
+                        continue
+                    sm.append(float(p[2]))
+                    mx.append(float(p[3]))
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[6:10]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
             os.unlink(self.path)
@@ -145,15 +170,16 @@ def cpu_knn_baseline(nd: int, want_seconds: float = 12.0, prefer_reference: bool
 
 
 def cpu_tri_baseline(case, want_seconds: float = 10.0):
+    """reference SearchForTriangulation on the first pairs of the SAME case the GPU arm runs, all host threads"""
     from oracle.pyoracle import Oracle, Reference
     cores = os.cpu_count() or 1
     P = case.kf1.shape[0]
     if Reference.available(fast=True):
         impl, kind = Reference(fast=True), "reference"
-        run = lambda n: impl.search_for_triangulation_batch(case.kfs, case.kf1[:n], case.kf2[:n], case.T1w[:n], case.T2w[:n], case.K, 0, 0, 0, 0.6, cores)
+        run = lambda n: impl.search_for_triangulation_batch(case.kfs, case.kf1[:n], case.kf2[:n], case.T1w[:n], case.T2w[:n], case.K, 0, 0, 0, 0.6, cores)  # noqa: E731
     else:
         impl, kind = Oracle(), "port"
-        run = lambda n: impl.search_for_triangulation_batch(case.kfs, case.kf1[:n], case.kf2[:n], case.ep[:n], case.f12[:n], 0, 0, 0, cores)
+        run = lambda n: impl.search_for_triangulation_batch(case.kfs, case.kf1[:n], case.kf2[:n], case.ep[:n], case.f12[:n], 0, 0, 0, cores)  # noqa: E731
     n0 = min(P, max(cores, 16))
     t = time.perf_counter(); run(n0); t0 = time.perf_counter() - t
     n = int(min(P, max(n0, n0 * want_seconds / max(t0, 1e-3))))
@@ -166,7 +192,11 @@ def cpu_tri_baseline(case, want_seconds: float = 10.0):
     dt = time.perf_counter() - t
     val = n * reps / dt
     return val, {"value": val, "unit": "frame_pairs/s", "cores": cores, "kind": kind,
-                 "sample": f"{reps} x {n} of {C4_PAIRS} keyframe pairs x {case.kfs.n_feat} features, {dt:.1f} s, {cores} threads"}
+                 "sample": f"{reps} x the first {n} of {P} keyframe pairs x {case.kfs.n_feat} features of the GPU arm's case, {dt:.1f} s, {cores} threads"}
+
+
+def c4_case(synth, seed, n_pairs):
+    return synth.fill_geometry(synth.make_triangulation_case(seed, n_pairs=max(n_pairs, 1), n_feat=C4_FEAT))
 
 
 # ------------------------------------------------------------------------------------------
@@ -177,13 +207,15 @@ def run_reference(args, rank, world):
         return
     nd = args.nd
     vals, info = [], None
+    case = None
+    if args.workload == "c4":
+        from orb_slam3_comments_ghr_b200 import synth
+        case = c4_case(synth, C4_SEED, args.pairs)  # the GPU arm's case (rank 0's shard at N = 1 is the whole batch)
     for s in range(args.warmup + args.steps):
         per = max(4.0, min(20.0, 150.0 / max(1, args.warmup + args.steps)))
         if args.workload == "c5":
             v, info = cpu_knn_baseline(nd, want_seconds=per)
         else:
-            from orb_slam3_comments_ghr_b200 import synth
-            case = synth.fill_geometry(synth.make_triangulation_case(9, n_pairs=256, n_feat=C4_FEAT))
             v, info = cpu_tri_baseline(case, want_seconds=per)
         if s >= args.warmup:
             vals.append(v)
@@ -192,20 +224,408 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "hamming_comparisons_per_s" if args.workload == "c5" else "frame_pairs_matched_per_s",
             "value": value, "unit": info["unit"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
-            "data": "synthetic", "config": workload_config(args), "cpu_baseline": info,
+            "data": "synthetic", "config": workload_config(args.workload, args), "cpu_baseline": info,
             "e2e": {"value": value, "unit": info["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args):
-    if args.workload == "c5":
+def workload_config(workload, args):
+    if workload == "c5":
         return {"workload": f"C5 brute-force 2-NN Hamming + ratio test: {args.nq} queries x {args.nd} database descriptors (256-bit), "
                             f"th_low={TH_LOW}, nnratio={NNRATIO}", "nq": args.nq, "nd": args.nd,
                 "sharding": "queries by row, database replicated, one all-gather of match indices",
                 "l2": "L2 flushed (512 MiB write) between timed steps; database (128 MiB) also exceeds L2"}
     return {"workload": f"C4 batched SearchForTriangulation: {args.pairs} keyframe pairs x {C4_FEAT} features, epipolar check, checkOri=false",
-            "pairs": args.pairs, "n_feat": C4_FEAT, "sharding": "pairs by index, keyframe set per rank, one all-gather of match indices",
-            "l2": "L2 flushed (512 MiB write) between timed steps"}
+            "pairs": args.pairs, "n_feat": C4_FEAT,
+            "sharding": "pairs by index, keyframe set per rank; result = vMatchedPairs (ORBmatcher.cc:1317-1325) of ALL pairs on every rank: "
+                        "compact (idx1, idx2) uint16 pairs stored by the search kernel into every rank's buffer over NVLink peer memory, "
+                        "epoch flags, no barrier",
+            "l2": "L2 flushed (512 MiB write) between timed steps, every step timed with its own CUDA event pair"}
+
+
+class Env:
+    pass
+
+
+# ------------------------------------------------------------------------------------------
+def bench_c5(E, args, K, W):
+    torch, dist, matcher = E.torch, E.dist, E.matcher
+    from orb_slam3_comments_ghr_b200.sharding import all_gather_rows, shard_bounds
+    dev, rank, world, ctx = E.dev, E.rank, E.world, E.ctx
+    nq_total, nd = args.nq, args.nd
+    lo, hi = shard_bounds(nq_total, rank, world)
+    nq = hi - lo
+    g = torch.Generator(device=dev)
+    g.manual_seed(20261018)
+    db = torch.randint(0, 256, (nd, 32), dtype=torch.uint8, device=dev, generator=g)
+    q_all = torch.randint(0, 256, (nq_total, 32), dtype=torch.uint8, device=dev, generator=g)
+    n_pl = nq_total // 10  # 10 % planted: database rows with ~1/16 of the bits flipped
+    who = torch.randperm(nq_total, device=dev, generator=g)[:n_pl]
+    src = torch.randint(0, nd, (n_pl,), device=dev, generator=g)
+    mask = torch.randint(0, 256, (n_pl, 32), dtype=torch.uint8, device=dev, generator=g)
+    for _ in range(3):
+        mask &= torch.randint(0, 256, (n_pl, 32), dtype=torch.uint8, device=dev, generator=g)
+    q_all[who] = db[src] ^ mask
+    q = q_all[lo:hi].contiguous()
+    del q_all
+    res = torch.empty((4, max(nq, 1)), dtype=torch.int32, device=dev)
+    m = matcher.ORBmatcher(NNRATIO, True, ctx)
+    ctx.set_knn_engine(args.engine)
+    ddb = ctx.database_from_device(db.data_ptr(), nd, keepalive=db)
+    gathered = torch.empty((nq_total, 4), dtype=torch.int32, device=dev) if world > 1 else None
+
+    def step():
+        m.SearchByNN_dev(ddb, nq, q.data_ptr(), res[0].data_ptr(), res[1].data_ptr(), res[2].data_ptr(), res[3].data_ptr(), TH_LOW)
+        if world > 1:
+            return all_gather_rows(res.t().contiguous(), nq_total, out=gathered)
+        return res
+
+    units_total = float(nq_total) * float(nd)
+    for _ in range(W):
+        step()
+    E.barrier_sync()
+    sampler = ClockSampler(E.local_rank)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_first_sample()
+    launches0 = ctx.launch_count
+    total_ms = 0.0
+    E.barrier_sync()
+    t_wall0 = time.time()
+    for _ in range(K):
+        E.flush_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        e1.synchronize()
+        total_ms += e0.elapsed_time(e1)
+    E.barrier_sync()
+    t_wall1 = time.time()
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else {}
+    total_ms = E.max_over_ranks(total_ms)
+    ms_per_step = total_ms / max(K, 1)
+    value = units_total / (ms_per_step * 1e-3)
+    ctx.synchronize()
+    extra = {"comparisons_per_step": int(units_total), "matches_rank0": int((res[3][:nq] >= 0).sum().item()),
+             "database_expansion": "the +-1 fp8 copy of the database is cached in the orbgpu_db (built once, before the timed steps): the "
+                                   "map changes at key-frame rate, queries arrive per frame; the e2e figure re-uploads AND re-expands "
+                                   "the database every step"}
+
+    # ---- end to end through the host-pointer C-ABI (what a reference-side caller uses): pinned host buffers, database + query H2D,
+    # result D2H, and at N > 1 the all-gather of the ranks' results, every step
+    e2e = None
+    if not args.no_e2e:
+        Ke = K if K < 5 else 5
+        db_h = db.cpu().pin_memory().numpy()
+        q_h = q.cpu().pin_memory().numpy()
+        h2d = db_h.nbytes + q_h.nbytes
+        d2h = 4 * 4 * nq
+        hdb = ctx.upload_database(db_h)
+        host_res = torch.empty((nq, 4), dtype=torch.int32).pin_memory()
+        dev_res = torch.empty((nq, 4), dtype=torch.int32, device=dev)
+
+        def e2e_step():
+            hdb.update(db_h)  # the database H2D copy (and its re-expansion) is part of the step
+            bi, bd, sd, mt = m.SearchByNN(hdb, q_h, TH_LOW)
+            if world > 1:  # every rank ends up with all rows: results back to the device, one NCCL all-gather, gathered rows to the host
+                host_res[:, 0], host_res[:, 1] = torch.from_numpy(bi), torch.from_numpy(bd)
+                host_res[:, 2], host_res[:, 3] = torch.from_numpy(sd), torch.from_numpy(mt)
+                dev_res.copy_(host_res, non_blocking=True)
+                return all_gather_rows(dev_res, nq_total, out=gathered).cpu()
+            return mt
+
+        e2e_step()
+        E.barrier_sync()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / max(Ke, 1)
+        dt = E.max_over_ranks(dt)
+        if world > 1:
+            h2d += 16 * nq
+            d2h += 16 * nq_total
+        e2e = {"value": units_total / dt, "unit": "hamming_comparisons/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": dt * 1e3, "steps": Ke,
+               "note": "host-pointer C-ABI call from pinned host buffers; re-uploads (and re-expands) the 128 MiB database every step"
+                       + ("; includes the all-gather of the ranks' results and the copy of the gathered rows to the host" if world > 1 else "")}
+        del hdb, db_h
+
+    line = None
+    if rank == 0:
+        engine = args.engine if args.engine else (4 if getattr(matcher, "TC_DEFAULT", False) else 1)
+        per_gpu_units = units_total / world
+        kern_s = ms_per_step * 1e-3
+        if engine >= 3:
+            flops = per_gpu_units * 512.0  # 256 MACs per 256-bit comparison on the +-1 fp8 contraction
+            peak2x = 2.0 * float(E.peaks.get("bf16_tflops", 1590.0))
+            fp8_meas = measure_fp8_peak(dev)
+            peak = max(peak2x, fp8_meas) if fp8_meas else peak2x
+            roof = {"bound": "tensor", "achieved": flops / kern_s / 1e12, "peak": peak, "unit": "TFLOP/s",
+                    "frac": flops / kern_s / 1e12 / peak, "traffic": E.traffic.get("c5"),
+                    "frac_of_nominal_fp8": flops / kern_s / 1e12 / 4500.0,
+                    "peak_2x_measured_bf16": peak2x, "peak_fp8_cublaslt_measured": fp8_meas,
+                    "note": "peak = the larger of (a) 2x the measured bf16 cuBLAS burst of MEASURED_PEAKS.json and (b) a dense fp8 "
+                            "cuBLASLt GEMM (torch._scaled_mm, 8192^3, best of 5) timed in this run; against the nominal 4.5 PFLOP/s see "
+                            "frac_of_nominal_fp8.  512 flop per 256-bit comparison"}
+        else:
+            popc = per_gpu_units * 8.0  # 8 POPC32 per comparison
+            pk = E.popc_peak()
+            roof = {"bound": "int-popc", "achieved": popc / kern_s / 1e12, "peak": pk["tpopc32_per_s"], "unit": "TPOPC32/s",
+                    "frac": popc / kern_s / 1e12 / pk["tpopc32_per_s"], "traffic": E.traffic.get("c5"), "peak_measured": pk,
+                    "note": "integer-pipe roofline: POPC32 issue rate measured in this run by orbgpu_measure_popc_peak (all SMs)"}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                _, cpu = cpu_knn_baseline(args.nd)
+            except Exception as e:  # the baseline is a reported number, never a reason to lose the bench line
+                cpu = {"value": None, "error": repr(e)}
+        line = {"metric": "hamming_comparisons_per_s", "value": value, "unit": "hamming_comparisons/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+                "data": "synthetic", "config": workload_config("c5", args), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roof, "cpu_baseline": cpu, "engine": engine, **extra}
+    E.keep_c5 = (db, ddb, m)  # the relocalisation shape reuses the resident database
+    return line
+
+
+def bench_reloc(E, args):
+    """the real relocalisation shape (Tracking.cc:4456-4495): ONE frame's ~2000 descriptors against the 4M-row map database,
+    expanded database cached in the orbgpu_db"""
+    torch, ctx = E.torch, E.ctx
+    db, ddb, m = E.keep_c5
+    nq, nd = 2000, args.nd
+    g = torch.Generator(device=E.dev)
+    g.manual_seed(7)
+    q = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, device=E.dev, generator=g)
+    res = torch.empty((4, nq), dtype=torch.int32, device=E.dev)
+
+    def step():
+        m.SearchByNN_dev(ddb, nq, q.data_ptr(), res[0].data_ptr(), res[1].data_ptr(), res[2].data_ptr(), res[3].data_ptr(), TH_LOW)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    n, total = 20, 0.0
+    for _ in range(n):
+        E.flush_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); step(); e1.record(); e1.synchronize()
+        total += e0.elapsed_time(e1)
+    ms = total / n
+    # the same call with the database expansion redone inside (what round 1 did on every call)
+    tot2 = 0.0
+    for _ in range(5):
+        ddb.invalidate()
+        E.flush_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); step(); e1.record(); e1.synchronize()
+        tot2 += e0.elapsed_time(e1)
+    q_h = q.cpu().pin_memory().numpy()
+    m.SearchByNN(ddb, q_h, TH_LOW)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        m.SearchByNN(ddb, q_h, TH_LOW)
+    e2e_ms = (time.perf_counter() - t0) / 10 * 1e3
+    return {"workload": f"relocalisation shape: {nq} queries (one frame) x {nd} database descriptors, th_low={TH_LOW}, nnratio={NNRATIO}",
+            "ms_per_call": ms, "hamming_comparisons_per_s": nq * nd / (ms * 1e-3), "steps": n,
+            "ms_per_call_with_database_expansion": tot2 / 5,
+            "e2e_ms_per_call": e2e_ms, "e2e_note": "host-pointer call: query H2D + result D2H, database resident",
+            "l2": "L2 flushed between calls"}
+
+
+def bench_c4(E, args, K, W):
+    torch, dist, matcher, synth = E.torch, E.dist, E.matcher, E.synth
+    from orb_slam3_comments_ghr_b200.sharding import TriangulationGather, shard_bounds
+    dev, rank, world = E.dev, E.rank, E.world
+    P_total = args.pairs
+    if P_total % world != 0:
+        raise SystemExit("--pairs must be divisible by the number of GPUs")
+    lo, hi = shard_bounds(P_total, rank, world)
+    P = hi - lo
+    case = c4_case(synth, C4_SEED + rank, P)  # independent pairs: every rank generates (and holds) the key frames of its own pairs
+    tg = TriangulationGather(matcher, case.kfs, P_total, C4_FEAT, rank, world, dev, 0.6, False, use_graph=not args.no_graph)
+    tg.ctx.set_triangulation_engine(args.tri_engine)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    tg.set_inputs(t(case.kf1), t(case.kf2), t(case.ep), t(case.f12))
+    extra = {"c4_result_form": "vMatchedPairs: counts[P] + (idx1 << 16 | idx2) entries, ascending idx1, on every rank",
+             "c4_gather": "none (one GPU)" if world == 1 else "fused: peer stores of the compact pairs from inside the search kernel + epoch flags, CUDA graph"}
+    for _ in range(max(W, 3)):
+        tg.step()
+    E.barrier_sync()
+    # enough back-to-back steps for nvidia-smi to sample the clocks under this load: ~1.5 s including the L2 flushes
+    cal0 = time.perf_counter()
+    for _ in range(20):
+        E.flush_l2()
+        tg.step()
+    torch.cuda.synchronize()
+    per_iter = E.max_over_ranks((time.perf_counter() - cal0) / 20)
+    K4 = int(min(20000, max(K, 200, 1.5 / max(per_iter, 1e-5))))
+    sampler = ClockSampler(E.local_rank, period_ms=50)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_first_sample()
+    E.barrier_sync()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K4)]
+    t_wall0 = time.time()
+    for e0, e1 in ev:
+        E.flush_l2()
+        e0.record()
+        tg.step()
+        e1.record()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    E.barrier_sync()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else {}
+    total_ms = E.max_over_ranks(float(sum(e0.elapsed_time(e1) for e0, e1 in ev)))
+    ms_per_step = total_ms / K4
+    value = P_total / (ms_per_step * 1e-3)
+    cmp_rank0 = tg.ctx.fetch_comparisons()  # DescriptorDistance-equivalents of the last step, counted on the device
+    cnt, ent = tg.step()
+    torch.cuda.synchronize()
+    extra["comparisons_per_step_rank0"] = int(cmp_rank0)
+    extra["matches_all_pairs"] = int(cnt.sum().item())
+    extra["gather_status"] = tg.status()
+
+    # ---- end to end: pinned host inputs -> device, the sharded search + gather, the vMatchedPairs of ALL pairs back on the host
+    e2e = None
+    if not args.no_e2e:
+        Ke = 5
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+        if world == 1:
+            m = matcher.ORBmatcher(0.6, False, E.ctx)
+            ks = E.ctx.upload_kfset(case.kfs)
+            h = [pin(a).numpy() for a in (case.kf1, case.kf2, case.ep, case.f12)]
+            h_out = (torch.empty(P + 1, dtype=torch.int32).pin_memory().numpy(), torch.empty((P * 512, 2), dtype=torch.int32).pin_memory().numpy())
+            d2h = [0]
+
+            def e2e_step():
+                offs, pairs = m.SearchForTriangulationPairs(ks, h[0], h[1], h[2], h[3], out=h_out)
+                d2h[0] = offs.nbytes + pairs.nbytes
+            note = "host-pointer C-ABI call returning vMatchedPairs; keyframe set resident (uploaded once like the reference's KeyFrames)"
+        else:
+            h = [pin(a) for a in (case.kf1, case.kf2, case.ep, case.f12)]
+            d_in = tg.inputs
+            ar = torch.arange(C4_FEAT, device=dev, dtype=torch.int32)[None, :]
+            d2h = [0]
+
+            def e2e_step():
+                for d_, h_ in zip(d_in, h):
+                    d_.copy_(h_, non_blocking=True)
+                c, e = tg.step()
+                packed = e[ar < c[:, None]]  # the valid prefix of every pair, in pair order
+                c_h, p_h = c.cpu(), packed.cpu()
+                d2h[0] = c_h.numel() * 4 + p_h.numel() * 4
+            note = ("pinned host inputs H2D, sharded search + fused all-gather, then counts and the valid (idx1, idx2) entries of ALL pairs "
+                    "D2H on every rank; keyframe set resident")
+        e2e_step(); e2e_step()
+        E.barrier_sync()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = E.max_over_ranks((time.perf_counter() - t0) / Ke)
+        h2d = case.kf1.nbytes * 2 + case.ep.nbytes + case.f12.nbytes
+        e2e = {"value": P_total / dt, "unit": "frame_pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h[0]),
+               "ms_per_step": dt * 1e3, "steps": Ke, "note": note}
+
+    line = None
+    if rank == 0:
+        kern_s = ms_per_step * 1e-3
+        cmp_step = float(cmp_rank0)
+        pk = E.popc_peak()
+        popc = cmp_step * 8.0 / kern_s / 1e12
+        roof = {"bound": "int-popc", "achieved": popc, "peak": pk["tpopc32_per_s"], "unit": "TPOPC32/s", "frac": popc / pk["tpopc32_per_s"],
+                "traffic": E.traffic.get("c4"), "peak_measured": pk,
+                "note": "8 POPC32 per 256-bit comparison (SURVEY.md 8(d)) x comparisons counted on the device (rank 0's pairs); peak = POPC32 "
+                        "issue rate measured in this run (orbgpu_measure_popc_peak: POPC + IADD3 only, all SMs).  The 128-bit prefilter "
+                        "executes ~4.2 POPC32 per comparison, which is why the fraction can exceed the XU pipe's own utilisation"}
+        # algorithmic bytes per pair (DESIGN.md): 32 B x map-point-free descriptors of both keyframes (~50 %), CSR feature ids + node
+        # ids, per-pair geometry, and the compact result (count + 4 B per match)
+        matches_pp = extra["matches_all_pairs"] / max(P_total, 1)
+        bytes_pair = 2 * (0.5 * C4_FEAT * 32 + 0.5 * C4_FEAT * 4 + 100 * 8) + 4 * matches_pp + 4 + 44
+        gb = (P_total / world) * bytes_pair / 1e9
+        peak = float(E.peaks.get("hbm_gbs", 6650.0))
+        extra["roofline_hbm"] = {"bound": "hbm", "achieved": gb / kern_s, "peak": peak, "unit": "GB/s", "frac": gb / kern_s / peak,
+                                 "bytes_per_pair": bytes_pair, "traffic": E.traffic.get("c4")}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                _, cpu = cpu_tri_baseline(case)
+            except Exception as e:
+                cpu = {"value": None, "error": repr(e)}
+        line = {"metric": "frame_pairs_matched_per_s", "value": value, "unit": "frame_pairs/s", "n_gpus": world, "steps": K4, "warmup": max(W, 3),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+                "data": "synthetic", "config": workload_config("c4", args), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(2 * K4), "gpu_launches_note": "triangulation_stream_kernel + tri_gather_wait_kernel per step (graph replays)",
+                "roofline": roof, "cpu_baseline": cpu, "engine": args.tri_engine if args.tri_engine else 2, **extra}
+    del tg
+    return line
+
+
+def bench_single_frame(E):
+    """C1-C3: single frame pairs through the host-pointer C-ABI (frames resident / uploaded inside the call) next to the reference's
+    CPU code on one core.  Latency-bound (6 k - 2 M comparisons): microseconds and comparisons/s, no roofline claim."""
+    from orb_slam3_comments_ghr_b200._abi import HostVoc
+    from oracle.pyoracle import Oracle, Reference
+    matcher, synth, ctx = E.matcher, E.synth, E.ctx
+    ref = Reference(fast=True) if Reference.available(fast=True) else None
+    orc = Oracle()
+    kind = "reference" if ref else "port"
+
+    def timeit(fn, n=30, warm=5):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(n):
+            t = time.perf_counter(); fn(); ts.append(time.perf_counter() - t)
+        return float(np.median(ts)) * 1e6
+
+    def row(workload, g, gu, r, ncmp):
+        return {"workload": workload, "gpu_us": g, "gpu_us_with_frame_upload": gu, "cpu_us": r, "cpu_kind": kind, "cpu_cores": 1,
+                "comparisons": int(ncmp), "hamming_comparisons_per_s": ncmp / (g * 1e-6),
+                "note": "median of 30 host-pointer C-ABI calls (H2D of the inputs, kernels, D2H of the results, one synchronisation)"}
+
+    out = {}
+    c = synth.make_init_case(11)
+    f1, f2 = ctx.upload_frame(c.f1), ctx.upload_frame(c.f2)
+    m = matcher.ORBmatcher(c.nnratio, True, ctx)
+    g = timeit(lambda: m.SearchForInitialization(f1, f2, c.prev_matched, c.window_size))
+    ncmp = ctx.last_comparisons
+    gu = timeit(lambda: m.SearchForInitialization(ctx.upload_frame(c.f1), ctx.upload_frame(c.f2), c.prev_matched, c.window_size))
+    cpu = ref or orc
+    r = timeit(lambda: cpu.search_for_initialization(c.f1, c.f2, c.prev_matched, c.window_size, c.nnratio, 1))
+    out["c1"] = row("C1 SearchForInitialization, 2 x 1000 keypoints, window 100", g, gu, r, ncmp)
+    for th in (1.0, 3.0):
+        pc = synth.make_projection_case(21, th=th)
+        fr = ctx.upload_frame(pc.frame)
+        m = matcher.ORBmatcher(pc.nnratio, True, ctx)
+        g = timeit(lambda: m.SearchByProjection(fr, pc.mps, th, False, 50.0, pc.kp_prior_obs, pc.kp_mp))
+        ncmp = ctx.last_comparisons
+        gu = timeit(lambda: m.SearchByProjection(ctx.upload_frame(pc.frame), pc.mps, th, False, 50.0, pc.kp_prior_obs, pc.kp_mp))
+        r = timeit(lambda: cpu.search_by_projection_local(pc.frame, pc.mps, th, 0, 50.0, pc.nnratio, pc.kp_prior_obs, pc.kp_mp))
+        out["c2_th%d" % int(th)] = row(f"C2 SearchByProjection, 2000 keypoints x 5000 map points, th={th}", g, gu, r, ncmp)
+    voc = HostVoc.load(os.path.join(ROOT, "tests", "golden", "voc_k10_L4.npz"))
+    dv = ctx.upload_vocabulary(voc)
+    hv = ref.voc_from_flat(voc) if ref else None
+    bc = synth.make_bow_case(31, voc, 2000)
+    for levelsup in (2, 4):
+        dk, df = ctx.upload_frame(bc.kf), ctx.upload_frame(bc.f)
+        g = timeit(lambda: dk.transform(dv, levelsup, True))
+        ncmp = ctx.last_comparisons
+        r = timeit(lambda: hv.transform(bc.kf.desc, levelsup), n=10, warm=2) if hv else timeit(lambda: orc.voc_transform(voc, bc.kf.desc, levelsup), n=5, warm=1)
+        out["c3_transform_l%d" % levelsup] = row(f"C3 TemplatedVocabulary::transform, 2000 features, k=10 L=4, levelsup={levelsup}", g, None, r, ncmp)
+        df.transform(dv, levelsup, True)
+        m = matcher.ORBmatcher(0.7, True, ctx)
+        g = timeit(lambda: m.SearchByBoW(dk, df, bc.kf_mp_valid))
+        ncmp = ctx.last_comparisons
+        w, nid, wt = orc.voc_transform(voc, bc.kf.desc, levelsup); kf = bc.kf.with_featvec(*orc.featvec(nid, wt))
+        w, nid, wt = orc.voc_transform(voc, bc.f.desc, levelsup); f = bc.f.with_featvec(*orc.featvec(nid, wt))
+        r = timeit(lambda: cpu.search_by_bow_kf_f(kf, f, bc.kf_mp_valid, 0.7, 1), n=10, warm=2)
+        out["c3_bow_l%d" % levelsup] = row(f"C3 SearchByBoW KeyFrame-Frame, 2000 x 2000 features, levelsup={levelsup}"
+                                           + (" (one root bucket: 1.9 M comparisons)" if levelsup == 4 else ""), g, None, r, ncmp)
+    return out
 
 
 def main():
@@ -219,12 +639,11 @@ def main():
     ap.add_argument("--nd", type=int, default=ND_FULL)
     ap.add_argument("--pairs", type=int, default=C4_PAIRS)
     ap.add_argument("--engine", type=int, default=0, help="knn2 engine: 0 auto, 1 POPC, 2 mma.sync b1, 3 tcgen05 1-CTA, 4 tcgen05 2-CTA")
-    ap.add_argument("--tri-engine", type=int, default=0, help="C4 kernel: 0 auto, 1 CTA per pair, 2 persistent bulk-copy pipeline")
-    ap.add_argument("--c4-gather", default="fused", choices=["fused", "nccl"],
-                    help="C4 at N > 1: 'fused' = the kernel stores matches into every rank's result buffer over NVLink peer memory "
-                         "(torch symmetric memory) + one device-side barrier; 'nccl' = kernel, then one NCCL all-gather of the dense rows")
+    ap.add_argument("--tri-engine", type=int, default=0, help="C4 kernel: 0 auto (2 = persistent bulk-copy pipeline; the gather form needs it)")
+    ap.add_argument("--no-graph", action="store_true", help="C4: launch the step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="main workload only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -237,7 +656,6 @@ def main():
     import torch.distributed as dist
 
     from orb_slam3_comments_ghr_b200 import matcher, synth
-    from orb_slam3_comments_ghr_b200.sharding import all_gather_rows, shard_bounds
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the CUDA path has no CPU fallback")
@@ -246,11 +664,12 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    ctx = matcher.Context(local_rank, stream=torch.cuda.current_stream().cuda_stream)
+    E = Env()
+    E.torch, E.dist, E.matcher, E.synth = torch, dist, matcher, synth
+    E.rank, E.world, E.local_rank, E.dev = rank, world, local_rank, dev
+    E.ctx = matcher.Context(local_rank, stream=torch.cuda.current_stream().cuda_stream)
     flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-
-    def flush_l2():
-        flush_buf.fill_(1)
+    E.flush_l2 = lambda: flush_buf.fill_(1)
 
     def barrier_sync():
         if world > 1:
@@ -264,289 +683,59 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    E.barrier_sync, E.max_over_ranks = barrier_sync, max_over_ranks
+    E.peaks, E.traffic = {}, {}
+    try:
+        E.peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels, from the ncu --set full captures
+        E.traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    _pk = {}
+
+    def popc_peak():
+        if not _pk:
+            r = max((E.ctx.measure_popc_peak(0) for _ in range(3)), key=lambda x: x["popc_per_s"])
+            h = max((E.ctx.measure_popc_peak(1) for _ in range(3)), key=lambda x: x["popc_per_s"])
+            _pk.update(tpopc32_per_s=r["popc_per_s"] / 1e12, popc32_per_clk_per_sm=r["per_clk_sm"], sm_mhz=r["sm_mhz"],
+                       hamming_triple_tpopc32_per_s=h["popc_per_s"] / 1e12)
+        return _pk
+
+    E.popc_peak = popc_peak
+
     K, W = args.steps, args.warmup
-    extra = {}
     if args.workload == "c5":
-        nq_total, nd = args.nq, args.nd
-        lo, hi = shard_bounds(nq_total, rank, world)
-        nq = hi - lo
-        g = torch.Generator(device=dev)
-        g.manual_seed(20261018)
-        db = torch.randint(0, 256, (nd, 32), dtype=torch.uint8, device=dev, generator=g)
-        q_all = torch.randint(0, 256, (nq_total, 32), dtype=torch.uint8, device=dev, generator=g)
-        n_pl = nq_total // 10  # 10 % planted: database rows with ~1/16 of the bits flipped
-        who = torch.randperm(nq_total, device=dev, generator=g)[:n_pl]
-        src = torch.randint(0, nd, (n_pl,), device=dev, generator=g)
-        mask = torch.randint(0, 256, (n_pl, 32), dtype=torch.uint8, device=dev, generator=g)
-        for _ in range(3):
-            mask &= torch.randint(0, 256, (n_pl, 32), dtype=torch.uint8, device=dev, generator=g)
-        q_all[who] = db[src] ^ mask
-        q = q_all[lo:hi].contiguous()
-        res = torch.empty((4, max(nq, 1)), dtype=torch.int32, device=dev)
-        m = matcher.ORBmatcher(NNRATIO, True, ctx)
-        ctx.set_knn_engine(args.engine)
-        ddb = ctx.database_from_device(db.data_ptr(), nd, keepalive=db)
-
-        gathered = torch.empty((nq_total, 4), dtype=torch.int32, device=dev) if world > 1 else None
-
-        def step():
-            m.SearchByNN_dev(ddb, nq, q.data_ptr(), res[0].data_ptr(), res[1].data_ptr(), res[2].data_ptr(), res[3].data_ptr(), TH_LOW)
-            if world > 1:
-                return all_gather_rows(res.t().contiguous(), nq_total, out=gathered)
-            return res
-
-        units_total = float(nq_total) * float(nd)
-        metric, unit = "hamming_comparisons_per_s", "hamming_comparisons/s"
+        line = bench_c5(E, args, K, W)
+        secondary = {}
+        if not args.no_secondary:
+            if world == 1:
+                try:
+                    secondary["reloc_2k"] = bench_reloc(E, args)
+                except Exception as e:
+                    secondary["reloc_2k"] = {"error": repr(e)}
+            E.keep_c5 = None
+            torch.cuda.empty_cache()
+            try:
+                secondary["c4"] = bench_c4(E, args, K, W)
+            except Exception as e:  # the secondary block never costs the headline line
+                secondary["c4"] = {"error": repr(e)}
+                if world > 1:
+                    raise
+            if world == 1:
+                try:
+                    secondary.update(bench_single_frame(E))
+                except Exception as e:
+                    secondary["single_frame"] = {"error": repr(e)}
+        if rank == 0:
+            if secondary:
+                line["secondary"] = secondary
+            print(json.dumps(line), flush=True)
     else:
-        P_total = args.pairs
-        lo, hi = shard_bounds(P_total, rank, world)
-        P = hi - lo
-        case = synth.fill_geometry(synth.make_triangulation_case(20261018 + rank, n_pairs=max(P, 1), n_feat=C4_FEAT))
-        ks = ctx.upload_kfset(case.kfs)
-        ctx.set_triangulation_engine(args.tri_engine)
-        m = matcher.ORBmatcher(0.6, False, ctx)
-        kf1, kf2 = torch.from_numpy(case.kf1).to(dev), torch.from_numpy(case.kf2).to(dev)
-        ep, f12 = torch.from_numpy(case.ep).to(dev), torch.from_numpy(case.f12).to(dev)
-        out = torch.empty((max(P, 1), C4_FEAT), dtype=torch.int32, device=dev)
-        nmt = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
-
-        gathered = torch.empty((P_total, C4_FEAT), dtype=torch.int32, device=dev) if world > 1 else None
-        extra["c4_gather"] = "none" if world == 1 else args.c4_gather
-        state = {}
-
-        def step_nccl():
-            m.SearchForTriangulation_dev(ks, P, kf1.data_ptr(), kf2.data_ptr(), ep.data_ptr(), f12.data_ptr(), out.data_ptr(), nmt.data_ptr())
-            if world > 1:
-                return all_gather_rows(out, P_total, out=gathered)
-            return out
-
-        step = step_nccl
-        if world > 1 and args.c4_gather == "fused" and P_total % world == 0:
-            # Fused search + all-gather: every rank's kernel builds each match row in its own result buffer and ships the finished
-            # row to the result buffers of ALL other ranks (symmetric memory = peer mappings over NVLink / NVSwitch) with coalesced
-            # 128-bit stores while the next pairs are being compared.  Result buffers are double-buffered; ONE device-side barrier
-            # per step.  Both step variants are captured in CUDA graphs: a step is tens of microseconds of GPU work.
-            import torch.distributed._symmetric_memory as symm_mem
-            rows = symm_mem.empty((2, P_total * C4_FEAT), dtype=torch.int32, device=dev)
-            cnts = symm_mem.empty((2, P_total), dtype=torch.int32, device=dev)
-            hr = symm_mem.rendezvous(rows, dist.group.WORLD.group_name)
-            hc = symm_mem.rendezvous(cnts, dist.group.WORLD.group_name)
-            rows.fill_(-1)
-            cnts.fill_(0)
-            hr.barrier(channel=0)
-            state.update(k=0, graphs=None, gctx=None)
-
-            order = [rank] + [r_ for r_ in range(world) if r_ != rank]  # target 0 = this rank's own buffer
-
-            def fused_once(mm, b):
-                tm = [hr.buffer_ptrs[r_] + b * P_total * C4_FEAT * 4 for r_ in order]
-                tn = [hc.buffer_ptrs[r_] + b * P_total * 4 for r_ in order]
-                # rows_preset = 2: the row is built in this rank's buffer and shipped whole to the peers (coalesced 128-bit stores)
-                mm.SearchForTriangulation_peers_dev(ks, P, kf1.data_ptr(), kf2.data_ptr(), ep.data_ptr(), f12.data_ptr(), tm, tn, lo, 2)
-                hr.barrier(channel=0)
-
-            try:
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    gctx = matcher.Context(local_rank, stream=side.cuda_stream)
-                    gm = matcher.ORBmatcher(0.6, False, gctx)
-                    fused_once(gm, 0); fused_once(gm, 1)
-                    side.synchronize()
-                    graphs = []
-                    for b in (0, 1):
-                        g_ = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(g_, stream=side):
-                            fused_once(gm, b)
-                        graphs.append(g_)
-                torch.cuda.current_stream().wait_stream(side)
-                state["graphs"], state["gctx"] = graphs, gctx
-                extra["c4_gather"] = "fused (peer stores over NVLink + device barrier, CUDA graph)"
-            except Exception as e:  # eager launches are still correct, only launch-bound
-                extra["c4_gather"] = f"fused (eager: graph capture failed: {e!r})"
-
-            def step():
-                b = state["k"] & 1
-                state["k"] += 1
-                if state["graphs"] is not None:
-                    state["graphs"][b].replay()
-                else:
-                    fused_once(m, b)
-                return rows[b].view(P_total, C4_FEAT)
-
-        units_total = float(P_total)
-        metric, unit = "frame_pairs_matched_per_s", "frame_pairs/s"
-        if world == 1 and not args.no_e2e:
-            # the caller before this path: KeyFrame::ComputeBoW for the whole set on the device (vocabulary descent of every feature
-            # + CSR rebuild), reported next to the headline; run on a second copy of the set so that the timed search keeps its inputs
-            try:
-                from orb_slam3_comments_ghr_b200._abi import HostVoc
-                voc = HostVoc.load(os.path.join(ROOT, "tests", "golden", "voc_k10_L4.npz"))
-                dv = ctx.upload_vocabulary(voc)
-                nodes_host = case.kfs.node_id
-                case.kfs.node_id = None
-                ks2 = ctx.upload_kfset(case.kfs)
-                case.kfs.node_id = nodes_host
-                ks2.transform(dv, 2)
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                ncmp = ks2.transform(dv, 2)
-                dt = time.perf_counter() - t0
-                extra["kfset_transform"] = {"features": int(case.kfs.desc.shape[0] * case.kfs.desc.shape[1]), "vocabulary": "k=10 L=4, levelsup=2",
-                                            "ms": dt * 1e3, "comparisons": int(ncmp), "comparisons_per_s": ncmp / dt,
-                                            "note": "vocabulary descent of every feature of the 8192 key frames + CSR / stream-blob rebuild, one call"}
-                del ks2
-            except Exception as e:
-                extra["kfset_transform"] = {"error": repr(e)}
-
-    # ---- device-resident timing: W warm-up steps, then exactly K timed steps
-    for _ in range(W):
-        step()
-    barrier_sync()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = ctx.launch_count
-    total_ms = 0.0
-    barrier_sync()
-    for _ in range(K):
-        flush_l2()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step()
-        e1.record()
-        e1.synchronize()
-        total_ms += e0.elapsed_time(e1)
-    barrier_sync()
-    launches = ctx.launch_count - launches0
-    if extra.get("c4_gather", "").startswith("fused (peer") and launches == 0:
-        launches = K  # graph replays: one triangulation_stream_kernel per step (the context only counts direct launches)
-    clocks = sampler.stop() if rank == 0 else {}
-    total_ms = max_over_ranks(total_ms)
-    ms_per_step = total_ms / max(K, 1)
-    value = units_total / (ms_per_step * 1e-3)
-    if args.workload == "c5":
-        ctx.synchronize()
-        extra["comparisons_per_step"] = int(units_total)
-        extra["matches_rank0"] = int((res[3][:nq] >= 0).sum().item())
-    else:
-        cctx = state.get("gctx") or ctx
-        extra["comparisons_per_step_rank0"] = cctx.fetch_comparisons()  # DescriptorDistance-equivalents, counted on the device
-        extra["matches_rank0"] = int(nmt[:P].sum().item()) if extra.get("c4_gather", "none") in ("none", "nccl") else int(cnts[0][lo:hi].sum().item())
-
-    # ---- end to end through the host-pointer C-ABI (what a reference-side caller uses)
-    e2e = None
-    if not args.no_e2e:
-        Ke = min(K, 2)
-        if args.workload == "c5":
-            db_h = db.cpu().pin_memory().numpy()
-            q_h = q.cpu().pin_memory().numpy()
-            h2d = db_h.nbytes + q_h.nbytes
-            d2h = 4 * 4 * nq
-
-            hdb = ctx.upload_database(db_h)
-
-            def e2e_step():
-                hdb.update(db_h)  # the database H2D copy is part of the step (same allocation: no cudaMalloc / cudaFree inside)
-                return m.SearchByNN(hdb, q_h, TH_LOW)
-        else:
-            h2d = case.kf1.nbytes * 2 + case.ep.nbytes + case.f12.nbytes
-            pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
-            h_kf1, h_kf2, h_ep, h_f12 = pin(case.kf1), pin(case.kf2), pin(case.ep), pin(case.f12)
-            # the result in the reference's own form: vMatchedPairs per key-frame pair (ORBmatcher.cc:1317-1325)
-            h_out = (torch.empty(P + 1, dtype=torch.int32).pin_memory().numpy(),
-                     torch.empty((P * 512, 2), dtype=torch.int32).pin_memory().numpy())
-            d2h = [0]
-
-            def e2e_step():
-                offs, pairs = m.SearchForTriangulationPairs(ks, h_kf1, h_kf2, h_ep, h_f12, out=h_out)
-                d2h[0] = offs.nbytes + pairs.nbytes
-                return offs, pairs
-        e2e_step()
-        e2e_step()
-        barrier_sync()
-        t0 = time.perf_counter()
-        for _ in range(Ke):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / Ke
-        dt = max_over_ranks(dt)
-        if isinstance(d2h, list):
-            d2h = d2h[0]
-        e2e = {"value": units_total / dt, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": dt * 1e3, "steps": Ke,
-               "note": "host-pointer C-ABI call; C5 re-uploads the 128 MiB database every step" if args.workload == "c5" else
-                       "host-pointer C-ABI call returning vMatchedPairs; keyframe set resident (uploaded once like the reference's KeyFrames)"}
-
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        engine = args.engine if args.engine else (4 if getattr(matcher, "TC_DEFAULT", False) else 1)
-        if args.workload == "c4":
-            engine = args.tri_engine if args.tri_engine else 2  # auto = persistent warp-specialised pipeline (monocular sets)
-        traffic = {}
-        try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full capture
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        except Exception:
-            pass
-        per_gpu_units = units_total / world
-        kern_s = ms_per_step * 1e-3
-        if args.workload == "c5":
-            if engine >= 3:
-                flops = per_gpu_units * 512.0  # 256 MACs per 256-bit comparison on the +-1 fp8 contraction
-                peak2x = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
-                fp8_meas = measure_fp8_peak(dev)
-                peak = max(peak2x, fp8_meas) if fp8_meas else peak2x
-                roof = {"bound": "tensor", "achieved": flops / kern_s / 1e12, "peak": peak, "unit": "TFLOP/s",
-                        "frac": flops / kern_s / 1e12 / peak, "traffic": traffic.get("c5"),
-                        "frac_of_nominal_fp8": flops / kern_s / 1e12 / 4500.0,
-                        "peak_2x_measured_bf16": peak2x, "peak_fp8_cublaslt_measured": fp8_meas,
-                        "note": "peak = the larger of (a) 2x the measured bf16 cuBLAS burst of MEASURED_PEAKS.json and (b) a dense fp8 "
-                                "cuBLASLt GEMM (torch._scaled_mm, 8192^3, best of 5) timed in this run; against the nominal 4.5 PFLOP/s see "
-                                "frac_of_nominal_fp8.  512 flop per 256-bit comparison"}
-            else:
-                popc = per_gpu_units * 8.0  # 8 POPC32 per comparison
-                sm_mhz = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
-                peak = 148 * 16 * sm_mhz * 1e6 / 1e12
-                roof = {"bound": "int-popc", "achieved": popc / kern_s / 1e12, "peak": peak, "unit": "TPOPC32/s",
-                        "frac": popc / kern_s / 1e12 / peak, "traffic": traffic.get("c5"),
-                        "note": "integer-pipe roofline: 16 POPC/clk/SM x 148 SMs at the SM clock sampled during the run"}
-        else:
-            # C4 is bucketed all-pairs work: SURVEY.md 8(d) names the integer pipe as the binding bound (8 POPC32 per
-            # Hamming comparison, 16 POPC32/clk/SM) and HBM as the close second; both are reported, the binding one first
-            cmp_step = float(extra.get("comparisons_per_step_rank0", 0))
-            sm_mhz = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
-            popc_peak = 148 * 16 * sm_mhz * 1e6 / 1e12
-            popc = cmp_step * 8.0 / kern_s / 1e12
-            roof = {"bound": "int-popc", "achieved": popc, "peak": popc_peak, "unit": "TPOPC32/s", "frac": popc / popc_peak,
-                    "traffic": traffic.get("c4"),
-                    "note": "8 POPC32 per 256-bit comparison x comparisons counted on the device; peak = 16 POPC32/clk/SM x 148 SMs at the "
-                            "SM clock sampled during the run.  The 128-bit prefilter executes ~4.2 POPC32 per comparison, which is why "
-                            "the fraction can approach 1 while the XU pipe is not saturated"}
-            # algorithmic bytes per pair: 32 B x map-point-free descriptors of both keyframes (~50 %), CSR
-            # feature ids + node ids, match row out
-            bytes_pair = 2 * (0.5 * C4_FEAT * 32 + 0.5 * C4_FEAT * 4 + 100 * 8) + C4_FEAT * 4 + 4 + 44
-            gb = per_gpu_units * bytes_pair / 1e9
-            peak = float(peaks.get("hbm_gbs", 6650.0))
-            extra["roofline_hbm"] = {"bound": "hbm", "achieved": gb / kern_s, "peak": peak, "unit": "GB/s", "frac": gb / kern_s / peak,
-                                     "traffic": traffic.get("c4")}
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            try:
-                if args.workload == "c5":
-                    _, cpu = cpu_knn_baseline(args.nd)
-                else:
-                    _, cpu = cpu_tri_baseline(case)
-            except Exception as e:  # the baseline is a reported number, never a reason to lose the bench line
-                cpu = {"value": None, "error": repr(e)}
-        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
-                "cpu_baseline": cpu, "engine": engine, **extra}
-        print(json.dumps(line), flush=True)
+        line = bench_c4(E, args, K, W)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -269,6 +269,29 @@ int orbgpu_search_for_triangulation_batch_peers_dev(orbgpu_ctx *ctx, const orbgp
                                                     const int32_t *kf2_dev, const float *ep_dev, const float *f12_dev,
                                                     int32_t coarse, int32_t check_ori, int32_t n_targets, void *const *target_matches,
                                                     void *const *target_nmatches, int64_t pair_offset, int32_t rows_preset);
+/* Fused search + all-gather in the reference's own result form, vMatchedPairs (ORBmatcher.cc:1317-1325): the matches of pair p,
+ * ascending idx1, as 32-bit entries (idx1 << 16 | idx2) at pairs[(pair_offset + p) * n_feat ...], counts[pair_offset + p] of
+ * them valid (the store granularity is 16 bytes: up to 3 entries 0xFFFFFFFF may follow).  Only the valid prefix of every pair
+ * crosses NVLink -- about 1/10 of the dense rows of the _peers_dev variant -- and it is stored from inside the search kernel,
+ * straight from shared memory, into the buffers of ALL ranks while later pairs are still being compared.  There is no
+ * cross-rank barrier: when a rank has shipped its last pair it publishes its epoch in slot `rank` of every rank's flag array
+ * (system-scope fences order the data before it), and a one-warp kernel at the end of the call waits until every source in
+ * wait_mask has published the current epoch, then advances epoch_done[0].  Buffers are peer-mapped device addresses valid on
+ * THIS GPU (e.g. torch symmetric memory); the caller double-buffers pairs / counts between consecutive steps (a rank may be one
+ * step ahead of its peers), flags / epoch_done / status are shared by both buffers.  n_feat must be a multiple of 4.
+ * Initial state: flags = 0, epoch_done = {1, 0}, status = {0}.  status[0] becomes 1 if a source did not arrive within 4 s. */
+typedef struct orbgpu_tri_gather {
+    int32_t n_ranks, rank;
+    void *pairs[8];    /* [n_ranks] -> uint32 [P_total][n_feat] */
+    void *counts[8];   /* [n_ranks] -> int32  [P_total] */
+    void *flags[8];    /* [n_ranks] -> uint32 [n_ranks]: flags[t][s] = last epoch rank s has completed into rank t's buffers */
+    void *epoch_done;  /* local uint32 [2] */
+    void *status;      /* local uint32 [1], may be NULL */
+    uint32_t wait_mask; /* sources to wait for (bit s); (1 << n_ranks) - 1 in normal use */
+} orbgpu_tri_gather;
+int orbgpu_search_for_triangulation_batch_gather_dev(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs, const int32_t *kf1_dev,
+                                                     const int32_t *kf2_dev, const float *ep_dev, const float *f12_dev, int32_t coarse,
+                                                     int32_t check_ori, const orbgpu_tri_gather *g, int64_t pair_offset);
 /* Same search with the result in the reference's vMatchedPairs form (ORBmatcher.cc:1317-1325): for pair p the matches are
  * pairs[2*j], pairs[2*j+1] = (idx1, idx2), j in [pair_offsets[p], pair_offsets[p+1]), ascending idx1.  pair_offsets has
  * n_pairs+1 entries; cap = capacity of pairs in (idx1, idx2) entries; *total = entries produced (ORBGPU_ERR_OVERFLOW and the
@@ -291,6 +314,10 @@ int orbgpu_db_upload(orbgpu_ctx *ctx, int64_t nd, const uint8_t *db_desc, orbgpu
 /* refresh an uploaded database in place (nd <= the size it was created with): one H2D copy, no allocation */
 int orbgpu_db_update(orbgpu_ctx *ctx, orbgpu_db *db, int64_t nd, const uint8_t *db_desc);
 int orbgpu_db_from_dev(orbgpu_ctx *ctx, int64_t nd, const void *db_desc_dev, orbgpu_db **out); /* borrows the pointer */
+/* The tensor engine keeps an expanded (+-1 fp8) copy of the database inside the orbgpu_db, built by the first search and reused by
+ * the following ones (the map changes at key-frame rate, relocalisation queries it per frame).  orbgpu_db_update drops it; for a
+ * borrowed database (orbgpu_db_from_dev) the caller reports changed contents with orbgpu_db_invalidate. */
+int orbgpu_db_invalidate(orbgpu_db *db);
 void orbgpu_db_destroy(orbgpu_db *db);
 int orbgpu_knn2_ratio(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const uint8_t *q_desc, int32_t th_low, float nnratio,
                       int32_t *best_idx, int32_t *best_dist, int32_t *second_dist, int32_t *match);
@@ -337,6 +364,12 @@ int orbgpu_stereo_coarse_match(orbgpu_ctx *ctx, int32_t n_left, const uint8_t *d
                                int32_t n_right, const uint8_t *desc_r, const float *kp_xy_r, const int32_t *octave_r,
                                const float *scale_factors, int32_t n_levels, int32_t n_rows, float mb, float mbf,
                                int32_t *best_idx_r, int32_t *best_dist);
+
+/* ---- measurement aid: integer-pipe peak of this GPU, measured with a register-only microbenchmark on all SMs.
+ * variant 0 = POPC + IADD3 only, variant 1 = the Hamming triple LOP3(xor) + POPC + IADD3 (one 32-bit slice of
+ * DescriptorDistance, ORBmatcher.cc:2397-2405).  popc_per_s = POPC32 per second over the whole GPU; per_clk_sm = per SM clock
+ * per SM; sm_mhz = the SM clock the kernel ran at.  Used by bench.py as the denominator of the POPC rooflines. */
+int orbgpu_measure_popc_peak(orbgpu_ctx *ctx, int32_t variant, double *popc_per_s, double *per_clk_sm, double *sm_mhz);
 
 /* ---- a10: ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:2341-2383) exposed for testing:
  * histo[30] bin sizes -> ind[3]. Runs on the device. */

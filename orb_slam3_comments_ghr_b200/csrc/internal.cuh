@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -57,7 +58,7 @@ struct orbgpu_ctx {
     int knn_engine = 0;
     void *tri_timeline = nullptr; // debug time-stamp buffer (null = off)
     int tri_engine = 0; // 0 auto, 1 CTA-per-pair kernel, 2 persistent bulk-copy pipelined kernel
-    // tcgen05 engine scratch (expanded database), owned by the context
+    // tcgen05 engine scratch (expanded queries + per-split partial results), owned by the context
     void *knn_expanded = nullptr;
     size_t knn_expanded_bytes = 0;
     // pinned host staging (grow-only) used to pack uploads into one H2D copy
@@ -220,6 +221,14 @@ struct orbgpu_db {
     int64_t nd = 0, capacity = 0;
     const uint4 *desc = nullptr; // [nd][2]
     bool owned = false;
+    // tcgen05 engine: the database expanded to +-1 fp8 (256 B per row, rows padded to a multiple of 256 with zeros), built by the
+    // first search that needs it and kept until the descriptors change (orbgpu_db_update / orbgpu_db_invalidate).  `x_ready` is
+    // recorded on the expanding context's stream; other contexts make their stream wait on it.
+    mutable std::mutex x_mu;
+    mutable void *x_desc = nullptr;
+    mutable size_t x_bytes = 0;
+    mutable bool x_valid = false;
+    mutable cudaEvent_t x_ready = nullptr;
 };
 
 // POD view of a frame passed by value to kernels

@@ -306,6 +306,19 @@ extern "C" int orbgpu_db_update(orbgpu_ctx *ctx, orbgpu_db *db, int64_t nd, cons
     if (nd > 0) CU_TRY(cudaMemcpyAsync((void *)db->desc, db_desc, nd * 32, cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     db->nd = nd;
+    {
+        std::lock_guard<std::mutex> lock(db->x_mu);
+        db->x_valid = false; // the expanded copy is rebuilt by the next tensor-engine search
+    }
+    return ORBGPU_OK;
+}
+
+// a database that borrows the caller's device memory (orbgpu_db_from_dev) cannot see its contents change: the caller says so
+extern "C" int orbgpu_db_invalidate(orbgpu_db *db)
+{
+    ARG_TRY(db);
+    std::lock_guard<std::mutex> lock(db->x_mu);
+    db->x_valid = false;
     return ORBGPU_OK;
 }
 
@@ -325,10 +338,10 @@ extern "C" int orbgpu_db_from_dev(orbgpu_ctx *ctx, int64_t nd, const void *db_de
 extern "C" void orbgpu_db_destroy(orbgpu_db *db)
 {
     if (!db) return;
-    if (db->owned && db->desc) {
-        cudaSetDevice(db->device);
-        cudaFree((void *)db->desc);
-    }
+    cudaSetDevice(db->device);
+    if (db->owned && db->desc) cudaFree((void *)db->desc);
+    if (db->x_desc) cudaFree(db->x_desc);
+    if (db->x_ready) cudaEventDestroy(db->x_ready);
     delete db;
 }
 

@@ -726,23 +726,27 @@ int knn2_tc_run(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const uint4 *q
 {
     const int64_t nd = db->nd;
     const int bn = two_cta ? BN2 : BN; // database rows per stage
-    const int64_t nq_pad = (nq + 2 * BM - 1) / (2 * BM) * (2 * BM), nd_pad = (nd + bn - 1) / bn * bn;
+    // rows padded to 256 for both engines, so that one expanded copy of the database serves either
+    const int64_t nq_pad = (nq + 2 * BM - 1) / (2 * BM) * (2 * BM), nd_pad = (nd + BN2 - 1) / BN2 * BN2;
     const int n_qtiles = (int)(nq_pad / BM);
-    const int total_stages = (int)(nd_pad / bn);
+    const int total_stages = (int)((nd + bn - 1) / bn);
+    const int n_units = two_cta ? (n_qtiles + 1) / 2 : n_qtiles; // work items per split
+    const int n_workers = two_cta ? ctx->sm_count / 2 : ctx->sm_count;
     // database splits: each split (expanded: rows x 256 B) should stay L2 resident while every query tile sweeps it
     int stages_per_split = std::min(total_stages, (128 * 1024) / bn); // 128k rows = 32 MiB expanded per split
     int n_splits = (total_stages + stages_per_split - 1) / stages_per_split;
-    // not enough items to fill the machine: split finer
-    const int n_units = two_cta ? (n_qtiles + 1) / 2 : n_qtiles; // work items per split
-    const int n_workers = two_cta ? ctx->sm_count / 2 : ctx->sm_count;
-    while (n_splits * n_units < 2 * n_workers && stages_per_split > 8) {
-        stages_per_split = (stages_per_split + 1) / 2;
+    if (n_units * n_splits < 2 * n_workers) {
+        // few query tiles (one frame against the map: 2 k queries): the items must fill the persistent grid in whole waves --
+        // the largest item count not above a multiple of the worker count, one wave when that still leaves >= 64 stages per item
+        int want = std::max(1, n_workers / n_units); // one wave
+        while (want > 1 && (total_stages + want - 1) / want < 8) want--;
+        stages_per_split = (total_stages + want - 1) / want;
         n_splits = (total_stages + stages_per_split - 1) / stages_per_split;
     }
-    // persistent scratch: expanded database + expanded queries + partials
+    // context scratch: expanded queries + partials.  The expanded database belongs to the database object and is kept.
     const size_t e_db = (size_t)nd_pad * ROW_BYTES, e_q = (size_t)nq_pad * ROW_BYTES;
     const size_t part = (size_t)n_splits * nq_pad;
-    const size_t need = align256(e_db) + align256(e_q) + align256(part * 2) * 2 + align256(part * 4) + 4096;
+    const size_t need = align256(e_q) + align256(part * 2) * 2 + align256(part * 4) + 4096;
     if (need > ctx->knn_expanded_bytes) {
         CU_TRY(cudaStreamSynchronize(ctx->stream));
         if (ctx->knn_expanded) CU_TRY(cudaFree(ctx->knn_expanded));
@@ -752,15 +756,38 @@ int knn2_tc_run(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const uint4 *q
         ctx->knn_expanded_bytes = need;
     }
     char *base = (char *)(((uintptr_t)ctx->knn_expanded + 1023) & ~(uintptr_t)1023);
-    uint8_t *x_db = (uint8_t *)base;
-    uint8_t *x_q = x_db + align256(e_db);
+    uint8_t *x_q = (uint8_t *)base;
     uint16_t *pb = (uint16_t *)(x_q + align256(e_q));
     uint16_t *ps = (uint16_t *)((char *)pb + align256(part * 2));
     int32_t *pst = (int32_t *)((char *)ps + align256(part * 2));
-
-    expand_kernel<<<(unsigned)((nd_pad * 8 + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t *)db->desc, nd, nd_pad, (uint4 *)x_db);
+    uint8_t *x_db = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(db->x_mu);
+        if (db->x_bytes < e_db + 1024) {
+            if (db->x_desc) { // grown database (or first use): nothing may still be reading the old copy
+                CU_TRY(cudaDeviceSynchronize());
+                CU_TRY(cudaFree(db->x_desc));
+                db->x_desc = nullptr;
+                db->x_bytes = 0;
+            }
+            CU_TRY(cudaMalloc(&db->x_desc, e_db + 1024));
+            db->x_bytes = e_db + 1024;
+            db->x_valid = false;
+        }
+        if (!db->x_ready) CU_TRY(cudaEventCreateWithFlags(&db->x_ready, cudaEventDisableTiming));
+        x_db = (uint8_t *)(((uintptr_t)db->x_desc + 1023) & ~(uintptr_t)1023);
+        if (!db->x_valid) {
+            expand_kernel<<<(unsigned)((nd_pad * 8 + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t *)db->desc, nd, nd_pad, (uint4 *)x_db);
+            LAUNCH_COUNT(ctx);
+            CU_TRY(cudaGetLastError());
+            CU_TRY(cudaEventRecord(db->x_ready, ctx->stream));
+            db->x_valid = true;
+        } else {
+            CU_TRY(cudaStreamWaitEvent(ctx->stream, db->x_ready, 0)); // expanded on another context's stream, possibly still in flight
+        }
+    }
     expand_kernel<<<(unsigned)((nq_pad * 8 + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t *)q, nq, nq_pad, (uint4 *)x_q);
-    ctx->launches += 2;
+    LAUNCH_COUNT(ctx);
     CUtensorMap mq, mdb;
     int rc = make_map(&mq, x_q, (uint64_t)nq_pad, BM);
     if (rc) return rc;

@@ -444,8 +444,17 @@ struct TsParams {
     // were preset to -1 by their owners and only matches and counts cross the links.
     int n_targets, rows_preset; // rows_preset 2: "copy rows" -- target 0 is this rank's own buffer, built as in the plain call; the
                                 // finished 8 KB row is then copied to the other targets with coalesced 128-bit stores (no preset needed)
+                                // rows_preset 3: "compact pairs" -- the reference's vMatchedPairs form (:1317-1325): the matches of pair
+                                // p, ascending idx1, as (idx1 << 16 | idx2) entries at tgt_m[r] + (pair0 + p) * n_feat; only the
+                                // counts[p] valid entries (rounded up to 16 bytes) are stored, to every target, straight from shared memory
     long long pair0;
     int32_t *tgt_m[8], *tgt_nm[8];
+    // compact mode, completion protocol of the fused all-gather: every post group bumps `done` when its pair has been shipped; the
+    // one that completes the batch publishes this rank's epoch in slot src_rank of every target's flag array (system-scope
+    // fences order the pair stores before it)
+    uint32_t *tgt_flag[8];
+    uint32_t *epoch_done; // [0] current epoch (read), [1] pairs shipped so far (reset by tri_gather_wait_kernel)
+    int src_rank;
     unsigned long long *counters;
     long long *timeline; // debug: [n_my of CTA 0][8] SM-clock stamps, or null
 };
@@ -488,6 +497,7 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
     const int S = P.n_stages, cap = P.cap_bytes, mf = P.max_free;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int n = P.n_feat;
+    const bool compact = P.rows_preset == 3;
     const int n_my = (P.n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const uint32_t bar0 = ts_smem_u32(&bars[0][0]);
     auto bar_of = [&](int st, int which) { return bar0 + (uint32_t)(st * 4 + which) * 8u; };
@@ -511,6 +521,9 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
 
     // per-stage carve-up of the dynamic shared memory
     auto stage_base = [&](int st) { return ts_smem + (size_t)st * P.stage_bytes; };
+    // compact mode: behind the stages, per post group a bitmap of the matched features and its per-word prefix counts
+    const int n_words = (n + 31) >> 5;
+    uint32_t *bm_all = (uint32_t *)(ts_smem + (size_t)S * P.stage_bytes);
     // [A cap][B cap][sCand mf x4][sMask mf x4][sBest mf x4][sList mf x2][sPerm mf x2][sOvf TS_OVF x4][sNodeE max_nodes x4]
 
     if (warp == NC + NG + NJ) {
@@ -716,7 +729,10 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
         const size_t row_off = (size_t)(P.pair0 + p) * n;
         // vMatches12(N, -1) (:1092), while the pair is still being compared
         const int n_scatter = P.rows_preset == 2 ? 1 : P.n_targets; // targets that receive individual match stores
-        if (P.rows_preset != 1) {
+        uint32_t *bm = bm_all + (size_t)grp * 2 * n_words, *wbase = bm + n_words;
+        if (compact) {
+            for (int x = gt; x < n_words; x += GT) bm[x] = 0;
+        } else if (P.rows_preset != 1) {
             for (int r = 0; r < n_scatter; r++) {
                 int32_t *row = P.tgt_m[r] + row_off;
                 if ((n & 3) == 0) {
@@ -746,6 +762,12 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
         const uint4 *lo1 = (const uint4 *)base, *lo2 = (const uint4 *)(base + cap);
         const uint32_t *sCand = (const uint32_t *)(base + 2 * (size_t)cap), *sMask = sCand + mf;
         uint32_t *best = (uint32_t *)sMask + mf;
+        // compact mode: the entry of a slot replaces its (consumed) mask; the ordered list is built over the (dead) join table
+        uint32_t *sEnt = (uint32_t *)sMask, *sOut = (uint32_t *)sCand;
+        auto mark = [&](int slot, int f1, int idx2) {
+            sEnt[slot] = ((uint32_t)f1 << 16) | (uint32_t)idx2;
+            atomicOr(&bm[f1 >> 5], 1u << (f1 & 31));
+        };
         const uint16_t *sList = (const uint16_t *)(best + mf);
         const uint32_t *sOvf = (const uint32_t *)(sList + 2 * mf);
         const uint4 *aux1 = P.aux + (size_t)k1 * n * 2, *aux2 = P.aux + (size_t)k2 * n * 2;
@@ -773,9 +795,12 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
                 mask &= mask - 1;
                 key = min(key, ts_gate(a_lo, h1, q1, c2, lo2, aux2, C.geo, sScale, sSigma, P.coarse));
             }
-            if (key == KEY_NONE) continue;
-            if (via_best) atomicMin(&best[c1], key);
-            else {
+            if (via_best) {
+                if (key != KEY_NONE) atomicMin(&best[c1], key);
+            } else if (compact) {
+                if (key != KEY_NONE) { mark(c1, (int)q1.w, (int)(0xFFFFFu - (key & 0xFFFFFu))); mine++; }
+                else sEnt[c1] = ENT_NONE;
+            } else if (key != KEY_NONE) {
                 put_match((int)q1.w, (int)(0xFFFFFu - (key & 0xFFFFFu)));
                 mine++;
             }
@@ -804,13 +829,14 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
             }
             for (int c = gt; c < m1; c += GT) {
                 const uint32_t key = best[c];
+                if (compact) sEnt[c] = ENT_NONE;
                 if (key == KEY_NONE) continue;
                 const int f1 = (int)aux1[2 * c + 1].w, idx2 = (int)(0xFFFFFu - (key & 0xFFFFFu));
                 if (P.check_ori) {
                     const int bin = rot_bin(ang1[f1], ang2[idx2]);
                     if (bin >= 0 && bin < ORBGPU_HISTO_LENGTH && bin != ind[0] && bin != ind[1] && bin != ind[2]) continue;
                 }
-                put_match(f1, idx2);
+                if (compact) mark(c, f1, idx2); else put_match(f1, idx2);
                 mine++;
             }
         }
@@ -820,6 +846,52 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
         if (gt == 0) {
             const int cnt = s_cnt[grp];
             for (int r = 0; r < P.n_targets; r++) P.tgt_nm[r][P.pair0 + p] = cnt;
+        }
+        if (compact) {
+            // ascending idx1 (:1319-1324): the rank of a match is the number of matched features before it -- prefix counts of the
+            // bitmap words by one warp, then every entry finds its place with one popcount
+            if (gt < 32) {
+                const int per = (n_words + 31) >> 5, w0 = min(n_words, gt * per), w1 = min(n_words, w0 + per);
+                int sum = 0;
+                for (int w = w0; w < w1; w++) sum += __popc(bm[w]);
+                int incl = sum;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(FULL_MASK, incl, o);
+                    if (gt >= o) incl += u;
+                }
+                int run = incl - sum;
+                for (int w = w0; w < w1; w++) { wbase[w] = (uint32_t)run; run += __popc(bm[w]); }
+            }
+            bar_post();
+            const int cnt = s_cnt[grp];
+            auto place = [&](int slot) {
+                const uint32_t en = sEnt[slot];
+                if (en == ENT_NONE) return;
+                const int f1 = (int)(en >> 16);
+                sOut[wbase[f1 >> 5] + __popc(bm[f1 >> 5] & ((1u << (f1 & 31)) - 1u))] = en;
+            };
+            if (via_best) for (int c = gt; c < m1; c += GT) place(c);
+            else for (int e = gt; e < ns; e += GT) place((int)sList[e]);
+            const int n16 = (cnt + 3) >> 2;
+            if (gt < 4 && cnt + gt < 4 * n16) sOut[cnt + gt] = ENT_NONE; // pads the last 16-byte chunk (4 * n16 <= max_free: a multiple of 4)
+            bar_post();
+            // ship: only the valid prefix crosses the links, 16 bytes per store, every target (this rank's own buffer included)
+            for (int r = 0; r < P.n_targets; r++) {
+                uint4 *dst = (uint4 *)(P.tgt_m[r] + row_off);
+                for (int x = gt; x < n16; x += GT) dst[x] = ((const uint4 *)sOut)[x];
+            }
+            if (P.epoch_done) {
+                bar_post(); // all stores of the pair precede the leader's fence
+                if (gt == 0) {
+                    __threadfence_system();
+                    const unsigned old = atomicAdd(&P.epoch_done[1], 1u);
+                    if (old == (unsigned)P.n_pairs - 1u) { // the batch is complete on this rank: publish the epoch everywhere
+                        __threadfence_system();
+                        const unsigned epoch = *(volatile uint32_t *)&P.epoch_done[0];
+                        for (int r = 0; r < P.n_targets; r++) *(volatile uint32_t *)(P.tgt_flag[r] + P.src_rank) = epoch;
+                    }
+                }
+            }
         }
         if (P.rows_preset == 2) { // the row is complete in this rank's buffer (all stores precede the barrier above): ship it whole
             const int32_t *src = P.tgt_m[0] + row_off;
@@ -886,6 +958,35 @@ __global__ void tri_compact_kernel(int n_pairs, int n_feat, const int32_t *__res
         const long long pos = out + __popc(bal & lanemask_lt());
         if (m >= 0 && pos < cap) pairs[pos] = make_int2(i, m);
         out += __popc(bal);
+    }
+}
+
+// Completion of the fused all-gather on the receiving side: one lane per source rank spins until that rank has published the
+// current epoch (or a later one: a fast rank may already have finished the next step into the other buffer), then the epoch
+// advances and the shipped-pairs counter is cleared for the next step.  A source that never arrives trips the time-out instead
+// of hanging the GPU: status[0] = 1.
+__global__ void tri_gather_wait_kernel(const uint32_t *__restrict__ flags, uint32_t wait_mask, uint32_t *__restrict__ epoch_done,
+                                       uint32_t *__restrict__ status)
+{
+    const int lane = threadIdx.x;
+    const uint32_t epoch = epoch_done[0];
+    bool ok = true;
+    if ((wait_mask >> lane) & 1u) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while ((int32_t)(*(volatile const uint32_t *)(flags + lane) - epoch) < 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 4000000000ull) { ok = false; break; } // 4 s
+            __nanosleep(200);
+        }
+    }
+    ok = __all_sync(FULL_MASK, ok);
+    __threadfence_system(); // acquire side: the pair data stored before the flags is visible to what follows in the stream
+    if (lane == 0) {
+        if (!ok && status) status[0] = 1;
+        epoch_done[1] = 0;
+        epoch_done[0] = epoch + 1;
     }
 }
 
@@ -1020,7 +1121,7 @@ extern "C" int orbgpu_triangulation_set_engine(orbgpu_ctx *ctx, int32_t engine)
 static int tri_launch(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs, const int32_t *kf1_dev, const int32_t *kf2_dev,
                       const float *ep_dev, const float *f12_dev, int32_t only_stereo, int32_t coarse, int32_t check_ori,
                       int32_t *matches12_dev, int32_t *nmatches_dev, int n_targets, void *const *tgt_m, void *const *tgt_nm,
-                      int64_t pair_offset, int rows_preset)
+                      int64_t pair_offset, int rows_preset, const orbgpu_tri_gather *gather = nullptr)
 {
     ARG_TRY(ctx && s && n_pairs >= 0);
     ARG_TRY(n_pairs == 0 || (kf1_dev && kf2_dev && ep_dev && f12_dev && matches12_dev && nmatches_dev));
@@ -1033,7 +1134,8 @@ static int tri_launch(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs, c
         constexpr int NC = 16, NG = 12, NJ = 3; // compare / post (two groups) / join warps (+ 1 producer warp = 1024 threads)
         const int cap = (s->max_blob + 127) & ~127;
         const size_t stage_bytes = (2 * (size_t)cap + (size_t)s->max_free * 16 + (size_t)TS_OVF * 4 + (size_t)s->max_nodes * 4 + 127) & ~size_t(127);
-        int n_stages = (int)((227 * 1024 - 2048) / stage_bytes);
+        const size_t bm_bytes = rows_preset == 3 ? (size_t)4 * ((s->n_feat + 31) / 32) * 4 : 0; // 2 post groups x {bitmap, prefix counts}
+        int n_stages = (int)((227 * 1024 - 2048 - bm_bytes) / stage_bytes);
         if (n_stages > 4) n_stages = 4;
         const bool can = !s->u_right && !only_stereo && n_stages >= 3 && s->max_free <= 8192; // each post group holds a stage
         if ((ctx->tri_engine == 2 || tgt_m) && !can)
@@ -1060,8 +1162,16 @@ static int tri_launch(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs, c
                 P.tgt_m[0] = matches12_dev; P.tgt_nm[0] = nmatches_dev;
             }
             P.timeline = (long long *)ctx->tri_timeline;
+            for (int r = 0; r < 8; r++) P.tgt_flag[r] = nullptr;
+            P.epoch_done = nullptr;
+            P.src_rank = 0;
+            if (gather) {
+                for (int r = 0; r < n_targets; r++) P.tgt_flag[r] = (uint32_t *)gather->flags[r];
+                P.epoch_done = (uint32_t *)gather->epoch_done;
+                P.src_rank = gather->rank;
+            }
             auto kern2 = triangulation_stream_kernel<NC, NG, NJ>;
-            const size_t smem2 = stage_bytes * n_stages;
+            const size_t smem2 = stage_bytes * n_stages + bm_bytes;
             const int grid = n_pairs < ctx->sm_count ? n_pairs : ctx->sm_count;
             kern2<<<grid, (NC + NG + NJ + 1) * 32, smem2, ctx->stream>>>(P);
             LAUNCH_COUNT(ctx);
@@ -1196,6 +1306,34 @@ extern "C" int orbgpu_search_for_triangulation_batch_pairs(orbgpu_ctx *ctx, cons
         CU_TRY(cudaStreamSynchronize(ctx->stream));
     }
     return *total <= cap ? ORBGPU_OK : orbgpu_fail(ORBGPU_ERR_OVERFLOW, "pairs capacity too small: see *total");
+}
+
+// Fused search + all-gather in the reference's vMatchedPairs form (see orbgpu_tri_gather in the header): compact (idx1, idx2)
+// entries of this rank's pairs stored straight from shared memory into every rank's buffers, epoch flags instead of a barrier.
+extern "C" int orbgpu_search_for_triangulation_batch_gather_dev(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs,
+                                                                const int32_t *kf1_dev, const int32_t *kf2_dev, const float *ep_dev,
+                                                                const float *f12_dev, int32_t coarse, int32_t check_ori,
+                                                                const orbgpu_tri_gather *g, int64_t pair_offset)
+{
+    ARG_TRY(ctx && s && g && n_pairs > 0 && pair_offset >= 0); // every rank ships at least one pair (its peers wait for its epoch)
+    ARG_TRY(g->n_ranks >= 1 && g->n_ranks <= 8 && g->rank >= 0 && g->rank < g->n_ranks && g->epoch_done);
+    ARG_TRY((s->n_feat & 3) == 0 && s->n_feat <= 65535); // 16-byte stores of (idx1 << 16 | idx2) entries
+    for (int r = 0; r < g->n_ranks; r++) ARG_TRY(g->pairs[r] && g->counts[r] && g->flags[r]);
+    // target 0 = this rank's own buffers, then the peers in ring order (spreads the first stores of a step over the links)
+    void *tm[8], *tn[8];
+    orbgpu_tri_gather go = *g;
+    for (int i = 0; i < g->n_ranks; i++) {
+        const int r = (g->rank + i) % g->n_ranks;
+        tm[i] = g->pairs[r]; tn[i] = g->counts[r]; go.flags[i] = g->flags[r];
+    }
+    int rc = tri_launch(ctx, s, n_pairs, kf1_dev, kf2_dev, ep_dev, f12_dev, 0, coarse, check_ori, (int32_t *)tm[0], (int32_t *)tn[0],
+                        g->n_ranks, tm, tn, pair_offset, 3, &go);
+    if (rc) return rc;
+    tri_gather_wait_kernel<<<1, 32, 0, ctx->stream>>>((const uint32_t *)g->flags[g->rank], g->wait_mask, (uint32_t *)g->epoch_done,
+                                                      (uint32_t *)g->status);
+    LAUNCH_COUNT(ctx);
+    CU_TRY(cudaGetLastError());
+    return ORBGPU_OK;
 }
 
 int triangulation_device_init()

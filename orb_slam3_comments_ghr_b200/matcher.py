@@ -28,6 +28,24 @@ class OrbGpuError(RuntimeError):
     pass
 
 
+class TriGatherStruct(C.Structure):
+    """orbgpu_tri_gather (include/orbmatch_b200.h)"""
+    _fields_ = [("n_ranks", C.c_int32), ("rank", C.c_int32), ("pairs", C.c_void_p * 8), ("counts", C.c_void_p * 8),
+                ("flags", C.c_void_p * 8), ("epoch_done", C.c_void_p), ("status", C.c_void_p), ("wait_mask", C.c_uint32)]
+
+
+def tri_gather_struct(rank: int, pairs, counts, flags, epoch_done: int, status: int = 0, wait_mask: Optional[int] = None) -> TriGatherStruct:
+    n = len(pairs)
+    g = TriGatherStruct()
+    g.n_ranks, g.rank = n, int(rank)
+    for r in range(n):
+        g.pairs[r], g.counts[r], g.flags[r] = int(pairs[r]), int(counts[r]), int(flags[r])
+    g.epoch_done = int(epoch_done)
+    g.status = int(status) if status else None
+    g.wait_mask = ((1 << n) - 1) if wait_mask is None else int(wait_mask)
+    return g
+
+
 def lib_path() -> str:
     return _LIB_PATH
 
@@ -151,6 +169,14 @@ class Context:
         L.orbgpu_fetch_comparisons.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         _check(L.orbgpu_fetch_comparisons(self._h, C.byref(out)))
         return int(out.value)
+
+    def measure_popc_peak(self, variant: int = 0):
+        """integer-pipe peak of this GPU (register-only microbenchmark on all SMs) -> dict(popc_per_s, per_clk_sm, sm_mhz)"""
+        L = load_library()
+        L.orbgpu_measure_popc_peak.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
+        _check(L.orbgpu_measure_popc_peak(self._h, int(variant), C.byref(a), C.byref(b), C.byref(c)))
+        return {"popc_per_s": a.value, "per_clk_sm": b.value, "sm_mhz": c.value}
 
     def set_knn_engine(self, engine: int):
         _check(load_library().orbgpu_knn2_set_engine(self._h, int(engine)))
@@ -384,6 +410,12 @@ class DeviceDb:
             self.nd = int(nd)
             _check(load_library().orbgpu_db_from_dev(ctx.handle, self.nd, C.c_void_p(dev_ptr), C.byref(self._h)))
 
+    def invalidate(self):
+        """the borrowed device memory changed: drop the cached +-1 fp8 expansion (rebuilt by the next tensor-engine search)"""
+        L = load_library()
+        L.orbgpu_db_invalidate.argtypes = [C.c_void_p]
+        _check(L.orbgpu_db_invalidate(self._h))
+
     def update(self, host):
         """re-upload the descriptors in place (no reallocation)"""
         d = as_u8(host).reshape(-1, 32)
@@ -532,6 +564,18 @@ class ORBmatcher:
         _check(L.orbgpu_search_for_triangulation_batch_peers_dev(self.ctx.handle, kfs.handle, int(n_pairs), vp(kf1_ptr), vp(kf2_ptr),
                                                                  vp(ep_ptr), vp(f12_ptr), int(bCoarse), int(self.mbCheckOrientation), n, tm, tn,
                                                                  int(pair_offset), int(rows_preset)))
+
+    # fused search + all-gather in the vMatchedPairs form: compact (idx1 << 16 | idx2) entries + counts into every rank's buffers,
+    # epoch flags instead of a barrier (orbgpu_search_for_triangulation_batch_gather_dev)
+    def SearchForTriangulation_gather_dev(self, kfs: DeviceKfSet, n_pairs, kf1_ptr, kf2_ptr, ep_ptr, f12_ptr, gather: TriGatherStruct,
+                                          pair_offset: int, bCoarse=False):
+        vp = C.c_void_p
+        L = load_library()
+        L.orbgpu_search_for_triangulation_batch_gather_dev.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_int32,
+                                                                       C.POINTER(TriGatherStruct), C.c_int64]
+        _check(L.orbgpu_search_for_triangulation_batch_gather_dev(self.ctx.handle, kfs.handle, int(n_pairs), vp(kf1_ptr), vp(kf2_ptr),
+                                                                  vp(ep_ptr), vp(f12_ptr), int(bCoarse), int(self.mbCheckOrientation),
+                                                                  C.byref(gather), int(pair_offset)))
 
     # brute-force 2-NN + ratio test ("SearchByNN" of BASELINE.json) -> best_idx, best_dist, second_dist, match
     def SearchByNN(self, db: DeviceDb, q, th_low: int = TH_LOW):

@@ -569,6 +569,57 @@ def test_triangulation_multi_target_output(ctx, M):
             assert (c[:lo] == -5).all() and (c[hi:] == -5).all()
 
 
+@pytest.mark.parametrize("seed,n_pairs,n_feat,ori,dense", [(541, 300, 900, 0, 0), (542, 64, 2000, 1, 0), (543, 10, 1200, 0, 1), (544, 10, 1200, 1, 1),
+                                                          (545, 2, 64, 0, 0)])
+def test_triangulation_compact_gather(ctx, M, oracle, seed, n_pairs, n_feat, ori, dense):
+    """the fused search + all-gather in the vMatchedPairs form on ONE GPU: two 'ranks' (one call each, each waiting only for its
+    own epoch) own the two halves of the batch and store into both ranks' buffers; afterwards both buffers hold, for every pair,
+    exactly the compact form of the oracle's dense rows (ascending idx1), both flag arrays carry both epochs, and a second step
+    (epoch 2) lands the same way."""
+    import torch
+    from orb_slam3_comments_ghr_b200.sharding import compact_pairs_from_rows, pairs_from_compact
+    tc = synth.fill_geometry(synth.make_triangulation_case(seed, n_pairs=n_pairs, n_feat=n_feat, n_nodes=12 if dense else 100))
+    if dense:  # a handful of distinct descriptors: nodes with more than 32 surviving candidates -> the sBest / overflow path
+        rng = np.random.default_rng(seed)
+        base = synth.random_descriptors(rng, 3)
+        pick = rng.integers(0, 3, size=tc.kfs.desc.shape[:2])
+        tc.kfs.desc[:] = base[pick] ^ synth.flip_mask(rng, pick.size, np.full(pick.size, 6)).reshape(*pick.shape, 32)
+    enm, em = oracle.search_for_triangulation_batch(tc.kfs, tc.kf1, tc.kf2, tc.ep, tc.f12, 0, 0, ori, n_threads=os.cpu_count() or 1)
+    ecnt, eent = compact_pairs_from_rows(em)
+    assert np.array_equal(ecnt, enm)
+    ks = ctx.upload_kfset(tc.kfs)
+    mm = M.ORBmatcher(0.6, bool(ori), ctx)
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    half = n_pairs // 2
+    bounds = [(0, half), (half, n_pairs)]
+    pairs = [torch.full((n_pairs, n_feat), 0x5A5A5A5A, dtype=torch.int32, device=dev) for _ in range(2)]
+    cnts = [torch.full((n_pairs,), -5, dtype=torch.int32, device=dev) for _ in range(2)]
+    flags = [torch.zeros(8, dtype=torch.int32, device=dev) for _ in range(2)]
+    state = [torch.tensor([1, 0, 0, 0, 0, 0, 0, 0], dtype=torch.int32, device=dev) for _ in range(2)]
+    ins = [[t(a[lo:hi]) for a in (tc.kf1, tc.kf2, tc.ep, tc.f12)] for lo, hi in bounds]
+    for step in (1, 2):
+        for r, (lo, hi) in enumerate(bounds):
+            g = M.tri_gather_struct(r, [x.data_ptr() for x in pairs], [x.data_ptr() for x in cnts], [x.data_ptr() for x in flags],
+                                    state[r].data_ptr(), state[r].data_ptr() + 16, wait_mask=1 << r)
+            mm.SearchForTriangulation_gather_dev(ks, hi - lo, ins[r][0].data_ptr(), ins[r][1].data_ptr(), ins[r][2].data_ptr(),
+                                                 ins[r][3].data_ptr(), g, lo)
+        ctx.synchronize()
+        for r in range(2):
+            assert flags[r][:2].tolist() == [step, step] and state[r].tolist()[:5] == [step + 1, 0, 0, 0, 0]
+            c = cnts[r].cpu().numpy()
+            e = pairs[r].cpu().numpy().view(np.uint32)
+            assert np.array_equal(c, ecnt)
+            for p in range(n_pairs):
+                assert np.array_equal(e[p, :c[p]], eent[p, :c[p]]), (step, r, p)
+                pad = e[p, c[p]:(c[p] + 3) // 4 * 4]
+                assert np.all(pad == 0xFFFFFFFF) and np.all(e[p, (c[p] + 3) // 4 * 4:] == 0x5A5A5A5A)
+                assert np.array_equal(pairs_from_compact(c, e, p)[:, 0], np.flatnonzero(em[p] >= 0))
+        for x in pairs:
+            x.fill_(0x5A5A5A5A)
+    assert int(enm.sum()) > 0
+
+
 @pytest.mark.parametrize("levelsup", [2, 3])
 def test_kfset_transform_then_triangulation(ctx, M, oracle, levelsup):
     """KeyFrame::ComputeBoW for a whole key-frame set on the device: FeatureVector nodes from the vocabulary descent feed the

@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 
 from helpers import ROOT
 from orb_slam3_comments_ghr_b200 import synth
-from orb_slam3_comments_ghr_b200.sharding import all_gather_rows, max_shard, shard_bounds
+from orb_slam3_comments_ghr_b200.sharding import all_gather_rows, compact_pairs_from_rows, max_shard, pairs_from_compact, shard_bounds
 
 
 def test_shard_bounds_cover():
@@ -41,6 +41,13 @@ def _worker(rank, world, port, nq, nd, ret):
     plo, phi = shard_bounds(5, rank, world)
     nm, m = o.search_for_triangulation_batch(tc.kfs, tc.kf1[plo:phi], tc.kf2[plo:phi], tc.ep[plo:phi], tc.f12[plo:phi])
     fullm = all_gather_rows(torch.from_numpy(m), 5)
+    # C4 result form of the fused GPU all-gather (vMatchedPairs: counts + (idx1 << 16 | idx2) entries): shard, compact, gather
+    tc6 = synth.fill_geometry(synth.make_triangulation_case(63, n_pairs=6, n_feat=256))
+    clo, chi = shard_bounds(6, rank, world)
+    _, m6 = o.search_for_triangulation_batch(tc6.kfs, tc6.kf1[clo:chi], tc6.kf2[clo:chi], tc6.ep[clo:chi], tc6.f12[clo:chi])
+    c6, e6 = compact_pairs_from_rows(m6)
+    gc = all_gather_rows(torch.from_numpy(c6), 6)
+    ge = all_gather_rows(torch.from_numpy(e6.view(np.int32)), 6)
     # equal shards: the direct path into a caller-owned buffer
     elo, ehi = shard_bounds(300, rank, world)
     buf = torch.empty((300, 4), dtype=local.dtype)
@@ -49,6 +56,7 @@ def _worker(rank, world, port, nq, nd, ret):
         ret["knn"] = full.numpy()
         ret["tri"] = fullm.numpy()
         ret["knn_eq"] = eq.numpy()
+        ret["tri_counts"], ret["tri_entries"] = gc.numpy(), ge.numpy().view(np.uint32)
         ret["eq_in_place"] = eq.data_ptr() == buf.data_ptr()
     dist.barrier()
     dist.destroy_process_group()
@@ -68,3 +76,9 @@ def test_world2_allgather_matches_single_rank(oracle):
     tc = synth.fill_geometry(synth.make_triangulation_case(62, n_pairs=5, n_feat=256))
     nm, m = oracle.search_for_triangulation_batch(tc.kfs, tc.kf1, tc.kf2, tc.ep, tc.f12)
     assert np.array_equal(ret["tri"], m)
+    tc6 = synth.fill_geometry(synth.make_triangulation_case(63, n_pairs=6, n_feat=256))
+    nm6, m6 = oracle.search_for_triangulation_batch(tc6.kfs, tc6.kf1, tc6.kf2, tc6.ep, tc6.f12)
+    assert np.array_equal(ret["tri_counts"], nm6) and int(nm6.sum()) > 0
+    for p in range(6):  # vMatchedPairs of every pair, ascending idx1 (ORBmatcher.cc:1317-1325)
+        i1 = np.flatnonzero(m6[p] >= 0)
+        assert np.array_equal(pairs_from_compact(ret["tri_counts"], ret["tri_entries"], p), np.stack([i1, m6[p, i1]], axis=1))
