@@ -42,6 +42,12 @@ TH_LOW, NNRATIO = 50, 0.8
 C4_SEED = 20261018
 
 
+def log(msg):
+    """progress on stderr (rank 0): the JSON line on stdout stays the only thing printed there"""
+    if os.environ.get("RANK", "0") == "0":
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -281,6 +287,7 @@ def bench_c5(E, args, K, W):
         return res
 
     units_total = float(nq_total) * float(nd)
+    log(f"c5: {nq_total} x {nd}, warm-up")
     for _ in range(W):
         step()
     E.barrier_sync()
@@ -308,6 +315,7 @@ def bench_c5(E, args, K, W):
     ms_per_step = total_ms / max(K, 1)
     value = units_total / (ms_per_step * 1e-3)
     ctx.synchronize()
+    log(f"c5: {ms_per_step:.2f} ms/step")
     extra = {"comparisons_per_step": int(units_total), "matches_rank0": int((res[3][:nq] >= 0).sum().item()),
              "database_expansion": "the +-1 fp8 copy of the database is cached in the orbgpu_db (built once, before the timed steps): the "
                                    "map changes at key-frame rate, queries arrive per frame; the e2e figure re-uploads AND re-expands "
@@ -444,7 +452,9 @@ def bench_c4(E, args, K, W):
         raise SystemExit("--pairs must be divisible by the number of GPUs")
     lo, hi = shard_bounds(P_total, rank, world)
     P = hi - lo
+    log(f"c4: generating {P} keyframe pairs x {C4_FEAT} features")
     case = c4_case(synth, C4_SEED + rank, P)  # independent pairs: every rank generates (and holds) the key frames of its own pairs
+    log("c4: uploading the keyframe set, peer buffers")
     tg = TriangulationGather(matcher, case.kfs, P_total, C4_FEAT, rank, world, dev, 0.6, False, use_graph=not args.no_graph)
     tg.ctx.set_triangulation_engine(args.tri_engine)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
@@ -454,6 +464,7 @@ def bench_c4(E, args, K, W):
     for _ in range(max(W, 3)):
         tg.step()
     E.barrier_sync()
+    log("c4: graphs captured, calibrating")
     # enough back-to-back steps for nvidia-smi to sample the clocks under this load: ~1.5 s including the L2 flushes
     cal0 = time.perf_counter()
     for _ in range(20):
@@ -487,6 +498,7 @@ def bench_c4(E, args, K, W):
     extra["comparisons_per_step_rank0"] = int(cmp_rank0)
     extra["matches_all_pairs"] = int(cnt.sum().item())
     extra["gather_status"] = tg.status()
+    log(f"c4: {ms_per_step * 1e3:.1f} us/step over {K4} steps")
 
     # ---- end to end: pinned host inputs -> device, the sharded search + gather, the vMatchedPairs of ALL pairs back on the host
     e2e = None
@@ -527,6 +539,7 @@ def bench_c4(E, args, K, W):
         torch.cuda.synchronize()
         dt = E.max_over_ranks((time.perf_counter() - t0) / Ke)
         h2d = case.kf1.nbytes * 2 + case.ep.nbytes + case.f12.nbytes
+        log("c4: e2e done")
         e2e = {"value": P_total / dt, "unit": "frame_pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h[0]),
                "ms_per_step": dt * 1e3, "steps": Ke, "note": note}
 
@@ -652,6 +665,8 @@ def main():
         run_reference(args, rank, world)
         return
 
+    import faulthandler
+    faulthandler.enable()
     import torch
     import torch.distributed as dist
 
@@ -736,6 +751,8 @@ def main():
         line = bench_c4(E, args, K, W)
         if rank == 0:
             print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    log("done")
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

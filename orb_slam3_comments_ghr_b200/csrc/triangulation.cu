@@ -21,6 +21,8 @@
 //            shared memory;
 //   phase C  optional rotation histogram + cull, coalesced write of the match row, match count.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "internal.cuh"
@@ -449,9 +451,9 @@ struct TsParams {
                                 // counts[p] valid entries (rounded up to 16 bytes) are stored, to every target, straight from shared memory
     long long pair0;
     int32_t *tgt_m[8], *tgt_nm[8];
-    // compact mode, completion protocol of the fused all-gather: every post group bumps `done` when its pair has been shipped; the
-    // one that completes the batch publishes this rank's epoch in slot src_rank of every target's flag array (system-scope
-    // fences order the pair stores before it)
+    // compact mode, completion protocol of the fused all-gather: every CTA adds its pairs to `done` when all of them have been
+    // shipped; the one that completes the batch publishes this rank's epoch in slot src_rank of every target's flag array
+    // (system-scope fences order the pair stores before it)
     uint32_t *tgt_flag[8];
     uint32_t *epoch_done; // [0] current epoch (read), [1] pairs shipped so far (reset by tri_gather_wait_kernel)
     int src_rank;
@@ -880,18 +882,6 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
                 uint4 *dst = (uint4 *)(P.tgt_m[r] + row_off);
                 for (int x = gt; x < n16; x += GT) dst[x] = ((const uint4 *)sOut)[x];
             }
-            if (P.epoch_done) {
-                bar_post(); // all stores of the pair precede the leader's fence
-                if (gt == 0) {
-                    __threadfence_system();
-                    const unsigned old = atomicAdd(&P.epoch_done[1], 1u);
-                    if (old == (unsigned)P.n_pairs - 1u) { // the batch is complete on this rank: publish the epoch everywhere
-                        __threadfence_system();
-                        const unsigned epoch = *(volatile uint32_t *)&P.epoch_done[0];
-                        for (int r = 0; r < P.n_targets; r++) *(volatile uint32_t *)(P.tgt_flag[r] + P.src_rank) = epoch;
-                    }
-                }
-            }
         }
         if (P.rows_preset == 2) { // the row is complete in this rank's buffer (all stores precede the barrier above): ship it whole
             const int32_t *src = P.tgt_m[0] + row_off;
@@ -907,6 +897,21 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
         __syncwarp();
         if (gt == 0 && grp == 0) stamp(i, 7);
         if (lane == 0) ts_mbar_arrive(bar_of(st, B_EMPTY));
+    }
+    if (compact && P.epoch_done) {
+        // completion protocol of the fused all-gather, once per CTA: both post groups have issued the stores of all their pairs
+        // (named barrier), then ONE thread orders them at system scope and adds the CTA's pairs to the rank's counter; the CTA that
+        // completes the batch publishes the rank's epoch in every target's flag array
+        asm volatile("bar.sync 5, %0;" ::"r"(NG * 32) : "memory");
+        if (warp == NC && lane == 0) {
+            __threadfence_system();
+            const unsigned old = atomicAdd(&P.epoch_done[1], (unsigned)n_my);
+            if (old + (unsigned)n_my == (unsigned)P.n_pairs) {
+                __threadfence_system();
+                const unsigned epoch = *(volatile uint32_t *)&P.epoch_done[0];
+                for (int r = 0; r < P.n_targets; r++) *(volatile uint32_t *)(P.tgt_flag[r] + P.src_rank) = epoch;
+            }
+        }
     }
 }
 
@@ -1172,6 +1177,9 @@ static int tri_launch(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs, c
             }
             auto kern2 = triangulation_stream_kernel<NC, NG, NJ>;
             const size_t smem2 = stage_bytes * n_stages + bm_bytes;
+            if (getenv("ORBGPU_DEBUG"))
+                fprintf(stderr, "[orbgpu] triangulation_stream_kernel: %d stages x %zu B (+%zu B), max_free %d, max_blob %d, mode %d\n", n_stages,
+                        stage_bytes, bm_bytes, s->max_free, s->max_blob, rows_preset);
             const int grid = n_pairs < ctx->sm_count ? n_pairs : ctx->sm_count;
             kern2<<<grid, (NC + NG + NJ + 1) * 32, smem2, ctx->stream>>>(P);
             LAUNCH_COUNT(ctx);
