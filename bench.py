@@ -455,16 +455,16 @@ def bench_c4(E, args, K, W):
     log(f"c4: generating {P} keyframe pairs x {C4_FEAT} features")
     case = c4_case(synth, C4_SEED + rank, P)  # independent pairs: every rank generates (and holds) the key frames of its own pairs
     log("c4: uploading the keyframe set, peer buffers")
-    tg = TriangulationGather(matcher, case.kfs, P_total, C4_FEAT, rank, world, dev, 0.6, False, use_graph=not args.no_graph)
+    tg = TriangulationGather(matcher, case.kfs, P_total, C4_FEAT, rank, world, dev, 0.6, False, use_graph=args.graph)
     tg.ctx.set_triangulation_engine(args.tri_engine)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     tg.set_inputs(t(case.kf1), t(case.kf2), t(case.ep), t(case.f12))
     extra = {"c4_result_form": "vMatchedPairs: counts[P] + (idx1 << 16 | idx2) entries, ascending idx1, on every rank",
-             "c4_gather": "none (one GPU)" if world == 1 else "fused: peer stores of the compact pairs from inside the search kernel + epoch flags, CUDA graph"}
+             "c4_gather": "none (one GPU)" if world == 1 else "fused: peer stores of the compact pairs from inside the search kernel + epoch flags, one kernel launch per step"}
     for _ in range(max(W, 3)):
         tg.step()
     E.barrier_sync()
-    log("c4: graphs captured, calibrating")
+    log("c4: warm-up done, calibrating")
     # enough back-to-back steps for nvidia-smi to sample the clocks under this load: ~1.5 s including the L2 flushes
     cal0 = time.perf_counter()
     for _ in range(20):
@@ -571,7 +571,7 @@ def bench_c4(E, args, K, W):
         line = {"metric": "frame_pairs_matched_per_s", "value": value, "unit": "frame_pairs/s", "n_gpus": world, "steps": K4, "warmup": max(W, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic", "config": workload_config("c4", args), "clocks": clocks, "e2e": e2e,
-                "gpu_launches": int(2 * K4), "gpu_launches_note": "triangulation_stream_kernel + tri_gather_wait_kernel per step (graph replays)",
+                "gpu_launches": int(K4), "gpu_launches_note": "one triangulation_stream_kernel per step (graph replays): search, compaction, peer stores and the epoch wait in one launch",
                 "roofline": roof, "cpu_baseline": cpu, "engine": args.tri_engine if args.tri_engine else 2, **extra}
     del tg
     return line
@@ -653,7 +653,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=C4_PAIRS)
     ap.add_argument("--engine", type=int, default=0, help="knn2 engine: 0 auto, 1 POPC, 2 mma.sync b1, 3 tcgen05 1-CTA, 4 tcgen05 2-CTA")
     ap.add_argument("--tri-engine", type=int, default=0, help="C4 kernel: 0 auto (2 = persistent bulk-copy pipeline; the gather form needs it)")
-    ap.add_argument("--no-graph", action="store_true", help="C4: launch the step eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--graph", action="store_true", help="C4: replay the step from a CUDA graph (the step is ONE kernel launch: the direct launch is shorter)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="main workload only")
@@ -667,6 +667,14 @@ def main():
 
     import faulthandler
     faulthandler.enable()
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) are sent to stderr instead
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     import torch
     import torch.distributed as dist
 
@@ -746,11 +754,11 @@ def main():
         if rank == 0:
             if secondary:
                 line["secondary"] = secondary
-            print(json.dumps(line), flush=True)
+            emit(line)
     else:
         line = bench_c4(E, args, K, W)
         if rank == 0:
-            print(json.dumps(line), flush=True)
+            emit(line)
     sys.stdout.flush()
     log("done")
     if world > 1:

@@ -275,8 +275,9 @@ int orbgpu_search_for_triangulation_batch_peers_dev(orbgpu_ctx *ctx, const orbgp
  * crosses NVLink -- about 1/10 of the dense rows of the _peers_dev variant -- and it is stored from inside the search kernel,
  * straight from shared memory, into the buffers of ALL ranks while later pairs are still being compared.  There is no
  * cross-rank barrier: when a rank has shipped its last pair it publishes its epoch in slot `rank` of every rank's flag array
- * (system-scope fences order the data before it), and a one-warp kernel at the end of the call waits until every source in
- * wait_mask has published the current epoch, then advances epoch_done[0].  Buffers are peer-mapped device addresses valid on
+ * (system-scope fences order the data before it); the CTA that completes the rank's batch then waits until every source in
+ * wait_mask has published the current epoch and advances epoch_done[0] -- the kernel ends when the gathered result is complete
+ * on this rank, one launch per step.  Buffers are peer-mapped device addresses valid on
  * THIS GPU (e.g. torch symmetric memory); the caller double-buffers pairs / counts between consecutive steps (a rank may be one
  * step ahead of its peers), flags / epoch_done / status are shared by both buffers.  n_feat must be a multiple of 4.
  * Initial state: flags = 0, epoch_done = {1, 0}, status = {0}.  status[0] becomes 1 if a source did not arrive within 4 s. */

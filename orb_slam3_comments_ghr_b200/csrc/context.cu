@@ -166,6 +166,8 @@ int ctx_begin(orbgpu_ctx *ctx)
     ARG_TRY(ctx != nullptr);
     CU_TRY(cudaSetDevice(ctx->device));
     arena_reset(ctx);
+    ctx->gather_counters_clean = false;
+    ctx->cmp_slot = 0;
     CU_TRY(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     return ORBGPU_OK;
 }
@@ -175,7 +177,7 @@ int ctx_fetch_comparisons(orbgpu_ctx *ctx)
     CU_TRY(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                            ctx->stream));
     CU_TRY(cudaStreamSynchronize(ctx->stream));
-    ctx->last_comparisons = (int64_t)ctx->h_counters[0];
+    ctx->last_comparisons = (int64_t)ctx->h_counters[ctx->cmp_slot];
     return ORBGPU_OK;
 }
 

@@ -53,6 +53,8 @@ struct orbgpu_ctx {
     Arena arena;
     int64_t launches = 0;
     int64_t last_comparisons = 0;
+    bool gather_counters_clean = false; // the last call on this context was a fused-gather search (it leaves d_counters[0] == 0)
+    int cmp_slot = 0;                   // d_counters slot that holds the comparisons of the last search (2 after a fused-gather search)
     unsigned long long *d_counters = nullptr; // [8] device counters: [0] comparisons, [1] overflow flag, ...
     unsigned long long *h_counters = nullptr; // pinned mirror
     int knn_engine = 0;

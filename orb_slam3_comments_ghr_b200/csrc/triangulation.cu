@@ -454,11 +454,13 @@ struct TsParams {
     // compact mode, completion protocol of the fused all-gather: every CTA adds its pairs to `done` when all of them have been
     // shipped; the one that completes the batch publishes this rank's epoch in slot src_rank of every target's flag array
     // (system-scope fences order the pair stores before it)
-    uint32_t *tgt_flag[8];
-    uint32_t *epoch_done; // [0] current epoch (read), [1] pairs shipped so far (reset by tri_gather_wait_kernel)
+    uint32_t *tgt_flag[8]; // target 0 = this rank's own flag array
+    uint32_t *epoch_done;  // [0] current epoch, [1] pairs shipped so far; both advanced / cleared by the CTA that completes the batch
+    uint32_t *status;      // [0] = 1 when a peer did not arrive within the time-out (may be null)
+    uint32_t wait_mask;    // source ranks whose epoch the completing CTA waits for before the kernel ends
     int src_rank;
     unsigned long long *counters;
-    long long *timeline; // debug: [n_my of CTA 0][8] SM-clock stamps, or null
+    long long *timeline; // debug: [n_my of CTA 0][16] SM-clock stamps, or null
 };
 
 // One prefilter survivor (slot c1 of keyframe 1 with its aux record {h1, q1} already loaded, slot c2 of keyframe 2):
@@ -483,7 +485,7 @@ __device__ __forceinline__ uint32_t ts_gate(const uint4 a_lo, const uint4 h1, co
     return ts_gate_loaded(a_lo, h1, q1, lo2[c2], aux2[2 * c2], aux2[2 * c2 + 1], geo, sScale, sSigma, coarse);
 }
 
-template <int NC, int NG, int NJ>
+template <int NC, int NG, int NJ, int NGRP>
 __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stream_kernel(const TsParams P)
 {
     constexpr int JT = NJ * 32;
@@ -492,6 +494,7 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
     __shared__ TsStageCtl ctl[4];
     __shared__ float sScale[64], sSigma[64];
     __shared__ int s_cnt[2];    // post groups: matches of the pair in flight
+    __shared__ unsigned long long s_ncmp; // gather mode: this CTA's comparisons (added to the global counter by the post leader)
     __shared__ int sBucket[64]; // join warps: slots per candidate-count bucket, then the buckets' bases
     __shared__ int hist2[2][ORBGPU_HISTO_LENGTH + 2];
     __shared__ int ind2[2][4];
@@ -503,7 +506,7 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
     const int n_my = (P.n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const uint32_t bar0 = ts_smem_u32(&bars[0][0]);
     auto bar_of = [&](int st, int which) { return bar0 + (uint32_t)(st * 4 + which) * 8u; };
-    auto stamp = [&](int i, int ev) { if (P.timeline && blockIdx.x == 0) P.timeline[i * 8 + ev] = clock64(); };
+    auto stamp = [&](int i, int ev) { if (P.timeline && blockIdx.x == 0) P.timeline[i * 16 + ev] = clock64(); };
     enum { B_FULL = 0, B_JOINED = 1, B_COMPARED = 2, B_EMPTY = 3 };
 
     if (t == 0) {
@@ -511,10 +514,11 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
             ts_mbar_init(bar_of(st, B_FULL), 1);
             ts_mbar_init(bar_of(st, B_JOINED), NJ);
             ts_mbar_init(bar_of(st, B_COMPARED), NC);
-            ts_mbar_init(bar_of(st, B_EMPTY), NG / 2);
+            ts_mbar_init(bar_of(st, B_EMPTY), NG / NGRP);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (t == 0) s_ncmp = 0;
     if (t < 64) {
         sScale[t] = t < P.n_levels ? P.scale_factors[t] : 0.f;
         sSigma[t] = t < P.n_levels ? P.level_sigma2[t] : 0.f;
@@ -710,23 +714,29 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
             }
             __syncwarp();
             if (t == 0) stamp(i, 4);
+            if (P.epoch_done && i == n_my - 1) { // gather mode: the CTA's total is complete when the last pair has been compared
+                for (int o = 16; o; o >>= 1) ncmp += __shfl_xor_sync(FULL_MASK, ncmp, o);
+                if (lane == 0 && ncmp) atomicAdd(&s_ncmp, ncmp);
+            }
             if (lane == 0) ts_mbar_arrive(bar_of(st, B_COMPARED));
             if (++st == S) { st = 0; round++; }
         }
-        for (int o = 16; o; o >>= 1) ncmp += __shfl_xor_sync(FULL_MASK, ncmp, o);
-        if (lane == 0 && ncmp) atomicAdd(&P.counters[0], ncmp);
+        if (!P.epoch_done) {
+            for (int o = 16; o; o >>= 1) ncmp += __shfl_xor_sync(FULL_MASK, ncmp, o);
+            if (lane == 0 && ncmp) atomicAdd(&P.counters[0], ncmp);
+        }
         return;
     }
 
     // ---------------- post warps: two groups of NG/2 warps take alternate pairs, so that each group has two compare
     // periods to cover the round trips of its pair's gating step
-    constexpr int GT = (NG / 2) * 32;
-    const int grp = (warp - NC) / (NG / 2), gt = (warp - NC - grp * (NG / 2)) * 32 + lane;
+    constexpr int GT = (NG / NGRP) * 32;
+    const int grp = (warp - NC) / (NG / NGRP), gt = (warp - NC - grp * (NG / NGRP)) * 32 + lane;
     const int bar_id = 2 + grp;
     auto bar_post = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(GT) : "memory"); };
     int *hist = hist2[grp], *ind = ind2[grp];
     for (int i = 0, st = 0, round = 0; i < n_my; i++, st = (st + 1 == S ? 0 : st + 1), round += (st == 0)) {
-        if ((i & 1) != grp) continue;
+        if ((i % NGRP) != grp) continue;
         const int p = blockIdx.x + i * gridDim.x;
         const size_t row_off = (size_t)(P.pair0 + p) * n;
         // vMatches12(N, -1) (:1092), while the pair is still being compared
@@ -751,97 +761,98 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
         if (gt == 0) s_cnt[grp] = 0;
         if (P.check_ori && gt < ORBGPU_HISTO_LENGTH) hist[gt] = 0;
         bar_post(); // the row is initialised before any thread of the group writes a match into it
-        if (gt == 0 && grp == 0) stamp(i, 5);
+        if (gt == 0) stamp(i, 5);
         ts_mbar_wait_relaxed(bar_of(st, B_COMPARED), round & 1);
-        if (gt == 0 && grp == 0) stamp(i, 6);
-        const TsStageCtl &C = ctl[st];
+        if (gt == 0) stamp(i, 6);
+        TsStageCtl &C = ctl[st];
         const int k1 = C.k1, k2 = C.k2, m1 = C.m1, ns = C.n_list;
-        const int n_ovf_all = C.n_ovf, n_ovf = min(n_ovf_all, TS_OVF);
-        // a slot's candidates are all in its mask unless its node has more than 32: then (and for the rotation
-        // histogram) the per-slot minimum goes through sBest and the slot owners write the row after a barrier
-        const bool via_best = n_ovf_all > 0 || P.check_ori;
+        const int n_ovf_cmp = C.n_ovf; // entries the compare warps left: nodes with more than 32 candidates (rare)
         unsigned char *base = stage_base(st);
         const uint4 *lo1 = (const uint4 *)base, *lo2 = (const uint4 *)(base + cap);
         const uint32_t *sCand = (const uint32_t *)(base + 2 * (size_t)cap), *sMask = sCand + mf;
         uint32_t *best = (uint32_t *)sMask + mf;
-        // compact mode: the entry of a slot replaces its (consumed) mask; the ordered list is built over the (dead) join table
+        const uint16_t *sList = (const uint16_t *)(best + mf);
+        uint32_t *sOvf = (uint32_t *)(sList + 2 * mf);
+        const uint4 *aux1 = P.aux + (size_t)k1 * n * 2, *aux2 = P.aux + (size_t)k2 * n * 2;
+        // the feature id of a listed slot replaces its (consumed) mask; compact mode: its entry does, and the ordered list is built
+        // over the (dead) join table
         uint32_t *sEnt = (uint32_t *)sMask, *sOut = (uint32_t *)sCand;
         auto mark = [&](int slot, int f1, int idx2) {
             sEnt[slot] = ((uint32_t)f1 << 16) | (uint32_t)idx2;
             atomicOr(&bm[f1 >> 5], 1u << (f1 & 31));
         };
-        const uint16_t *sList = (const uint16_t *)(best + mf);
-        const uint32_t *sOvf = (const uint32_t *)(sList + 2 * mf);
-        const uint4 *aux1 = P.aux + (size_t)k1 * n * 2, *aux2 = P.aux + (size_t)k2 * n * 2;
         int mine = 0;
-        // ---- one listed slot per thread: finish the distances, gates, minimum
+        // ---- pass A: one listed slot per thread and its FIRST flagged candidate.  A slot rarely has a second one (a false positive
+        // of the 128-bit prefilter next to the true match: ~4 % of the slots); those go to the stage's overflow list instead of making
+        // every lane of the warp walk a second gate.  The per-slot minimum (last-wins ties of :1180) is collected in sBest.
         for (int e = gt; e < ns; e += GT) {
             const int c1 = (int)sList[e];
             uint32_t mask = sMask[c1];
             const int s2 = (int)(sCand[c1] & 0xFFFF);
-            // the records of the slot and of its first two candidates are requested together: one round trip for
-            // nearly every slot (a third candidate is rare)
             const int ca = s2 + __ffs(mask) - 1;
-            mask &= mask - 1;
-            const bool two = mask != 0;
-            const int cb = two ? s2 + __ffs(mask) - 1 : ca;
             mask &= mask - 1;
             const uint4 h1 = aux1[2 * c1], q1 = aux1[2 * c1 + 1];
             const uint4 ha = aux2[2 * ca], qa = aux2[2 * ca + 1];
-            const uint4 hb = aux2[2 * cb], qb = aux2[2 * cb + 1];
             const uint4 a_lo = lo1[c1];
-            uint32_t key = ts_gate_loaded(a_lo, h1, q1, lo2[ca], ha, qa, C.geo, sScale, sSigma, P.coarse);
-            if (two) key = min(key, ts_gate_loaded(a_lo, h1, q1, lo2[cb], hb, qb, C.geo, sScale, sSigma, P.coarse));
             while (mask) {
                 const int c2 = s2 + __ffs(mask) - 1;
                 mask &= mask - 1;
-                key = min(key, ts_gate(a_lo, h1, q1, c2, lo2, aux2, C.geo, sScale, sSigma, P.coarse));
+                const int slot = atomicAdd(&C.n_ovf, 1);
+                if (slot < TS_OVF) sOvf[slot] = (uint32_t)c1 | ((uint32_t)c2 << 13);
+                else { // list full (adversarial inputs only): gate in place
+                    const uint32_t k2nd = ts_gate(a_lo, h1, q1, c2, lo2, aux2, C.geo, sScale, sSigma, P.coarse);
+                    if (k2nd != KEY_NONE) atomicMin(&best[c1], k2nd);
+                }
             }
-            if (via_best) {
-                if (key != KEY_NONE) atomicMin(&best[c1], key);
-            } else if (compact) {
-                if (key != KEY_NONE) { mark(c1, (int)q1.w, (int)(0xFFFFFu - (key & 0xFFFFFu))); mine++; }
-                else sEnt[c1] = ENT_NONE;
-            } else if (key != KEY_NONE) {
-                put_match((int)q1.w, (int)(0xFFFFFu - (key & 0xFFFFFu)));
-                mine++;
-            }
+            const uint32_t key = ts_gate_loaded(a_lo, h1, q1, lo2[ca], ha, qa, C.geo, sScale, sSigma, P.coarse);
+            if (key != KEY_NONE) atomicMin(&best[c1], key);
+            sEnt[c1] = q1.w; // feature id of the slot, for the output pass
         }
-        if (via_best) {
-            for (int e = gt; e < n_ovf; e += GT) {
-                const uint32_t en = sOvf[e];
-                const int c1 = (int)(en & 0x1FFF);
-                const uint32_t key = ts_gate(lo1[c1], aux1[2 * c1], aux1[2 * c1 + 1], (int)((en >> 13) & 0x1FFF), lo2, aux2, C.geo, sScale,
-                                             sSigma, P.coarse);
-                if (key != KEY_NONE) atomicMin(&best[c1], key);
+        bar_post();
+        // ---- pass B: the overflow list (compare warps' and pass A's entries), one candidate per thread
+        const int n_ovf = min(C.n_ovf, TS_OVF);
+        for (int e = gt; e < n_ovf; e += GT) {
+            const uint32_t en = sOvf[e];
+            const int c1 = (int)(en & 0x1FFF);
+            const uint32_t key = ts_gate(lo1[c1], aux1[2 * c1], aux1[2 * c1 + 1], (int)((en >> 13) & 0x1FFF), lo2, aux2, C.geo, sScale,
+                                         sSigma, P.coarse);
+            if (key != KEY_NONE) atomicMin(&best[c1], key);
+        }
+        if (n_ovf > 0) bar_post();
+        // ---- output by the slots' owners: the listed slots, or every slot when the compare warps found a node with more than 32
+        // candidates (such a slot can have survivors without being listed)
+        const bool all_slots = n_ovf_cmp > 0;
+        const int n_own = all_slots ? m1 : ns;
+        const float *ang1 = P.angle + (size_t)k1 * n, *ang2 = P.angle + (size_t)k2 * n;
+        auto slot_of = [&](int e) { return all_slots ? e : (int)sList[e]; };
+        auto feat_of = [&](int c) { return all_slots ? (int)aux1[2 * c + 1].w : (int)sEnt[c]; };
+        if (P.check_ori) { // :1266-1277, :1295-1314
+            for (int e = gt; e < n_own; e += GT) {
+                const int c = slot_of(e);
+                const uint32_t key = best[c];
+                if (key == KEY_NONE) continue;
+                const int bin = rot_bin(ang1[feat_of(c)], ang2[(int)(0xFFFFFu - (key & 0xFFFFFu))]);
+                if (bin >= 0 && bin < ORBGPU_HISTO_LENGTH) atomicAdd(&hist[bin], 1);
             }
             bar_post();
-            // ---- output by slot owners
-            const float *ang1 = P.angle + (size_t)k1 * n, *ang2 = P.angle + (size_t)k2 * n;
-            if (P.check_ori) { // :1266-1277, :1295-1314
-                for (int c = gt; c < m1; c += GT) {
-                    const uint32_t key = best[c];
-                    if (key == KEY_NONE) continue;
-                    const int bin = rot_bin(ang1[aux1[2 * c + 1].w], ang2[(int)(0xFFFFFu - (key & 0xFFFFFu))]);
-                    if (bin >= 0 && bin < ORBGPU_HISTO_LENGTH) atomicAdd(&hist[bin], 1);
-                }
-                bar_post();
-                if (gt == 0) three_maxima(hist, ORBGPU_HISTO_LENGTH, ind[0], ind[1], ind[2]);
-                bar_post();
-            }
-            for (int c = gt; c < m1; c += GT) {
-                const uint32_t key = best[c];
-                if (compact) sEnt[c] = ENT_NONE;
-                if (key == KEY_NONE) continue;
-                const int f1 = (int)aux1[2 * c + 1].w, idx2 = (int)(0xFFFFFu - (key & 0xFFFFFu));
-                if (P.check_ori) {
-                    const int bin = rot_bin(ang1[f1], ang2[idx2]);
-                    if (bin >= 0 && bin < ORBGPU_HISTO_LENGTH && bin != ind[0] && bin != ind[1] && bin != ind[2]) continue;
-                }
-                if (compact) mark(c, f1, idx2); else put_match(f1, idx2);
-                mine++;
-            }
+            if (gt == 0) three_maxima(hist, ORBGPU_HISTO_LENGTH, ind[0], ind[1], ind[2]);
+            bar_post();
         }
+        for (int e = gt; e < n_own; e += GT) {
+            const int c = slot_of(e);
+            const uint32_t key = best[c];
+            const int f1 = key != KEY_NONE || !compact ? feat_of(c) : 0;
+            if (compact) sEnt[c] = ENT_NONE;
+            if (key == KEY_NONE) continue;
+            const int idx2 = (int)(0xFFFFFu - (key & 0xFFFFFu));
+            if (P.check_ori) {
+                const int bin = rot_bin(ang1[f1], ang2[idx2]);
+                if (bin >= 0 && bin < ORBGPU_HISTO_LENGTH && bin != ind[0] && bin != ind[1] && bin != ind[2]) continue;
+            }
+            if (compact) mark(c, f1, idx2); else put_match(f1, idx2);
+            mine++;
+        }
+        if (gt == 0) stamp(i, 8);
         for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(FULL_MASK, mine, o);
         if (lane == 0 && mine) atomicAdd(&s_cnt[grp], mine);
         bar_post(); // the group's count is complete; hist / ind may be reused by the next pair
@@ -872,11 +883,11 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
                 const int f1 = (int)(en >> 16);
                 sOut[wbase[f1 >> 5] + __popc(bm[f1 >> 5] & ((1u << (f1 & 31)) - 1u))] = en;
             };
-            if (via_best) for (int c = gt; c < m1; c += GT) place(c);
-            else for (int e = gt; e < ns; e += GT) place((int)sList[e]);
+            for (int e = gt; e < n_own; e += GT) place(slot_of(e));
             const int n16 = (cnt + 3) >> 2;
             if (gt < 4 && cnt + gt < 4 * n16) sOut[cnt + gt] = ENT_NONE; // pads the last 16-byte chunk (4 * n16 <= max_free: a multiple of 4)
             bar_post();
+            if (gt == 0) stamp(i, 9);
             // ship: only the valid prefix crosses the links, 16 bytes per store, every target (this rank's own buffer included)
             for (int r = 0; r < P.n_targets; r++) {
                 uint4 *dst = (uint4 *)(P.tgt_m[r] + row_off);
@@ -895,21 +906,41 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
             }
         }
         __syncwarp();
-        if (gt == 0 && grp == 0) stamp(i, 7);
+        if (gt == 0) stamp(i, 7);
         if (lane == 0) ts_mbar_arrive(bar_of(st, B_EMPTY));
     }
     if (compact && P.epoch_done) {
         // completion protocol of the fused all-gather, once per CTA: both post groups have issued the stores of all their pairs
-        // (named barrier), then ONE thread orders them at system scope and adds the CTA's pairs to the rank's counter; the CTA that
-        // completes the batch publishes the rank's epoch in every target's flag array
+        // (named barrier), then ONE thread orders them at system scope and adds the CTA's pairs to the rank's counter.  The CTA that
+        // completes the batch publishes the rank's epoch in every target's flag array, waits until every source in wait_mask has
+        // published it too (or a later one: a fast rank may already have finished the next step into the other buffer), and
+        // advances the epoch -- the kernel ends when the gathered result is complete on this rank.  No memset, no second kernel.
         asm volatile("bar.sync 5, %0;" ::"r"(NG * 32) : "memory");
         if (warp == NC && lane == 0) {
+            if (s_ncmp) atomicAdd(&P.counters[0], s_ncmp);
             __threadfence_system();
             const unsigned old = atomicAdd(&P.epoch_done[1], (unsigned)n_my);
             if (old + (unsigned)n_my == (unsigned)P.n_pairs) {
                 __threadfence_system();
                 const unsigned epoch = *(volatile uint32_t *)&P.epoch_done[0];
                 for (int r = 0; r < P.n_targets; r++) *(volatile uint32_t *)(P.tgt_flag[r] + P.src_rank) = epoch;
+                P.counters[2] = atomicExch(&P.counters[0], 0ull); // comparisons of this step; the running counter restarts at zero
+                bool ok = true;
+                unsigned long long t0;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                for (int src = 0; src < P.n_targets && ok; src++) {
+                    if (!((P.wait_mask >> src) & 1u)) continue;
+                    while ((int32_t)(*(volatile const uint32_t *)(P.tgt_flag[0] + src) - epoch) < 0) {
+                        unsigned long long t1;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                        if (t1 - t0 > 4000000000ull) { ok = false; break; } // 4 s: a peer that never arrives must not hang the GPU
+                        __nanosleep(100);
+                    }
+                }
+                __threadfence_system(); // acquire side: the peers' pair data precedes their flags
+                if (!ok && P.status) P.status[0] = 1;
+                *(volatile uint32_t *)&P.epoch_done[1] = 0;
+                *(volatile uint32_t *)&P.epoch_done[0] = epoch + 1;
             }
         }
     }
@@ -963,35 +994,6 @@ __global__ void tri_compact_kernel(int n_pairs, int n_feat, const int32_t *__res
         const long long pos = out + __popc(bal & lanemask_lt());
         if (m >= 0 && pos < cap) pairs[pos] = make_int2(i, m);
         out += __popc(bal);
-    }
-}
-
-// Completion of the fused all-gather on the receiving side: one lane per source rank spins until that rank has published the
-// current epoch (or a later one: a fast rank may already have finished the next step into the other buffer), then the epoch
-// advances and the shipped-pairs counter is cleared for the next step.  A source that never arrives trips the time-out instead
-// of hanging the GPU: status[0] = 1.
-__global__ void tri_gather_wait_kernel(const uint32_t *__restrict__ flags, uint32_t wait_mask, uint32_t *__restrict__ epoch_done,
-                                       uint32_t *__restrict__ status)
-{
-    const int lane = threadIdx.x;
-    const uint32_t epoch = epoch_done[0];
-    bool ok = true;
-    if ((wait_mask >> lane) & 1u) {
-        unsigned long long t0;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        while ((int32_t)(*(volatile const uint32_t *)(flags + lane) - epoch) < 0) {
-            unsigned long long t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 4000000000ull) { ok = false; break; } // 4 s
-            __nanosleep(200);
-        }
-    }
-    ok = __all_sync(FULL_MASK, ok);
-    __threadfence_system(); // acquire side: the pair data stored before the flags is visible to what follows in the stream
-    if (lane == 0) {
-        if (!ok && status) status[0] = 1;
-        epoch_done[1] = 0;
-        epoch_done[0] = epoch + 1;
     }
 }
 
@@ -1131,7 +1133,11 @@ static int tri_launch(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs, c
     ARG_TRY(ctx && s && n_pairs >= 0);
     ARG_TRY(n_pairs == 0 || (kf1_dev && kf2_dev && ep_dev && f12_dev && matches12_dev && nmatches_dev));
     CU_TRY(cudaSetDevice(ctx->device));
-    CU_TRY(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    // the gather form keeps the comparison counter itself (the completing CTA moves it to slot 2 and clears it): no memset node in
+    // the step unless another call has used the counters in between
+    if (!gather || !ctx->gather_counters_clean) CU_TRY(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    ctx->gather_counters_clean = gather != nullptr;
+    ctx->cmp_slot = gather ? 2 : 0;
     if (n_pairs == 0) return ORBGPU_OK;
     // engine 2: persistent warp-specialised pipeline (monocular sets; bOnlyStereo on a monocular set matches nothing
     // and is left to the per-pair kernel)
@@ -1169,13 +1175,19 @@ static int tri_launch(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs, c
             P.timeline = (long long *)ctx->tri_timeline;
             for (int r = 0; r < 8; r++) P.tgt_flag[r] = nullptr;
             P.epoch_done = nullptr;
+            P.status = nullptr;
+            P.wait_mask = 0;
             P.src_rank = 0;
             if (gather) {
                 for (int r = 0; r < n_targets; r++) P.tgt_flag[r] = (uint32_t *)gather->flags[r];
                 P.epoch_done = (uint32_t *)gather->epoch_done;
+                P.status = (uint32_t *)gather->status;
                 P.src_rank = gather->rank;
+                // wait_mask is given by rank; the kernel's targets are in ring order starting at this rank
+                for (int i = 0; i < n_targets; i++)
+                    if ((gather->wait_mask >> ((gather->rank + i) % n_targets)) & 1u) P.wait_mask |= 1u << i;
             }
-            auto kern2 = triangulation_stream_kernel<NC, NG, NJ>;
+            auto kern2 = triangulation_stream_kernel<NC, NG, NJ, 2>;
             const size_t smem2 = stage_bytes * n_stages + bm_bytes;
             if (getenv("ORBGPU_DEBUG"))
                 fprintf(stderr, "[orbgpu] triangulation_stream_kernel: %d stages x %zu B (+%zu B), max_free %d, max_blob %d, mode %d\n", n_stages,
@@ -1334,20 +1346,14 @@ extern "C" int orbgpu_search_for_triangulation_batch_gather_dev(orbgpu_ctx *ctx,
         const int r = (g->rank + i) % g->n_ranks;
         tm[i] = g->pairs[r]; tn[i] = g->counts[r]; go.flags[i] = g->flags[r];
     }
-    int rc = tri_launch(ctx, s, n_pairs, kf1_dev, kf2_dev, ep_dev, f12_dev, 0, coarse, check_ori, (int32_t *)tm[0], (int32_t *)tn[0],
-                        g->n_ranks, tm, tn, pair_offset, 3, &go);
-    if (rc) return rc;
-    tri_gather_wait_kernel<<<1, 32, 0, ctx->stream>>>((const uint32_t *)g->flags[g->rank], g->wait_mask, (uint32_t *)g->epoch_done,
-                                                      (uint32_t *)g->status);
-    LAUNCH_COUNT(ctx);
-    CU_TRY(cudaGetLastError());
-    return ORBGPU_OK;
+    return tri_launch(ctx, s, n_pairs, kf1_dev, kf2_dev, ep_dev, f12_dev, 0, coarse, check_ori, (int32_t *)tm[0], (int32_t *)tn[0], g->n_ranks,
+                      tm, tn, pair_offset, 3, &go);
 }
 
 int triangulation_device_init()
 {
     int rc;
-    if ((rc = set_max_dyn_smem(kfset_csr_kernel)) || (rc = set_max_dyn_smem(triangulation_stream_kernel<16, 12, 3>)) ||
+    if ((rc = set_max_dyn_smem(kfset_csr_kernel)) || (rc = set_max_dyn_smem(triangulation_stream_kernel<16, 12, 3, 2>)) ||
         (rc = set_max_dyn_smem(triangulation_pairs_kernel<true>)) || (rc = set_max_dyn_smem(triangulation_pairs_kernel<false>)))
         return rc;
     return ORBGPU_OK;
