@@ -156,6 +156,50 @@ int orbgpu_search_by_projection_local(orbgpu_ctx *ctx, const orbgpu_frame *f, co
                                       float th, int32_t far_points, float th_far_points, float nnratio,
                                       const int32_t *kp_prior_obs, int32_t *kp_mp, int32_t *nmatches);
 
+/* ---- 8(f) rank 1: Frame::isInFrustum (Frame.cc:676-782, Nleft == -1) for a whole list of map points, on the device, and the fused
+ * Tracking::SearchLocalPoints step: isInFrustum + SearchByProjection(Frame&, vector<MapPoint*>&) without the host loop between them.
+ * The frame's pose members are inputs exactly as the reference holds them (mRcw, mtcw, mOw: Frame.h, filled by
+ * Frame::UpdatePoseMatrices with the host's own Sophus); everything from `mRcw * P + mtcw` on is evaluated on the device in the
+ * reference's fp32 operation order.  PredictScale (MapPoint.cc:695-738) takes the logarithm in double precision and rounds it to
+ * float: it can differ from the host libm's logf by one ulp, which moves the predicted level only when log(ratio) / logScaleFactor
+ * lies within one ulp of an integer -- the C++ adapter's checker mode counts such disagreements (north_star target: zero). */
+typedef struct orbgpu_frustum_host {
+    float Rcw[9];            /* Frame::mRcw, row-major */
+    float tcw[3];            /* Frame::mtcw */
+    float Ow[3];             /* Frame::mOw */
+    float K[4];              /* pinhole fx fy cx cy (mpCamera->project, Pinhole.cpp:64-71) */
+    float mbf;               /* Frame::mbf (mTrackProjXR = u - mbf / z) */
+    float min_x, min_y, max_x, max_y; /* Frame::mnMinX .. mnMaxY */
+    float viewing_cos_limit; /* 0.5 in Tracking::SearchLocalPoints */
+    float log_scale_factor;  /* Frame::mfLogScaleFactor */
+    int32_t n_levels;        /* Frame::mnScaleLevels */
+} orbgpu_frustum_host;
+/* world_pos [n][3], normal [n][3], min_distance / max_distance [n] = MapPoint::mfMinDistance / mfMaxDistance (the 0.8 / 1.2
+ * invariance factors of MapPoint.cc:665-678 are applied inside).  Outputs [n] (each may be NULL): the members isInFrustum writes --
+ * in_view = mbTrackInView, proj_xy = mTrackProjX/Y (-1 when rejected before the image-bounds test passed), proj_xr, depth,
+ * scale_level, view_cos (0 when the point is rejected). */
+int orbgpu_is_in_frustum(orbgpu_ctx *ctx, const orbgpu_frustum_host *fr, int32_t n, const float *world_pos, const float *normal,
+                         const float *min_distance, const float *max_distance, uint8_t *in_view, float *proj_xy, float *proj_xr,
+                         float *depth, int32_t *scale_level, float *view_cos);
+/* Tracking::SearchLocalPoints (Tracking.cc: isInFrustum over mvpLocalMapPoints, then SearchByProjection): map points as the
+ * reference's loop sees them.  skip [n] = 1 for points the loop does not test (already matched in the current frame, isBad): they
+ * keep mbTrackInView = false.  in_view [n] out (may be NULL) tells the caller which points to IncreaseVisible(); the rest is
+ * orbgpu_search_by_projection_local on the device-resident projections. */
+typedef struct orbgpu_localpoints_host {
+    int32_t n;
+    const uint8_t *desc;         /* [n][32] MapPoint::GetDescriptor() */
+    const float *world_pos;      /* [n][3] */
+    const float *normal;         /* [n][3] */
+    const float *min_distance;   /* [n] mfMinDistance */
+    const float *max_distance;   /* [n] mfMaxDistance */
+    const uint8_t *skip;         /* [n] or NULL */
+    const uint8_t *bad;          /* [n] isBad() at matching time (ORBmatcher.cc:62) */
+    const int32_t *n_obs;        /* [n] Observations() */
+} orbgpu_localpoints_host;
+int orbgpu_search_local_points(orbgpu_ctx *ctx, const orbgpu_frame *f, const orbgpu_frustum_host *fr, const orbgpu_localpoints_host *pts,
+                               float th, int32_t far_points, float th_far_points, float nnratio, const int32_t *kp_prior_obs,
+                               int32_t *kp_mp, uint8_t *in_view, int32_t *nmatches);
+
 /* ---- a6: the projection-gated searches that do their own projection: SearchByProjection(Cur, Last) (ORBmatcher.cc:1957-2191),
  * SearchByProjection(Cur, KF, sAlreadyFound) (:2203-2330), SearchByProjection(KF, Sim3, ...) x2 (:498-733),
  * Fuse x2 (:1330-1682), SearchBySim3 (:1684-1955).  They share one skeleton after the per-point prologue

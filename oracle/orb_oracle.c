@@ -487,9 +487,9 @@ void oracle_compute_distinctive_descriptors(int32_t n_mp, const int32_t *offsets
     }
 }
 
-/* Coarse stage of Frame::ComputeStereoMatches (src/Frame.cc:1139-1216).  Frame.cc cannot be compiled here (OpenCV image
- * pyramids), so this is a restatement only, cross-checked with numpy in tests/test_oracle_golden.py.  Rows outside
- * [0, n_rows) are undefined behaviour in the reference (vRowIndices[yi]) and are ignored here. */
+/* Coarse stage of Frame::ComputeStereoMatches (src/Frame.cc:1117-1247).  Pinned on the reference's own text of that stage
+ * (oracle/extract_ref.py cuts Frame.cc:1117-1247 into oracle/_ref, ref_stereo_coarse_match; tests/test_oracle_vs_ref.py).  Rows
+ * outside [0, n_rows) are undefined behaviour in the reference (vRowIndices[yi]) and are ignored here. */
 void oracle_stereo_coarse_match(int32_t n_left, const uint8_t *desc_l, const float *kp_xy_l, const int32_t *octave_l, int32_t n_right,
                                 const uint8_t *desc_r, const float *kp_xy_r, const int32_t *octave_r, const float *scale_factors,
                                 int32_t n_rows, float mb, float mbf, int32_t *best_idx_r, int32_t *best_dist)
@@ -761,6 +761,73 @@ static int epipolar_constrain(const float *F12, float x1, float y1, float x2, fl
     if (den == 0) return 0;
     const float dsqr = num * num / den;
     return dsqr < 3.84 * unc; /* double compare */
+}
+
+int oracle_epipolar_constrain(const float *F12, float x1, float y1, float x2, float y2, float unc)
+{
+    return epipolar_constrain(F12, x1, y1, x2, y2, unc);
+}
+
+/* Pinhole.cpp:64-71 */
+void oracle_pinhole_project(const float *K, const float *xyz, float *uv)
+{
+    uv[0] = K[0] * xyz[0] / xyz[2] + K[2];
+    uv[1] = K[1] * xyz[1] / xyz[2] + K[3];
+}
+
+/* MapPoint.cc:695-738: ratio = mfMaxDistance / currentDist; ceil(log(ratio) / mfLogScaleFactor) with the float overload of log,
+ * clamped to [0, nLevels - 1] */
+int oracle_predict_scale(float max_distance, float current_dist, float log_scale_factor, int n_levels)
+{
+    const float ratio = max_distance / current_dist;
+    int nScale = (int)ceilf(logf(ratio) / log_scale_factor);
+    if (nScale < 0)
+        nScale = 0;
+    else if (nScale >= n_levels)
+        nScale = n_levels - 1;
+    return nScale;
+}
+
+/* Frame::isInFrustum, Nleft == -1 (Frame.cc:676-782).  The frame's pose members are inputs exactly as the reference holds them:
+ * mRcw (row-major 3x3), mtcw, mOw (Frame.h; filled by UpdatePoseMatrices with the host's Sophus).  Outputs = the MapPoint members
+ * the function writes; a point rejected after the image-bounds test keeps its projection in proj_xy (:712-713) with in_view 0. */
+void oracle_is_in_frustum(const orbgpu_frustum_host *fr, int32_t n, const float *world_pos, const float *normal,
+                          const float *min_distance, const float *max_distance, uint8_t *in_view, float *proj_xy, float *proj_xr,
+                          float *depth, int32_t *scale_level, float *view_cos)
+{
+    const float *R = fr->Rcw, *t = fr->tcw, *Ow = fr->Ow;
+    for (int i = 0; i < n; i++) {
+        in_view[i] = 0;            /* :682 */
+        proj_xy[2 * i] = -1.f;     /* :683-684 */
+        proj_xy[2 * i + 1] = -1.f;
+        proj_xr[i] = 0.f; depth[i] = 0.f; scale_level[i] = 0; view_cos[i] = 0.f; /* untouched members: reported as 0 */
+        const float *P = world_pos + 3 * i;
+        float Pc[3];
+        for (int r = 0; r < 3; r++) Pc[r] = (R[3 * r] * P[0] + R[3 * r + 1] * P[1] + R[3 * r + 2] * P[2]) + t[r]; /* :695 */
+        const float Pc_dist = sqrtf(Pc[0] * Pc[0] + Pc[1] * Pc[1] + Pc[2] * Pc[2]);
+        const float PcZ = Pc[2];
+        const float invz = 1.0f / PcZ;
+        if (PcZ < 0.0f) continue; /* :701 */
+        float uv[2];
+        oracle_pinhole_project(fr->K, Pc, uv); /* :704 */
+        if (uv[0] < fr->min_x || uv[0] > fr->max_x) continue; /* :707 */
+        if (uv[1] < fr->min_y || uv[1] > fr->max_y) continue;
+        proj_xy[2 * i] = uv[0]; /* :712-713 */
+        proj_xy[2 * i + 1] = uv[1];
+        const float maxDistance = 1.2f * max_distance[i], minDistance = 0.8f * min_distance[i]; /* MapPoint.cc:665-678 */
+        const float PO[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]};
+        const float dist = sqrtf(PO[0] * PO[0] + PO[1] * PO[1] + PO[2] * PO[2]);
+        if (dist < minDistance || dist > maxDistance) continue; /* :723 */
+        const float *Pn = normal + 3 * i;
+        const float viewCos = (PO[0] * Pn[0] + PO[1] * Pn[1] + PO[2] * Pn[2]) / dist; /* :730 */
+        if (viewCos < fr->viewing_cos_limit) continue;
+        const int nPredictedLevel = oracle_predict_scale(max_distance[i], dist, fr->log_scale_factor, fr->n_levels); /* :737 */
+        in_view[i] = 1;
+        proj_xr[i] = uv[0] - fr->mbf * invz; /* :743 */
+        depth[i] = Pc_dist;
+        scale_level[i] = nPredictedLevel;
+        view_cos[i] = viewCos;
+    }
 }
 
 /* per-keyframe FeatureVector CSR from the per-feature node ids of a kfset */

@@ -12,12 +12,13 @@
  * tests/test_oracle_vs_ref.py) and against the golden vectors generated from that build
  * (tests/golden/, scripts/make_golden.py).
  *
- * PARITY UNPINNED for one function only: oracle_stereo_coarse_match (Frame.cc:1139-1216).  Frame.cc needs OpenCV image
- * operations, Eigen, Boost and g2o headers that do not exist in this image, so the reference cannot be compiled for it; the
- * restatement is cross-checked against an independent numpy evaluation (tests/test_oracle_golden.py) instead.  Everything
- * else is pinned on the reference's own compiled code: oracle_search_projected (the self-projecting overloads, via the
- * harnesses of ref_adapter.cc), oracle_bow_score_l1 (ScoringObject.cpp) and oracle_compute_distinctive_descriptors
- * (src/MapPoint.cc compiled unmodified with its real include/MapPoint.h against shim_mp/, ref_mappoint_adapter.cc).
+ * Every function here is pinned on the reference's own compiled code: the matcher and DBoW2 sources compiled whole, the helper
+ * functions of Frame.cc / KeyFrame.cc / MapPoint.cc / Pinhole.cpp (grid, GetFeaturesInArea, IsInImage, isInFrustum, PredictScale,
+ * project, epipolarConstrain, the coarse stage of ComputeStereoMatches) from their own text cut out by line range at build time
+ * (oracle/extract_ref.py), oracle_search_projected via the harnesses of ref_adapter.cc, oracle_bow_score_l1 (ScoringObject.cpp),
+ * oracle_compute_distinctive_descriptors (src/MapPoint.cc compiled unmodified with its real include/MapPoint.h against shim_mp/).
+ * What stays unpinned is only the fp32 rounding INSIDE the un-vendored Sophus / Eigen (quaternion-form SE3 * point, 3x3 inverse):
+ * poses, epipoles and F12 are therefore inputs.
  *
  * The flat input structs are the ones of the product ABI (include/orbmatch_b200.h) so that
  * oracle and GPU consume byte-identical inputs.
@@ -73,6 +74,15 @@ void oracle_compute_distinctive_descriptors(int32_t n_mp, const int32_t *offsets
 void oracle_stereo_coarse_match(int32_t n_left, const uint8_t *desc_l, const float *kp_xy_l, const int32_t *octave_l, int32_t n_right,
                                 const uint8_t *desc_r, const float *kp_xy_r, const int32_t *octave_r, const float *scale_factors,
                                 int32_t n_rows, float mb, float mbf, int32_t *best_idx_r, int32_t *best_dist);
+
+/* Pinhole.cpp:203-218 with F12 given (row-major); Pinhole.cpp:64-71; MapPoint.cc:695-738 */
+int oracle_epipolar_constrain(const float *F12, float x1, float y1, float x2, float y2, float unc);
+void oracle_pinhole_project(const float *K, const float *xyz, float *uv);
+int oracle_predict_scale(float max_distance, float current_dist, float log_scale_factor, int n_levels);
+/* Frame.cc:676-782 (Nleft == -1) */
+void oracle_is_in_frustum(const orbgpu_frustum_host *fr, int32_t n, const float *world_pos, const float *normal,
+                          const float *min_distance, const float *max_distance, uint8_t *in_view, float *proj_xy, float *proj_xr,
+                          float *depth, int32_t *scale_level, float *view_cos);
 
 /* TemplatedVocabulary.h:1216-1258 per feature */
 void oracle_voc_transform(const orbgpu_voc_host *v, int32_t n, const uint8_t *desc, int levelsup, uint32_t *word_id,

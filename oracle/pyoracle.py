@@ -132,6 +132,42 @@ class Oracle:
                                             _p(left.scale_factors, f32p), int(n_rows), float(mb), float(mbf), _p(bi, i32p), _p(bd, i32p))
         return bi[:nl], bd[:nl]
 
+    # -- Frame::isInFrustum and its helpers
+    def is_in_frustum(self, fr, world_pos, normal, min_distance, max_distance):
+        """Frame.cc:676-782 -> dict of the MapPoint members the function writes"""
+        wp, nm = as_f32(world_pos).reshape(-1, 3), as_f32(normal).reshape(-1, 3)
+        mn, mx = as_f32(min_distance), as_f32(max_distance)
+        n = wp.shape[0]
+        out = _frustum_outputs(n)
+        from orb_slam3_comments_ghr_b200._abi import FrustumHostStruct
+        self.lib.oracle_is_in_frustum.argtypes = [C.POINTER(FrustumHostStruct), C.c_int32, f32p, f32p, f32p, f32p, u8p, f32p, f32p, f32p,
+                                                  i32p, f32p]
+        self.lib.oracle_is_in_frustum.restype = None
+        self.lib.oracle_is_in_frustum(C.byref(fr), n, _p(wp, f32p), _p(nm, f32p), _p(mn, f32p), _p(mx, f32p), _p(out["in_view"], u8p),
+                                      _p(out["proj_xy"], f32p), _p(out["proj_xr"], f32p), _p(out["depth"], f32p),
+                                      _p(out["scale_level"], i32p), _p(out["view_cos"], f32p))
+        return {k: v[:n] for k, v in out.items()}
+
+    def predict_scale(self, max_distance, current_dist, log_scale_factor, n_levels):
+        self.lib.oracle_predict_scale.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int]
+        return np.array([self.lib.oracle_predict_scale(float(a), float(b), float(log_scale_factor), int(n_levels))
+                         for a, b in zip(max_distance, current_dist)], dtype=np.int32)
+
+    def pinhole_project(self, K, xyz):
+        K, xyz = as_f32(K), as_f32(xyz).reshape(-1, 3)
+        uv = np.empty((xyz.shape[0], 2), dtype=np.float32)
+        self.lib.oracle_pinhole_project.argtypes = [f32p, f32p, f32p]
+        self.lib.oracle_pinhole_project.restype = None
+        for i in range(xyz.shape[0]):
+            self.lib.oracle_pinhole_project(_p(K, f32p), xyz[i].ctypes.data_as(f32p), uv[i].ctypes.data_as(f32p))
+        return uv
+
+    def epipolar_constrain(self, f12, kp1_xy, kp2_xy, unc):
+        f12, a, b, u = as_f32(f12).reshape(9), as_f32(kp1_xy).reshape(-1, 2), as_f32(kp2_xy).reshape(-1, 2), as_f32(unc)
+        self.lib.oracle_epipolar_constrain.argtypes = [f32p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]
+        return np.array([self.lib.oracle_epipolar_constrain(_p(f12, f32p), float(a[i, 0]), float(a[i, 1]), float(b[i, 0]), float(b[i, 1]),
+                                                            float(u[i])) for i in range(a.shape[0])], dtype=np.uint8)
+
     def compute_distinctive_descriptors(self, offsets, desc):
         off = as_i32(offsets)
         d = as_u8(desc).reshape(-1, 32)
@@ -235,6 +271,12 @@ class Oracle:
         return bi, bd, sd, mt
 
 
+def _frustum_outputs(n):
+    m = max(n, 1)
+    return {"in_view": np.zeros(m, dtype=np.uint8), "proj_xy": np.zeros((m, 2), dtype=np.float32), "proj_xr": np.zeros(m, dtype=np.float32),
+            "depth": np.zeros(m, dtype=np.float32), "scale_level": np.zeros(m, dtype=np.int32), "view_cos": np.zeros(m, dtype=np.float32)}
+
+
 class Reference:
     """The reference's own ORBmatcher.cc / DBoW2 (oracle/_ref/libref_orbmatcher*.so)."""
 
@@ -290,6 +332,77 @@ class Reference:
     def descriptor_distance(self, a, b) -> int:
         a, b = as_u8(a), as_u8(b)
         return int(self.lib.ref_descriptor_distance(_p(a, u8p), _p(b, u8p)))
+
+    # ---- the helpers whose bodies are the reference's own text cut out by oracle/extract_ref.py
+    def keyframe_features_in_area(self, f: HostFrame, x, y, r):
+        """KeyFrame::GetFeaturesInArea (KeyFrame.cc:859-907) + IsInImage (:910-913) -> (indices, in_image)"""
+        s = f.struct()
+        out = np.empty(max(f.n, 1), dtype=np.int32)
+        inimg = C.c_int32(0)
+        self.lib.ref_keyframe_features_in_area.argtypes = [C.POINTER(FrameHostStruct), C.c_float, C.c_float, C.c_float, i32p, C.POINTER(C.c_int32)]
+        n = self.lib.ref_keyframe_features_in_area(C.byref(s), float(x), float(y), float(r), _p(out, i32p), C.byref(inimg))
+        return out[:n].copy(), bool(inimg.value)
+
+    def predict_scale(self, max_distance, min_distance, current_dist, log_scale_factor, n_levels):
+        """MapPoint::PredictScale x2 + Get{Min,Max}DistanceInvariance (MapPoint.cc:665-738) -> (level_kf, level_f, min_inv, max_inv)"""
+        mx, mn, cd = as_f32(max_distance), as_f32(min_distance), as_f32(current_dist)
+        n = mx.shape[0]
+        lk, lf = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32)
+        a, b = np.empty(n, dtype=np.float32), np.empty(n, dtype=np.float32)
+        self.lib.ref_predict_scale.argtypes = [C.c_int, f32p, f32p, f32p, C.c_float, C.c_int, i32p, i32p, f32p, f32p]
+        self.lib.ref_predict_scale.restype = None
+        self.lib.ref_predict_scale(n, _p(mx, f32p), _p(mn, f32p), _p(cd, f32p), float(log_scale_factor), int(n_levels), _p(lk, i32p),
+                                   _p(lf, i32p), _p(a, f32p), _p(b, f32p))
+        return lk, lf, a, b
+
+    def pinhole_project(self, K, xyz):
+        K, xyz = as_f32(K), as_f32(xyz).reshape(-1, 3)
+        uv = np.empty((xyz.shape[0], 2), dtype=np.float32)
+        self.lib.ref_pinhole_project.argtypes = [f32p, C.c_int, f32p, f32p]
+        self.lib.ref_pinhole_project.restype = None
+        self.lib.ref_pinhole_project(_p(K, f32p), xyz.shape[0], _p(xyz, f32p), _p(uv, f32p))
+        return uv
+
+    def epipolar_constrain(self, K1, K2, R12, t12, kp1_xy, kp2_xy, unc):
+        """Pinhole::epipolarConstrain (Pinhole.cpp:189-219) -> (ok[n], the F12 it forms)"""
+        a, b, u = as_f32(kp1_xy).reshape(-1, 2), as_f32(kp2_xy).reshape(-1, 2), as_f32(unc)
+        ok = np.zeros(a.shape[0], dtype=np.uint8)
+        f12 = np.zeros(9, dtype=np.float32)
+        self.lib.ref_epipolar_constrain.argtypes = [f32p, f32p, f32p, f32p, C.c_int, f32p, f32p, f32p, u8p, f32p]
+        self.lib.ref_epipolar_constrain.restype = None
+        self.lib.ref_epipolar_constrain(_p(as_f32(K1), f32p), _p(as_f32(K2), f32p), _p(as_f32(R12).reshape(9), f32p), _p(as_f32(t12), f32p),
+                                        a.shape[0], _p(a, f32p), _p(b, f32p), _p(u, f32p), _p(ok, u8p), _p(f12, f32p))
+        return ok, f12
+
+    def is_in_frustum(self, f: HostFrame, Tcw34, K, mbf, viewing_cos_limit, world_pos, normal, min_distance, max_distance):
+        """Frame::isInFrustum (Frame.cc:676-782) on a stand-in Frame with pose Tcw -> (ret, dict of the MapPoint members written)"""
+        wp, nm = as_f32(world_pos).reshape(-1, 3), as_f32(normal).reshape(-1, 3)
+        mn, mx = as_f32(min_distance), as_f32(max_distance)
+        n = wp.shape[0]
+        out = _frustum_outputs(n)
+        ret = np.zeros(max(n, 1), dtype=np.uint8)
+        s = f.struct()
+        self.lib.ref_is_in_frustum.argtypes = [C.POINTER(FrameHostStruct), f32p, f32p, C.c_float, C.c_float, C.c_int, f32p, f32p, f32p, f32p,
+                                               u8p, f32p, f32p, f32p, i32p, f32p, u8p]
+        self.lib.ref_is_in_frustum.restype = None
+        self.lib.ref_is_in_frustum(C.byref(s), _p(as_f32(Tcw34).reshape(12), f32p), _p(as_f32(K), f32p), float(mbf), float(viewing_cos_limit), n,
+                                   _p(wp, f32p), _p(nm, f32p), _p(mn, f32p), _p(mx, f32p), _p(out["in_view"], u8p), _p(out["proj_xy"], f32p),
+                                   _p(out["proj_xr"], f32p), _p(out["depth"], f32p), _p(out["scale_level"], i32p), _p(out["view_cos"], f32p),
+                                   _p(ret, u8p))
+        return ret[:n], {k: v[:n] for k, v in out.items()}
+
+    def stereo_coarse_match(self, left: HostFrame, right: HostFrame, n_rows, mb, mbf):
+        """coarse stage of Frame::ComputeStereoMatches (Frame.cc:1117-1247), the reference's own text"""
+        nl = left.n
+        bi = np.full(max(nl, 1), -1, dtype=np.int32)
+        bd = np.full(max(nl, 1), 100, dtype=np.int32)
+        self.lib.ref_stereo_coarse_match.argtypes = [C.c_int32, u8p, f32p, i32p, C.c_int32, u8p, f32p, i32p, f32p, C.c_int32, C.c_int32,
+                                                     C.c_float, C.c_float, i32p, i32p]
+        self.lib.ref_stereo_coarse_match.restype = None
+        self.lib.ref_stereo_coarse_match(nl, _p(left.desc, u8p), _p(left.kp_xy, f32p), _p(left.octave, i32p), right.n, _p(right.desc, u8p),
+                                         _p(right.kp_xy, f32p), _p(right.octave, i32p), _p(left.scale_factors, f32p),
+                                         int(left.scale_factors.shape[0]), int(n_rows), float(mb), float(mbf), _p(bi, i32p), _p(bd, i32p))
+        return bi[:nl], bd[:nl]
 
     def compute_three_maxima(self, sizes):
         sizes = as_i32(sizes)

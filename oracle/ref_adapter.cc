@@ -73,7 +73,6 @@ namespace
         s.mfGridElementWidthInv = h->grid_inv_w;
         s.mfGridElementHeightInv = h->grid_inv_h;
         s.mvpMapPoints.assign(h->n, nullptr);
-        s.AssignFeaturesToGrid(h->min_x, h->min_y);
         s.mFeatVec.clear();
         for (int a = 0; a < h->fv_n_nodes; a++)
             for (int j = h->fv_offsets[a]; j < h->fv_offsets[a + 1]; j++)
@@ -84,11 +83,17 @@ namespace
         fill_feature_set(F, h);
         F.mnMinX = h->min_x; F.mnMinY = h->min_y; F.mnMaxX = h->max_x; F.mnMaxY = h->max_y;
         F.mvbOutlier.assign(h->n, false);
+        F.AssignFeaturesToGrid(); // the reference's own Frame.cc:469-507 / :973-989 (oracle/_ref/gen/ref_extracted.cc)
     }
     void fill_keyframe(KeyFrame &K, const orbgpu_frame_host *h)
     {
         fill_feature_set(K, h);
-        K.mnMinX = (int)h->min_x; K.mnMinY = (int)h->min_y; K.mnMaxX = (int)h->max_x; K.mnMaxY = (int)h->max_y;
+        Frame F; // a key frame takes the grid of the frame it is made from (KeyFrame.cc:66-82)
+        F.N = K.N; F.mvKeysUn = K.mvKeysUn;
+        F.mfGridElementWidthInv = K.mfGridElementWidthInv; F.mfGridElementHeightInv = K.mfGridElementHeightInv;
+        F.mnMinX = h->min_x; F.mnMinY = h->min_y; F.mnMaxX = h->max_x; F.mnMaxY = h->max_y;
+        F.AssignFeaturesToGrid();
+        K.CopyGridFrom(F);
     }
 
     struct ExposedMatcher : public ORBmatcher
@@ -130,7 +135,7 @@ extern "C"
         ind[0] = a; ind[1] = b; ind[2] = c;
     }
 
-    // Frame::GetFeaturesInArea as restated in the stub (a second, independent restatement)
+    // Frame::GetFeaturesInArea / AssignFeaturesToGrid / PosInGrid: the reference's own text (Frame.cc:868-962, 469-507, 973-989)
     int ref_features_in_area(const orbgpu_frame_host *f, float x, float y, float r, int min_level, int max_level,
                              int32_t *out_idx)
     {
@@ -153,6 +158,145 @@ extern "C"
                 for (size_t j = 0; j < F.mGrid[ix][iy].size(); j++) cell_items[acc++] = (int32_t)F.mGrid[ix][iy][j];
             }
         cell_start[FRAME_GRID_COLS * FRAME_GRID_ROWS] = acc;
+    }
+
+    // KeyFrame::GetFeaturesInArea (KeyFrame.cc:859-907) + IsInImage (:910-913), the reference's own text; bounds as the KeyFrame
+    // holds them (ints).  in_image [1] out.
+    int ref_keyframe_features_in_area(const orbgpu_frame_host *f, float x, float y, float r, int32_t *out_idx, int32_t *in_image)
+    {
+        KeyFrame K;
+        fill_keyframe(K, f);
+        std::vector<size_t> v = K.GetFeaturesInArea(x, y, r);
+        for (size_t i = 0; i < v.size(); i++) out_idx[i] = (int32_t)v[i];
+        if (in_image) *in_image = K.IsInImage(x, y) ? 1 : 0;
+        return (int)v.size();
+    }
+
+    // MapPoint::PredictScale (MapPoint.cc:695-738, both overloads) and Get{Min,Max}DistanceInvariance (:665-678)
+    void ref_predict_scale(int n, const float *max_distance, const float *min_distance, const float *current_dist, float log_scale_factor,
+                           int n_levels, int32_t *level_kf, int32_t *level_f, float *min_inv, float *max_inv)
+    {
+        KeyFrame K;
+        Frame F;
+        K.mfLogScaleFactor = F.mfLogScaleFactor = log_scale_factor;
+        K.mnScaleLevels = F.mnScaleLevels = n_levels;
+        for (int i = 0; i < n; i++)
+        {
+            MapPoint mp;
+            mp.mfMaxDistance = max_distance[i];
+            mp.mfMinDistance = min_distance[i];
+            level_kf[i] = mp.PredictScale(current_dist[i], &K);
+            level_f[i] = mp.PredictScale(current_dist[i], &F);
+            min_inv[i] = mp.GetMinDistanceInvariance();
+            max_inv[i] = mp.GetMaxDistanceInvariance();
+        }
+    }
+
+    // Pinhole::project (Pinhole.cpp:64-71) and Pinhole::epipolarConstrain (:189-219) with the camera pair (K1, K2 = fx fy cx cy)
+    void ref_pinhole_project(const float *K, int n, const float *xyz, float *uv)
+    {
+        Pinhole cam(K[0], K[1], K[2], K[3]);
+        for (int i = 0; i < n; i++)
+        {
+            const Eigen::Vector2f p = cam.project(Eigen::Vector3f(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+            uv[2 * i] = p(0);
+            uv[2 * i + 1] = p(1);
+        }
+    }
+    void ref_epipolar_constrain(const float *K1, const float *K2, const float *R12, const float *t12, int n, const float *kp1_xy,
+                                const float *kp2_xy, const float *unc, uint8_t *ok, float *f12_out)
+    {
+        Pinhole c1(K1[0], K1[1], K1[2], K1[3]), c2(K2[0], K2[1], K2[2], K2[3]);
+        Eigen::Matrix3f R;
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) R(r, c) = R12[3 * r + c];
+        const Eigen::Vector3f t(t12[0], t12[1], t12[2]);
+        for (int i = 0; i < n; i++)
+        {
+            cv::KeyPoint a, b;
+            a.pt.x = kp1_xy[2 * i]; a.pt.y = kp1_xy[2 * i + 1];
+            b.pt.x = kp2_xy[2 * i]; b.pt.y = kp2_xy[2 * i + 1];
+            ok[i] = c1.epipolarConstrain(&c2, a, b, R, t, 1.f, unc[i]) ? 1 : 0;
+        }
+        if (f12_out) // the F12 the function forms (Pinhole.cpp:194-197), for callers that feed it to the flat-input oracle / the GPU
+        {
+            const Eigen::Matrix3f F = c1.fundamental(&c2, R, t);
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) f12_out[3 * r + c] = F(r, c);
+        }
+    }
+
+    // Frame::isInFrustum (Frame.cc:676-782, Nleft == -1 path): the reference's own text on a frame with pose Tcw (row-major 3x4),
+    // pinhole K, image bounds of the frame.  Outputs = the members the function writes into each MapPoint.
+    void ref_is_in_frustum(const orbgpu_frame_host *f, const float *Tcw34, const float *K, float mbf, float viewing_cos_limit, int n,
+                           const float *world_pos, const float *normal, const float *min_distance, const float *max_distance,
+                           uint8_t *in_view, float *proj_xy, float *proj_xr, float *depth, int32_t *scale_level, float *view_cos, uint8_t *ret)
+    {
+        Frame F;
+        fill_frame(F, f);
+        Eigen::Matrix3f R;
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) R(r, c) = Tcw34[4 * r + c];
+        F.SetPose(Sophus::SE3f(R, Eigen::Vector3f(Tcw34[3], Tcw34[7], Tcw34[11])));
+        Pinhole cam(K[0], K[1], K[2], K[3]);
+        F.mpCamera = &cam;
+        F.mbf = mbf;
+        for (int i = 0; i < n; i++)
+        {
+            MapPoint mp;
+            mp.worldPos_ = Eigen::Vector3f(world_pos[3 * i], world_pos[3 * i + 1], world_pos[3 * i + 2]);
+            mp.normal_ = Eigen::Vector3f(normal[3 * i], normal[3 * i + 1], normal[3 * i + 2]);
+            mp.mfMinDistance = min_distance[i];
+            mp.mfMaxDistance = max_distance[i];
+            ret[i] = F.isInFrustum(&mp, viewing_cos_limit) ? 1 : 0;
+            in_view[i] = mp.mbTrackInView ? 1 : 0;
+            proj_xy[2 * i] = mp.mTrackProjX;
+            proj_xy[2 * i + 1] = mp.mTrackProjY;
+            proj_xr[i] = mp.mTrackProjXR;
+            depth[i] = mp.mTrackDepth;
+            scale_level[i] = mp.mnTrackScaleLevel;
+            view_cos[i] = mp.mTrackViewCos;
+        }
+    }
+
+    // coarse stage of Frame::ComputeStereoMatches (Frame.cc:1117-1247): the reference's own text up to the SAD refinement
+    void ref_stereo_coarse_match(int32_t n_left, const uint8_t *desc_l, const float *kp_xy_l, const int32_t *octave_l, int32_t n_right,
+                                 const uint8_t *desc_r, const float *kp_xy_r, const int32_t *octave_r, const float *scale_factors,
+                                 int32_t n_levels, int32_t n_rows, float mb, float mbf, int32_t *best_idx_r, int32_t *best_dist)
+    {
+        Frame F;
+        F.N = n_left;
+        F.mvKeys.resize(n_left);
+        for (int i = 0; i < n_left; i++)
+        {
+            F.mvKeys[i].pt.x = kp_xy_l[2 * i]; F.mvKeys[i].pt.y = kp_xy_l[2 * i + 1]; F.mvKeys[i].octave = octave_l[i];
+        }
+        F.mvKeysRight.resize(n_right);
+        for (int i = 0; i < n_right; i++)
+        {
+            F.mvKeysRight[i].pt.x = kp_xy_r[2 * i]; F.mvKeysRight[i].pt.y = kp_xy_r[2 * i + 1]; F.mvKeysRight[i].octave = octave_r[i];
+        }
+        F.mDescriptors.create(n_left > 0 ? n_left : 1, 32, CV_8U);
+        if (n_left > 0) std::memcpy(F.mDescriptors.data, desc_l, (size_t)n_left * 32);
+        F.mDescriptorsRight.create(n_right > 0 ? n_right : 1, 32, CV_8U);
+        if (n_right > 0) std::memcpy(F.mDescriptorsRight.data, desc_r, (size_t)n_right * 32);
+        F.mvScaleFactors.assign(scale_factors, scale_factors + n_levels);
+        F.mvInvScaleFactors.resize(n_levels);
+        for (int i = 0; i < n_levels; i++) F.mvInvScaleFactors[i] = 1.0f / scale_factors[i];
+        F.mb = mb;
+        F.mbf = mbf;
+        ORBextractorStub ex;
+        ex.mvImagePyramid.resize(1);
+        ex.mvImagePyramid[0].rows = n_rows;
+        F.mpORBextractorLeft = F.mpORBextractorRight = &ex;
+        F.stereo_best_idx_.assign(n_left > 0 ? n_left : 1, -1);
+        F.stereo_best_dist_.assign(n_left > 0 ? n_left : 1, ORBmatcher::TH_HIGH);
+        F.ComputeStereoMatches();
+        for (int i = 0; i < n_left; i++)
+        {
+            best_idx_r[i] = F.stereo_best_idx_[i];
+            best_dist[i] = F.stereo_best_dist_[i];
+        }
     }
 
     int ref_search_for_initialization(const orbgpu_frame_host *f1, const orbgpu_frame_host *f2, float *prev_matched_xy,

@@ -4,20 +4,24 @@
 // UNMODIFIED into oracle/_ref/libref_orbmatcher.so (oracle/Makefile).  The real headers
 // pull in OpenCV/Eigen/Sophus/Boost/g2o/Pangolin, none of which exist in this image.
 //
-// The few helper functions ORBmatcher.cc calls INTO these classes are restated here,
-// citing the reference lines they follow:
-//   Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea   src/Frame.cc:469-507, 973-989, 868-962
-//   KeyFrame::GetFeaturesInArea / IsInImage                       src/KeyFrame.cc:859-913
-//   MapPoint::PredictScale / Get{Min,Max}DistanceInvariance       src/MapPoint.cc:665-738
-//   Pinhole::project / epipolarConstrain / toK_                   src/CameraModels/Pinhole.cpp:64-71, 171-219
-// Nothing here is product code.
+// The helper functions ORBmatcher.cc calls INTO these classes are only DECLARED here.  Their bodies are the reference's own
+// text, cut out of /root/reference by line range at build time (oracle/extract_ref.py -> oracle/_ref/gen/ref_extracted.cc):
+//   Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea / isInFrustum   src/Frame.cc:469-507, 973-989, 868-962, 676-782
+//   Frame::ComputeStereoMatches, coarse stage                                  src/Frame.cc:1117-1247
+//   KeyFrame::GetFeaturesInArea / IsInImage                                    src/KeyFrame.cc:859-913
+//   MapPoint::PredictScale x2 / Get{Min,Max}DistanceInvariance                 src/MapPoint.cc:665-738
+//   Pinhole::project / toK_ / epipolarConstrain                                src/CameraModels/Pinhole.cpp:64-71, 171-176, 189-219
+// What IS written here: data members, trivial accessors, and the grid copy of the KeyFrame constructor (KeyFrame.cc:66-82, a
+// member-wise copy).  Nothing here is product code.
 #ifndef ORB_ORACLE_SHIM_ORBSLAM_STUBS_H
 #define ORB_ORACLE_SHIM_ORBSLAM_STUBS_H
 
 #include <cassert>
 #include <cmath>
 #include <map>
+#include <mutex>
 #include <set>
+#include <stdexcept>
 #include <tuple>
 #include <vector>
 
@@ -53,47 +57,17 @@ namespace ORB_SLAM3
     public:
         float mvParameters[4]; // fx fy cx cy
         Pinhole(float fx, float fy, float cx, float cy) : mvParameters{fx, fy, cx, cy} {}
-        // Pinhole.cpp:64-71
-        Eigen::Vector2f project(const Eigen::Vector3f &v3D) override
-        {
-            Eigen::Vector2f res;
-            res[0] = mvParameters[0] * v3D[0] / v3D[2] + mvParameters[2];
-            res[1] = mvParameters[1] * v3D[1] / v3D[2] + mvParameters[3];
-            return res;
-        }
-        // Pinhole.cpp:171-176
-        Eigen::Matrix3f toK_() override
-        {
-            Eigen::Matrix3f K;
-            K(0, 0) = mvParameters[0]; K(0, 2) = mvParameters[2];
-            K(1, 1) = mvParameters[1]; K(1, 2) = mvParameters[3];
-            K(2, 2) = 1.f;
-            return K;
-        }
-        // Pinhole.cpp:194-197
+        Eigen::Vector2f project(const Eigen::Vector3f &v3D) override; // Pinhole.cpp:64-71 (extracted)
+        Eigen::Matrix3f toK_() override;                              // Pinhole.cpp:171-176 (extracted)
+        bool epipolarConstrain(GeometricCamera *pCamera2, const cv::KeyPoint &kp1, const cv::KeyPoint &kp2, const Eigen::Matrix3f &R12,
+                               const Eigen::Vector3f &t12, const float sigmaLevel, const float unc) override; // :189-219 (extracted)
+        // harness helper (NOT reference text): F12 as Pinhole.cpp:194-197 forms it, for the entry points that take F12 as an input
         Eigen::Matrix3f fundamental(GeometricCamera *pCamera2, const Eigen::Matrix3f &R12, const Eigen::Vector3f &t12)
         {
             Eigen::Matrix3f t12x = Sophus::SO3f::hat(t12);
             Eigen::Matrix3f K1 = this->toK_();
             Eigen::Matrix3f K2 = pCamera2->toK_();
             return K1.transpose().inverse() * t12x * R12 * K2.inverse();
-        }
-        // Pinhole.cpp:189-219
-        bool epipolarConstrain(GeometricCamera *pCamera2, const cv::KeyPoint &kp1, const cv::KeyPoint &kp2,
-                               const Eigen::Matrix3f &R12, const Eigen::Vector3f &t12, const float sigmaLevel,
-                               const float unc) override
-        {
-            (void)sigmaLevel;
-            Eigen::Matrix3f F12 = fundamental(pCamera2, R12, t12);
-            const float a = kp1.pt.x * F12(0, 0) + kp1.pt.y * F12(1, 0) + F12(2, 0);
-            const float b = kp1.pt.x * F12(0, 1) + kp1.pt.y * F12(1, 1) + F12(2, 1);
-            const float c = kp1.pt.x * F12(0, 2) + kp1.pt.y * F12(1, 2) + F12(2, 2);
-            const float num = a * kp2.pt.x + b * kp2.pt.y + c;
-            const float den = a * a + b * b;
-            if (den == 0)
-                return false;
-            const float dsqr = num * num / den;
-            return dsqr < 3.84 * unc;
         }
     };
 
@@ -104,6 +78,14 @@ namespace ORB_SLAM3
         static thread_local std::vector<std::pair<MapPoint *, MapPoint *>> log;
         return log;
     }
+
+    // the stand-in map points are copied around by the harnesses; a copy gets a fresh (unlocked) mutex
+    struct CopyableMutex : public std::mutex
+    {
+        CopyableMutex() {}
+        CopyableMutex(const CopyableMutex &) {}
+        CopyableMutex &operator=(const CopyableMutex &) { return *this; }
+    };
 
     class MapPoint
     {
@@ -121,6 +103,7 @@ namespace ORB_SLAM3
         cv::Mat descriptor_;
         Eigen::Vector3f worldPos_, normal_;
         float mfMinDistance = 0, mfMaxDistance = 0;
+        CopyableMutex mMutexPos; // taken by the extracted bodies (MapPoint.cc:667, :698)
         std::map<KeyFrame *, std::tuple<int, int>> observations_;
 
         bool isBad() { return bad_; }
@@ -128,10 +111,10 @@ namespace ORB_SLAM3
         cv::Mat GetDescriptor() { return descriptor_.clone(); } // MapPoint.cc:540-544
         Eigen::Vector3f GetWorldPos() { return worldPos_; }
         Eigen::Vector3f GetNormal() { return normal_; }
-        float GetMinDistanceInvariance() { return 0.8f * mfMinDistance; } // MapPoint.cc:665-669
-        float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; } // MapPoint.cc:674-678
-        int PredictScale(const float &currentDist, KeyFrame *pKF);        // MapPoint.cc:695-713
-        int PredictScale(const float &currentDist, Frame *pF);            // MapPoint.cc:722-738
+        float GetMinDistanceInvariance();                          // MapPoint.cc:665-669 (extracted)
+        float GetMaxDistanceInvariance();                          // MapPoint.cc:674-678 (extracted)
+        int PredictScale(const float &currentDist, KeyFrame *pKF); // MapPoint.cc:695-713 (extracted)
+        int PredictScale(const float &currentDist, Frame *pF);     // MapPoint.cc:722-738 (extracted)
         void Replace(MapPoint *pMP) { g_replace_log().push_back(std::make_pair(this, pMP)); }
         void AddObservation(KeyFrame *pKF, int idx) { observations_[pKF] = std::make_tuple(idx, -1); nObs_++; }
         bool IsInKeyFrame(KeyFrame *pKF) { return observations_.count(pKF) > 0; }
@@ -158,32 +141,23 @@ namespace ORB_SLAM3
         float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
         GeometricCamera *mpCamera = nullptr, *mpCamera2 = nullptr;
         float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0, mb = 0;
+        std::vector<float> mvInvScaleFactors;
         std::vector<MapPoint *> mvpMapPoints;
         std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
         std::vector<std::size_t> mGridRight[FRAME_GRID_COLS][FRAME_GRID_ROWS];
         Sophus::SE3f mTcw;
-
-        // Frame.cc:973-989
-        bool PosInGrid(const cv::KeyPoint &kp, int &posX, int &posY, float minX, float minY)
-        {
-            posX = round((kp.pt.x - minX) * mfGridElementWidthInv);
-            posY = round((kp.pt.y - minY) * mfGridElementHeightInv);
-            if (posX < 0 || posX >= FRAME_GRID_COLS || posY < 0 || posY >= FRAME_GRID_ROWS)
-                return false;
-            return true;
-        }
-        // Frame.cc:469-507
-        void AssignFeaturesToGrid(float minX, float minY)
-        {
-            for (int i = 0; i < N; i++)
-            {
-                const cv::KeyPoint &kp = mvKeysUn[i];
-                int nGridPosX, nGridPosY;
-                if (PosInGrid(kp, nGridPosX, nGridPosY, minX, minY))
-                    mGrid[nGridPosX][nGridPosY].push_back(i);
-            }
-        }
     };
+
+    // what Frame::ComputeStereoMatches reads of the ORB extractors: the size of the pyramid's base image (Frame.cc:1143)
+    struct ImageSizeStub { int rows = 0, cols = 0; };
+    struct ORBextractorStub { std::vector<ImageSizeStub> mvImagePyramid; };
+    // closes the extracted coarse stage of ComputeStereoMatches (oracle/extract_ref.py): bestIdxR is accepted iff bestDist <
+    // thOrbDist (Frame.cc:1248); a left key point that `continue`s earlier keeps the defaults (-1, TH_HIGH)
+#define ORB_ORACLE_STEREO_COARSE_HOOK(iL, bestDist, bestIdxR, thOrbDist) \
+    do {                                                                   \
+        stereo_best_dist_[iL] = (bestDist);                                \
+        stereo_best_idx_[iL] = (bestDist) < (thOrbDist) ? (int)(bestIdxR) : -1; \
+    } while (0)
 
     class Frame : public FeatureSet
     {
@@ -193,58 +167,33 @@ namespace ORB_SLAM3
         std::vector<bool> mvbOutlier;
         std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;
         Sophus::SE3f mTrl;
+        // pose pieces Frame::isInFrustum reads (Frame.h: mRcw, mtcw, mOw), kept in step with mTcw by SetPose
+        Eigen::Matrix3f mRcw;
+        Eigen::Vector3f mtcw, mOw;
+        // stereo members of ComputeStereoMatches
+        std::vector<float> mvDepth;
+        cv::Mat mDescriptorsRight;
+        ORBextractorStub *mpORBextractorLeft = nullptr, *mpORBextractorRight = nullptr;
+        std::vector<int> stereo_best_idx_, stereo_best_dist_; // filled by ORB_ORACLE_STEREO_COARSE_HOOK
 
         Sophus::SE3f GetPose() const { return mTcw; }
         Sophus::SE3f GetRelativePoseTrl() { return mTrl; }
-
-        // Frame.cc:868-962
-        vector<size_t> GetFeaturesInArea(const float &x, const float &y, const float &r, const int minLevel = -1,
-                                         const int maxLevel = -1, const bool bRight = false) const
+        void SetPose(const Sophus::SE3f &Tcw) // Frame::SetPose + UpdatePoseMatrices (Frame.cc:600-660): member-wise
         {
-            vector<size_t> vIndices;
-            vIndices.reserve(N);
-            float factorX = r;
-            float factorY = r;
-            const int nMinCellX = max(0, (int)floor((x - mnMinX - factorX) * mfGridElementWidthInv));
-            if (nMinCellX >= FRAME_GRID_COLS)
-                return vIndices;
-            const int nMaxCellX = min((int)FRAME_GRID_COLS - 1, (int)ceil((x - mnMinX + factorX) * mfGridElementWidthInv));
-            if (nMaxCellX < 0)
-                return vIndices;
-            const int nMinCellY = max(0, (int)floor((y - mnMinY - factorY) * mfGridElementHeightInv));
-            if (nMinCellY >= FRAME_GRID_ROWS)
-                return vIndices;
-            const int nMaxCellY = min((int)FRAME_GRID_ROWS - 1, (int)ceil((y - mnMinY + factorY) * mfGridElementHeightInv));
-            if (nMaxCellY < 0)
-                return vIndices;
-            const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
-            for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
-            {
-                for (int iy = nMinCellY; iy <= nMaxCellY; iy++)
-                {
-                    const vector<size_t> &vCell = (!bRight) ? mGrid[ix][iy] : mGridRight[ix][iy];
-                    if (vCell.empty())
-                        continue;
-                    for (size_t j = 0, jend = vCell.size(); j < jend; j++)
-                    {
-                        const cv::KeyPoint &kpUn = mvKeysUn[vCell[j]];
-                        if (bCheckLevels)
-                        {
-                            if (kpUn.octave < minLevel)
-                                continue;
-                            if (maxLevel >= 0)
-                                if (kpUn.octave > maxLevel)
-                                    continue;
-                        }
-                        const float distx = kpUn.pt.x - x;
-                        const float disty = kpUn.pt.y - y;
-                        if (fabs(distx) < factorX && fabs(disty) < factorY)
-                            vIndices.push_back(vCell[j]);
-                    }
-                }
-            }
-            return vIndices;
+            mTcw = Tcw;
+            Sophus::SE3f Twc = mTcw.inverse();
+            mOw = Twc.translation();
+            mRcw = mTcw.rotationMatrix();
+            mtcw = mTcw.translation();
         }
+
+        void AssignFeaturesToGrid();                                    // Frame.cc:469-507 (extracted)
+        bool PosInGrid(const cv::KeyPoint &kp, int &posX, int &posY);   // Frame.cc:973-989 (extracted)
+        vector<size_t> GetFeaturesInArea(const float &x, const float &y, const float &r, const int minLevel = -1, const int maxLevel = -1,
+                                         const bool bRight = false) const; // Frame.cc:868-962 (extracted)
+        bool isInFrustum(MapPoint *pMP, float viewingCosLimit);         // Frame.cc:676-782 (extracted)
+        bool isInFrustumChecks(MapPoint *, float, bool = false) { throw std::logic_error("stereo-fisheye path (Nleft != -1) is out of scope"); }
+        void ComputeStereoMatches();                                    // Frame.cc:1117-1247, coarse stage (extracted + hook)
     };
 
     class KeyFrame : public FeatureSet
@@ -273,69 +222,17 @@ namespace ORB_SLAM3
         Sophus::SE3f GetRightPoseInverse() { return (mTrl * mTcw).inverse(); }
         Eigen::Vector3f GetRightCameraCenter() { return (mTrl * mTcw).inverse().translation(); }
 
-        // KeyFrame.cc:910-913
-        bool IsInImage(const float &x, const float &y) const { return (x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY); }
-
-        // KeyFrame.cc:859-907
-        vector<size_t> GetFeaturesInArea(const float &x, const float &y, const float &r, const bool bRight = false) const
+        bool IsInImage(const float &x, const float &y) const; // KeyFrame.cc:910-913 (extracted)
+        vector<size_t> GetFeaturesInArea(const float &x, const float &y, const float &r, const bool bRight = false) const; // :859-907 (extracted)
+        // grid of a key frame = the grid of the Frame it was made from (KeyFrame.cc:66-82: mGrid[i][j] = F.mGrid[i][j]); the bounds
+        // become ints (KeyFrame.h:403-406 `const int mnMinX` initialised from the Frame's floats)
+        void CopyGridFrom(const Frame &F)
         {
-            vector<size_t> vIndices;
-            vIndices.reserve(N);
-            float factorX = r;
-            float factorY = r;
-            const int nMinCellX = max(0, (int)floor((x - mnMinX - factorX) * mfGridElementWidthInv));
-            if (nMinCellX >= mnGridCols)
-                return vIndices;
-            const int nMaxCellX = min((int)mnGridCols - 1, (int)ceil((x - mnMinX + factorX) * mfGridElementWidthInv));
-            if (nMaxCellX < 0)
-                return vIndices;
-            const int nMinCellY = max(0, (int)floor((y - mnMinY - factorY) * mfGridElementHeightInv));
-            if (nMinCellY >= mnGridRows)
-                return vIndices;
-            const int nMaxCellY = min((int)mnGridRows - 1, (int)ceil((y - mnMinY + factorY) * mfGridElementHeightInv));
-            if (nMaxCellY < 0)
-                return vIndices;
-            for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
-            {
-                for (int iy = nMinCellY; iy <= nMaxCellY; iy++)
-                {
-                    const vector<size_t> &vCell = (!bRight) ? mGrid[ix][iy] : mGridRight[ix][iy];
-                    for (size_t j = 0, jend = vCell.size(); j < jend; j++)
-                    {
-                        const cv::KeyPoint &kpUn = mvKeysUn[vCell[j]];
-                        const float distx = kpUn.pt.x - x;
-                        const float disty = kpUn.pt.y - y;
-                        if (fabs(distx) < r && fabs(disty) < r)
-                            vIndices.push_back(vCell[j]);
-                    }
-                }
-            }
-            return vIndices;
+            mnMinX = F.mnMinX; mnMinY = F.mnMinY; mnMaxX = F.mnMaxX; mnMaxY = F.mnMaxY;
+            for (int i = 0; i < mnGridCols; i++)
+                for (int j = 0; j < mnGridRows; j++) mGrid[i][j] = F.mGrid[i][j];
         }
     };
-
-    // MapPoint.cc:695-713
-    inline int MapPoint::PredictScale(const float &currentDist, KeyFrame *pKF)
-    {
-        float ratio = mfMaxDistance / currentDist;
-        int nScale = ceil(log(ratio) / pKF->mfLogScaleFactor);
-        if (nScale < 0)
-            nScale = 0;
-        else if (nScale >= pKF->mnScaleLevels)
-            nScale = pKF->mnScaleLevels - 1;
-        return nScale;
-    }
-    // MapPoint.cc:722-738
-    inline int MapPoint::PredictScale(const float &currentDist, Frame *pF)
-    {
-        float ratio = mfMaxDistance / currentDist;
-        int nScale = ceil(log(ratio) / pF->mfLogScaleFactor);
-        if (nScale < 0)
-            nScale = 0;
-        else if (nScale >= pF->mnScaleLevels)
-            nScale = pF->mnScaleLevels - 1;
-        return nScale;
-    }
 } // namespace ORB_SLAM3
 
 #endif

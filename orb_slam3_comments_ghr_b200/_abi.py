@@ -109,6 +109,60 @@ class ProjPointsHostStruct(C.Structure):
     ]
 
 
+class FrustumHostStruct(C.Structure):
+    """orbgpu_frustum_host: the Frame members Frame::isInFrustum reads (Frame.cc:676-782)"""
+    _fields_ = [
+        ("Rcw", C.c_float * 9), ("tcw", C.c_float * 3), ("Ow", C.c_float * 3), ("K", C.c_float * 4), ("mbf", C.c_float),
+        ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float),
+        ("viewing_cos_limit", C.c_float), ("log_scale_factor", C.c_float), ("n_levels", C.c_int32),
+    ]
+
+
+def frustum_struct(Rcw, tcw, Ow, K, mbf, bounds, viewing_cos_limit, log_scale_factor, n_levels) -> FrustumHostStruct:
+    f = FrustumHostStruct()
+    f.Rcw[:] = [float(x) for x in np.asarray(Rcw, dtype=np.float32).reshape(9)]
+    f.tcw[:] = [float(x) for x in np.asarray(tcw, dtype=np.float32).reshape(3)]
+    f.Ow[:] = [float(x) for x in np.asarray(Ow, dtype=np.float32).reshape(3)]
+    f.K[:] = [float(x) for x in np.asarray(K, dtype=np.float32).reshape(4)]
+    f.mbf = float(mbf)
+    f.min_x, f.min_y, f.max_x, f.max_y = [float(x) for x in bounds]
+    f.viewing_cos_limit, f.log_scale_factor, f.n_levels = float(viewing_cos_limit), float(log_scale_factor), int(n_levels)
+    return f
+
+
+class LocalPointsHostStruct(C.Structure):
+    """orbgpu_localpoints_host: the map points of Tracking::SearchLocalPoints"""
+    _fields_ = [("n", C.c_int32), ("desc", u8p), ("world_pos", f32p), ("normal", f32p), ("min_distance", f32p), ("max_distance", f32p),
+                ("skip", u8p), ("bad", u8p), ("n_obs", i32p)]
+
+
+@dataclass
+class HostLocalPoints:
+    desc: np.ndarray
+    world_pos: np.ndarray
+    normal: np.ndarray
+    min_distance: np.ndarray
+    max_distance: np.ndarray
+    bad: np.ndarray
+    n_obs: np.ndarray
+    skip: Optional[np.ndarray] = None
+
+    @property
+    def n(self) -> int:
+        return int(self.desc.shape[0])
+
+    def struct(self) -> LocalPointsHostStruct:
+        self.desc, self.bad = as_u8(self.desc), as_u8(self.bad)
+        self.world_pos, self.normal = as_f32(self.world_pos), as_f32(self.normal)
+        self.min_distance, self.max_distance = as_f32(self.min_distance), as_f32(self.max_distance)
+        self.n_obs = as_i32(self.n_obs)
+        if self.skip is not None:
+            self.skip = as_u8(self.skip)
+        return LocalPointsHostStruct(self.n, _ptr(self.desc, u8p), _ptr(self.world_pos, f32p), _ptr(self.normal, f32p),
+                                     _ptr(self.min_distance, f32p), _ptr(self.max_distance, f32p), _ptr(self.skip, u8p),
+                                     _ptr(self.bad, u8p), _ptr(self.n_obs, i32p))
+
+
 class ProjSearchParamsStruct(C.Structure):
     _fields_ = [
         ("max_dist", C.c_float),

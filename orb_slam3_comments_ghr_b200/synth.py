@@ -575,3 +575,88 @@ def make_knn_case(seed: int, nq: int, nd: int, planted_frac: float = 0.1) -> Knn
     db[b] = db[a]
     # re-plant after duplication so that planted rows still exist; ties on duplicates are intended
     return KnnCase(q, db)
+
+
+# ---------------------------------------------------------------- 8(f) rank 1: Frame::isInFrustum / Tracking::SearchLocalPoints
+@dataclass
+class FrustumCase:
+    frame: HostFrame
+    Tcw34: np.ndarray       # [3][4] row-major pose of the frame (the stand-in Sophus of the oracle build decomposes it)
+    Rcw: np.ndarray
+    tcw: np.ndarray
+    Ow: np.ndarray          # -Rcw^T tcw evaluated in fp32 exactly as the stand-in SE3f::inverse() does
+    K: np.ndarray
+    mbf: float
+    viewing_cos_limit: float
+    log_scale_factor: float
+    world_pos: np.ndarray
+    normal: np.ndarray
+    min_distance: np.ndarray
+    max_distance: np.ndarray
+    desc: np.ndarray
+    bad: np.ndarray
+    n_obs: np.ndarray
+    skip: np.ndarray
+    kp_prior_obs: np.ndarray
+    kp_mp: np.ndarray
+    nnratio: float = 0.8
+
+
+def _f32_matvec_t(R, t):
+    """-(R^T t) in fp32, left to right, as the oracle build's matrix-form SE3f::inverse() evaluates it"""
+    Rt = R.T.astype(np.float32)
+    out = np.empty(3, dtype=np.float32)
+    for r in range(3):
+        acc = np.float32(Rt[r, 0] * t[0])
+        acc = np.float32(acc + np.float32(Rt[r, 1] * t[1]))
+        acc = np.float32(acc + np.float32(Rt[r, 2] * t[2]))
+        out[r] = -acc
+    return out
+
+
+def make_frustum_case(seed: int, n_kp: int = 2000, n_mp: int = 5000, planted_frac: float = 0.35) -> FrustumCase:
+    """Local map points around a camera: a third project onto keypoints of the frame (planted descriptors, distance chosen so that
+    PredictScale lands on the keypoint's octave), the rest are spread in front of, behind and beside the camera so that every gate of
+    Frame::isInFrustum (depth sign, image bounds, distance invariance, viewing cosine) rejects some of them.  Points exactly on the
+    image border and on the distance limits are included."""
+    rng = np.random.default_rng(seed)
+    frame = make_frame(rng, n_kp)
+    sf = frame.scale_factors
+    R = _small_rotation(rng, 1)[0].astype(np.float32)
+    t = rng.normal(0, 0.3, 3).astype(np.float32)
+    Ow = _f32_matvec_t(R, t)
+    K = np.array([FX, FY, CX, CY], dtype=np.float32)
+    # random points in camera coordinates -> world
+    Pc = np.stack([rng.uniform(-6, 6, n_mp), rng.uniform(-5, 5, n_mp), rng.uniform(-2, 14, n_mp)], axis=1)
+    n_pl = int(planted_frac * n_mp)
+    kp = rng.integers(0, n_kp, n_pl)
+    z = rng.uniform(1.5, 12.0, n_pl)
+    u = frame.kp_xy[kp, 0] + rng.normal(0, 1.0, n_pl)
+    v = frame.kp_xy[kp, 1] + rng.normal(0, 1.0, n_pl)
+    Pc[:n_pl] = np.stack([(u - CX) * z / FX, (v - CY) * z / FY, z], axis=1)
+    Pw = (Pc - t.astype(np.float64)) @ R.astype(np.float64)  # R^T (Pc - t)
+    world = Pw.astype(np.float32)
+    dist = np.linalg.norm(world.astype(np.float64) - Ow.astype(np.float64), axis=1)
+    # distance limits: the planted points get max_distance = dist * sf[octave] (so PredictScale = octave); others random
+    lvl = rng.integers(0, 8, n_mp)
+    lvl[:n_pl] = frame.octave[kp]
+    max_d = (dist * sf[lvl] * rng.uniform(0.98, 1.02, n_mp)).astype(np.float32)
+    min_d = (max_d / (1.2 ** 7) * rng.uniform(0.5, 1.4, n_mp)).astype(np.float32)
+    far = rng.random(n_mp) < 0.1
+    max_d[far] = (dist[far] * rng.uniform(0.5, 0.9, far.sum())).astype(np.float32)  # beyond 1.2 x max for some of these
+    normal = (world.astype(np.float64) - Ow.astype(np.float64)) / np.maximum(dist, 1e-6)[:, None]
+    normal += rng.normal(0, 0.5, (n_mp, 3))  # some viewing angles beyond the limit
+    normal /= np.linalg.norm(normal, axis=1)[:, None]
+    desc = random_descriptors(rng, n_mp)
+    desc[:n_pl] = planted_copies(rng, frame.desc[kp])
+    bad = (rng.random(n_mp) < 0.03).astype(np.uint8)
+    n_obs = rng.integers(1, 20, n_mp).astype(np.int32)
+    skip = ((rng.random(n_mp) < 0.08) | (bad > 0)).astype(np.uint8)
+    prior = np.zeros(n_kp, dtype=np.int32)
+    kp_mp = np.full(n_kp, -1, dtype=np.int32)
+    held = rng.permutation(n_kp)[: n_kp // 10]
+    prior[held] = rng.integers(0, 4, held.size)
+    kp_mp[held] = rng.integers(0, n_mp, held.size)
+    T = np.concatenate([R, t[:, None]], axis=1).astype(np.float32)
+    return FrustumCase(frame, T, R, t, Ow, K, 40.0, 0.5, float(np.log(np.float32(1.2))), world, normal.astype(np.float32), min_d, max_d, desc,
+                       bad, n_obs, skip, prior, kp_mp)

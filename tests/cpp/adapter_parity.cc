@@ -77,8 +77,16 @@ static void plant(FeatureSet &dst, int i, const FeatureSet &src, int j, int flip
     dst.mvKeys[i] = kp;
 }
 
-static void finish_frame(Frame &F) { F.mnMinX = 0; F.mnMinY = 0; F.mnMaxX = 640; F.mnMaxY = 480; F.mvbOutlier.assign(F.N, false); F.AssignFeaturesToGrid(0, 0); }
-static void finish_kf(KeyFrame &K) { K.mnMinX = 0; K.mnMinY = 0; K.mnMaxX = 640; K.mnMaxY = 480; K.AssignFeaturesToGrid(0, 0); }
+static void finish_frame(Frame &F) { F.mnMinX = 0; F.mnMinY = 0; F.mnMaxX = 640; F.mnMaxY = 480; F.mvbOutlier.assign(F.N, false); F.AssignFeaturesToGrid(); }
+static void finish_kf(KeyFrame &K)
+{
+    Frame F; // a key frame takes the grid of the frame it is made from (KeyFrame.cc:66-82)
+    F.N = K.N; F.mvKeysUn = K.mvKeysUn;
+    F.mfGridElementWidthInv = K.mfGridElementWidthInv; F.mfGridElementHeightInv = K.mfGridElementHeightInv;
+    F.mnMinX = 0; F.mnMinY = 0; F.mnMaxX = 640; F.mnMaxY = 480;
+    F.AssignFeaturesToGrid();
+    K.CopyGridFrom(F);
+}
 
 
 // ---- a scene with real geometry for the overloads that project on their own.  Built twice from the

@@ -259,3 +259,91 @@ def test_bow_conflicts(oracle, reference, seed, layout, ratio):
         got = oracle.search_by_bow_kf_kf(bc.kf, bc.f, bc.kf_mp_valid, bc.f_mp_valid, ratio, ori)
         assert got[0] == exp[0] and np.array_equal(got[1], exp[1])
     assert exp[0] > 20
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# The helpers whose bodies are the reference's OWN TEXT, cut out of Frame.cc / KeyFrame.cc / MapPoint.cc / Pinhole.cpp by line range at
+# build time (oracle/extract_ref.py): the C restatement must agree with them bit for bit.
+@pytest.mark.parametrize("seed", [111, 112])
+def test_keyframe_area_and_is_in_image(oracle, reference, seed):
+    """KeyFrame::GetFeaturesInArea / IsInImage with the key frame's int bounds and the grid copied from its Frame (KeyFrame.cc:66-82)"""
+    rng = np.random.default_rng(seed)
+    f = synth.make_frame(rng, 1500)
+    f.min_x, f.min_y, f.max_x, f.max_y = 0.0, 0.0, 640.0, 480.0
+    cs, ci = oracle.grid(f)
+    for _ in range(300):
+        x, y = float(rng.uniform(-40, 690)), float(rng.uniform(-40, 520))
+        if rng.random() < 0.2:
+            x, y = float(rng.choice([0.0, 640.0, 639.75])), float(rng.choice([0.0, 480.0, 479.75]))
+        r = float(rng.choice([1.0, 3.0, 7.5, 60.0]))
+        a = oracle.features_in_area(f, x, y, r, -1, -1, grid=(cs, ci))
+        b, inimg = reference.keyframe_features_in_area(f, x, y, r)
+        assert np.array_equal(a, b)
+        assert inimg == (x >= 0 and x < 640 and y >= 0 and y < 480)  # what the adapter's prologue evaluates (ORBmatcher.hpp)
+
+
+def test_predict_scale_and_distance_invariance(oracle, reference):
+    rng = np.random.default_rng(5)
+    n = 20000
+    lsf = float(np.log(np.float32(1.2)))
+    mx = rng.uniform(0.5, 60, n).astype(np.float32)
+    mn = (mx / 3.5).astype(np.float32)
+    cd = (mx / (np.float32(1.2) ** rng.integers(-2, 10, n)) * rng.choice(np.array([1.0, 1.0, 1.0000001, 0.9999999, 1.01], dtype=np.float32), n)).astype(np.float32)
+    lk, lf, a, b = reference.predict_scale(mx, mn, cd, lsf, 8)
+    o = oracle.predict_scale(mx, cd, lsf, 8)
+    assert np.array_equal(lk, o) and np.array_equal(lf, o)
+    assert np.array_equal(a, np.float32(0.8) * mn) and np.array_equal(b, np.float32(1.2) * mx)
+    assert set(np.unique(o)) == set(range(8))
+
+
+def test_pinhole_project_and_epipolar_constrain(oracle, reference):
+    rng = np.random.default_rng(6)
+    K = np.array([synth.FX, synth.FY, synth.CX, synth.CY], dtype=np.float32)
+    xyz = np.stack([rng.uniform(-5, 5, 5000), rng.uniform(-4, 4, 5000), rng.uniform(0.2, 15, 5000)], axis=1).astype(np.float32)
+    assert np.array_equal(oracle.pinhole_project(K, xyz), reference.pinhole_project(K, xyz))
+    tc = synth.fill_geometry(synth.make_triangulation_case(17, n_pairs=6, n_feat=400))
+    for p in range(6):
+        R1, t1 = tc.T1w[p][:9].reshape(3, 3).astype(np.float64), tc.T1w[p][9:12].astype(np.float64)
+        R2, t2 = tc.T2w[p][:9].reshape(3, 3).astype(np.float64), tc.T2w[p][9:12].astype(np.float64)
+        R12, t12 = (R1 @ R2.T).astype(np.float32), (t1 - R1 @ R2.T @ t2).astype(np.float32)  # any pair of floats: both sides consume them
+        k1, k2 = tc.kf1[p], tc.kf2[p]
+        a, b = tc.kfs.kp_xy[k1], tc.kfs.kp_xy[k2][rng.permutation(400)]
+        b[:200] = tc.kfs.kp_xy[k2][:200]  # planted correspondences next to random pairs
+        unc = tc.kfs.level_sigma2[tc.kfs.octave[k2]]
+        ok, f12 = reference.epipolar_constrain(K, K, R12, t12, a, b, unc)
+        assert np.array_equal(ok, oracle.epipolar_constrain(f12, a, b, unc))
+        assert 0 < ok.sum() < ok.size
+
+
+@pytest.mark.parametrize("seed", [701, 702, 703])
+def test_is_in_frustum(oracle, reference, seed):
+    """Frame::isInFrustum (Frame.cc:676-782): every member the function writes, for points that fail each gate in turn"""
+    from orb_slam3_comments_ghr_b200._abi import frustum_struct
+    c = synth.make_frustum_case(seed)
+    f = c.frame
+    ret, r = reference.is_in_frustum(f, c.Tcw34, c.K, c.mbf, c.viewing_cos_limit, c.world_pos, c.normal, c.min_distance, c.max_distance)
+    fr = frustum_struct(c.Rcw, c.tcw, c.Ow, c.K, c.mbf, (f.min_x, f.min_y, f.max_x, f.max_y), c.viewing_cos_limit, c.log_scale_factor, 8)
+    o = oracle.is_in_frustum(fr, c.world_pos, c.normal, c.min_distance, c.max_distance)
+    assert np.array_equal(ret, r["in_view"])
+    for k in ("in_view", "proj_xy"):
+        assert np.array_equal(o[k], r[k]), k
+    v = r["in_view"] > 0  # the other members are only written for accepted points
+    for k in ("proj_xr", "depth", "scale_level", "view_cos"):
+        assert np.array_equal(o[k][v], r[k][v]), k
+    assert 0.15 < v.mean() < 0.8 and (r["proj_xy"][~v, 0] >= 0).any() and (r["proj_xy"][~v, 0] < 0).any()
+    assert len(np.unique(r["scale_level"][v])) >= 6
+
+
+@pytest.mark.parametrize("seed,n", [(801, 2000), (802, 500), (803, 1)])
+def test_stereo_coarse_match_reference(oracle, reference, seed, n):
+    """row f3: the coarse stage of Frame::ComputeStereoMatches, the reference's own text (Frame.cc:1117-1247).  The reference indexes
+    vRowIndices with rows outside the image (undefined behaviour), so the case is shifted 16 rows down inside a taller image."""
+    left, right, n_rows, mb, mbf = synth.make_stereo_case(seed, n=n)
+    for fr in (left, right):
+        fr.kp_xy[:, 1] += 16.0
+    n_rows += 32
+    a = oracle.stereo_coarse_match(left, right, n_rows, mb, mbf)
+    b = reference.stereo_coarse_match(left, right, n_rows, mb, mbf)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    if n >= 500:
+        assert (a[0] >= 0).mean() > 0.3
