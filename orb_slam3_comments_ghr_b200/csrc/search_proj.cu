@@ -164,6 +164,75 @@ proj_resolve_kernel(FrameView f, MapPointsView mp, const uint32_t *__restrict__ 
     }
 }
 
+// Frame::isInFrustum, Nleft == -1 (Frame.cc:676-782), one thread per map point, the reference's fp32 operation order
+// (no contraction: every product and sum is its own rounding).  Writes the members the function sets in the MapPoint;
+// a point rejected after the image-bounds test keeps its projection (:712-713).
+struct FrustumView {
+    orbgpu_frustum_host fr;
+    int n;
+    const float *world_pos, *normal, *min_distance, *max_distance;
+    const uint8_t *skip;
+    uint8_t *in_view;
+    float2 *proj_xy;
+    float *proj_xr, *depth, *view_cos;
+    int32_t *scale_level;
+};
+__global__ void frustum_kernel(const FrustumView v)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.n) return;
+    const orbgpu_frustum_host &fr = v.fr;
+    uint8_t inview = 0;
+    float2 uvout = make_float2(-1.f, -1.f); // :682-684
+    float xr = 0.f, dep = 0.f, vc = 0.f;
+    int lvl = 0;
+    if (!(v.skip && v.skip[i])) {
+        const float P0 = v.world_pos[3 * i], P1 = v.world_pos[3 * i + 1], P2 = v.world_pos[3 * i + 2];
+        float Pc[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) // :695 mRcw * P + mtcw
+            Pc[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(fr.Rcw[3 * r], P0), __fmul_rn(fr.Rcw[3 * r + 1], P1)), __fmul_rn(fr.Rcw[3 * r + 2], P2)),
+                              fr.tcw[r]);
+        const float Pc_dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(Pc[0], Pc[0]), __fmul_rn(Pc[1], Pc[1])), __fmul_rn(Pc[2], Pc[2])));
+        const float PcZ = Pc[2];
+        const float invz = __fdiv_rn(1.0f, PcZ);
+        if (!(PcZ < 0.0f)) { // :701
+            // Pinhole::project (Pinhole.cpp:64-71): fx * X / Z + cx
+            const float u = __fadd_rn(__fdiv_rn(__fmul_rn(fr.K[0], Pc[0]), PcZ), fr.K[2]);
+            const float w = __fadd_rn(__fdiv_rn(__fmul_rn(fr.K[1], Pc[1]), PcZ), fr.K[3]);
+            if (!(u < fr.min_x || u > fr.max_x) && !(w < fr.min_y || w > fr.max_y)) { // :707-710
+                uvout = make_float2(u, w); // :712-713
+                const float maxDistance = __fmul_rn(1.2f, v.max_distance[i]), minDistance = __fmul_rn(0.8f, v.min_distance[i]);
+                const float PO0 = __fsub_rn(P0, fr.Ow[0]), PO1 = __fsub_rn(P1, fr.Ow[1]), PO2 = __fsub_rn(P2, fr.Ow[2]);
+                const float dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(PO0, PO0), __fmul_rn(PO1, PO1)), __fmul_rn(PO2, PO2)));
+                if (!(dist < minDistance || dist > maxDistance)) { // :723
+                    const float dot = __fadd_rn(__fadd_rn(__fmul_rn(PO0, v.normal[3 * i]), __fmul_rn(PO1, v.normal[3 * i + 1])),
+                                                __fmul_rn(PO2, v.normal[3 * i + 2]));
+                    const float viewCos = __fdiv_rn(dot, dist); // :730
+                    if (!(viewCos < fr.viewing_cos_limit)) {
+                        // MapPoint::PredictScale (MapPoint.cc:722-738): log in double, rounded to float (see the header)
+                        const float ratio = __fdiv_rn(v.max_distance[i], dist);
+                        int nScale = (int)ceilf(__fdiv_rn((float)log((double)ratio), fr.log_scale_factor));
+                        if (nScale < 0) nScale = 0;
+                        else if (nScale >= fr.n_levels) nScale = fr.n_levels - 1;
+                        inview = 1;
+                        xr = __fsub_rn(u, __fmul_rn(fr.mbf, invz)); // :743
+                        dep = Pc_dist;
+                        lvl = nScale;
+                        vc = viewCos;
+                    }
+                }
+            }
+        }
+    }
+    v.in_view[i] = inview;
+    v.proj_xy[i] = uvout;
+    v.proj_xr[i] = xr;
+    v.depth[i] = dep;
+    v.scale_level[i] = lvl;
+    v.view_cos[i] = vc;
+}
+
 } // namespace
 
 extern "C" int orbgpu_search_by_projection_local(orbgpu_ctx *ctx, const orbgpu_frame *f, const orbgpu_mappoints_host *mps,
@@ -232,6 +301,123 @@ extern "C" int orbgpu_search_by_projection_local(orbgpu_ctx *ctx, const orbgpu_f
     CU_TRY(cudaGetLastError());
     const OutPiece out[2] = {{kp_mp, d_kpmp, (size_t)n * 4}, {nmatches, d_nm, 4}};
     return ctx_download(ctx, out, 2);
+}
+
+extern "C" int orbgpu_is_in_frustum(orbgpu_ctx *ctx, const orbgpu_frustum_host *fr, int32_t n, const float *world_pos, const float *normal,
+                                    const float *min_distance, const float *max_distance, uint8_t *in_view, float *proj_xy, float *proj_xr,
+                                    float *depth, int32_t *scale_level, float *view_cos)
+{
+    ARG_TRY(ctx && fr && n >= 0 && (n == 0 || (world_pos && normal && min_distance && max_distance)));
+    ARG_TRY(fr->n_levels > 0 && fr->n_levels <= 64);
+    int rc = ctx_begin(ctx);
+    if (rc) return rc;
+    if (n == 0) return ORBGPU_OK;
+    const size_t N = (size_t)n;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+    const size_t o_wp = take(N * 12), o_nm = take(N * 12), o_mn = take(N * 4), o_mx = take(N * 4);
+    const size_t up_bytes = off;
+    const size_t o_iv = take(N), o_xy = take(N * 8), o_xr = take(N * 4), o_dp = take(N * 4), o_lv = take(N * 4), o_vc = take(N * 4);
+    rc = stage_reserve(ctx, up_bytes);
+    if (rc) return rc;
+    rc = arena_reserve(ctx, off + 256);
+    if (rc) return rc;
+    char *H = ctx->h_stage;
+    memcpy(H + o_wp, world_pos, N * 12);
+    memcpy(H + o_nm, normal, N * 12);
+    memcpy(H + o_mn, min_distance, N * 4);
+    memcpy(H + o_mx, max_distance, N * 4);
+    char *D = (char *)arena_take(ctx, off);
+    if (!D) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
+    CU_TRY(cudaMemcpyAsync(D, H, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    FrustumView v;
+    v.fr = *fr; v.n = n;
+    v.world_pos = (const float *)(D + o_wp); v.normal = (const float *)(D + o_nm);
+    v.min_distance = (const float *)(D + o_mn); v.max_distance = (const float *)(D + o_mx); v.skip = nullptr;
+    v.in_view = (uint8_t *)(D + o_iv); v.proj_xy = (float2 *)(D + o_xy); v.proj_xr = (float *)(D + o_xr); v.depth = (float *)(D + o_dp);
+    v.scale_level = (int32_t *)(D + o_lv); v.view_cos = (float *)(D + o_vc);
+    frustum_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(v);
+    LAUNCH_COUNT(ctx);
+    CU_TRY(cudaGetLastError());
+    const OutPiece out[6] = {{in_view, v.in_view, N}, {proj_xy, v.proj_xy, N * 8}, {proj_xr, v.proj_xr, N * 4},
+                             {depth, v.depth, N * 4}, {scale_level, v.scale_level, N * 4}, {view_cos, v.view_cos, N * 4}};
+    return ctx_download(ctx, out, 6);
+}
+
+// Tracking::SearchLocalPoints on the device: isInFrustum of every local map point, then SearchByProjection(Frame&, vector<MapPoint*>&)
+// on the projections it left in HBM -- no host loop (5000 transforms / projections / gates on one host thread) between the two.
+extern "C" int orbgpu_search_local_points(orbgpu_ctx *ctx, const orbgpu_frame *f, const orbgpu_frustum_host *fr,
+                                          const orbgpu_localpoints_host *pts, float th, int32_t far_points, float th_far_points,
+                                          float nnratio, const int32_t *kp_prior_obs, int32_t *kp_mp, uint8_t *in_view, int32_t *nmatches)
+{
+    ARG_TRY(ctx && f && fr && pts && nmatches);
+    ARG_TRY(f->n == 0 || (kp_prior_obs && kp_mp));
+    ARG_TRY(pts->n >= 0 && (pts->n == 0 || (pts->desc && pts->world_pos && pts->normal && pts->min_distance && pts->max_distance &&
+                                            pts->bad && pts->n_obs)));
+    ARG_TRY(f->n < (1 << 20) && fr->n_levels > 0 && fr->n_levels <= f->n_levels);
+    int rc = ctx_begin(ctx);
+    if (rc) return rc;
+    *nmatches = 0;
+    const int n = f->n, M = pts->n;
+    if (M == 0) return ORBGPU_OK;
+    const size_t Mz = (size_t)M, nz = (size_t)(n > 0 ? n : 1);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+    const size_t o_desc = take(Mz * 32), o_wp = take(Mz * 12), o_nm = take(Mz * 12), o_mn = take(Mz * 4), o_mx = take(Mz * 4),
+                 o_skip = take(Mz), o_bad = take(Mz), o_nobs = take(Mz * 4), o_prior = take(nz * 4), o_kpmp = take(nz * 4);
+    const size_t up_bytes = off;
+    const size_t o_iv = take(Mz), o_xy = take(Mz * 8), o_xr = take(Mz * 4), o_dp = take(Mz * 4), o_lv = take(Mz * 4), o_vc = take(Mz * 4);
+    const int stride = n > 0 ? n : 1;
+    rc = stage_reserve(ctx, up_bytes);
+    if (rc) return rc;
+    rc = arena_reserve(ctx, off + align256(Mz * stride * 4) + 2 * align256(Mz * 4) + 512);
+    if (rc) return rc;
+    char *H = ctx->h_stage;
+    memcpy(H + o_desc, pts->desc, Mz * 32);
+    memcpy(H + o_wp, pts->world_pos, Mz * 12);
+    memcpy(H + o_nm, pts->normal, Mz * 12);
+    memcpy(H + o_mn, pts->min_distance, Mz * 4);
+    memcpy(H + o_mx, pts->max_distance, Mz * 4);
+    if (pts->skip) memcpy(H + o_skip, pts->skip, Mz); else memset(H + o_skip, 0, Mz);
+    memcpy(H + o_bad, pts->bad, Mz);
+    memcpy(H + o_nobs, pts->n_obs, Mz * 4);
+    if (n > 0) {
+        memcpy(H + o_prior, kp_prior_obs, (size_t)n * 4);
+        memcpy(H + o_kpmp, kp_mp, (size_t)n * 4);
+    }
+    char *D = (char *)arena_take(ctx, off);
+    uint32_t *lists = (uint32_t *)arena_take(ctx, Mz * stride * 4);
+    int32_t *counts = (int32_t *)arena_take(ctx, Mz * 4), *choice = (int32_t *)arena_take(ctx, Mz * 4);
+    int32_t *d_nm = (int32_t *)arena_take(ctx, 256);
+    if (!D || !lists || !counts || !choice || !d_nm) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
+    CU_TRY(cudaMemcpyAsync(D, H, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemsetAsync(d_nm, 0, 4, ctx->stream));
+    FrustumView v;
+    v.fr = *fr; v.n = M;
+    v.world_pos = (const float *)(D + o_wp); v.normal = (const float *)(D + o_nm);
+    v.min_distance = (const float *)(D + o_mn); v.max_distance = (const float *)(D + o_mx); v.skip = (const uint8_t *)(D + o_skip);
+    v.in_view = (uint8_t *)(D + o_iv); v.proj_xy = (float2 *)(D + o_xy); v.proj_xr = (float *)(D + o_xr); v.depth = (float *)(D + o_dp);
+    v.scale_level = (int32_t *)(D + o_lv); v.view_cos = (float *)(D + o_vc);
+    frustum_kernel<<<(M + 255) / 256, 256, 0, ctx->stream>>>(v);
+    LAUNCH_COUNT(ctx);
+    if (n > 0) {
+        MapPointsView mv;
+        mv.n = M;
+        mv.desc = (const uint4 *)(D + o_desc); mv.proj_xy = v.proj_xy; mv.proj_xr = v.proj_xr; mv.scale_level = v.scale_level;
+        mv.view_cos = v.view_cos; mv.depth = v.depth; mv.in_view = v.in_view; mv.bad = (const uint8_t *)(D + o_bad);
+        mv.n_obs = (const int32_t *)(D + o_nobs);
+        const FrameView fv = frame_view(f);
+        proj_candidates_kernel<<<(M * 32 + 255) / 256, 256, 0, ctx->stream>>>(fv, mv, th, far_points, th_far_points, lists, stride, counts,
+                                                                             ctx->d_counters);
+        const size_t lock_bytes = (size_t)n * sizeof(int);
+        if (lock_bytes > 200 * 1024) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "frame too large for the shared-memory lock table");
+        proj_resolve_kernel<<<1, RESOLVE_THREADS, lock_bytes, ctx->stream>>>(fv, mv, lists, stride, counts, nnratio, (int32_t *)(D + o_prior),
+                                                                            choice, (int32_t *)(D + o_kpmp), d_nm, ctx->d_counters);
+        ctx->launches += 2;
+    }
+    CU_TRY(cudaGetLastError());
+    const OutPiece out[3] = {{kp_mp, D + o_kpmp, (size_t)n * 4}, {nmatches, d_nm, 4}, {in_view, v.in_view, Mz}};
+    return ctx_download(ctx, out, 3);
 }
 
 int search_proj_device_init() { return set_max_dyn_smem(proj_resolve_kernel); }

@@ -14,7 +14,7 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-from ._abi import (BowDbHostStruct, HostBowDb, FrameHostStruct, HostFrame, HostKfSet, HostMapPoints, HostProjPoints, HostVoc, KfSetHostStruct, MapPointsHostStruct,
+from ._abi import (FrustumHostStruct, HostLocalPoints, LocalPointsHostStruct, BowDbHostStruct, HostBowDb, FrameHostStruct, HostFrame, HostKfSet, HostMapPoints, HostProjPoints, HostVoc, KfSetHostStruct, MapPointsHostStruct,
                    ProjPointsHostStruct, ProjSearchParamsStruct, proj_params, VocHostStruct, as_f32, as_i32, as_u8, f32p, f64p, i32p, i64p, u8p, u32p)
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liborbmatch_b200.so")
@@ -196,6 +196,22 @@ class Context:
         ind = np.zeros(3, dtype=np.int32)
         _check(load_library().orbgpu_compute_three_maxima(self._h, _p(sizes, i32p), int(sizes.shape[0]), _p(ind, i32p)))
         return ind
+
+    # ---- 8(f) rank 1: Frame::isInFrustum (Frame.cc:676-782) for a list of map points -> dict of the MapPoint members it writes
+    def is_in_frustum(self, fr: FrustumHostStruct, world_pos, normal, min_distance, max_distance):
+        wp, nm = as_f32(world_pos).reshape(-1, 3), as_f32(normal).reshape(-1, 3)
+        mn, mx = as_f32(min_distance), as_f32(max_distance)
+        n = wp.shape[0]
+        m = max(n, 1)
+        out = {"in_view": np.zeros(m, dtype=np.uint8), "proj_xy": np.zeros((m, 2), dtype=np.float32), "proj_xr": np.zeros(m, dtype=np.float32),
+               "depth": np.zeros(m, dtype=np.float32), "scale_level": np.zeros(m, dtype=np.int32), "view_cos": np.zeros(m, dtype=np.float32)}
+        L = load_library()
+        L.orbgpu_is_in_frustum.argtypes = [C.c_void_p, C.POINTER(FrustumHostStruct), C.c_int32, f32p, f32p, f32p, f32p, u8p, f32p, f32p, f32p,
+                                           i32p, f32p]
+        _check(L.orbgpu_is_in_frustum(self._h, C.byref(fr), n, _p(wp, f32p), _p(nm, f32p), _p(mn, f32p), _p(mx, f32p), _p(out["in_view"], u8p),
+                                      _p(out["proj_xy"], f32p), _p(out["proj_xr"], f32p), _p(out["depth"], f32p),
+                                      _p(out["scale_level"], i32p), _p(out["view_cos"], f32p)))
+        return {k: v[:n] for k, v in out.items()}
 
     # ---- uploads
     def upload_frame(self, f: HostFrame) -> "DeviceFrame":
@@ -472,6 +488,23 @@ class ORBmatcher:
                                                                 float(thFarPoints), self.mfNNratio, _p(prior, i32p), _p(out, i32p),
                                                                 C.byref(nm)))
         return nm.value, out
+
+    # Tracking::SearchLocalPoints: Frame::isInFrustum of every local map point + SearchByProjection (ORBmatcher.h:44), fused on the
+    # device -> (nmatches, F.mvpMapPoints as indices into the local points, mbTrackInView per point)
+    def SearchLocalPoints(self, F: DeviceFrame, fr: FrustumHostStruct, pts: HostLocalPoints, th: float = 1.0, bFarPoints: bool = False,
+                          thFarPoints: float = 50.0, kp_prior_obs=None, kp_mp=None):
+        n = F.n
+        prior = as_i32(kp_prior_obs) if kp_prior_obs is not None else np.zeros(n, dtype=np.int32)
+        out = as_i32(kp_mp).copy() if kp_mp is not None else np.full(n, -1, dtype=np.int32)
+        inv = np.zeros(max(pts.n, 1), dtype=np.uint8)
+        nm = C.c_int32(0)
+        s = pts.struct()
+        L = load_library()
+        L.orbgpu_search_local_points.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(FrustumHostStruct), C.POINTER(LocalPointsHostStruct),
+                                                 C.c_float, C.c_int32, C.c_float, C.c_float, i32p, i32p, u8p, C.POINTER(C.c_int32)]
+        _check(L.orbgpu_search_local_points(self.ctx.handle, F.handle, C.byref(fr), C.byref(s), float(th), int(bFarPoints),
+                                            float(thFarPoints), self.mfNNratio, _p(prior, i32p), _p(out, i32p), _p(inv, u8p), C.byref(nm)))
+        return nm.value, out, inv[:pts.n]
 
     # search core of the self-projecting overloads (ORBmatcher.h:48-60, 78-84): points already projected by the caller
     # -> (nmatches, best_idx per point, best_dist per point, owner point per keypoint)

@@ -689,3 +689,40 @@ def test_knn2_full_size_engines_agree(ctx, M):
     acc = (bd <= 50) & (bd.float() < 0.8 * sd.float())
     assert torch.equal(mt >= 0, acc) and torch.equal(mt[acc], bi[acc])
     assert int(acc.sum()) >= int(0.95 * n_pl)
+
+
+@pytest.mark.parametrize("seed,n_mp", [(711, 5000), (712, 20000), (713, 1)])
+def test_is_in_frustum(ctx, oracle, seed, n_mp):
+    """row f1: Frame::isInFrustum (Frame.cc:676-782) on the device == the C restatement (pinned on the reference's own text): every
+    member the function writes, bit for bit, incl. the predicted level (log taken in double on the device, logf on the host)"""
+    from orb_slam3_comments_ghr_b200._abi import frustum_struct
+    c = synth.make_frustum_case(seed, n_mp=n_mp)
+    f = c.frame
+    fr = frustum_struct(c.Rcw, c.tcw, c.Ow, c.K, c.mbf, (f.min_x, f.min_y, f.max_x, f.max_y), c.viewing_cos_limit, c.log_scale_factor, 8)
+    g = ctx.is_in_frustum(fr, c.world_pos, c.normal, c.min_distance, c.max_distance)
+    o = oracle.is_in_frustum(fr, c.world_pos, c.normal, c.min_distance, c.max_distance)
+    for k in ("in_view", "proj_xy", "proj_xr", "depth", "scale_level", "view_cos"):
+        assert np.array_equal(g[k], o[k]), k
+    if n_mp > 100:
+        assert 0.15 < o["in_view"].mean() < 0.8
+
+
+@pytest.mark.parametrize("seed,th,far", [(721, 1.0, 0), (722, 3.0, 0), (723, 3.0, 1)])
+def test_search_local_points_fused(ctx, M, oracle, seed, th, far):
+    """Tracking::SearchLocalPoints on the device (isInFrustum + SearchByProjection, one call, projections never leave HBM) == the two
+    host-visible steps of the oracle; also == the two GPU calls made separately"""
+    from orb_slam3_comments_ghr_b200._abi import HostLocalPoints, HostMapPoints, frustum_struct
+    c = synth.make_frustum_case(seed)
+    f = c.frame
+    fr = frustum_struct(c.Rcw, c.tcw, c.Ow, c.K, c.mbf, (f.min_x, f.min_y, f.max_x, f.max_y), c.viewing_cos_limit, c.log_scale_factor, 8)
+    o = oracle.is_in_frustum(fr, c.world_pos, c.normal, c.min_distance, c.max_distance)
+    inv = (o["in_view"] > 0) & (c.skip == 0)  # the loop of SearchLocalPoints does not test skipped points: mbTrackInView stays false
+    mps = HostMapPoints(c.desc, o["proj_xy"], o["scale_level"], o["view_cos"], o["depth"], inv.astype(np.uint8), c.bad, c.n_obs, proj_xr=o["proj_xr"])
+    en, ekp = oracle.search_by_projection_local(f, mps, th, far, 6.0, c.nnratio, c.kp_prior_obs, c.kp_mp)
+    d = ctx.upload_frame(f)
+    m = M.ORBmatcher(c.nnratio, True, ctx)
+    pts = HostLocalPoints(c.desc, c.world_pos, c.normal, c.min_distance, c.max_distance, c.bad, c.n_obs, skip=c.skip)
+    n, kp, giv = m.SearchLocalPoints(d, fr, pts, th, bool(far), 6.0, c.kp_prior_obs, c.kp_mp)
+    assert n == en and np.array_equal(kp, ekp) and np.array_equal(giv, inv.astype(np.uint8))
+    n2, kp2 = m.SearchByProjection(d, mps, th, bool(far), 6.0, c.kp_prior_obs, c.kp_mp)
+    assert n2 == n and np.array_equal(kp2, kp) and en > 200
