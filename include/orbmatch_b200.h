@@ -247,6 +247,13 @@ void orbgpu_voc_destroy(orbgpu_voc *v);
  * SearchByBoW / SearchForTriangulation can run without a host round trip. */
 int orbgpu_transform(orbgpu_ctx *ctx, const orbgpu_voc *voc, orbgpu_frame *f, int32_t levelsup, int32_t store_featvec,
                      uint32_t *word_id, uint32_t *node_id, double *weight);
+/* The same transform for a bare list of descriptors with the reference's outputs in flat form, one call and one synchronisation
+ * (what Frame::ComputeBoW, Frame.cc:1005-1008, and KeyFrame::ComputeBoW, KeyFrame.cc:113, need): BowVector as (words ascending,
+ * values) with n_words entries, FeatureVector as CSR (node ids ascending, offsets, feature ids ascending inside a node) with
+ * n_nodes nodes.  Capacities: n entries each (n + 1 offsets). */
+int orbgpu_transform_descriptors(orbgpu_ctx *ctx, const orbgpu_voc *voc, int32_t n, const uint8_t *desc, int32_t levelsup,
+                                 int32_t *n_words, uint32_t *words, double *values, int32_t *n_nodes, uint32_t *node_ids,
+                                 int32_t *offsets, uint32_t *features);
 /* device-built BowVector (BowVector.cpp:35-85): words ascending, value = idf added count
  * times in feature order, then L1-normalised in ascending word order.  Capacity n each. */
 int orbgpu_bowvector_download(orbgpu_ctx *ctx, const orbgpu_frame *f, int32_t *n_words, uint32_t *words, double *values);

@@ -115,6 +115,102 @@ namespace orbgpu
         DeviceFrameGuard &operator=(const DeviceFrameGuard &) = delete;
     };
 
+    // Device frames are cached per calling thread, keyed on the reference's own identity of the object: Frame::mnId / KeyFrame::mnId
+    // (Frame.h:278, KeyFrame.h:243; key points and descriptors are immutable after construction, KeyFrame.h:378-400) plus what can
+    // still change afterwards -- the FeatureVector (ComputeBoW runs once, later) and whether mvuRight is needed.  A repeated call on
+    // the same Frame / KeyFrame (TrackReferenceKeyFrame then TrackLocalMap on the current frame; a key frame matched against each of
+    // its neighbours in CreateNewMapPoints / SearchInNeighbors / loop detection) skips the pack + upload + grid build, which cost
+    // more than the search itself.  Bounded LRU; set_frame_cache_capacity(0) turns it off.
+    struct FrameCache
+    {
+        struct Key
+        {
+            int kind; // 0 Frame, 1 KeyFrame
+            unsigned long id;
+            int n, with_uright;
+            size_t fv_nodes;
+            bool operator==(const Key &o) const { return kind == o.kind && id == o.id && n == o.n && with_uright == o.with_uright && fv_nodes == o.fv_nodes; }
+        };
+        struct Entry { Key key; orbgpu_frame *f; unsigned long stamp; };
+        std::vector<Entry> entries;
+        unsigned long clock = 0, hits = 0, misses = 0;
+        size_t capacity = 48;
+        ~FrameCache() { clear(); }
+        void clear()
+        {
+            for (Entry &e : entries) orbgpu_frame_destroy(e.f);
+            entries.clear();
+        }
+        orbgpu_frame *find(const Key &k)
+        {
+            for (Entry &e : entries)
+                if (e.key == k) { e.stamp = ++clock; hits++; return e.f; }
+            misses++;
+            return nullptr;
+        }
+        void insert(const Key &k, orbgpu_frame *f)
+        {
+            // an older copy of the same object (its FeatureVector has been computed since) is dropped, then the least recently used
+            for (size_t i = 0; i < entries.size();)
+                if (entries[i].key.kind == k.kind && entries[i].key.id == k.id) { orbgpu_frame_destroy(entries[i].f); entries.erase(entries.begin() + i); }
+                else i++;
+            while (entries.size() >= capacity && !entries.empty())
+            {
+                size_t lru = 0;
+                for (size_t i = 1; i < entries.size(); i++)
+                    if (entries[i].stamp < entries[lru].stamp) lru = i;
+                orbgpu_frame_destroy(entries[lru].f);
+                entries.erase(entries.begin() + lru);
+            }
+            entries.push_back(Entry{k, f, ++clock});
+        }
+    };
+    // the cache lives and dies with the thread's context (its frames were uploaded on that context's stream)
+    inline FrameCache &frame_cache()
+    {
+        thread_local FrameCache c;
+        return c;
+    }
+    inline void set_frame_cache_capacity(size_t n)
+    {
+        frame_cache().capacity = n;
+        if (n == 0) frame_cache().clear();
+    }
+    // device copy of a Frame (kind 0) or KeyFrame (kind 1): from the thread's cache, or packed + uploaded now
+    struct FrameRef
+    {
+        orbgpu_frame *f = nullptr;
+        bool owned = false;
+        template <class FS>
+        FrameRef(orbgpu_ctx *ctx, int kind, const FS &F, float minX, float minY, float maxX, float maxY, bool with_uright)
+        {
+            FrameCache &c = frame_cache();
+            const FrameCache::Key k{kind, (unsigned long)F.mnId, (int)F.N, with_uright ? 1 : 0, F.mFeatVec.size()};
+            if (c.capacity > 0 && (f = c.find(k))) return;
+            PackedFrame p;
+            p.pack(F, minX, minY, maxX, maxY, with_uright);
+            check(orbgpu_frame_upload(ctx, &p.h, &f));
+            if (c.capacity > 0) c.insert(k, f);
+            else owned = true;
+        }
+        ~FrameRef() { if (owned) orbgpu_frame_destroy(f); }
+        FrameRef(const FrameRef &) = delete;
+        FrameRef &operator=(const FrameRef &) = delete;
+    };
+    // Checker of the device-side Frame::isInFrustum (north_star: "any window-boundary candidate disagreement is reported, with a target
+    // of zero"): when enabled, ORBmatcherT::SearchLocalPoints also runs the reference's own Frame::isInFrustum on the host for every
+    // point it tested on the device and counts the points whose result differs.
+    struct FrustumReport
+    {
+        bool enabled = false;
+        unsigned long points = 0, in_view_mismatch = 0, level_mismatch = 0, projection_mismatch = 0;
+    };
+    inline FrustumReport &frustum_report()
+    {
+        static FrustumReport r;
+        return r;
+    }
+
 
     // points already projected into the target frame (inputs of orbgpu_search_projected); index m == source index
     struct ProjBatch
@@ -212,10 +308,7 @@ namespace orbgpu
                                     int windowSize = 10)
         {
             orbgpu_ctx *ctx = thread_context();
-            PackedFrame p1, p2;
-            p1.pack(F1, F1.mnMinX, F1.mnMinY, F1.mnMaxX, F1.mnMaxY, false);
-            p2.pack(F2, F2.mnMinX, F2.mnMinY, F2.mnMaxX, F2.mnMaxY, false);
-            DeviceFrameGuard d1(ctx, p1.h), d2(ctx, p2.h);
+            FrameRef d1(ctx, 0, F1, F1.mnMinX, F1.mnMinY, F1.mnMaxX, F1.mnMaxY, false), d2(ctx, 0, F2, F2.mnMinX, F2.mnMinY, F2.mnMaxX, F2.mnMaxY, false);
             const int n1 = F1.N;
             std::vector<float> prev((size_t)n1 * 2);
             for (int i = 0; i < n1; i++) { prev[2 * i] = vbPrevMatched[i].x; prev[2 * i + 1] = vbPrevMatched[i].y; }
@@ -234,11 +327,9 @@ namespace orbgpu
         {
             if (F.Nleft != -1) throw std::runtime_error("orbmatch_b200: stereo-fisheye (Nleft != -1) path is not on the GPU hot path");
             orbgpu_ctx *ctx = thread_context();
-            PackedFrame pf;
             bool any_right = false;
             for (int i = 0; i < F.N && !any_right; i++) any_right = F.mvuRight[i] > 0;
-            pf.pack(F, F.mnMinX, F.mnMinY, F.mnMaxX, F.mnMaxY, any_right);
-            DeviceFrameGuard df(ctx, pf.h);
+            FrameRef df(ctx, 0, F, F.mnMinX, F.mnMinY, F.mnMaxX, F.mnMaxY, any_right);
             const int M = (int)vpMapPoints.size();
             std::vector<uint8_t> desc((size_t)M * 32), in_view(M), bad(M);
             std::vector<float> proj((size_t)M * 2), xr(M), cosv(M), depth(M);
@@ -268,15 +359,111 @@ namespace orbgpu
             return nmatches;
         }
 
+        // Tracking::SearchLocalPoints (Tracking.cc:4125-4182) in one device call: Frame::isInFrustum(pMP, viewingCosLimit) of every local
+        // map point the loop tests -- not already seen by this frame (mnLastFrameSeen == F.mnId, :4133), not bad (:4136) -- then
+        // SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints) on the projections, which never leave HBM.  Per point the
+        // adapter writes mbTrackInView (what the caller's IncreaseVisible() loop and the matcher's :55 test read); *nToMatch = number
+        // of points in view (:4140-4144).  The pose members are read exactly as Frame::UpdatePoseMatrices fills them (Frame.cc:
+        // mRcw = mTcw.rotationMatrix(), mtcw = mTcw.translation(), mOw = GetCameraCenter()).  MapPointT needs GetMinDistanceRaw() /
+        // GetMaxDistanceRaw(): PredictScale reads the raw mfMaxDistance.  With frustum_report().enabled the
+        // reference's own host isInFrustum is run as the checker and every disagreement is counted.
+        int SearchLocalPoints(FrameT &F, const std::vector<MapPointT *> &vpMapPoints, const float th = 1, const bool bFarPoints = false,
+                              const float thFarPoints = 50.0f, const float viewingCosLimit = 0.5f, int *nToMatch = nullptr)
+        {
+            if (F.Nleft != -1) throw std::runtime_error("orbmatch_b200: stereo-fisheye (Nleft != -1) path is not on the GPU hot path");
+            orbgpu_ctx *ctx = thread_context();
+            bool any_right = false;
+            for (int i = 0; i < F.N && !any_right; i++) any_right = F.mvuRight[i] > 0;
+            FrameRef df(ctx, 0, F, F.mnMinX, F.mnMinY, F.mnMaxX, F.mnMaxY, any_right);
+            orbgpu_frustum_host fr;
+            std::memset(&fr, 0, sizeof(fr));
+            const auto Tcw = F.GetPose();
+            const auto R = Tcw.rotationMatrix();
+            const auto t = Tcw.translation();
+            const auto Ow = F.GetCameraCenter();
+            for (int r = 0; r < 3; r++)
+            {
+                for (int c = 0; c < 3; c++) fr.Rcw[3 * r + c] = R(r, c);
+                fr.tcw[r] = t(r);
+                fr.Ow[r] = Ow(r);
+            }
+            fr.K[0] = F.fx; fr.K[1] = F.fy; fr.K[2] = F.cx; fr.K[3] = F.cy;
+            fr.mbf = F.mbf;
+            fr.min_x = F.mnMinX; fr.min_y = F.mnMinY; fr.max_x = F.mnMaxX; fr.max_y = F.mnMaxY;
+            fr.viewing_cos_limit = viewingCosLimit;
+            fr.log_scale_factor = F.mfLogScaleFactor;
+            fr.n_levels = F.mnScaleLevels;
+            const int M = (int)vpMapPoints.size();
+            std::vector<uint8_t> desc((size_t)M * 32, 0), skip(M, 1), bad(M, 0), in_view(M > 0 ? M : 1, 0);
+            std::vector<float> wp((size_t)M * 3, 0.f), nm((size_t)M * 3, 0.f), mind(M, 0.f), maxd(M, 0.f);
+            std::vector<int32_t> nobs(M, 0);
+            for (int i = 0; i < M; i++)
+            {
+                MapPointT *p = vpMapPoints[i];
+                if (!p) continue;
+                bad[i] = p->isBad() ? 1 : 0;
+                if (p->mnLastFrameSeen == F.mnId || bad[i]) { p->mbTrackInView = p->mnLastFrameSeen == F.mnId ? false : p->mbTrackInView; continue; }
+                skip[i] = 0;
+                const auto P = p->GetWorldPos();
+                const auto Pn = p->GetNormal();
+                for (int c = 0; c < 3; c++) { wp[3 * i + c] = P(c); nm[3 * i + c] = Pn(c); }
+                mind[i] = p->GetMinDistanceRaw();
+                maxd[i] = p->GetMaxDistanceRaw();
+                nobs[i] = p->Observations();
+                std::memcpy(&desc[(size_t)i * 32], p->GetDescriptor().template ptr<uint8_t>(), 32);
+            }
+            orbgpu_localpoints_host lp;
+            std::memset(&lp, 0, sizeof(lp));
+            lp.n = M; lp.desc = desc.data(); lp.world_pos = wp.data(); lp.normal = nm.data(); lp.min_distance = mind.data();
+            lp.max_distance = maxd.data(); lp.skip = skip.data(); lp.bad = bad.data(); lp.n_obs = nobs.data();
+            std::vector<int32_t> prior(F.N > 0 ? F.N : 1, 0), kp_mp(F.N > 0 ? F.N : 1, -1);
+            for (int i = 0; i < F.N; i++)
+                if (F.mvpMapPoints[i]) prior[i] = F.mvpMapPoints[i]->Observations();
+            int32_t nmatches = 0;
+            check(orbgpu_search_local_points(ctx, df.f, &fr, &lp, th, bFarPoints ? 1 : 0, thFarPoints, mfNNratio, prior.data(), kp_mp.data(),
+                                             in_view.data(), &nmatches));
+            int n_in_view = 0;
+            FrustumReport &rep = frustum_report();
+            std::vector<uint8_t> g_iv;
+            std::vector<float> g_xy, g_xr, g_dp, g_vc;
+            std::vector<int32_t> g_lv;
+            if (rep.enabled && M > 0)
+            {   // the device's full isInFrustum record, to compare member by member with the host's
+                g_iv.resize(M); g_xy.resize((size_t)M * 2); g_xr.resize(M); g_dp.resize(M); g_vc.resize(M); g_lv.resize(M);
+                check(orbgpu_is_in_frustum(ctx, &fr, M, wp.data(), nm.data(), mind.data(), maxd.data(), g_iv.data(), g_xy.data(), g_xr.data(),
+                                           g_dp.data(), g_lv.data(), g_vc.data()));
+            }
+            for (int i = 0; i < M; i++)
+            {
+                MapPointT *p = vpMapPoints[i];
+                if (!p || skip[i]) continue;
+                if (rep.enabled)
+                {
+                    const bool host = F.isInFrustum(p, viewingCosLimit); // the reference's own code (writes the members like it always did)
+                    rep.points++;
+                    if (host != (in_view[i] != 0)) rep.in_view_mismatch++;
+                    else if (host)
+                    {
+                        if (p->mnTrackScaleLevel != g_lv[i]) rep.level_mismatch++;
+                        if (p->mTrackProjX != g_xy[2 * i] || p->mTrackProjY != g_xy[2 * i + 1] || p->mTrackProjXR != g_xr[i]) rep.projection_mismatch++;
+                    }
+                }
+                p->mbTrackInView = in_view[i] != 0;
+                n_in_view += in_view[i] != 0;
+            }
+            if (nToMatch) *nToMatch = n_in_view;
+            for (int i = 0; i < F.N; i++)
+                if (kp_mp[i] >= 0) F.mvpMapPoints[i] = vpMapPoints[kp_mp[i]]; // ORBmatcher.cc:156
+            return nmatches;
+        }
+
         // ORBmatcher.h:65 (ORBmatcher.cc:262-496)
         int SearchByBoW(KeyFrameT *pKF, FrameT &F, std::vector<MapPointT *> &vpMapPointMatches)
         {
             orbgpu_ctx *ctx = thread_context();
             const std::vector<MapPointT *> vpMapPointsKF = pKF->GetMapPointMatches();
-            PackedFrame pk, pf;
-            pk.pack(*pKF, (float)pKF->mnMinX, (float)pKF->mnMinY, (float)pKF->mnMaxX, (float)pKF->mnMaxY, false);
-            pf.pack(F, F.mnMinX, F.mnMinY, F.mnMaxX, F.mnMaxY, false);
-            DeviceFrameGuard dk(ctx, pk.h), df(ctx, pf.h);
+            FrameRef dk(ctx, 1, *pKF, (float)pKF->mnMinX, (float)pKF->mnMinY, (float)pKF->mnMaxX, (float)pKF->mnMaxY, false);
+            FrameRef df(ctx, 0, F, F.mnMinX, F.mnMinY, F.mnMaxX, F.mnMaxY, false);
             std::vector<uint8_t> valid(pKF->N > 0 ? pKF->N : 1, 0);
             for (int i = 0; i < pKF->N; i++) valid[i] = (vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad()) ? 1 : 0; // :311-315
             std::vector<int32_t> m(F.N > 0 ? F.N : 1, -1);
@@ -293,10 +480,8 @@ namespace orbgpu
         {
             orbgpu_ctx *ctx = thread_context();
             const std::vector<MapPointT *> vp1 = pKF1->GetMapPointMatches(), vp2 = pKF2->GetMapPointMatches();
-            PackedFrame p1, p2;
-            p1.pack(*pKF1, (float)pKF1->mnMinX, (float)pKF1->mnMinY, (float)pKF1->mnMaxX, (float)pKF1->mnMaxY, false);
-            p2.pack(*pKF2, (float)pKF2->mnMinX, (float)pKF2->mnMinY, (float)pKF2->mnMaxX, (float)pKF2->mnMaxY, false);
-            DeviceFrameGuard d1(ctx, p1.h), d2(ctx, p2.h);
+            FrameRef d1(ctx, 1, *pKF1, (float)pKF1->mnMinX, (float)pKF1->mnMinY, (float)pKF1->mnMaxX, (float)pKF1->mnMaxY, false);
+            FrameRef d2(ctx, 1, *pKF2, (float)pKF2->mnMinX, (float)pKF2->mnMinY, (float)pKF2->mnMaxX, (float)pKF2->mnMaxY, false);
             std::vector<uint8_t> v1(pKF1->N > 0 ? pKF1->N : 1, 0), v2(pKF2->N > 0 ? pKF2->N : 1, 0);
             for (int i = 0; i < pKF1->N; i++) v1[i] = (vp1[i] && !vp1[i]->isBad()) ? 1 : 0;
             for (int i = 0; i < pKF2->N; i++) v2[i] = (vp2[i] && !vp2[i]->isBad()) ? 1 : 0;
@@ -418,11 +603,9 @@ namespace orbgpu
                 b.locks[i] = pMP->Observations() > 0 ? 1 : 0; // what a later point's :2046-2049 test will see
                 b.angle[i] = LastFrame.mvKeysUn[i].angle;
             }
-            PackedFrame pf;
             bool any_right = false;
             for (int i = 0; i < CurrentFrame.N && !any_right; i++) any_right = CurrentFrame.mvuRight[i] > 0;
-            pf.pack(CurrentFrame, CurrentFrame.mnMinX, CurrentFrame.mnMinY, CurrentFrame.mnMaxX, CurrentFrame.mnMaxY, any_right);
-            DeviceFrameGuard df(ctx, pf.h);
+            FrameRef df(ctx, 0, CurrentFrame, CurrentFrame.mnMinX, CurrentFrame.mnMinY, CurrentFrame.mnMaxX, CurrentFrame.mnMaxY, any_right);
             std::vector<uint8_t> locked(CurrentFrame.N > 0 ? CurrentFrame.N : 1, 0);
             for (int i = 0; i < CurrentFrame.N; i++)
                 locked[i] = (CurrentFrame.mvpMapPoints[i] && CurrentFrame.mvpMapPoints[i]->Observations() > 0) ? 1 : 0;
@@ -460,9 +643,7 @@ namespace orbgpu
                 b.set((int)i, pMP->GetDescriptor(), uv(0), uv(1), radius, nPredictedLevel - 1, nPredictedLevel + 1);
                 b.angle[i] = pKF->mvKeysUn[i].angle;
             }
-            PackedFrame pf;
-            pf.pack(CurrentFrame, CurrentFrame.mnMinX, CurrentFrame.mnMinY, CurrentFrame.mnMaxX, CurrentFrame.mnMaxY, false);
-            DeviceFrameGuard df(ctx, pf.h);
+            FrameRef df(ctx, 0, CurrentFrame, CurrentFrame.mnMinX, CurrentFrame.mnMinY, CurrentFrame.mnMaxX, CurrentFrame.mnMaxY, false);
             std::vector<uint8_t> locked(CurrentFrame.N > 0 ? CurrentFrame.N : 1, 0);
             for (int i = 0; i < CurrentFrame.N; i++) locked[i] = CurrentFrame.mvpMapPoints[i] ? 1 : 0; // :2262-2263
             const ProjResult r = run_projected(ctx, df.f, CurrentFrame.N, b, (float)ORBdist, true, false, false, mbCheckOrientation, nullptr,
@@ -531,11 +712,9 @@ namespace orbgpu
                 b.set(i, pMP->GetDescriptor(), uv(0), uv(1), radius, nPredictedLevel - 1, nPredictedLevel);
                 b.ur[i] = ur;
             }
-            PackedFrame pk;
             bool any_right = false;
             for (int i = 0; i < pKF->N && !any_right; i++) any_right = pKF->mvuRight[i] >= 0;
-            pk.pack(*pKF, (float)pKF->mnMinX, (float)pKF->mnMinY, (float)pKF->mnMaxX, (float)pKF->mnMaxY, any_right);
-            DeviceFrameGuard dk(ctx, pk.h);
+            FrameRef dk(ctx, 1, *pKF, (float)pKF->mnMinX, (float)pKF->mnMinY, (float)pKF->mnMaxX, (float)pKF->mnMaxY, any_right);
             const std::vector<float> inv(pKF->mvInvLevelSigma2.begin(), pKF->mvInvLevelSigma2.end());
             const ProjResult r = run_projected(ctx, dk.f, pKF->N, b, (float)ORBGPU_TH_LOW, false, false, true, false, &inv, nullptr);
             // the map mutations stay on the host, applied in the reference's order (:1502-1523)
@@ -586,9 +765,7 @@ namespace orbgpu
                 const float radius = th * pKF->mvScaleFactors[nPredictedLevel];
                 b.set(iMP, pMP->GetDescriptor(), u, v, radius, nPredictedLevel - 1, nPredictedLevel);
             }
-            PackedFrame pk;
-            pk.pack(*pKF, (float)pKF->mnMinX, (float)pKF->mnMinY, (float)pKF->mnMaxX, (float)pKF->mnMaxY, false);
-            DeviceFrameGuard dk(ctx, pk.h);
+            FrameRef dk(ctx, 1, *pKF, (float)pKF->mnMinX, (float)pKF->mnMinY, (float)pKF->mnMaxX, (float)pKF->mnMaxY, false);
             const ProjResult r = run_projected(ctx, dk.f, pKF->N, b, (float)ORBGPU_TH_LOW, false, false, false, false, nullptr, nullptr);
             int nFused = 0;
             for (int iMP = 0; iMP < nPoints; iMP++) // :1657-1672
@@ -654,9 +831,7 @@ namespace orbgpu
                     const float radius = th * to->mvScaleFactors[nPredictedLevel];
                     b.set(i, pMP->GetDescriptor(), u, v, radius, nPredictedLevel - 1, nPredictedLevel);
                 }
-                PackedFrame pk;
-                pk.pack(*to, (float)to->mnMinX, (float)to->mnMinY, (float)to->mnMaxX, (float)to->mnMaxY, false);
-                DeviceFrameGuard dk(ctx, pk.h);
+                FrameRef dk(ctx, 1, *to, (float)to->mnMinX, (float)to->mnMinY, (float)to->mnMaxX, (float)to->mnMaxY, false);
                 return run_projected(ctx, dk.f, to->N, b, (float)ORBGPU_TH_HIGH, false, false, false, false, nullptr, nullptr).best_idx;
             };
             const std::vector<int32_t> vnMatch1 = direction(pKF2, vpMapPoints1, vbAlreadyMatched1, T1w, S21, N1);
@@ -737,9 +912,7 @@ namespace orbgpu
                 const float radius = th * pKF->mvScaleFactors[nPredictedLevel];
                 b.set(iMP, pMP->GetDescriptor(), u, v, radius, nPredictedLevel - 1, nPredictedLevel);
             }
-            PackedFrame pk;
-            pk.pack(*pKF, (float)pKF->mnMinX, (float)pKF->mnMinY, (float)pKF->mnMaxX, (float)pKF->mnMaxY, false);
-            DeviceFrameGuard dk(ctx, pk.h);
+            FrameRef dk(ctx, 1, *pKF, (float)pKF->mnMinX, (float)pKF->mnMinY, (float)pKF->mnMaxX, (float)pKF->mnMaxY, false);
             std::vector<uint8_t> locked(pKF->N > 0 ? pKF->N : 1, 0);
             for (int k = 0; k < pKF->N; k++) locked[k] = vpMatched[k] ? 1 : 0; // :580-581
             return run_projected(ctx, dk.f, pKF->N, b, ORBGPU_TH_LOW * ratioHamming, true, false, false, false, nullptr, &locked);

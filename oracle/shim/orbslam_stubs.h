@@ -103,6 +103,11 @@ namespace ORB_SLAM3
         cv::Mat descriptor_;
         Eigen::Vector3f worldPos_, normal_;
         float mfMinDistance = 0, mfMaxDistance = 0;
+        long unsigned int mnLastFrameSeen = 0; // MapPoint.h:184 (Tracking::SearchLocalPoints)
+        // the two accessors INTEGRATION.md asks a maintainer to add to MapPoint.h for the device-side isInFrustum (PredictScale reads
+        // the raw mfMaxDistance, MapPoint.cc:699,:726; the public getters only return 0.8 x / 1.2 x of the limits)
+        float GetMinDistanceRaw() { return mfMinDistance; }
+        float GetMaxDistanceRaw() { return mfMaxDistance; }
         CopyableMutex mMutexPos; // taken by the extracted bodies (MapPoint.cc:667, :698)
         std::map<KeyFrame *, std::tuple<int, int>> observations_;
 
@@ -129,6 +134,12 @@ namespace ORB_SLAM3
     class FeatureSet
     {
     public:
+        long unsigned int mnId = next_id_(); // Frame.h:278, KeyFrame.h:243: mnId = nNextId++ in the constructors, kept by copies
+        static long unsigned int next_id_()
+        {
+            static long unsigned int n = 1;
+            return n++;
+        }
         int N = 0;
         std::vector<cv::KeyPoint> mvKeys, mvKeysRight, mvKeysUn;
         std::vector<float> mvuRight;
@@ -177,6 +188,7 @@ namespace ORB_SLAM3
         std::vector<int> stereo_best_idx_, stereo_best_dist_; // filled by ORB_ORACLE_STEREO_COARSE_HOOK
 
         Sophus::SE3f GetPose() const { return mTcw; }
+        Eigen::Vector3f GetCameraCenter() { return mOw; } // Frame.h:135-138
         Sophus::SE3f GetRelativePoseTrl() { return mTrl; }
         void SetPose(const Sophus::SE3f &Tcw) // Frame::SetPose + UpdatePoseMatrices (Frame.cc:600-660): member-wise
         {

@@ -379,6 +379,65 @@ extern "C" int orbgpu_transform(orbgpu_ctx *ctx, const orbgpu_voc *voc, orbgpu_f
     return ORBGPU_OK;
 }
 
+// TemplatedVocabulary::transform(const vector<TDescriptor>&, BowVector&, FeatureVector&, int levelsup) (TemplatedVocabulary.h:
+// 1127-1194) for a bare list of descriptors, host pointers in / host pointers out, ONE synchronisation: what the drop-in
+// vocabulary wrapper (include/orbmatch_b200/ORBVocabulary.hpp) calls from Frame::ComputeBoW / KeyFrame::ComputeBoW.
+extern "C" int orbgpu_transform_descriptors(orbgpu_ctx *ctx, const orbgpu_voc *voc, int32_t n, const uint8_t *desc, int32_t levelsup,
+                                            int32_t *n_words, uint32_t *words, double *values, int32_t *n_nodes, uint32_t *node_ids,
+                                            int32_t *offsets, uint32_t *features)
+{
+    ARG_TRY(ctx && voc && n >= 0 && n_words && n_nodes && (n == 0 || (desc && words && values && node_ids && offsets && features)));
+    int rc = ctx_begin(ctx);
+    if (rc) return rc;
+    *n_words = 0;
+    *n_nodes = 0;
+    if (offsets) offsets[0] = 0;
+    if (n == 0) return ORBGPU_OK;
+    const size_t N = (size_t)n;
+    int cap = 1;
+    while (cap < n) cap <<= 1;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+    const size_t o_desc = take(N * 32), o_w = take(N * 4), o_nid = take(N * 4), o_wt = take(N * 8), o_fvn = take(N * 4), o_fvo = take((N + 1) * 4),
+                 o_fvf = take(N * 4), o_bw = take(N * 4), o_bv = take(N * 8), o_tmp = take((N + 1) * 4), o_sk = take((size_t)cap * 8),
+                 o_meta = take(64);
+    rc = arena_reserve(ctx, off + 256);
+    if (rc) return rc;
+    char *D = (char *)arena_take(ctx, off);
+    if (!D) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
+    CU_TRY(cudaMemcpyAsync(D + o_desc, desc, N * 32, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t *d_w = (uint32_t *)(D + o_w), *d_nid = (uint32_t *)(D + o_nid);
+    double *d_wt = (double *)(D + o_wt);
+    voc_transform_kernel<<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>(n, (const uint4 *)(D + o_desc), voc->node_desc, voc->child_offsets,
+                                                                       voc->child_ids, voc->weight, voc->word_id, voc->L, levelsup, d_w, d_nid,
+                                                                       d_wt, ctx->d_counters);
+    LAUNCH_COUNT(ctx);
+    const size_t smem = (size_t)cap * 8;
+    if (smem <= 160 * 1024) {
+        featvec_bow_build_kernel<<<2, SORT_THREADS, smem, ctx->stream>>>(0, n, cap, d_nid, d_w, d_wt, nullptr, (uint32_t *)(D + o_fvn),
+                                                                       (int32_t *)(D + o_fvo), (uint32_t *)(D + o_fvf), (uint32_t *)(D + o_bw),
+                                                                       (int32_t *)(D + o_tmp), (double *)(D + o_bv), (int32_t *)(D + o_meta));
+        LAUNCH_COUNT(ctx);
+    } else {
+        for (int job = 0; job < 2; job++) {
+            featvec_bow_build_kernel<<<1, SORT_THREADS, 0, ctx->stream>>>(job, n, cap, d_nid, d_w, d_wt, (unsigned long long *)(D + o_sk),
+                                                                        (uint32_t *)(D + o_fvn), (int32_t *)(D + o_fvo), (uint32_t *)(D + o_fvf),
+                                                                        (uint32_t *)(D + o_bw), (int32_t *)(D + o_tmp), (double *)(D + o_bv),
+                                                                        (int32_t *)(D + o_meta));
+            LAUNCH_COUNT(ctx);
+        }
+    }
+    CU_TRY(cudaGetLastError());
+    int32_t meta[4] = {0, 0, 0, 0}; // n_nodes, total features, max node size, n_words
+    const OutPiece out[6] = {{meta, D + o_meta, sizeof(meta)}, {words, D + o_bw, N * 4}, {values, D + o_bv, N * 8},
+                             {node_ids, D + o_fvn, N * 4}, {offsets, D + o_fvo, (N + 1) * 4}, {features, D + o_fvf, N * 4}};
+    rc = ctx_download(ctx, out, 6);
+    if (rc) return rc;
+    *n_nodes = meta[0];
+    *n_words = meta[3];
+    return ORBGPU_OK;
+}
+
 extern "C" int orbgpu_bowvector_download(orbgpu_ctx *ctx, const orbgpu_frame *f, int32_t *n_words, uint32_t *words, double *values)
 {
     ARG_TRY(ctx && f && n_words);

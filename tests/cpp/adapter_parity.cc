@@ -13,6 +13,19 @@
 #include "ORBmatcher.h" // the reference's header (stubs resolve MapPoint.h / KeyFrame.h / Frame.h)
 #include "orbmatch_b200/ORBmatcher.hpp"
 
+// the reference's vocabulary (DBoW2, compiled unmodified) and the drop-in wrapper that overrides its transform
+#include "Thirdparty/DBoW2/DBoW2/FORB.h"
+namespace std
+{
+    template <>
+    struct pair<cv::Mat, DBoW2::FORB> // TemplatedVocabulary.h:435 declares a vector of this pair with abstract FORB (unused member)
+    {
+    };
+}
+#include "Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h"
+#include "Thirdparty/DBoW2/DUtils/Random.h"
+#include "orbmatch_b200/ORBVocabulary.hpp"
+
 using namespace ORB_SLAM3;
 typedef orbgpu::ORBmatcherT<Frame, KeyFrame, MapPoint> GpuMatcher;
 
@@ -451,6 +464,98 @@ int main()
         for (int i = 0; i < 32; i++) { a.ptr<uint8_t>()[i] = (uint8_t)(rng() & 0xFF); b.ptr<uint8_t>()[i] = (uint8_t)(rng() & 0xFF); }
         EXPECT(ORBmatcher::DescriptorDistance(a, b) == GpuMatcher::DescriptorDistance(a, b), "DescriptorDistance");
     }
+    // ---- Tracking::SearchLocalPoints: Frame::isInFrustum (the reference's own text) + SearchByProjection on the host, against the
+    // adapter's single device call, with the adapter's checker counting every isInFrustum disagreement
+    {
+        Scene A, B;
+        build_scene(A, 91, true); build_scene(B, 91, true);
+        int toMatchA = 0, toMatchB = 0, nA = 0, nB = 0;
+        for (Scene *S : {&A, &B})
+        {
+            Frame &F = S->Cur;
+            F.SetPose(F.mTcw); // fills mRcw / mtcw / mOw like Frame::UpdatePoseMatrices
+            for (int i = 0; i < F.N; i++) F.mvpMapPoints[i] = nullptr;
+            for (size_t i = 0; i < S->vp.size(); i++)
+            {
+                MapPoint *p = S->vp[i];
+                p->mnLastFrameSeen = (i % 11 == 3) ? F.mnId : 0; // already matched in this frame: not tested (Tracking.cc:4133)
+                p->mbTrackInView = false;
+                const float d = (p->worldPos_ - F.mOw).norm();
+                p->mfMaxDistance = d * F.mvScaleFactors[i % 8] * (i % 13 == 5 ? 0.4f : 1.0f); // some beyond the distance invariance
+                p->mfMinDistance = p->mfMaxDistance / 3.6f;
+                Eigen::Vector3f nrm = (p->worldPos_ - F.mOw) / d;
+                if (i % 9 == 4) nrm = Eigen::Vector3f(nrm(1), -nrm(0), 0.2f); // outside the viewing-angle gate
+                p->normal_ = nrm;
+            }
+        }
+        {
+            Frame &F = A.Cur; // the reference's loop (Tracking.cc:4125-4182)
+            for (MapPoint *p : A.vp)
+            {
+                if (p->mnLastFrameSeen == F.mnId) continue;
+                if (p->isBad()) continue;
+                if (F.isInFrustum(p, 0.5f)) toMatchA++;
+            }
+            ORBmatcher ref(0.8f, true);
+            nA = ref.SearchByProjection(F, A.vp, 3.0f, false, 50.0f);
+        }
+        {
+            orbgpu::frustum_report() = orbgpu::FrustumReport();
+            orbgpu::frustum_report().enabled = true;
+            GpuMatcher gpu(0.8f, true);
+            nB = gpu.SearchLocalPoints(B.Cur, B.vp, 3.0f, false, 50.0f, 0.5f, &toMatchB);
+            orbgpu::frustum_report().enabled = false;
+        }
+        bool iv = true;
+        for (size_t i = 0; i < A.vp.size(); i++) iv = iv && A.vp[i]->mbTrackInView == B.vp[i]->mbTrackInView;
+        const orbgpu::FrustumReport &rep = orbgpu::frustum_report();
+        std::printf("SearchLocalPoints: ref %d matches / %d in view, gpu %d / %d; isInFrustum checker: %lu points, %lu in-view, %lu level, %lu projection disagreements\n",
+                    nA, toMatchA, nB, toMatchB, rep.points, rep.in_view_mismatch, rep.level_mismatch, rep.projection_mismatch);
+        EXPECT(nA == nB && toMatchA == toMatchB && iv && tags(A.Cur.mvpMapPoints) == tags(B.Cur.mvpMapPoints) && nA > 100 && toMatchA > 300,
+               "SearchLocalPoints (isInFrustum + SearchByProjection fused) F.mvpMapPoints / mbTrackInView / counts");
+        EXPECT(rep.points > 1000 && rep.in_view_mismatch == 0 && rep.level_mismatch == 0 && rep.projection_mismatch == 0,
+               "device isInFrustum vs the reference's host isInFrustum: zero disagreements");
+    }
+    // ---- ORBVocabulary::transform (TemplatedVocabulary.h:1127-1194): the reference's own code against the drop-in override
+    {
+        typedef DBoW2::TemplatedVocabulary<DBoW2::FORB::TDescriptor, DBoW2::FORB> RefVoc;
+        typedef orbgpu::ORBVocabularyT<DBoW2::FORB::TDescriptor, DBoW2::FORB> GpuVoc;
+        DUtils::Random::SeedRandOnce(7);
+        // training set: 40 "images" of 300 descriptors drawn around 500 prototypes
+        std::vector<cv::Mat> proto(500);
+        for (auto &m : proto) { m.create(1, 32, CV_8U); for (int b = 0; b < 32; b++) m.ptr<uint8_t>()[b] = (uint8_t)(rng() & 0xFF); }
+        auto noisy = [&](int flips) {
+            cv::Mat d = proto[rng() % proto.size()].clone();
+            for (int f = 0; f < flips; f++) { int bit = (int)(rng() % 256); d.ptr<uint8_t>()[bit >> 3] ^= (uint8_t)(1 << (bit & 7)); }
+            return d;
+        };
+        std::vector<std::vector<cv::Mat>> training(40);
+        for (auto &img : training) for (int i = 0; i < 300; i++) img.push_back(noisy((int)(rng() % 12)));
+        GpuVoc voc(6, 4, DBoW2::TF_IDF, DBoW2::L1_NORM);
+        voc.create(training); // the reference's create() (inherited)
+        std::vector<cv::Mat> feats;
+        for (int i = 0; i < 2000; i++) feats.push_back(noisy((int)(rng() % 20)));
+        bool all = true;
+        size_t words = 0, nodes = 0;
+        for (int levelsup = 0; levelsup <= 5; levelsup++)
+        {
+            DBoW2::BowVector vA, vB;
+            DBoW2::FeatureVector fA, fB;
+            voc.RefVoc::transform(feats, vA, fA, levelsup); // the reference's implementation, statically bound
+            voc.transform(feats, vB, fB, levelsup);         // the device override (virtual dispatch)
+            all = all && vA == vB && fA == fB && !vA.empty();
+            words = vA.size(); nodes = fA.size();
+        }
+        std::printf("ORBVocabulary::transform: %u-word vocabulary, 2000 features -> %zu words, %zu nodes at levelsup 5; bit-exact at levelsup 0..5: %d\n",
+                    voc.size(), words, nodes, (int)all);
+        EXPECT(all && voc.size() > 500, "ORBVocabulary::transform BowVector (bit-exact doubles) / FeatureVector maps");
+        DBoW2::BowVector e1; DBoW2::FeatureVector e2;
+        voc.transform(std::vector<cv::Mat>(), e1, e2, 4);
+        EXPECT(e1.empty() && e2.empty(), "transform of an empty feature list");
+    }
+    // the thread's device-frame cache served the repeated key frames / frames of the cases above
+    std::printf("device frame cache: %lu hits, %lu misses\n", orbgpu::frame_cache().hits, orbgpu::frame_cache().misses);
+    EXPECT(orbgpu::frame_cache().hits > 0, "frame cache hits");
     { // SearchByNN (defined by this repo): against a loop over the reference's own DescriptorDistance with SearchByBoW's accept rule
         const int nq = 700, nd = 3000;
         cv::Mat Q(nq, 32, CV_8U), D(nd, 32, CV_8U);
