@@ -443,7 +443,10 @@ def bench_reloc(E, args):
             "l2": "L2 flushed between calls"}
 
 
-def bench_c4(E, args, K, W):
+def bench_c4(E, args, K, W, shared=False):
+    """shared=False: BASELINE's config, 4096 INDEPENDENT key-frame pairs (8192 key frames, 870 MB resident).  shared=True: the
+    shared-key-frame variant of SURVEY 8(d) -- 512 key frames, each against its 8 nearest neighbours (the shape of
+    LocalMapping::CreateNewMapPoints): the same 4096 pairs over a 54 MB key-frame set that stays L2 resident within a step."""
     torch, dist, matcher, synth = E.torch, E.dist, E.matcher, E.synth
     from orb_slam3_comments_ghr_b200.sharding import TriangulationGather, shard_bounds
     dev, rank, world = E.dev, E.rank, E.world
@@ -452,8 +455,14 @@ def bench_c4(E, args, K, W):
         raise SystemExit("--pairs must be divisible by the number of GPUs")
     lo, hi = shard_bounds(P_total, rank, world)
     P = hi - lo
-    log(f"c4: generating {P} keyframe pairs x {C4_FEAT} features")
-    case = c4_case(synth, C4_SEED + rank, P)  # independent pairs: every rank generates (and holds) the key frames of its own pairs
+    if shared:
+        log(f"c4 (shared key frames): {P_total // 8} key frames x 8 neighbours")
+        case = synth.fill_geometry(synth.make_triangulation_case_shared(C4_SEED, n_kf=P_total // 8, n_neighbours=8, n_feat=C4_FEAT))
+        for name in ("kf1", "kf2", "ep", "f12", "T1w", "T2w"):  # every rank holds the whole (small) set and takes its shard of the pair list
+            setattr(case, name, np.ascontiguousarray(getattr(case, name)[lo:hi]))
+    else:
+        log(f"c4: generating {P} keyframe pairs x {C4_FEAT} features")
+        case = c4_case(synth, C4_SEED + rank, P)  # independent pairs: every rank generates (and holds) the key frames of its own pairs
     log("c4: uploading the keyframe set, peer buffers")
     tg = TriangulationGather(matcher, case.kfs, P_total, C4_FEAT, rank, world, dev, 0.6, False, use_graph=args.graph)
     tg.ctx.set_triangulation_engine(args.tri_engine)
@@ -570,7 +579,11 @@ def bench_c4(E, args, K, W):
                 cpu = {"value": None, "error": repr(e)}
         line = {"metric": "frame_pairs_matched_per_s", "value": value, "unit": "frame_pairs/s", "n_gpus": world, "steps": K4, "warmup": max(W, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
-                "data": "synthetic", "config": workload_config("c4", args), "clocks": clocks, "e2e": e2e,
+                "data": "synthetic", "config": workload_config("c4", args) if not shared else
+                {"workload": f"C4 shared-key-frame variant: {P_total // 8} keyframes x 8 neighbours = {P_total} pairs x {C4_FEAT} features "
+                             "(LocalMapping::CreateNewMapPoints shape, LocalMapping.cc:556-630)", "pairs": P_total, "n_feat": C4_FEAT,
+                 "l2": "L2 flushed (512 MiB write) between timed steps; within a step every key frame is read 16 times and stays in L2"},
+                "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(K4), "gpu_launches_note": "one triangulation_stream_kernel per step (graph replays): search, compaction, peer stores and the epoch wait in one launch",
                 "roofline": roof, "cpu_baseline": cpu, "engine": args.tri_engine if args.tri_engine else 2, **extra}
     del tg
@@ -638,6 +651,28 @@ def bench_single_frame(E):
         r = timeit(lambda: cpu.search_by_bow_kf_f(kf, f, bc.kf_mp_valid, 0.7, 1), n=10, warm=2)
         out["c3_bow_l%d" % levelsup] = row(f"C3 SearchByBoW KeyFrame-Frame, 2000 x 2000 features, levelsup={levelsup}"
                                            + (" (one root bucket: 1.9 M comparisons)" if levelsup == 4 else ""), g, None, r, ncmp)
+        if levelsup == 2:
+            # the relocalisation loop (Tracking.cc:4469-4495): one frame against K candidate key frames in ONE call
+            Kc = 32
+            dks, valids = [], []
+            for k in range(Kc):
+                ck = synth.make_bow_case(3100 + k, voc, 2000)
+                dkk = ctx.upload_frame(ck.kf)
+                dkk.transform(dv, levelsup, True)
+                dks.append(dkk)
+                valids.append(ck.kf_mp_valid)
+            gb = timeit(lambda: m.SearchByBoWBatch(dks, df, valids), n=20, warm=3)
+            ncb = ctx.last_comparisons
+            bytes_pair = 32 * (2000 + 2000) + 12 * 4000 + 4 * 4000 + 4 * 2000  # descriptors + keypoints + CSR + output
+            out["c3_bow_batch32"] = {"workload": f"one frame against {Kc} candidate key frames (relocalisation loop) in one call, 2000 features each, levelsup=2",
+                                     "gpu_us_per_call": gb, "gpu_us_per_pair": gb / Kc, "frame_pairs_per_s": Kc / (gb * 1e-6),
+                                     "gpu_us_per_pair_single_calls": g, "cpu_us_per_pair": r, "cpu_kind": kind, "comparisons": int(ncb),
+                                     "roofline_hbm": {"bound": "hbm", "bytes_per_pair": bytes_pair, "achieved": Kc * bytes_pair / (gb * 1e-6) / 1e9,
+                                                      "peak": float(E.peaks.get("hbm_gbs", 6650.0)), "unit": "GB/s",
+                                                      "frac": Kc * bytes_pair / (gb * 1e-6) / 1e9 / float(E.peaks.get("hbm_gbs", 6650.0))},
+                                     "note": "the K searches are enqueued back to back with one upload, one download and one synchronisation; each is still "
+                                             "a few ~100-CTA launches, so the call is launch-bound far below the HBM roofline (stated, not claimed)"}
+            del dks
     return out
 
 
@@ -746,6 +781,11 @@ def main():
                 secondary["c4"] = {"error": repr(e)}
                 if world > 1:
                     raise
+            if world == 1:
+                try:
+                    secondary["c4_shared_kf"] = bench_c4(E, args, K, W, shared=True)
+                except Exception as e:
+                    secondary["c4_shared_kf"] = {"error": repr(e)}
             if world == 1:
                 try:
                     secondary.update(bench_single_frame(E))

@@ -267,6 +267,13 @@ int orbgpu_featvec_download(orbgpu_ctx *ctx, const orbgpu_frame *f, int32_t *n_n
  * (vpMapPointMatches[i] = vpMapPointsKF[match]), -1 none. */
 int orbgpu_search_by_bow_kf_f(orbgpu_ctx *ctx, const orbgpu_frame *kf, const orbgpu_frame *f, const uint8_t *kf_mp_valid,
                               float nnratio, int32_t check_ori, int32_t *match_f2kf, int32_t *nmatches);
+/* One frame against n_kf candidate key frames -- the relocalisation loop (Tracking.cc:4469-4495: SearchByBoW(vpCandidateKFs[i],
+ * mCurrentFrame, vvpMapPointMatches[i]) for every candidate) and the loop / merge candidate loops of LoopClosing -- in ONE call: one
+ * upload of the validity masks, the searches enqueued back to back, one download, one synchronisation.  match_f2kf [n_kf][f.N],
+ * nmatches [n_kf]; results identical to n_kf separate calls. */
+int orbgpu_search_by_bow_kf_f_batch(orbgpu_ctx *ctx, int32_t n_kf, const orbgpu_frame *const *kfs, const orbgpu_frame *f,
+                                    const uint8_t *const *kf_mp_valid, float nnratio, int32_t check_ori, int32_t *match_f2kf,
+                                    int32_t *nmatches);
 /* KeyFrame <-> KeyFrame variant (ORBmatcher.cc:890-1043): strict best < TH_LOW, vbMatched2.
  * match_12 [kf1.N] out: index of the KF2 feature matched to KF1 feature i, -1 none. */
 int orbgpu_search_by_bow_kf_kf(orbgpu_ctx *ctx, const orbgpu_frame *kf1, const orbgpu_frame *kf2,

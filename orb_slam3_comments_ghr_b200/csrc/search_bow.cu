@@ -8,6 +8,9 @@
 // the other FeatureVector), keyframe features replayed in order inside the CTA, threads over the
 // partner's features with a block-wide lexicographic (distance, position) top-2.  The rotation
 // histogram is accumulated with atomics (bin sizes are order independent) and culled afterwards.
+#include <cstring>
+#include <vector>
+
 #include "internal.cuh"
 
 namespace {
@@ -385,32 +388,34 @@ __global__ void bow_cull_kernel(int n, int check_ori, int32_t *__restrict__ matc
     if (threadIdx.x == 0) *nmatches -= removed;
 }
 
-int run_bow(orbgpu_ctx *ctx, int mode, const orbgpu_frame *kf, const orbgpu_frame *f, const uint8_t *kf_valid, const uint8_t *f_valid,
-            float nnratio, int check_ori, int32_t *match_out, int32_t *nmatches)
+// arena bytes one pair needs (scratch + masks); the match vector and the histogram block are the caller's
+size_t bow_scratch_bytes(const orbgpu_frame *kf, const orbgpu_frame *f, int mode, bool *big_out)
 {
-    int rc = ctx_begin(ctx);
-    if (rc) return rc;
-    *nmatches = 0;
-    const int n_out = (mode == 0) ? f->n : kf->n; // size of the match vector
-    if (n_out == 0) return ORBGPU_OK;
-    const size_t ob = align256((size_t)n_out * 4);
+    const int n_out = (mode == 0) ? f->n : kf->n;
     // fixed-point path for big node pairs (both sizes are known on the host as launch hints)
     const bool big = kf->fv_max_node >= BOW_BIG_N1 && f->fv_max_node >= BOW_BIG_N2 && kf->fv_n_nodes > 0 && f->fv_n_nodes > 0 &&
                      ((size_t)f->fv_max_node + 2 * (size_t)kf->fv_max_node) * 4 <= 200 * 1024; // else: replay kernel for every node
-    rc = arena_reserve(ctx, 2 * ob + align256(kf->n + 1) + 2 * align256(f->n + 1) + 1024 +
-                                (big ? align256((size_t)kf->n * BOW_LIST_K * 4) + align256((size_t)kf->n * 4) : 0));
-    if (rc) return rc;
-    int32_t *d_match = (int32_t *)arena_take(ctx, (size_t)n_out * 4), *d_bin = (int32_t *)arena_take(ctx, (size_t)n_out * 4);
-    uint8_t *d_kfv = (uint8_t *)arena_take(ctx, kf->n + 1), *d_fv = (uint8_t *)arena_take(ctx, f->n + 1),
-            *d_m2 = (uint8_t *)arena_take(ctx, f->n + 1);
-    int *d_hist = (int *)arena_take(ctx, 256); // [0..29] histogram, [32] nmatches
-    int *d_nm = d_hist + 32;
+    if (big_out) *big_out = big;
+    return align256((size_t)n_out * 4) + align256(f->n + 1) + 256 +
+           (big ? align256((size_t)kf->n * BOW_LIST_K * 4) + align256((size_t)kf->n * 4) : 0);
+}
+
+// enqueues one SearchByBoW on the context's stream: masks already on the device, results left in d_match [n_out] and d_hist[32]
+// (= nmatches).  The arena must hold bow_scratch_bytes() more bytes.
+int bow_enqueue(orbgpu_ctx *ctx, int mode, const orbgpu_frame *kf, const orbgpu_frame *f, const uint8_t *d_kfv, const uint8_t *d_fv,
+                float nnratio, int check_ori, int32_t *d_match, int *d_hist)
+{
+    const int n_out = (mode == 0) ? f->n : kf->n;
+    bool big = false;
+    bow_scratch_bytes(kf, f, mode, &big);
+    int32_t *d_bin = (int32_t *)arena_take(ctx, (size_t)n_out * 4);
+    uint8_t *d_m2 = (uint8_t *)arena_take(ctx, f->n + 1);
+    if (!d_bin || !d_m2) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
+    int *d_nm = d_hist + 32; // [0..29] histogram, [32] nmatches
     CU_TRY(cudaMemsetAsync(d_match, 0xFF, (size_t)n_out * 4, ctx->stream));
     CU_TRY(cudaMemsetAsync(d_bin, 0xFF, (size_t)n_out * 4, ctx->stream));
     CU_TRY(cudaMemsetAsync(d_hist, 0, 256, ctx->stream));
     CU_TRY(cudaMemsetAsync(d_m2, 0, f->n + 1, ctx->stream));
-    if (kf->n) CU_TRY(cudaMemcpyAsync(d_kfv, kf_valid, kf->n, cudaMemcpyHostToDevice, ctx->stream));
-    if (mode == 1 && f->n) CU_TRY(cudaMemcpyAsync(d_fv, f_valid, f->n, cudaMemcpyHostToDevice, ctx->stream));
     if (kf->fv_n_nodes > 0 && f->fv_n_nodes > 0) {
         const int threads = f->fv_max_node <= 32 ? 32 : (f->fv_max_node <= 512 ? 128 : (f->fv_max_node <= 1024 ? 256 : 1024));
         // staging capacity: the largest partner node, as far as shared memory goes (33 B per descriptor)
@@ -429,6 +434,7 @@ int run_bow(orbgpu_ctx *ctx, int mode, const orbgpu_frame *kf, const orbgpu_fram
         LAUNCH_COUNT(ctx);
         if (big) {
             uint32_t *d_lists = (uint32_t *)arena_take(ctx, (size_t)kf->n * BOW_LIST_K * 4), *d_meta = (uint32_t *)arena_take(ctx, (size_t)kf->n * 4);
+            if (!d_lists || !d_meta) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
             const int n1_cap = kf->fv_max_node, n2_cap = f->fv_max_node;
             const size_t smem_big = ((size_t)n2_cap + 2 * (size_t)n1_cap) * 4;
             const int blocks = (int)(((size_t)kf->n * 32 + 255) / 256);
@@ -449,7 +455,68 @@ int run_bow(orbgpu_ctx *ctx, int mode, const orbgpu_frame *kf, const orbgpu_fram
         LAUNCH_COUNT(ctx);
         CU_TRY(cudaGetLastError());
     }
-    const OutPiece out[2] = {{match_out, d_match, (size_t)n_out * 4}, {nmatches, d_nm, 4}};
+    return ORBGPU_OK;
+}
+
+int run_bow(orbgpu_ctx *ctx, int mode, const orbgpu_frame *kf, const orbgpu_frame *f, const uint8_t *kf_valid, const uint8_t *f_valid,
+            float nnratio, int check_ori, int32_t *match_out, int32_t *nmatches)
+{
+    int rc = ctx_begin(ctx);
+    if (rc) return rc;
+    *nmatches = 0;
+    const int n_out = (mode == 0) ? f->n : kf->n; // size of the match vector
+    if (n_out == 0) return ORBGPU_OK;
+    rc = arena_reserve(ctx, bow_scratch_bytes(kf, f, mode, nullptr) + align256((size_t)n_out * 4) + align256(kf->n + 1) + align256(f->n + 1) + 1024);
+    if (rc) return rc;
+    int32_t *d_match = (int32_t *)arena_take(ctx, (size_t)n_out * 4);
+    uint8_t *d_kfv = (uint8_t *)arena_take(ctx, kf->n + 1), *d_fv = (uint8_t *)arena_take(ctx, f->n + 1);
+    int *d_hist = (int *)arena_take(ctx, 256);
+    if (!d_match || !d_kfv || !d_fv || !d_hist) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
+    if (kf->n) CU_TRY(cudaMemcpyAsync(d_kfv, kf_valid, kf->n, cudaMemcpyHostToDevice, ctx->stream));
+    if (mode == 1 && f->n) CU_TRY(cudaMemcpyAsync(d_fv, f_valid, f->n, cudaMemcpyHostToDevice, ctx->stream));
+    rc = bow_enqueue(ctx, mode, kf, f, d_kfv, d_fv, nnratio, check_ori, d_match, d_hist);
+    if (rc) return rc;
+    const OutPiece out[2] = {{match_out, d_match, (size_t)n_out * 4}, {nmatches, d_hist + 32, 4}};
+    return ctx_download(ctx, out, 2);
+}
+
+// One frame against K candidate key frames (Tracking::Relocalization, Tracking.cc:4469-4495; the loop / merge candidate loops of
+// LoopClosing): the K searches are enqueued back to back on the context's stream with ONE upload of the K validity masks, ONE
+// download of the K match vectors and ONE synchronisation.
+int run_bow_batch(orbgpu_ctx *ctx, int K, const orbgpu_frame *const *kfs, const orbgpu_frame *f, const uint8_t *const *kf_valid, float nnratio,
+                  int check_ori, int32_t *match_out, int32_t *nmatches)
+{
+    int rc = ctx_begin(ctx);
+    if (rc) return rc;
+    for (int k = 0; k < K; k++) nmatches[k] = 0;
+    const int n_out = f->n;
+    if (n_out == 0 || K == 0) return ORBGPU_OK;
+    size_t total = align256((size_t)K * n_out * 4) + align256((size_t)K * 256) + 1024, mask_bytes = 0;
+    std::vector<size_t> mask_off(K);
+    for (int k = 0; k < K; k++) {
+        total += bow_scratch_bytes(kfs[k], f, 0, nullptr);
+        mask_off[k] = mask_bytes;
+        mask_bytes += align256(kfs[k]->n + 1);
+    }
+    rc = stage_reserve(ctx, mask_bytes + 256);
+    if (rc) return rc;
+    rc = arena_reserve(ctx, total + align256(mask_bytes) + align256(f->n + 1));
+    if (rc) return rc;
+    int32_t *d_match = (int32_t *)arena_take(ctx, (size_t)K * n_out * 4);
+    int *d_hist = (int *)arena_take(ctx, (size_t)K * 256);
+    uint8_t *d_masks = (uint8_t *)arena_take(ctx, mask_bytes + 1), *d_fv = (uint8_t *)arena_take(ctx, f->n + 1);
+    if (!d_match || !d_hist || !d_masks || !d_fv) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
+    for (int k = 0; k < K; k++)
+        if (kfs[k]->n) memcpy(ctx->h_stage + mask_off[k], kf_valid[k], kfs[k]->n);
+    CU_TRY(cudaMemcpyAsync(d_masks, ctx->h_stage, mask_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    for (int k = 0; k < K; k++) {
+        rc = bow_enqueue(ctx, 0, kfs[k], f, d_masks + mask_off[k], d_fv, nnratio, check_ori, d_match + (size_t)k * n_out, d_hist + (size_t)k * 64);
+        if (rc) return rc;
+    }
+    // nmatches live at d_hist[k * 64 + 32]: gather them with one strided copy
+    int32_t *d_nm = (int32_t *)d_masks; // the masks have been consumed by the kernels enqueued above (stream order)
+    CU_TRY(cudaMemcpy2DAsync(d_nm, 4, d_hist + 32, 256, 4, K, cudaMemcpyDeviceToDevice, ctx->stream));
+    const OutPiece out[2] = {{match_out, d_match, (size_t)K * n_out * 4}, {nmatches, d_nm, (size_t)K * 4}};
     return ctx_download(ctx, out, 2);
 }
 
@@ -493,6 +560,16 @@ extern "C" int orbgpu_search_by_bow_kf_kf(orbgpu_ctx *ctx, const orbgpu_frame *k
     ARG_TRY(ctx && kf1 && kf2 && nmatches && (kf1->n == 0 || (match_12 && kf1_mp_valid)) && (kf2->n == 0 || kf2_mp_valid));
     ARG_TRY(kf2->n < (1 << 20));
     return run_bow(ctx, 1, kf1, kf2, kf1_mp_valid, kf2_mp_valid, nnratio, check_ori, match_12, nmatches);
+}
+
+extern "C" int orbgpu_search_by_bow_kf_f_batch(orbgpu_ctx *ctx, int32_t n_kf, const orbgpu_frame *const *kfs, const orbgpu_frame *f,
+                                               const uint8_t *const *kf_mp_valid, float nnratio, int32_t check_ori, int32_t *match_f2kf,
+                                               int32_t *nmatches)
+{
+    ARG_TRY(ctx && f && n_kf >= 0 && (n_kf == 0 || (kfs && kf_mp_valid && nmatches)) && (f->n == 0 || n_kf == 0 || match_f2kf));
+    ARG_TRY(f->n < (1 << 20));
+    for (int k = 0; k < n_kf; k++) ARG_TRY(kfs[k] && (kfs[k]->n == 0 || kf_mp_valid[k]));
+    return run_bow_batch(ctx, n_kf, kfs, f, kf_mp_valid, nnratio, check_ori, match_f2kf, nmatches);
 }
 
 int search_bow_device_init()

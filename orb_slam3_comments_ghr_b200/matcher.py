@@ -537,6 +537,22 @@ class ORBmatcher:
                                                              self.mfNNratio, int(self.mbCheckOrientation), _p(out, i32p), C.byref(nm)))
         return nm.value, out
 
+    # one frame against K candidate key frames (Tracking::Relocalization's loop over SearchByBoW, Tracking.cc:4469-4495) in one call
+    # -> (nmatches[K], vpMapPointMatches[K, F.N] as KF feature indices)
+    def SearchByBoWBatch(self, KFs, F: DeviceFrame, kf_mp_valids):
+        K = len(KFs)
+        vs = [as_u8(v) for v in kf_mp_valids]
+        out = np.full((max(K, 1), max(F.n, 1)), -1, dtype=np.int32)
+        nm = np.zeros(max(K, 1), dtype=np.int32)
+        hs = (C.c_void_p * max(K, 1))(*[k.handle for k in KFs])
+        ps = (u8p * max(K, 1))(*[_p(v, u8p) for v in vs])
+        L = load_library()
+        L.orbgpu_search_by_bow_kf_f_batch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(u8p), C.c_float,
+                                                      C.c_int32, i32p, i32p]
+        _check(L.orbgpu_search_by_bow_kf_f_batch(self.ctx.handle, K, hs, F.handle, ps, self.mfNNratio, int(self.mbCheckOrientation),
+                                                 _p(out, i32p), _p(nm, i32p)))
+        return nm[:K], out[:K, :F.n]
+
     # ORBmatcher.h:72, batched over pairs -> (nmatches[P], vMatches12[P, n_feat])
     def SearchForTriangulation(self, kfs: DeviceKfSet, kf1, kf2, ep, f12, bOnlyStereo: bool = False, bCoarse: bool = False, out=None):
         """out: optional caller-owned (vMatches12[P, n_feat] int32, nmatches[P] int32) host buffers -- pinned memory makes the

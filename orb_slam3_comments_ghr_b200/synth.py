@@ -491,6 +491,61 @@ def make_triangulation_case(seed: int, n_pairs: int = 64, n_feat: int = 2000, n_
     return TriangulationCase(kfs, kf1, kf2, T1w, T2w, K_PINHOLE.copy())
 
 
+def make_triangulation_case_shared(seed: int, n_kf: int = 512, n_neighbours: int = 8, n_feat: int = 2000, n_nodes: int = 100,
+                                   mp_frac: float = 0.5, node_base: int = 11) -> TriangulationCase:
+    """C4, shared-key-frame variant (SURVEY 8(d)): the shape of LocalMapping::CreateNewMapPoints (LocalMapping.cc:556-630) -- every
+    key frame is matched against its n_neighbours best covisible key frames.  n_kf key frames along a trajectory observe a common
+    landmark cloud (a sliding window of it each, so neighbours share most of their landmarks); pair list = (i, i + j) for j = 1 ..
+    n_neighbours (wrapping around), i.e. n_kf * n_neighbours pairs over only n_kf key frames: the key-frame set is small (32 MB at
+    512 x 2000) and every key frame is read 2 * n_neighbours times per step."""
+    rng = np.random.default_rng(seed)
+    nk = n_kf
+    sf, s2 = orb_scale_tables(8)
+    desc = random_descriptors(rng, nk * n_feat).reshape(nk, n_feat, 32)
+    xy = random_keypoints(rng, nk * n_feat).reshape(nk, n_feat, 2)
+    octv = random_octaves(rng, nk * n_feat).reshape(nk, n_feat)
+    ang = quantise(rng.uniform(0, 360, nk * n_feat) % 360.0).reshape(nk, n_feat)
+    node = (node_base + rng.integers(0, n_nodes, nk * n_feat)).astype(np.uint32).reshape(nk, n_feat)
+    has_mp = (rng.random((nk, n_feat)) < mp_frac).astype(np.uint8)
+    # trajectory: the camera drifts sideways through a long landmark cloud, 0.12 m per key frame, small rotations
+    R = _small_rotation(rng, nk, max_angle=0.05)
+    cx_world = 0.12 * np.arange(nk)
+    n_win = int(0.6 * n_feat)          # landmarks seen by one key frame
+    step = 30                          # new landmarks per key frame -> neighbours j apart share n_win - 30 j of them
+    n_lm = n_win + step * nk
+    lm_x0 = np.arange(n_lm) / step * 0.12  # a landmark enters the view when the camera reaches it
+    X = np.stack([lm_x0 + rng.uniform(-4, 4, n_lm), rng.uniform(-3, 3, n_lm), rng.uniform(2.5, 12, n_lm)], axis=1)
+    lm_desc = random_descriptors(rng, n_lm)
+    lm_node = (node_base + rng.integers(0, n_nodes, n_lm)).astype(np.uint32)
+    lm_oct = random_octaves(rng, n_lm)
+    lm_ang = rng.uniform(0, 360, n_lm)
+    t_all = np.zeros((nk, 3))
+    for k in range(nk):
+        Cw = np.array([cx_world[k] + 0.5 * n_win / step * 0.12, 0.0, 0.0]) + rng.normal(0, 0.03, 3)
+        t = -R[k] @ Cw
+        t_all[k] = t
+        lm = np.arange(k * step, k * step + n_win)
+        Xc = X[lm] @ R[k].T + t
+        u = FX * Xc[:, 0] / Xc[:, 2] + CX + rng.normal(0, 0.7, n_win)
+        v = FY * Xc[:, 1] / Xc[:, 2] + CY + rng.normal(0, 0.7, n_win)
+        ok = (Xc[:, 2] > 0.5) & (u >= 0) & (u < IMG_W - 0.25) & (v >= 0) & (v < IMG_H - 0.25)
+        slot = rng.permutation(n_feat)[:n_win]
+        d = lm_desc[lm] ^ flip_mask(rng, n_win, rng.choice(np.array([3, 4, 4, 5, 5, 9]), size=n_win))
+        desc[k, slot[ok]] = d[ok]
+        xy[k, slot[ok], 0] = quantise(u[ok])
+        xy[k, slot[ok], 1] = quantise(v[ok])
+        octv[k, slot[ok]] = np.clip(lm_oct[lm][ok] + rng.integers(-1, 2, int(ok.sum())), 0, 7)
+        ang[k, slot[ok]] = quantise((lm_ang[lm][ok] + rng.normal(0, 4.0, int(ok.sum()))) % 360.0)
+        keep = ok & (rng.random(n_win) < 0.9)
+        node[k, slot[keep]] = lm_node[lm][keep]
+    node[rng.random((nk, n_feat)) < 0.01] = np.uint32(0xFFFFFFFF)
+    kfs = HostKfSet(desc, xy, octv, ang, has_mp, node, scale_factors=sf, level_sigma2=s2)
+    kf1 = np.repeat(np.arange(nk), n_neighbours).astype(np.int32)
+    kf2 = ((kf1 + np.tile(np.arange(1, n_neighbours + 1), nk)) % nk).astype(np.int32)
+    Tw = np.concatenate([R.reshape(nk, 9), t_all], axis=1).astype(np.float32)
+    return TriangulationCase(kfs, kf1, kf2, Tw[kf1], Tw[kf2], K_PINHOLE.copy())
+
+
 def triangulation_geometry_numpy(T1w, T2w, K1, K2):
     """fp32 restatement of the host-side pose algebra of ORBmatcher.cc:1053-1071 + Pinhole.cpp:194-197 in
     plain left-to-right matrix form: ep = project(T2w * Cw), F12 = K1^-T [t12]x R12 K2^-1.

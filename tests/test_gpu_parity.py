@@ -726,3 +726,52 @@ def test_search_local_points_fused(ctx, M, oracle, seed, th, far):
     assert n == en and np.array_equal(kp, ekp) and np.array_equal(giv, inv.astype(np.uint8))
     n2, kp2 = m.SearchByProjection(d, mps, th, bool(far), 6.0, c.kp_prior_obs, c.kp_mp)
     assert n2 == n and np.array_equal(kp2, kp) and en > 200
+
+
+@pytest.mark.parametrize("levelsup,K", [(2, 12), (4, 3), (3, 1)])
+def test_search_by_bow_batch(ctx, M, oracle, levelsup, K):
+    """one frame against K candidate key frames in one call (the relocalisation loop, Tracking.cc:4469-4495) == K separate calls ==
+    the oracle, incl. the comparison counter summed over the candidates"""
+    voc = golden_voc()
+    f_host = None
+    kfs, valids, exp = [], [], []
+    total_cmp = 0
+    for k in range(K):
+        c = synth.make_bow_case(2000 + 10 * levelsup + k, voc, 1500 if k % 2 else 2000)
+        if f_host is None:
+            f_host = attach_featvec(oracle, voc, c.f, levelsup)
+        kf = attach_featvec(oracle, voc, c.kf, levelsup)
+        if k > 0:  # candidates that really look like the frame: planted copies of its features
+            rng = np.random.default_rng(k)
+            src = rng.permutation(f_host.n)[: kf.n // 2]
+            kf.desc[: src.size] = synth.planted_copies(rng, f_host.desc[src])
+            kf = attach_featvec(oracle, voc, kf, levelsup)
+        kfs.append(kf)
+        valids.append(c.kf_mp_valid[: kf.n])
+        oracle.reset_comparisons()
+        exp.append(oracle.search_by_bow_kf_f(kf, f_host, valids[-1], 0.7, 1))
+        total_cmp += oracle.comparisons()
+    df = ctx.upload_frame(f_host)
+    dks = [ctx.upload_frame(kf) for kf in kfs]
+    m = M.ORBmatcher(0.7, True, ctx)
+    nm, out = m.SearchByBoWBatch(dks, df, valids)
+    assert ctx.last_comparisons == total_cmp
+    for k in range(K):
+        assert nm[k] == exp[k][0] and np.array_equal(out[k], exp[k][1]), k
+        n1, m1 = m.SearchByBoW(dks[k], df, valids[k])
+        assert n1 == nm[k] and np.array_equal(m1, out[k])
+    assert int(nm.sum()) > 0
+
+
+def test_triangulation_shared_keyframes(ctx, M, oracle):
+    """C4 shared-key-frame variant (LocalMapping::CreateNewMapPoints: every key frame against its 8 best neighbours): both engines and
+    the compact form against the oracle"""
+    tc = synth.fill_geometry(synth.make_triangulation_case_shared(551, n_kf=24, n_neighbours=8, n_feat=1600))
+    ks = ctx.upload_kfset(tc.kfs)
+    enm, em = oracle.search_for_triangulation_batch(tc.kfs, tc.kf1, tc.kf2, tc.ep, tc.f12, 0, 0, 0, n_threads=os.cpu_count() or 1)
+    for engine in (1, 2):
+        ctx.set_triangulation_engine(engine)
+        nm, m = M.ORBmatcher(0.6, False, ctx).SearchForTriangulation(ks, tc.kf1, tc.kf2, tc.ep, tc.f12)
+        ctx.set_triangulation_engine(0)
+        assert np.array_equal(nm, enm) and np.array_equal(m, em), engine
+    assert enm.shape[0] == 192 and enm[0] > 50 and enm[7] > 20  # nearer neighbours share more landmarks
