@@ -507,6 +507,15 @@ def bench_c4(E, args, K, W, shared=False):
     extra["comparisons_per_step_rank0"] = int(cmp_rank0)
     extra["matches_all_pairs"] = int(cnt.sum().item())
     extra["gather_status"] = tg.status()
+    if world > 1:
+        # what crosses NVLink per step: every rank stores the valid (idx1, idx2) entries (4 B each, 16-byte granules) and the counts
+        # of ITS pairs into the buffers of the N - 1 other ranks, plus one 4-byte epoch flag per peer
+        sent = (world - 1) * (4.0 * extra["matches_all_pairs"] / world + 8.0 * P + 4.0 * P + 4)
+        extra["nvlink_bytes_sent_per_rank_per_step"] = int(sent)
+        extra["nvlink_note"] = ("compact vMatchedPairs: ~%.2f MB leave every rank per step (dense int32 rows would be %.1f MB); at ~700 GB/s per "
+                                "direction that is ~%.1f us, hidden behind the search of the following pairs -- the step time at N > 1 is the "
+                                "kernel's fixed latency (launch + first-pair pipeline fill + last-pair drain ~ 20 us) plus P/N pairs at the "
+                                "single-GPU rate, not the links" % (sent / 1e6, (world - 1) * P * C4_FEAT * 4 / 1e6, sent / 700e3))
     log(f"c4: {ms_per_step * 1e3:.1f} us/step over {K4} steps")
 
     # ---- end to end: pinned host inputs -> device, the sharded search + gather, the vMatchedPairs of ALL pairs back on the host

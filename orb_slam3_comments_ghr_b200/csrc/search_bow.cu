@@ -396,26 +396,36 @@ size_t bow_scratch_bytes(const orbgpu_frame *kf, const orbgpu_frame *f, int mode
     const bool big = kf->fv_max_node >= BOW_BIG_N1 && f->fv_max_node >= BOW_BIG_N2 && kf->fv_n_nodes > 0 && f->fv_n_nodes > 0 &&
                      ((size_t)f->fv_max_node + 2 * (size_t)kf->fv_max_node) * 4 <= 200 * 1024; // else: replay kernel for every node
     if (big_out) *big_out = big;
-    return align256((size_t)n_out * 4) + align256(f->n + 1) + 256 +
-           (big ? align256((size_t)kf->n * BOW_LIST_K * 4) + align256((size_t)kf->n * 4) : 0);
+    (void)n_out;
+    return 256 + (big ? align256((size_t)kf->n * BOW_LIST_K * 4) + align256((size_t)kf->n * 4) : 0);
+}
+// per-pair result / state block, initialised by the caller with two memsets (0xFF part, zero part) -- for a batch, two memsets in all
+struct BowBlock {
+    int32_t *d_match, *d_bin; // [n_out] each, 0xFF
+    int *d_hist;              // [64] zero: [0..29] histogram, [32] nmatches
+    uint8_t *d_m2;            // [f->n + 1] zero
+};
+inline size_t bow_ff_bytes(int n_out) { return 2 * align256((size_t)n_out * 4); }
+inline size_t bow_zero_bytes(int fn) { return 256 + align256((size_t)fn + 1); }
+inline BowBlock bow_block(char *ff, char *zero, int n_out)
+{
+    BowBlock b;
+    b.d_match = (int32_t *)ff; b.d_bin = (int32_t *)(ff + align256((size_t)n_out * 4));
+    b.d_hist = (int *)zero; b.d_m2 = (uint8_t *)(zero + 256);
+    return b;
 }
 
 // enqueues one SearchByBoW on the context's stream: masks already on the device, results left in d_match [n_out] and d_hist[32]
 // (= nmatches).  The arena must hold bow_scratch_bytes() more bytes.
 int bow_enqueue(orbgpu_ctx *ctx, int mode, const orbgpu_frame *kf, const orbgpu_frame *f, const uint8_t *d_kfv, const uint8_t *d_fv,
-                float nnratio, int check_ori, int32_t *d_match, int *d_hist)
+                float nnratio, int check_ori, const BowBlock &blk)
 {
     const int n_out = (mode == 0) ? f->n : kf->n;
     bool big = false;
     bow_scratch_bytes(kf, f, mode, &big);
-    int32_t *d_bin = (int32_t *)arena_take(ctx, (size_t)n_out * 4);
-    uint8_t *d_m2 = (uint8_t *)arena_take(ctx, f->n + 1);
-    if (!d_bin || !d_m2) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
-    int *d_nm = d_hist + 32; // [0..29] histogram, [32] nmatches
-    CU_TRY(cudaMemsetAsync(d_match, 0xFF, (size_t)n_out * 4, ctx->stream));
-    CU_TRY(cudaMemsetAsync(d_bin, 0xFF, (size_t)n_out * 4, ctx->stream));
-    CU_TRY(cudaMemsetAsync(d_hist, 0, 256, ctx->stream));
-    CU_TRY(cudaMemsetAsync(d_m2, 0, f->n + 1, ctx->stream));
+    int32_t *d_match = blk.d_match, *d_bin = blk.d_bin;
+    uint8_t *d_m2 = blk.d_m2;
+    int *d_hist = blk.d_hist, *d_nm = d_hist + 32; // [0..29] histogram, [32] nmatches
     if (kf->fv_n_nodes > 0 && f->fv_n_nodes > 0) {
         const int threads = f->fv_max_node <= 32 ? 32 : (f->fv_max_node <= 512 ? 128 : (f->fv_max_node <= 1024 ? 256 : 1024));
         // staging capacity: the largest partner node, as far as shared memory goes (33 B per descriptor)
@@ -466,17 +476,20 @@ int run_bow(orbgpu_ctx *ctx, int mode, const orbgpu_frame *kf, const orbgpu_fram
     *nmatches = 0;
     const int n_out = (mode == 0) ? f->n : kf->n; // size of the match vector
     if (n_out == 0) return ORBGPU_OK;
-    rc = arena_reserve(ctx, bow_scratch_bytes(kf, f, mode, nullptr) + align256((size_t)n_out * 4) + align256(kf->n + 1) + align256(f->n + 1) + 1024);
+    const size_t ffb = bow_ff_bytes(n_out), zb = bow_zero_bytes(f->n);
+    rc = arena_reserve(ctx, bow_scratch_bytes(kf, f, mode, nullptr) + ffb + zb + align256(kf->n + 1) + align256(f->n + 1) + 1024);
     if (rc) return rc;
-    int32_t *d_match = (int32_t *)arena_take(ctx, (size_t)n_out * 4);
+    char *ff = (char *)arena_take(ctx, ffb), *zero = (char *)arena_take(ctx, zb);
     uint8_t *d_kfv = (uint8_t *)arena_take(ctx, kf->n + 1), *d_fv = (uint8_t *)arena_take(ctx, f->n + 1);
-    int *d_hist = (int *)arena_take(ctx, 256);
-    if (!d_match || !d_kfv || !d_fv || !d_hist) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
+    if (!ff || !zero || !d_kfv || !d_fv) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
+    CU_TRY(cudaMemsetAsync(ff, 0xFF, ffb, ctx->stream));
+    CU_TRY(cudaMemsetAsync(zero, 0, zb, ctx->stream));
     if (kf->n) CU_TRY(cudaMemcpyAsync(d_kfv, kf_valid, kf->n, cudaMemcpyHostToDevice, ctx->stream));
     if (mode == 1 && f->n) CU_TRY(cudaMemcpyAsync(d_fv, f_valid, f->n, cudaMemcpyHostToDevice, ctx->stream));
-    rc = bow_enqueue(ctx, mode, kf, f, d_kfv, d_fv, nnratio, check_ori, d_match, d_hist);
+    const BowBlock blk = bow_block(ff, zero, n_out);
+    rc = bow_enqueue(ctx, mode, kf, f, d_kfv, d_fv, nnratio, check_ori, blk);
     if (rc) return rc;
-    const OutPiece out[2] = {{match_out, d_match, (size_t)n_out * 4}, {nmatches, d_hist + 32, 4}};
+    const OutPiece out[2] = {{match_out, blk.d_match, (size_t)n_out * 4}, {nmatches, blk.d_hist + 32, 4}};
     return ctx_download(ctx, out, 2);
 }
 
@@ -491,7 +504,8 @@ int run_bow_batch(orbgpu_ctx *ctx, int K, const orbgpu_frame *const *kfs, const 
     for (int k = 0; k < K; k++) nmatches[k] = 0;
     const int n_out = f->n;
     if (n_out == 0 || K == 0) return ORBGPU_OK;
-    size_t total = align256((size_t)K * n_out * 4) + align256((size_t)K * 256) + 1024, mask_bytes = 0;
+    const size_t ffb = bow_ff_bytes(n_out), zb = bow_zero_bytes(f->n);
+    size_t total = K * (ffb + zb) + align256((size_t)K * n_out * 4) + 2048, mask_bytes = 0;
     std::vector<size_t> mask_off(K);
     for (int k = 0; k < K; k++) {
         total += bow_scratch_bytes(kfs[k], f, 0, nullptr);
@@ -502,21 +516,24 @@ int run_bow_batch(orbgpu_ctx *ctx, int K, const orbgpu_frame *const *kfs, const 
     if (rc) return rc;
     rc = arena_reserve(ctx, total + align256(mask_bytes) + align256(f->n + 1));
     if (rc) return rc;
-    int32_t *d_match = (int32_t *)arena_take(ctx, (size_t)K * n_out * 4);
-    int *d_hist = (int *)arena_take(ctx, (size_t)K * 256);
+    char *ff = (char *)arena_take(ctx, K * ffb), *zero = (char *)arena_take(ctx, K * zb);
+    int32_t *d_out = (int32_t *)arena_take(ctx, (size_t)K * n_out * 4 + 4 * K);
     uint8_t *d_masks = (uint8_t *)arena_take(ctx, mask_bytes + 1), *d_fv = (uint8_t *)arena_take(ctx, f->n + 1);
-    if (!d_match || !d_hist || !d_masks || !d_fv) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
+    if (!ff || !zero || !d_out || !d_masks || !d_fv) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
     for (int k = 0; k < K; k++)
         if (kfs[k]->n) memcpy(ctx->h_stage + mask_off[k], kf_valid[k], kfs[k]->n);
     CU_TRY(cudaMemcpyAsync(d_masks, ctx->h_stage, mask_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemsetAsync(ff, 0xFF, K * ffb, ctx->stream)); // the match / bin vectors of ALL pairs
+    CU_TRY(cudaMemsetAsync(zero, 0, K * zb, ctx->stream));   // histograms, counts and taken flags of ALL pairs
     for (int k = 0; k < K; k++) {
-        rc = bow_enqueue(ctx, 0, kfs[k], f, d_masks + mask_off[k], d_fv, nnratio, check_ori, d_match + (size_t)k * n_out, d_hist + (size_t)k * 64);
+        rc = bow_enqueue(ctx, 0, kfs[k], f, d_masks + mask_off[k], d_fv, nnratio, check_ori, bow_block(ff + k * ffb, zero + k * zb, n_out));
         if (rc) return rc;
     }
-    // nmatches live at d_hist[k * 64 + 32]: gather them with one strided copy
-    int32_t *d_nm = (int32_t *)d_masks; // the masks have been consumed by the kernels enqueued above (stream order)
-    CU_TRY(cudaMemcpy2DAsync(d_nm, 4, d_hist + 32, 256, 4, K, cudaMemcpyDeviceToDevice, ctx->stream));
-    const OutPiece out[2] = {{match_out, d_match, (size_t)K * n_out * 4}, {nmatches, d_nm, (size_t)K * 4}};
+    // results to one contiguous block: [K][n_out] matches (pitch ffb -> n_out * 4), then the K counts (zero + k * zb + 128)
+    int32_t *d_nm = d_out + (size_t)K * n_out;
+    CU_TRY(cudaMemcpy2DAsync(d_out, (size_t)n_out * 4, ff, ffb, (size_t)n_out * 4, K, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU_TRY(cudaMemcpy2DAsync(d_nm, 4, zero + 128, zb, 4, K, cudaMemcpyDeviceToDevice, ctx->stream));
+    const OutPiece out[2] = {{match_out, d_out, (size_t)K * n_out * 4}, {nmatches, d_nm, (size_t)K * 4}};
     return ctx_download(ctx, out, 2);
 }
 
