@@ -351,6 +351,12 @@ typedef struct orbgpu_tri_gather {
 int orbgpu_search_for_triangulation_batch_gather_dev(orbgpu_ctx *ctx, const orbgpu_kfset *s, int32_t n_pairs, const int32_t *kf1_dev,
                                                      const int32_t *kf2_dev, const float *ep_dev, const float *f12_dev, int32_t coarse,
                                                      int32_t check_ori, const orbgpu_tri_gather *g, int64_t pair_offset);
+/* The gathered result on the host, in the form of orbgpu_search_for_triangulation_batch_pairs below (pair_offsets [n_pairs + 1],
+ * pairs [total][2] = (idx1, idx2), ascending idx1 inside a pair): offsets scan and packing on the device, then only the valid
+ * pairs cross PCIe.  counts_dev / entries_dev are this rank's gather buffers (device pointers); the call runs on ctx's stream, so
+ * it is ordered after a gather step launched on the same context. */
+int orbgpu_tri_gather_download(orbgpu_ctx *ctx, int32_t n_pairs, int32_t n_feat, const void *counts_dev, const void *entries_dev,
+                               int32_t *pair_offsets, int32_t *pairs, int64_t cap, int64_t *total);
 /* Same search with the result in the reference's vMatchedPairs form (ORBmatcher.cc:1317-1325): for pair p the matches are
  * pairs[2*j], pairs[2*j+1] = (idx1, idx2), j in [pair_offsets[p], pair_offsets[p+1]), ascending idx1.  pair_offsets has
  * n_pairs+1 entries; cap = capacity of pairs in (idx1, idx2) entries; *total = entries produced (ORBGPU_ERR_OVERFLOW and the

@@ -997,6 +997,22 @@ __global__ void tri_compact_kernel(int n_pairs, int n_feat, const int32_t *__res
     }
 }
 
+// compact form (counts + fixed-stride (idx1 << 16 | idx2) entries) -> contiguous (idx1, idx2) pairs at the scanned offsets
+__global__ void tri_pack_entries_kernel(int n_pairs, int n_feat, const uint32_t *__restrict__ entries, const int32_t *__restrict__ offsets,
+                                        int2 *__restrict__ pairs, long long cap)
+{
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; // one warp per key-frame pair
+    if (p >= n_pairs) return;
+    const int lane = lane_id();
+    const long long o = offsets[p];
+    const int cnt = offsets[p + 1] - offsets[p];
+    const uint32_t *src = entries + (size_t)p * n_feat;
+    for (int j = lane; j < cnt; j += 32) {
+        const uint32_t e = src[j];
+        if (o + j < cap) pairs[o + j] = make_int2((int)(e >> 16), (int)(e & 0xFFFFu));
+    }
+}
+
 KfSetView kfset_view(const orbgpu_kfset *s)
 {
     KfSetView v;
@@ -1348,6 +1364,41 @@ extern "C" int orbgpu_search_for_triangulation_batch_gather_dev(orbgpu_ctx *ctx,
     }
     return tri_launch(ctx, s, n_pairs, kf1_dev, kf2_dev, ep_dev, f12_dev, 0, coarse, check_ori, (int32_t *)tm[0], (int32_t *)tn[0], g->n_ranks,
                       tm, tn, pair_offset, 3, &go);
+}
+
+// The gathered result of orbgpu_search_for_triangulation_batch_gather_dev on the host, in the form of
+// orbgpu_search_for_triangulation_batch_pairs: offsets scan + pack on the device, one download of the valid pairs only.
+extern "C" int orbgpu_tri_gather_download(orbgpu_ctx *ctx, int32_t n_pairs, int32_t n_feat, const void *counts_dev, const void *entries_dev,
+                                          int32_t *pair_offsets, int32_t *pairs, int64_t cap, int64_t *total)
+{
+    ARG_TRY(ctx && n_pairs >= 0 && n_feat > 0 && pair_offsets && total && cap >= 0 && (cap == 0 || pairs));
+    ARG_TRY(n_pairs == 0 || (counts_dev && entries_dev));
+    int rc = ctx_begin(ctx);
+    if (rc) return rc;
+    *total = 0;
+    pair_offsets[0] = 0;
+    if (n_pairs == 0) return ORBGPU_OK;
+    const size_t P = (size_t)n_pairs;
+    rc = arena_reserve(ctx, align256((P + 1) * 4) + align256((size_t)cap * 8 + 8) + 512);
+    if (rc) return rc;
+    int32_t *d_off = (int32_t *)arena_take(ctx, (P + 1) * 4);
+    int2 *d_pairs = (int2 *)arena_take(ctx, (size_t)cap * 8 + 8);
+    if (!d_off || !d_pairs) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
+    tri_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(n_pairs, (const int32_t *)counts_dev, d_off);
+    tri_pack_entries_kernel<<<(unsigned)((P * 32 + 255) / 256), 256, 0, ctx->stream>>>(n_pairs, n_feat, (const uint32_t *)entries_dev, d_off, d_pairs,
+                                                                                        (long long)cap);
+    ctx->launches += 2;
+    CU_TRY(cudaGetLastError());
+    // offsets and (speculatively) the whole capacity of pairs in one go would move unused bytes: the total comes first
+    CU_TRY(cudaMemcpyAsync(pair_offsets, d_off, (P + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    *total = pair_offsets[n_pairs];
+    const int64_t n_copy = *total < cap ? *total : cap;
+    if (n_copy > 0) {
+        CU_TRY(cudaMemcpyAsync(pairs, d_pairs, (size_t)n_copy * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return *total <= cap ? ORBGPU_OK : orbgpu_fail(ORBGPU_ERR_OVERFLOW, "pairs capacity too small: see *total");
 }
 
 int triangulation_device_init()

@@ -626,6 +626,19 @@ class ORBmatcher:
                                                                   vp(ep_ptr), vp(f12_ptr), int(bCoarse), int(self.mbCheckOrientation),
                                                                   C.byref(gather), int(pair_offset)))
 
+    # the gathered compact result on the host as (pair_offsets[P+1], pairs[total, 2]) -- offsets scan + packing on the device
+    def TriangulationGatherDownload(self, n_pairs: int, n_feat: int, counts_ptr: int, entries_ptr: int, out=None):
+        if out is None:
+            out = (np.empty(n_pairs + 1, dtype=np.int32), np.empty((n_pairs * 512, 2), dtype=np.int32))
+        offs, pairs = out
+        total = C.c_int64(0)
+        L = load_library()
+        L.orbgpu_tri_gather_download.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, i32p, i32p, C.c_int64,
+                                                 C.POINTER(C.c_int64)]
+        _check(L.orbgpu_tri_gather_download(self.ctx.handle, int(n_pairs), int(n_feat), C.c_void_p(counts_ptr), C.c_void_p(entries_ptr),
+                                            _p(offs, i32p), _p(pairs, i32p), pairs.shape[0], C.byref(total)))
+        return offs, pairs[:total.value]
+
     # brute-force 2-NN + ratio test ("SearchByNN" of BASELINE.json) -> best_idx, best_dist, second_dist, match
     def SearchByNN(self, db: DeviceDb, q, th_low: int = TH_LOW):
         q = as_u8(q).reshape(-1, 32)

@@ -157,6 +157,13 @@ class TriangulationGather:
             cur.wait_stream(self.side)
         return self.counts[b], self.pairs[b].view(self.p_total, self.n_feat)
 
+    def download(self, counts: torch.Tensor, entries: torch.Tensor, out=None):
+        """the gathered result of a step on the host: (pair_offsets[P_total + 1], pairs[total, 2]) -- vMatchedPairs of ALL pairs"""
+        cur = torch.cuda.current_stream(self.dev)
+        self.side.wait_stream(cur)  # the step was replayed / launched on the current stream; the download runs on the context's
+        offs, pairs = self.m.TriangulationGatherDownload(self.p_total, self.n_feat, counts.data_ptr(), entries.data_ptr(), out=out)
+        return offs, pairs
+
     def status(self) -> int:
         """non-zero when a peer did not arrive within the time-out of the wait kernel"""
         return int(self.state[4].item())

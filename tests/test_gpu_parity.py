@@ -615,6 +615,12 @@ def test_triangulation_compact_gather(ctx, M, oracle, seed, n_pairs, n_feat, ori
                 pad = e[p, c[p]:(c[p] + 3) // 4 * 4]
                 assert np.all(pad == 0xFFFFFFFF) and np.all(e[p, (c[p] + 3) // 4 * 4:] == 0x5A5A5A5A)
                 assert np.array_equal(pairs_from_compact(c, e, p)[:, 0], np.flatnonzero(em[p] >= 0))
+        # the gathered result on the host in the vMatchedPairs form of orbgpu_search_for_triangulation_batch_pairs
+        offs, pr = mm.TriangulationGatherDownload(n_pairs, n_feat, cnts[1].data_ptr(), pairs[1].data_ptr())
+        assert np.array_equal(offs, np.concatenate([[0], np.cumsum(ecnt)]).astype(np.int32))
+        for p in range(n_pairs):
+            i1 = np.flatnonzero(em[p] >= 0)
+            assert np.array_equal(pr[offs[p]:offs[p + 1]], np.stack([i1, em[p, i1]], axis=1)), p
         for x in pairs:
             x.fill_(0x5A5A5A5A)
     assert int(enm.sum()) > 0
