@@ -518,6 +518,25 @@ def bench_c4(E, args, K, W, shared=False):
                                 "single-GPU rate, not the links" % (sent / 1e6, (world - 1) * P * C4_FEAT * 4 / 1e6, sent / 700e3))
     log(f"c4: {ms_per_step * 1e3:.1f} us/step over {K4} steps")
 
+    if world == 1 and not shared:
+        # the same search leaving dense vMatches12 rows (orbgpu_search_for_triangulation_batch_dev, the form the parity tests read)
+        out_rows = torch.empty((P, C4_FEAT), dtype=torch.int32, device=dev)
+        nmt = torch.empty(P, dtype=torch.int32, device=dev)
+        mm = matcher.ORBmatcher(0.6, False, E.ctx)
+        ks_d = E.ctx.upload_kfset(case.kfs)
+        d_in = tg.inputs
+        dense = lambda: mm.SearchForTriangulation_dev(ks_d, P, d_in[0].data_ptr(), d_in[1].data_ptr(), d_in[2].data_ptr(), d_in[3].data_ptr(),  # noqa: E731
+                                                      out_rows.data_ptr(), nmt.data_ptr())
+        for _ in range(5):
+            dense()
+        evd = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(300)]
+        for e0, e1 in evd:
+            E.flush_l2()
+            e0.record(); dense(); e1.record()
+        torch.cuda.synchronize()
+        extra["dense_rows_ms_per_step"] = float(sum(e0.elapsed_time(e1) for e0, e1 in evd)) / len(evd)
+        del ks_d, out_rows
+
     # ---- end to end: pinned host inputs -> device, the sharded search + gather, the vMatchedPairs of ALL pairs back on the host
     e2e = None
     if not args.no_e2e:
