@@ -54,6 +54,7 @@ struct orbgpu_ctx {
     int64_t launches = 0;
     int64_t last_comparisons = 0;
     bool gather_counters_clean = false; // the last call on this context was a fused-gather search (it leaves d_counters[0] == 0)
+    size_t list_pool_hint = 0;          // candidate-list pool entries a projection search on this context has needed so far (grow-only)
     int cmp_slot = 0;                   // d_counters slot that holds the comparisons of the last search (2 after a fused-gather search)
     unsigned long long *d_counters = nullptr; // [8] device counters: [0] comparisons, [1] overflow flag, ...
     unsigned long long *h_counters = nullptr; // pinned mirror
@@ -85,6 +86,24 @@ inline void arena_reset(orbgpu_ctx *ctx) { ctx->arena.used = 0; }
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 int ctx_begin(orbgpu_ctx *ctx); // set device, reset arena, zero counters
+// candidate-list pool of the projection searches (search_proj.cu, search_projected.cu): entries to reserve for M points against an
+// n-key-point frame -- 64 per point to begin with (a window holds a few dozen), never more than the dense M x n, at least what an
+// earlier call on this context needed.  The kernels count every candidate in d_counters[1]; list_pool_overflowed() reads the
+// downloaded count, and when it exceeded the capacity remembers it so that the repeated call fits.
+inline size_t list_pool_entries(orbgpu_ctx *ctx, size_t M, size_t n)
+{
+    size_t want = M * 64 > (size_t(1) << 16) ? M * 64 : (size_t(1) << 16);
+    if (ctx->list_pool_hint > want) want = ctx->list_pool_hint;
+    if (want > M * n) want = M * n;
+    return want > 0 ? want : 1;
+}
+inline bool list_pool_overflowed(orbgpu_ctx *ctx, size_t cap)
+{
+    const size_t needed = (size_t)ctx->h_counters[1];
+    if (needed <= cap) return false;
+    ctx->list_pool_hint = needed + needed / 8;
+    return true;
+}
 
 // Per-device kernel attributes.  cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device, per-function limit: it is raised ONCE
 // per device, to the opt-in maximum, when the first context on that device is created (context.cu: device_attrs_once) -- never per

@@ -6,13 +6,13 @@
 //   variant 0  POPC + IADD3 only: 8 independent chains per thread, x = popc(x) + c   (the POPC issue rate itself)
 //   variant 1  the Hamming triple LOP3(xor) + POPC + IADD3: a += popc(v ^ w), what a 32-bit slice of DescriptorDistance costs
 //
-// All SMs, 1024 threads per SM x 2 CTAs; time from CUDA events, SM cycles from clock64 of CTA 0 (so the result is also
-// reported per clock per SM, at the clock the kernel actually ran at).
+// All SMs, one CTA of 1024 threads per SM (one wave: CTA 0 spans the kernel); time from CUDA events, SM cycles from clock64 of
+// CTA 0, so the result is also reported per clock per SM at the clock the kernel actually ran at.
 #include "internal.cuh"
 
 namespace {
 
-constexpr int MB_THREADS = 512;
+constexpr int MB_THREADS = 1024;
 constexpr int MB_CHAINS = 8;
 
 template <int VARIANT>
@@ -58,7 +58,7 @@ extern "C" int orbgpu_measure_popc_peak(orbgpu_ctx *ctx, int32_t variant, double
     cudaEvent_t e0, e1;
     CU_TRY(cudaEventCreate(&e0));
     CU_TRY(cudaEventCreate(&e1));
-    const int grid = ctx->sm_count * 4, iters = 4096;
+    const int grid = ctx->sm_count, iters = 8192;
     double best_ms = 1e30;
     long long best_cyc = 0;
     for (int rep = 0; rep < 6; rep++) { // first two repetitions warm the clocks up
@@ -79,7 +79,7 @@ extern "C" int orbgpu_measure_popc_peak(orbgpu_ctx *ctx, int32_t variant, double
     cudaEventDestroy(e1);
     const double n_popc = (double)grid * MB_THREADS * (double)iters * 4 * MB_CHAINS;
     *popc_per_s = n_popc / (best_ms * 1e-3);
-    // CTA 0 runs for (nearly) the whole kernel: 4 CTAs of 512 threads per SM = one wave
+    // CTA 0 runs for the whole kernel: one CTA per SM = one wave
     const double mhz = (double)best_cyc / (best_ms * 1e-3) / 1e6;
     if (sm_mhz) *sm_mhz = mhz;
     if (per_clk_sm) *per_clk_sm = n_popc / ((double)best_cyc * ctx->sm_count);

@@ -6,6 +6,7 @@
 // replays the reference's sequential rule "skip a keypoint whose current map point has
 // Observations() > 0" (:102-104) -- a later map point sees the assignments of earlier ones.
 #include <cstring>
+#include <vector>
 
 #include "internal.cuh"
 
@@ -26,9 +27,13 @@ struct MapPointsView {
     const int32_t *n_obs;
 };
 
+// Candidate lists live in ONE pool sized by the candidates that actually exist (a window holds a few dozen key points; a dense
+// M x n matrix would be 160-400 MB for a loop-closing Fuse): every warp first counts its window, reserves a contiguous range with
+// one atomic on counters[1] and then fills it.  A pool that turns out too small drops nothing silently: the cursor keeps counting,
+// the host sees it exceed the capacity and repeats the call with a pool of exactly that size.
 __global__ void proj_candidates_kernel(FrameView f, MapPointsView mp, float th, int far_points, float th_far,
-                                       uint32_t *__restrict__ lists, int stride, int32_t *__restrict__ counts,
-                                       unsigned long long *__restrict__ counters)
+                                       uint32_t *__restrict__ lists, unsigned long long pool_cap, uint32_t *__restrict__ offs,
+                                       int32_t *__restrict__ counts, unsigned long long *__restrict__ counters)
 {
     const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (m >= mp.n) return;
@@ -43,25 +48,34 @@ __global__ void proj_candidates_kernel(FrameView f, MapPointsView mp, float th, 
         const float2 p = mp.proj_xy[m];
         const uint4 qa = mp.desc[2 * m], qb = mp.desc[2 * m + 1];
         const float xr = (f.u_right && mp.proj_xr) ? mp.proj_xr[m] : 0.f;
-        uint32_t *out = lists + (size_t)m * stride;
-        cnt = window_scan_if(
-            f, p.x, p.y, radius, level - 1, level,
-            [&](const int4 &it) {
-                if (f.u_right) { // :107-117 stereo gate (static per candidate)
-                    const float ur = f.u_right[it.w];
-                    if (ur > 0.f) {
-                        const float er = fabsf(__fsub_rn(xr, ur));
-                        if (er > radius) return false;
+        auto gate = [&](const int4 &it) {
+            if (f.u_right) { // :107-117 stereo gate (static per candidate)
+                const float ur = f.u_right[it.w];
+                if (ur > 0.f) {
+                    const float er = fabsf(__fsub_rn(xr, ur));
+                    if (er > radius) return false;
+                }
+            }
+            return true;
+        };
+        cnt = window_scan_if(f, p.x, p.y, radius, level - 1, level, gate, [](bool, int, int, int4) {});
+        if (cnt) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&counters[1], (unsigned long long)cnt);
+            base = __shfl_sync(FULL_MASK, base, 0);
+            if (base + cnt <= pool_cap) {
+                uint32_t *out = lists + base;
+                window_scan_if(f, p.x, p.y, radius, level - 1, level, gate, [&](bool ok, int pos, int slot, int4 it) {
+                    if (ok) {
+                        const int dist = ham256(qa, qb, f.desc_sorted[2 * slot], f.desc_sorted[2 * slot + 1]);
+                        out[pos] = ((uint32_t)dist << 20) | (uint32_t)it.w;
                     }
-                }
-                return true;
-            },
-            [&](bool ok, int pos, int slot, int4 it) {
-                if (ok) {
-                    const int dist = ham256(qa, qb, f.desc_sorted[2 * slot], f.desc_sorted[2 * slot + 1]);
-                    out[pos] = ((uint32_t)dist << 20) | (uint32_t)it.w;
-                }
-            });
+                });
+                if (lane == 0) offs[m] = (uint32_t)base;
+            } else {
+                cnt = 0; // pool too small: the host repeats the call (see above)
+            }
+        }
     }
     if (lane == 0) counts[m] = cnt;
 }
@@ -77,7 +91,7 @@ __global__ void proj_candidates_kernel(FrameView f, MapPointsView mp, float th, 
 // One CTA: lock times live in shared memory, a thread owns map points m = t, t+T, ...
 constexpr int RESOLVE_THREADS = 1024;
 __global__ void __launch_bounds__(RESOLVE_THREADS)
-proj_resolve_kernel(FrameView f, MapPointsView mp, const uint32_t *__restrict__ lists, int stride,
+proj_resolve_kernel(FrameView f, MapPointsView mp, const uint32_t *__restrict__ lists, const uint32_t *__restrict__ offs,
                     const int32_t *__restrict__ counts, float nnratio, const int32_t *__restrict__ prior_obs,
                     int32_t *__restrict__ choice, int32_t *__restrict__ kp_mp, int32_t *__restrict__ nmatches_out,
                     unsigned long long *__restrict__ counters)
@@ -98,7 +112,7 @@ proj_resolve_kernel(FrameView f, MapPointsView mp, const uint32_t *__restrict__ 
             const int cnt = counts[m];
             int pick = -1;
             if (cnt > 0) { // else filtered (:55-62) or empty window (:84)
-                const uint32_t *lst = lists + (size_t)m * stride;
+                const uint32_t *lst = lists + offs[m];
                 int bestDist = 256, bestDist2 = 256, bestIdx = -1, idx2 = -1; // :89-93
                 for (int p = 0; p < cnt; p++) {
                     const uint32_t e = lst[p];
@@ -259,10 +273,10 @@ extern "C" int orbgpu_search_by_projection_local(orbgpu_ctx *ctx, const orbgpu_f
                  o_cos = take((size_t)M * 4), o_dep = take((size_t)M * 4), o_nobs = take((size_t)M * 4), o_inv = take(M),
                  o_bad = take(M), o_prior = take((size_t)n * 4), o_kpmp = take((size_t)n * 4);
     const size_t up_bytes = off;
-    const int stride = n;
+    const size_t pool_cap = list_pool_entries(ctx, M, n);
     rc = stage_reserve(ctx, up_bytes);
     if (rc) return rc;
-    rc = arena_reserve(ctx, up_bytes + align256((size_t)M * stride * 4) + 2 * align256((size_t)M * 4) + 512);
+    rc = arena_reserve(ctx, up_bytes + align256(pool_cap * 4) + 3 * align256((size_t)M * 4) + 512);
     if (rc) return rc;
     char *H = ctx->h_stage;
     memcpy(H + o_desc, mps->desc, (size_t)M * 32);
@@ -277,11 +291,11 @@ extern "C" int orbgpu_search_by_projection_local(orbgpu_ctx *ctx, const orbgpu_f
     memcpy(H + o_prior, kp_prior_obs, (size_t)n * 4);
     memcpy(H + o_kpmp, kp_mp, (size_t)n * 4);
     char *D = (char *)arena_take(ctx, up_bytes);
-    uint32_t *lists = (uint32_t *)arena_take(ctx, (size_t)M * stride * 4);
+    uint32_t *lists = (uint32_t *)arena_take(ctx, pool_cap * 4), *offs = (uint32_t *)arena_take(ctx, (size_t)M * 4);
     int32_t *counts = (int32_t *)arena_take(ctx, (size_t)M * 4);
     int32_t *choice = (int32_t *)arena_take(ctx, (size_t)M * 4);
     int32_t *d_nm = (int32_t *)arena_take(ctx, 256);
-    if (!D || !lists || !counts || !choice || !d_nm) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
+    if (!D || !lists || !offs || !counts || !choice || !d_nm) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
     CU_TRY(cudaMemcpyAsync(D, H, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
     MapPointsView mv;
     mv.n = M;
@@ -291,16 +305,23 @@ extern "C" int orbgpu_search_by_projection_local(orbgpu_ctx *ctx, const orbgpu_f
     mv.in_view = (const uint8_t *)(D + o_inv); mv.bad = (const uint8_t *)(D + o_bad); mv.n_obs = (const int32_t *)(D + o_nobs);
     int32_t *cur_obs = (int32_t *)(D + o_prior), *d_kpmp = (int32_t *)(D + o_kpmp);
     const FrameView v = frame_view(f);
-    proj_candidates_kernel<<<(M * 32 + 255) / 256, 256, 0, ctx->stream>>>(v, mv, th, far_points, th_far_points, lists, stride, counts,
+    proj_candidates_kernel<<<(M * 32 + 255) / 256, 256, 0, ctx->stream>>>(v, mv, th, far_points, th_far_points, lists, pool_cap, offs, counts,
                                                                          ctx->d_counters);
     const size_t lock_bytes = (size_t)n * sizeof(int);
     if (lock_bytes > 200 * 1024) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "frame too large for the shared-memory lock table");
-    proj_resolve_kernel<<<1, RESOLVE_THREADS, lock_bytes, ctx->stream>>>(v, mv, lists, stride, counts, nnratio, cur_obs, choice, d_kpmp,
+    proj_resolve_kernel<<<1, RESOLVE_THREADS, lock_bytes, ctx->stream>>>(v, mv, lists, offs, counts, nnratio, cur_obs, choice, d_kpmp,
                                                                         d_nm, ctx->d_counters);
     ctx->launches += 2;
     CU_TRY(cudaGetLastError());
+    std::vector<int32_t> kp_in(kp_mp, kp_mp + n); // in/out argument: kept for the (rare) repeat with a larger pool
     const OutPiece out[2] = {{kp_mp, d_kpmp, (size_t)n * 4}, {nmatches, d_nm, 4}};
-    return ctx_download(ctx, out, 2);
+    rc = ctx_download(ctx, out, 2);
+    if (rc) return rc;
+    if (list_pool_overflowed(ctx, pool_cap)) {
+        memcpy(kp_mp, kp_in.data(), (size_t)n * 4);
+        return orbgpu_search_by_projection_local(ctx, f, mps, th, far_points, th_far_points, nnratio, kp_prior_obs, kp_mp, nmatches);
+    }
+    return ORBGPU_OK;
 }
 
 extern "C" int orbgpu_is_in_frustum(orbgpu_ctx *ctx, const orbgpu_frustum_host *fr, int32_t n, const float *world_pos, const float *normal,
@@ -367,10 +388,10 @@ extern "C" int orbgpu_search_local_points(orbgpu_ctx *ctx, const orbgpu_frame *f
                  o_skip = take(Mz), o_bad = take(Mz), o_nobs = take(Mz * 4), o_prior = take(nz * 4), o_kpmp = take(nz * 4);
     const size_t up_bytes = off;
     const size_t o_iv = take(Mz), o_xy = take(Mz * 8), o_xr = take(Mz * 4), o_dp = take(Mz * 4), o_lv = take(Mz * 4), o_vc = take(Mz * 4);
-    const int stride = n > 0 ? n : 1;
+    const size_t pool_cap = list_pool_entries(ctx, M, n > 0 ? n : 1);
     rc = stage_reserve(ctx, up_bytes);
     if (rc) return rc;
-    rc = arena_reserve(ctx, off + align256(Mz * stride * 4) + 2 * align256(Mz * 4) + 512);
+    rc = arena_reserve(ctx, off + align256(pool_cap * 4) + 3 * align256(Mz * 4) + 512);
     if (rc) return rc;
     char *H = ctx->h_stage;
     memcpy(H + o_desc, pts->desc, Mz * 32);
@@ -386,10 +407,10 @@ extern "C" int orbgpu_search_local_points(orbgpu_ctx *ctx, const orbgpu_frame *f
         memcpy(H + o_kpmp, kp_mp, (size_t)n * 4);
     }
     char *D = (char *)arena_take(ctx, off);
-    uint32_t *lists = (uint32_t *)arena_take(ctx, Mz * stride * 4);
+    uint32_t *lists = (uint32_t *)arena_take(ctx, pool_cap * 4), *offs = (uint32_t *)arena_take(ctx, Mz * 4);
     int32_t *counts = (int32_t *)arena_take(ctx, Mz * 4), *choice = (int32_t *)arena_take(ctx, Mz * 4);
     int32_t *d_nm = (int32_t *)arena_take(ctx, 256);
-    if (!D || !lists || !counts || !choice || !d_nm) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
+    if (!D || !lists || !offs || !counts || !choice || !d_nm) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
     CU_TRY(cudaMemcpyAsync(D, H, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(cudaMemsetAsync(d_nm, 0, 4, ctx->stream));
     FrustumView v;
@@ -407,17 +428,24 @@ extern "C" int orbgpu_search_local_points(orbgpu_ctx *ctx, const orbgpu_frame *f
         mv.view_cos = v.view_cos; mv.depth = v.depth; mv.in_view = v.in_view; mv.bad = (const uint8_t *)(D + o_bad);
         mv.n_obs = (const int32_t *)(D + o_nobs);
         const FrameView fv = frame_view(f);
-        proj_candidates_kernel<<<(M * 32 + 255) / 256, 256, 0, ctx->stream>>>(fv, mv, th, far_points, th_far_points, lists, stride, counts,
+        proj_candidates_kernel<<<(M * 32 + 255) / 256, 256, 0, ctx->stream>>>(fv, mv, th, far_points, th_far_points, lists, pool_cap, offs, counts,
                                                                              ctx->d_counters);
         const size_t lock_bytes = (size_t)n * sizeof(int);
         if (lock_bytes > 200 * 1024) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "frame too large for the shared-memory lock table");
-        proj_resolve_kernel<<<1, RESOLVE_THREADS, lock_bytes, ctx->stream>>>(fv, mv, lists, stride, counts, nnratio, (int32_t *)(D + o_prior),
+        proj_resolve_kernel<<<1, RESOLVE_THREADS, lock_bytes, ctx->stream>>>(fv, mv, lists, offs, counts, nnratio, (int32_t *)(D + o_prior),
                                                                             choice, (int32_t *)(D + o_kpmp), d_nm, ctx->d_counters);
         ctx->launches += 2;
     }
     CU_TRY(cudaGetLastError());
+    std::vector<int32_t> kp_in(kp_mp, kp_mp + n);
     const OutPiece out[3] = {{kp_mp, D + o_kpmp, (size_t)n * 4}, {nmatches, d_nm, 4}, {in_view, v.in_view, Mz}};
-    return ctx_download(ctx, out, 3);
+    rc = ctx_download(ctx, out, 3);
+    if (rc) return rc;
+    if (list_pool_overflowed(ctx, pool_cap)) {
+        if (n > 0) memcpy(kp_mp, kp_in.data(), (size_t)n * 4);
+        return orbgpu_search_local_points(ctx, f, fr, pts, th, far_points, th_far_points, nnratio, kp_prior_obs, kp_mp, in_view, nmatches);
+    }
+    return ORBGPU_OK;
 }
 
 int search_proj_device_init() { return set_max_dyn_smem(proj_resolve_kernel); }

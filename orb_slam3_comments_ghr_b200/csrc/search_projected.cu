@@ -30,7 +30,8 @@ struct ProjPointsView {
 };
 
 __global__ void projected_candidates_kernel(FrameView f, ProjPointsView pt, int stereo_gate, int chi2_gate,
-                                            const float *__restrict__ inv_sigma2, uint32_t *__restrict__ lists, int stride,
+                                            const float *__restrict__ inv_sigma2, uint32_t *__restrict__ lists, unsigned long long pool_cap,
+                                            uint32_t *__restrict__ offs, unsigned long long *__restrict__ counters,
                                             int32_t *__restrict__ counts)
 {
     const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -42,40 +43,50 @@ __global__ void projected_candidates_kernel(FrameView f, ProjPointsView pt, int 
         const float radius = pt.radius[m];
         const float ur = pt.ur ? pt.ur[m] : 0.f;
         const uint4 qa = pt.desc[2 * m], qb = pt.desc[2 * m + 1];
-        uint32_t *out = lists + (size_t)m * stride;
-        cnt = window_scan_if(
-            f, p.x, p.y, radius, pt.min_level[m], pt.max_level[m],
-            [&](const int4 &it) {
-                if (stereo_gate && f.u_right) { // :2052-2059
-                    const float kr = f.u_right[it.w];
-                    if (kr > 0.f && fabsf(__fsub_rn(ur, kr)) > radius) return false;
-                }
-                if (chi2_gate) { // :1463-1492
-                    const float ex = __fsub_rn(p.x, __int_as_float(it.x)), ey = __fsub_rn(p.y, __int_as_float(it.y));
-                    const float inv = inv_sigma2[it.z & 0xffff];
-                    const float kr = f.u_right ? f.u_right[it.w] : -1.f;
-                    float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
-                    if (kr >= 0.f) {
-                        const float er = __fsub_rn(ur, kr);
-                        e2 = __fadd_rn(e2, __fmul_rn(er, er));
-                        if ((double)__fmul_rn(e2, inv) > 7.8) return false;
-                    } else if ((double)__fmul_rn(e2, inv) > 5.99) return false;
-                }
-                return true;
-            },
-            [&](bool ok, int pos, int slot, int4 it) {
-                if (ok) {
-                    const int dist = ham256(qa, qb, f.desc_sorted[2 * slot], f.desc_sorted[2 * slot + 1]);
-                    out[pos] = ((uint32_t)dist << 20) | (uint32_t)it.w;
-                }
-            });
+        auto gate = [&](const int4 &it) {
+            if (stereo_gate && f.u_right) { // :2052-2059
+                const float kr = f.u_right[it.w];
+                if (kr > 0.f && fabsf(__fsub_rn(ur, kr)) > radius) return false;
+            }
+            if (chi2_gate) { // :1463-1492
+                const float ex = __fsub_rn(p.x, __int_as_float(it.x)), ey = __fsub_rn(p.y, __int_as_float(it.y));
+                const float inv = inv_sigma2[it.z & 0xffff];
+                const float kr = f.u_right ? f.u_right[it.w] : -1.f;
+                float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                if (kr >= 0.f) {
+                    const float er = __fsub_rn(ur, kr);
+                    e2 = __fadd_rn(e2, __fmul_rn(er, er));
+                    if ((double)__fmul_rn(e2, inv) > 7.8) return false;
+                } else if ((double)__fmul_rn(e2, inv) > 5.99) return false;
+            }
+            return true;
+        };
+        // count, reserve a range of the pool with one atomic, fill (see proj_candidates_kernel in search_proj.cu)
+        cnt = window_scan_if(f, p.x, p.y, radius, pt.min_level[m], pt.max_level[m], gate, [](bool, int, int, int4) {});
+        if (cnt) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&counters[1], (unsigned long long)cnt);
+            base = __shfl_sync(FULL_MASK, base, 0);
+            if (base + cnt <= pool_cap) {
+                uint32_t *out = lists + base;
+                window_scan_if(f, p.x, p.y, radius, pt.min_level[m], pt.max_level[m], gate, [&](bool ok, int pos, int slot, int4 it) {
+                    if (ok) {
+                        const int dist = ham256(qa, qb, f.desc_sorted[2 * slot], f.desc_sorted[2 * slot + 1]);
+                        out[pos] = ((uint32_t)dist << 20) | (uint32_t)it.w;
+                    }
+                });
+                if (lane == 0) offs[m] = (uint32_t)base;
+            } else {
+                cnt = 0; // pool too small: the host repeats the call with the size the cursor reports
+            }
+        }
     }
     if (lane == 0) counts[m] = cnt;
 }
 
 constexpr int PR_THREADS = 1024;
 __global__ void __launch_bounds__(PR_THREADS)
-projected_resolve_kernel(FrameView f, ProjPointsView pt, const uint32_t *__restrict__ lists, int stride,
+projected_resolve_kernel(FrameView f, ProjPointsView pt, const uint32_t *__restrict__ lists, const uint32_t *__restrict__ offs,
                          const int32_t *__restrict__ counts, float max_dist, int ordered, int check_ori,
                          const uint8_t *__restrict__ kp_locked, int32_t *__restrict__ choice, int32_t *__restrict__ best_dist,
                          int32_t *__restrict__ kp_owner, int32_t *__restrict__ nmatches_out, unsigned long long *__restrict__ counters)
@@ -104,7 +115,7 @@ projected_resolve_kernel(FrameView f, ProjPointsView pt, const uint32_t *__restr
             const int cnt = counts[m];
             int pick = -1, bestDist = 256;
             if (cnt > 0) {
-                const uint32_t *lst = lists + (size_t)m * stride;
+                const uint32_t *lst = lists + offs[m];
                 int bestIdx = -1;
                 for (int p = 0; p < cnt; p++) {
                     const uint32_t e = lst[p];
@@ -220,10 +231,10 @@ extern "C" int orbgpu_search_projected(orbgpu_ctx *ctx, const orbgpu_frame *f, c
                  o_max = take((size_t)M * 4), o_ur = take((size_t)M * 4), o_ang = take((size_t)M * 4), o_act = take(M), o_lck = take(M),
                  o_kl = take(n), o_sig = take(64 * 4);
     const size_t up_bytes = off;
-    const int stride = n;
+    const size_t pool_cap = list_pool_entries(ctx, M, n);
     rc = stage_reserve(ctx, up_bytes);
     if (rc) return rc;
-    rc = arena_reserve(ctx, up_bytes + align256((size_t)M * stride * 4) + 3 * align256((size_t)M * 4) + align256((size_t)n * 4) + 512);
+    rc = arena_reserve(ctx, up_bytes + align256(pool_cap * 4) + 4 * align256((size_t)M * 4) + align256((size_t)n * 4) + 512);
     if (rc) return rc;
     char *H = ctx->h_stage;
     memcpy(H + o_desc, pts->desc, (size_t)M * 32);
@@ -238,11 +249,11 @@ extern "C" int orbgpu_search_projected(orbgpu_ctx *ctx, const orbgpu_frame *f, c
     if (kp_locked) memcpy(H + o_kl, kp_locked, n);
     if (prm->chi2_gate) memcpy(H + o_sig, prm->inv_level_sigma2, (size_t)(f->n_levels < 64 ? f->n_levels : 64) * 4);
     char *D = (char *)arena_take(ctx, up_bytes);
-    uint32_t *lists = (uint32_t *)arena_take(ctx, (size_t)M * stride * 4);
+    uint32_t *lists = (uint32_t *)arena_take(ctx, pool_cap * 4), *offs = (uint32_t *)arena_take(ctx, (size_t)M * 4);
     int32_t *counts = (int32_t *)arena_take(ctx, (size_t)M * 4), *choice = (int32_t *)arena_take(ctx, (size_t)M * 4),
             *d_bd = (int32_t *)arena_take(ctx, (size_t)M * 4), *d_owner = (int32_t *)arena_take(ctx, (size_t)n * 4),
             *d_nm = (int32_t *)arena_take(ctx, 256);
-    if (!D || !lists || !counts || !choice || !d_bd || !d_owner || !d_nm) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
+    if (!D || !lists || !offs || !counts || !choice || !d_bd || !d_owner || !d_nm) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
     CU_TRY(cudaMemcpyAsync(D, H, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
     ProjPointsView pv;
     pv.n = M;
@@ -254,17 +265,21 @@ extern "C" int orbgpu_search_projected(orbgpu_ctx *ctx, const orbgpu_frame *f, c
     pv.locks = pts->locks ? (const uint8_t *)(D + o_lck) : nullptr;
     const FrameView v = frame_view(f);
     projected_candidates_kernel<<<(M * 32 + 255) / 256, 256, 0, ctx->stream>>>(v, pv, prm->stereo_gate, prm->chi2_gate,
-                                                                              (const float *)(D + o_sig), lists, stride, counts);
+                                                                              (const float *)(D + o_sig), lists, pool_cap, offs, ctx->d_counters, counts);
     const size_t lock_bytes = (size_t)n * sizeof(int);
     if (lock_bytes > 200 * 1024) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "frame too large for the shared-memory lock table");
-    projected_resolve_kernel<<<1, PR_THREADS, lock_bytes, ctx->stream>>>(v, pv, lists, stride, counts, prm->max_dist, prm->ordered,
+    projected_resolve_kernel<<<1, PR_THREADS, lock_bytes, ctx->stream>>>(v, pv, lists, offs, counts, prm->max_dist, prm->ordered,
                                                                         prm->check_ori, kp_locked ? (const uint8_t *)(D + o_kl) : nullptr,
                                                                         choice, d_bd, kp_owner ? d_owner : nullptr, d_nm, ctx->d_counters);
     ctx->launches += 2;
     CU_TRY(cudaGetLastError());
     const OutPiece out[4] = {{best_idx, choice, (size_t)M * 4}, {best_dist, d_bd, (size_t)M * 4},
                              {kp_owner, kp_owner ? d_owner : nullptr, (size_t)n * 4}, {nmatches, d_nm, 4}};
-    return ctx_download(ctx, out, 4);
+    rc = ctx_download(ctx, out, 4);
+    if (rc) return rc;
+    if (list_pool_overflowed(ctx, pool_cap)) // the pool was too small for these windows: once more with the size the kernels counted
+        return orbgpu_search_projected(ctx, f, pts, prm, kp_locked, best_idx, best_dist, kp_owner, nmatches);
+    return ORBGPU_OK;
 }
 
 int search_projected_device_init() { return set_max_dyn_smem(projected_resolve_kernel); }

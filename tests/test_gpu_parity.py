@@ -781,3 +781,32 @@ def test_triangulation_shared_keyframes(ctx, M, oracle):
         ctx.set_triangulation_engine(0)
         assert np.array_equal(nm, enm) and np.array_equal(m, em), engine
     assert enm.shape[0] == 192 and enm[0] > 50 and enm[7] > 20  # nearer neighbours share more landmarks
+
+
+def test_candidate_pool_regrow(M, oracle):
+    """the candidate lists of the projection searches live in a pool sized for ~64 candidates per point; wide windows need more: the
+    kernels count what they would have written, the host sees the count exceed the capacity and repeats the call with a pool of that
+    size (twice the launches on the first call of a fresh context, none extra on the second).  Results equal the oracle's either way."""
+    from orb_slam3_comments_ghr_b200 import matcher
+    from orb_slam3_comments_ghr_b200._abi import HostLocalPoints, frustum_struct
+    ctx = matcher.Context(0)  # a fresh context: no pool hint yet
+    frame, pts, kl = synth.make_projected_case(191, n_kp=6000, n_pts=1500, th=60.0)
+    d = ctx.upload_frame(frame)
+    m = M.ORBmatcher(0.9, True, ctx)
+    exp = oracle.search_projected(frame, pts, 100.0, 1, kl, check_ori=1)
+    l0 = ctx.launch_count
+    got = m.SearchProjected(d, pts, 100.0, True, kl)
+    l1 = ctx.launch_count
+    got2 = m.SearchProjected(d, pts, 100.0, True, kl)
+    l2 = ctx.launch_count
+    for g in (got, got2):
+        assert g[0] == exp[0] and all(np.array_equal(a, b) for a, b in zip(g[1:], exp[1:]))
+    assert l1 - l0 == 4 and l2 - l1 == 2, (l1 - l0, l2 - l1)
+    # SearchByProjection(Frame, MapPoints): in/out F.mvpMapPoints must survive the repeated call
+    ctx2 = matcher.Context(0)
+    c = synth.make_projection_case(192, n_kp=8000, n_mp=3000, th=30.0)
+    d2 = ctx2.upload_frame(c.frame)
+    l0 = ctx2.launch_count
+    g = M.ORBmatcher(c.nnratio, True, ctx2).SearchByProjection(d2, c.mps, 30.0, False, 50.0, c.kp_prior_obs, c.kp_mp)
+    e = oracle.search_by_projection_local(c.frame, c.mps, 30.0, 0, 50.0, c.nnratio, c.kp_prior_obs, c.kp_mp)
+    assert g[0] == e[0] and np.array_equal(g[1], e[1]) and ctx2.launch_count - l0 == 4
