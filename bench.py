@@ -698,8 +698,9 @@ def bench_single_frame(E):
                                      "roofline_hbm": {"bound": "hbm", "bytes_per_pair": bytes_pair, "achieved": Kc * bytes_pair / (gb * 1e-6) / 1e9,
                                                       "peak": float(E.peaks.get("hbm_gbs", 6650.0)), "unit": "GB/s",
                                                       "frac": Kc * bytes_pair / (gb * 1e-6) / 1e9 / float(E.peaks.get("hbm_gbs", 6650.0))},
-                                     "note": "the K searches are enqueued back to back with one upload, one download and one synchronisation; each is still "
-                                             "a few ~100-CTA launches, so the call is launch-bound far below the HBM roofline (stated, not claimed)"}
+                                     "note": "ONE match launch over (node, key frame) and one cull launch for all K searches, one upload, one download, one "
+                                             "synchronisation; the call is ~80 us of fixed host / launch / copy latency plus ~4 us per candidate: "
+                                             "latency-bound far below the HBM roofline (stated, not claimed)"}
             del dks
     return out
 

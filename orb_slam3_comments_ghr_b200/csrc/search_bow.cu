@@ -8,6 +8,7 @@
 // the other FeatureVector), keyframe features replayed in order inside the CTA, threads over the
 // partner's features with a block-wide lexicographic (distance, position) top-2.  The rotation
 // histogram is accumulated with atomics (bin sizes are order independent) and culled afterwards.
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -41,10 +42,11 @@ __device__ __forceinline__ int bow_partner(const FrameView &f, uint32_t nid)
 // MODE 0: KF <-> F   (match indexed by F feature, value = KF feature)
 // MODE 1: KF1 <-> KF2 (match indexed by KF1 feature, value = KF2 feature)
 template <int MODE>
-__global__ void bow_match_kernel(FrameView kf, FrameView f, const uint8_t *__restrict__ kf_valid,
-                                 const uint8_t *__restrict__ f_valid, float nnratio, int check_ori, int32_t *match,
-                                 uint8_t *matched2, int32_t *__restrict__ bin_of, int *__restrict__ hist, int *__restrict__ nmatches,
-                                 unsigned long long *__restrict__ counters, int stage_cap, int skip_big)
+__device__ __forceinline__ void bow_match_body(const int a, const FrameView &kf, const FrameView &f, const uint8_t *__restrict__ kf_valid,
+                                               const uint8_t *__restrict__ f_valid, float nnratio, int check_ori, int32_t *match,
+                                               uint8_t *matched2, int32_t *__restrict__ bin_of, int *__restrict__ hist,
+                                               int *__restrict__ nmatches, unsigned long long *__restrict__ counters, int stage_cap,
+                                               int skip_big)
 {
     // optional staging (dynamic shared memory, stage_cap descriptors): when the partner node fits, its descriptors and
     // "already matched" flags are copied once and every keyframe feature of the node is replayed against shared memory --
@@ -52,7 +54,6 @@ __global__ void bow_match_kernel(FrameView kf, FrameView f, const uint8_t *__res
     extern __shared__ uint4 bow_smem[];
     __shared__ uint32_t wm1[BOW_MAX_WARPS], wm2[BOW_MAX_WARPS];
     __shared__ int s_b;
-    const int a = blockIdx.x;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
     if (t == 0) s_b = bow_partner(f, kf.fv_node_ids[a]);
     __syncthreads();
@@ -366,8 +367,52 @@ __global__ void bow_big_resolve_kernel(FrameView kf, FrameView f, const uint8_t 
     if (lane == 0 && my_matches) atomicAdd(nmatches, my_matches);
 }
 
+template <int MODE>
+__global__ void bow_match_kernel(FrameView kf, FrameView f, const uint8_t *__restrict__ kf_valid,
+                                 const uint8_t *__restrict__ f_valid, float nnratio, int check_ori, int32_t *match,
+                                 uint8_t *matched2, int32_t *__restrict__ bin_of, int *__restrict__ hist, int *__restrict__ nmatches,
+                                 unsigned long long *__restrict__ counters, int stage_cap, int skip_big)
+{
+    bow_match_body<MODE>(blockIdx.x, kf, f, kf_valid, f_valid, nnratio, check_ori, match, matched2, bin_of, hist, nmatches, counters, stage_cap,
+                         skip_big);
+}
+
+// One frame against K key frames (the relocalisation loop): blockIdx.y = key frame, blockIdx.x = node of that key frame.  ONE launch
+// for all K searches; the per-key-frame arguments are read from a device array.
+struct BowBatchArg {
+    FrameView kf;
+    const uint8_t *kf_valid;
+    int32_t *match, *bin_of;
+    uint8_t *matched2;
+    int *hist; // [64]: [0..29] histogram, [32] nmatches
+    int skip_big;
+};
+__global__ void bow_match_batch_kernel(const BowBatchArg *__restrict__ args, FrameView f, float nnratio, int check_ori,
+                                       unsigned long long *__restrict__ counters, int stage_cap)
+{
+    const BowBatchArg &A = args[blockIdx.y];
+    if ((int)blockIdx.x >= A.kf.fv_n_nodes) return;
+    bow_match_body<0>(blockIdx.x, A.kf, f, A.kf_valid, nullptr, nnratio, check_ori, A.match, A.matched2, A.bin_of, A.hist, A.hist + 32, counters,
+                      stage_cap, A.skip_big);
+}
+
+__device__ __forceinline__ void bow_cull_body(int n, int check_ori, int32_t *__restrict__ match, const int32_t *__restrict__ bin_of,
+                                              const int *__restrict__ hist, int *__restrict__ nmatches);
+__global__ void bow_cull_batch_kernel(const BowBatchArg *__restrict__ args, int n, int check_ori)
+{
+    const BowBatchArg &A = args[blockIdx.x];
+    if (!A.match) return; // a pair that went through its own launches (big node pairs)
+    bow_cull_body(n, check_ori, A.match, A.bin_of, A.hist, A.hist + 32);
+}
+
 __global__ void bow_cull_kernel(int n, int check_ori, int32_t *__restrict__ match, const int32_t *__restrict__ bin_of,
                                 const int *__restrict__ hist, int *__restrict__ nmatches)
+{
+    bow_cull_body(n, check_ori, match, bin_of, hist, nmatches);
+}
+
+__device__ __forceinline__ void bow_cull_body(int n, int check_ori, int32_t *__restrict__ match, const int32_t *__restrict__ bin_of,
+                                              const int *__restrict__ hist, int *__restrict__ nmatches)
 {
     __shared__ int ind[3];
     __shared__ int removed;
@@ -494,8 +539,8 @@ int run_bow(orbgpu_ctx *ctx, int mode, const orbgpu_frame *kf, const orbgpu_fram
 }
 
 // One frame against K candidate key frames (Tracking::Relocalization, Tracking.cc:4469-4495; the loop / merge candidate loops of
-// LoopClosing): the K searches are enqueued back to back on the context's stream with ONE upload of the K validity masks, ONE
-// download of the K match vectors and ONE synchronisation.
+// LoopClosing): ONE match launch over (node, key frame) and ONE cull launch for all K searches, one upload of the arguments and
+// validity masks, two memsets, one download and one synchronisation.  Key frames that need the big-node fixed point keep their own launches.
 int run_bow_batch(orbgpu_ctx *ctx, int K, const orbgpu_frame *const *kfs, const orbgpu_frame *f, const uint8_t *const *kf_valid, float nnratio,
                   int check_ori, int32_t *match_out, int32_t *nmatches)
 {
@@ -512,20 +557,52 @@ int run_bow_batch(orbgpu_ctx *ctx, int K, const orbgpu_frame *const *kfs, const 
         mask_off[k] = mask_bytes;
         mask_bytes += align256(kfs[k]->n + 1);
     }
-    rc = stage_reserve(ctx, mask_bytes + 256);
+    const size_t arg_bytes = align256((size_t)K * sizeof(BowBatchArg));
+    rc = stage_reserve(ctx, mask_bytes + arg_bytes + 256);
     if (rc) return rc;
-    rc = arena_reserve(ctx, total + align256(mask_bytes) + align256(f->n + 1));
+    rc = arena_reserve(ctx, total + align256(mask_bytes) + arg_bytes + align256(f->n + 1));
     if (rc) return rc;
     char *ff = (char *)arena_take(ctx, K * ffb), *zero = (char *)arena_take(ctx, K * zb);
     int32_t *d_out = (int32_t *)arena_take(ctx, (size_t)K * n_out * 4 + 4 * K);
-    uint8_t *d_masks = (uint8_t *)arena_take(ctx, mask_bytes + 1), *d_fv = (uint8_t *)arena_take(ctx, f->n + 1);
-    if (!ff || !zero || !d_out || !d_masks || !d_fv) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
-    for (int k = 0; k < K; k++)
-        if (kfs[k]->n) memcpy(ctx->h_stage + mask_off[k], kf_valid[k], kfs[k]->n);
-    CU_TRY(cudaMemcpyAsync(d_masks, ctx->h_stage, mask_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t *d_up = (uint8_t *)arena_take(ctx, mask_bytes + arg_bytes), *d_fv = (uint8_t *)arena_take(ctx, f->n + 1);
+    if (!ff || !zero || !d_out || !d_up || !d_fv) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
+    uint8_t *d_masks = d_up + arg_bytes;
+    // per-key-frame arguments of the batch kernels + the validity masks: one pinned block, one H2D copy
+    BowBatchArg *h_args = (BowBatchArg *)ctx->h_stage;
+    int max_nodes = 0, n_big = 0;
+    std::vector<char> is_big(K, 0);
+    for (int k = 0; k < K; k++) {
+        bool big = false;
+        bow_scratch_bytes(kfs[k], f, 0, &big);
+        is_big[k] = big;
+        n_big += big;
+        const BowBlock blk = bow_block(ff + k * ffb, zero + k * zb, n_out);
+        BowBatchArg &A = h_args[k];
+        A.kf = frame_view(kfs[k]);
+        A.kf_valid = d_masks + mask_off[k];
+        A.match = big ? nullptr : blk.d_match;
+        A.bin_of = blk.d_bin; A.matched2 = blk.d_m2; A.hist = blk.d_hist; A.skip_big = 0;
+        if (big || f->fv_n_nodes == 0) A.kf.fv_n_nodes = 0; // its blocks exit at once
+        max_nodes = std::max(max_nodes, A.kf.fv_n_nodes);
+        if (kfs[k]->n) memcpy(ctx->h_stage + arg_bytes + mask_off[k], kf_valid[k], kfs[k]->n);
+    }
+    CU_TRY(cudaMemcpyAsync(d_up, ctx->h_stage, arg_bytes + mask_bytes, cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(cudaMemsetAsync(ff, 0xFF, K * ffb, ctx->stream)); // the match / bin vectors of ALL pairs
     CU_TRY(cudaMemsetAsync(zero, 0, K * zb, ctx->stream));   // histograms, counts and taken flags of ALL pairs
-    for (int k = 0; k < K; k++) {
+    if (max_nodes > 0) { // ONE launch for all the ordinary pairs: blockIdx.y = key frame, blockIdx.x = node
+        const int threads = f->fv_max_node <= 32 ? 32 : (f->fv_max_node <= 512 ? 128 : (f->fv_max_node <= 1024 ? 256 : 1024));
+        int stage_cap = f->fv_max_node > 64 ? f->fv_max_node : 0;
+        if (stage_cap > 4800) stage_cap = 4800;
+        stage_cap = (stage_cap + 15) & ~15;
+        const size_t smem = (size_t)stage_cap * 41;
+        bow_match_batch_kernel<<<dim3(max_nodes, K), threads, smem, ctx->stream>>>((const BowBatchArg *)d_up, frame_view(f), nnratio, check_ori,
+                                                                                   ctx->d_counters, stage_cap);
+        bow_cull_batch_kernel<<<K, 256, 0, ctx->stream>>>((const BowBatchArg *)d_up, n_out, check_ori);
+        ctx->launches += 2;
+        CU_TRY(cudaGetLastError());
+    }
+    for (int k = 0; k < K && n_big; k++) { // key frames with a big node pair (one root bucket): the fixed-point path, their own launches
+        if (!is_big[k]) continue;
         rc = bow_enqueue(ctx, 0, kfs[k], f, d_masks + mask_off[k], d_fv, nnratio, check_ori, bow_block(ff + k * ffb, zero + k * zb, n_out));
         if (rc) return rc;
     }
@@ -592,6 +669,7 @@ extern "C" int orbgpu_search_by_bow_kf_f_batch(orbgpu_ctx *ctx, int32_t n_kf, co
 int search_bow_device_init()
 {
     int rc;
+    if ((rc = set_max_dyn_smem(bow_match_batch_kernel))) return rc;
     if ((rc = set_max_dyn_smem(bow_match_kernel<0>)) || (rc = set_max_dyn_smem(bow_match_kernel<1>)) ||
         (rc = set_max_dyn_smem(bow_big_resolve_kernel<0>)) || (rc = set_max_dyn_smem(bow_big_resolve_kernel<1>)))
         return rc;
