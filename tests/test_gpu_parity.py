@@ -810,3 +810,40 @@ def test_candidate_pool_regrow(M, oracle):
     g = M.ORBmatcher(c.nnratio, True, ctx2).SearchByProjection(d2, c.mps, 30.0, False, 50.0, c.kp_prior_obs, c.kp_mp)
     e = oracle.search_by_projection_local(c.frame, c.mps, 30.0, 0, 50.0, c.nnratio, c.kp_prior_obs, c.kp_mp)
     assert g[0] == e[0] and np.array_equal(g[1], e[1]) and ctx2.launch_count - l0 == 4
+
+
+def test_round2_entry_points_edge_cases(ctx, M, oracle):
+    """empty and degenerate inputs of the entry points added in round 2: no map points, an empty frame, every point skipped, an empty
+    candidate list, an empty descriptor list"""
+    import ctypes as C
+    from orb_slam3_comments_ghr_b200._abi import HostLocalPoints, frustum_struct, u8p, u32p, f64p, i32p
+    c = synth.make_frustum_case(731, n_kp=300, n_mp=200)
+    f = c.frame
+    fr = frustum_struct(c.Rcw, c.tcw, c.Ow, c.K, c.mbf, (f.min_x, f.min_y, f.max_x, f.max_y), c.viewing_cos_limit, c.log_scale_factor, 8)
+    d = ctx.upload_frame(f)
+    m = M.ORBmatcher(0.8, True, ctx)
+    # no map points
+    e = np.zeros((0,), dtype=np.float32)
+    empty = HostLocalPoints(np.zeros((0, 32), np.uint8), np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), e, e,
+                            np.zeros(0, np.uint8), np.zeros(0, np.int32))
+    n, kp, iv = m.SearchLocalPoints(d, fr, empty, 3.0, False, 50.0, c.kp_prior_obs, c.kp_mp)
+    assert n == 0 and np.array_equal(kp, c.kp_mp) and iv.size == 0
+    # every point skipped: nothing in view, nothing matched, F.mvpMapPoints untouched
+    pts = HostLocalPoints(c.desc, c.world_pos, c.normal, c.min_distance, c.max_distance, c.bad, c.n_obs, skip=np.ones(c.desc.shape[0], np.uint8))
+    n, kp, iv = m.SearchLocalPoints(d, fr, pts, 3.0, False, 50.0, c.kp_prior_obs, c.kp_mp)
+    assert n == 0 and np.array_equal(kp, c.kp_mp) and not iv.any()
+    g = ctx.is_in_frustum(fr, np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), e, e)
+    assert g["in_view"].size == 0
+    # an empty candidate list for the batched SearchByBoW
+    nm, out = m.SearchByBoWBatch([], d, [])
+    assert nm.size == 0 and out.shape[0] == 0
+    # transform of an empty descriptor list
+    voc = ctx.upload_vocabulary(golden_voc())
+    L = M.load_library()
+    L.orbgpu_transform_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, u8p, C.c_int32, C.POINTER(C.c_int32), u32p, f64p,
+                                               C.POINTER(C.c_int32), u32p, i32p, u32p]
+    nw, nn = C.c_int32(7), C.c_int32(7)
+    off = np.full(1, 5, dtype=np.int32)
+    rc = L.orbgpu_transform_descriptors(ctx.handle, voc.handle, 0, C.cast(None, u8p), 4, C.byref(nw), C.cast(None, u32p), C.cast(None, f64p),
+                                        C.byref(nn), C.cast(None, u32p), off.ctypes.data_as(i32p), C.cast(None, u32p))
+    assert rc == 0 and nw.value == 0 and nn.value == 0 and off[0] == 0
