@@ -355,6 +355,26 @@ def bench_c5(E, args, K, W):
         if world > 1:
             h2d += 16 * nq
             d2h += 16 * nq_total
+        # the same call with the database resident (uploaded and expanded once, like the map it stands for): queries H2D, results D2H
+        def e2e_resident_step():
+            bi, bd, sd, mt = m.SearchByNN(hdb, q_h, TH_LOW)
+            if world > 1:
+                host_res[:, 0], host_res[:, 1] = torch.from_numpy(bi), torch.from_numpy(bd)
+                host_res[:, 2], host_res[:, 3] = torch.from_numpy(sd), torch.from_numpy(mt)
+                dev_res.copy_(host_res, non_blocking=True)
+                return all_gather_rows(dev_res, nq_total, out=gathered).cpu()
+            return mt
+
+        e2e_resident_step()
+        E.barrier_sync()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            e2e_resident_step()
+        torch.cuda.synchronize()
+        dt_res = E.max_over_ranks((time.perf_counter() - t0) / max(Ke, 1))
+        extra["e2e_database_resident"] = {"value": units_total / dt_res, "unit": "hamming_comparisons/s", "ms_per_step": dt_res * 1e3,
+                                          "h2d_bytes_per_step": int(q_h.nbytes + (16 * nq if world > 1 else 0)), "d2h_bytes_per_step": int(d2h),
+                                          "note": "as e2e, but the database stays on the device between steps (only the queries travel)"}
         e2e = {"value": units_total / dt, "unit": "hamming_comparisons/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": dt * 1e3, "steps": Ke,
                "note": "host-pointer C-ABI call from pinned host buffers; re-uploads (and re-expands) the 128 MiB database every step"
