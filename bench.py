@@ -463,14 +463,17 @@ def bench_reloc(E, args):
             "l2": "L2 flushed between calls"}
 
 
-def bench_c4(E, args, K, W, shared=False):
-    """shared=False: BASELINE's config, 4096 INDEPENDENT key-frame pairs (8192 key frames, 870 MB resident).  shared=True: the
+def bench_c4(E, args, K, W, shared=False, weak=False):
+    """weak=True: every rank keeps the WHOLE single-GPU workload (--pairs independent pairs per GPU, N x that in the job) and still
+    receives the compact vMatchedPairs of all N x pairs through the fused gather -- the partitioned-path reading of the scaling run;
+    the default (strong) shards the fixed --pairs over the ranks.
+    shared=False: BASELINE's config, 4096 INDEPENDENT key-frame pairs (8192 key frames, 870 MB resident).  shared=True: the
     shared-key-frame variant of SURVEY 8(d) -- 512 key frames, each against its 8 nearest neighbours (the shape of
     LocalMapping::CreateNewMapPoints): the same 4096 pairs over a 54 MB key-frame set that stays L2 resident within a step."""
     torch, dist, matcher, synth = E.torch, E.dist, E.matcher, E.synth
     from orb_slam3_comments_ghr_b200.sharding import TriangulationGather, shard_bounds
     dev, rank, world = E.dev, E.rank, E.world
-    P_total = args.pairs
+    P_total = args.pairs * (world if weak else 1)
     if P_total % world != 0:
         raise SystemExit("--pairs must be divisible by the number of GPUs")
     lo, hi = shard_bounds(P_total, rank, world)
@@ -559,7 +562,7 @@ def bench_c4(E, args, K, W, shared=False):
 
     # ---- end to end: pinned host inputs -> device, the sharded search + gather, the vMatchedPairs of ALL pairs back on the host
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not weak:
         Ke = 5
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
         if world == 1:
@@ -626,8 +629,8 @@ def bench_c4(E, args, K, W, shared=False):
             except Exception as e:
                 cpu = {"value": None, "error": repr(e)}
         line = {"metric": "frame_pairs_matched_per_s", "value": value, "unit": "frame_pairs/s", "n_gpus": world, "steps": K4, "warmup": max(W, 3),
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
-                "data": "synthetic", "config": workload_config("c4", args) if not shared else
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "u8",
+                "data": "synthetic", "pairs_total": P_total, "pairs_per_gpu": P, "config": workload_config("c4", args) if not shared else
                 {"workload": f"C4 shared-key-frame variant: {P_total // 8} keyframes x 8 neighbours = {P_total} pairs x {C4_FEAT} features "
                              "(LocalMapping::CreateNewMapPoints shape, LocalMapping.cc:556-630)", "pairs": P_total, "n_feat": C4_FEAT,
                  "l2": "L2 flushed (512 MiB write) between timed steps; within a step every key frame is read 16 times and stays in L2"},
@@ -829,6 +832,15 @@ def main():
             except Exception as e:  # the secondary block never costs the headline line
                 secondary["c4"] = {"error": repr(e)}
                 if world > 1:
+                    raise
+            if world > 1:
+                # the same kernel with the per-GPU work held at the single-GPU workload (the fixed 4096-pair job above leaves 512
+                # pairs = 3.5 per CTA on each of 8 GPUs, where the kernel's ~24 us fixed latency dominates)
+                torch.cuda.empty_cache()
+                try:
+                    secondary["c4_weak"] = bench_c4(E, args, K, W, weak=True)
+                except Exception as e:
+                    secondary["c4_weak"] = {"error": repr(e)}
                     raise
             if world == 1:
                 try:

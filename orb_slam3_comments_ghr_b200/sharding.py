@@ -81,8 +81,10 @@ class TriangulationGather:
         self.p_total, self.n_feat = p_total, n_feat
         assert p_total % world == 0 and n_feat % 4 == 0
         self.lo, self.hi = shard_bounds(p_total, rank, world)
-        self.side = torch.cuda.Stream(device=device)
-        self.ctx = matcher_mod.Context(device.index, stream=self.side.cuda_stream)
+        # graph replays need a capturable (non-default) stream; the direct launch goes on the caller's current stream, with no
+        # cross-stream event hops around the one kernel of the step
+        self.side = torch.cuda.Stream(device=device) if use_graph else None
+        self.ctx = matcher_mod.Context(device.index, stream=(self.side or torch.cuda.current_stream(device)).cuda_stream)
         self.m = matcher_mod.ORBmatcher(nnratio, check_ori, self.ctx)
         self.ks = self.ctx.upload_kfset(kfset_host)
         if world > 1:
@@ -149,6 +151,8 @@ class TriangulationGather:
         self.k += 1
         if self.graphs is not None:
             self.graphs[b].replay()
+        elif self.side is None:
+            self._launch(b)
         else:
             cur = torch.cuda.current_stream(self.dev)
             self.side.wait_stream(cur)
@@ -159,8 +163,8 @@ class TriangulationGather:
 
     def download(self, counts: torch.Tensor, entries: torch.Tensor, out=None):
         """the gathered result of a step on the host: (pair_offsets[P_total + 1], pairs[total, 2]) -- vMatchedPairs of ALL pairs"""
-        cur = torch.cuda.current_stream(self.dev)
-        self.side.wait_stream(cur)  # the step was replayed / launched on the current stream; the download runs on the context's
+        if self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream(self.dev))  # the step was replayed on the current stream; the download runs on the context's
         offs, pairs = self.m.TriangulationGatherDownload(self.p_total, self.n_feat, counts.data_ptr(), entries.data_ptr(), out=out)
         return offs, pairs
 
