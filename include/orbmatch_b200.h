@@ -279,6 +279,12 @@ int orbgpu_search_by_bow_kf_f_batch(orbgpu_ctx *ctx, int32_t n_kf, const orbgpu_
 int orbgpu_search_by_bow_kf_kf(orbgpu_ctx *ctx, const orbgpu_frame *kf1, const orbgpu_frame *kf2,
                                const uint8_t *kf1_mp_valid, const uint8_t *kf2_mp_valid, float nnratio, int32_t check_ori,
                                int32_t *match_12, int32_t *nmatches);
+/* The current key frame against the n_kf key frames of a candidate's covisibility window -- the loop / merge detection loop
+ * (LoopClosing.cc:909-925: matcherBoW.SearchByBoW(mpCurrentKF, vpCovKFi[j], vvpMatchedMPs[j]) for every j) -- in ONE call, one launch
+ * over (node, window key frame).  match_12 [n_kf][kf1.N], nmatches [n_kf]; results identical to n_kf separate calls. */
+int orbgpu_search_by_bow_kf_kf_batch(orbgpu_ctx *ctx, const orbgpu_frame *kf1, const uint8_t *kf1_mp_valid, int32_t n_kf,
+                                     const orbgpu_frame *const *kf2s, const uint8_t *const *kf2_mp_valid, float nnratio,
+                                     int32_t check_ori, int32_t *match_12, int32_t *nmatches);
 
 /* ---- a8/a9: batched ORBmatcher::SearchForTriangulation (ORBmatcher.cc:1045-1328) with
  * Pinhole::epipolarConstrain (Pinhole.cpp:189-219), monocular pinhole path.

@@ -29,6 +29,7 @@
 #include <string>
 #include <tuple>
 #include <utility>
+#include <memory>
 #include <vector>
 
 #include <orbmatch_b200.h> // compile with -I<repo>/include
@@ -120,7 +121,8 @@ namespace orbgpu
     // still change afterwards -- the FeatureVector (ComputeBoW runs once, later) and whether mvuRight is needed.  A repeated call on
     // the same Frame / KeyFrame (TrackReferenceKeyFrame then TrackLocalMap on the current frame; a key frame matched against each of
     // its neighbours in CreateNewMapPoints / SearchInNeighbors / loop detection) skips the pack + upload + grid build, which cost
-    // more than the search itself.  Bounded LRU; set_frame_cache_capacity(0) turns it off.
+    // more than the search itself.  Bounded LRU; set_frame_cache_capacity(0) turns it off.  Entries referenced by a call in progress
+    // (a batched search holds K + 1 of them) are pinned: eviction skips them, and the cache may exceed its capacity until they are released.
     struct FrameCache
     {
         struct Key
@@ -131,7 +133,7 @@ namespace orbgpu
             size_t fv_nodes;
             bool operator==(const Key &o) const { return kind == o.kind && id == o.id && n == o.n && with_uright == o.with_uright && fv_nodes == o.fv_nodes; }
         };
-        struct Entry { Key key; orbgpu_frame *f; unsigned long stamp; };
+        struct Entry { Key key; orbgpu_frame *f; unsigned long stamp; int pins; };
         std::vector<Entry> entries;
         unsigned long clock = 0, hits = 0, misses = 0;
         size_t capacity = 48;
@@ -144,25 +146,31 @@ namespace orbgpu
         orbgpu_frame *find(const Key &k)
         {
             for (Entry &e : entries)
-                if (e.key == k) { e.stamp = ++clock; hits++; return e.f; }
+                if (e.key == k) { e.stamp = ++clock; e.pins++; hits++; return e.f; }
             misses++;
             return nullptr;
+        }
+        void unpin(const orbgpu_frame *f)
+        {
+            for (Entry &e : entries)
+                if (e.f == f) { if (e.pins > 0) e.pins--; return; }
         }
         void insert(const Key &k, orbgpu_frame *f)
         {
             // an older copy of the same object (its FeatureVector has been computed since) is dropped, then the least recently used
             for (size_t i = 0; i < entries.size();)
-                if (entries[i].key.kind == k.kind && entries[i].key.id == k.id) { orbgpu_frame_destroy(entries[i].f); entries.erase(entries.begin() + i); }
+                if (entries[i].key.kind == k.kind && entries[i].key.id == k.id && entries[i].pins == 0) { orbgpu_frame_destroy(entries[i].f); entries.erase(entries.begin() + i); }
                 else i++;
-            while (entries.size() >= capacity && !entries.empty())
+            while (entries.size() >= capacity)
             {
-                size_t lru = 0;
-                for (size_t i = 1; i < entries.size(); i++)
-                    if (entries[i].stamp < entries[lru].stamp) lru = i;
+                size_t lru = entries.size();
+                for (size_t i = 0; i < entries.size(); i++)
+                    if (entries[i].pins == 0 && (lru == entries.size() || entries[i].stamp < entries[lru].stamp)) lru = i;
+                if (lru == entries.size()) break; // everything is in use by the call in progress
                 orbgpu_frame_destroy(entries[lru].f);
                 entries.erase(entries.begin() + lru);
             }
-            entries.push_back(Entry{k, f, ++clock});
+            entries.push_back(Entry{k, f, ++clock, 1});
         }
     };
     // the cache lives and dies with the thread's context (its frames were uploaded on that context's stream)
@@ -193,7 +201,11 @@ namespace orbgpu
             if (c.capacity > 0) c.insert(k, f);
             else owned = true;
         }
-        ~FrameRef() { if (owned) orbgpu_frame_destroy(f); }
+        ~FrameRef()
+        {
+            if (owned) orbgpu_frame_destroy(f);
+            else if (f) frame_cache().unpin(f);
+        }
         FrameRef(const FrameRef &) = delete;
         FrameRef &operator=(const FrameRef &) = delete;
     };
@@ -492,6 +504,23 @@ namespace orbgpu
             for (int i = 0; i < pKF1->N; i++)
                 if (m[i] >= 0) vpMatches12[i] = vp2[m[i]]; // :989
             return nmatches;
+        }
+
+        // Batched forms of the two SearchByBoW overloads (not in ORBmatcher.h: the reference calls them in a loop).  One device call
+        // for the whole loop; entry i equals what the single call on vpKFs[i] returns.  NULL entries are skipped (0 matches).
+        //   Tracking::Relocalization (Tracking.cc:4469-4495):  vnMatches[i] = SearchByBoW(vpKFs[i], F, vvpMapPointMatches[i])
+        void SearchByBoW(const std::vector<KeyFrameT *> &vpKFs, FrameT &F, std::vector<std::vector<MapPointT *>> &vvpMapPointMatches,
+                         std::vector<int> &vnMatches)
+        {
+            bow_batch(0, vpKFs, F, F.mnMinX, F.mnMinY, F.mnMaxX, F.mnMaxY, nullptr, vvpMapPointMatches, vnMatches);
+        }
+        //   LoopClosing's candidate window (LoopClosing.cc:909-925):  vnMatches[j] = SearchByBoW(pKF1, vpKF2s[j], vvpMatches12[j])
+        void SearchByBoW(KeyFrameT *pKF1, const std::vector<KeyFrameT *> &vpKF2s, std::vector<std::vector<MapPointT *>> &vvpMatches12,
+                         std::vector<int> &vnMatches)
+        {
+            const std::vector<MapPointT *> vp1 = pKF1->GetMapPointMatches();
+            bow_batch(1, vpKF2s, *pKF1, (float)pKF1->mnMinX, (float)pKF1->mnMinY, (float)pKF1->mnMaxX, (float)pKF1->mnMaxY, &vp1, vvpMatches12,
+                      vnMatches);
         }
 
         // ORBmatcher.h:72 (ORBmatcher.cc:1045-1328), monocular pinhole path (mpCamera2 == NULL).
@@ -850,6 +879,58 @@ namespace orbgpu
         }
 
     protected:
+        // mode 0: K key frames against the frame `fixed` (results indexed by the frame's features, values = the key frames' map points);
+        // mode 1: the key frame `fixed` (map points *vpFixed) against K key frames (indexed by its features, values = theirs)
+        template <class FS>
+        void bow_batch(int mode, const std::vector<KeyFrameT *> &vpKFs, FS &fixed, float minX, float minY, float maxX, float maxY,
+                       const std::vector<MapPointT *> *vpFixed, std::vector<std::vector<MapPointT *>> &vvpMatches, std::vector<int> &vnMatches)
+        {
+            orbgpu_ctx *ctx = thread_context();
+            const size_t K_all = vpKFs.size();
+            vvpMatches.assign(K_all, std::vector<MapPointT *>());
+            vnMatches.assign(K_all, 0);
+            std::vector<size_t> live;
+            for (size_t i = 0; i < K_all; i++)
+                if (vpKFs[i]) live.push_back(i);
+            const int K = (int)live.size(), n_out = fixed.N;
+            if (K == 0) return;
+            FrameRef dfix(ctx, mode == 0 ? 0 : 1, fixed, minX, minY, maxX, maxY, false);
+            std::vector<std::unique_ptr<FrameRef>> refs;
+            std::vector<const orbgpu_frame *> handles(K);
+            std::vector<std::vector<MapPointT *>> vps(K);
+            std::vector<std::vector<uint8_t>> valid(K);
+            std::vector<const uint8_t *> valid_ptr(K);
+            for (int k = 0; k < K; k++)
+            {
+                KeyFrameT *pKF = vpKFs[live[k]];
+                vps[k] = pKF->GetMapPointMatches();
+                refs.emplace_back(new FrameRef(ctx, 1, *pKF, (float)pKF->mnMinX, (float)pKF->mnMinY, (float)pKF->mnMaxX, (float)pKF->mnMaxY, false));
+                handles[k] = refs.back()->f;
+                valid[k].assign(pKF->N > 0 ? pKF->N : 1, 0);
+                for (int i = 0; i < pKF->N; i++) valid[k][i] = (vps[k][i] && !vps[k][i]->isBad()) ? 1 : 0; // :311-315 / :941-957
+                valid_ptr[k] = valid[k].data();
+            }
+            std::vector<int32_t> m((size_t)K * (n_out > 0 ? n_out : 1), -1), nm(K, 0);
+            if (mode == 0)
+                check(orbgpu_search_by_bow_kf_f_batch(ctx, K, handles.data(), dfix.f, valid_ptr.data(), mfNNratio, mbCheckOrientation ? 1 : 0,
+                                                      m.data(), nm.data()));
+            else
+            {
+                std::vector<uint8_t> v1(n_out > 0 ? n_out : 1, 0);
+                for (int i = 0; i < n_out; i++) v1[i] = ((*vpFixed)[i] && !(*vpFixed)[i]->isBad()) ? 1 : 0;
+                check(orbgpu_search_by_bow_kf_kf_batch(ctx, dfix.f, v1.data(), K, handles.data(), valid_ptr.data(), mfNNratio,
+                                                       mbCheckOrientation ? 1 : 0, m.data(), nm.data()));
+            }
+            for (int k = 0; k < K; k++)
+            {
+                std::vector<MapPointT *> &out = vvpMatches[live[k]];
+                out.assign(mode == 0 ? (size_t)n_out : vpFixed->size(), static_cast<MapPointT *>(NULL)); // :268 / :904
+                for (int i = 0; i < n_out; i++)
+                    if (m[(size_t)k * n_out + i] >= 0) out[i] = vps[k][m[(size_t)k * n_out + i]]; // :398 / :989
+                vnMatches[live[k]] = nm[k];
+            }
+        }
+
         // writes the GPU's owner table into the caller's map-point slots: a keypoint some point took ends up holding the
         // last taker, or NULL when the rotation histogram culled it (ORBmatcher.cc:2074 + :2163-2186, :2290 + :2310-2325)
         template <class Get>

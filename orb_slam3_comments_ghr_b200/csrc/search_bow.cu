@@ -377,23 +377,30 @@ __global__ void bow_match_kernel(FrameView kf, FrameView f, const uint8_t *__res
                          skip_big);
 }
 
-// One frame against K key frames (the relocalisation loop): blockIdx.y = key frame, blockIdx.x = node of that key frame.  ONE launch
-// for all K searches; the per-key-frame arguments are read from a device array.
+// One frame (or key frame) against K key frames -- the relocalisation loop (MODE 0: the K key frames are the `kf` side, the frame is
+// fixed) and the loop / merge candidate window (MODE 1: the current key frame is the fixed `kf` side, the K window key frames are the
+// `f` side).  blockIdx.y = pair, blockIdx.x = node of the pair's `kf` side.  ONE launch for all K searches; the per-pair arguments are
+// read from a device array.
 struct BowBatchArg {
-    FrameView kf;
-    const uint8_t *kf_valid;
+    FrameView other;            // the side that varies over the batch
+    const uint8_t *other_valid; // its map-point mask
     int32_t *match, *bin_of;
     uint8_t *matched2;
     int *hist; // [64]: [0..29] histogram, [32] nmatches
-    int skip_big;
+    int n_nodes; // blocks of this pair (0: it went through its own launches, or has nothing to join)
 };
-__global__ void bow_match_batch_kernel(const BowBatchArg *__restrict__ args, FrameView f, float nnratio, int check_ori,
-                                       unsigned long long *__restrict__ counters, int stage_cap)
+template <int MODE>
+__global__ void bow_match_batch_kernel(const BowBatchArg *__restrict__ args, FrameView fixed, const uint8_t *__restrict__ fixed_valid,
+                                       float nnratio, int check_ori, unsigned long long *__restrict__ counters, int stage_cap)
 {
     const BowBatchArg &A = args[blockIdx.y];
-    if ((int)blockIdx.x >= A.kf.fv_n_nodes) return;
-    bow_match_body<0>(blockIdx.x, A.kf, f, A.kf_valid, nullptr, nnratio, check_ori, A.match, A.matched2, A.bin_of, A.hist, A.hist + 32, counters,
-                      stage_cap, A.skip_big);
+    if ((int)blockIdx.x >= A.n_nodes) return;
+    if (MODE == 0)
+        bow_match_body<0>(blockIdx.x, A.other, fixed, A.other_valid, nullptr, nnratio, check_ori, A.match, A.matched2, A.bin_of, A.hist,
+                          A.hist + 32, counters, stage_cap, 0);
+    else
+        bow_match_body<1>(blockIdx.x, fixed, A.other, fixed_valid, A.other_valid, nnratio, check_ori, A.match, A.matched2, A.bin_of, A.hist,
+                          A.hist + 32, counters, stage_cap, 0);
 }
 
 __device__ __forceinline__ void bow_cull_body(int n, int check_ori, int32_t *__restrict__ match, const int32_t *__restrict__ bin_of,
@@ -538,72 +545,87 @@ int run_bow(orbgpu_ctx *ctx, int mode, const orbgpu_frame *kf, const orbgpu_fram
     return ctx_download(ctx, out, 2);
 }
 
-// One frame against K candidate key frames (Tracking::Relocalization, Tracking.cc:4469-4495; the loop / merge candidate loops of
-// LoopClosing): ONE match launch over (node, key frame) and ONE cull launch for all K searches, one upload of the arguments and
-// validity masks, two memsets, one download and one synchronisation.  Key frames that need the big-node fixed point keep their own launches.
-int run_bow_batch(orbgpu_ctx *ctx, int K, const orbgpu_frame *const *kfs, const orbgpu_frame *f, const uint8_t *const *kf_valid, float nnratio,
-                  int check_ori, int32_t *match_out, int32_t *nmatches)
+// One frame against K candidate key frames (mode 0: Tracking::Relocalization, Tracking.cc:4469-4495) or the current key frame against
+// the K key frames of a candidate's covisibility window (mode 1: LoopClosing.cc:909-925): ONE match launch over (node, pair) and ONE
+// cull launch for all K searches, one upload of the arguments and validity masks, two memsets, one download and one synchronisation.
+// Pairs that need the big-node fixed point keep their own launches.
+int run_bow_batch(orbgpu_ctx *ctx, int mode, int K, const orbgpu_frame *const *others, const orbgpu_frame *fixed,
+                  const uint8_t *const *other_valid, const uint8_t *fixed_valid, float nnratio, int check_ori, int32_t *match_out,
+                  int32_t *nmatches)
 {
     int rc = ctx_begin(ctx);
     if (rc) return rc;
     for (int k = 0; k < K; k++) nmatches[k] = 0;
-    const int n_out = f->n;
+    const int n_out = fixed->n; // mode 0: indexed by the frame's features; mode 1: by the current key frame's
     if (n_out == 0 || K == 0) return ORBGPU_OK;
-    const size_t ffb = bow_ff_bytes(n_out), zb = bow_zero_bytes(f->n);
-    size_t total = K * (ffb + zb) + align256((size_t)K * n_out * 4) + 2048, mask_bytes = 0;
+    auto kf_of = [&](int k) { return mode == 0 ? others[k] : fixed; };
+    auto f_of = [&](int k) { return mode == 0 ? fixed : others[k]; };
+    int f_n_max = 0, f_node_max = 0;
+    for (int k = 0; k < K; k++) {
+        f_n_max = std::max(f_n_max, f_of(k)->n);
+        f_node_max = std::max(f_node_max, f_of(k)->fv_max_node);
+    }
+    const size_t ffb = bow_ff_bytes(n_out), zb = bow_zero_bytes(f_n_max);
+    size_t total = K * (ffb + zb) + align256((size_t)K * n_out * 4) + 2048, mask_bytes = align256(fixed->n + 1);
     std::vector<size_t> mask_off(K);
     for (int k = 0; k < K; k++) {
-        total += bow_scratch_bytes(kfs[k], f, 0, nullptr);
+        total += bow_scratch_bytes(kf_of(k), f_of(k), mode, nullptr);
         mask_off[k] = mask_bytes;
-        mask_bytes += align256(kfs[k]->n + 1);
+        mask_bytes += align256(others[k]->n + 1);
     }
     const size_t arg_bytes = align256((size_t)K * sizeof(BowBatchArg));
     rc = stage_reserve(ctx, mask_bytes + arg_bytes + 256);
     if (rc) return rc;
-    rc = arena_reserve(ctx, total + align256(mask_bytes) + arg_bytes + align256(f->n + 1));
+    rc = arena_reserve(ctx, total + align256(mask_bytes) + arg_bytes + 1024);
     if (rc) return rc;
     char *ff = (char *)arena_take(ctx, K * ffb), *zero = (char *)arena_take(ctx, K * zb);
     int32_t *d_out = (int32_t *)arena_take(ctx, (size_t)K * n_out * 4 + 4 * K);
-    uint8_t *d_up = (uint8_t *)arena_take(ctx, mask_bytes + arg_bytes), *d_fv = (uint8_t *)arena_take(ctx, f->n + 1);
-    if (!ff || !zero || !d_out || !d_up || !d_fv) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
-    uint8_t *d_masks = d_up + arg_bytes;
-    // per-key-frame arguments of the batch kernels + the validity masks: one pinned block, one H2D copy
+    uint8_t *d_up = (uint8_t *)arena_take(ctx, mask_bytes + arg_bytes);
+    if (!ff || !zero || !d_out || !d_up) return orbgpu_fail(ORBGPU_ERR_OVERFLOW, "arena exhausted");
+    uint8_t *d_masks = d_up + arg_bytes; // [0] the fixed side's mask (mode 1), then one per pair
+    // per-pair arguments of the batch kernels + the validity masks: one pinned block, one H2D copy
     BowBatchArg *h_args = (BowBatchArg *)ctx->h_stage;
     int max_nodes = 0, n_big = 0;
     std::vector<char> is_big(K, 0);
+    if (mode == 1 && fixed->n) memcpy(ctx->h_stage + arg_bytes, fixed_valid, fixed->n);
     for (int k = 0; k < K; k++) {
         bool big = false;
-        bow_scratch_bytes(kfs[k], f, 0, &big);
+        bow_scratch_bytes(kf_of(k), f_of(k), mode, &big);
         is_big[k] = big;
         n_big += big;
         const BowBlock blk = bow_block(ff + k * ffb, zero + k * zb, n_out);
         BowBatchArg &A = h_args[k];
-        A.kf = frame_view(kfs[k]);
-        A.kf_valid = d_masks + mask_off[k];
+        A.other = frame_view(others[k]);
+        A.other_valid = d_masks + mask_off[k];
         A.match = big ? nullptr : blk.d_match;
-        A.bin_of = blk.d_bin; A.matched2 = blk.d_m2; A.hist = blk.d_hist; A.skip_big = 0;
-        if (big || f->fv_n_nodes == 0) A.kf.fv_n_nodes = 0; // its blocks exit at once
-        max_nodes = std::max(max_nodes, A.kf.fv_n_nodes);
-        if (kfs[k]->n) memcpy(ctx->h_stage + arg_bytes + mask_off[k], kf_valid[k], kfs[k]->n);
+        A.bin_of = blk.d_bin; A.matched2 = blk.d_m2; A.hist = blk.d_hist;
+        A.n_nodes = (big || kf_of(k)->fv_n_nodes == 0 || f_of(k)->fv_n_nodes == 0) ? 0 : kf_of(k)->fv_n_nodes; // else its blocks exit at once
+        max_nodes = std::max(max_nodes, A.n_nodes);
+        if (others[k]->n) memcpy(ctx->h_stage + arg_bytes + mask_off[k], other_valid[k], others[k]->n);
     }
     CU_TRY(cudaMemcpyAsync(d_up, ctx->h_stage, arg_bytes + mask_bytes, cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(cudaMemsetAsync(ff, 0xFF, K * ffb, ctx->stream)); // the match / bin vectors of ALL pairs
     CU_TRY(cudaMemsetAsync(zero, 0, K * zb, ctx->stream));   // histograms, counts and taken flags of ALL pairs
-    if (max_nodes > 0) { // ONE launch for all the ordinary pairs: blockIdx.y = key frame, blockIdx.x = node
-        const int threads = f->fv_max_node <= 32 ? 32 : (f->fv_max_node <= 512 ? 128 : (f->fv_max_node <= 1024 ? 256 : 1024));
-        int stage_cap = f->fv_max_node > 64 ? f->fv_max_node : 0;
+    if (max_nodes > 0) { // ONE launch for all the ordinary pairs: blockIdx.y = pair, blockIdx.x = node
+        const int threads = f_node_max <= 32 ? 32 : (f_node_max <= 512 ? 128 : (f_node_max <= 1024 ? 256 : 1024));
+        int stage_cap = f_node_max > 64 ? f_node_max : 0;
         if (stage_cap > 4800) stage_cap = 4800;
         stage_cap = (stage_cap + 15) & ~15;
         const size_t smem = (size_t)stage_cap * 41;
-        bow_match_batch_kernel<<<dim3(max_nodes, K), threads, smem, ctx->stream>>>((const BowBatchArg *)d_up, frame_view(f), nnratio, check_ori,
-                                                                                   ctx->d_counters, stage_cap);
+        if (mode == 0)
+            bow_match_batch_kernel<0><<<dim3(max_nodes, K), threads, smem, ctx->stream>>>((const BowBatchArg *)d_up, frame_view(fixed), d_masks, nnratio,
+                                                                                          check_ori, ctx->d_counters, stage_cap);
+        else
+            bow_match_batch_kernel<1><<<dim3(max_nodes, K), threads, smem, ctx->stream>>>((const BowBatchArg *)d_up, frame_view(fixed), d_masks, nnratio,
+                                                                                          check_ori, ctx->d_counters, stage_cap);
         bow_cull_batch_kernel<<<K, 256, 0, ctx->stream>>>((const BowBatchArg *)d_up, n_out, check_ori);
         ctx->launches += 2;
         CU_TRY(cudaGetLastError());
     }
-    for (int k = 0; k < K && n_big; k++) { // key frames with a big node pair (one root bucket): the fixed-point path, their own launches
+    for (int k = 0; k < K && n_big; k++) { // pairs with a big node pair (one root bucket): the fixed-point path, their own launches
         if (!is_big[k]) continue;
-        rc = bow_enqueue(ctx, 0, kfs[k], f, d_masks + mask_off[k], d_fv, nnratio, check_ori, bow_block(ff + k * ffb, zero + k * zb, n_out));
+        const uint8_t *d_kfv = mode == 0 ? d_masks + mask_off[k] : d_masks, *d_fv = mode == 0 ? d_masks : d_masks + mask_off[k];
+        rc = bow_enqueue(ctx, mode, kf_of(k), f_of(k), d_kfv, d_fv, nnratio, check_ori, bow_block(ff + k * ffb, zero + k * zb, n_out));
         if (rc) return rc;
     }
     // results to one contiguous block: [K][n_out] matches (pitch ffb -> n_out * 4), then the K counts (zero + k * zb + 128)
@@ -663,13 +685,22 @@ extern "C" int orbgpu_search_by_bow_kf_f_batch(orbgpu_ctx *ctx, int32_t n_kf, co
     ARG_TRY(ctx && f && n_kf >= 0 && (n_kf == 0 || (kfs && kf_mp_valid && nmatches)) && (f->n == 0 || n_kf == 0 || match_f2kf));
     ARG_TRY(f->n < (1 << 20));
     for (int k = 0; k < n_kf; k++) ARG_TRY(kfs[k] && (kfs[k]->n == 0 || kf_mp_valid[k]));
-    return run_bow_batch(ctx, n_kf, kfs, f, kf_mp_valid, nnratio, check_ori, match_f2kf, nmatches);
+    return run_bow_batch(ctx, 0, n_kf, kfs, f, kf_mp_valid, nullptr, nnratio, check_ori, match_f2kf, nmatches);
+}
+
+extern "C" int orbgpu_search_by_bow_kf_kf_batch(orbgpu_ctx *ctx, const orbgpu_frame *kf1, const uint8_t *kf1_mp_valid, int32_t n_kf,
+                                                const orbgpu_frame *const *kf2s, const uint8_t *const *kf2_mp_valid, float nnratio,
+                                                int32_t check_ori, int32_t *match_12, int32_t *nmatches)
+{
+    ARG_TRY(ctx && kf1 && n_kf >= 0 && (n_kf == 0 || (kf2s && kf2_mp_valid && nmatches)) && (kf1->n == 0 || n_kf == 0 || (match_12 && kf1_mp_valid)));
+    for (int k = 0; k < n_kf; k++) ARG_TRY(kf2s[k] && kf2s[k]->n < (1 << 20) && (kf2s[k]->n == 0 || kf2_mp_valid[k]));
+    return run_bow_batch(ctx, 1, n_kf, kf2s, kf1, kf2_mp_valid, kf1_mp_valid, nnratio, check_ori, match_12, nmatches);
 }
 
 int search_bow_device_init()
 {
     int rc;
-    if ((rc = set_max_dyn_smem(bow_match_batch_kernel))) return rc;
+    if ((rc = set_max_dyn_smem(bow_match_batch_kernel<0>)) || (rc = set_max_dyn_smem(bow_match_batch_kernel<1>))) return rc;
     if ((rc = set_max_dyn_smem(bow_match_kernel<0>)) || (rc = set_max_dyn_smem(bow_match_kernel<1>)) ||
         (rc = set_max_dyn_smem(bow_big_resolve_kernel<0>)) || (rc = set_max_dyn_smem(bow_big_resolve_kernel<1>)))
         return rc;

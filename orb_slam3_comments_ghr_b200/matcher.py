@@ -553,6 +553,23 @@ class ORBmatcher:
                                                  _p(out, i32p), _p(nm, i32p)))
         return nm[:K], out[:K, :F.n]
 
+    # the current key frame against the K key frames of a candidate's covisibility window (LoopClosing.cc:909-925) in one call
+    # -> (nmatches[K], vpMatches12[K, KF1.N] as KF2 feature indices)
+    def SearchByBoWBatchKF(self, KF1: DeviceFrame, kf1_mp_valid, KF2s, kf2_mp_valids):
+        K = len(KF2s)
+        v1 = as_u8(kf1_mp_valid)
+        vs = [as_u8(v) for v in kf2_mp_valids]
+        out = np.full((max(K, 1), max(KF1.n, 1)), -1, dtype=np.int32)
+        nm = np.zeros(max(K, 1), dtype=np.int32)
+        hs = (C.c_void_p * max(K, 1))(*[k.handle for k in KF2s])
+        ps = (u8p * max(K, 1))(*[_p(v, u8p) for v in vs])
+        L = load_library()
+        L.orbgpu_search_by_bow_kf_kf_batch.argtypes = [C.c_void_p, C.c_void_p, u8p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(u8p),
+                                                       C.c_float, C.c_int32, i32p, i32p]
+        _check(L.orbgpu_search_by_bow_kf_kf_batch(self.ctx.handle, KF1.handle, _p(v1, u8p), K, hs, ps, self.mfNNratio,
+                                                  int(self.mbCheckOrientation), _p(out, i32p), _p(nm, i32p)))
+        return nm[:K], out[:K, :KF1.n]
+
     # ORBmatcher.h:72, batched over pairs -> (nmatches[P], vMatches12[P, n_feat])
     def SearchForTriangulation(self, kfs: DeviceKfSet, kf1, kf2, ep, f12, bOnlyStereo: bool = False, bCoarse: bool = False, out=None):
         """out: optional caller-owned (vMatches12[P, n_feat] int32, nmatches[P] int32) host buffers -- pinned memory makes the

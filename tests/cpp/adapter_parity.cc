@@ -348,6 +348,40 @@ int main()
             std::printf("SearchByBoW KF-KF: ref %d gpu %d\n", nA, nB);
             EXPECT(nA == nB && mA == mB && nA > 20, "SearchByBoW(KeyFrame*, KeyFrame*) vpMatches12 / return value");
         }
+        { // the batched overloads == the reference's own loops (Tracking.cc:4469-4495, LoopClosing.cc:909-925), NULL entries skipped
+            std::vector<KeyFrame *> cands = {&K1, static_cast<KeyFrame *>(NULL), &K2, &K1};
+            ORBmatcher ref(0.75f, true);
+            GpuMatcher gpu(0.75f, true);
+            std::vector<std::vector<MapPoint *>> vvB;
+            std::vector<int> vnB;
+            gpu.SearchByBoW(cands, F, vvB, vnB);
+            bool ok = vvB.size() == cands.size() && vnB.size() == cands.size();
+            int total = 0;
+            for (size_t i = 0; ok && i < cands.size(); i++)
+            {
+                if (!cands[i]) { ok = vnB[i] == 0 && vvB[i].empty(); continue; }
+                std::vector<MapPoint *> mA;
+                const int nA = ref.SearchByBoW(cands[i], F, mA);
+                ok = nA == vnB[i] && mA == vvB[i];
+                total += nA;
+            }
+            std::printf("SearchByBoW batch KF-F: %d matches over %zu candidates\n", total, cands.size());
+            EXPECT(ok && total > 100, "SearchByBoW(vector<KeyFrame*>, Frame&) == the loop over the reference's SearchByBoW");
+            std::vector<KeyFrame *> window = {&K2, &K1, static_cast<KeyFrame *>(NULL), &K2};
+            gpu.SearchByBoW(&K1, window, vvB, vnB);
+            ok = vvB.size() == window.size();
+            total = 0;
+            for (size_t i = 0; ok && i < window.size(); i++)
+            {
+                if (!window[i]) { ok = vnB[i] == 0 && vvB[i].empty(); continue; }
+                std::vector<MapPoint *> mA;
+                const int nA = ref.SearchByBoW(&K1, window[i], mA);
+                ok = nA == vnB[i] && mA == vvB[i];
+                total += nA;
+            }
+            std::printf("SearchByBoW batch KF-KF: %d matches over %zu window key frames\n", total, window.size());
+            EXPECT(ok && total > 50, "SearchByBoW(KeyFrame*, vector<KeyFrame*>) == the loop over the reference's SearchByBoW");
+        }
         for (int ori = 0; ori < 2; ori++)
         {
             std::vector<std::pair<size_t, size_t>> vA, vB;

@@ -769,6 +769,44 @@ def test_search_by_bow_batch(ctx, M, oracle, levelsup, K):
     assert int(nm.sum()) > 0
 
 
+@pytest.mark.parametrize("levelsup,K", [(2, 6), (4, 5), (6, 2)])
+def test_search_by_bow_batch_kf_kf(ctx, M, oracle, levelsup, K):
+    """the current key frame against the K key frames of a candidate window in one call (LoopClosing.cc:909-925) == K separate
+    SearchByBoW(KF, KF) calls == the oracle; window key frames of different sizes, levelsup 6 = one root node (the big-node path)"""
+    voc = golden_voc()
+    kf1 = None
+    kf2s, valids, exp = [], [], []
+    total_cmp = 0
+    for k in range(K):
+        c = synth.make_bow_case(2600 + 10 * levelsup + k, voc, 1200 if k % 2 else 1800)
+        if kf1 is None:
+            kf1 = attach_featvec(oracle, voc, c.kf, levelsup)
+            v1 = c.kf_mp_valid[: kf1.n]
+        f = c.f
+        if k > 0:  # window key frames that really look like the current one
+            rng = np.random.default_rng(100 + k)
+            src = rng.permutation(kf1.n)[: f.n // 2]
+            f.desc[: src.size] = synth.planted_copies(rng, kf1.desc[src])
+        f = attach_featvec(oracle, voc, f, levelsup)
+        kf2s.append(f)
+        valids.append(c.f_mp_valid[: f.n])
+        oracle.reset_comparisons()
+        exp.append(oracle.search_by_bow_kf_kf(kf1, f, v1, valids[-1], 0.8, 1))
+        total_cmp += oracle.comparisons()
+    d1 = ctx.upload_frame(kf1)
+    d2s = [ctx.upload_frame(f) for f in kf2s]
+    m = M.ORBmatcher(0.8, True, ctx)
+    nm, out = m.SearchByBoWBatchKF(d1, v1, d2s, valids)
+    assert ctx.last_comparisons == total_cmp
+    for k in range(K):
+        assert nm[k] == exp[k][0] and np.array_equal(out[k], exp[k][1]), k
+        n1, m1 = m.SearchByBoW(d1, d2s[k], v1, valids[k])
+        assert n1 == nm[k] and np.array_equal(m1, out[k])
+    assert int(nm.sum()) > 0
+    nm0, out0 = m.SearchByBoWBatchKF(d1, v1, [], [])
+    assert nm0.size == 0 and out0.shape[0] == 0
+
+
 def test_triangulation_shared_keyframes(ctx, M, oracle):
     """C4 shared-key-frame variant (LocalMapping::CreateNewMapPoints: every key frame against its 8 best neighbours): both engines and
     the compact form against the oracle"""
