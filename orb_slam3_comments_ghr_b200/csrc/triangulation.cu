@@ -366,9 +366,9 @@ triangulation_pairs_kernel(KfSetView s, int n_pairs, int max_free, int max_nodes
 //                      halves, bit j of a per-slot mask = candidate j is already <= TH_LOW (2 % of them are).
 //                      Slots with a non-zero mask are compacted into the stage's list (one ballot per chunk) and
 //                      the aux records of their candidates are prefetched into L2 -> compared[st]
-//   post     (NG warps) waits compared[st]; one listed slot per thread: fetches the 32-byte aux records {hi half,
-//                      keypoint} of the flagged candidates, finishes the distances, fp32 gates, keeps the
-//                      (dist, -idx2) minimum and writes the match -> empty[st]
+//   post     (NG warps) waits compared[st]; one (slot, flagged candidate) entry per thread, ONE pass: fetches the 32-byte
+//                      aux records {hi half, keypoint} of both, finishes the distance, fp32 gates, keeps the
+//                      (dist, -idx2) minimum per slot and writes the match -> empty[st]
 //
 // The compare warps never meet a CTA-wide barrier: while they stream pair i, the post warps finish pair i-1, the join
 // warps prepare pair i+1 and the bulk copies of pair i+2 are in flight.
@@ -382,7 +382,8 @@ constexpr uint32_t ENT_NONE = 0xFFFFFFFFu;
 struct TsStageCtl {
     int k1, k2, m1, m2, nn1, nn2;
     int n_list;     // slots with a non-zero mask listed so far
-    int n_ovf;      // entries in the overflow list
+    int n_ovf;      // entries in the overflow list: second and later flagged candidates of a slot, candidates past the 32nd of a node
+    int n_long;     // != 0: some node had more than 32 candidates (a slot can then have survivors without being listed)
     float geo[12];  // f12[9], ep[2]
 };
 
@@ -564,7 +565,7 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
                 C.k1 = cur.k1; C.k2 = cur.k2;
                 C.m1 = cur.m1; C.m2 = cur.m2;
                 C.nn1 = cur.nn1; C.nn2 = cur.nn2;
-                C.n_list = 0; C.n_ovf = 0;
+                C.n_list = 0; C.n_ovf = 0; C.n_long = 0;
                 const uint32_t bar = bar_of(st, B_FULL);
                 ts_mbar_expect_tx(bar, (uint32_t)(cur.b1 + cur.b2));
                 unsigned char *dst = stage_base(st);
@@ -691,16 +692,29 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
                     if (lane == 0) slot0 = atomicAdd(&C.n_list, __popc(bal));
                     slot0 = __shfl_sync(FULL_MASK, slot0, 0);
                     if (mask) {
+                        // the slot is listed with its FIRST flagged candidate; a second one is rare (a false positive of the 128-bit
+                        // prefilter next to the true match: ~7 % of the listed slots) and goes to the overflow list as its own
+                        // (slot, candidate) entry, so that the post warps gate every entry in ONE pass
                         sMask[c1] = mask;
                         sList[slot0 + __popc(bal & lanemask_lt())] = (uint16_t)c1;
                         TS_PREFETCH("prefetch.global.L2 [%0];" ::"l"(aux1 + 2 * c1));
-                        do {
-                            TS_PREFETCH("prefetch.global.L2 [%0];" ::"l"(aux2 + 2 * (s2 + __ffs(mask) - 1)));
+                        TS_PREFETCH("prefetch.global.L2 [%0];" ::"l"(aux2 + 2 * (s2 + __ffs(mask) - 1)));
+                        mask &= mask - 1;
+                        while (mask) {
+                            const int c2 = s2 + __ffs(mask) - 1;
                             mask &= mask - 1;
-                        } while (mask);
+                            TS_PREFETCH("prefetch.global.L2 [%0];" ::"l"(aux2 + 2 * c2));
+                            const int slot = atomicAdd(&C.n_ovf, 1);
+                            if (slot < TS_OVF) sOvf[slot] = (uint32_t)c1 | ((uint32_t)c2 << 13);
+                            else { // list full (adversarial inputs only): gate in place
+                                const uint32_t key = ts_gate(a_lo, aux1[2 * c1], aux1[2 * c1 + 1], c2, lo2, aux2, C.geo, sScale, sSigma, P.coarse);
+                                if (key != KEY_NONE) atomicMin(&sBest[c1], key);
+                            }
+                        }
                     }
                 }
                 // a node with more than 32 candidates (rare with a real vocabulary): the rest goes through the overflow list
+                if (n2f > 32) C.n_long = 1;
                 for (int j = 32; j < n2f; j++) {
                     if (ham128(a_lo, lo2[s2 + j]) > ORBGPU_TH_LOW) continue;
                     const int slot = atomicAdd(&C.n_ovf, 1);
@@ -766,7 +780,6 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
         if (gt == 0) stamp(i, 6);
         TsStageCtl &C = ctl[st];
         const int k1 = C.k1, k2 = C.k2, m1 = C.m1, ns = C.n_list;
-        const int n_ovf_cmp = C.n_ovf; // entries the compare warps left: nodes with more than 32 candidates (rare)
         unsigned char *base = stage_base(st);
         const uint4 *lo1 = (const uint4 *)base, *lo2 = (const uint4 *)(base + cap);
         const uint32_t *sCand = (const uint32_t *)(base + 2 * (size_t)cap), *sMask = sCand + mf;
@@ -782,46 +795,31 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
             atomicOr(&bm[f1 >> 5], 1u << (f1 & 31));
         };
         int mine = 0;
-        // ---- pass A: one listed slot per thread and its FIRST flagged candidate.  A slot rarely has a second one (a false positive
-        // of the 128-bit prefilter next to the true match: ~4 % of the slots); those go to the stage's overflow list instead of making
-        // every lane of the warp walk a second gate.  The per-slot minimum (last-wins ties of :1180) is collected in sBest.
-        for (int e = gt; e < ns; e += GT) {
-            const int c1 = (int)sList[e];
-            uint32_t mask = sMask[c1];
-            const int s2 = (int)(sCand[c1] & 0xFFFF);
-            const int ca = s2 + __ffs(mask) - 1;
-            mask &= mask - 1;
+        // ---- gate: one entry per thread -- the listed slots with their first flagged candidate, then the overflow entries (further
+        // candidates of a slot, candidates past the 32nd of a node).  The per-slot minimum (last-wins ties of :1180) is collected in sBest.
+        const int n_ovf = min(C.n_ovf, TS_OVF), n_ent = ns + n_ovf;
+        for (int e = gt; e < n_ent; e += GT) {
+            int c1, ca;
+            const bool first = e < ns;
+            if (first) {
+                c1 = (int)sList[e];
+                ca = (int)(sCand[c1] & 0xFFFF) + __ffs(sMask[c1]) - 1;
+            } else {
+                const uint32_t en = sOvf[e - ns];
+                c1 = (int)(en & 0x1FFF);
+                ca = (int)((en >> 13) & 0x1FFF);
+            }
             const uint4 h1 = aux1[2 * c1], q1 = aux1[2 * c1 + 1];
             const uint4 ha = aux2[2 * ca], qa = aux2[2 * ca + 1];
-            const uint4 a_lo = lo1[c1];
-            while (mask) {
-                const int c2 = s2 + __ffs(mask) - 1;
-                mask &= mask - 1;
-                const int slot = atomicAdd(&C.n_ovf, 1);
-                if (slot < TS_OVF) sOvf[slot] = (uint32_t)c1 | ((uint32_t)c2 << 13);
-                else { // list full (adversarial inputs only): gate in place
-                    const uint32_t k2nd = ts_gate(a_lo, h1, q1, c2, lo2, aux2, C.geo, sScale, sSigma, P.coarse);
-                    if (k2nd != KEY_NONE) atomicMin(&best[c1], k2nd);
-                }
-            }
-            const uint32_t key = ts_gate_loaded(a_lo, h1, q1, lo2[ca], ha, qa, C.geo, sScale, sSigma, P.coarse);
+            const uint32_t key = ts_gate_loaded(lo1[c1], h1, q1, lo2[ca], ha, qa, C.geo, sScale, sSigma, P.coarse);
             if (key != KEY_NONE) atomicMin(&best[c1], key);
-            sEnt[c1] = q1.w; // feature id of the slot, for the output pass
+            if (first) sEnt[c1] = q1.w; // feature id of the slot, for the output pass
         }
         bar_post();
-        // ---- pass B: the overflow list (compare warps' and pass A's entries), one candidate per thread
-        const int n_ovf = min(C.n_ovf, TS_OVF);
-        for (int e = gt; e < n_ovf; e += GT) {
-            const uint32_t en = sOvf[e];
-            const int c1 = (int)(en & 0x1FFF);
-            const uint32_t key = ts_gate(lo1[c1], aux1[2 * c1], aux1[2 * c1 + 1], (int)((en >> 13) & 0x1FFF), lo2, aux2, C.geo, sScale,
-                                         sSigma, P.coarse);
-            if (key != KEY_NONE) atomicMin(&best[c1], key);
-        }
-        if (n_ovf > 0) bar_post();
+        if (gt == 0) { stamp(i, 10); if (P.timeline && blockIdx.x == 0) { P.timeline[i * 16 + 12] = ns; P.timeline[i * 16 + 13] = n_ovf; P.timeline[i * 16 + 14] = C.n_long; } }
         // ---- output by the slots' owners: the listed slots, or every slot when the compare warps found a node with more than 32
         // candidates (such a slot can have survivors without being listed)
-        const bool all_slots = n_ovf_cmp > 0;
+        const bool all_slots = C.n_long != 0;
         const int n_own = all_slots ? m1 : ns;
         const float *ang1 = P.angle + (size_t)k1 * n, *ang2 = P.angle + (size_t)k2 * n;
         auto slot_of = [&](int e) { return all_slots ? e : (int)sList[e]; };

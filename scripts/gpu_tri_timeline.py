@@ -36,11 +36,11 @@ torch.cuda.synchronize()
 L.orbgpu_debug_triangulation_timeline(ctx.handle, ctypes.c_void_p(0))
 tt = tl.cpu().numpy()[:n_my]
 t0 = tt[0, 0]
-names = ["empty_ok", "full_ok", "join_done", "joined_ok", "cmp_done", "post_ready", "compared_ok", "post_done", "gated", "placed"]
+names = ["empty_ok", "full_ok", "join_done", "joined_ok", "cmp_done", "post_ready", "compared_ok", "post_done", "output", "placed", "gated"]
 print(f"# {MODE} output, {P} pairs, CTA 0 handles {n_my}; SM clocks after the producer's first stamp (L2 flushed before the launch)")
 print("pair " + " ".join(n.rjust(11) for n in names))
 for i in range(min(n_my, 28)):
-    print(f"{i:4d} " + " ".join(f"{int(x - t0) if x else 0:11d}" for x in tt[i][:len(names)]))
+    print(f"{i:4d} " + " ".join(f"{int(x - t0) if x else 0:11d}" for x in tt[i][:len(names)]) + "  listed %d ovf %d long %d" % tuple(int(x) for x in tt[i][12:15]))
 d = tt
 k = min(4, n_my - 1)
 print("mean cycles: load (full_ok - empty_ok) %.0f | join %.0f | compare %.0f | post (post_done - compared_ok) %.0f" %
