@@ -798,10 +798,8 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
         // ---- gate: one entry per thread -- the listed slots with their first flagged candidate, then the overflow entries (further
         // candidates of a slot, candidates past the 32nd of a node).  The per-slot minimum (last-wins ties of :1180) is collected in sBest.
         const int n_ovf = min(C.n_ovf, TS_OVF), n_ent = ns + n_ovf;
-        for (int e = gt; e < n_ent; e += GT) {
-            int c1, ca;
-            const bool first = e < ns;
-            if (first) {
+        auto entry = [&](int e, int &c1, int &ca) {
+            if (e < ns) {
                 c1 = (int)sList[e];
                 ca = (int)(sCand[c1] & 0xFFFF) + __ffs(sMask[c1]) - 1;
             } else {
@@ -809,6 +807,17 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
                 c1 = (int)(en & 0x1FFF);
                 ca = (int)((en >> 13) & 0x1FFF);
             }
+        };
+        if (gt + GT < n_ent) { // ~300 entries for 192 threads: the records of this thread's second entry are pulled into L1 while
+            int c1, ca;        // the first is gated (holding both in registers spills: 64 registers per thread at 1024 threads)
+            entry(gt + GT, c1, ca);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(aux1 + 2 * c1));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(aux2 + 2 * ca));
+        }
+        for (int e = gt; e < n_ent; e += GT) {
+            int c1, ca;
+            const bool first = e < ns;
+            entry(e, c1, ca);
             const uint4 h1 = aux1[2 * c1], q1 = aux1[2 * c1 + 1];
             const uint4 ha = aux2[2 * ca], qa = aux2[2 * ca + 1];
             const uint32_t key = ts_gate_loaded(lo1[c1], h1, q1, lo2[ca], ha, qa, C.geo, sScale, sSigma, P.coarse);
