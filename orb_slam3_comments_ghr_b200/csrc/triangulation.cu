@@ -663,9 +663,12 @@ __global__ void __launch_bounds__((NC + NG + NJ + 1) * 32, 1) triangulation_stre
             const uint16_t *sPerm = sList + mf;
             uint32_t *sOvf = (uint32_t *)(sPerm + mf);
             const uint4 *aux1 = P.aux + (size_t)k1 * n * 2, *aux2 = P.aux + (size_t)k2 * n * 2;
-            // 32-slot chunks are dealt round-robin to the warps, rotated from pair to pair so that the odd chunk does
-            // not always land on the same warps
-            for (int c0 = ((warp + NC - (i % NC)) % NC) * 32; c0 < m1; c0 += NC * 32) {
+            // 32-slot chunks are dealt to the warps in snake order (rounds alternate direction): the slots are sorted by candidate
+            // count, descending, so warp w's chunks w, 2 NC - 1 - w, 2 NC + w, ... add up to nearly the same number of trips for
+            // every warp (plain round-robin gives the first warp the two longest chunks of their rounds, the last the two shortest).
+            // Rotated from pair to pair so that the odd chunk does not always land on the same warps.
+            const int wr = (warp + NC - (i % NC)) % NC;
+            for (int r = 0, c0 = wr * 32; c0 < m1; r++, c0 = (r * NC + ((r & 1) ? NC - 1 - wr : wr)) * 32) {
                 int c1 = c0 + lane;
                 uint32_t cand = 0;
                 uint4 a_lo = make_uint4(0, 0, 0, 0);
