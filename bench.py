@@ -599,6 +599,27 @@ def bench_c4(E, args, K, W, shared=False, weak=False):
         torch.cuda.synchronize()
         dt = E.max_over_ranks((time.perf_counter() - t0) / Ke)
         h2d = case.kf1.nbytes * 2 + case.ep.nbytes + case.f12.nbytes
+        if world > 1:
+            # the same step with the host side sharded like the device side: every rank's host receives the vMatchedPairs of ITS pairs
+            # (all ranks still hold the gathered result on the device)
+            own = [0]
+
+            def e2e_own_step():
+                for d_, h_ in zip(d_in, h):
+                    d_.copy_(h_, non_blocking=True)
+                c, e = tg.step()
+                offs, pairs = tg.download(c, e, out=h_out, own_only=True)
+                own[0] = offs.nbytes + pairs.nbytes
+            e2e_own_step(); e2e_own_step()
+            E.barrier_sync()
+            t0 = time.perf_counter()
+            for _ in range(Ke):
+                e2e_own_step()
+            torch.cuda.synchronize()
+            dt_own = E.max_over_ranks((time.perf_counter() - t0) / Ke)
+            extra["e2e_own_shard"] = {"value": P_total / dt_own, "unit": "frame_pairs/s", "ms_per_step": dt_own * 1e3,
+                                      "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(own[0]),
+                                      "note": "as e2e, but every rank's host downloads the vMatchedPairs of its own pairs only"}
         log("c4: e2e done")
         e2e = {"value": P_total / dt, "unit": "frame_pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h[0]),
                "ms_per_step": dt * 1e3, "steps": Ke, "note": note}

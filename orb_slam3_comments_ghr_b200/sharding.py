@@ -161,8 +161,14 @@ class TriangulationGather:
             cur.wait_stream(self.side)
         return self.counts[b], self.pairs[b].view(self.p_total, self.n_feat)
 
-    def download(self, counts: torch.Tensor, entries: torch.Tensor, out=None):
-        """the gathered result of a step on the host: (pair_offsets[P_total + 1], pairs[total, 2]) -- vMatchedPairs of ALL pairs"""
+    def download(self, counts: torch.Tensor, entries: torch.Tensor, out=None, own_only: bool = False):
+        """the gathered result of a step on the host: (pair_offsets[P_total + 1], pairs[total, 2]) -- vMatchedPairs of ALL pairs;
+        own_only: only this rank's pairs [lo, hi) (the host work that follows -- triangulating the matches -- shards the same way)"""
+        if own_only:
+            if self.side is not None:
+                self.side.wait_stream(torch.cuda.current_stream(self.dev))
+            return self.m.TriangulationGatherDownload(self.hi - self.lo, self.n_feat, counts.data_ptr() + 4 * self.lo,
+                                                      entries.data_ptr() + 4 * self.lo * self.n_feat, out=out)
         if self.side is not None:
             self.side.wait_stream(torch.cuda.current_stream(self.dev))  # the step was replayed on the current stream; the download runs on the context's
         offs, pairs = self.m.TriangulationGatherDownload(self.p_total, self.n_feat, counts.data_ptr(), entries.data_ptr(), out=out)
