@@ -39,6 +39,9 @@ for graph in (False, True):
             print(f"rank {rank} graph={graph} step {step}: MISMATCH (counts equal: {np.array_equal(c, c0)})", flush=True)
     offs, pairs = tg.download(*tg.step())
     ok = ok and np.array_equal(offs, np.concatenate([[0], np.cumsum(c0)]).astype(np.int32)) and pairs.shape[0] == int(c0.sum())
+    offs, pairs = np.array(offs), np.array(pairs)
+    o_own, p_own = tg.download(*tg.step(), own_only=True)  # this rank's pairs only == its slice of the full download
+    ok = ok and np.array_equal(np.asarray(o_own), offs[lo:hi + 1] - offs[lo]) and np.array_equal(np.asarray(p_own), pairs[offs[lo]:offs[hi]])
     del tg
 if rank == 0:  # and the oracle, for a sample of pairs
     from oracle.pyoracle import Oracle
@@ -48,6 +51,6 @@ if rank == 0:  # and the oracle, for a sample of pairs
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(f"GATHER CHECK {'OK' if int(flag.item()) else 'FAILED'}: {world} ranks, {P} pairs x {NF} features, {int(c0.sum())} matches, 12 steps + 2 downloads per rank")
+    print(f"GATHER CHECK {'OK' if int(flag.item()) else 'FAILED'}: {world} ranks, {P} pairs x {NF} features, {int(c0.sum())} matches, 14 steps + 4 downloads per rank")
 dist.barrier()
 dist.destroy_process_group()
