@@ -392,6 +392,11 @@ int orbgpu_db_invalidate(orbgpu_db *db);
 void orbgpu_db_destroy(orbgpu_db *db);
 int orbgpu_knn2_ratio(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const uint8_t *q_desc, int32_t th_low, float nnratio,
                       int32_t *best_idx, int32_t *best_dist, int32_t *second_dist, int32_t *match);
+/* orbgpu_db_update + orbgpu_knn2_ratio in one call with the upload overlapped: the descriptors are copied in chunks on the database's
+ * own stream and every chunk is searched as soon as it has arrived (SearchByNN(queries, database) on two host matrices).  db must be
+ * an owned database (orbgpu_db_upload) with capacity >= nd.  Results identical to the two separate calls. */
+int orbgpu_knn2_ratio_update(orbgpu_ctx *ctx, orbgpu_db *db, int64_t nd, const uint8_t *db_desc, int64_t nq, const uint8_t *q_desc,
+                             int32_t th_low, float nnratio, int32_t *best_idx, int32_t *best_dist, int32_t *second_dist, int32_t *match);
 int orbgpu_knn2_ratio_dev(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const void *q_desc_dev, int32_t th_low,
                           float nnratio, int32_t *best_idx_dev, int32_t *best_dist_dev, int32_t *second_dist_dev,
                           int32_t *match_dev);

@@ -250,7 +250,16 @@ struct orbgpu_db {
     mutable size_t x_bytes = 0;
     mutable bool x_valid = false;
     mutable cudaEvent_t x_ready = nullptr;
+    // chunked re-upload (orbgpu_knn2_ratio_update): the descriptors cross PCIe in three chunks on the database's own stream, one event
+    // per chunk; up_pending > 0 until a search has consumed (or waited for) them
+    mutable cudaStream_t up_stream = nullptr;
+    mutable cudaEvent_t up_ev[16] = {};
+    mutable cudaEvent_t up_gate = nullptr;
+    mutable int up_pending = 0;
+    mutable int64_t up_row_end[16] = {}; // chunk c = rows [up_row_end[c - 1], up_row_end[c]): whole 131 072-row splits, 1/8 + 1/4 + 5/8 of them
 };
+// makes ctx's stream wait for every chunk of a pending upload (readers that need the whole database)
+int db_wait_upload(orbgpu_ctx *ctx, const orbgpu_db *db);
 
 // POD view of a frame passed by value to kernels
 struct FrameView {

@@ -303,6 +303,8 @@ extern "C" int orbgpu_db_update(orbgpu_ctx *ctx, orbgpu_db *db, int64_t nd, cons
 {
     ARG_TRY(ctx && db && db->owned && nd >= 0 && nd <= db->capacity && (nd == 0 || db_desc));
     CU_TRY(cudaSetDevice(ctx->device));
+    if (db->up_stream) CU_TRY(cudaStreamSynchronize(db->up_stream)); // an earlier chunked upload nobody consumed
+    db->up_pending = 0;
     if (nd > 0) CU_TRY(cudaMemcpyAsync((void *)db->desc, db_desc, nd * 32, cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     db->nd = nd;
@@ -310,6 +312,49 @@ extern "C" int orbgpu_db_update(orbgpu_ctx *ctx, orbgpu_db *db, int64_t nd, cons
         std::lock_guard<std::mutex> lock(db->x_mu);
         db->x_valid = false; // the expanded copy is rebuilt by the next tensor-engine search
     }
+    return ORBGPU_OK;
+}
+
+int db_wait_upload(orbgpu_ctx *ctx, const orbgpu_db *db)
+{
+    if (db->up_pending > 0) {
+        CU_TRY(cudaStreamWaitEvent(ctx->stream, db->up_ev[db->up_pending - 1], 0)); // the chunks are copied in order on one stream
+        db->up_pending = 0;
+    }
+    return ORBGPU_OK;
+}
+
+// starts the H2D copy of new descriptors into an owned database in chunks of whole tensor-engine splits (131 072 rows = 4 MiB) on the
+// database's own stream; does not wait.  The caller's buffer must stay valid until a search that consumed the upload has synchronised.
+static int db_begin_chunked_upload(orbgpu_ctx *ctx, orbgpu_db *db, int64_t nd, const uint8_t *db_desc)
+{
+    std::lock_guard<std::mutex> lock(db->x_mu);
+    if (!db->up_stream) {
+        CU_TRY(cudaStreamCreateWithFlags(&db->up_stream, cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreateWithFlags(&db->up_gate, cudaEventDisableTiming));
+        for (int c = 0; c < 16; c++) CU_TRY(cudaEventCreateWithFlags(&db->up_ev[c], cudaEventDisableTiming));
+    }
+    // nothing enqueued so far on the caller's stream may still be reading the old descriptors when the copy lands
+    CU_TRY(cudaEventRecord(db->up_gate, ctx->stream));
+    CU_TRY(cudaStreamWaitEvent(db->up_stream, db->up_gate, 0));
+    // three chunks of 1/8, 1/4 and 5/8 of the splits: the search of a chunk covers the copy of the next whether the call is
+    // compute-bound (one GPU: 128 MiB cross PCIe in ~1 ms, the search takes 165) or closer to copy-bound (a query shard of 1/8 on each
+    // of 8 GPUs sharing the host's memory system: ~5 ms against 20), and every extra launch costs a partial last wave
+    const int64_t split_rows = 131072;
+    const int64_t n_split = (nd + split_rows - 1) / split_rows;
+    int chunks = 0;
+    for (int64_t done = 0; done < n_split; chunks++) {
+        int64_t take = chunks == 0 ? std::max<int64_t>(1, n_split / 8) : (chunks == 1 ? std::max<int64_t>(1, n_split / 4) : n_split - done);
+        take = std::min(take, n_split - done);
+        const int64_t r0 = done * split_rows, r1 = std::min(nd, (done + take) * split_rows);
+        CU_TRY(cudaMemcpyAsync((char *)db->desc + r0 * 32, db_desc + r0 * 32, (r1 - r0) * 32, cudaMemcpyHostToDevice, db->up_stream));
+        CU_TRY(cudaEventRecord(db->up_ev[chunks], db->up_stream));
+        db->up_row_end[chunks] = r1;
+        done += take;
+    }
+    db->nd = nd;
+    db->x_valid = false;
+    db->up_pending = chunks;
     return ORBGPU_OK;
 }
 
@@ -342,6 +387,12 @@ extern "C" void orbgpu_db_destroy(orbgpu_db *db)
     if (db->owned && db->desc) cudaFree((void *)db->desc);
     if (db->x_desc) cudaFree(db->x_desc);
     if (db->x_ready) cudaEventDestroy(db->x_ready);
+    if (db->up_stream) {
+        cudaStreamSynchronize(db->up_stream);
+        cudaStreamDestroy(db->up_stream);
+        cudaEventDestroy(db->up_gate);
+        for (int c = 0; c < 16; c++) cudaEventDestroy(db->up_ev[c]);
+    }
     delete db;
 }
 
@@ -388,6 +439,10 @@ static int knn2_launch(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const u
     if (p.engine >= 3 && nd > 0) // tensor engines: expansion + tcgen05 search + their own merge (4 = cta_group::2)
         return knn2_tc_run(ctx, db, nq, q, th_low, nnratio, best_idx, best_dist, second_dist, match, p.engine == 4);
     int n_splits = (int)p.splits;
+    {
+        int rc = db_wait_upload(ctx, db);
+        if (rc) return rc;
+    }
     if (nd > 0) {
         if (p.engine == 1) {
             dim3 grid((unsigned)p.qtiles, (unsigned)p.splits);
@@ -425,14 +480,14 @@ extern "C" int orbgpu_knn2_ratio_dev(orbgpu_ctx *ctx, const orbgpu_db *db, int64
                        match_dev);
 }
 
-extern "C" int orbgpu_knn2_ratio(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const uint8_t *q_desc, int32_t th_low,
-                                 float nnratio, int32_t *best_idx, int32_t *best_dist, int32_t *second_dist, int32_t *match)
+// host-pointer search; up_desc != nullptr: the database is re-uploaded first (chunked, on its own stream) -- AFTER the query copy has
+// been enqueued: the H2D engine serves the streams in submission order, and the first search launch needs the queries, not the last chunk
+static int knn2_ratio_host(orbgpu_ctx *ctx, orbgpu_db *db, int64_t up_nd, const uint8_t *up_desc, int64_t nq, const uint8_t *q_desc,
+                           int32_t th_low, float nnratio, int32_t *best_idx, int32_t *best_dist, int32_t *second_dist, int32_t *match)
 {
-    ARG_TRY(ctx && db && nq >= 0 && (nq == 0 || q_desc));
     int rc = ctx_begin(ctx);
     if (rc) return rc;
-    if (nq == 0) return ORBGPU_OK;
-    const KnnPlan p = knn2_plan(ctx, nq, db->nd);
+    const KnnPlan p = knn2_plan(ctx, nq, up_desc ? up_nd : db->nd);
     const size_t qbytes = align256(nq * 32), rbytes = align256(nq * 4);
     rc = arena_reserve(ctx, p.part_bytes + qbytes + 4 * rbytes);
     if (rc) return rc;
@@ -441,6 +496,10 @@ extern "C" int orbgpu_knn2_ratio(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t n
     int32_t *dbi = (int32_t *)(base + qbytes), *dbd = (int32_t *)(base + qbytes + rbytes),
             *dsd = (int32_t *)(base + qbytes + 2 * rbytes), *dmt = (int32_t *)(base + qbytes + 3 * rbytes);
     CU_TRY(cudaMemcpyAsync(base, q_desc, nq * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if (up_desc) {
+        rc = db_begin_chunked_upload(ctx, db, up_nd, up_desc);
+        if (rc) return rc;
+    }
     rc = knn2_launch(ctx, db, nq, (const uint4 *)base, p, th_low, nnratio, dbi, dbd, dsd, dmt);
     if (rc) return rc;
     if (best_idx) CU_TRY(cudaMemcpyAsync(best_idx, dbi, nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -449,6 +508,31 @@ extern "C" int orbgpu_knn2_ratio(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t n
     if (match) CU_TRY(cudaMemcpyAsync(match, dmt, nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     return ORBGPU_OK;
+}
+
+extern "C" int orbgpu_knn2_ratio(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const uint8_t *q_desc, int32_t th_low,
+                                 float nnratio, int32_t *best_idx, int32_t *best_dist, int32_t *second_dist, int32_t *match)
+{
+    ARG_TRY(ctx && db && nq >= 0 && (nq == 0 || q_desc));
+    if (nq == 0) return ctx_begin(ctx);
+    return knn2_ratio_host(ctx, const_cast<orbgpu_db *>(db), 0, nullptr, nq, q_desc, th_low, nnratio, best_idx, best_dist, second_dist, match);
+}
+
+// orbgpu_db_update + orbgpu_knn2_ratio in one call, overlapped: the new descriptors are copied in chunks on the database's own stream
+// and the tensor engine searches each chunk as soon as it has arrived (what a SearchByNN(queries, database) on host matrices does).
+// Returns after the results are on the host; the caller's buffers are free again.
+extern "C" int orbgpu_knn2_ratio_update(orbgpu_ctx *ctx, orbgpu_db *db, int64_t nd, const uint8_t *db_desc, int64_t nq, const uint8_t *q_desc,
+                                        int32_t th_low, float nnratio, int32_t *best_idx, int32_t *best_dist, int32_t *second_dist,
+                                        int32_t *match)
+{
+    ARG_TRY(ctx && db && db->owned && nd >= 0 && nd <= db->capacity && (nd == 0 || db_desc) && nq >= 0 && (nq == 0 || q_desc));
+    CU_TRY(cudaSetDevice(ctx->device));
+    if (nq == 0) { // nothing to search: plain update
+        return orbgpu_db_update(ctx, db, nd, db_desc);
+    }
+    const int rc = knn2_ratio_host(ctx, db, nd, db_desc, nq, q_desc, th_low, nnratio, best_idx, best_dist, second_dist, match);
+    if (rc && db->up_stream) cudaStreamSynchronize(db->up_stream); // the caller's buffer is free again on every path
+    return rc;
 }
 
 extern "C" int orbgpu_descriptor_distance(orbgpu_ctx *ctx, int64_t n, const uint8_t *a, const uint8_t *b, int32_t *out)

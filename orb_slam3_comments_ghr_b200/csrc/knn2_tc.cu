@@ -133,7 +133,8 @@ constexpr uint32_t IDESC = ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) <<
 
 struct TcParams {
     int64_t nq, nd;
-    int n_qtiles, n_splits;
+    int n_qtiles, n_splits; // n_splits: the splits THIS launch sweeps, starting at split0 (a launch per uploaded chunk, or all at once)
+    int split0;
     int stages_per_split; // 128-row stages per database split
     int total_stages;     // ceil(nd / 128)
     uint16_t *out_best;   // [n_splits][nq_pad] best hamming distance (0xFFFF none)
@@ -185,7 +186,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             uint32_t sb = 0, pb = 0; // B ring stage / phase
             int it_local = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, it_local++) {
-                const int qt = item % P.n_qtiles, split = item / P.n_qtiles;
+                const int qt = item % P.n_qtiles, split = P.split0 + item / P.n_qtiles;
                 const int abuf = it_local & 1;
                 mbar_wait(smem_u32(&a_empty[abuf]), ((it_local >> 1) & 1) ^ 1);
                 mbar_expect_tx(smem_u32(&a_full[abuf]), STAGE_BYTES);
@@ -207,7 +208,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             uint32_t sb = 0, pb = 0, ta = 0, pt = 0;
             int it_local = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, it_local++) {
-                const int split = item / P.n_qtiles;
+                const int split = P.split0 + item / P.n_qtiles;
                 const int abuf = it_local & 1;
                 mbar_wait(smem_u32(&a_full[abuf]), (it_local >> 1) & 1);
                 const int s0 = split * P.stages_per_split, s1 = min(P.total_stages, s0 + P.stages_per_split);
@@ -243,7 +244,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         int it_local = 0;
         int stage_counter = 0;   // global (per CTA) stage counter to know which buffer a stage uses
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, it_local++) {
-            const int qt = item % P.n_qtiles, split = item / P.n_qtiles;
+            const int qt = item % P.n_qtiles, split = P.split0 + item / P.n_qtiles;
             const int s0 = split * P.stages_per_split, s1 = min(P.total_stages, s0 + P.stages_per_split);
             __half2 m1 = NEG_INF2, m2 = NEG_INF2;
             float gmax = -1e30f;
@@ -480,7 +481,7 @@ knn2_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             uint32_t sb = 0, pb = 0;
             int it_local = 0;
             for (int item = cluster_id; item < n_items; item += n_clusters, it_local++) {
-                const int qt = 2 * (item % n_qt2) + (int)rank, split = item / n_qt2;
+                const int qt = 2 * (item % n_qt2) + (int)rank, split = P.split0 + item / n_qt2;
                 const int abuf = it_local & 1;
                 mbar_wait(smem_u32(&a_empty[abuf]), ((it_local >> 1) & 1) ^ 1);
                 const uint32_t afull_leader = mapa(smem_u32(&a_full[abuf]), 0);
@@ -505,7 +506,7 @@ knn2_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             uint32_t sb = 0, pb = 0, ta = 0, pt = 0;
             int it_local = 0;
             for (int item = cluster_id; item < n_items; item += n_clusters, it_local++) {
-                const int split = item / n_qt2;
+                const int split = P.split0 + item / n_qt2;
                 const int abuf = it_local & 1;
                 mbar_wait(smem_u32(&a_full[abuf]), (it_local >> 1) & 1);
                 const int s0 = split * P.stages_per_split, s1 = min(P.total_stages, s0 + P.stages_per_split);
@@ -541,7 +542,7 @@ knn2_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         uint32_t pt = 0;
         int stage_counter = 0;
         for (int item = cluster_id; item < n_items; item += n_clusters) {
-            const int qt = 2 * (item % n_qt2) + (int)rank, split = item / n_qt2;
+            const int qt = 2 * (item % n_qt2) + (int)rank, split = P.split0 + item / n_qt2;
             const int s0 = split * P.stages_per_split, s1 = min(P.total_stages, s0 + P.stages_per_split);
             __half2 m1 = NEG_INF2, m2 = NEG_INF2;
             float gmax = -1e30f;
@@ -761,6 +762,9 @@ int knn2_tc_run(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const uint4 *q
     uint16_t *ps = (uint16_t *)((char *)pb + align256(part * 2));
     int32_t *pst = (int32_t *)((char *)ps + align256(part * 2));
     uint8_t *x_db = nullptr;
+    // a chunked upload in flight (orbgpu_knn2_ratio_update): the search of a chunk's splits starts as soon as the chunk has arrived
+    // and been expanded, while the following chunks are still crossing PCIe on the database's own stream
+    int up_chunks = 0;
     {
         std::lock_guard<std::mutex> lock(db->x_mu);
         if (db->x_bytes < e_db + 1024) {
@@ -776,14 +780,21 @@ int knn2_tc_run(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const uint4 *q
         }
         if (!db->x_ready) CU_TRY(cudaEventCreateWithFlags(&db->x_ready, cudaEventDisableTiming));
         x_db = (uint8_t *)(((uintptr_t)db->x_desc + 1023) & ~(uintptr_t)1023);
-        if (!db->x_valid) {
-            expand_kernel<<<(unsigned)((nd_pad * 8 + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t *)db->desc, nd, nd_pad, (uint4 *)x_db);
-            LAUNCH_COUNT(ctx);
-            CU_TRY(cudaGetLastError());
-            CU_TRY(cudaEventRecord(db->x_ready, ctx->stream));
-            db->x_valid = true;
+        const int64_t split_rows = (int64_t)stages_per_split * bn;
+        if (db->up_pending > 0 && !db->x_valid && split_rows == 131072) { // the chunks are whole splits of this plan
+            up_chunks = db->up_pending;
         } else {
-            CU_TRY(cudaStreamWaitEvent(ctx->stream, db->x_ready, 0)); // expanded on another context's stream, possibly still in flight
+            int rc = db_wait_upload(ctx, db); // whole database first (no upload pending: nothing to wait for)
+            if (rc) return rc;
+            if (!db->x_valid) {
+                expand_kernel<<<(unsigned)((nd_pad * 8 + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t *)db->desc, nd, nd_pad, (uint4 *)x_db);
+                LAUNCH_COUNT(ctx);
+                CU_TRY(cudaGetLastError());
+                CU_TRY(cudaEventRecord(db->x_ready, ctx->stream));
+                db->x_valid = true;
+            } else {
+                CU_TRY(cudaStreamWaitEvent(ctx->stream, db->x_ready, 0)); // expanded on another context's stream, possibly still in flight
+            }
         }
     }
     expand_kernel<<<(unsigned)((nq_pad * 8 + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t *)q, nq, nq_pad, (uint4 *)x_q);
@@ -794,17 +805,42 @@ int knn2_tc_run(orbgpu_ctx *ctx, const orbgpu_db *db, int64_t nq, const uint4 *q
     rc = make_map(&mdb, x_db, (uint64_t)nd_pad, BN); // 128-row boxes: a whole 1-CTA stage / this CTA's half of a 2-CTA stage
     if (rc) return rc;
     TcParams P;
-    P.nq = nq; P.nd = nd; P.n_qtiles = n_qtiles; P.n_splits = n_splits; P.stages_per_split = stages_per_split;
+    P.nq = nq; P.nd = nd; P.n_qtiles = n_qtiles; P.n_splits = n_splits; P.split0 = 0; P.stages_per_split = stages_per_split;
     P.total_stages = total_stages; P.out_best = pb; P.out_second = ps; P.out_stage = pst; P.out_stride = nq_pad;
-    if (two_cta) {
-        const int grid = 2 * std::min(n_units * n_splits, n_workers); // whole clusters
-        knn2_tc2_kernel<<<grid, NUM_THREADS, SMEM2_BYTES, ctx->stream>>>(mq, mdb, P);
+    auto launch = [&](int split0, int splits) {
+        P.split0 = split0;
+        P.n_splits = splits;
+        if (two_cta) {
+            const int grid = 2 * std::min(n_units * splits, n_workers); // whole clusters
+            knn2_tc2_kernel<<<grid, NUM_THREADS, SMEM2_BYTES, ctx->stream>>>(mq, mdb, P);
+        } else {
+            const int grid = std::min(n_qtiles * splits, ctx->sm_count);
+            knn2_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(mq, mdb, P);
+        }
+        LAUNCH_COUNT(ctx);
+    };
+    if (up_chunks > 0) {
+        const int64_t split_rows = (int64_t)stages_per_split * bn;
+        for (int c = 0; c < up_chunks; c++) {
+            const int64_t r0 = c ? db->up_row_end[c - 1] : 0, r1 = db->up_row_end[c];
+            const bool last = c == up_chunks - 1;
+            CU_TRY(cudaStreamWaitEvent(ctx->stream, db->up_ev[c], 0));
+            const int64_t rows_pad = (last ? nd_pad : r1) - r0;
+            expand_kernel<<<(unsigned)((rows_pad * 8 + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t *)db->desc + r0 * 8, r1 - r0, rows_pad,
+                                                                                           (uint4 *)(x_db + r0 * ROW_BYTES));
+            LAUNCH_COUNT(ctx);
+            const int s0 = (int)(r0 / split_rows), s1 = last ? n_splits : (int)(r1 / split_rows);
+            launch(s0, s1 - s0);
+        }
+        CU_TRY(cudaGetLastError());
+        std::lock_guard<std::mutex> lock(db->x_mu);
+        CU_TRY(cudaEventRecord(db->x_ready, ctx->stream));
+        db->x_valid = true;
+        db->up_pending = 0;
     } else {
-        const int grid = std::min(n_qtiles * n_splits, ctx->sm_count);
-        knn2_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(mq, mdb, P);
+        launch(0, n_splits);
+        CU_TRY(cudaGetLastError());
     }
-    LAUNCH_COUNT(ctx);
-    CU_TRY(cudaGetLastError());
     knn2_tc_merge_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, ctx->stream>>>(q, db->desc, nq, nd, n_splits, bn, nq_pad, pb, ps, pst, th_low,
                                                                                 nnratio, best_idx, best_dist, second_dist, match);
     LAUNCH_COUNT(ctx);

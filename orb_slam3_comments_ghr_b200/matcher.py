@@ -657,15 +657,26 @@ class ORBmatcher:
         return offs, pairs[:total.value]
 
     # brute-force 2-NN + ratio test ("SearchByNN" of BASELINE.json) -> best_idx, best_dist, second_dist, match
-    def SearchByNN(self, db: DeviceDb, q, th_low: int = TH_LOW):
+    def SearchByNN(self, db: DeviceDb, q, th_low: int = TH_LOW, database=None):
+        """database: new host descriptors for `db` (an owned database of at least that many rows) -- uploaded in chunks on the database's
+        own stream and searched chunk by chunk as they arrive (orbgpu_knn2_ratio_update); None: search the resident database"""
         q = as_u8(q).reshape(-1, 32)
         nq = q.shape[0]
         bi = np.empty(nq, dtype=np.int32)
         bd = np.empty(nq, dtype=np.int32)
         sd = np.empty(nq, dtype=np.int32)
         mt = np.empty(nq, dtype=np.int32)
-        _check(load_library().orbgpu_knn2_ratio(self.ctx.handle, db.handle, nq, _p(q, u8p), int(th_low), self.mfNNratio, _p(bi, i32p),
-                                                _p(bd, i32p), _p(sd, i32p), _p(mt, i32p)))
+        L = load_library()
+        if database is not None:
+            d = as_u8(database).reshape(-1, 32)
+            L.orbgpu_knn2_ratio_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, u8p, C.c_int64, u8p, C.c_int32, C.c_float, i32p, i32p,
+                                                   i32p, i32p]
+            _check(L.orbgpu_knn2_ratio_update(self.ctx.handle, db.handle, d.shape[0], _p(d, u8p), nq, _p(q, u8p), int(th_low), self.mfNNratio,
+                                              _p(bi, i32p), _p(bd, i32p), _p(sd, i32p), _p(mt, i32p)))
+            db.nd = d.shape[0]
+            return bi, bd, sd, mt
+        _check(L.orbgpu_knn2_ratio(self.ctx.handle, db.handle, nq, _p(q, u8p), int(th_low), self.mfNNratio, _p(bi, i32p),
+                                   _p(bd, i32p), _p(sd, i32p), _p(mt, i32p)))
         return bi, bd, sd, mt
 
     def SearchByNN_dev(self, db: DeviceDb, nq: int, q_ptr: int, best_idx_ptr: int, best_dist_ptr: int, second_ptr: int, match_ptr: int,

@@ -370,6 +370,39 @@ def test_knn2_tc_ties_and_duplicates(ctx, M, oracle, engine):
         assert np.array_equal(a, e), name
 
 
+@pytest.mark.parametrize("engine", [0, 1, 3])
+@pytest.mark.parametrize("nd", [1500, 131072, 700001])
+def test_knn2_update_and_search_overlapped(ctx, M, oracle, engine, nd):
+    """orbgpu_knn2_ratio_update: new descriptors uploaded in chunks on the database's own stream, every chunk searched as it arrives --
+    same results as update + search, as the oracle on the NEW descriptors, for sizes of less than one split, exactly one split and
+    several chunks with a ragged tail; then a smaller database in the same object, then the plain call on the resident rows"""
+    rng = np.random.default_rng(nd + engine)
+    nq = 6656 if nd > 200000 else 700  # the large case has enough query tiles for whole 131 072-row splits: the chunked path proper
+    old = synth.random_descriptors(rng, nd)
+    new = synth.random_descriptors(rng, nd)
+    q = new[rng.integers(0, nd, nq)] ^ synth.flip_mask(rng, nq, 6)
+    q[::7] = synth.random_descriptors(rng, len(q[::7]))
+    ctx.set_knn_engine(engine)
+    m = M.ORBmatcher(0.8, True, ctx)
+    d = ctx.upload_database(old)
+    m.SearchByNN(d, q, 50)  # the expansion of the OLD rows is cached now
+    got = m.SearchByNN(d, q, 50, database=new)
+    exp = oracle.knn2_ratio(q, new, 50, 0.8, n_threads=os.cpu_count() or 1)
+    for a, e, name in zip(got, exp, ("best_idx", "best_dist", "second_dist", "match")):
+        assert np.array_equal(a, e), name
+    again = m.SearchByNN(d, q, 50)  # resident rows = the new ones
+    assert all(np.array_equal(a, b) for a, b in zip(got, again))
+    n2 = nd - nd // 3  # fewer rows in the same object: the tail of the old expansion must not be seen
+    got2 = m.SearchByNN(d, q, 50, database=old[:n2])
+    exp2 = oracle.knn2_ratio(q, old[:n2], 50, 0.8, n_threads=os.cpu_count() or 1)
+    for a, e, name in zip(got2, exp2, ("best_idx", "best_dist", "second_dist", "match")):
+        assert np.array_equal(a, e), name
+    d.update(new)  # the plain update after a chunked one
+    got3 = m.SearchByNN(d, q, 50)
+    assert all(np.array_equal(a, b) for a, b in zip(got, got3))
+    ctx.set_knn_engine(0)
+
+
 def test_knn2_properties_large(ctx, M):
     """size-independent properties at a size the oracle cannot finish: planted queries must find their
     source row (or an earlier exact duplicate), best <= second, idempotence."""
