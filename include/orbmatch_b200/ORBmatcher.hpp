@@ -300,12 +300,28 @@ namespace orbgpu
             const int nq = queries.rows, nd = database.rows;
             vnMatches.assign((size_t)nq, -1);
             if (nq == 0 || nd == 0) return 0;
-            orbgpu_db *db = nullptr;
-            check(orbgpu_db_upload(ctx, nd, database.template ptr<uint8_t>(), &db));
+            // the device database lives with the calling thread and is re-used while it is large enough: a repeated call re-uploads the
+            // rows in chunks on the database's own stream and searches every chunk as it arrives (orbgpu_knn2_ratio_update)
+            struct DbHolder
+            {
+                orbgpu_db *db = nullptr;
+                int64_t capacity = 0;
+                ~DbHolder() { if (db) orbgpu_db_destroy(db); }
+            };
+            thread_local DbHolder holder;
             std::vector<int32_t> bi((size_t)nq), bd((size_t)nq), sd((size_t)nq), m((size_t)nq);
-            const int rc = orbgpu_knn2_ratio(ctx, db, nq, queries.template ptr<uint8_t>(), th, mfNNratio, bi.data(), bd.data(), sd.data(), m.data());
-            orbgpu_db_destroy(db);
-            check(rc);
+            if (holder.capacity < nd)
+            {
+                if (holder.db) orbgpu_db_destroy(holder.db);
+                holder.db = nullptr;
+                holder.capacity = 0;
+                check(orbgpu_db_upload(ctx, nd, database.template ptr<uint8_t>(), &holder.db));
+                holder.capacity = nd;
+                check(orbgpu_knn2_ratio(ctx, holder.db, nq, queries.template ptr<uint8_t>(), th, mfNNratio, bi.data(), bd.data(), sd.data(), m.data()));
+            }
+            else
+                check(orbgpu_knn2_ratio_update(ctx, holder.db, nd, database.template ptr<uint8_t>(), nq, queries.template ptr<uint8_t>(), th, mfNNratio,
+                                               bi.data(), bd.data(), sd.data(), m.data()));
             int nmatches = 0;
             for (int i = 0; i < nq; i++) {
                 vnMatches[(size_t)i] = m[(size_t)i];

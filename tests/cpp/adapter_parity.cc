@@ -619,6 +619,24 @@ int main()
         const int nGot = gpu.SearchByNN(Q, D, got);
         std::printf("SearchByNN: ref %d gpu %d\n", nExp, nGot);
         EXPECT(nGot == nExp && got == exp && nExp > 100, "SearchByNN vnMatches / return value");
+        // a second call with a smaller, different database goes through the thread's resident database object (chunked re-upload)
+        const int nd2 = 2000;
+        cv::Mat D2(nd2, 32, CV_8U);
+        for (int d = 0; d < nd2; d++) std::memcpy(D2.ptr<uint8_t>(d), D.ptr<uint8_t>(nd - 1 - d), 32);
+        std::vector<int> exp2(nq, -1), got2;
+        int nExp2 = 0;
+        for (int q = 0; q < nq; q++) {
+            int best = 256, second = 256, bi = -1;
+            for (int d = 0; d < nd2; d++) {
+                const int dist = ORBmatcher::DescriptorDistance(Q.row(q), D2.row(d));
+                if (dist < best) { second = best; best = dist; bi = d; }
+                else if (dist < second) second = dist;
+            }
+            if (best <= ORBmatcher::TH_LOW && (float)best < ratio * (float)second) { exp2[q] = bi; nExp2++; }
+        }
+        const int nGot2 = gpu.SearchByNN(Q, D2, got2);
+        std::printf("SearchByNN (second database, re-upload): ref %d gpu %d\n", nExp2, nGot2);
+        EXPECT(nGot2 == nExp2 && got2 == exp2 && nExp2 > 50, "SearchByNN on a re-uploaded database");
     }
     std::printf(fails ? "ADAPTER PARITY FAILED (%d)\n" : "ADAPTER PARITY OK (%d failures)\n", fails);
     return fails ? 1 : 0;
