@@ -849,13 +849,15 @@ def main():
                     secondary["reloc_2k"] = {"error": repr(e)}
             E.keep_c5 = None
             torch.cuda.empty_cache()
+            # a secondary leg never costs the headline line: at N > 1 a failure leaves the ranks out of step, so the remaining legs are
+            # skipped, rank 0 still prints the line, and the processes leave without the collective tear-down
+            failed = False
             try:
                 secondary["c4"] = bench_c4(E, args, K, W)
-            except Exception as e:  # the secondary block never costs the headline line
+            except Exception as e:
                 secondary["c4"] = {"error": repr(e)}
-                if world > 1:
-                    raise
-            if world > 1:
+                failed = world > 1
+            if world > 1 and not failed:
                 # the same kernel with the per-GPU work held at the single-GPU workload (the fixed 4096-pair job above leaves 512
                 # pairs = 3.5 per CTA on each of 8 GPUs, where the kernel's ~24 us fixed latency dominates)
                 torch.cuda.empty_cache()
@@ -863,7 +865,14 @@ def main():
                     secondary["c4_weak"] = bench_c4(E, args, K, W, weak=True)
                 except Exception as e:
                     secondary["c4_weak"] = {"error": repr(e)}
-                    raise
+                    failed = True
+            if failed:
+                if rank == 0:
+                    line["secondary"] = secondary
+                    emit(line)
+                log("a secondary leg failed: " + json.dumps({k: v.get("error") for k, v in secondary.items() if isinstance(v, dict) and v.get("error")}))
+                sys.stderr.flush()
+                os._exit(0)
             if world == 1:
                 try:
                     secondary["c4_shared_kf"] = bench_c4(E, args, K, W, shared=True)
